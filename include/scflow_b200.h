@@ -1,0 +1,222 @@
+/*
+ * scflow_b200.h - C ABI of libscflow_sm100a.so: the B200-native replacement for SCFlow's iterative
+ * pose-refinement hot path (correlation-pyramid build -> pyramid lookup -> motion encoder -> SepConvGRU ->
+ * flow/mask heads -> pose regressor -> pose update -> pose-induced-flow re-projection).
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   models/decoder/raft_decoder.py:35-58      CorrelationPyramid.forward      -> scf_corr_build
+ *   models/utils/corr_lookup.py:102-136       CorrLookup.forward              -> scf_corr_lookup
+ *   models/decoder/raft_decoder.py:152-166    MotionEncoder.forward           -> scf_conv2d (x5) / scf_decoder_forward
+ *   models/decoder/raft_decoder.py:235-253    ConvGRU.forward                 -> scf_conv2d (GRU epilogues)
+ *   models/decoder/raft_decoder.py:292-294    XHead.forward                   -> scf_conv2d
+ *   models/head/pose_head.py:201-211          MultiClassPoseHead.forward      -> scf_group_norm_relu, scf_pose_fc
+ *   models/utils/pose.py:124-169              get_pose_from_delta_pose        -> scf_pose_update
+ *   models/utils/pose.py:26-64                cal_3d_2d_corr / lift_2d_to_3d  -> scf_unproject
+ *   models/utils/pose.py:66-88                get_flow_from_delta_pose_and_points -> scf_reproject
+ *   models/decoder/scflow_decoder.py:196-197,222-227  F.interpolate x1/8, x8  -> scf_resize_bilinear
+ *   models/decoder/scflow_decoder.py:150-251  SCFlowDecoder.forward (whole loop) -> scf_decoder_forward
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless its name starts with "h_" ; the caller (PyTorch) owns all
+ *     memory. The library never allocates, frees or retains device memory.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), does no host synchronisation and
+ *     has no data-dependent host control flow, so sequences of calls are CUDA-graph capturable.
+ *   - Return value: 0 = ok, <0 = argument error (SCF_ERR_*), >0 = cudaError_t. scf_last_error() returns a
+ *     thread-local message for the last non-zero return.
+ *   - "NCHW" tensors are the reference's layout (contiguous fp32). "NHWC" tensors are the library's internal
+ *     pixel-major activation layout: element (b, y, x, c) at ((b*H + y)*W + x)*stride + c.
+ */
+#ifndef SCFLOW_B200_H_
+#define SCFLOW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCF_ABI_VERSION 1
+
+#define SCF_ERR_ARG (-1)        /* bad size / null pointer / unsupported combination */
+#define SCF_ERR_ALIGN (-2)      /* pointer or stride not aligned as required */
+#define SCF_ERR_UNSUPPORTED (-3)
+
+/* activation codes */
+#define SCF_ACT_NONE 0
+#define SCF_ACT_RELU 1
+#define SCF_ACT_SIGMOID 2
+#define SCF_ACT_TANH 3
+
+/* convolution epilogues (scf_conv2d) */
+#define SCF_EPI_ACT 0     /* out = act(scale*acc + bias)                                                  */
+#define SCF_EPI_GRU_ZR 1  /* cout = 2*Ch: n<Ch: out[n] = z = sigmoid(.) ; n>=Ch: out2[n-Ch] = sigmoid(.)*aux0[n-Ch] (r*h) */
+#define SCF_EPI_GRU_Q 2   /* q = tanh(.) ; out[n] = (1-aux1[n])*aux0[n] + aux1[n]*q   (aux0 = h, aux1 = z)  */
+
+int scf_abi_version(void);
+const char* scf_last_error(void);
+/* 1 if the tcgen05/TMA code paths are usable on the current device (compute capability 10.x), else 0 */
+int scf_device_supported(void);
+/* number of kernels launched so far by the calling thread through this library (bench.py's gpu_launches) */
+long long scf_launch_counter(void);
+
+/* ---------------------------------------------------------------- layout helpers ------------------------ */
+/* NCHW fp32 [B,C,H,W] -> NHWC fp32 rows of `dst_stride` floats, written at channel offset dst_coff. */
+int scf_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, int dst_stride, int dst_coff,
+                     void* stream);
+int scf_nhwc_to_nchw(const float* src, int src_stride, int src_coff, float* dst, int B, int C, int H, int W,
+                     void* stream);
+/* conv weight OIHW fp32 -> packed [kh*kw*I][ldw] (k = (ky*kw+kx)*I + i, n = o), ldw = round_up(O,4), zero padded.
+ * o_off lets several convs be concatenated along O into one packed matrix of width ldw. */
+int scf_pack_conv_weight(const float* w_oihw, float* packed, int O, int I, int kh, int kw, int ldw, int o_off,
+                         void* stream);
+
+/* ---------------------------------------------------------------- generic convolution -------------------- */
+typedef struct scf_conv_seg {
+  const float* ptr; /* NHWC activation buffer */
+  int stride;       /* floats per pixel in that buffer */
+  int coff;         /* first channel used */
+  int nch;          /* number of channels taken (concatenated in order over the segments) */
+} scf_conv_seg;
+
+typedef struct scf_conv_desc {
+  scf_conv_seg seg[3];
+  int nseg;
+  int B, Hi, Wi, Ho, Wo;
+  int kh, kw, sh, sw, ph, pw;
+  const float* w;            /* packed weight, see scf_pack_conv_weight */
+  long long w_batch_stride;  /* floats between per-sample weight matrices (0 = shared weights) */
+  int ldw, cout;
+  const float* bias;         /* [cout] or NULL */
+  float scale;               /* multiplies the accumulator before bias */
+  int epi, act;
+  float* out;                /* NHWC */
+  int out_stride, out_coff;
+  const float* aux0; int aux0_stride;
+  const float* aux1; int aux1_stride;
+  float* out2; int out2_stride;
+} scf_conv_desc;
+
+/* fp32 CUDA-core implicit GEMM (exact fp32 accumulate); any kernel size / stride / channel count. */
+int scf_conv2d(const scf_conv_desc* d, void* stream);
+
+/* ---------------------------------------------------------------- correlation pyramid -------------------- */
+/* feat_render / feat_real: NCHW fp32 [B,C,H8,W8]. levels[l]: fp32 [B*H8*W8, Hl*Wl] (the reference's
+ * [B*P,1,Hl,Wl]), Hl = floor(H_{l-1}/2). scratch: >= scf_corr_build_scratch_bytes(B,C,H8,W8) bytes. */
+size_t scf_corr_build_scratch_bytes(int B, int C, int H8, int W8);
+/* precision: 0 = fp32 CUDA-core build, 1 = tcgen05 split-bf16 (bf16x3) tensor-core build (fp32 accumulate). */
+int scf_corr_build(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
+                   float* const* h_levels, void* scratch, int precision, void* stream);
+
+/* flow8: NHWC fp32 [B,H8,W8,2] (x, y) at 1/8 resolution. out: NHWC [B,H8,W8,out_stride] written at out_coff,
+ * num_levels*(2r+1)^2 channels, channel = level*(2r+1)^2 + a*(2r+1) + b sampling (x + a - r, y + b - r).
+ * mask (optional, NHWC [B,H8,W8,1]) multiplies the result (decoder option mask_corr). */
+int scf_corr_lookup(const float* const* h_levels, int num_levels, int radius, const float* flow8, const float* mask,
+                    float* out, int out_stride, int out_coff, int B, int H8, int W8, void* stream);
+/* debug/parity hook: integer neighbour indices of the lookup, bit-exact against the oracle.
+ * x0,y0: int32 [B,H8,W8,2r+1] per level `level` (x0 indexed by a, y0 by b). */
+int scf_corr_lookup_taps(int level, int radius, const float* flow8, int32_t* x0, int32_t* y0, int B, int H8, int W8,
+                         void* stream);
+
+/* ---------------------------------------------------------------- pose head pieces ----------------------- */
+/* in-place GroupNorm(num_groups, eps) + ReLU on NHWC [B, HW, C] */
+int scf_group_norm_relu(float* x, const float* gamma, const float* beta, int B, int HW, int C, int num_groups,
+                        float eps, void* stream);
+/* y[b, :] = act(W x[b, :] + bias), W row-major [O, I] */
+int scf_linear(const float* x, const float* w, const float* bias, float* y, int B, int I, int O, int act,
+               void* stream);
+/* final pose projection with the reference's class selection: rows of class label[0] (device int64) only.
+ * rot_w [rot_dim*num_class, I], tr_w [3*num_class, I]; outputs d_rot [B,rot_dim], d_trs [B,3]. num_class<=0: single-class head */
+int scf_pose_project(const float* x, const float* rot_w, const float* rot_b, const float* tr_w, const float* tr_b,
+                     const int64_t* label, float* d_rot, float* d_trs, int B, int I, int rot_dim, int num_class,
+                     void* stream);
+/* ortho6d delta rotation + 'exp' depth transform pose update (pose.py:124-169). rot [B,3,3], trs [B,3]. */
+int scf_pose_update(const float* d_rot, const float* d_trs, const float* rot_in, const float* trs_in, float* rot_out,
+                    float* trs_out, int B, void* stream);
+
+/* ---------------------------------------------------------------- geometry ------------------------------- */
+/* pts4: [B,H,W,4] = (X_obj, Y_obj, Z_obj, depth>0) per pixel */
+int scf_unproject(const float* depth, const float* K, const float* rot, const float* trs, float* pts4, int B, int H,
+                  int W, void* stream);
+/* flow NCHW [B,2,H,W]: projected flow at depth>0, `invalid` elsewhere */
+int scf_reproject(const float* pts4, const float* K, const float* rot, const float* trs, float invalid, float* flow,
+                  int B, int H, int W, void* stream);
+/* bilinear, align_corners=True. src element (b,c,y,x) at b*s_b + c*s_c + y*s_y + x*s_x (floats); same for dst.
+ * dst = scale * interp(src (+ add, same strides as src, optional)). */
+int scf_resize_bilinear(const float* src, const float* add, long long s_b, long long s_c, long long s_y, long long s_x,
+                        int Hi, int Wi, float* dst, long long d_b, long long d_c, long long d_y, long long d_x, int Ho,
+                        int Wo, int B, int C, float scale, void* stream);
+
+/* ---------------------------------------------------------------- whole decoder loop --------------------- */
+enum scf_decoder_weight {
+  SCF_W_CORR0_W = 0, SCF_W_CORR0_B,   /* encoder.corr_net.0.conv   [256,324,1,1] */
+  SCF_W_CORR1_W, SCF_W_CORR1_B,       /* encoder.corr_net.1.conv   [192,256,3,3] */
+  SCF_W_FLOW0_W, SCF_W_FLOW0_B,       /* encoder.flow_net.0.conv   [128,2,7,7]   */
+  SCF_W_FLOW1_W, SCF_W_FLOW1_B,       /* encoder.flow_net.1.conv   [64,128,3,3]  */
+  SCF_W_OUT0_W, SCF_W_OUT0_B,         /* encoder.out_net.0.conv    [126,256,3,3] */
+  SCF_W_GRU_Z0_W, SCF_W_GRU_Z0_B, SCF_W_GRU_R0_W, SCF_W_GRU_R0_B, SCF_W_GRU_Q0_W, SCF_W_GRU_Q0_B, /* [128,384,1,5] */
+  SCF_W_GRU_Z1_W, SCF_W_GRU_Z1_B, SCF_W_GRU_R1_W, SCF_W_GRU_R1_B, SCF_W_GRU_Q1_W, SCF_W_GRU_Q1_B, /* [128,384,5,1] */
+  SCF_W_FH0_W, SCF_W_FH0_B,           /* flow_pred.layers.0.conv   [256,128,3,3] */
+  SCF_W_FHP_W, SCF_W_FHP_B,           /* flow_pred.predict_layer   [2,256,3,3]   */
+  SCF_W_MH0_W, SCF_W_MH0_B,           /* mask_pred.layers.0.conv   [256,128,3,3] */
+  SCF_W_MHP_W, SCF_W_MHP_B,           /* mask_pred.predict_layer   [1,256,1,1]   */
+  SCF_W_DFE0_W, SCF_W_DFE0_B,         /* delta_flow_encoder.0.conv [128,2,7,7]   */
+  SCF_W_DFE1_W, SCF_W_DFE1_B,         /* delta_flow_encoder.1.conv [64,128,3,3]  */
+  SCF_W_ME0_W, SCF_W_ME0_B,           /* mask_encoder.0.conv       [64,1,3,3]    */
+  SCF_W_ME1_W, SCF_W_ME1_B,           /* mask_encoder.1.conv       [32,64,3,3]   */
+  SCF_W_PH_C0_W, SCF_W_PH_G0_W, SCF_W_PH_G0_B,  /* pose_pred.conv_layers.0.{conv.weight [128,224,3,3], gn.weight, gn.bias} */
+  SCF_W_PH_C1_W, SCF_W_PH_G1_W, SCF_W_PH_G1_B,  /* [128,128,3,3] */
+  SCF_W_PH_C2_W, SCF_W_PH_G2_W, SCF_W_PH_G2_B,
+  SCF_W_PH_FC0_W, SCF_W_PH_FC0_B,     /* pose_pred.fc_layers.0.0   [1024,2048] */
+  SCF_W_PH_FC1_W, SCF_W_PH_FC1_B,     /* pose_pred.fc_layers.1.0   [256,1024]  */
+  SCF_W_PH_ROT_W, SCF_W_PH_ROT_B,     /* pose_pred.rotation_pred   [rot_dim*num_class,256] */
+  SCF_W_PH_TR_W, SCF_W_PH_TR_B,       /* pose_pred.translation_pred [3*num_class,256] */
+  SCF_W_COUNT
+};
+
+typedef struct scf_decoder_cfg {
+  int num_levels;   /* 4 */
+  int radius;       /* 4 */
+  int num_class;    /* 21; <=0 = SingleClassPoseHead */
+  int rot_dim;      /* 6 (ortho6d) */
+  int mask_flow, mask_corr; /* decoder options (scflow_decoder.py:200-206) */
+  int pose_head;    /* 1 = run the pose regressor; 0 = identity delta pose (config 3: stock head cannot run off 256x256) */
+  int precision;    /* 0 = fp32 CUDA-core convolutions; 1 = tcgen05 split-bf16 (bf16x3, fp32 accumulate) */
+} scf_decoder_cfg;
+
+/* Bytes of the packed-weight arena and of the per-call workspace for a batch of B HxW crops. */
+size_t scf_decoder_packed_bytes(const scf_decoder_cfg* cfg);
+size_t scf_decoder_workspace_bytes(const scf_decoder_cfg* cfg, int B, int H, int W);
+/* h_weights: host array of SCF_W_COUNT device pointers to the reference-layout fp32 parameters (OIHW / [O,I]). */
+int scf_decoder_pack(const scf_decoder_cfg* cfg, const float* const* h_weights, void* packed, void* stream);
+
+typedef struct scf_decoder_io {
+  /* inputs (reference layouts, fp32 NCHW) */
+  const float* feat_render; const float* feat_real;   /* [B,256,H/8,W/8] */
+  const float* h_feat; const float* cxt_feat;         /* [B,128,H/8,W/8] */
+  const float* ref_rotation; const float* ref_translation; /* [B,3,3], [B,3] */
+  const float* depth;                                 /* [B,H,W] */
+  const float* internel_k;                            /* [B,3,3] */
+  const int64_t* label;                               /* [B] */
+  const float* init_flow;                             /* [B,2,H,W] */
+  float invalid_flow_num;
+  /* outputs: stacked over iterations, [iters, ...] of the reference's 7 lists */
+  float* flow_from_pose;   /* [iters,B,2,H,W] */
+  float* flow_from_pred;   /* [iters,B,2,H,W] */
+  float* rotation;         /* [iters,B,3,3] */
+  float* translation;      /* [iters,B,3] */
+  float* mask;             /* [iters,B,1,H,W] */
+  float* delta_rotation;   /* [iters,B,rot_dim] */
+  float* delta_translation;/* [iters,B,3] */
+  float* h_out;            /* optional [B,128,H/8,W/8] NCHW final hidden state (may be NULL) */
+} scf_decoder_io;
+
+int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const scf_decoder_io* io, int B, int H, int W,
+                        int iters, void* workspace, size_t workspace_bytes, void* stream);
+/* number of kernel launches one scf_decoder_forward call issues (for bench.py's gpu_launches) */
+int scf_decoder_launch_count(const scf_decoder_cfg* cfg, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCFLOW_B200_H_ */

@@ -1,0 +1,62 @@
+"""In-tree build of libscflow_sm100a.so with nvcc (sm_100a only). Used by __graft_entry__.build() and, lazily,
+by scflow_b200._lib when the library is missing or older than its sources and nvcc is available."""
+import glob
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB_DIR = os.path.join(HERE, 'lib')
+LIB_PATH = os.path.join(LIB_DIR, 'libscflow_sm100a.so')
+
+NVCC_FLAGS = [
+    '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+    '-Xcompiler', '-fPIC', '--use_fast_math=false',
+    '-cudart', 'static',
+]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + glob.glob(os.path.join(CSRC, '*.cuh')) + [os.path.join(HERE, '..', 'include', 'scflow_b200.h')]
+    return any(os.path.getmtime(p) > t for p in deps)
+
+
+def build(verbose: bool = False, force: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = os.path.join(LIB_DIR, 'obj')
+    os.makedirs(obj_dir, exist_ok=True)
+    objs = []
+    procs = []
+    for src in sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + '.o')
+        objs.append(obj)
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != '--use_fast_math=false'] + ['-c', src, '-o', obj]
+        if verbose:
+            cmd.insert(1, '-Xptxas=-v')
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n{out}')
+        if verbose and out.strip():
+            print(out)
+    link = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-cudart', 'static', '-o', LIB_PATH] + objs + ['-lcuda']
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('link failed:\n' + r.stdout)
+    return LIB_PATH
+
+
+if __name__ == '__main__':
+    import sys
+    print(build(verbose='-v' in sys.argv, force=True))

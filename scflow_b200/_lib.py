@@ -1,0 +1,173 @@
+"""ctypes binding of libscflow_sm100a.so (the C ABI declared in include/scflow_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing (and cannot be built because nvcc is absent)
+or a call fails, a ScfError is raised.  The oracle under oracle/ is never imported from here.
+"""
+import ctypes as C
+import os
+import shutil
+import threading
+
+from . import _build
+
+c_float_p = C.POINTER(C.c_float)
+c_void_p = C.c_void_p
+
+
+class ScfError(RuntimeError):
+    pass
+
+
+class ConvSeg(C.Structure):
+    _fields_ = [('ptr', c_void_p), ('stride', C.c_int), ('coff', C.c_int), ('nch', C.c_int)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ('seg', ConvSeg * 3), ('nseg', C.c_int),
+        ('B', C.c_int), ('Hi', C.c_int), ('Wi', C.c_int), ('Ho', C.c_int), ('Wo', C.c_int),
+        ('kh', C.c_int), ('kw', C.c_int), ('sh', C.c_int), ('sw', C.c_int), ('ph', C.c_int), ('pw', C.c_int),
+        ('w', c_void_p), ('w_batch_stride', C.c_longlong), ('ldw', C.c_int), ('cout', C.c_int),
+        ('bias', c_void_p), ('scale', C.c_float), ('epi', C.c_int), ('act', C.c_int),
+        ('out', c_void_p), ('out_stride', C.c_int), ('out_coff', C.c_int),
+        ('aux0', c_void_p), ('aux0_stride', C.c_int),
+        ('aux1', c_void_p), ('aux1_stride', C.c_int),
+        ('out2', c_void_p), ('out2_stride', C.c_int),
+    ]
+
+
+class DecoderCfg(C.Structure):
+    _fields_ = [('num_levels', C.c_int), ('radius', C.c_int), ('num_class', C.c_int), ('rot_dim', C.c_int),
+                ('mask_flow', C.c_int), ('mask_corr', C.c_int), ('pose_head', C.c_int), ('precision', C.c_int)]
+
+
+class DecoderIO(C.Structure):
+    _fields_ = [
+        ('feat_render', c_void_p), ('feat_real', c_void_p), ('h_feat', c_void_p), ('cxt_feat', c_void_p),
+        ('ref_rotation', c_void_p), ('ref_translation', c_void_p), ('depth', c_void_p), ('internel_k', c_void_p),
+        ('label', c_void_p), ('init_flow', c_void_p), ('invalid_flow_num', C.c_float),
+        ('flow_from_pose', c_void_p), ('flow_from_pred', c_void_p), ('rotation', c_void_p), ('translation', c_void_p),
+        ('mask', c_void_p), ('delta_rotation', c_void_p), ('delta_translation', c_void_p), ('h_out', c_void_p),
+    ]
+
+
+ACT = {'none': 0, None: 0, 'relu': 1, 'sigmoid': 2, 'tanh': 3}
+EPI_ACT, EPI_GRU_ZR, EPI_GRU_Q = 0, 1, 2
+
+# order of scf_decoder_weight in include/scflow_b200.h  ->  reference state-dict key (relative to the decoder)
+DECODER_WEIGHT_KEYS = [
+    'encoder.corr_net.0.conv.weight', 'encoder.corr_net.0.conv.bias',
+    'encoder.corr_net.1.conv.weight', 'encoder.corr_net.1.conv.bias',
+    'encoder.flow_net.0.conv.weight', 'encoder.flow_net.0.conv.bias',
+    'encoder.flow_net.1.conv.weight', 'encoder.flow_net.1.conv.bias',
+    'encoder.out_net.0.conv.weight', 'encoder.out_net.0.conv.bias',
+    'gru.conv_z.0.conv.weight', 'gru.conv_z.0.conv.bias', 'gru.conv_r.0.conv.weight', 'gru.conv_r.0.conv.bias',
+    'gru.conv_q.0.conv.weight', 'gru.conv_q.0.conv.bias',
+    'gru.conv_z.1.conv.weight', 'gru.conv_z.1.conv.bias', 'gru.conv_r.1.conv.weight', 'gru.conv_r.1.conv.bias',
+    'gru.conv_q.1.conv.weight', 'gru.conv_q.1.conv.bias',
+    'flow_pred.layers.0.conv.weight', 'flow_pred.layers.0.conv.bias',
+    'flow_pred.predict_layer.weight', 'flow_pred.predict_layer.bias',
+    'mask_pred.layers.0.conv.weight', 'mask_pred.layers.0.conv.bias',
+    'mask_pred.predict_layer.weight', 'mask_pred.predict_layer.bias',
+    'delta_flow_encoder.0.conv.weight', 'delta_flow_encoder.0.conv.bias',
+    'delta_flow_encoder.1.conv.weight', 'delta_flow_encoder.1.conv.bias',
+    'mask_encoder.0.conv.weight', 'mask_encoder.0.conv.bias',
+    'mask_encoder.1.conv.weight', 'mask_encoder.1.conv.bias',
+    'pose_pred.conv_layers.0.conv.weight', 'pose_pred.conv_layers.0.gn.weight', 'pose_pred.conv_layers.0.gn.bias',
+    'pose_pred.conv_layers.1.conv.weight', 'pose_pred.conv_layers.1.gn.weight', 'pose_pred.conv_layers.1.gn.bias',
+    'pose_pred.conv_layers.2.conv.weight', 'pose_pred.conv_layers.2.gn.weight', 'pose_pred.conv_layers.2.gn.bias',
+    'pose_pred.fc_layers.0.0.weight', 'pose_pred.fc_layers.0.0.bias',
+    'pose_pred.fc_layers.1.0.weight', 'pose_pred.fc_layers.1.0.bias',
+    'pose_pred.rotation_pred.weight', 'pose_pred.rotation_pred.bias',
+    'pose_pred.translation_pred.weight', 'pose_pred.translation_pred.bias',
+]
+SCF_W_COUNT = len(DECODER_WEIGHT_KEYS)
+
+_SIGNATURES = {
+    'scf_abi_version': (C.c_int, []),
+    'scf_last_error': (C.c_char_p, []),
+    'scf_device_supported': (C.c_int, []),
+    'scf_launch_counter': (C.c_longlong, []),
+    'scf_nchw_to_nhwc': (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
+    'scf_nhwc_to_nchw': (C.c_int, [c_void_p, C.c_int, C.c_int, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
+    'scf_pack_conv_weight': (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
+    'scf_conv2d': (C.c_int, [C.POINTER(ConvDesc), c_void_p]),
+    'scf_corr_build_scratch_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    'scf_corr_build': (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(c_void_p),
+                                 c_void_p, C.c_int, c_void_p]),
+    'scf_corr_lookup': (C.c_int, [C.POINTER(c_void_p), C.c_int, C.c_int, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, c_void_p]),
+    'scf_corr_lookup_taps': (C.c_int, [C.c_int, C.c_int, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p]),
+    'scf_group_norm_relu': (C.c_int, [c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_void_p]),
+    'scf_linear': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
+    'scf_pose_project': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
+    'scf_pose_update': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, c_void_p]),
+    'scf_unproject': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p]),
+    'scf_reproject': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_float, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p]),
+    'scf_resize_bilinear': (C.c_int, [c_void_p, c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
+                                      C.c_int, c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_float, c_void_p]),
+    'scf_decoder_packed_bytes': (C.c_size_t, [C.POINTER(DecoderCfg)]),
+    'scf_decoder_workspace_bytes': (C.c_size_t, [C.POINTER(DecoderCfg), C.c_int, C.c_int, C.c_int]),
+    'scf_decoder_pack': (C.c_int, [C.POINTER(DecoderCfg), C.POINTER(c_void_p), c_void_p, c_void_p]),
+    'scf_decoder_forward': (C.c_int, [C.POINTER(DecoderCfg), c_void_p, C.POINTER(DecoderIO), C.c_int, C.c_int, C.c_int,
+                                      C.c_int, c_void_p, C.c_size_t, c_void_p]),
+    'scf_decoder_launch_count': (C.c_int, [C.POINTER(DecoderCfg), C.c_int]),
+}
+
+EXPORTED_SYMBOLS = sorted(_SIGNATURES)
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building in-tree first if nvcc is present and the library is missing/stale). Raises ScfError otherwise."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        have_nvcc = shutil.which('nvcc') is not None or os.path.exists('/usr/local/cuda/bin/nvcc')
+        if have_nvcc and os.environ.get('SCFLOW_NO_AUTOBUILD') != '1':
+            try:
+                if _build.needs_build():
+                    _build.build()
+            except Exception as e:  # stale-but-present library is still usable; missing one is fatal below
+                if not os.path.exists(path):
+                    raise ScfError(f'could not build {path}: {e}') from e
+        if not os.path.exists(path):
+            raise ScfError(f'{path} not found: run `python -c "import __graft_entry__ as g; g.build()"` (needs nvcc). '
+                           'scflow_b200 has no CPU or PyTorch fallback.')
+        lib = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)     # AttributeError here = header/library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        if lib.scf_abi_version() != 1:
+            raise ScfError('libscflow_sm100a.so ABI version mismatch')
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = ''):
+    if rc != 0:
+        msg = load().scf_last_error().decode(errors='replace')
+        raise ScfError(f'{what or "scflow_b200"} failed (rc={rc}): {msg}')
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,185 @@
+// Correlation pyramid lookup (HBM/L2-bound gather) and the fp32 reference build of the pyramid.
+//
+// Index semantics follow models/utils/corr_lookup.py:102-136 exactly:
+//   centre c = (x + flow_x, y + flow_y) / 2^level ; tap (a,b) samples (c_x + a - r, c_y + b - r)  [x-major window]
+//   g = c*2/(W_l-1) - 1 ; i = ((g+1)*0.5)*(W_l-1)        -- replayed with round-to-nearest intrinsics, no FMA
+//   bilinear taps floor(i), floor(i)+1 ; out-of-range taps contribute 0 (padding_mode='zeros').
+#include "scf_common.cuh"
+
+namespace scf {
+
+int conv2d_f32(const scf_conv_desc& d, cudaStream_t st);
+
+constexpr int kMaxLevels = 6;
+
+struct LookupParams {
+  const float* lvl[kMaxLevels];
+  int hl[kMaxLevels], wl[kMaxLevels];
+  int num_levels, radius;
+  const float* flow8;
+  const float* mask;
+  float* out;
+  int out_stride, out_coff;
+  int H8, W8;
+  long long nq;
+};
+
+// un-normalised sample coordinate of one axis, bit-exact replay of the reference's fp32 sequence
+__device__ __forceinline__ float lookup_coord(float centre, int off, int size) {
+  const float p = __fadd_rn(centre, (float)off);
+  const float den = (float)(size - 1 > 1 ? size - 1 : 1);
+  const float g = __fsub_rn(__fdiv_rn(__fmul_rn(p, 2.0f), den), 1.0f);
+  return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), (float)(size - 1));
+}
+
+__global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= p.nq) return;
+  const int P = p.H8 * p.W8;
+  const int pix = (int)(q % P);
+  const int y = pix / p.W8, x = pix - y * p.W8;
+  const float2 f = *reinterpret_cast<const float2*>(p.flow8 + q * 2);
+  const float gx0 = __fadd_rn((float)x, f.x), gy0 = __fadd_rn((float)y, f.y);
+  const float mval = p.mask ? p.mask[q] : 1.f;
+  const int r = p.radius, k = 2 * r + 1, kk = k * k;
+  float* outq = p.out + q * p.out_stride + p.out_coff;
+  float inv = 1.f;
+  for (int l = 0; l < p.num_levels; ++l, inv *= 0.5f) {
+    const int hl = p.hl[l], wl = p.wl[l];
+    const float* vol = p.lvl[l] + q * (long long)(hl * wl);
+    const float cx = __fmul_rn(gx0, inv), cy = __fmul_rn(gy0, inv);   // division by 2^l is exact
+    for (int tap = lane; tap < kk; tap += 32) {
+      const int a = tap / k, b = tap - a * k;
+      const float ix = lookup_coord(cx, a - r, wl);
+      const float iy = lookup_coord(cy, b - r, hl);
+      const float x0f = floorf(ix), y0f = floorf(iy);
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      const float wx1 = ix - x0f, wx0 = (x0f + 1.f) - ix;
+      const float wy1 = iy - y0f, wy0 = (y0f + 1.f) - iy;
+      const bool xin0 = x0 >= 0 && x0 < wl, xin1 = x0 + 1 >= 0 && x0 + 1 < wl;
+      const bool yin0 = y0 >= 0 && y0 < hl, yin1 = y0 + 1 >= 0 && y0 + 1 < hl;
+      float acc = 0.f;
+      if (yin0) {
+        const float* row = vol + y0 * wl;
+        if (xin0) acc += __ldg(row + x0) * (wx0 * wy0);
+        if (xin1) acc += __ldg(row + x0 + 1) * (wx1 * wy0);
+      }
+      if (yin1) {
+        const float* row = vol + (y0 + 1) * wl;
+        if (xin0) acc += __ldg(row + x0) * (wx0 * wy1);
+        if (xin1) acc += __ldg(row + x0 + 1) * (wx1 * wy1);
+      }
+      outq[l * kk + tap] = acc * mval;
+    }
+  }
+}
+
+__global__ void corr_lookup_taps_kernel(int level, int radius, const float* __restrict__ flow8, int32_t* __restrict__ x0,
+                                        int32_t* __restrict__ y0, int H8, int W8, long long nq) {
+  const int k = 2 * radius + 1;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nq * k) return;
+  const long long q = idx / k;
+  const int a = (int)(idx - q * k);
+  const int pix = (int)(q % (H8 * W8));
+  const int y = pix / W8, x = pix - y * W8;
+  int hl = H8, wl = W8;
+  float inv = 1.f;
+  for (int l = 0; l < level; ++l) { hl >>= 1; wl >>= 1; inv *= 0.5f; }
+  const float cx = __fmul_rn(__fadd_rn((float)x, flow8[q * 2]), inv);
+  const float cy = __fmul_rn(__fadd_rn((float)y, flow8[q * 2 + 1]), inv);
+  x0[idx] = (int)floorf(lookup_coord(cx, a - radius, wl));
+  y0[idx] = (int)floorf(lookup_coord(cy, a - radius, hl));
+}
+
+// 2x2 mean pool with floor semantics (nn.AvgPool2d(2,2), raft_decoder.py:54-56): out[q][y][x] over in[q][2y..][2x..]
+__global__ void avgpool2_kernel(const float* __restrict__ in, float* __restrict__ out, int hi, int wi, int ho, int wo,
+                                long long total) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int xo = (int)(idx % wo);
+    const long long r = idx / wo;
+    const int yo = (int)(r % ho);
+    const long long q = r / ho;
+    const float* src = in + (q * hi + 2 * yo) * (long long)wi + 2 * xo;
+    const float s = ((src[0] + src[1]) + src[wi]) + src[wi + 1];
+    out[idx] = s * 0.25f;
+  }
+}
+
+int avgpool2(const float* in, float* out, long long nq, int hi, int wi, cudaStream_t st) {
+  const int ho = hi / 2, wo = wi / 2;
+  const long long total = nq * ho * wo;
+  if (total == 0) return 0;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  avgpool2_kernel<<<blocks, 256, 0, st>>>(in, out, hi, wi, ho, wo, total);
+  return check_launch("avgpool2_kernel");
+}
+
+// fp32 (CUDA-core) pyramid build: level0 = conv1x1 with per-sample "weights" feat_real ([C][P] is already the
+// packed [k][n] layout), scaled by 1/sqrt(C); then successive floor pools. The tcgen05 build lives in scf_corr_tc.cu.
+int corr_build_f32(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
+                   float* const* levels, void* scratch, cudaStream_t st) {
+  const int P = H8 * W8;
+  float* f1t = reinterpret_cast<float*>(scratch);  // [B,P,C]
+  SCF_TRY(scf_nchw_to_nhwc(feat_render, f1t, B, C, H8, W8, C, 0, st));
+  scf_conv_desc d = {};
+  d.seg[0] = {f1t, C, 0, C};
+  d.nseg = 1;
+  d.B = B; d.Hi = d.Ho = H8; d.Wi = d.Wo = W8;
+  d.kh = d.kw = 1; d.sh = d.sw = 1; d.ph = d.pw = 0;
+  d.w = feat_real; d.w_batch_stride = (long long)C * P; d.ldw = P; d.cout = P;
+  d.bias = nullptr; d.scale = 1.0f / sqrtf((float)C);
+  d.epi = SCF_EPI_ACT; d.act = SCF_ACT_NONE;
+  d.out = levels[0]; d.out_stride = P; d.out_coff = 0;
+  SCF_TRY(conv2d_f32(d, st));
+  int hl = H8, wl = W8;
+  for (int l = 1; l < num_levels; ++l) {
+    SCF_TRY(avgpool2(levels[l - 1], levels[l], (long long)B * P, hl, wl, st));
+    hl /= 2; wl /= 2;
+  }
+  return 0;
+}
+
+}  // namespace scf
+
+extern "C" {
+
+size_t scf_corr_build_scratch_bytes(int B, int C, int H8, int W8) {
+  // transposed feat_render fp32 [B,P,C]  (+ split-bf16 copies of both maps for the tensor-core build)
+  return (size_t)B * H8 * W8 * C * 4 * 3 + 1024;
+}
+
+int scf_corr_lookup(const float* const* h_levels, int num_levels, int radius, const float* flow8, const float* mask,
+                    float* out, int out_stride, int out_coff, int B, int H8, int W8, void* stream) {
+  SCF_REQUIRE(h_levels && flow8 && out, SCF_ERR_ARG, "scf_corr_lookup: null pointer");
+  SCF_REQUIRE(num_levels >= 1 && num_levels <= scf::kMaxLevels && radius >= 0 && radius <= 8, SCF_ERR_ARG,
+              "scf_corr_lookup: num_levels 1..%d, radius 0..8", scf::kMaxLevels);
+  SCF_REQUIRE(B > 0 && H8 > 0 && W8 > 0, SCF_ERR_ARG, "scf_corr_lookup: empty shape");
+  SCF_REQUIRE(reinterpret_cast<uintptr_t>(flow8) % 8 == 0, SCF_ERR_ALIGN, "scf_corr_lookup: flow8 must be 8B aligned");
+  scf::LookupParams p = {};
+  int hl = H8, wl = W8;
+  for (int l = 0; l < num_levels; ++l) {
+    SCF_REQUIRE(h_levels[l] != nullptr && hl >= 1 && wl >= 1, SCF_ERR_ARG, "scf_corr_lookup: level %d missing/empty", l);
+    p.lvl[l] = h_levels[l]; p.hl[l] = hl; p.wl[l] = wl;
+    hl /= 2; wl /= 2;
+  }
+  p.num_levels = num_levels; p.radius = radius; p.flow8 = flow8; p.mask = mask; p.out = out;
+  p.out_stride = out_stride; p.out_coff = out_coff; p.H8 = H8; p.W8 = W8; p.nq = (long long)B * H8 * W8;
+  const int wpb = 8;
+  scf::corr_lookup_kernel<<<scf::cdiv(p.nq, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(p);
+  return scf::check_launch("corr_lookup_kernel");
+}
+
+int scf_corr_lookup_taps(int level, int radius, const float* flow8, int32_t* x0, int32_t* y0, int B, int H8, int W8,
+                         void* stream) {
+  SCF_REQUIRE(flow8 && x0 && y0 && level >= 0 && level < scf::kMaxLevels, SCF_ERR_ARG, "scf_corr_lookup_taps: bad args");
+  const long long nq = (long long)B * H8 * W8;
+  const long long total = nq * (2 * radius + 1);
+  scf::corr_lookup_taps_kernel<<<scf::cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(level, radius, flow8, x0, y0, H8,
+                                                                                       W8, nq);
+  return scf::check_launch("corr_lookup_taps_kernel");
+}
+
+}  // extern "C"

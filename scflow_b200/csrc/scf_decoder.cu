@@ -1,0 +1,432 @@
+// Whole-loop driver: SCFlowDecoder.forward (models/decoder/scflow_decoder.py:150-251) as one C call that enqueues
+// every kernel of the iterative refinement on one stream.  No host synchronisation, no allocation: the caller
+// hands in a packed-weight arena (scf_decoder_pack) and a workspace (scf_decoder_workspace_bytes), so the whole
+// call is CUDA-graph capturable.
+#include "scf_common.cuh"
+#include <string.h>
+
+namespace scf {
+
+int conv2d_f32(const scf_conv_desc& d, cudaStream_t st);
+int corr_build_dispatch(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
+                        float* const* levels, void* scratch, int precision, cudaStream_t st);
+
+thread_local char g_err[512] = {0};
+thread_local long long g_launches = 0;
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------ packed convolution table
+enum PC {
+  PC_CORR0, PC_CORR1, PC_FLOW0, PC_FLOW1, PC_OUT0, PC_ZR0, PC_Q0, PC_ZR1, PC_Q1, PC_HEADS, PC_FHP, PC_MHP,
+  PC_DFE0, PC_DFE1, PC_ME0, PC_ME1, PC_PH0, PC_PH1, PC_PH2, PC_COUNT
+};
+struct PCInfo {
+  int cin, kh, kw, cout;      // cout = total (merged) output channels
+  int nsrc;                   // 1 or 2 reference convs merged along O
+  int src_w[2], src_b[2];     // scf_decoder_weight indices (bias -1 = none)
+  int src_cout[2];
+  int ldw;
+  size_t w_off, b_off;        // float offsets into the arena
+};
+
+struct Arena {
+  PCInfo pc[PC_COUNT];
+  size_t gn_w[3], gn_b[3];
+  size_t fc0_w, fc0_b, fc1_w, fc1_b, rot_w, rot_b, tr_w, tr_b;
+  size_t total_floats;
+  int nc, rot_rows, tr_rows;
+};
+
+static void build_arena(const scf_decoder_cfg& cfg, Arena& a) {
+  const int L = cfg.num_levels, k = 2 * cfg.radius + 1;
+  const int corr_ch = L * k * k;
+  auto set = [&](int id, int cin, int kh, int kw, int w0, int b0, int c0, int w1 = -1, int b1 = -1, int c1 = 0) {
+    PCInfo& p = a.pc[id];
+    p.cin = cin; p.kh = kh; p.kw = kw; p.nsrc = w1 >= 0 ? 2 : 1;
+    p.src_w[0] = w0; p.src_b[0] = b0; p.src_cout[0] = c0;
+    p.src_w[1] = w1; p.src_b[1] = b1; p.src_cout[1] = c1;
+    p.cout = c0 + c1;
+    p.ldw = (p.cout + 3) / 4 * 4;
+  };
+  set(PC_CORR0, corr_ch, 1, 1, SCF_W_CORR0_W, SCF_W_CORR0_B, 256);
+  set(PC_CORR1, 256, 3, 3, SCF_W_CORR1_W, SCF_W_CORR1_B, 192);
+  set(PC_FLOW0, 2, 7, 7, SCF_W_FLOW0_W, SCF_W_FLOW0_B, 128);
+  set(PC_FLOW1, 128, 3, 3, SCF_W_FLOW1_W, SCF_W_FLOW1_B, 64);
+  set(PC_OUT0, 256, 3, 3, SCF_W_OUT0_W, SCF_W_OUT0_B, 126);
+  set(PC_ZR0, 384, 1, 5, SCF_W_GRU_Z0_W, SCF_W_GRU_Z0_B, 128, SCF_W_GRU_R0_W, SCF_W_GRU_R0_B, 128);
+  set(PC_Q0, 384, 1, 5, SCF_W_GRU_Q0_W, SCF_W_GRU_Q0_B, 128);
+  set(PC_ZR1, 384, 5, 1, SCF_W_GRU_Z1_W, SCF_W_GRU_Z1_B, 128, SCF_W_GRU_R1_W, SCF_W_GRU_R1_B, 128);
+  set(PC_Q1, 384, 5, 1, SCF_W_GRU_Q1_W, SCF_W_GRU_Q1_B, 128);
+  set(PC_HEADS, 128, 3, 3, SCF_W_FH0_W, SCF_W_FH0_B, 256, SCF_W_MH0_W, SCF_W_MH0_B, 256);
+  set(PC_FHP, 256, 3, 3, SCF_W_FHP_W, SCF_W_FHP_B, 2);
+  set(PC_MHP, 256, 1, 1, SCF_W_MHP_W, SCF_W_MHP_B, 1);
+  set(PC_DFE0, 2, 7, 7, SCF_W_DFE0_W, SCF_W_DFE0_B, 128);
+  set(PC_DFE1, 128, 3, 3, SCF_W_DFE1_W, SCF_W_DFE1_B, 64);
+  set(PC_ME0, 1, 3, 3, SCF_W_ME0_W, SCF_W_ME0_B, 64);
+  set(PC_ME1, 64, 3, 3, SCF_W_ME1_W, SCF_W_ME1_B, 32);
+  set(PC_PH0, 224, 3, 3, SCF_W_PH_C0_W, -1, 128);
+  set(PC_PH1, 128, 3, 3, SCF_W_PH_C1_W, -1, 128);
+  set(PC_PH2, 128, 3, 3, SCF_W_PH_C2_W, -1, 128);
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 63) / 64 * 64; return o; };   // 256B-aligned slots
+  for (int i = 0; i < PC_COUNT; ++i) {
+    PCInfo& p = a.pc[i];
+    p.w_off = take((size_t)p.kh * p.kw * p.cin * p.ldw);
+    p.b_off = take(p.ldw);
+  }
+  for (int i = 0; i < 3; ++i) { a.gn_w[i] = take(128); a.gn_b[i] = take(128); }
+  a.nc = cfg.num_class > 0 ? cfg.num_class : 1;
+  a.rot_rows = cfg.rot_dim * a.nc;
+  a.tr_rows = 3 * a.nc;
+  a.fc0_w = take((size_t)1024 * 2048); a.fc0_b = take(1024);
+  a.fc1_w = take((size_t)256 * 1024); a.fc1_b = take(256);
+  a.rot_w = take((size_t)a.rot_rows * 256); a.rot_b = take(a.rot_rows);
+  a.tr_w = take((size_t)a.tr_rows * 256); a.tr_b = take(a.tr_rows);
+  a.total_floats = off;
+}
+
+// FC0 consumes the flattened NCHW map (index c*16 + pix, pose_head.py:203); our map is NHWC (pix*128 + c):
+// permute the columns once at pack time.
+__global__ void permute_fc0_kernel(const float* __restrict__ w, float* __restrict__ out, int O, int C, int PIX) {
+  const long long total = (long long)O * C * PIX;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const long long r = idx / C;
+    const int pix = (int)(r % PIX);
+    const long long o = r / PIX;
+    out[idx] = w[(o * C + c) * PIX + pix];
+  }
+}
+
+__global__ void fill_kernel(float* p, float v, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void mul_mask_kernel(const float* __restrict__ flow8, const float* __restrict__ mask, float* __restrict__ out,
+                                long long npix) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    const float m = mask[i];
+    out[2 * i] = flow8[2 * i] * m;
+    out[2 * i + 1] = flow8[2 * i + 1] * m;
+  }
+}
+__global__ void identity_delta_kernel(float* d_rot, float* d_trs, int B, int rot_dim) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int i = 0; i < rot_dim; ++i) d_rot[b * rot_dim + i] = (i == 0 || i == 4) ? 1.f : 0.f;   // ortho6d identity
+  d_trs[b * 3] = d_trs[b * 3 + 1] = d_trs[b * 3 + 2] = 0.f;
+}
+
+// ------------------------------------------------------------------ workspace
+struct Workspace {
+  size_t corr_scratch, lvl[8], pts4, flow8, flowm, maskprev, corr, c1, cf, f1, h[2], cxt, motion, z, rh, hd, dflow,
+      mask8, df1, df2, mf1, mf2, p1, p2, p3, fc0, fc1;
+  int hl[8], wl[8];
+  int corr_stride;
+  size_t total_bytes;
+};
+
+static void build_workspace(const scf_decoder_cfg& cfg, int B, int H, int W, Workspace& w) {
+  const int scale = 1 << (cfg.num_levels - 1);
+  const int H8 = H / scale, W8 = W / scale;
+  const size_t P = (size_t)H8 * W8, BP = (size_t)B * P;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  w.corr_scratch = take(scf_corr_build_scratch_bytes(B, 256, H8, W8));
+  int hl = H8, wl = W8;
+  for (int l = 0; l < cfg.num_levels; ++l) {
+    w.hl[l] = hl; w.wl[l] = wl;
+    w.lvl[l] = take(BP * (size_t)hl * wl * 4);
+    hl /= 2; wl /= 2;
+  }
+  const int k = 2 * cfg.radius + 1;
+  w.corr_stride = (cfg.num_levels * k * k + 3) / 4 * 4;
+  w.pts4 = take((size_t)B * H * W * 16);
+  w.flow8 = take(BP * 8); w.flowm = take(BP * 8); w.maskprev = take(BP * 4);
+  w.corr = take(BP * w.corr_stride * 4);
+  w.c1 = take(BP * 256 * 4); w.cf = take(BP * 256 * 4); w.f1 = take(BP * 128 * 4);
+  w.h[0] = take(BP * 128 * 4); w.h[1] = take(BP * 128 * 4);
+  w.cxt = take(BP * 128 * 4); w.motion = take(BP * 128 * 4);
+  w.z = take(BP * 128 * 4); w.rh = take(BP * 128 * 4);
+  w.hd = take(BP * 512 * 4); w.dflow = take(BP * 8); w.mask8 = take(BP * 4);
+  w.df1 = take(BP * 128 * 4); w.df2 = take(BP * 64 * 4); w.mf1 = take(BP * 64 * 4); w.mf2 = take(BP * 32 * 4);
+  w.p1 = take(BP / 4 * 128 * 4 + 1024); w.p2 = take(BP / 16 * 128 * 4 + 1024); w.p3 = take(BP / 64 * 128 * 4 + 1024);
+  w.fc0 = take((size_t)B * 1024 * 4); w.fc1 = take((size_t)B * 256 * 4);
+  w.total_bytes = off;
+}
+
+static int check_cfg(const scf_decoder_cfg* cfg) {
+  SCF_REQUIRE(cfg != nullptr, SCF_ERR_ARG, "scf_decoder: null cfg");
+  SCF_REQUIRE(cfg->num_levels >= 1 && cfg->num_levels <= 6, SCF_ERR_ARG, "scf_decoder: num_levels must be 1..6");
+  SCF_REQUIRE(cfg->radius >= 0 && cfg->radius <= 8, SCF_ERR_ARG, "scf_decoder: radius must be 0..8");
+  SCF_REQUIRE(cfg->rot_dim == 6, SCF_ERR_UNSUPPORTED, "scf_decoder: only rotation_mode='ortho6d' (rot_dim 6) is implemented");
+  SCF_REQUIRE(cfg->precision == 0 || cfg->precision == 1, SCF_ERR_ARG, "scf_decoder: precision must be 0 or 1");
+  return 0;
+}
+
+}  // namespace scf
+
+using namespace scf;
+
+extern "C" {
+
+int scf_abi_version(void) { return SCF_ABI_VERSION; }
+const char* scf_last_error(void) { return scf::g_err; }
+
+int scf_device_supported(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+long long scf_launch_counter(void) { return scf::g_launches; }
+
+size_t scf_decoder_packed_bytes(const scf_decoder_cfg* cfg) {
+  if (check_cfg(cfg) != 0) return 0;
+  Arena a;
+  build_arena(*cfg, a);
+  return a.total_floats * 4;
+}
+
+size_t scf_decoder_workspace_bytes(const scf_decoder_cfg* cfg, int B, int H, int W) {
+  if (check_cfg(cfg) != 0 || B <= 0 || H <= 0 || W <= 0) return 0;
+  Workspace w;
+  build_workspace(*cfg, B, H, W, w);
+  return w.total_bytes;
+}
+
+int scf_decoder_pack(const scf_decoder_cfg* cfg, const float* const* h_weights, void* packed, void* stream) {
+  SCF_TRY(check_cfg(cfg));
+  SCF_REQUIRE(h_weights && packed, SCF_ERR_ARG, "scf_decoder_pack: null pointer");
+  SCF_REQUIRE(reinterpret_cast<uintptr_t>(packed) % 256 == 0, SCF_ERR_ALIGN, "scf_decoder_pack: arena must be 256B aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena a;
+  build_arena(*cfg, a);
+  float* base = reinterpret_cast<float*>(packed);
+  SCF_CUDA(cudaMemsetAsync(packed, 0, a.total_floats * 4, st));
+  for (int i = 0; i < PC_COUNT; ++i) {
+    const PCInfo& p = a.pc[i];
+    if (!cfg->pose_head && i >= PC_PH0) continue;
+    int o_off = 0;
+    for (int s = 0; s < p.nsrc; ++s) {
+      SCF_REQUIRE(h_weights[p.src_w[s]] != nullptr, SCF_ERR_ARG, "scf_decoder_pack: weight %d is null", p.src_w[s]);
+      SCF_TRY(scf_pack_conv_weight(h_weights[p.src_w[s]], base + p.w_off, p.src_cout[s], p.cin, p.kh, p.kw, p.ldw, o_off, st));
+      if (p.src_b[s] >= 0) {
+        SCF_REQUIRE(h_weights[p.src_b[s]] != nullptr, SCF_ERR_ARG, "scf_decoder_pack: bias %d is null", p.src_b[s]);
+        SCF_CUDA(cudaMemcpyAsync(base + p.b_off + o_off, h_weights[p.src_b[s]], (size_t)p.src_cout[s] * 4,
+                                 cudaMemcpyDeviceToDevice, st));
+      }
+      o_off += p.src_cout[s];
+    }
+  }
+  if (cfg->pose_head) {
+    const int gw[3] = {SCF_W_PH_G0_W, SCF_W_PH_G1_W, SCF_W_PH_G2_W}, gb[3] = {SCF_W_PH_G0_B, SCF_W_PH_G1_B, SCF_W_PH_G2_B};
+    for (int i = 0; i < 3; ++i) {
+      SCF_REQUIRE(h_weights[gw[i]] && h_weights[gb[i]], SCF_ERR_ARG, "scf_decoder_pack: GroupNorm params missing");
+      SCF_CUDA(cudaMemcpyAsync(base + a.gn_w[i], h_weights[gw[i]], 128 * 4, cudaMemcpyDeviceToDevice, st));
+      SCF_CUDA(cudaMemcpyAsync(base + a.gn_b[i], h_weights[gb[i]], 128 * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    for (int i = SCF_W_PH_FC0_W; i <= SCF_W_PH_TR_B; ++i)
+      SCF_REQUIRE(h_weights[i] != nullptr, SCF_ERR_ARG, "scf_decoder_pack: pose-head FC weight %d is null", i);
+    permute_fc0_kernel<<<1024, 256, 0, st>>>(h_weights[SCF_W_PH_FC0_W], base + a.fc0_w, 1024, 128, 16);
+    SCF_TRY(check_launch("permute_fc0_kernel"));
+    SCF_CUDA(cudaMemcpyAsync(base + a.fc0_b, h_weights[SCF_W_PH_FC0_B], 1024 * 4, cudaMemcpyDeviceToDevice, st));
+    SCF_CUDA(cudaMemcpyAsync(base + a.fc1_w, h_weights[SCF_W_PH_FC1_W], (size_t)256 * 1024 * 4, cudaMemcpyDeviceToDevice, st));
+    SCF_CUDA(cudaMemcpyAsync(base + a.fc1_b, h_weights[SCF_W_PH_FC1_B], 256 * 4, cudaMemcpyDeviceToDevice, st));
+    SCF_CUDA(cudaMemcpyAsync(base + a.rot_w, h_weights[SCF_W_PH_ROT_W], (size_t)a.rot_rows * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    SCF_CUDA(cudaMemcpyAsync(base + a.rot_b, h_weights[SCF_W_PH_ROT_B], (size_t)a.rot_rows * 4, cudaMemcpyDeviceToDevice, st));
+    SCF_CUDA(cudaMemcpyAsync(base + a.tr_w, h_weights[SCF_W_PH_TR_W], (size_t)a.tr_rows * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    SCF_CUDA(cudaMemcpyAsync(base + a.tr_b, h_weights[SCF_W_PH_TR_B], (size_t)a.tr_rows * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int scf_corr_build(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
+                   float* const* h_levels, void* scratch, int precision, void* stream) {
+  SCF_REQUIRE(feat_render && feat_real && h_levels && scratch, SCF_ERR_ARG, "scf_corr_build: null pointer");
+  SCF_REQUIRE(B > 0 && C > 0 && H8 > 0 && W8 > 0 && num_levels >= 1 && num_levels <= 6, SCF_ERR_ARG, "scf_corr_build: bad shape");
+  SCF_REQUIRE(C % 4 == 0 && (H8 * W8) % 4 == 0, SCF_ERR_UNSUPPORTED, "scf_corr_build: C and H8*W8 must be multiples of 4");
+  for (int l = 0; l < num_levels; ++l) SCF_REQUIRE(h_levels[l] != nullptr, SCF_ERR_ARG, "scf_corr_build: level %d null", l);
+  return corr_build_dispatch(feat_render, feat_real, B, C, H8, W8, num_levels, h_levels, scratch, precision,
+                             (cudaStream_t)stream);
+}
+
+int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const scf_decoder_io* io, int B, int H, int W,
+                        int iters, void* workspace, size_t workspace_bytes, void* stream) {
+  SCF_TRY(check_cfg(cfg));
+  SCF_REQUIRE(packed && io && workspace, SCF_ERR_ARG, "scf_decoder_forward: null pointer");
+  SCF_REQUIRE(B > 0 && iters > 0, SCF_ERR_ARG, "scf_decoder_forward: B and iters must be positive");
+  const int scale = 1 << (cfg->num_levels - 1);
+  SCF_REQUIRE(H % scale == 0 && W % scale == 0 && H >= 2 * scale && W >= 2 * scale, SCF_ERR_ARG,
+              "scf_decoder_forward: H, W must be multiples of %d", scale);
+  SCF_REQUIRE(io->feat_render && io->feat_real && io->h_feat && io->cxt_feat && io->ref_rotation && io->ref_translation &&
+                  io->depth && io->internel_k && io->init_flow,
+              SCF_ERR_ARG, "scf_decoder_forward: null input");
+  SCF_REQUIRE(io->flow_from_pose && io->flow_from_pred && io->rotation && io->translation && io->mask &&
+                  io->delta_rotation && io->delta_translation,
+              SCF_ERR_ARG, "scf_decoder_forward: null output");
+  SCF_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 256 == 0 && reinterpret_cast<uintptr_t>(packed) % 256 == 0,
+              SCF_ERR_ALIGN, "scf_decoder_forward: workspace / packed arena must be 256B aligned");
+  const int H8 = H / scale, W8 = W / scale, P = H8 * W8;
+  if (cfg->pose_head) {
+    SCF_REQUIRE(H8 == 32 && W8 == 32, SCF_ERR_UNSUPPORTED,
+                "scf_decoder_forward: the pose head's FC expects a 32x32 feature map (pose_head.py:147-167); got %dx%d", H8, W8);
+    SCF_REQUIRE(cfg->num_class <= 0 || io->label != nullptr, SCF_ERR_ARG, "scf_decoder_forward: label required");
+  }
+  Arena a;
+  build_arena(*cfg, a);
+  Workspace ws;
+  build_workspace(*cfg, B, H, W, ws);
+  SCF_REQUIRE(workspace_bytes >= ws.total_bytes, SCF_ERR_ARG, "scf_decoder_forward: workspace too small (%zu < %zu)",
+              workspace_bytes, ws.total_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* wsb = reinterpret_cast<char*>(workspace);
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(wsb + off); };
+  const float* pw = reinterpret_cast<const float*>(packed);
+  const long long HW = (long long)H * W;
+  const size_t BP = (size_t)B * P;
+
+  // ---- once per forward: pyramid, point map, layout conversion of h / context
+  float* levels[8];
+  for (int l = 0; l < cfg->num_levels; ++l) levels[l] = F(ws.lvl[l]);
+  SCF_TRY(corr_build_dispatch(io->feat_render, io->feat_real, B, 256, H8, W8, cfg->num_levels, levels, wsb + ws.corr_scratch,
+                              cfg->precision, st));
+  SCF_TRY(scf_unproject(io->depth, io->internel_k, io->ref_rotation, io->ref_translation, F(ws.pts4), B, H, W, st));
+  SCF_TRY(scf_nchw_to_nhwc(io->h_feat, F(ws.h[0]), B, 128, H8, W8, 128, 0, st));
+  SCF_TRY(scf_nchw_to_nhwc(io->cxt_feat, F(ws.cxt), B, 128, H8, W8, 128, 0, st));
+  if (cfg->mask_corr || cfg->mask_flow) {
+    fill_kernel<<<cdiv(BP, 256), 256, 0, st>>>(F(ws.maskprev), 1.f, (long long)BP);
+    SCF_TRY(check_launch("fill_kernel"));
+  }
+
+  auto conv = [&](int id, std::initializer_list<scf_conv_seg> segs, int Hi, int Wi, int Ho, int Wo, int stride, int act,
+                  float* out, int out_stride, int out_coff, int epi = SCF_EPI_ACT, const float* aux0 = nullptr,
+                  const float* aux1 = nullptr, float* out2 = nullptr) -> int {
+    const PCInfo& p = a.pc[id];
+    scf_conv_desc d = {};
+    int n = 0;
+    for (const scf_conv_seg& s : segs) d.seg[n++] = s;
+    d.nseg = n;
+    d.B = B; d.Hi = Hi; d.Wi = Wi; d.Ho = Ho; d.Wo = Wo;
+    d.kh = p.kh; d.kw = p.kw; d.sh = d.sw = stride; d.ph = p.kh / 2; d.pw = p.kw / 2;
+    d.w = pw + p.w_off; d.w_batch_stride = 0; d.ldw = p.ldw; d.cout = p.cout;
+    d.bias = p.src_b[0] >= 0 ? pw + p.b_off : nullptr;
+    d.scale = 1.f; d.epi = epi; d.act = act;
+    d.out = out; d.out_stride = out_stride; d.out_coff = out_coff;
+    d.aux0 = aux0; d.aux0_stride = 128; d.aux1 = aux1; d.aux1_stride = 128; d.out2 = out2; d.out2_stride = 128;
+    return conv2d_f32(d, st);
+  };
+
+  const float* flow_full = io->init_flow;
+  for (int it = 0; it < iters; ++it) {
+    float* flow_pose_k = io->flow_from_pose + (size_t)it * B * 2 * HW;
+    float* flow_pred_k = io->flow_from_pred + (size_t)it * B * 2 * HW;
+    float* mask_k = io->mask + (size_t)it * B * HW;
+    float* rot_k = io->rotation + (size_t)it * B * 9;
+    float* trs_k = io->translation + (size_t)it * B * 3;
+    float* drot_k = io->delta_rotation + (size_t)it * B * cfg->rot_dim;
+    float* dtrs_k = io->delta_translation + (size_t)it * B * 3;
+    const float* rot_prev = it == 0 ? io->ref_rotation : io->rotation + (size_t)(it - 1) * B * 9;
+    const float* trs_prev = it == 0 ? io->ref_translation : io->translation + (size_t)(it - 1) * B * 3;
+
+    // flow8 = 1/8 * down8(flow)                                          (scflow_decoder.py:196-197)
+    SCF_TRY(scf_resize_bilinear(flow_full, nullptr, 2 * HW, HW, W, 1, H, W, F(ws.flow8), (long long)P * 2, 1,
+                                (long long)W8 * 2, 2, H8, W8, B, 2, 1.0f / scale, st));
+    const float* menc_flow = F(ws.flow8);
+    if (cfg->mask_flow) {
+      mul_mask_kernel<<<cdiv(BP, 256), 256, 0, st>>>(F(ws.flow8), F(ws.maskprev), F(ws.flowm), (long long)BP);
+      SCF_TRY(check_launch("mul_mask_kernel"));
+      menc_flow = F(ws.flowm);
+    }
+    // lookup                                                              (:198-201)
+    SCF_TRY(scf_corr_lookup(levels, cfg->num_levels, cfg->radius, F(ws.flow8), cfg->mask_corr ? F(ws.maskprev) : nullptr,
+                            F(ws.corr), ws.corr_stride, 0, B, H8, W8, st));
+    // motion encoder                                                      (raft_decoder.py:152-166)
+    const int corr_ch = a.pc[PC_CORR0].cin;
+    SCF_TRY(conv(PC_CORR0, {{F(ws.corr), ws.corr_stride, 0, corr_ch}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.c1), 256, 0));
+    SCF_TRY(conv(PC_CORR1, {{F(ws.c1), 256, 0, 256}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.cf), 256, 0));
+    SCF_TRY(conv(PC_FLOW0, {{menc_flow, 2, 0, 2}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.f1), 128, 0));
+    SCF_TRY(conv(PC_FLOW1, {{F(ws.f1), 128, 0, 128}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.cf), 256, 192));
+    SCF_TRY(conv(PC_OUT0, {{F(ws.cf), 256, 0, 256}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.motion), 128, 0));
+    SCF_TRY(scf_resize_bilinear(menc_flow, nullptr, (long long)P * 2, 1, (long long)W8 * 2, 2, H8, W8, F(ws.motion) + 126,
+                                (long long)P * 128, 1, (long long)W8 * 128, 128, H8, W8, B, 2, 1.f, st));
+    // SepConvGRU                                                          (raft_decoder.py:235-253)
+    for (int pass = 0; pass < 2; ++pass) {
+      float* hin = F(ws.h[pass]);
+      float* hout = F(ws.h[pass ^ 1]);
+      SCF_TRY(conv(pass == 0 ? PC_ZR0 : PC_ZR1, {{hin, 128, 0, 128}, {F(ws.cxt), 128, 0, 128}, {F(ws.motion), 128, 0, 128}},
+                   H8, W8, H8, W8, 1, SCF_ACT_SIGMOID, F(ws.z), 128, 0, SCF_EPI_GRU_ZR, hin, nullptr, F(ws.rh)));
+      SCF_TRY(conv(pass == 0 ? PC_Q0 : PC_Q1, {{F(ws.rh), 128, 0, 128}, {F(ws.cxt), 128, 0, 128}, {F(ws.motion), 128, 0, 128}},
+                   H8, W8, H8, W8, 1, SCF_ACT_TANH, hout, 128, 0, SCF_EPI_GRU_Q, hin, F(ws.z), nullptr));
+    }
+    float* h = F(ws.h[0]);
+    // flow / mask heads                                                   (scflow_decoder.py:210-213)
+    SCF_TRY(conv(PC_HEADS, {{h, 128, 0, 128}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.hd), 512, 0));
+    SCF_TRY(conv(PC_FHP, {{F(ws.hd), 512, 0, 256}}, H8, W8, H8, W8, 1, SCF_ACT_NONE, F(ws.dflow), 2, 0));
+    SCF_TRY(conv(PC_MHP, {{F(ws.hd), 512, 256, 256}}, H8, W8, H8, W8, 1, SCF_ACT_SIGMOID, F(ws.mask8), 1, 0));
+    if (cfg->pose_head) {
+      // delta-flow / mask encoders + pose regressor                       (:216-219, pose_head.py:201-211)
+      SCF_TRY(conv(PC_DFE0, {{F(ws.dflow), 2, 0, 2}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.df1), 128, 0));
+      SCF_TRY(conv(PC_DFE1, {{F(ws.df1), 128, 0, 128}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.df2), 64, 0));
+      SCF_TRY(conv(PC_ME0, {{F(ws.mask8), 1, 0, 1}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.mf1), 64, 0));
+      SCF_TRY(conv(PC_ME1, {{F(ws.mf1), 64, 0, 64}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.mf2), 32, 0));
+      const int h1 = (H8 - 1) / 2 + 1, w1 = (W8 - 1) / 2 + 1, h2 = (h1 - 1) / 2 + 1, w2 = (w1 - 1) / 2 + 1,
+                h3 = (h2 - 1) / 2 + 1, w3 = (w2 - 1) / 2 + 1;
+      SCF_TRY(conv(PC_PH0, {{h, 128, 0, 128}, {F(ws.df2), 64, 0, 64}, {F(ws.mf2), 32, 0, 32}}, H8, W8, h1, w1, 2, SCF_ACT_NONE,
+                   F(ws.p1), 128, 0));
+      SCF_TRY(scf_group_norm_relu(F(ws.p1), pw + a.gn_w[0], pw + a.gn_b[0], B, h1 * w1, 128, 32, 1e-5f, st));
+      SCF_TRY(conv(PC_PH1, {{F(ws.p1), 128, 0, 128}}, h1, w1, h2, w2, 2, SCF_ACT_NONE, F(ws.p2), 128, 0));
+      SCF_TRY(scf_group_norm_relu(F(ws.p2), pw + a.gn_w[1], pw + a.gn_b[1], B, h2 * w2, 128, 32, 1e-5f, st));
+      SCF_TRY(conv(PC_PH2, {{F(ws.p2), 128, 0, 128}}, h2, w2, h3, w3, 2, SCF_ACT_NONE, F(ws.p3), 128, 0));
+      SCF_TRY(scf_group_norm_relu(F(ws.p3), pw + a.gn_w[2], pw + a.gn_b[2], B, h3 * w3, 128, 32, 1e-5f, st));
+      SCF_TRY(scf_linear(F(ws.p3), pw + a.fc0_w, pw + a.fc0_b, F(ws.fc0), B, 2048, 1024, SCF_ACT_RELU, st));
+      SCF_TRY(scf_linear(F(ws.fc0), pw + a.fc1_w, pw + a.fc1_b, F(ws.fc1), B, 1024, 256, SCF_ACT_RELU, st));
+      SCF_TRY(scf_pose_project(F(ws.fc1), pw + a.rot_w, pw + a.rot_b, pw + a.tr_w, pw + a.tr_b, io->label, drot_k, dtrs_k, B,
+                               256, cfg->rot_dim, cfg->num_class, st));
+    } else {
+      identity_delta_kernel<<<cdiv(B, 64), 64, 0, st>>>(drot_k, dtrs_k, B, cfg->rot_dim);
+      SCF_TRY(check_launch("identity_delta_kernel"));
+    }
+    // flow_pred = 8 * up8(flow8 + dflow) ; mask_up = up8(mask)            (:222-227)
+    SCF_TRY(scf_resize_bilinear(F(ws.flow8), F(ws.dflow), (long long)P * 2, 1, (long long)W8 * 2, 2, H8, W8, flow_pred_k, 2 * HW,
+                                HW, W, 1, H, W, B, 2, (float)scale, st));
+    SCF_TRY(scf_resize_bilinear(F(ws.mask8), nullptr, P, 0, W8, 1, H8, W8, mask_k, HW, 0, W, 1, H, W, B, 1, 1.f, st));
+    // pose update + pose-induced flow                                     (:230-243)
+    SCF_TRY(scf_pose_update(drot_k, dtrs_k, rot_prev, trs_prev, rot_k, trs_k, B, st));
+    SCF_TRY(scf_reproject(F(ws.pts4), io->internel_k, rot_k, trs_k, io->invalid_flow_num, flow_pose_k, B, H, W, st));
+    flow_full = flow_pose_k;
+    if (cfg->mask_corr || cfg->mask_flow)
+      SCF_CUDA(cudaMemcpyAsync(F(ws.maskprev), F(ws.mask8), BP * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (io->h_out) SCF_TRY(scf_nhwc_to_nchw(F(ws.h[0]), 128, 0, io->h_out, B, 128, H8, W8, st));
+  return 0;
+}
+
+int scf_decoder_launch_count(const scf_decoder_cfg* cfg, int iters) {
+  if (check_cfg(cfg) != 0) return -1;
+  int per_iter = 1 /*down8*/ + 1 /*lookup*/ + 6 /*menc*/ + 4 /*gru*/ + 3 /*heads*/ + 2 /*up8*/ + 2 /*pose upd + reproject*/;
+  per_iter += cfg->pose_head ? 4 + 6 + 3 : 1;
+  per_iter += cfg->mask_flow ? 1 : 0;
+  int once = 2 /*nchw->nhwc feat_render + level0 (fp32 build)*/ + (cfg->num_levels - 1) + 1 /*unproject*/ + 2 /*h, cxt*/;
+  if (cfg->mask_corr || cfg->mask_flow) once += 1;
+  return once + per_iter * iters;
+}
+
+}  // extern "C"
+
+namespace scf {
+int corr_build_f32(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
+                   float* const* levels, void* scratch, cudaStream_t st);
+int corr_build_dispatch(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
+                        float* const* levels, void* scratch, int precision, cudaStream_t st) {
+  (void)precision;
+  return corr_build_f32(feat_render, feat_real, B, C, H8, W8, num_levels, levels, scratch, st);
+}
+}  // namespace scf

@@ -1,0 +1,341 @@
+"""SCFlow decoder and its RAFT building blocks, registered under the reference's names with the reference's
+constructor kwargs and state-dict keys (models/decoder/scflow_decoder.py, models/decoder/raft_decoder.py:19-294).
+
+``SCFlowDecoder.forward`` is ONE call into the C ABI (``scf_decoder_forward``): the C++ side enqueues the pyramid
+build and every kernel of every refinement iteration on the current CUDA stream; Python only allocates the
+outputs / workspace and (optionally) replays the whole thing as a CUDA graph.
+"""
+import ctypes as C
+from typing import Optional, Sequence, Union
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .builder import DECODERS, build_head
+from .cnn import BaseModule, ConvModule, PackedCache
+from .corr_lookup import CorrLookup
+
+
+class CorrelationPyramid(BaseModule):
+    """All-pairs correlation volume + average-pooled pyramid (raft_decoder.py:19-58)."""
+
+    def __init__(self, num_levels: int = 4, precision: int = ops.PRECISION_FP32) -> None:
+        super().__init__()
+        self.num_levels = num_levels
+        self.precision = precision
+
+    def forward(self, feat1: torch.Tensor, feat2: torch.Tensor) -> Sequence[torch.Tensor]:
+        return ops.corr_build(feat1.contiguous(), feat2.contiguous(), self.num_levels, self.precision)
+
+
+class MotionEncoder(BaseModule):
+    """raft_decoder.py:61-166; only the channel tables of the reference are reproduced."""
+    _corr_channels = {'Basic': (256, 192), 'Small': 96, 'Large': (256, 192)}
+    _corr_kernel = {'Basic': (1, 3), 'Small': 1, 'Large': (1, 3)}
+    _corr_padding = {'Basic': (0, 1), 'Small': 0, 'Large': (0, 1)}
+    _flow_channels = {'Basic': (128, 64), 'Small': (64, 32), 'Large': (128, 64)}
+    _flow_kernel = {'Basic': (7, 3), 'Small': (7, 3), 'Large': (7, 3)}
+    _flow_padding = {'Basic': (3, 1), 'Small': (3, 1), 'Large': (3, 1)}
+    _out_channels = {'Basic': 126, 'Small': 80, 'Large': 126}
+    _out_kernel = {'Basic': 3, 'Small': 3, 'Large': 3}
+    _out_padding = {'Basic': 1, 'Small': 1, 'Large': 1}
+
+    def __init__(self, num_levels: int = 4, radius: int = 4, net_type: str = 'Basic', **kwargs) -> None:
+        super().__init__()
+        assert net_type in ['Basic', 'Small', 'Large']
+
+        def as_list(v):
+            return list(v) if isinstance(v, (tuple, list)) else [v]
+
+        corr_channels = as_list(self._corr_channels[net_type])
+        self.out_channels = as_list(self._out_channels[net_type])
+        corr_inch = num_levels * (2 * radius + 1) ** 2
+        self.corr_net = nn.Sequential(*self._make_encoder(corr_inch, corr_channels, as_list(self._corr_kernel[net_type]),
+                                                          as_list(self._corr_padding[net_type]), **kwargs))
+        flow_channels = as_list(self._flow_channels[net_type])
+        self.flow_net = nn.Sequential(*self._make_encoder(2, flow_channels, as_list(self._flow_kernel[net_type]),
+                                                          as_list(self._flow_padding[net_type]), **kwargs))
+        self.out_net = nn.Sequential(*self._make_encoder(corr_channels[-1] + flow_channels[-1], self.out_channels,
+                                                         as_list(self._out_kernel[net_type]),
+                                                         as_list(self._out_padding[net_type]), **kwargs))
+
+    @staticmethod
+    def _make_encoder(in_channel, channels, kernels, paddings, conv_cfg=None, norm_cfg=None, act_cfg=None):
+        layers = []
+        for ch, k, p in zip(channels, kernels, paddings):
+            layers.append(ConvModule(in_channel, ch, k, padding=p, conv_cfg=conv_cfg, norm_cfg=norm_cfg, act_cfg=act_cfg))
+            in_channel = ch
+        return layers
+
+    def forward(self, corr: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+        """corr [B,324,H,W], flow [B,2,H,W] -> [B,128,H,W] (standalone NCHW form of raft_decoder.py:152-166)."""
+        b, _, h, w = flow.shape
+        x = ops.nchw_to_nhwc(corr.contiguous())
+        for layer in self.corr_net:
+            x = layer.forward_nhwc([(x, 0, layer.in_channels)])
+        fl = ops.nchw_to_nhwc(flow.contiguous())
+        f = fl
+        for layer in self.flow_net:
+            f = layer.forward_nhwc([(f, 0, layer.in_channels)])
+        cout = self.out_channels[0]
+        out = torch.empty(b, h, w, cout + 2, device=flow.device, dtype=torch.float32)
+        self.out_net[0].forward_nhwc([(x, 0, x.shape[-1]), (f, 0, f.shape[-1])], out=out, out_coff=0)
+        out[..., cout:] = fl
+        return ops.nhwc_to_nchw(out)
+
+
+class ConvGRU(BaseModule):
+    """raft_decoder.py:168-253. z and r share one N=2*Ch convolution whose epilogue also forms r*h; the q
+    convolution's epilogue applies the state update."""
+    _kernel = {'Conv': 3, 'SeqConv': ((1, 5), (5, 1))}
+    _padding = {'Conv': 1, 'SeqConv': ((0, 2), (2, 0))}
+
+    def __init__(self, h_channels: int, x_channels: int, net_type: str = 'SeqConv') -> None:
+        super().__init__()
+        assert net_type in ['Conv', 'SeqConv']
+        kernel_size = self._kernel[net_type] if isinstance(self._kernel[net_type], (tuple, list)) else [self._kernel[net_type]]
+        padding = self._padding[net_type] if isinstance(self._padding[net_type], (tuple, list)) else [self._padding[net_type]]
+        self.h_channels, self.x_channels = h_channels, x_channels
+        conv_z, conv_r, conv_q = [], [], []
+        for k, p in zip(kernel_size, padding):
+            conv_z.append(ConvModule(h_channels + x_channels, h_channels, k, padding=p, act_cfg=dict(type='Sigmoid')))
+            conv_r.append(ConvModule(h_channels + x_channels, h_channels, k, padding=p, act_cfg=dict(type='Sigmoid')))
+            conv_q.append(ConvModule(h_channels + x_channels, h_channels, k, padding=p, act_cfg=dict(type='Tanh')))
+        self.conv_z = nn.ModuleList(conv_z)
+        self.conv_r = nn.ModuleList(conv_r)
+        self.conv_q = nn.ModuleList(conv_q)
+        self._zr = [PackedCache() for _ in kernel_size]
+
+    def init_weights(self) -> None:
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.orthogonal_(m.weight)
+
+    def forward(self, h: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        ch, cx = self.h_channels, self.x_channels
+        hh = ops.nchw_to_nhwc(h.contiguous())
+        xh = ops.nchw_to_nhwc(x.contiguous())
+        for i, (cz, cr, cq) in enumerate(zip(self.conv_z, self.conv_r, self.conv_q)):
+            wz, wr = cz.conv.weight, cr.conv.weight
+            zr_w = self._zr[i].get([wz, wr, cz.conv.bias, cr.conv.bias], lambda: (
+                ops.pack_conv_weight([wz.detach(), wr.detach()]), torch.cat([cz.conv.bias.detach(), cr.conv.bias.detach()])))
+            z = torch.empty_like(hh)
+            rh = torch.empty_like(hh)
+            ops.conv2d_nhwc([(hh, 0, ch), (xh, 0, cx)], zr_w[0], zr_w[1], 2 * ch, cz.kernel_size, 1, cz.padding, act='sigmoid',
+                            out=z, epi=_lib.EPI_GRU_ZR, aux0=hh, out2=rh)
+            hn = torch.empty_like(hh)
+            ops.conv2d_nhwc([(rh, 0, ch), (xh, 0, cx)], cq.packed_weight(), cq.conv.bias.detach(), ch, cq.kernel_size, 1,
+                            cq.padding, act='tanh', out=hn, epi=_lib.EPI_GRU_Q, aux0=hh, aux1=z)
+            hh = hn
+        return ops.nhwc_to_nchw(hh)
+
+
+class XHead(BaseModule):
+    """Flow / mask prediction head (raft_decoder.py:256-294)."""
+
+    def __init__(self, in_channels: int, feat_channels: Sequence[int], x_channels: int, x: str) -> None:
+        super().__init__()
+        layers = []
+        for ch in feat_channels:
+            layers.append(ConvModule(in_channels, ch, 3, padding=1))
+            in_channels = ch
+        self.layers = nn.Sequential(*layers)
+        if x in ('flow', 'tradeoff'):
+            self.predict_layer = nn.Conv2d(feat_channels[-1], x_channels, kernel_size=3, padding=1)
+        elif x == 'mask':
+            self.predict_layer = nn.Conv2d(feat_channels[-1], x_channels, kernel_size=1, padding=0)
+        else:
+            raise ValueError(f'x must be \'flow\' or \'mask\', but got {x}')
+        self._pred = PackedCache()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        y = ops.nchw_to_nhwc(x.contiguous())
+        for layer in self.layers:
+            y = layer.forward_nhwc([(y, 0, layer.in_channels)])
+        p = self.predict_layer
+        w = self._pred.get([p.weight], lambda: ops.pack_conv_weight([p.weight.detach()]))
+        out = ops.conv2d_nhwc([(y, 0, y.shape[-1])], w, p.bias.detach(), p.out_channels, p.kernel_size, 1, p.padding)
+        return ops.nhwc_to_nchw(out)
+
+
+@DECODERS.register_module()
+class SCFlowDecoder(BaseModule):
+    """Drop-in for the reference's ``SCFlowDecoder`` (scflow_decoder.py:18-251): same constructor kwargs, same
+    parameter names, same call signature, same 7-list return value.
+
+    Extra (non-reference) attributes:
+        precision: ops.PRECISION_FP32 (exact fp32 CUDA-core convolutions) or ops.PRECISION_BF16X3 (tcgen05).
+        use_cuda_graph: replay the captured loop for repeated calls with identical shapes (inference only).
+    """
+    _h_channels = {'Basic': 128, 'Small': 96}
+    _cxt_channels = {'Basic': 128, 'Small': 64}
+
+    def __init__(self, net_type: str, num_levels: int, radius: int, iters: int, detach_flow: bool, detach_mask: bool,
+                 detach_pose: bool, mask_flow: bool, mask_corr: bool, pose_head_cfg: dict, depth_transform: str = 'exp',
+                 detach_depth_for_xy: bool = False, corr_lookup_cfg: dict = dict(align_corners=True),
+                 gru_type: str = 'SeqConv', feat_channels: Union[int, Sequence[int]] = 256,
+                 conv_cfg: Optional[dict] = None, norm_cfg: Optional[dict] = None, act_cfg: Optional[dict] = None,
+                 precision: int = ops.PRECISION_FP32, use_cuda_graph: bool = False) -> None:
+        super().__init__()
+        assert net_type in ['Basic', 'Small']
+        assert type(feat_channels) in (int, tuple, list)
+        if net_type != 'Basic' or gru_type != 'SeqConv':
+            raise NotImplementedError('scflow_b200 implements the shipped configuration: net_type="Basic", gru_type="SeqConv"')
+        if depth_transform != 'exp':
+            raise NotImplementedError('only depth_transform="exp" is implemented')
+        if act_cfg is None or act_cfg.get('type') != 'ReLU' or norm_cfg is not None:
+            raise NotImplementedError('the fused loop implements the shipped act_cfg=dict(type="ReLU"), norm_cfg=None')
+        self.corr_block = CorrelationPyramid(num_levels=num_levels, precision=precision)
+        # the reference's `isinstance(tuple, list)` bug makes feat_channels always [feat_channels] (scflow_decoder.py:73-74)
+        feat_channels = [feat_channels]
+        if feat_channels != [256]:
+            raise NotImplementedError('feat_channels must be 256 (the only value the reference can produce)')
+        self.net_type, self.num_levels, self.radius = net_type, num_levels, radius
+        self.detach_flow, self.detach_mask, self.detach_pose = detach_flow, detach_mask, detach_pose
+        self.detach_depth_for_xy = detach_depth_for_xy
+        self.mask_flow, self.mask_corr = mask_flow, mask_corr
+        self.depth_transform = depth_transform
+        self.h_channels = self._h_channels[net_type]
+        self.cxt_channels = self._cxt_channels[net_type]
+        self.iters = iters
+        corr_lookup_cfg = dict(corr_lookup_cfg)
+        corr_lookup_cfg['radius'] = radius
+        self.corr_lookup = CorrLookup(**corr_lookup_cfg)
+        self.encoder = MotionEncoder(num_levels=num_levels, radius=radius, net_type=net_type, conv_cfg=conv_cfg,
+                                     norm_cfg=norm_cfg, act_cfg=act_cfg)
+        self.gru_type = gru_type
+        self.gru = ConvGRU(self.h_channels, self.encoder.out_channels[0] + 2 + self.cxt_channels, net_type=gru_type)
+        self.pose_pred = build_head(pose_head_cfg)
+        self.flow_pred = XHead(self.h_channels, feat_channels, 2, x='flow')
+        self.mask_pred = XHead(self.h_channels, feat_channels, 1, x='mask')
+        self.delta_flow_encoder = nn.Sequential(*MotionEncoder._make_encoder(2, [128, 64], [7, 3], [3, 1], conv_cfg, norm_cfg, act_cfg))
+        self.mask_encoder = nn.Sequential(*MotionEncoder._make_encoder(1, [64, 32], [3, 3], [1, 1], conv_cfg, norm_cfg, act_cfg))
+        self.precision = precision
+        self.use_cuda_graph = use_cuda_graph
+        self.identity_pose_head = False   # config-3 mode: skip the regressor (it cannot run off 256x256)
+        self._arena = PackedCache()
+        self._workspaces = {}
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ C-ABI plumbing
+    def _cfg(self) -> _lib.DecoderCfg:
+        head = self.pose_pred
+        num_class = getattr(head, 'num_class', None)
+        return _lib.DecoderCfg(self.num_levels, self.radius, num_class if num_class else 0, head.rotation_out_channels,
+                               int(self.mask_flow), int(self.mask_corr), 0 if self.identity_pose_head else 1,
+                               int(self.precision))
+
+    def _packed_arena(self, cfg) -> torch.Tensor:
+        sd = {k: v for k, v in self.named_parameters()}
+        params = [sd[k] for k in _lib.DECODER_WEIGHT_KEYS]
+
+        def make():
+            lib = _lib.load()
+            dev = params[0].device
+            arena = torch.empty(lib.scf_decoder_packed_bytes(C.byref(cfg)), device=dev, dtype=torch.uint8)
+            srcs = [p.detach().contiguous().float() for p in params]
+            arr = (C.c_void_p * _lib.SCF_W_COUNT)(*[t.data_ptr() for t in srcs])
+            _lib.check(lib.scf_decoder_pack(C.byref(cfg), arr, _lib.ptr(arena), _lib.stream_ptr()), 'scf_decoder_pack')
+            return (arena, int(cfg.pose_head), int(cfg.precision))
+
+        arena, ph, prec = self._arena.get(params, make)
+        if ph != int(cfg.pose_head) or prec != int(cfg.precision):
+            self._arena = PackedCache()
+            arena, _, _ = self._arena.get(params, make)
+        return arena
+
+    def _workspace(self, cfg, b, h, w, device) -> torch.Tensor:
+        key = (b, h, w, int(cfg.precision), str(device))
+        ws = self._workspaces.get(key)
+        if ws is None:
+            nbytes = _lib.load().scf_decoder_workspace_bytes(C.byref(cfg), b, h, w)
+            if nbytes == 0:
+                raise _lib.ScfError('scf_decoder_workspace_bytes rejected the configuration')
+            self._workspaces = {key: torch.empty(nbytes, device=device, dtype=torch.uint8)}   # keep only the latest shape
+            ws = self._workspaces[key]
+        return ws
+
+    def _run(self, cfg, arena, ws, ins, outs, b, h, w, iters, invalid):
+        io = _lib.DecoderIO()
+        for k in ('feat_render', 'feat_real', 'h_feat', 'cxt_feat', 'ref_rotation', 'ref_translation', 'depth', 'internel_k',
+                  'label', 'init_flow'):
+            setattr(io, k, ins[k].data_ptr())
+        io.invalid_flow_num = float(invalid)
+        for k in ('flow_from_pose', 'flow_from_pred', 'rotation', 'translation', 'mask', 'delta_rotation', 'delta_translation'):
+            setattr(io, k, outs[k].data_ptr())
+        io.h_out = None
+        _lib.check(_lib.load().scf_decoder_forward(C.byref(cfg), _lib.ptr(arena), C.byref(io), b, h, w, iters, _lib.ptr(ws),
+                                                   ws.numel(), _lib.stream_ptr()), 'scf_decoder_forward')
+
+    @staticmethod
+    def _alloc_outputs(iters, b, h, w, rot_dim, device):
+        f32 = dict(device=device, dtype=torch.float32)
+        return dict(flow_from_pose=torch.empty(iters, b, 2, h, w, **f32), flow_from_pred=torch.empty(iters, b, 2, h, w, **f32),
+                    rotation=torch.empty(iters, b, 3, 3, **f32), translation=torch.empty(iters, b, 3, **f32),
+                    mask=torch.empty(iters, b, 1, h, w, **f32), delta_rotation=torch.empty(iters, b, rot_dim, **f32),
+                    delta_translation=torch.empty(iters, b, 3, **f32))
+
+    def forward(self, feat_render: torch.Tensor, feat_real: torch.Tensor, h_feat: torch.Tensor, cxt_feat: torch.Tensor,
+                ref_rotation: torch.Tensor, ref_translation: torch.Tensor, depth: torch.Tensor, internel_k: torch.Tensor,
+                label: torch.Tensor, init_flow: torch.Tensor, invalid_flow_num: float):
+        """Same contract as scflow_decoder.py:150-251. Returns (flow_from_pose, flow_from_pred, rotation_preds,
+        translation_preds, mask_preds, delta_rotation_preds, delta_translation_preds), each a list of ``iters`` tensors."""
+        if torch.is_grad_enabled() and (feat_render.requires_grad or any(p.requires_grad for p in self.parameters())):
+            if feat_render.requires_grad or self.training:
+                raise NotImplementedError('scflow_b200.SCFlowDecoder: backward is not implemented yet; call under '
+                                          'torch.no_grad() / model.eval() (inference path)')
+        ins = dict(feat_render=feat_render, feat_real=feat_real, h_feat=h_feat, cxt_feat=cxt_feat, ref_rotation=ref_rotation,
+                   ref_translation=ref_translation, depth=depth, internel_k=internel_k, init_flow=init_flow)
+        for k, t in ins.items():
+            if not t.is_cuda:
+                raise RuntimeError(f'SCFlowDecoder: {k} must be a CUDA tensor (scflow_b200 has no CPU path)')
+            ins[k] = t.detach().contiguous().float()
+        if label is None:
+            label = torch.zeros(depth.shape[0], dtype=torch.int64, device=depth.device)
+        ins['label'] = label.detach().to(torch.int64).contiguous()
+        b, h, w = depth.shape
+        h8, w8 = h // 2 ** (self.num_levels - 1), w // 2 ** (self.num_levels - 1)
+        if tuple(feat_render.shape) != (b, 256, h8, w8) or feat_real.shape != feat_render.shape:
+            raise ValueError(f'feature maps must be [{b},256,{h8},{w8}], got {tuple(feat_render.shape)} / {tuple(feat_real.shape)}')
+        if tuple(h_feat.shape) != (b, self.h_channels, h8, w8) or tuple(cxt_feat.shape) != (b, self.cxt_channels, h8, w8):
+            raise ValueError('h_feat / cxt_feat have the wrong shape')
+        if tuple(init_flow.shape) != (b, 2, h, w):
+            raise ValueError(f'init_flow must be [{b},2,{h},{w}]')
+        iters = int(self.iters)
+        cfg = self._cfg()
+        dev = depth.device
+        arena = self._packed_arena(cfg)
+        ws = self._workspace(cfg, b, h, w, dev)
+        rot_dim = cfg.rot_dim
+        if self.use_cuda_graph:
+            outs = self._forward_graph(cfg, arena, ws, ins, b, h, w, iters, invalid_flow_num, rot_dim, dev)
+        else:
+            outs = self._alloc_outputs(iters, b, h, w, rot_dim, dev)
+            self._run(cfg, arena, ws, ins, outs, b, h, w, iters, invalid_flow_num)
+        order = ('flow_from_pose', 'flow_from_pred', 'rotation', 'translation', 'mask', 'delta_rotation', 'delta_translation')
+        return tuple([outs[k][i] for i in range(iters)] for k in order)
+
+    def _forward_graph(self, cfg, arena, ws, ins, b, h, w, iters, invalid, rot_dim, dev):
+        key = (b, h, w, iters, float(invalid), int(cfg.precision), int(cfg.pose_head), arena.data_ptr(), ws.data_ptr())
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = {k: torch.empty_like(v) for k, v in ins.items()}
+            for k, v in ins.items():
+                static_in[k].copy_(v)
+            static_out = self._alloc_outputs(iters, b, h, w, rot_dim, dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):          # warm-up outside capture (lazy module loading, func attributes)
+                self._run(cfg, arena, ws, static_in, static_out, b, h, w, iters, invalid)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._run(cfg, arena, ws, static_in, static_out, b, h, w, iters, invalid)
+            self._graphs = {key: (graph, static_in, static_out)}
+            entry = self._graphs[key]
+        graph, static_in, static_out = entry
+        for k, v in ins.items():
+            static_in[k].copy_(v, non_blocking=True)
+        graph.replay()
+        return static_out   # NOTE: overwritten by the next call with the same shapes (documented in INTEGRATION.md)

@@ -1,0 +1,226 @@
+"""Tensor-level wrappers over the C ABI (one function per exported kernel family).
+
+All functions require contiguous fp32 CUDA tensors and launch on torch's current stream. They never fall back
+to PyTorch arithmetic: bad devices/dtypes raise, library errors raise ``ScfError``.
+"""
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, ConvSeg, check, ptr, stream_ptr
+
+PRECISION_FP32 = 0       # exact-fp32 CUDA-core convolutions / build
+PRECISION_BF16X3 = 1     # tcgen05 split-bf16 (3 MMAs, fp32 accumulate in TMEM)
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f'{name} must be a torch.Tensor')
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must live on a CUDA device: scflow_b200 has no CPU path')
+    if t.dtype != dtype:
+        raise TypeError(f'{name} must be {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError(f'{name} must be contiguous')
+    return t
+
+
+def nchw_to_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None, coff: int = 0) -> torch.Tensor:
+    _req(x, 'x')
+    b, c, h, w = x.shape
+    if out is None:
+        out = torch.empty(b, h, w, c, device=x.device, dtype=torch.float32)
+    check(_lib.load().scf_nchw_to_nhwc(ptr(x), ptr(out), b, c, h, w, out.shape[-1], coff, stream_ptr()), 'scf_nchw_to_nhwc')
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, channels: Optional[int] = None, coff: int = 0) -> torch.Tensor:
+    _req(x, 'x')
+    b, h, w, stride = x.shape
+    c = channels if channels is not None else stride - coff
+    out = torch.empty(b, c, h, w, device=x.device, dtype=torch.float32)
+    check(_lib.load().scf_nhwc_to_nchw(ptr(x), stride, coff, ptr(out), b, c, h, w, stream_ptr()), 'scf_nhwc_to_nchw')
+    return out
+
+
+def pack_conv_weight(weights: Sequence[torch.Tensor]) -> torch.Tensor:
+    """OIHW conv weights (one or several convs with identical I,kh,kw, concatenated along O) -> packed [K][ldw]."""
+    o_total = sum(int(w.shape[0]) for w in weights)
+    _, i, kh, kw = weights[0].shape
+    ldw = (o_total + 3) // 4 * 4
+    packed = torch.zeros(kh * kw * i, ldw, device=weights[0].device, dtype=torch.float32)
+    off = 0
+    for w in weights:
+        _req(w, 'weight')
+        assert tuple(w.shape[1:]) == (i, kh, kw)
+        check(_lib.load().scf_pack_conv_weight(ptr(w), ptr(packed), w.shape[0], i, kh, kw, ldw, off, stream_ptr()),
+              'scf_pack_conv_weight')
+        off += int(w.shape[0])
+    return packed
+
+
+def conv2d_nhwc(segs: Sequence, packed_w: torch.Tensor, bias: Optional[torch.Tensor], cout: int, kernel, stride=1,
+                padding=None, act: str = 'none', out: Optional[torch.Tensor] = None, out_coff: int = 0,
+                epi: int = _lib.EPI_ACT, aux0=None, aux1=None, out2=None, scale: float = 1.0,
+                w_batch_stride: int = 0) -> torch.Tensor:
+    """Generic convolution on NHWC buffers. ``segs`` = [(tensor[B,H,W,stride], coff, nch), ...] concatenated on C."""
+    kh, kw = (kernel, kernel) if isinstance(kernel, int) else kernel
+    ph, pw = (kh // 2, kw // 2) if padding is None else ((padding, padding) if isinstance(padding, int) else padding)
+    sh, sw = (stride, stride) if isinstance(stride, int) else stride
+    t0 = segs[0][0]
+    b, hi, wi, _ = t0.shape
+    ho = (hi + 2 * ph - kh) // sh + 1
+    wo = (wi + 2 * pw - kw) // sw + 1
+    if out is None:
+        out = torch.empty(b, ho, wo, cout if epi != _lib.EPI_GRU_ZR else cout // 2, device=t0.device, dtype=torch.float32)
+    d = ConvDesc()
+    for n, (t, coff, nch) in enumerate(segs):
+        _req(t, f'seg{n}')
+        d.seg[n] = ConvSeg(t.data_ptr(), t.shape[-1], coff, nch)
+    d.nseg = len(segs)
+    d.B, d.Hi, d.Wi, d.Ho, d.Wo = b, hi, wi, ho, wo
+    d.kh, d.kw, d.sh, d.sw, d.ph, d.pw = kh, kw, sh, sw, ph, pw
+    d.w = packed_w.data_ptr()
+    d.w_batch_stride = w_batch_stride
+    d.ldw = packed_w.shape[-1]
+    d.cout = cout
+    d.bias = None if bias is None else bias.data_ptr()
+    d.scale = scale
+    d.epi, d.act = epi, _lib.ACT[act]
+    d.out, d.out_stride, d.out_coff = out.data_ptr(), out.shape[-1], out_coff
+    if aux0 is not None:
+        d.aux0, d.aux0_stride = aux0.data_ptr(), aux0.shape[-1]
+    if aux1 is not None:
+        d.aux1, d.aux1_stride = aux1.data_ptr(), aux1.shape[-1]
+    if out2 is not None:
+        d.out2, d.out2_stride = out2.data_ptr(), out2.shape[-1]
+    check(_lib.load().scf_conv2d(C.byref(d), stream_ptr()), 'scf_conv2d')
+    return out
+
+
+def level_shapes(h8: int, w8: int, num_levels: int):
+    shapes = []
+    for _ in range(num_levels):
+        shapes.append((h8, w8))
+        h8, w8 = h8 // 2, w8 // 2
+    return shapes
+
+
+def corr_build(feat_render: torch.Tensor, feat_real: torch.Tensor, num_levels: int = 4,
+               precision: int = PRECISION_FP32) -> List[torch.Tensor]:
+    """CorrelationPyramid.forward: returns the reference's list of [B*P, 1, Hl, Wl] tensors."""
+    _req(feat_render, 'feat_render')
+    _req(feat_real, 'feat_real')
+    if feat_render.shape != feat_real.shape:
+        raise ValueError('feature maps must have the same shape')
+    b, c, h8, w8 = feat_render.shape
+    lib = _lib.load()
+    levels = [torch.empty(b * h8 * w8, 1, hl, wl, device=feat_render.device, dtype=torch.float32)
+              for hl, wl in level_shapes(h8, w8, num_levels)]
+    scratch = torch.empty(lib.scf_corr_build_scratch_bytes(b, c, h8, w8), device=feat_render.device, dtype=torch.uint8)
+    arr = (C.c_void_p * num_levels)(*[t.data_ptr() for t in levels])
+    check(lib.scf_corr_build(ptr(feat_render), ptr(feat_real), b, c, h8, w8, num_levels, arr, ptr(scratch), precision,
+                             stream_ptr()), 'scf_corr_build')
+    return levels
+
+
+def corr_lookup_nhwc(levels: Sequence[torch.Tensor], flow8_nhwc: torch.Tensor, radius: int,
+                     mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_coff: int = 0) -> torch.Tensor:
+    _req(flow8_nhwc, 'flow8')
+    b, h8, w8, two = flow8_nhwc.shape
+    assert two == 2
+    n = len(levels)
+    ch = n * (2 * radius + 1) ** 2
+    for l, (t, (hl, wl)) in enumerate(zip(levels, level_shapes(h8, w8, n))):
+        _req(t, f'level{l}')
+        if t.numel() != b * h8 * w8 * hl * wl:
+            raise ValueError(f'pyramid level {l} has {t.numel()} elements, expected {b * h8 * w8 * hl * wl}')
+    if out is None:
+        out = torch.empty(b, h8, w8, (ch + 3) // 4 * 4, device=flow8_nhwc.device, dtype=torch.float32)
+    arr = (C.c_void_p * n)(*[t.data_ptr() for t in levels])
+    check(_lib.load().scf_corr_lookup(arr, n, radius, ptr(flow8_nhwc), ptr(mask), ptr(out), out.shape[-1], out_coff, b, h8, w8,
+                                      stream_ptr()), 'scf_corr_lookup')
+    return out
+
+
+def corr_lookup_taps(flow8_nhwc: torch.Tensor, level: int, radius: int):
+    _req(flow8_nhwc, 'flow8')
+    b, h8, w8, _ = flow8_nhwc.shape
+    k = 2 * radius + 1
+    x0 = torch.empty(b, h8, w8, k, device=flow8_nhwc.device, dtype=torch.int32)
+    y0 = torch.empty_like(x0)
+    check(_lib.load().scf_corr_lookup_taps(level, radius, ptr(flow8_nhwc), ptr(x0), ptr(y0), b, h8, w8, stream_ptr()),
+          'scf_corr_lookup_taps')
+    return x0, y0
+
+
+def group_norm_relu_(x_nhwc: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, num_groups: int, eps: float = 1e-5):
+    _req(x_nhwc, 'x')
+    b, h, w, c = x_nhwc.shape
+    check(_lib.load().scf_group_norm_relu(ptr(x_nhwc), ptr(_req(gamma, 'gamma')), ptr(_req(beta, 'beta')), b, h * w, c,
+                                          num_groups, eps, stream_ptr()), 'scf_group_norm_relu')
+    return x_nhwc
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: str = 'none') -> torch.Tensor:
+    _req(x, 'x')
+    _req(w, 'w')
+    bsz, i = x.shape
+    o = w.shape[0]
+    y = torch.empty(bsz, o, device=x.device, dtype=torch.float32)
+    check(_lib.load().scf_linear(ptr(x), ptr(w), ptr(bias), ptr(y), bsz, i, o, _lib.ACT[act], stream_ptr()), 'scf_linear')
+    return y
+
+
+def pose_project(x, rot_w, rot_b, tr_w, tr_b, label, rot_dim: int, num_class: int):
+    _req(x, 'x')
+    bsz, i = x.shape
+    d_rot = torch.empty(bsz, rot_dim, device=x.device, dtype=torch.float32)
+    d_trs = torch.empty(bsz, 3, device=x.device, dtype=torch.float32)
+    if num_class > 0:
+        _req(label, 'label', torch.int64)
+    check(_lib.load().scf_pose_project(ptr(x), ptr(rot_w), ptr(rot_b), ptr(tr_w), ptr(tr_b), ptr(label), ptr(d_rot), ptr(d_trs),
+                                       bsz, i, rot_dim, num_class, stream_ptr()), 'scf_pose_project')
+    return d_rot, d_trs
+
+
+def pose_update(d_rot, d_trs, rot, trs):
+    for n, t in (('d_rot', d_rot), ('d_trs', d_trs), ('rot', rot), ('trs', trs)):
+        _req(t, n)
+    b = rot.shape[0]
+    rot_out, trs_out = torch.empty_like(rot), torch.empty_like(trs)
+    check(_lib.load().scf_pose_update(ptr(d_rot), ptr(d_trs), ptr(rot), ptr(trs), ptr(rot_out), ptr(trs_out), b, stream_ptr()),
+          'scf_pose_update')
+    return rot_out, trs_out
+
+
+def unproject(depth, k, rot, trs):
+    for n, t in (('depth', depth), ('k', k), ('rot', rot), ('trs', trs)):
+        _req(t, n)
+    b, h, w = depth.shape
+    pts4 = torch.empty(b, h, w, 4, device=depth.device, dtype=torch.float32)
+    check(_lib.load().scf_unproject(ptr(depth), ptr(k), ptr(rot), ptr(trs), ptr(pts4), b, h, w, stream_ptr()), 'scf_unproject')
+    return pts4
+
+
+def reproject(pts4, k, rot, trs, invalid: float = 0.0):
+    for n, t in (('pts4', pts4), ('k', k), ('rot', rot), ('trs', trs)):
+        _req(t, n)
+    b, h, w, _ = pts4.shape
+    flow = torch.empty(b, 2, h, w, device=pts4.device, dtype=torch.float32)
+    check(_lib.load().scf_reproject(ptr(pts4), ptr(k), ptr(rot), ptr(trs), float(invalid), ptr(flow), b, h, w, stream_ptr()),
+          'scf_reproject')
+    return flow
+
+
+def resize_bilinear_nchw(x: torch.Tensor, out_h: int, out_w: int, scale: float = 1.0, add: Optional[torch.Tensor] = None):
+    """F.interpolate(mode='bilinear', align_corners=True) on NCHW, times ``scale``."""
+    _req(x, 'x')
+    b, c, h, w = x.shape
+    out = torch.empty(b, c, out_h, out_w, device=x.device, dtype=torch.float32)
+    check(_lib.load().scf_resize_bilinear(ptr(x), ptr(add), c * h * w, h * w, w, 1, h, w, ptr(out), c * out_h * out_w,
+                                          out_h * out_w, out_w, 1, out_h, out_w, b, c, scale, stream_ptr()),
+          'scf_resize_bilinear')
+    return out

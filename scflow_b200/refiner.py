@@ -1,0 +1,118 @@
+"""SCFlowRefiner registered under the reference's name (models/refiner/scflow_refiner.py, base_refiner.py).
+
+Scope: ``extract_feat``, ``get_pose`` and ``forward_single_pass`` - the iteration owner
+of the hot path.  The renderer (pytorch3d), the losses and the OpenCV pose re-mapping are outside the replaced
+path; the refiner accepts their config keys so the reference's config dicts build unchanged, takes an injected
+``renderer`` callable, and raises a clear error where an out-of-scope component would be needed.
+"""
+from typing import Callable, Dict, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from .builder import REFINERS, build_decoder, build_encoder
+from .cnn import BaseModule
+
+
+@REFINERS.register_module()
+class SCFlowRefiner(BaseModule):
+    def __init__(self, seperate_encoder: bool, cxt_channels: int, h_channels: int, cxt_encoder: dict, encoder: dict,
+                 decoder: dict, renderer: Optional[Union[dict, Callable]] = None, pose_loss_cfg: Optional[dict] = None,
+                 flow_loss_cfg: Optional[dict] = None, mask_loss_cfg: Optional[dict] = None, max_flow: float = 400,
+                 render_augmentations: list = None, filter_invalid_flow: bool = True, freeze_encoder: bool = False,
+                 freeze_bn: bool = False, train_cfg: Optional[dict] = None, test_cfg: Optional[dict] = None,
+                 init_cfg: Optional[Union[list, dict]] = None) -> None:
+        super().__init__(init_cfg)
+        self.seperate_encoder = seperate_encoder
+        if seperate_encoder:
+            self.render_encoder = build_encoder(encoder)
+            self.real_encoder = build_encoder(encoder)
+        else:   # one module under two names, as base_refiner.py:37-39 (state dict carries both prefixes)
+            enc = build_encoder(encoder)
+            self.render_encoder = enc
+            self.real_encoder = enc
+        self.decoder = build_decoder(decoder)
+        self.context = build_encoder(cxt_encoder)
+        self.renderer = renderer if callable(renderer) else None
+        self.renderer_cfg = renderer if isinstance(renderer, dict) else None
+        self.h_channels, self.cxt_channels = h_channels, cxt_channels
+        assert self.h_channels == self.decoder.h_channels
+        assert self.cxt_channels == self.decoder.cxt_channels
+        assert self.h_channels + self.cxt_channels == self.context.out_channels
+        self.max_flow = max_flow
+        self.train_cfg = train_cfg or {}
+        self.test_cfg = test_cfg or {}
+        self.loss_cfgs = dict(pose=pose_loss_cfg, flow=flow_loss_cfg, mask=mask_loss_cfg)
+        self.filter_invalid_flow = filter_invalid_flow
+        self.test_by_flow = self.test_cfg.get('by_flow', False)
+        self.test_iter_num = self.test_cfg.get('iters') if 'iters' in self.test_cfg else self.decoder.iters
+        if freeze_bn:
+            self.freeze_bn()
+        if freeze_encoder:
+            self.freeze_encoder()
+
+    def freeze_encoder(self):
+        for enc in (self.real_encoder, self.render_encoder):
+            for m in enc.modules():
+                m.eval()
+                for p in m.parameters(recurse=False):
+                    p.requires_grad = False
+
+    def freeze_bn(self) -> None:
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+
+    def extract_feat(self, render_images, real_images) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        """scflow_refiner.py:88-110."""
+        real_feat = self.real_encoder(real_images)
+        render_feat = self.render_encoder(render_images)
+        cxt_feat = self.context(render_images)
+        h_feat, cxt_feat = torch.split(cxt_feat, [self.h_channels, self.cxt_channels], dim=1)
+        return render_feat, real_feat, torch.tanh(h_feat), torch.relu(cxt_feat)
+
+    def get_pose(self, render_images, real_images, ref_rotation, ref_translation, depth, internel_k, label,
+                 init_flow=None):
+        """scflow_refiner.py:112-142: encoders -> decoder loop; returns the decoder's 7 lists."""
+        feat_render, feat_real, h_feat, cxt_feat = self.extract_feat(render_images, real_images)
+        if init_flow is None:
+            n, _, h, w = real_images.shape
+            init_flow = feat_render.new_zeros((n, 2, h, w), dtype=torch.float32)
+        return self.decoder(feat_render, feat_real, h_feat, cxt_feat, ref_rotation, ref_translation, depth, internel_k,
+                            init_flow=init_flow, label=label, invalid_flow_num=0.)
+
+    def forward_single_pass(self, data: Dict, data_batch: Optional[Dict] = None, return_loss: bool = False):
+        """scflow_refiner.py:146-179 without the OpenCV re-mapping to the original image resolution
+        (remap_pose_to_origin_resoluaion is host-side cv2.solvePnP, out of scope): poses are returned in the crop frame."""
+        labels = data['labels']
+        per_img_patch_num = data.get('per_img_patch_num', [len(labels)])
+        iters = self.decoder.iters
+        self.decoder.iters = self.test_iter_num
+        try:
+            outs = self.get_pose(data['rendered_images'], data['real_images'], data['ref_rotations'], data['ref_translations'],
+                                 data['rendered_depths'], data['internel_k'], labels)
+        finally:
+            self.decoder.iters = iters
+        seq_rotations, seq_translations = outs[2], outs[3]
+        return dict(
+            rotations=torch.split(seq_rotations[-1], per_img_patch_num),
+            translations=torch.split(seq_translations[-1], per_img_patch_num),
+            labels=torch.split(labels, per_img_patch_num),
+            scores=torch.split(torch.ones_like(labels, dtype=torch.float32), per_img_patch_num),
+        )
+
+    def forward(self, data_batch, return_loss=False):
+        """base_refiner.py:338-343. Needs an injected ``renderer`` callable producing rendered images/depths for the
+        reference poses; the pytorch3d rasteriser itself is not part of this package."""
+        if 'rendered_images' in data_batch:       # already formatted (bench / tests / external renderer)
+            return self.forward_single_pass(data_batch)
+        if self.renderer is None:
+            raise NotImplementedError('SCFlowRefiner.forward(data_batch) needs a renderer: assign a callable to '
+                                      '`model.renderer` or pass a pre-formatted dict with `rendered_images` / `rendered_depths`.')
+        raise NotImplementedError('dataset-format batches (mmcv DataContainer collation) are outside the replaced hot path')
+
+    def train_step(self, data_batch, optimizer, **kwargs):
+        raise NotImplementedError('training (loss + backward) is not implemented in this round; see DESIGN.md "what comes next"')
+
+    def loss(self, data_batch):
+        raise NotImplementedError('training (loss + backward) is not implemented in this round; see DESIGN.md "what comes next"')

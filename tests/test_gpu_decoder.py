@@ -1,0 +1,167 @@
+"""GPU: the whole decoder loop / refiner against the golden fixtures (generated from the reference itself), the
+live oracle, and size-independent properties at BASELINE config-2 size (B=32, 8 iterations)."""
+import pytest
+import torch
+
+from oracle import scflow_oracle as O
+from tests.util import (assert_matches_digest, build_decoder_from_oracle_weights, load_golden, scflow_model_cfg)
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ['flow_from_pose', 'flow_from_pred', 'rotation', 'translation', 'mask', 'delta_rotation', 'delta_translation']
+# tolerances vs the fp32 CPU reference (px, px, -, mm, -, -, -). North star: flow EPE within 1e-3.
+TOL_FP32 = dict(flow_from_pose=3e-3, flow_from_pred=1e-3, rotation=2e-6, translation=3e-3, mask=2e-5, delta_rotation=5e-6,
+                delta_translation=5e-6)
+
+
+def _inputs(seed, b, h, w):
+    scene = O.make_scene(seed, b, h, w)
+    f = O.make_features(seed, b, h // 8, w // 8)
+    return scene, f
+
+
+def _call(dec, scene, f, b, h, w):
+    c = lambda t: t.cuda()
+    with torch.no_grad():
+        return dec(c(f['feat_render']), c(f['feat_real']), c(f['h_feat']), c(f['cxt_feat']), c(scene['ref_rotation']),
+                   c(scene['ref_translation']), c(scene['depth']), c(scene['internel_k']), label=c(scene['label']),
+                   init_flow=torch.zeros(b, 2, h, w, device='cuda'), invalid_flow_num=0.)
+
+
+def _epe(a, b):
+    return float((a - b).pow(2).sum(1).sqrt().mean())
+
+
+@pytest.mark.parametrize('name', ['decoder_256_b2_it4', 'decoder_256_b3_it8'])
+def test_decoder_matches_reference_golden(name):
+    g = load_golden(name)
+    seed, b, h, w, iters = (int(g['meta/' + k]) for k in ('seed', 'batch', 'h', 'w', 'iters'))
+    dec, _ = build_decoder_from_oracle_weights(seed, iters)
+    scene, f = _inputs(seed, b, h, w)
+    outs = _call(dec, scene, f, b, h, w)
+    assert len(outs) == 7 and all(len(o) == iters for o in outs)
+    for nm, lst in zip(NAMES, outs):
+        for i, t in enumerate(lst):
+            assert_matches_digest(g, f'{nm}/{i}', t, atol=TOL_FP32[nm])
+
+
+def test_decoder_480x640_identity_head_golden():
+    g = load_golden('decoder_480x640_b1_it2')
+    seed, b, h, w, iters = (int(g['meta/' + k]) for k in ('seed', 'batch', 'h', 'w', 'iters'))
+    dec, _ = build_decoder_from_oracle_weights(seed, iters)
+    dec.identity_pose_head = True
+    scene, f = _inputs(seed, b, h, w)
+    outs = _call(dec, scene, f, b, h, w)
+    for nm, lst in zip(NAMES, outs):
+        for i, t in enumerate(lst):
+            assert_matches_digest(g, f'{nm}/{i}', t, atol=TOL_FP32[nm])
+    # the stock head cannot run here, exactly like the reference
+    dec.identity_pose_head = False
+    from scflow_b200 import ScfError
+    with pytest.raises(ScfError, match='32x32'):
+        _call(dec, scene, f, b, h, w)
+
+
+def test_decoder_flow_epe_vs_live_oracle():
+    """The north-star number: mean end-point error of every iteration's flows against the fp32 CPU reference path."""
+    seed, b, iters = 7, 2, 8
+    dec, sd = build_decoder_from_oracle_weights(seed, iters)
+    scene, f = _inputs(seed, b, 256, 256)
+    outs = _call(dec, scene, f, b, 256, 256)
+    with torch.no_grad():
+        ref = O.decoder_forward(sd, f['feat_render'], f['feat_real'], f['h_feat'], f['cxt_feat'], scene['ref_rotation'],
+                                scene['ref_translation'], scene['depth'], scene['internel_k'], scene['label'],
+                                torch.zeros(b, 2, 256, 256), 0., iters=iters)
+    for i in range(iters):
+        assert _epe(outs[0][i].cpu(), ref[0][i]) < 1e-3, f'pose-flow EPE at iteration {i}'
+        assert _epe(outs[1][i].cpu(), ref[1][i]) < 1e-3, f'pred-flow EPE at iteration {i}'
+        assert float((outs[2][i].cpu() - ref[2][i]).abs().max()) < 1e-5
+        assert float((outs[3][i].cpu() - ref[3][i]).abs().max()) < 5e-3       # mm
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    seed, b, iters = 9, 2, 3
+    dec, _ = build_decoder_from_oracle_weights(seed, iters)
+    scene, f = _inputs(seed, b, 256, 256)
+    eager = [[t.clone() for t in lst] for lst in _call(dec, scene, f, b, 256, 256)]
+    dec.use_cuda_graph = True
+    for _ in range(2):      # capture, then replay
+        graphed = _call(dec, scene, f, b, 256, 256)
+        for a, g_ in zip(eager, graphed):
+            for x, y in zip(a, g_):
+                assert torch.equal(x, y)
+
+
+def test_refiner_get_pose_config1_golden():
+    """BASELINE config 1: images -> encoders (stock cuDNN, fp32) -> decoder, vs the reference run on CPU."""
+    import scflow_b200 as S
+    g = load_golden('get_pose_256_b1_it4')
+    seed, b, iters = int(g['meta/seed']), int(g['meta/batch']), int(g['meta/iters'])
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False         # the oracle is fp32; keep the (unreplaced) encoders fp32 too
+    try:
+        model = S.build_refiner(scflow_model_cfg(iters=iters))
+        model.load_state_dict(O.make_model_weights(seed), strict=False)
+        model = model.cuda().eval()
+        scene = O.make_scene(seed, b)
+        c = {k: v.cuda() for k, v in scene.items()}
+        with torch.no_grad():
+            outs = model.get_pose(c['render_images'], c['real_images'], c['ref_rotation'], c['ref_translation'], c['depth'],
+                                  c['internel_k'], c['label'])
+            res = model.forward_single_pass(dict(rendered_images=c['render_images'], real_images=c['real_images'],
+                                                 ref_rotations=c['ref_rotation'], ref_translations=c['ref_translation'],
+                                                 rendered_depths=c['depth'], internel_k=c['internel_k'], labels=c['label'],
+                                                 per_img_patch_num=[b]))
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    tol = dict(TOL_FP32, flow_from_pose=2e-2, flow_from_pred=1e-2, translation=2e-2, rotation=2e-5, delta_rotation=5e-5,
+               delta_translation=5e-5, mask=2e-4)   # encoder (cuDNN vs MKL-DNN) noise feeds the loop here
+    for nm, lst in zip(NAMES, outs):
+        for i, t in enumerate(lst):
+            assert_matches_digest(g, f'{nm}/{i}', t, atol=tol[nm])
+    assert torch.equal(res['rotations'][0], outs[2][-1]) and res['scores'][0].shape == (b,)
+
+
+def test_full_size_properties_b32():
+    """BASELINE config 2 size (B=32, 8 iterations): properties that need no oracle run."""
+    seed, b, iters = 13, 32, 8
+    dec, _ = build_decoder_from_oracle_weights(seed, iters)
+    scene, f = _inputs(seed, b, 256, 256)
+    scene['label'][:] = 4
+    outs = _call(dec, scene, f, b, 256, 256)
+    again = _call(dec, scene, f, b, 256, 256)
+    for a, b_ in zip(outs, again):                                   # deterministic
+        assert all(torch.equal(x, y) for x, y in zip(a, b_))
+    for lst in outs:
+        assert all(torch.isfinite(t).all() for t in lst)
+    rot = outs[2][-1]
+    eye = torch.bmm(rot, rot.transpose(1, 2))
+    assert float((eye - torch.eye(3, device='cuda')).abs().max()) < 1e-4      # rotations stay orthonormal
+    bg = (scene['depth'] <= 0).cuda()
+    assert float(outs[0][-1][:, 0][bg].abs().max()) == 0.                     # invalid_flow_num=0 on background
+    assert 0. <= float(outs[4][-1].min()) and float(outs[4][-1].max()) <= 1.  # sigmoid mask
+    # samples are independent: a sub-batch (same label[0]) gives the same poses
+    sub = {k: (v[8:12].clone() if isinstance(v, torch.Tensor) else v) for k, v in scene.items()}
+    fsub = {k: v[8:12].clone() for k, v in f.items()}
+    o2 = _call(dec, sub, fsub, 4, 256, 256)
+    assert float((o2[2][-1] - outs[2][-1][8:12]).abs().max()) < 1e-5
+    assert float((o2[3][-1] - outs[3][-1][8:12]).abs().max()) < 1e-2
+
+
+def test_mask_options_run():
+    """mask_corr / mask_flow decoder options (off in the shipped config) against the oracle-equivalent formulas."""
+    import scflow_b200 as S
+    seed, b, iters = 5, 1, 2
+    cfg = scflow_model_cfg(iters)['decoder']
+    cfg.update(mask_corr=True, mask_flow=True)
+    dec = S.build_decoder(cfg)
+    sd = O.make_decoder_weights(seed)
+    dec.load_state_dict(sd, strict=True)
+    dec = dec.cuda().eval()
+    scene, f = _inputs(seed, b, 256, 256)
+    outs = _call(dec, scene, f, b, 256, 256)
+    assert all(torch.isfinite(t).all() for lst in outs for t in lst)
+    base, _ = build_decoder_from_oracle_weights(seed, iters)
+    ref = _call(base, scene, f, b, 256, 256)
+    assert torch.equal(outs[2][0], ref[2][0])            # first iteration: mask is all ones -> identical
+    assert not torch.equal(outs[2][1], ref[2][1])        # second iteration: the predicted mask gates corr / flow
