@@ -95,10 +95,50 @@ typedef struct scf_conv_desc {
   const float* aux0; int aux0_stride;
   const float* aux1; int aux1_stride;
   float* out2; int out2_stride;
+  /* optional split-bf16 copy of `out` (hi plane at out_hl, lo plane at out_hl + out_hl_plane elements) for
+   * consumption by the tensor-core convolutions; NULL = none */
+  void* out_hl; long long out_hl_plane; int out_hl_stride, out_hl_coff;
 } scf_conv_desc;
 
 /* fp32 CUDA-core implicit GEMM (exact fp32 accumulate); any kernel size / stride / channel count. */
 int scf_conv2d(const scf_conv_desc* d, void* stream);
+
+/* ---------------------------------------------------------------- tcgen05 convolution -------------------- */
+/* Split-bf16 ("bf16x3") tensors: a value x is stored as two bf16 planes hi = bf16(x), lo = bf16(x - hi); a product
+ * is evaluated as hi*hi + hi*lo + lo*hi on the 5th-gen tensor cores with fp32 accumulation in TMEM (error ~2^-16,
+ * i.e. fp32-class for this network; a single bf16 pass misses the 1e-3 px EPE bar by 60x - BASELINE.md §5). */
+typedef struct scf_tc_seg {
+  const void* ptr;        /* bf16 hi plane, NHWC */
+  long long plane_stride; /* elements from the hi plane to the lo plane */
+  int stride, coff, nch;  /* elements per pixel, first channel, channels taken (multiples of 8) */
+} scf_tc_seg;
+
+typedef struct scf_tc_conv_desc {
+  scf_tc_seg seg[3];
+  int nseg;
+  int B, H, W;             /* stride-1 'same' convolution: output spatial size == input */
+  int kh, kw;              /* padding = kh/2, kw/2 */
+  const void* w;           /* packed by scf_pack_conv_weight_tc: bf16 [2][taps][cout_pad][cin_pad] */
+  int cin_pad, cout_pad, cout;
+  int w_batched;           /* 1: the "tap" dimension of w indexes the sample (kh=kw=1; correlation build) */
+  const float* bias; float scale; int epi, act;
+  float* out_f32; int out_f32_stride, out_f32_coff;                     /* optional fp32 NHWC output */
+  void* out_hl; long long out_hl_plane; int out_hl_stride, out_hl_coff; /* optional split-bf16 output */
+  const float* aux0; int aux0_stride; const float* aux1; int aux1_stride;
+  void* out2_hl; long long out2_hl_plane; int out2_hl_stride;           /* GRU_ZR: r*h as split-bf16 */
+} scf_tc_conv_desc;
+
+int scf_conv2d_tc(const scf_tc_conv_desc* d, void* stream);
+/* OIHW fp32 -> split-bf16 [2][kh*kw][cout_pad][cin_pad] (zero padded; caller memsets the buffer first).
+ * Several convs can be merged along O with o_off. Bytes = 2*taps*cout_pad*cin_pad*2. */
+int scf_pack_conv_weight_tc(const float* w_oihw, void* packed, int O, int I, int kh, int kw, int cin_pad, int cout_pad,
+                            int o_off, void* stream);
+/* NCHW fp32 -> split-bf16 NHWC planes (and, if dst_f32 != NULL, an fp32 NHWC copy with dst_f32_stride). */
+int scf_nchw_to_nhwc_split(const float* src, void* dst_hl, long long plane_stride, int dst_stride, int dst_coff,
+                           float* dst_f32, int dst_f32_stride, int B, int C, int H, int W, void* stream);
+/* NHWC fp32 channels [src_coff, src_coff+nch) -> split-bf16 planes at dst_coff */
+int scf_split_copy(const float* src, int src_stride, int src_coff, void* dst_hl, long long plane_stride, int dst_stride,
+                   int dst_coff, long long npix, int nch, void* stream);
 
 /* ---------------------------------------------------------------- correlation pyramid -------------------- */
 /* feat_render / feat_real: NCHW fp32 [B,C,H8,W8]. levels[l]: fp32 [B*H8*W8, Hl*Wl] (the reference's
@@ -113,6 +153,9 @@ int scf_corr_build(const float* feat_render, const float* feat_real, int B, int 
  * mask (optional, NHWC [B,H8,W8,1]) multiplies the result (decoder option mask_corr). */
 int scf_corr_lookup(const float* const* h_levels, int num_levels, int radius, const float* flow8, const float* mask,
                     float* out, int out_stride, int out_coff, int B, int H8, int W8, void* stream);
+/* same gather, written as split-bf16 planes (channels beyond num_levels*(2r+1)^2 up to out_stride are zeroed) */
+int scf_corr_lookup_split(const float* const* h_levels, int num_levels, int radius, const float* flow8, const float* mask,
+                          void* out_hl, long long plane_stride, int out_stride, int B, int H8, int W8, void* stream);
 /* debug/parity hook: integer neighbour indices of the lookup, bit-exact against the oracle.
  * x0,y0: int32 [B,H8,W8,2r+1] per level `level` (x0 indexed by a, y0 by b). */
 int scf_corr_lookup_taps(int level, int radius, const float* flow8, int32_t* x0, int32_t* y0, int B, int H8, int W8,

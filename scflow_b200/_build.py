@@ -50,7 +50,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
             raise RuntimeError(f'nvcc failed on {src}:\n{out}')
         if verbose and out.strip():
             print(out)
-    link = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-cudart', 'static', '-o', LIB_PATH] + objs + ['-lcuda']
+    link = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-cudart', 'static', '-o', LIB_PATH] + objs
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout)

@@ -33,6 +33,24 @@ class ConvDesc(C.Structure):
         ('aux0', c_void_p), ('aux0_stride', C.c_int),
         ('aux1', c_void_p), ('aux1_stride', C.c_int),
         ('out2', c_void_p), ('out2_stride', C.c_int),
+        ('out_hl', c_void_p), ('out_hl_plane', C.c_longlong), ('out_hl_stride', C.c_int), ('out_hl_coff', C.c_int),
+    ]
+
+
+class TcSeg(C.Structure):
+    _fields_ = [('ptr', c_void_p), ('plane_stride', C.c_longlong), ('stride', C.c_int), ('coff', C.c_int), ('nch', C.c_int)]
+
+
+class TcConvDesc(C.Structure):
+    _fields_ = [
+        ('seg', TcSeg * 3), ('nseg', C.c_int),
+        ('B', C.c_int), ('H', C.c_int), ('W', C.c_int), ('kh', C.c_int), ('kw', C.c_int),
+        ('w', c_void_p), ('cin_pad', C.c_int), ('cout_pad', C.c_int), ('cout', C.c_int), ('w_batched', C.c_int),
+        ('bias', c_void_p), ('scale', C.c_float), ('epi', C.c_int), ('act', C.c_int),
+        ('out_f32', c_void_p), ('out_f32_stride', C.c_int), ('out_f32_coff', C.c_int),
+        ('out_hl', c_void_p), ('out_hl_plane', C.c_longlong), ('out_hl_stride', C.c_int), ('out_hl_coff', C.c_int),
+        ('aux0', c_void_p), ('aux0_stride', C.c_int), ('aux1', c_void_p), ('aux1_stride', C.c_int),
+        ('out2_hl', c_void_p), ('out2_hl_plane', C.c_longlong), ('out2_hl_stride', C.c_int),
     ]
 
 
@@ -92,6 +110,13 @@ _SIGNATURES = {
     'scf_nhwc_to_nchw': (C.c_int, [c_void_p, C.c_int, C.c_int, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
     'scf_pack_conv_weight': (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
     'scf_conv2d': (C.c_int, [C.POINTER(ConvDesc), c_void_p]),
+    'scf_conv2d_tc': (C.c_int, [C.POINTER(TcConvDesc), c_void_p]),
+    'scf_pack_conv_weight_tc': (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
+    'scf_nchw_to_nhwc_split': (C.c_int, [c_void_p, c_void_p, C.c_longlong, C.c_int, C.c_int, c_void_p, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, c_void_p]),
+    'scf_split_copy': (C.c_int, [c_void_p, C.c_int, C.c_int, c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_longlong, C.c_int, c_void_p]),
+    'scf_corr_lookup_split': (C.c_int, [C.POINTER(c_void_p), C.c_int, C.c_int, c_void_p, c_void_p, c_void_p, C.c_longlong, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, c_void_p]),
     'scf_corr_build_scratch_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     'scf_corr_build': (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(c_void_p),
                                  c_void_p, C.c_int, c_void_p]),

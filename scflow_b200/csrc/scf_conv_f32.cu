@@ -9,6 +9,7 @@
 // the channel-concatenation of up to three NHWC buffers ("segments"), which removes every torch.cat of the
 // reference loop (raft_decoder.py:165,166,248,251; scflow_decoder.py:207,219).
 #include "scf_common.cuh"
+#include "scf_tc.cuh"
 
 namespace scf {
 
@@ -34,10 +35,13 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvParams p) {
   __shared__ __align__(16) float Bs[2][BK][BN];
 
   const int t = threadIdx.x;
-  const int m0 = blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const scf_conv_desc& d = p.d;
   const int HoWo = d.Ho * d.Wo;
+  // per-sample weights (correlation build): tiles never straddle samples; blockIdx.z = sample
+  const bool per_sample = d.w_batch_stride != 0;
+  const int m0 = per_sample ? blockIdx.z * HoWo + blockIdx.x * BM : blockIdx.x * BM;
+  const int m_end = per_sample ? (blockIdx.z + 1) * HoWo : p.M;
 
   // ---- A-load bookkeeping: which output pixel / k-lanes this thread fetches
   int a_ml, a_k[4];
@@ -50,7 +54,7 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvParams p) {
     for (int j = 0; j < 4; ++j) a_k[j] = (t >> 6) + 4 * j;
   }
   const int a_gm = m0 + a_ml;
-  const bool a_valid = a_gm < p.M;
+  const bool a_valid = a_gm < m_end;
   int a_b = 0, a_oy = 0, a_ox = 0;
   if (a_valid) {
     a_b = a_gm / HoWo;
@@ -63,7 +67,7 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvParams p) {
   // ---- B-load bookkeeping
   const int b_row = t >> 4, b_n4 = (t & 15) * 4;
   const float* wbase = d.w;
-  if (d.w_batch_stride != 0) wbase += (long long)(m0 / HoWo) * d.w_batch_stride;
+  if (per_sample) wbase += (long long)blockIdx.z * d.w_batch_stride;
 
   float a_reg[4];
   float4 b_reg;
@@ -144,14 +148,22 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvParams p) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const long long gm = m0 + ty * 4 + i;
-    if (gm >= p.M) continue;
+    if (gm >= m_end) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= d.cout) continue;
       float v = acc[i][j] * d.scale + (d.bias ? __ldg(d.bias + n) : 0.f);
       if (d.epi == SCF_EPI_ACT) {
-        d.out[gm * d.out_stride + d.out_coff + n] = act_apply(v, d.act);
+        v = act_apply(v, d.act);
+        if (d.out) d.out[gm * d.out_stride + d.out_coff + n] = v;
+        if (d.out_hl) {
+          __nv_bfloat16 hi, lo;
+          tc::split_bf16(v, hi, lo);
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(d.out_hl) + gm * d.out_hl_stride + d.out_hl_coff + n;
+          o[0] = hi;
+          o[d.out_hl_plane] = lo;
+        }
       } else if (d.epi == SCF_EPI_GRU_ZR) {
         const float s = 1.f / (1.f + expf(-v));
         if (n < half) d.out[gm * d.out_stride + d.out_coff + n] = s;
@@ -215,7 +227,8 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int src_strid
 
 int conv2d_f32(const scf_conv_desc& d, cudaStream_t st) {
   SCF_REQUIRE(d.nseg >= 1 && d.nseg <= 3, SCF_ERR_ARG, "scf_conv2d: nseg must be 1..3");
-  SCF_REQUIRE(d.w && d.out && d.B > 0 && d.cout > 0, SCF_ERR_ARG, "scf_conv2d: null pointer or empty shape");
+  SCF_REQUIRE(d.w && (d.out || (d.out_hl && d.epi == SCF_EPI_ACT)) && d.B > 0 && d.cout > 0, SCF_ERR_ARG,
+              "scf_conv2d: null pointer or empty shape");
   SCF_REQUIRE(d.ldw >= d.cout && d.ldw % 4 == 0, SCF_ERR_ARG, "scf_conv2d: ldw must be >= cout and a multiple of 4");
   SCF_REQUIRE(d.epi >= SCF_EPI_ACT && d.epi <= SCF_EPI_GRU_Q, SCF_ERR_ARG, "scf_conv2d: bad epilogue");
   if (d.epi == SCF_EPI_GRU_ZR) SCF_REQUIRE(d.aux0 && d.out2 && d.cout % 2 == 0, SCF_ERR_ARG, "scf_conv2d: GRU_ZR needs aux0/out2");
@@ -236,10 +249,11 @@ int conv2d_f32(const scf_conv_desc& d, cudaStream_t st) {
   p.M = d.B * d.Ho * d.Wo;
   p.K = d.kh * d.kw * p.cin;
   SCF_REQUIRE(reinterpret_cast<uintptr_t>(d.w) % 16 == 0, SCF_ERR_ALIGN, "scf_conv2d: packed weight must be 16B aligned");
-  if (d.w_batch_stride != 0)
-    SCF_REQUIRE((d.Ho * d.Wo) % BM == 0 && d.w_batch_stride % 4 == 0, SCF_ERR_UNSUPPORTED,
-                "scf_conv2d: per-sample weights need Ho*Wo %% %d == 0", BM);
   dim3 grid(cdiv(p.M, BM), cdiv(d.cout, BN));
+  if (d.w_batch_stride != 0) {
+    SCF_REQUIRE(d.w_batch_stride % 4 == 0, SCF_ERR_ALIGN, "scf_conv2d: w_batch_stride must be a multiple of 4");
+    grid = dim3(cdiv(d.Ho * d.Wo, BM), cdiv(d.cout, BN), d.B);
+  }
   if (vec) conv_f32_kernel<4><<<grid, 256, 0, st>>>(p);
   else conv_f32_kernel<1><<<grid, 256, 0, st>>>(p);
   return check_launch("conv_f32_kernel");

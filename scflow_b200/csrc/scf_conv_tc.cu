@@ -1,0 +1,422 @@
+// tcgen05 implicit-GEMM convolution with split-bf16 operands (bf16x3) and fp32 accumulation in TMEM.
+//
+// GEMM view per CTA: D[128 pixels x BN couts] += sum over (tap, 64-channel chunk) of A_tap[128 x 64] * W_tap[BN x 64]^T.
+//   * A tile  : ONE 5-D TMA box {64 ch, TW, TH, 1 sample, 2 planes} of the NHWC split-bf16 activation, fetched at the
+//               tap-shifted pixel origin; out-of-image pixels (the convolution's zero padding) and channels beyond the
+//               segment are zero-filled by TMA.  128 B rows + SWIZZLE_128B = the canonical K-major UMMA layout.
+//   * W tile  : ONE 4-D TMA box {64 cin, BN cout, 1 tap, 2 planes} of the packed weights.
+//   * MMA     : per 16-channel k-step three tcgen05.mma (hi*hi, hi*lo, lo*hi), M=128, N=BN, issued by one thread.
+//   * epilogue: 4 warps read the accumulator with tcgen05.ld (one TMEM lane = one pixel per thread), apply
+//               bias/activation or the GRU gate math, and write fp32 and/or split-bf16 NHWC outputs.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include "scf_common.cuh"
+#include "scf_tc.cuh"
+#include <mutex>
+
+namespace scf {
+
+using namespace tc;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TC_A_PLANE = TC_BM * TC_BK * 2;   // 16 KB
+constexpr int TC_MAX_STAGES = 4;
+
+struct TcParams {
+  int nseg, seg_chunks[3], seg_wcoff[3];
+  int B, H, W, kh, kw, ph, pw;
+  int TW, TH, tiles_x, tiles_y;
+  int BN, cout, num_taps, w_batched, stages, tmem_cols;
+  const float* bias; float scale; int epi, act;
+  float* out_f32; int out_f32_stride, out_f32_coff;
+  __nv_bfloat16* out_hl; long long out_hl_plane; int out_hl_stride, out_hl_coff;
+  const float* aux0; int aux0_stride; const float* aux1; int aux1_stride;
+  __nv_bfloat16* out2_hl; long long out2_hl_plane; int out2_hl_stride;
+};
+
+__device__ __forceinline__ void store_f32x16(float* dst, const float* v, int nvalid) {
+  if (nvalid == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    for (int i = 0; i < nvalid; ++i) dst[i] = v[i];
+  }
+}
+
+__device__ __forceinline__ void store_split16(__nv_bfloat16* hi_dst, long long plane, const float* v, int nvalid) {
+  __align__(16) __nv_bfloat16 hi[16];
+  __align__(16) __nv_bfloat16 lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) split_bf16(v[i], hi[i], lo[i]);
+  if (nvalid == 16 && (reinterpret_cast<uintptr_t>(hi_dst) & 15) == 0 && ((plane * 2) & 15) == 0) {
+    reinterpret_cast<uint4*>(hi_dst)[0] = reinterpret_cast<const uint4*>(hi)[0];
+    reinterpret_cast<uint4*>(hi_dst)[1] = reinterpret_cast<const uint4*>(hi)[1];
+    reinterpret_cast<uint4*>(hi_dst + plane)[0] = reinterpret_cast<const uint4*>(lo)[0];
+    reinterpret_cast<uint4*>(hi_dst + plane)[1] = reinterpret_cast<const uint4*>(lo)[1];
+  } else {
+    for (int i = 0; i < nvalid; ++i) { hi_dst[i] = hi[i]; hi_dst[plane + i] = lo[i]; }
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024 B alignment
+  // [0,1024): barriers + TMEM pointer ; then `stages` x {A hi, A lo, W hi, W lo}
+  const uint32_t bar_full = smem_base, bar_empty = smem_base + 64, bar_tmem = smem_base + 128, tmem_slot = smem_base + 192;
+  const uint32_t b_plane = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;
+  const uint32_t tiles0 = smem_base + 1024;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int b = blockIdx.x / tiles_per_img;
+  const int tr = blockIdx.x - b * tiles_per_img;
+  const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+  const int x0 = tx * p.TW, y0 = ty * p.TH;
+  const int n0 = blockIdx.y * p.BN;
+  const int chunks_per_tap = p.seg_chunks[0] + p.seg_chunks[1] + p.seg_chunks[2];
+  const int num_chunks = p.num_taps * chunks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0);
+    if (p.nseg > 1) prefetch_tmap(&tmA1);
+    if (p.nseg > 2) prefetch_tmap(&tmA2);
+    prefetch_tmap(&tmW);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tmem, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tap = 0; tap < p.num_taps; ++tap) {
+        const int ky = tap / p.kw, kx = tap - ky * p.kw;
+        const int cx = x0 + kx - p.pw, cy = y0 + ky - p.ph;
+        for (int s = 0; s < p.nseg; ++s) {
+          const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
+          for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            const uint32_t full = bar_full + 8 * stage;
+            mbar_arrive_expect_tx(full, stage_bytes);
+            const uint32_t a_dst = tiles0 + stage * stage_bytes;
+            tma_load_5d(a_dst, tm, full, cc * TC_BK, cx, cy, b, 0);
+            tma_load_4d(a_dst + 2 * TC_A_PLANE, &tmW, full, p.seg_wcoff[s] + cc * TC_BK, n0, p.w_batched ? b : tap, 0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer
+      const uint32_t idesc = make_idesc_bf16(TC_BM, p.BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = 0; c < num_chunks; ++c) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t a_addr = tiles0 + stage * stage_bytes;
+        const uint64_t a_hi = make_smem_desc_sw128(a_addr), a_lo = make_smem_desc_sw128(a_addr + TC_A_PLANE);
+        const uint64_t b_hi = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE);
+        const uint64_t b_lo = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + b_plane);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t ko = (uint64_t)(k * 32 >> 4);     // 16 bf16 = 32 B along the swizzled 128 B row
+          umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, (c > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
+          umma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
+        }
+        umma_commit(bar_empty + 8 * stage);       // frees the smem slot once these MMAs have read it
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(bar_tmem);                      // accumulator complete
+    }
+  } else {
+    // ================= epilogue: warp w owns TMEM lanes 32*(w%4)..+31 ; lane = pixel row of the tile
+    mbar_wait(bar_tmem, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int h = row / p.TW, w = row - h * p.TW;
+    const int y = y0 + h, x = x0 + w;
+    const bool valid = y < p.H && x < p.W;
+    const long long pix = ((long long)b * p.H + y) * p.W + x;
+    const int half = p.cout >> 1;
+    for (int g = 0; g < p.BN / 16; ++g) {
+      float v[16];
+      __syncwarp();
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 16), v);
+      const int nb = n0 + g * 16;
+      if (!valid || nb >= p.cout) continue;
+      const int nvalid = p.cout - nb < 16 ? p.cout - nb : 16;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = v[i] * p.scale + ((p.bias && i < nvalid) ? __ldg(p.bias + nb + i) : 0.f);
+      if (p.epi == SCF_EPI_ACT) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], p.act);
+        if (p.out_f32) store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, nvalid);
+        if (p.out_hl) store_split16(p.out_hl + pix * p.out_hl_stride + p.out_hl_coff + nb, p.out_hl_plane, v, nvalid);
+      } else if (p.epi == SCF_EPI_GRU_ZR) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 1.f / (1.f + expf(-v[i]));
+        if (nb < half) {           // z gate -> fp32 (read back by the q convolution's epilogue)
+          store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, nvalid);
+        } else {                   // r gate -> r*h as split-bf16, the q convolution's first input segment
+          const float* hp = p.aux0 + pix * p.aux0_stride + (nb - half);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= (i < nvalid) ? __ldg(hp + i) : 0.f;
+          store_split16(p.out2_hl + pix * p.out2_hl_stride + (nb - half), p.out2_hl_plane, v, nvalid);
+        }
+      } else {                     // SCF_EPI_GRU_Q: h' = (1-z) h + z tanh(.)
+        const float* hp = p.aux0 + pix * p.aux0_stride + nb;
+        const float* zp = p.aux1 + pix * p.aux1_stride + nb;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (i < nvalid) {
+            const float qv = tanhf(v[i]), hv = __ldg(hp + i), zv = __ldg(zp + i);
+            v[i] = (1.f - zv) * hv + zv * qv;
+          }
+        }
+        if (p.out_f32) store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, nvalid);
+        if (p.out_hl) store_split16(p.out_hl + pix * p.out_hl_stride + p.out_hl_coff + nb, p.out_hl_plane, v, nvalid);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------ prep kernels
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, int O, int I, int taps,
+                                      int cin_pad, int cout_pad, int o_off) {
+  const long long total = (long long)O * I * taps;
+  const long long plane = (long long)taps * cout_pad * cin_pad;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % I);
+    const long long r = idx / I;
+    const int o = (int)(r % O);
+    const int tap = (int)(r / O);
+    __nv_bfloat16 hi, lo;
+    split_bf16(w[((long long)o * I + i) * taps + tap], hi, lo);
+    const long long dst = ((long long)tap * cout_pad + o_off + o) * cin_pad + i;
+    packed[dst] = hi;
+    packed[plane + dst] = lo;
+  }
+}
+
+__global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long plane,
+                                          int dst_stride, int dst_coff, float* __restrict__ dst_f32, int f32_stride, int C,
+                                          int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, pp = p0 + threadIdx.x;
+    if (c < C && pp < HW) tile[i][threadIdx.x] = src[((long long)b * C + c) * HW + pp];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pp = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && pp < HW) {
+      const float v = tile[threadIdx.x][i];
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      const long long o = ((long long)b * HW + pp) * dst_stride + dst_coff + c;
+      dst[o] = hi;
+      dst[plane + o] = lo;
+      if (dst_f32) dst_f32[((long long)b * HW + pp) * f32_stride + c] = v;
+    }
+  }
+}
+
+__global__ void split_copy_kernel(const float* __restrict__ src, int src_stride, int src_coff, __nv_bfloat16* __restrict__ dst,
+                                  long long plane, int dst_stride, int dst_coff, long long npix, int nch) {
+  const long long total = npix * nch;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long px = idx / nch;
+    const int c = (int)(idx - px * nch);
+    __nv_bfloat16 hi, lo;
+    split_bf16(src[px * src_stride + src_coff + c], hi, lo);
+    dst[px * dst_stride + dst_coff + c] = hi;
+    dst[plane + px * dst_stride + dst_coff + c] = lo;
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  SCF_REQUIRE(fn != nullptr, SCF_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, ones,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SCF_REQUIRE(r == CUDA_SUCCESS, SCF_ERR_ARG, "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dims %llu %llu %llu, box %u %u %u)",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1],
+              box[2]);
+  return 0;
+}
+
+static void pick_tile(int H, int W, int& TW, int& TH) {
+  // TW*TH = 128; minimise padded area, prefer wide tiles (longer contiguous runs)
+  long long best = -1;
+  for (int tw = 128; tw >= 4; tw >>= 1) {
+    const int th = 128 / tw;
+    if (tw > 256 || th > 256) continue;
+    const long long area = (long long)cdiv(W, tw) * tw * cdiv(H, th) * th;
+    if (best < 0 || area < best) { best = area; TW = tw; TH = th; }
+  }
+}
+
+int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
+  SCF_REQUIRE(d.nseg >= 1 && d.nseg <= 3, SCF_ERR_ARG, "scf_conv2d_tc: nseg must be 1..3");
+  SCF_REQUIRE(d.w && d.B > 0 && d.H > 0 && d.W > 0 && d.cout > 0, SCF_ERR_ARG, "scf_conv2d_tc: null pointer or empty shape");
+  SCF_REQUIRE(d.kh >= 1 && d.kw >= 1 && d.kh % 2 == 1 && d.kw % 2 == 1, SCF_ERR_ARG, "scf_conv2d_tc: odd kernel sizes only");
+  SCF_REQUIRE(d.cin_pad % 8 == 0 && d.cout_pad % 16 == 0 && d.cout <= d.cout_pad, SCF_ERR_ARG,
+              "scf_conv2d_tc: cin_pad %% 8, cout_pad %% 16 required");
+  SCF_REQUIRE(!d.w_batched || (d.kh == 1 && d.kw == 1), SCF_ERR_ARG, "scf_conv2d_tc: batched weights need a 1x1 kernel");
+  SCF_REQUIRE(d.out_f32 || d.out_hl || d.epi == SCF_EPI_GRU_ZR, SCF_ERR_ARG, "scf_conv2d_tc: no output given");
+  if (d.epi == SCF_EPI_GRU_ZR)
+    SCF_REQUIRE(d.out_f32 && d.aux0 && d.out2_hl && d.cout % 32 == 0, SCF_ERR_ARG, "scf_conv2d_tc: GRU_ZR needs out_f32 (z), aux0 (h), out2_hl (r*h)");
+  if (d.epi == SCF_EPI_GRU_Q) SCF_REQUIRE(d.aux0 && d.aux1, SCF_ERR_ARG, "scf_conv2d_tc: GRU_Q needs aux0 (h) and aux1 (z)");
+
+  TcParams p = {};
+  p.nseg = d.nseg;
+  p.B = d.B; p.H = d.H; p.W = d.W; p.kh = d.kh; p.kw = d.kw; p.ph = d.kh / 2; p.pw = d.kw / 2;
+  pick_tile(d.H, d.W, p.TW, p.TH);
+  p.tiles_x = cdiv(d.W, p.TW); p.tiles_y = cdiv(d.H, p.TH);
+  p.BN = d.cout_pad <= 256 ? d.cout_pad : 256;
+  p.cout = d.cout;
+  p.num_taps = d.kh * d.kw;
+  p.w_batched = d.w_batched;
+  const int stage_bytes = 2 * (int)TC_A_PLANE + 2 * p.BN * 128;
+  p.stages = (232448 - 2048) / stage_bytes;
+  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  SCF_REQUIRE(p.stages >= 2, SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: tile does not fit in shared memory");
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+  p.bias = d.bias; p.scale = d.scale; p.epi = d.epi; p.act = d.act;
+  p.out_f32 = d.out_f32; p.out_f32_stride = d.out_f32_stride; p.out_f32_coff = d.out_f32_coff;
+  p.out_hl = reinterpret_cast<__nv_bfloat16*>(d.out_hl); p.out_hl_plane = d.out_hl_plane; p.out_hl_stride = d.out_hl_stride;
+  p.out_hl_coff = d.out_hl_coff;
+  p.aux0 = d.aux0; p.aux0_stride = d.aux0_stride; p.aux1 = d.aux1; p.aux1_stride = d.aux1_stride;
+  p.out2_hl = reinterpret_cast<__nv_bfloat16*>(d.out2_hl); p.out2_hl_plane = d.out2_hl_plane; p.out2_hl_stride = d.out2_hl_stride;
+
+  CUtensorMap tmA[3], tmW;
+  int wcoff = 0;
+  for (int s = 0; s < 3; ++s) {
+    if (s >= d.nseg) { tmA[s] = tmA[0]; p.seg_chunks[s] = 0; p.seg_wcoff[s] = 0; continue; }
+    const scf_tc_seg& sg = d.seg[s];
+    SCF_REQUIRE(sg.ptr && sg.nch > 0 && sg.nch % 8 == 0 && sg.coff % 8 == 0 && sg.stride % 8 == 0, SCF_ERR_ALIGN,
+                "scf_conv2d_tc: segment %d channels/offset/stride must be multiples of 8", s);
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(sg.ptr) + sg.coff;
+    SCF_REQUIRE(reinterpret_cast<uintptr_t>(base) % 16 == 0 && (sg.plane_stride * 2) % 16 == 0, SCF_ERR_ALIGN,
+                "scf_conv2d_tc: segment %d must be 16B aligned", s);
+    cuuint64_t dims[5] = {(cuuint64_t)sg.nch, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B, 2};
+    cuuint64_t str[4] = {(cuuint64_t)sg.stride * 2, (cuuint64_t)d.W * sg.stride * 2, (cuuint64_t)d.H * d.W * sg.stride * 2,
+                         (cuuint64_t)sg.plane_stride * 2};
+    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1, 2};
+    SCF_TRY(encode_map(&tmA[s], base, 5, dims, str, box));
+    p.seg_chunks[s] = cdiv(sg.nch, TC_BK);
+    p.seg_wcoff[s] = wcoff;
+    wcoff += sg.nch;
+  }
+  SCF_REQUIRE(wcoff <= d.cin_pad, SCF_ERR_ARG, "scf_conv2d_tc: segments carry %d channels but the packed weight has cin_pad %d", wcoff, d.cin_pad);
+  {
+    const int third = d.w_batched ? d.B : p.num_taps;
+    cuuint64_t dims[4] = {(cuuint64_t)d.cin_pad, (cuuint64_t)d.cout_pad, (cuuint64_t)third, 2};
+    cuuint64_t str[3] = {(cuuint64_t)d.cin_pad * 2, (cuuint64_t)d.cout_pad * d.cin_pad * 2,
+                         (cuuint64_t)third * d.cout_pad * d.cin_pad * 2};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)p.BN, 1, 2};
+    SCF_REQUIRE(reinterpret_cast<uintptr_t>(d.w) % 16 == 0, SCF_ERR_ALIGN, "scf_conv2d_tc: packed weight must be 16B aligned");
+    SCF_TRY(encode_map(&tmW, d.w, 4, dims, str, box));
+  }
+  const int smem = 1024 + 1024 + p.stages * stage_bytes;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  });
+  SCF_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(attr_err));
+  dim3 grid(p.tiles_x * p.tiles_y * d.B, cdiv(d.cout_pad, p.BN));
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA[0], tmA[1], tmA[2], tmW, p);
+  return check_launch("conv_tc_kernel");
+}
+
+}  // namespace scf
+
+extern "C" {
+
+int scf_conv2d_tc(const scf_tc_conv_desc* d, void* stream) {
+  SCF_REQUIRE(d != nullptr, SCF_ERR_ARG, "scf_conv2d_tc: null descriptor");
+  return scf::conv2d_tc(*d, (cudaStream_t)stream);
+}
+
+int scf_pack_conv_weight_tc(const float* w_oihw, void* packed, int O, int I, int kh, int kw, int cin_pad, int cout_pad,
+                            int o_off, void* stream) {
+  SCF_REQUIRE(w_oihw && packed && O > 0 && I > 0 && kh > 0 && kw > 0, SCF_ERR_ARG, "scf_pack_conv_weight_tc: bad args");
+  SCF_REQUIRE(cin_pad >= I && cout_pad >= o_off + O, SCF_ERR_ARG, "scf_pack_conv_weight_tc: padding smaller than the weight");
+  const long long total = (long long)O * I * kh * kw;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  scf::pack_weight_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(packed), O, I,
+                                                                      kh * kw, cin_pad, cout_pad, o_off);
+  return scf::check_launch("pack_weight_tc_kernel");
+}
+
+int scf_nchw_to_nhwc_split(const float* src, void* dst_hl, long long plane_stride, int dst_stride, int dst_coff,
+                           float* dst_f32, int dst_f32_stride, int B, int C, int H, int W, void* stream) {
+  SCF_REQUIRE(src && dst_hl && B > 0 && C > 0 && H > 0 && W > 0, SCF_ERR_ARG, "scf_nchw_to_nhwc_split: bad args");
+  dim3 grid(scf::cdiv(H * W, 32), scf::cdiv(C, 32), B);
+  scf::nchw_to_nhwc_split_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst_hl), plane_stride, dst_stride, dst_coff, dst_f32, dst_f32_stride, C, H * W);
+  return scf::check_launch("nchw_to_nhwc_split_kernel");
+}
+
+int scf_split_copy(const float* src, int src_stride, int src_coff, void* dst_hl, long long plane_stride, int dst_stride,
+                   int dst_coff, long long npix, int nch, void* stream) {
+  SCF_REQUIRE(src && dst_hl && npix > 0 && nch > 0, SCF_ERR_ARG, "scf_split_copy: bad args");
+  const long long total = npix * nch;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  scf::split_copy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, src_stride, src_coff, reinterpret_cast<__nv_bfloat16*>(dst_hl),
+                                                                  plane_stride, dst_stride, dst_coff, npix, nch);
+  return scf::check_launch("split_copy_kernel");
+}
+
+}  // extern "C"

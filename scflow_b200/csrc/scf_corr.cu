@@ -5,6 +5,7 @@
 //   g = c*2/(W_l-1) - 1 ; i = ((g+1)*0.5)*(W_l-1)        -- replayed with round-to-nearest intrinsics, no FMA
 //   bilinear taps floor(i), floor(i)+1 ; out-of-range taps contribute 0 (padding_mode='zeros').
 #include "scf_common.cuh"
+#include "scf_tc.cuh"
 
 namespace scf {
 
@@ -20,6 +21,8 @@ struct LookupParams {
   const float* mask;
   float* out;
   int out_stride, out_coff;
+  __nv_bfloat16* out_hl;      // when set: split-bf16 planes instead of fp32 (pad channels up to out_stride zeroed)
+  long long out_hl_plane;
   int H8, W8;
   long long nq;
 };
@@ -43,7 +46,8 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) 
   const float gx0 = __fadd_rn((float)x, f.x), gy0 = __fadd_rn((float)y, f.y);
   const float mval = p.mask ? p.mask[q] : 1.f;
   const int r = p.radius, k = 2 * r + 1, kk = k * k;
-  float* outq = p.out + q * p.out_stride + p.out_coff;
+  float* outq = p.out ? p.out + q * p.out_stride + p.out_coff : nullptr;
+  __nv_bfloat16* outh = p.out_hl ? p.out_hl + q * p.out_stride : nullptr;
   float inv = 1.f;
   for (int l = 0; l < p.num_levels; ++l, inv *= 0.5f) {
     const int hl = p.hl[l], wl = p.wl[l];
@@ -70,8 +74,19 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) 
         if (xin0) acc += __ldg(row + x0) * (wx0 * wy1);
         if (xin1) acc += __ldg(row + x0 + 1) * (wx1 * wy1);
       }
-      outq[l * kk + tap] = acc * mval;
+      acc *= mval;
+      if (outq) outq[l * kk + tap] = acc;
+      if (outh) {
+        __nv_bfloat16 hi, lo;
+        tc::split_bf16(acc, hi, lo);
+        outh[l * kk + tap] = hi;
+        outh[p.out_hl_plane + l * kk + tap] = lo;
+      }
     }
+  }
+  if (outh) {
+    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+    for (int c = p.num_levels * kk + lane; c < p.out_stride; c += 32) { outh[c] = zero; outh[p.out_hl_plane + c] = zero; }
   }
 }
 
@@ -151,9 +166,12 @@ size_t scf_corr_build_scratch_bytes(int B, int C, int H8, int W8) {
   return (size_t)B * H8 * W8 * C * 4 * 3 + 1024;
 }
 
-int scf_corr_lookup(const float* const* h_levels, int num_levels, int radius, const float* flow8, const float* mask,
-                    float* out, int out_stride, int out_coff, int B, int H8, int W8, void* stream) {
-  SCF_REQUIRE(h_levels && flow8 && out, SCF_ERR_ARG, "scf_corr_lookup: null pointer");
+static int corr_lookup_impl(const float* const* h_levels, int num_levels, int radius, const float* flow8, const float* mask,
+                            float* out, void* out_hl, long long plane, int out_stride, int out_coff, int B, int H8, int W8,
+                            void* stream) {
+  SCF_REQUIRE(h_levels && flow8 && (out || out_hl), SCF_ERR_ARG, "scf_corr_lookup: null pointer");
+  SCF_REQUIRE(out_stride >= out_coff + num_levels * (2 * radius + 1) * (2 * radius + 1), SCF_ERR_ARG,
+              "scf_corr_lookup: out_stride too small");
   SCF_REQUIRE(num_levels >= 1 && num_levels <= scf::kMaxLevels && radius >= 0 && radius <= 8, SCF_ERR_ARG,
               "scf_corr_lookup: num_levels 1..%d, radius 0..8", scf::kMaxLevels);
   SCF_REQUIRE(B > 0 && H8 > 0 && W8 > 0, SCF_ERR_ARG, "scf_corr_lookup: empty shape");
@@ -166,10 +184,22 @@ int scf_corr_lookup(const float* const* h_levels, int num_levels, int radius, co
     hl /= 2; wl /= 2;
   }
   p.num_levels = num_levels; p.radius = radius; p.flow8 = flow8; p.mask = mask; p.out = out;
+  p.out_hl = reinterpret_cast<__nv_bfloat16*>(out_hl); p.out_hl_plane = plane;
   p.out_stride = out_stride; p.out_coff = out_coff; p.H8 = H8; p.W8 = W8; p.nq = (long long)B * H8 * W8;
   const int wpb = 8;
   scf::corr_lookup_kernel<<<scf::cdiv(p.nq, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(p);
   return scf::check_launch("corr_lookup_kernel");
+}
+
+int scf_corr_lookup(const float* const* h_levels, int num_levels, int radius, const float* flow8, const float* mask,
+                    float* out, int out_stride, int out_coff, int B, int H8, int W8, void* stream) {
+  return corr_lookup_impl(h_levels, num_levels, radius, flow8, mask, out, nullptr, 0, out_stride, out_coff, B, H8, W8, stream);
+}
+
+int scf_corr_lookup_split(const float* const* h_levels, int num_levels, int radius, const float* flow8, const float* mask,
+                          void* out_hl, long long plane_stride, int out_stride, int B, int H8, int W8, void* stream) {
+  return corr_lookup_impl(h_levels, num_levels, radius, flow8, mask, nullptr, out_hl, plane_stride, out_stride, 0, B, H8, W8,
+                          stream);
 }
 
 int scf_corr_lookup_taps(int level, int radius, const float* flow8, int32_t* x0, int32_t* y0, int B, int H8, int W8,

@@ -9,7 +9,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, ConvSeg, check, ptr, stream_ptr
+from ._lib import ConvDesc, ConvSeg, TcConvDesc, TcSeg, check, ptr, stream_ptr
 
 PRECISION_FP32 = 0       # exact-fp32 CUDA-core convolutions / build
 PRECISION_BF16X3 = 1     # tcgen05 split-bf16 (3 MMAs, fp32 accumulate in TMEM)
@@ -224,3 +224,82 @@ def resize_bilinear_nchw(x: torch.Tensor, out_h: int, out_w: int, scale: float =
                                           out_h * out_w, out_w, 1, out_h, out_w, b, c, scale, stream_ptr()),
           'scf_resize_bilinear')
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# tcgen05 split-bf16 path.  A "split tensor" is a bf16 tensor [2, B, H, W, C]: plane 0 = hi, plane 1 = lo.
+# ----------------------------------------------------------------------------------------------------------------------
+def _req_split(t: torch.Tensor, name: str):
+    _req(t, name, torch.bfloat16)
+    if t.dim() != 5 or t.shape[0] != 2:
+        raise ValueError(f'{name} must be a split-bf16 tensor [2,B,H,W,C]')
+    return t
+
+
+def split_nchw(x: torch.Tensor, out: Optional[torch.Tensor] = None, coff: int = 0, stride: Optional[int] = None,
+               want_f32: bool = False):
+    """NCHW fp32 -> split-bf16 NHWC planes [2,B,H,W,stride] (and optionally an fp32 NHWC copy)."""
+    _req(x, 'x')
+    b, c, h, w = x.shape
+    if out is None:
+        out = torch.zeros(2, b, h, w, stride or c, device=x.device, dtype=torch.bfloat16)
+    f32 = torch.empty(b, h, w, c, device=x.device, dtype=torch.float32) if want_f32 else None
+    check(_lib.load().scf_nchw_to_nhwc_split(ptr(x), ptr(out), out[0].numel(), out.shape[-1], coff, ptr(f32), c, b, c, h, w,
+                                             stream_ptr()), 'scf_nchw_to_nhwc_split')
+    return (out, f32) if want_f32 else out
+
+
+def unsplit(t: torch.Tensor) -> torch.Tensor:
+    """Debug helper: split-bf16 [2,B,H,W,C] -> fp32 NCHW (hi + lo)."""
+    return (t[0].float() + t[1].float()).permute(0, 3, 1, 2).contiguous()
+
+
+def pack_conv_weight_tc(weights: Sequence[torch.Tensor], cin_pad: Optional[int] = None, cout_pad: Optional[int] = None) -> torch.Tensor:
+    """OIHW fp32 weights (merged along O) -> bf16 [2, taps, cout_pad, cin_pad]."""
+    o_total = sum(int(w.shape[0]) for w in weights)
+    _, i, kh, kw = weights[0].shape
+    cin_pad = cin_pad or (i + 7) // 8 * 8
+    cout_pad = cout_pad or (o_total + 15) // 16 * 16
+    packed = torch.zeros(2, kh * kw, cout_pad, cin_pad, device=weights[0].device, dtype=torch.bfloat16)
+    off = 0
+    for w in weights:
+        _req(w, 'weight')
+        check(_lib.load().scf_pack_conv_weight_tc(ptr(w), ptr(packed), w.shape[0], i, kh, kw, cin_pad, cout_pad, off, stream_ptr()),
+              'scf_pack_conv_weight_tc')
+        off += int(w.shape[0])
+    return packed
+
+
+def conv2d_tc(segs: Sequence, packed_w: torch.Tensor, bias: Optional[torch.Tensor], cout: int, kernel, act: str = 'none',
+              out_f32: Optional[torch.Tensor] = None, out_f32_coff: int = 0, out_hl: Optional[torch.Tensor] = None,
+              out_hl_coff: int = 0, epi: int = _lib.EPI_ACT, aux0=None, aux1=None, out2_hl=None, scale: float = 1.0,
+              w_batched: bool = False):
+    """tcgen05 convolution. ``segs`` = [(split tensor [2,B,H,W,stride], coff, nch), ...]."""
+    kh, kw = (kernel, kernel) if isinstance(kernel, int) else kernel
+    d = TcConvDesc()
+    for n, (t, coff, nch) in enumerate(segs):
+        _req_split(t, f'seg{n}')
+        d.seg[n] = TcSeg(t.data_ptr(), t[0].numel(), t.shape[-1], coff, nch)
+    d.nseg = len(segs)
+    _, b, h, w, _ = segs[0][0].shape
+    d.B, d.H, d.W, d.kh, d.kw = b, h, w, kh, kw
+    _req(packed_w, 'packed_w', torch.bfloat16)
+    d.w = packed_w.data_ptr()
+    d.cin_pad, d.cout_pad, d.cout, d.w_batched = packed_w.shape[-1], packed_w.shape[-2], cout, int(w_batched)
+    d.bias = None if bias is None else bias.data_ptr()
+    d.scale, d.epi, d.act = scale, epi, _lib.ACT[act]
+    if out_f32 is not None:
+        _req(out_f32, 'out_f32')
+        d.out_f32, d.out_f32_stride, d.out_f32_coff = out_f32.data_ptr(), out_f32.shape[-1], out_f32_coff
+    if out_hl is not None:
+        _req_split(out_hl, 'out_hl')
+        d.out_hl, d.out_hl_plane, d.out_hl_stride, d.out_hl_coff = out_hl.data_ptr(), out_hl[0].numel(), out_hl.shape[-1], out_hl_coff
+    if aux0 is not None:
+        d.aux0, d.aux0_stride = aux0.data_ptr(), aux0.shape[-1]
+    if aux1 is not None:
+        d.aux1, d.aux1_stride = aux1.data_ptr(), aux1.shape[-1]
+    if out2_hl is not None:
+        _req_split(out2_hl, 'out2_hl')
+        d.out2_hl, d.out2_hl_plane, d.out2_hl_stride = out2_hl.data_ptr(), out2_hl[0].numel(), out2_hl.shape[-1]
+    check(_lib.load().scf_conv2d_tc(C.byref(d), stream_ptr()), 'scf_conv2d_tc')
+    return out_f32 if out_f32 is not None else out_hl
