@@ -8,6 +8,8 @@
 namespace scf {
 
 int conv2d_f32(const scf_conv_desc& d, cudaStream_t st);
+int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st);
+int avgpool2(const float* in, float* out, long long nq, int hi, int wi, cudaStream_t st);
 int corr_build_dispatch(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
                         float* const* levels, void* scratch, int precision, cudaStream_t st);
 
@@ -32,6 +34,9 @@ struct PCInfo {
   int src_cout[2];
   int ldw;
   size_t w_off, b_off;        // float offsets into the arena
+  // tensor-core copy (precision 1): bf16 [2][taps][cout_pad][cin_pad] at byte offset tc_off (0 = layer stays on fp32 cores)
+  int tc, cin_pad, cout_pad;
+  size_t tc_off;
 };
 
 struct Arena {
@@ -39,6 +44,7 @@ struct Arena {
   size_t gn_w[3], gn_b[3];
   size_t fc0_w, fc0_b, fc1_w, fc1_b, rot_w, rot_b, tr_w, tr_b;
   size_t total_floats;
+  size_t total_bytes;         // fp32 section + tensor-core section
   int nc, rot_rows, tr_rows;
 };
 
@@ -88,6 +94,20 @@ static void build_arena(const scf_decoder_cfg& cfg, Arena& a) {
   a.rot_w = take((size_t)a.rot_rows * 256); a.rot_b = take(a.rot_rows);
   a.tr_w = take((size_t)a.tr_rows * 256); a.tr_b = take(a.tr_rows);
   a.total_floats = off;
+  // tensor-core section: every stride-1 convolution with >= 8 input channels
+  size_t boff = (off * 4 + 1023) / 1024 * 1024;
+  for (int i = 0; i < PC_COUNT; ++i) {
+    PCInfo& p = a.pc[i];
+    p.tc = (cfg.precision == 1 && p.cin >= 8 && i < PC_PH0) ? 1 : 0;
+    p.cin_pad = (p.cin + 7) / 8 * 8;
+    p.cout_pad = (p.cout + 15) / 16 * 16;
+    p.tc_off = 0;
+    if (p.tc) {
+      p.tc_off = boff;
+      boff += ((size_t)2 * p.kh * p.kw * p.cout_pad * p.cin_pad * 2 + 1023) / 1024 * 1024;
+    }
+  }
+  a.total_bytes = boff;
 }
 
 // FC0 consumes the flattened NCHW map (index c*16 + pix, pose_head.py:203); our map is NHWC (pix*128 + c):
@@ -126,6 +146,9 @@ __global__ void identity_delta_kernel(float* d_rot, float* d_trs, int B, int rot
 struct Workspace {
   size_t corr_scratch, lvl[8], pts4, flow8, flowm, maskprev, corr, c1, cf, f1, h[2], cxt, motion, z, rh, hd, dflow,
       mask8, df1, df2, mf1, mf2, p1, p2, p3, fc0, fc1;
+  // precision 1: split-bf16 planes [2][B*P][C] (byte offsets) and their plane strides in elements
+  size_t s_corr, s_c1, s_cf, s_f1, s_h[2], s_cxt, s_motion, s_rh, s_hd, s_df1, s_mf1;
+  int corr_stride_s;
   int hl[8], wl[8];
   int corr_stride;
   size_t total_bytes;
@@ -157,6 +180,13 @@ static void build_workspace(const scf_decoder_cfg& cfg, int B, int H, int W, Wor
   w.df1 = take(BP * 128 * 4); w.df2 = take(BP * 64 * 4); w.mf1 = take(BP * 64 * 4); w.mf2 = take(BP * 32 * 4);
   w.p1 = take(BP / 4 * 128 * 4 + 1024); w.p2 = take(BP / 16 * 128 * 4 + 1024); w.p3 = take(BP / 64 * 128 * 4 + 1024);
   w.fc0 = take((size_t)B * 1024 * 4); w.fc1 = take((size_t)B * 256 * 4);
+  w.corr_stride_s = (cfg.num_levels * k * k + 7) / 8 * 8;
+  if (cfg.precision == 1) {
+    auto split = [&](int ch) { return take(BP * ch * 2 * 2); };
+    w.s_corr = split(w.corr_stride_s); w.s_c1 = split(256); w.s_cf = split(256); w.s_f1 = split(128);
+    w.s_h[0] = split(128); w.s_h[1] = split(128); w.s_cxt = split(128); w.s_motion = split(128); w.s_rh = split(128);
+    w.s_hd = split(512); w.s_df1 = split(128); w.s_mf1 = split(64);
+  }
   w.total_bytes = off;
 }
 
@@ -192,7 +222,7 @@ size_t scf_decoder_packed_bytes(const scf_decoder_cfg* cfg) {
   if (check_cfg(cfg) != 0) return 0;
   Arena a;
   build_arena(*cfg, a);
-  return a.total_floats * 4;
+  return a.total_bytes;
 }
 
 size_t scf_decoder_workspace_bytes(const scf_decoder_cfg* cfg, int B, int H, int W) {
@@ -210,7 +240,7 @@ int scf_decoder_pack(const scf_decoder_cfg* cfg, const float* const* h_weights, 
   Arena a;
   build_arena(*cfg, a);
   float* base = reinterpret_cast<float*>(packed);
-  SCF_CUDA(cudaMemsetAsync(packed, 0, a.total_floats * 4, st));
+  SCF_CUDA(cudaMemsetAsync(packed, 0, a.total_bytes, st));
   for (int i = 0; i < PC_COUNT; ++i) {
     const PCInfo& p = a.pc[i];
     if (!cfg->pose_head && i >= PC_PH0) continue;
@@ -218,6 +248,9 @@ int scf_decoder_pack(const scf_decoder_cfg* cfg, const float* const* h_weights, 
     for (int s = 0; s < p.nsrc; ++s) {
       SCF_REQUIRE(h_weights[p.src_w[s]] != nullptr, SCF_ERR_ARG, "scf_decoder_pack: weight %d is null", p.src_w[s]);
       SCF_TRY(scf_pack_conv_weight(h_weights[p.src_w[s]], base + p.w_off, p.src_cout[s], p.cin, p.kh, p.kw, p.ldw, o_off, st));
+      if (p.tc)
+        SCF_TRY(scf_pack_conv_weight_tc(h_weights[p.src_w[s]], reinterpret_cast<char*>(packed) + p.tc_off, p.src_cout[s], p.cin,
+                                        p.kh, p.kw, p.cin_pad, p.cout_pad, o_off, st));
       if (p.src_b[s] >= 0) {
         SCF_REQUIRE(h_weights[p.src_b[s]] != nullptr, SCF_ERR_ARG, "scf_decoder_pack: bias %d is null", p.src_b[s]);
         SCF_CUDA(cudaMemcpyAsync(base + p.b_off + o_off, h_weights[p.src_b[s]], (size_t)p.src_cout[s] * 4,
@@ -299,8 +332,15 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
   SCF_TRY(corr_build_dispatch(io->feat_render, io->feat_real, B, 256, H8, W8, cfg->num_levels, levels, wsb + ws.corr_scratch,
                               cfg->precision, st));
   SCF_TRY(scf_unproject(io->depth, io->internel_k, io->ref_rotation, io->ref_translation, F(ws.pts4), B, H, W, st));
-  SCF_TRY(scf_nchw_to_nhwc(io->h_feat, F(ws.h[0]), B, 128, H8, W8, 128, 0, st));
-  SCF_TRY(scf_nchw_to_nhwc(io->cxt_feat, F(ws.cxt), B, 128, H8, W8, 128, 0, st));
+  const bool tcp = cfg->precision == 1;
+  auto S = [&](size_t off) { return reinterpret_cast<void*>(wsb + off); };
+  if (tcp) {
+    SCF_TRY(scf_nchw_to_nhwc_split(io->h_feat, S(ws.s_h[0]), (long long)BP * 128, 128, 0, F(ws.h[0]), 128, B, 128, H8, W8, st));
+    SCF_TRY(scf_nchw_to_nhwc_split(io->cxt_feat, S(ws.s_cxt), (long long)BP * 128, 128, 0, nullptr, 0, B, 128, H8, W8, st));
+  } else {
+    SCF_TRY(scf_nchw_to_nhwc(io->h_feat, F(ws.h[0]), B, 128, H8, W8, 128, 0, st));
+    SCF_TRY(scf_nchw_to_nhwc(io->cxt_feat, F(ws.cxt), B, 128, H8, W8, 128, 0, st));
+  }
   if (cfg->mask_corr || cfg->mask_flow) {
     fill_kernel<<<cdiv(BP, 256), 256, 0, st>>>(F(ws.maskprev), 1.f, (long long)BP);
     SCF_TRY(check_launch("fill_kernel"));
@@ -308,7 +348,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
 
   auto conv = [&](int id, std::initializer_list<scf_conv_seg> segs, int Hi, int Wi, int Ho, int Wo, int stride, int act,
                   float* out, int out_stride, int out_coff, int epi = SCF_EPI_ACT, const float* aux0 = nullptr,
-                  const float* aux1 = nullptr, float* out2 = nullptr) -> int {
+                  const float* aux1 = nullptr, float* out2 = nullptr, void* out_hl = nullptr, int out_hl_stride = 0) -> int {
     const PCInfo& p = a.pc[id];
     scf_conv_desc d = {};
     int n = 0;
@@ -321,7 +361,30 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
     d.scale = 1.f; d.epi = epi; d.act = act;
     d.out = out; d.out_stride = out_stride; d.out_coff = out_coff;
     d.aux0 = aux0; d.aux0_stride = 128; d.aux1 = aux1; d.aux1_stride = 128; d.out2 = out2; d.out2_stride = 128;
+    d.out_hl = out_hl; d.out_hl_plane = (long long)BP * out_hl_stride; d.out_hl_stride = out_hl_stride; d.out_hl_coff = 0;
     return conv2d_f32(d, st);
+  };
+  // tensor-core convolution on split-bf16 buffers: segs = {plane base, channels per pixel, first channel, channels}
+  struct SSeg { void* ptr; int stride, coff, nch; };
+  auto convtc = [&](int id, std::initializer_list<SSeg> segs, int act, float* out_f32, int f32_stride, void* out_hl,
+                    int hl_stride, int hl_coff, int epi = SCF_EPI_ACT, const float* aux0 = nullptr, const float* aux1 = nullptr,
+                    void* out2_hl = nullptr) -> int {
+    const PCInfo& p = a.pc[id];
+    scf_tc_conv_desc d = {};
+    int n = 0;
+    for (const SSeg& sg : segs) { d.seg[n].ptr = sg.ptr; d.seg[n].plane_stride = (long long)BP * sg.stride; d.seg[n].stride = sg.stride;
+                                  d.seg[n].coff = sg.coff; d.seg[n].nch = sg.nch; ++n; }
+    d.nseg = n;
+    d.B = B; d.H = H8; d.W = W8; d.kh = p.kh; d.kw = p.kw;
+    d.w = reinterpret_cast<const char*>(packed) + p.tc_off; d.cin_pad = p.cin_pad; d.cout_pad = p.cout_pad; d.cout = p.cout;
+    d.w_batched = 0;
+    d.bias = p.src_b[0] >= 0 ? pw + p.b_off : nullptr;
+    d.scale = 1.f; d.epi = epi; d.act = act;
+    d.out_f32 = out_f32; d.out_f32_stride = f32_stride; d.out_f32_coff = 0;
+    d.out_hl = out_hl; d.out_hl_plane = (long long)BP * hl_stride; d.out_hl_stride = hl_stride; d.out_hl_coff = hl_coff;
+    d.aux0 = aux0; d.aux0_stride = 128; d.aux1 = aux1; d.aux1_stride = 128;
+    d.out2_hl = out2_hl; d.out2_hl_plane = (long long)BP * 128; d.out2_hl_stride = 128;
+    return conv2d_tc(d, st);
   };
 
   const float* flow_full = io->init_flow;
@@ -345,38 +408,72 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       SCF_TRY(check_launch("mul_mask_kernel"));
       menc_flow = F(ws.flowm);
     }
-    // lookup                                                              (:198-201)
-    SCF_TRY(scf_corr_lookup(levels, cfg->num_levels, cfg->radius, F(ws.flow8), cfg->mask_corr ? F(ws.maskprev) : nullptr,
-                            F(ws.corr), ws.corr_stride, 0, B, H8, W8, st));
-    // motion encoder                                                      (raft_decoder.py:152-166)
-    const int corr_ch = a.pc[PC_CORR0].cin;
-    SCF_TRY(conv(PC_CORR0, {{F(ws.corr), ws.corr_stride, 0, corr_ch}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.c1), 256, 0));
-    SCF_TRY(conv(PC_CORR1, {{F(ws.c1), 256, 0, 256}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.cf), 256, 0));
-    SCF_TRY(conv(PC_FLOW0, {{menc_flow, 2, 0, 2}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.f1), 128, 0));
-    SCF_TRY(conv(PC_FLOW1, {{F(ws.f1), 128, 0, 128}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.cf), 256, 192));
-    SCF_TRY(conv(PC_OUT0, {{F(ws.cf), 256, 0, 256}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.motion), 128, 0));
-    SCF_TRY(scf_resize_bilinear(menc_flow, nullptr, (long long)P * 2, 1, (long long)W8 * 2, 2, H8, W8, F(ws.motion) + 126,
-                                (long long)P * 128, 1, (long long)W8 * 128, 128, H8, W8, B, 2, 1.f, st));
-    // SepConvGRU                                                          (raft_decoder.py:235-253)
-    for (int pass = 0; pass < 2; ++pass) {
-      float* hin = F(ws.h[pass]);
-      float* hout = F(ws.h[pass ^ 1]);
-      SCF_TRY(conv(pass == 0 ? PC_ZR0 : PC_ZR1, {{hin, 128, 0, 128}, {F(ws.cxt), 128, 0, 128}, {F(ws.motion), 128, 0, 128}},
-                   H8, W8, H8, W8, 1, SCF_ACT_SIGMOID, F(ws.z), 128, 0, SCF_EPI_GRU_ZR, hin, nullptr, F(ws.rh)));
-      SCF_TRY(conv(pass == 0 ? PC_Q0 : PC_Q1, {{F(ws.rh), 128, 0, 128}, {F(ws.cxt), 128, 0, 128}, {F(ws.motion), 128, 0, 128}},
-                   H8, W8, H8, W8, 1, SCF_ACT_TANH, hout, 128, 0, SCF_EPI_GRU_Q, hin, F(ws.z), nullptr));
+    if (tcp) {
+      // ---------------- tensor-core path: activations live as split-bf16 planes
+      SCF_TRY(scf_split_copy(menc_flow, 2, 0, S(ws.s_motion), (long long)BP * 128, 128, 126, (long long)BP, 2, st));
+      SCF_TRY(scf_corr_lookup_split(levels, cfg->num_levels, cfg->radius, F(ws.flow8), cfg->mask_corr ? F(ws.maskprev) : nullptr,
+                                    S(ws.s_corr), (long long)BP * ws.corr_stride_s, ws.corr_stride_s, B, H8, W8, st));
+      SCF_TRY(convtc(PC_CORR0, {{S(ws.s_corr), ws.corr_stride_s, 0, ws.corr_stride_s}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_c1), 256, 0));
+      SCF_TRY(convtc(PC_CORR1, {{S(ws.s_c1), 256, 0, 256}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_cf), 256, 0));
+      SCF_TRY(conv(PC_FLOW0, {{menc_flow, 2, 0, 2}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, nullptr, 128, 0, SCF_EPI_ACT, nullptr, nullptr,
+                   nullptr, S(ws.s_f1), 128));
+      SCF_TRY(convtc(PC_FLOW1, {{S(ws.s_f1), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_cf), 256, 192));
+      SCF_TRY(convtc(PC_OUT0, {{S(ws.s_cf), 256, 0, 256}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_motion), 128, 0));
+      for (int pass = 0; pass < 2; ++pass) {
+        SCF_TRY(convtc(pass == 0 ? PC_ZR0 : PC_ZR1, {{S(ws.s_h[pass]), 128, 0, 128}, {S(ws.s_cxt), 128, 0, 128}, {S(ws.s_motion), 128, 0, 128}},
+                       SCF_ACT_SIGMOID, F(ws.z), 128, nullptr, 0, 0, SCF_EPI_GRU_ZR, F(ws.h[pass]), nullptr, S(ws.s_rh)));
+        SCF_TRY(convtc(pass == 0 ? PC_Q0 : PC_Q1, {{S(ws.s_rh), 128, 0, 128}, {S(ws.s_cxt), 128, 0, 128}, {S(ws.s_motion), 128, 0, 128}},
+                       SCF_ACT_TANH, F(ws.h[pass ^ 1]), 128, S(ws.s_h[pass ^ 1]), 128, 0, SCF_EPI_GRU_Q, F(ws.h[pass]), F(ws.z), nullptr));
+      }
+      SCF_TRY(convtc(PC_HEADS, {{S(ws.s_h[0]), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_hd), 512, 0));
+      SCF_TRY(convtc(PC_FHP, {{S(ws.s_hd), 512, 0, 256}}, SCF_ACT_NONE, F(ws.dflow), 2, nullptr, 0, 0));
+      SCF_TRY(convtc(PC_MHP, {{S(ws.s_hd), 512, 256, 256}}, SCF_ACT_SIGMOID, F(ws.mask8), 1, nullptr, 0, 0));
+      if (cfg->pose_head) {
+        SCF_TRY(conv(PC_DFE0, {{F(ws.dflow), 2, 0, 2}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, nullptr, 128, 0, SCF_EPI_ACT, nullptr, nullptr,
+                     nullptr, S(ws.s_df1), 128));
+        SCF_TRY(convtc(PC_DFE1, {{S(ws.s_df1), 128, 0, 128}}, SCF_ACT_RELU, F(ws.df2), 64, nullptr, 0, 0));
+        SCF_TRY(conv(PC_ME0, {{F(ws.mask8), 1, 0, 1}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, nullptr, 64, 0, SCF_EPI_ACT, nullptr, nullptr,
+                     nullptr, S(ws.s_mf1), 64));
+        SCF_TRY(convtc(PC_ME1, {{S(ws.s_mf1), 64, 0, 64}}, SCF_ACT_RELU, F(ws.mf2), 32, nullptr, 0, 0));
+      }
+    } else {
+      // lookup                                                              (:198-201)
+      SCF_TRY(scf_corr_lookup(levels, cfg->num_levels, cfg->radius, F(ws.flow8), cfg->mask_corr ? F(ws.maskprev) : nullptr,
+                              F(ws.corr), ws.corr_stride, 0, B, H8, W8, st));
+      // motion encoder                                                      (raft_decoder.py:152-166)
+      const int corr_ch = a.pc[PC_CORR0].cin;
+      SCF_TRY(conv(PC_CORR0, {{F(ws.corr), ws.corr_stride, 0, corr_ch}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.c1), 256, 0));
+      SCF_TRY(conv(PC_CORR1, {{F(ws.c1), 256, 0, 256}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.cf), 256, 0));
+      SCF_TRY(conv(PC_FLOW0, {{menc_flow, 2, 0, 2}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.f1), 128, 0));
+      SCF_TRY(conv(PC_FLOW1, {{F(ws.f1), 128, 0, 128}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.cf), 256, 192));
+      SCF_TRY(conv(PC_OUT0, {{F(ws.cf), 256, 0, 256}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.motion), 128, 0));
+      SCF_TRY(scf_resize_bilinear(menc_flow, nullptr, (long long)P * 2, 1, (long long)W8 * 2, 2, H8, W8, F(ws.motion) + 126,
+                                  (long long)P * 128, 1, (long long)W8 * 128, 128, H8, W8, B, 2, 1.f, st));
+      // SepConvGRU                                                          (raft_decoder.py:235-253)
+      for (int pass = 0; pass < 2; ++pass) {
+        float* hin = F(ws.h[pass]);
+        float* hout = F(ws.h[pass ^ 1]);
+        SCF_TRY(conv(pass == 0 ? PC_ZR0 : PC_ZR1, {{hin, 128, 0, 128}, {F(ws.cxt), 128, 0, 128}, {F(ws.motion), 128, 0, 128}},
+                     H8, W8, H8, W8, 1, SCF_ACT_SIGMOID, F(ws.z), 128, 0, SCF_EPI_GRU_ZR, hin, nullptr, F(ws.rh)));
+        SCF_TRY(conv(pass == 0 ? PC_Q0 : PC_Q1, {{F(ws.rh), 128, 0, 128}, {F(ws.cxt), 128, 0, 128}, {F(ws.motion), 128, 0, 128}},
+                     H8, W8, H8, W8, 1, SCF_ACT_TANH, hout, 128, 0, SCF_EPI_GRU_Q, hin, F(ws.z), nullptr));
+      }
+      float* h = F(ws.h[0]);
+      // flow / mask heads                                                   (scflow_decoder.py:210-213)
+      SCF_TRY(conv(PC_HEADS, {{h, 128, 0, 128}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.hd), 512, 0));
+      SCF_TRY(conv(PC_FHP, {{F(ws.hd), 512, 0, 256}}, H8, W8, H8, W8, 1, SCF_ACT_NONE, F(ws.dflow), 2, 0));
+      SCF_TRY(conv(PC_MHP, {{F(ws.hd), 512, 256, 256}}, H8, W8, H8, W8, 1, SCF_ACT_SIGMOID, F(ws.mask8), 1, 0));
+      if (cfg->pose_head) {
+        // delta-flow / mask encoders                                        (:216-217)
+        SCF_TRY(conv(PC_DFE0, {{F(ws.dflow), 2, 0, 2}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.df1), 128, 0));
+        SCF_TRY(conv(PC_DFE1, {{F(ws.df1), 128, 0, 128}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.df2), 64, 0));
+        SCF_TRY(conv(PC_ME0, {{F(ws.mask8), 1, 0, 1}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.mf1), 64, 0));
+        SCF_TRY(conv(PC_ME1, {{F(ws.mf1), 64, 0, 64}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.mf2), 32, 0));
+      }
     }
     float* h = F(ws.h[0]);
-    // flow / mask heads                                                   (scflow_decoder.py:210-213)
-    SCF_TRY(conv(PC_HEADS, {{h, 128, 0, 128}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.hd), 512, 0));
-    SCF_TRY(conv(PC_FHP, {{F(ws.hd), 512, 0, 256}}, H8, W8, H8, W8, 1, SCF_ACT_NONE, F(ws.dflow), 2, 0));
-    SCF_TRY(conv(PC_MHP, {{F(ws.hd), 512, 256, 256}}, H8, W8, H8, W8, 1, SCF_ACT_SIGMOID, F(ws.mask8), 1, 0));
     if (cfg->pose_head) {
-      // delta-flow / mask encoders + pose regressor                       (:216-219, pose_head.py:201-211)
-      SCF_TRY(conv(PC_DFE0, {{F(ws.dflow), 2, 0, 2}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.df1), 128, 0));
-      SCF_TRY(conv(PC_DFE1, {{F(ws.df1), 128, 0, 128}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.df2), 64, 0));
-      SCF_TRY(conv(PC_ME0, {{F(ws.mask8), 1, 0, 1}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.mf1), 64, 0));
-      SCF_TRY(conv(PC_ME1, {{F(ws.mf1), 64, 0, 64}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.mf2), 32, 0));
+      // pose regressor                                                    (:218-219, pose_head.py:201-211)
       const int h1 = (H8 - 1) / 2 + 1, w1 = (W8 - 1) / 2 + 1, h2 = (h1 - 1) / 2 + 1, w2 = (w1 - 1) / 2 + 1,
                 h3 = (h2 - 1) / 2 + 1, w3 = (w2 - 1) / 2 + 1;
       SCF_TRY(conv(PC_PH0, {{h, 128, 0, 128}, {F(ws.df2), 64, 0, 64}, {F(ws.mf2), 32, 0, 32}}, H8, W8, h1, w1, 2, SCF_ACT_NONE,
@@ -414,7 +511,8 @@ int scf_decoder_launch_count(const scf_decoder_cfg* cfg, int iters) {
   int per_iter = 1 /*down8*/ + 1 /*lookup*/ + 6 /*menc*/ + 4 /*gru*/ + 3 /*heads*/ + 2 /*up8*/ + 2 /*pose upd + reproject*/;
   per_iter += cfg->pose_head ? 4 + 6 + 3 : 1;
   per_iter += cfg->mask_flow ? 1 : 0;
-  int once = 2 /*nchw->nhwc feat_render + level0 (fp32 build)*/ + (cfg->num_levels - 1) + 1 /*unproject*/ + 2 /*h, cxt*/;
+  int once = (cfg->precision == 1 ? 3 : 2) /*layout change of the feature maps + level 0*/ + (cfg->num_levels - 1) + 1 /*unproject*/ +
+             2 /*h, cxt*/;
   if (cfg->mask_corr || cfg->mask_flow) once += 1;
   return once + per_iter * iters;
 }
@@ -424,9 +522,39 @@ int scf_decoder_launch_count(const scf_decoder_cfg* cfg, int iters) {
 namespace scf {
 int corr_build_f32(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
                    float* const* levels, void* scratch, cudaStream_t st);
+
+// tcgen05 build: both feature maps are transposed to pixel-major split-bf16 ([2][B][P][C], K-major for both GEMM
+// operands); level 0 = batched GEMM  f1[b] (P x C) * f2[b]^T (C x P) / sqrt(C)  on the tensor cores, written once as
+// fp32; levels 1.. are the reference's successive floor 2x2 means.
+static int corr_build_tc(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
+                         float* const* levels, void* scratch, cudaStream_t st) {
+  const int P = H8 * W8;
+  SCF_REQUIRE(C % 8 == 0 && P % 16 == 0, SCF_ERR_UNSUPPORTED, "scf_corr_build(tc): C %% 8 and H8*W8 %% 16 required");
+  char* sc = reinterpret_cast<char*>(scratch);
+  const long long plane = (long long)B * P * C;
+  void* f1s = sc;
+  void* f2s = sc + (size_t)plane * 2 * 2;
+  SCF_TRY(scf_nchw_to_nhwc_split(feat_render, f1s, plane, C, 0, nullptr, 0, B, C, H8, W8, st));
+  SCF_TRY(scf_nchw_to_nhwc_split(feat_real, f2s, plane, C, 0, nullptr, 0, B, C, H8, W8, st));
+  scf_tc_conv_desc d = {};
+  d.seg[0].ptr = f1s; d.seg[0].plane_stride = plane; d.seg[0].stride = C; d.seg[0].coff = 0; d.seg[0].nch = C;
+  d.nseg = 1;
+  d.B = B; d.H = H8; d.W = W8; d.kh = d.kw = 1;
+  d.w = f2s; d.cin_pad = C; d.cout_pad = P; d.cout = P; d.w_batched = 1;
+  d.bias = nullptr; d.scale = 1.0f / sqrtf((float)C); d.epi = SCF_EPI_ACT; d.act = SCF_ACT_NONE;
+  d.out_f32 = levels[0]; d.out_f32_stride = P; d.out_f32_coff = 0;
+  SCF_TRY(conv2d_tc(d, st));
+  int hl = H8, wl = W8;
+  for (int l = 1; l < num_levels; ++l) {
+    SCF_TRY(avgpool2(levels[l - 1], levels[l], (long long)B * P, hl, wl, st));
+    hl /= 2; wl /= 2;
+  }
+  return 0;
+}
+
 int corr_build_dispatch(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
                         float* const* levels, void* scratch, int precision, cudaStream_t st) {
-  (void)precision;
+  if (precision == 1) return corr_build_tc(feat_render, feat_real, B, C, H8, W8, num_levels, levels, scratch, st);
   return corr_build_f32(feat_render, feat_real, B, C, H8, W8, num_levels, levels, scratch, st);
 }
 }  // namespace scf

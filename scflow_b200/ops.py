@@ -303,3 +303,19 @@ def conv2d_tc(segs: Sequence, packed_w: torch.Tensor, bias: Optional[torch.Tenso
         d.out2_hl, d.out2_hl_plane, d.out2_hl_stride = out2_hl.data_ptr(), out2_hl[0].numel(), out2_hl.shape[-1]
     check(_lib.load().scf_conv2d_tc(C.byref(d), stream_ptr()), 'scf_conv2d_tc')
     return out_f32 if out_f32 is not None else out_hl
+
+
+def make_tc_gru_zr_bench(h, cxt, mot, wz, wr, bias, z, rh):
+    """bench.py helper: a closure launching the GRU z|r tensor-core convolution (the dominant kernel) on prepared
+    buffers. h/cxt/mot: fp32 NHWC [B,H,W,128]; wz/wr: OIHW; returns (launch, kernel name, mma passes)."""
+    hs = split_nchw(h.permute(0, 3, 1, 2).contiguous())
+    cs = split_nchw(cxt.permute(0, 3, 1, 2).contiguous())
+    ms = split_nchw(mot.permute(0, 3, 1, 2).contiguous())
+    pw = pack_conv_weight_tc([wz, wr])
+    rhs = torch.zeros(2, *rh.shape, device=rh.device, dtype=torch.bfloat16)
+    kernel = (int(wz.shape[2]), int(wz.shape[3]))
+
+    def launch():
+        conv2d_tc([(hs, 0, 128), (cs, 0, 128), (ms, 0, 128)], pw, bias, 256, kernel, act='sigmoid', out_f32=z,
+                  epi=_lib.EPI_GRU_ZR, aux0=h, out2_hl=rhs)
+    return launch, 'conv_tc_kernel (GRU z|r 1x5, tcgen05 split-bf16, N=256, K=1920)', 3

@@ -12,6 +12,11 @@ NAMES = ['flow_from_pose', 'flow_from_pred', 'rotation', 'translation', 'mask', 
 # tolerances vs the fp32 CPU reference (px, px, -, mm, -, -, -). North star: flow EPE within 1e-3.
 TOL_FP32 = dict(flow_from_pose=3e-3, flow_from_pred=1e-3, rotation=2e-6, translation=3e-3, mask=2e-5, delta_rotation=5e-6,
                 delta_translation=5e-6)
+# per-element tolerances of the tcgen05 split-bf16 path (each product carries ~2^-16 relative error; the loop feeds
+# errors back through pose -> flow -> lookup). The mean-EPE bar (1e-3 px) is asserted separately below.
+TOL_BF16X3 = dict(flow_from_pose=2e-2, flow_from_pred=2e-2, rotation=2e-5, translation=5e-2, mask=1e-3, delta_rotation=1e-4,
+                  delta_translation=1e-4)
+TOLS = {0: TOL_FP32, 1: TOL_BF16X3}
 
 
 def _inputs(seed, b, h, w):
@@ -32,29 +37,33 @@ def _epe(a, b):
     return float((a - b).pow(2).sum(1).sqrt().mean())
 
 
+@pytest.mark.parametrize('precision', [0, 1])
 @pytest.mark.parametrize('name', ['decoder_256_b2_it4', 'decoder_256_b3_it8'])
-def test_decoder_matches_reference_golden(name):
+def test_decoder_matches_reference_golden(name, precision):
     g = load_golden(name)
     seed, b, h, w, iters = (int(g['meta/' + k]) for k in ('seed', 'batch', 'h', 'w', 'iters'))
-    dec, _ = build_decoder_from_oracle_weights(seed, iters)
+    dec, _ = build_decoder_from_oracle_weights(seed, iters, precision=precision)
     scene, f = _inputs(seed, b, h, w)
     outs = _call(dec, scene, f, b, h, w)
     assert len(outs) == 7 and all(len(o) == iters for o in outs)
+    worst = {}
     for nm, lst in zip(NAMES, outs):
         for i, t in enumerate(lst):
-            assert_matches_digest(g, f'{nm}/{i}', t, atol=TOL_FP32[nm])
+            worst[nm] = max(worst.get(nm, 0.), assert_matches_digest(g, f'{nm}/{i}', t, atol=TOLS[precision][nm]))
+    print(f'{name} precision={precision} worst abs err:', {k: f'{v:.2e}' for k, v in worst.items()})
 
 
-def test_decoder_480x640_identity_head_golden():
+@pytest.mark.parametrize('precision', [0, 1])
+def test_decoder_480x640_identity_head_golden(precision):
     g = load_golden('decoder_480x640_b1_it2')
     seed, b, h, w, iters = (int(g['meta/' + k]) for k in ('seed', 'batch', 'h', 'w', 'iters'))
-    dec, _ = build_decoder_from_oracle_weights(seed, iters)
+    dec, _ = build_decoder_from_oracle_weights(seed, iters, precision=precision)
     dec.identity_pose_head = True
     scene, f = _inputs(seed, b, h, w)
     outs = _call(dec, scene, f, b, h, w)
     for nm, lst in zip(NAMES, outs):
         for i, t in enumerate(lst):
-            assert_matches_digest(g, f'{nm}/{i}', t, atol=TOL_FP32[nm])
+            assert_matches_digest(g, f'{nm}/{i}', t, atol=TOLS[precision][nm])
     # the stock head cannot run here, exactly like the reference
     dec.identity_pose_head = False
     from scflow_b200 import ScfError
@@ -62,26 +71,32 @@ def test_decoder_480x640_identity_head_golden():
         _call(dec, scene, f, b, h, w)
 
 
-def test_decoder_flow_epe_vs_live_oracle():
+@pytest.mark.parametrize('precision', [0, 1])
+def test_decoder_flow_epe_vs_live_oracle(precision):
     """The north-star number: mean end-point error of every iteration's flows against the fp32 CPU reference path."""
     seed, b, iters = 7, 2, 8
-    dec, sd = build_decoder_from_oracle_weights(seed, iters)
+    dec, sd = build_decoder_from_oracle_weights(seed, iters, precision=precision)
     scene, f = _inputs(seed, b, 256, 256)
     outs = _call(dec, scene, f, b, 256, 256)
     with torch.no_grad():
         ref = O.decoder_forward(sd, f['feat_render'], f['feat_real'], f['h_feat'], f['cxt_feat'], scene['ref_rotation'],
                                 scene['ref_translation'], scene['depth'], scene['internel_k'], scene['label'],
                                 torch.zeros(b, 2, 256, 256), 0., iters=iters)
+    print(f'precision={precision}: pose-flow EPE/iter', [f'{_epe(outs[0][i].cpu(), ref[0][i]):.2e}' for i in range(iters)],
+          'pred-flow EPE/iter', [f'{_epe(outs[1][i].cpu(), ref[1][i]):.2e}' for i in range(iters)],
+          'max|dR|', f'{max(float((outs[2][i].cpu() - ref[2][i]).abs().max()) for i in range(iters)):.2e}',
+          'max|dt| mm', f'{max(float((outs[3][i].cpu() - ref[3][i]).abs().max()) for i in range(iters)):.2e}')
     for i in range(iters):
         assert _epe(outs[0][i].cpu(), ref[0][i]) < 1e-3, f'pose-flow EPE at iteration {i}'
         assert _epe(outs[1][i].cpu(), ref[1][i]) < 1e-3, f'pred-flow EPE at iteration {i}'
-        assert float((outs[2][i].cpu() - ref[2][i]).abs().max()) < 1e-5
-        assert float((outs[3][i].cpu() - ref[3][i]).abs().max()) < 5e-3       # mm
+        assert float((outs[2][i].cpu() - ref[2][i]).abs().max()) < (1e-5 if precision == 0 else 2e-5)
+        assert float((outs[3][i].cpu() - ref[3][i]).abs().max()) < (5e-3 if precision == 0 else 5e-2)       # mm
 
 
-def test_cuda_graph_replay_is_bit_identical():
+@pytest.mark.parametrize('precision', [0, 1])
+def test_cuda_graph_replay_is_bit_identical(precision):
     seed, b, iters = 9, 2, 3
-    dec, _ = build_decoder_from_oracle_weights(seed, iters)
+    dec, _ = build_decoder_from_oracle_weights(seed, iters, precision=precision)
     scene, f = _inputs(seed, b, 256, 256)
     eager = [[t.clone() for t in lst] for lst in _call(dec, scene, f, b, 256, 256)]
     dec.use_cuda_graph = True
@@ -122,10 +137,11 @@ def test_refiner_get_pose_config1_golden():
     assert torch.equal(res['rotations'][0], outs[2][-1]) and res['scores'][0].shape == (b,)
 
 
-def test_full_size_properties_b32():
+@pytest.mark.parametrize('precision', [0, 1])
+def test_full_size_properties_b32(precision):
     """BASELINE config 2 size (B=32, 8 iterations): properties that need no oracle run."""
     seed, b, iters = 13, 32, 8
-    dec, _ = build_decoder_from_oracle_weights(seed, iters)
+    dec, _ = build_decoder_from_oracle_weights(seed, iters, precision=precision)
     scene, f = _inputs(seed, b, 256, 256)
     scene['label'][:] = 4
     outs = _call(dec, scene, f, b, 256, 256)
@@ -146,6 +162,10 @@ def test_full_size_properties_b32():
     o2 = _call(dec, sub, fsub, 4, 256, 256)
     assert float((o2[2][-1] - outs[2][-1][8:12]).abs().max()) < 1e-5
     assert float((o2[3][-1] - outs[3][-1][8:12]).abs().max()) < 1e-2
+    if precision == 1:      # the two arithmetic paths agree at full size too
+        base, _ = build_decoder_from_oracle_weights(seed, iters, precision=0)
+        o0 = _call(base, scene, f, b, 256, 256)
+        assert _epe(outs[1][-1], o0[1][-1]) < 1e-3 and _epe(outs[0][-1], o0[0][-1]) < 1e-3
 
 
 def test_mask_options_run():

@@ -67,16 +67,19 @@ def test_conv2d_segments_and_slices(S):
     assert torch.all(got[..., :8] == -7.0) and torch.all(got[..., 48:] == -7.0)      # neighbours untouched
 
 
-@pytest.mark.parametrize('shape,C,levels', [((32, 32), 256, 4), ((8, 12), 64, 3), ((15, 20), 32, 3)])
-def test_corr_build_fp32(S, shape, C, levels):
-    f = O.make_features(3, 2, shape[0], shape[1], channels=C)
+@pytest.mark.parametrize('precision', [0, 1])
+@pytest.mark.parametrize('shape,C,levels', [((32, 32), 256, 4), ((8, 12), 64, 3), ((15, 20), 32, 3), ((60, 80), 256, 4)])
+def test_corr_build(S, shape, C, levels, precision):
+    if precision == 1 and (shape[0] * shape[1]) % 16:
+        pytest.skip('tensor-core build needs H8*W8 % 16 == 0')
+    f = O.make_features(3, 2 if shape[0] < 60 else 1, shape[0], shape[1], channels=C)
     ref = O.correlation_pyramid(f['feat_render'], f['feat_real'], levels)
-    got = S.ops.corr_build(f['feat_render'].cuda(), f['feat_real'].cuda(), levels, precision=0)
+    got = S.ops.corr_build(f['feat_render'].cuda(), f['feat_real'].cuda(), levels, precision=precision)
     assert len(got) == levels
     for l, (r, g) in enumerate(zip(ref, got)):
         assert g.shape == r.shape
-        assert float((g.cpu() - r).abs().max()) < 5e-5, f'level {l}'
-    mod = S.CorrelationPyramid(num_levels=levels)
+        assert float((g.cpu() - r).abs().max()) < (5e-5 if precision == 0 else 2e-4), f'level {l}'
+    mod = S.CorrelationPyramid(num_levels=levels, precision=precision)
     again = mod(f['feat_render'].cuda(), f['feat_real'].cuda())
     assert all(torch.equal(a, b) for a, b in zip(got, again))      # deterministic
 
@@ -110,7 +113,11 @@ def test_corr_lookup_ramp_kat(S):
     vol = (100. * torch.arange(h).view(h, 1) + torch.arange(w).view(1, w)).float().view(1, 1, h, w).repeat(h * w, 1, 1, 1)
     out = S.CorrLookup(radius=1)([vol.cuda()], torch.zeros(1, 2, h, w, device='cuda')).cpu()
     assert out[0, :, 4, 3].tolist()[:4] == [302., 402., 502., 303.]
-    assert out[0, :, 0, 0].tolist() == [0., 0., 0., 0., 0., 100., 0., 1., 101.]       # zeros padding off the border
+    # zeros padding off the border; the normalise/un-normalise round trip leaves ~6e-8 weights on some OOB-adjacent taps
+    # (SURVEY Appendix A.4), so compare with the oracle rather than exact zeros
+    ref = O.corr_lookup([vol], torch.zeros(1, 2, h, w), radius=1)
+    assert float((out - ref).abs().max()) < 1e-5
+    assert [round(v) for v in out[0, :, 0, 0].tolist()] == [0, 0, 0, 0, 0, 100, 0, 1, 101]
 
 
 def test_motion_encoder_gru_heads_modules(S):
@@ -187,7 +194,7 @@ def test_resize_bilinear_align_corners(S):
 
 def test_argument_errors_are_reported(S):
     from scflow_b200 import ScfError
-    with pytest.raises(ScfError, match='num_levels'):
+    with pytest.raises(ScfError, match='bad shape'):
         S.ops.corr_build(torch.zeros(1, 8, 4, 4, device='cuda'), torch.zeros(1, 8, 4, 4, device='cuda'), num_levels=9)
     with pytest.raises(ValueError):
         S.ops.corr_lookup_nhwc([torch.zeros(5, device='cuda')], torch.zeros(1, 4, 4, 2, device='cuda'), 4)
