@@ -12,6 +12,7 @@
 #include "scf_common.cuh"
 #include "scf_tc.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace scf {
 
@@ -28,6 +29,9 @@ struct TcParams {
   int B, H, W, kh, kw, ph, pw;
   int TW, TH, tiles_x, tiles_y;
   int BN, cout, num_taps, w_batched, stages, tmem_cols;
+  long long* dbg_times;        // optional [grid][8] globaltimer stamps (timing experiments only)
+  int debug;                   // timing experiments only (SCFLOW_TC_DEBUG): 1 skip A loads, 2 skip W loads, 4 skip MMAs
+  int cluster;                 // CTAs per cluster sharing one weight tile via TMA multicast (1 = none)
   const float* bias; float scale; int epi, act;
   float* out_f32; int out_f32_stride, out_f32_coff;
   __nv_bfloat16* out_hl; long long out_hl_plane; int out_hl_stride, out_hl_coff;
@@ -35,33 +39,70 @@ struct TcParams {
   __nv_bfloat16* out2_hl; long long out2_hl_plane; int out2_hl_stride;
 };
 
+// ---- compact epilogue helpers (the whole epilogue loop body must stay well inside the instruction cache: a first
+// version with runtime-switched activations and local-memory staging arrays was ~50 KB of SASS and ran 10x slower)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+template <int ACT>
+__device__ __forceinline__ float act_ct(float v) {
+  if (ACT == SCF_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == SCF_ACT_SIGMOID) return sigmoid_fast(v);
+  if (ACT == SCF_ACT_TANH) return tanh_fast(v);
+  return v;
+}
+
+__device__ __forceinline__ void load16(const float* src, float* d) {     // src 16 B aligned
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src) + i);
+    d[4 * i] = t.x; d[4 * i + 1] = t.y; d[4 * i + 2] = t.z; d[4 * i + 3] = t.w;
+  }
+}
+
 __device__ __forceinline__ void store_f32x16(float* dst, const float* v, int nvalid) {
   if (nvalid == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   } else {
-    for (int i = 0; i < nvalid; ++i) dst[i] = v[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) dst[i] = v[i];
   }
 }
 
 __device__ __forceinline__ void store_split16(__nv_bfloat16* hi_dst, long long plane, const float* v, int nvalid) {
-  __align__(16) __nv_bfloat16 hi[16];
-  __align__(16) __nv_bfloat16 lo[16];
+  uint32_t hi[8], lo[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) split_bf16(v[i], hi[i], lo[i]);
-  if (nvalid == 16 && (reinterpret_cast<uintptr_t>(hi_dst) & 15) == 0 && ((plane * 2) & 15) == 0) {
-    reinterpret_cast<uint4*>(hi_dst)[0] = reinterpret_cast<const uint4*>(hi)[0];
-    reinterpret_cast<uint4*>(hi_dst)[1] = reinterpret_cast<const uint4*>(hi)[1];
-    reinterpret_cast<uint4*>(hi_dst + plane)[0] = reinterpret_cast<const uint4*>(lo)[0];
-    reinterpret_cast<uint4*>(hi_dst + plane)[1] = reinterpret_cast<const uint4*>(lo)[1];
+  for (int i = 0; i < 8; ++i) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  if (nvalid == 16 && (reinterpret_cast<uintptr_t>(hi_dst) & 15) == 0) {
+    uint4* dh = reinterpret_cast<uint4*>(hi_dst);
+    uint4* dl = reinterpret_cast<uint4*>(hi_dst + plane);
+    dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
   } else {
-    for (int i = 0; i < nvalid; ++i) { hi_dst[i] = hi[i]; hi_dst[plane + i] = lo[i]; }
+    unsigned short* dh = reinterpret_cast<unsigned short*>(hi_dst);
+    unsigned short* dl = reinterpret_cast<unsigned short*>(hi_dst + plane);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) {
+        dh[i] = (unsigned short)(hi[i >> 1] >> ((i & 1) * 16));
+        dl[i] = (unsigned short)(lo[i >> 1] >> ((i & 1) * 16));
+      }
   }
 }
 
+template <int EPI, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmWs, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024 B alignment
   // [0,1024): barriers + TMEM pointer ; then `stages` x {A hi, A lo, W hi, W lo}
@@ -71,6 +112,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t tiles0 = smem_base + 1024;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto stamp = [&](int slot) {
+    if (p.dbg_times) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.dbg_times[((long long)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+    }
+  };
+  if (threadIdx.x == 0) stamp(0);
 
   // ---- tile coordinates
   const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -86,20 +135,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     prefetch_tmap(&tmA0);
     if (p.nseg > 1) prefetch_tmap(&tmA1);
     if (p.nseg > 2) prefetch_tmap(&tmA2);
-    prefetch_tmap(&tmW);
+    prefetch_tmap(p.cluster > 1 ? &tmWs : &tmW);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, (uint32_t)p.cluster);   // every CTA of the cluster releases the stage
     }
     mbar_init(bar_tmem, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
-  __syncthreads();
+  if (p.cluster > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers must exist before any multicast
   tc_fence_after();
+  const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) stamp(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -114,10 +166,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
             const uint32_t full = bar_full + 8 * stage;
-            mbar_arrive_expect_tx(full, stage_bytes);
+            mbar_arrive_expect_tx(full, ((p.debug & 1) ? 0u : 2 * TC_A_PLANE) + ((p.debug & 2) ? 0u : 2 * b_plane));
             const uint32_t a_dst = tiles0 + stage * stage_bytes;
-            tma_load_5d(a_dst, tm, full, cc * TC_BK, cx, cy, b, 0);
-            tma_load_4d(a_dst + 2 * TC_A_PLANE, &tmW, full, p.seg_wcoff[s] + cc * TC_BK, n0, p.w_batched ? b : tap, 0);
+            if (!(p.debug & 1)) tma_load_5d(a_dst, tm, full, cc * TC_BK, cx, cy, b, 0);
+            const int wk = p.seg_wcoff[s] + cc * TC_BK, wt = p.w_batched ? b : tap;
+            if (p.debug & 2) {
+            } else if (p.cluster == 1) {
+              tma_load_4d(a_dst + 2 * TC_A_PLANE, &tmW, full, wk, n0, wt, 0);
+            } else {
+              // this CTA fetches rows [crank*BN/cluster, +BN/cluster) of both planes and multicasts them to the cluster
+              const int rows = p.BN / p.cluster;
+              const uint32_t w_dst = a_dst + 2 * TC_A_PLANE + crank * rows * 128;
+              tma_load_4d_mc(w_dst, &tmWs, full, wk, n0 + crank * rows, wt, 0, cmask);
+              tma_load_4d_mc(w_dst + b_plane, &tmWs, full, wk, n0 + crank * rows, wt, 1, cmask);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -132,26 +194,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int c = 0; c < num_chunks; ++c) {
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
+        if (c == 0) stamp(2);
         const uint32_t a_addr = tiles0 + stage * stage_bytes;
         const uint64_t a_hi = make_smem_desc_sw128(a_addr), a_lo = make_smem_desc_sw128(a_addr + TC_A_PLANE);
         const uint64_t b_hi = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE);
         const uint64_t b_lo = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + b_plane);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
+        for (int k = 0; k < ((p.debug & 4) ? 0 : TC_BK / 16); ++k) {
           const uint64_t ko = (uint64_t)(k * 32 >> 4);     // 16 bf16 = 32 B along the swizzled 128 B row
           umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, (c > 0 || k > 0) ? 1u : 0u);
           umma_bf16(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
           umma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
         }
-        umma_commit(bar_empty + 8 * stage);       // frees the smem slot once these MMAs have read it
+        if (p.cluster == 1) umma_commit(bar_empty + 8 * stage);   // frees the smem slot once these MMAs have read it
+        else umma_commit_mc(bar_empty + 8 * stage, cmask);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
       umma_commit(bar_tmem);                      // accumulator complete
+      stamp(3);
     }
   } else {
     // ================= epilogue: warp w owns TMEM lanes 32*(w%4)..+31 ; lane = pixel row of the tile
     mbar_wait(bar_tmem, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) stamp(4);
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int h = row / p.TW, w = row - h * p.TW;
@@ -159,6 +225,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const bool valid = y < p.H && x < p.W;
     const long long pix = ((long long)b * p.H + y) * p.W + x;
     const int half = p.cout >> 1;
+#pragma unroll 1
     for (int g = 0; g < p.BN / 16; ++g) {
       float v[16];
       __syncwarp();
@@ -166,42 +233,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int nb = n0 + g * 16;
       if (!valid || nb >= p.cout) continue;
       const int nvalid = p.cout - nb < 16 ? p.cout - nb : 16;
+      if (p.bias) {                          // bias buffers are readable up to cout_pad (multiple of 16)
+        float bv[16];
+        load16(p.bias + nb, bv);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = v[i] * p.scale + ((p.bias && i < nvalid) ? __ldg(p.bias + nb + i) : 0.f);
-      if (p.epi == SCF_EPI_ACT) {
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], p.scale, bv[i]);
+      } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], p.act);
+        for (int i = 0; i < 16; ++i) v[i] *= p.scale;
+      }
+      if (EPI == SCF_EPI_ACT) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = act_ct<ACT>(v[i]);
         if (p.out_f32) store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, nvalid);
         if (p.out_hl) store_split16(p.out_hl + pix * p.out_hl_stride + p.out_hl_coff + nb, p.out_hl_plane, v, nvalid);
-      } else if (p.epi == SCF_EPI_GRU_ZR) {
+      } else if (EPI == SCF_EPI_GRU_ZR) {    // cout = 2*Ch, Ch % 16 == 0: a group is entirely z or entirely r
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 1.f / (1.f + expf(-v[i]));
-        if (nb < half) {           // z gate -> fp32 (read back by the q convolution's epilogue)
-          store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, nvalid);
-        } else {                   // r gate -> r*h as split-bf16, the q convolution's first input segment
-          const float* hp = p.aux0 + pix * p.aux0_stride + (nb - half);
+        for (int i = 0; i < 16; ++i) v[i] = sigmoid_fast(v[i]);
+        if (nb < half) {                     // z gate -> fp32 (read back by the q convolution's epilogue)
+          store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, 16);
+        } else {                             // r gate -> r*h as split-bf16, the q convolution's first input segment
+          float hv[16];
+          load16(p.aux0 + pix * p.aux0_stride + (nb - half), hv);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= (i < nvalid) ? __ldg(hp + i) : 0.f;
-          store_split16(p.out2_hl + pix * p.out2_hl_stride + (nb - half), p.out2_hl_plane, v, nvalid);
+          for (int i = 0; i < 16; ++i) v[i] *= hv[i];
+          store_split16(p.out2_hl + pix * p.out2_hl_stride + (nb - half), p.out2_hl_plane, v, 16);
         }
-      } else {                     // SCF_EPI_GRU_Q: h' = (1-z) h + z tanh(.)
-        const float* hp = p.aux0 + pix * p.aux0_stride + nb;
-        const float* zp = p.aux1 + pix * p.aux1_stride + nb;
+      } else {                               // SCF_EPI_GRU_Q: h' = (1-z) h + z tanh(.)   (cout % 16 == 0)
+        float hv[16], zv[16];
+        load16(p.aux0 + pix * p.aux0_stride + nb, hv);
+        load16(p.aux1 + pix * p.aux1_stride + nb, zv);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (i < nvalid) {
-            const float qv = tanhf(v[i]), hv = __ldg(hp + i), zv = __ldg(zp + i);
-            v[i] = (1.f - zv) * hv + zv * qv;
-          }
-        }
-        if (p.out_f32) store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, nvalid);
-        if (p.out_hl) store_split16(p.out_hl + pix * p.out_hl_stride + p.out_hl_coff + nb, p.out_hl_plane, v, nvalid);
+        for (int i = 0; i < 16; ++i) v[i] = (1.f - zv[i]) * hv[i] + zv[i] * tanh_fast(v[i]);
+        if (p.out_f32) store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, 16);
+        if (p.out_hl) store_split16(p.out_hl + pix * p.out_hl_stride + p.out_hl_coff + nb, p.out_hl_plane, v, 16);
       }
     }
   }
+  if (threadIdx.x == 64) stamp(5);
   tc_fence_before();
-  __syncthreads();
+  if (p.cluster > 1) cluster_sync_all(); else __syncthreads();   // no CTA may exit while peers can still signal it
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (threadIdx.x == 32) stamp(6);
 }
 
 // ------------------------------------------------------------------ prep kernels
@@ -315,7 +388,19 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   SCF_REQUIRE(d.out_f32 || d.out_hl || d.epi == SCF_EPI_GRU_ZR, SCF_ERR_ARG, "scf_conv2d_tc: no output given");
   if (d.epi == SCF_EPI_GRU_ZR)
     SCF_REQUIRE(d.out_f32 && d.aux0 && d.out2_hl && d.cout % 32 == 0, SCF_ERR_ARG, "scf_conv2d_tc: GRU_ZR needs out_f32 (z), aux0 (h), out2_hl (r*h)");
-  if (d.epi == SCF_EPI_GRU_Q) SCF_REQUIRE(d.aux0 && d.aux1, SCF_ERR_ARG, "scf_conv2d_tc: GRU_Q needs aux0 (h) and aux1 (z)");
+  if (d.epi == SCF_EPI_GRU_Q)
+    SCF_REQUIRE(d.aux0 && d.aux1 && d.cout % 16 == 0, SCF_ERR_ARG, "scf_conv2d_tc: GRU_Q needs aux0 (h), aux1 (z), cout %% 16 == 0");
+  if (d.epi != SCF_EPI_ACT)
+    SCF_REQUIRE(d.aux0_stride % 4 == 0 && reinterpret_cast<uintptr_t>(d.aux0) % 16 == 0 &&
+                    (d.epi != SCF_EPI_GRU_Q || (d.aux1_stride % 4 == 0 && reinterpret_cast<uintptr_t>(d.aux1) % 16 == 0)),
+                SCF_ERR_ALIGN, "scf_conv2d_tc: aux buffers must be 16B aligned with strides %% 4 == 0");
+  SCF_REQUIRE(!d.bias || reinterpret_cast<uintptr_t>(d.bias) % 16 == 0, SCF_ERR_ALIGN, "scf_conv2d_tc: bias must be 16B aligned");
+  if (d.out_hl)
+    SCF_REQUIRE((d.out_hl_plane * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(d.out_hl) % 16 == 0, SCF_ERR_ALIGN,
+                "scf_conv2d_tc: out_hl and its plane stride must be 16B aligned");
+  if (d.epi != SCF_EPI_ACT && d.out_f32)
+    SCF_REQUIRE(d.out_f32_stride % 4 == 0 && d.out_f32_coff % 4 == 0 && reinterpret_cast<uintptr_t>(d.out_f32) % 16 == 0,
+                SCF_ERR_ALIGN, "scf_conv2d_tc: GRU epilogues need 16B-aligned fp32 outputs");
 
   TcParams p = {};
   p.nseg = d.nseg;
@@ -339,7 +424,26 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.aux0 = d.aux0; p.aux0_stride = d.aux0_stride; p.aux1 = d.aux1; p.aux1_stride = d.aux1_stride;
   p.out2_hl = reinterpret_cast<__nv_bfloat16*>(d.out2_hl); p.out2_hl_plane = d.out2_hl_plane; p.out2_hl_stride = d.out2_hl_stride;
 
-  CUtensorMap tmA[3], tmW;
+  // cluster size: share the weight tile between CTAs of consecutive pixel tiles (same sample when weights are batched)
+  {
+    int cs = 1;
+    const char* env = getenv("SCFLOW_TC_CLUSTER");
+    int want = env ? atoi(env) : 4;
+    const int mt = p.tiles_x * p.tiles_y * d.B;
+    for (int c = 8; c >= 2; c >>= 1) {
+      if (c > want) continue;
+      if (mt % c != 0 || (p.BN / c) % 8 != 0 || p.BN % c != 0) continue;
+      if (d.w_batched && (p.tiles_x * p.tiles_y) % c != 0) continue;
+      cs = c;
+      break;
+    }
+    p.cluster = cs;
+    const char* dbg = getenv("SCFLOW_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+    const char* dt = getenv("SCFLOW_TC_DBG_TIMES");       // address of a device buffer, hex (timing experiments only)
+    p.dbg_times = dt ? reinterpret_cast<long long*>(strtoull(dt, nullptr, 16)) : nullptr;
+  }
+  CUtensorMap tmA[3], tmW, tmWs;
   int wcoff = 0;
   for (int s = 0; s < 3; ++s) {
     if (s >= d.nseg) { tmA[s] = tmA[0]; p.seg_chunks[s] = 0; p.seg_wcoff[s] = 0; continue; }
@@ -367,16 +471,45 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)p.BN, 1, 2};
     SCF_REQUIRE(reinterpret_cast<uintptr_t>(d.w) % 16 == 0, SCF_ERR_ALIGN, "scf_conv2d_tc: packed weight must be 16B aligned");
     SCF_TRY(encode_map(&tmW, d.w, 4, dims, str, box));
+    tmWs = tmW;
+    if (p.cluster > 1) {
+      cuuint32_t boxs[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.BN / p.cluster), 1, 1};
+      SCF_TRY(encode_map(&tmWs, d.w, 4, dims, str, boxs));
+    }
   }
   const int smem = 1024 + 1024 + p.stages * stage_bytes;
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
+  KernelFn kernel = nullptr;
+  if (d.epi == SCF_EPI_GRU_ZR) kernel = conv_tc_kernel<SCF_EPI_GRU_ZR, SCF_ACT_SIGMOID>;
+  else if (d.epi == SCF_EPI_GRU_Q) kernel = conv_tc_kernel<SCF_EPI_GRU_Q, SCF_ACT_TANH>;
+  else if (d.act == SCF_ACT_NONE) kernel = conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_NONE>;
+  else if (d.act == SCF_ACT_RELU) kernel = conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_RELU>;
+  else if (d.act == SCF_ACT_SIGMOID) kernel = conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_SIGMOID>;
+  else if (d.act == SCF_ACT_TANH) kernel = conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_TANH>;
+  SCF_REQUIRE(kernel != nullptr, SCF_ERR_ARG, "scf_conv2d_tc: bad epilogue / activation");
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    KernelFn all[6] = {conv_tc_kernel<SCF_EPI_GRU_ZR, SCF_ACT_SIGMOID>, conv_tc_kernel<SCF_EPI_GRU_Q, SCF_ACT_TANH>,
+                       conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_NONE>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_RELU>,
+                       conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_SIGMOID>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_TANH>};
+    for (KernelFn f : all) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      if (e != cudaSuccess) attr_err = e;
+    }
   });
   SCF_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(attr_err));
-  dim3 grid(p.tiles_x * p.tiles_y * d.B, cdiv(d.cout_pad, p.BN));
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA[0], tmA[1], tmA[2], tmW, p);
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(p.tiles_x * p.tiles_y * d.B, cdiv(d.cout_pad, p.BN));
+  lc.blockDim = dim3(TC_THREADS);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  lc.attrs = attr; lc.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&lc, kernel, tmA[0], tmA[1], tmA[2], tmW, tmWs, p);
+  if (le != cudaSuccess) { cudaGetLastError(); set_error("conv_tc_kernel launch (cluster %d): %s", p.cluster, cudaGetErrorString(le)); return (int)le; }
   return check_launch("conv_tc_kernel");
 }
 

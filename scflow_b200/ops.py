@@ -286,6 +286,8 @@ def conv2d_tc(segs: Sequence, packed_w: torch.Tensor, bias: Optional[torch.Tenso
     _req(packed_w, 'packed_w', torch.bfloat16)
     d.w = packed_w.data_ptr()
     d.cin_pad, d.cout_pad, d.cout, d.w_batched = packed_w.shape[-1], packed_w.shape[-2], cout, int(w_batched)
+    if bias is not None and bias.numel() % 16:      # the epilogue reads bias in aligned groups of 16
+        bias = torch.nn.functional.pad(bias, (0, 16 - bias.numel() % 16))
     d.bias = None if bias is None else bias.data_ptr()
     d.scale, d.epi, d.act = scale, epi, _lib.ACT[act]
     if out_f32 is not None:
