@@ -116,8 +116,9 @@ typedef struct scf_tc_seg {
 typedef struct scf_tc_conv_desc {
   scf_tc_seg seg[3];
   int nseg;
-  int B, H, W;             /* stride-1 'same' convolution: output spatial size == input */
-  int kh, kw;              /* padding = kh/2, kw/2 */
+  int B, H, W;             /* INPUT spatial size; output = (H + 2*(kh/2) - kh)/stride + 1 */
+  int kh, kw;              /* odd; padding = kh/2, kw/2 */
+  int stride;              /* 1 (0 is read as 1) or 2 */
   const void* w;           /* packed by scf_pack_conv_weight_tc: bf16 [2][taps][cout_pad][cin_pad] */
   int cin_pad, cout_pad, cout;
   int w_batched;           /* 1: the "tap" dimension of w indexes the sample (kh=kw=1; correlation build) */
@@ -165,6 +166,9 @@ int scf_corr_lookup_taps(int level, int radius, const float* flow8, int32_t* x0,
 /* in-place GroupNorm(num_groups, eps) + ReLU on NHWC [B, HW, C] */
 int scf_group_norm_relu(float* x, const float* gamma, const float* beta, int B, int HW, int C, int num_groups,
                         float eps, void* stream);
+/* same (C=128, 32 groups only) plus an optional split-bf16 copy of the result for a following tensor-core conv */
+int scf_group_norm_relu_split(float* x, const float* gamma, const float* beta, int B, int HW, int C, int num_groups,
+                              float eps, void* out_hl, long long plane_stride, void* stream);
 /* y[b, :] = act(W x[b, :] + bias), W row-major [O, I] */
 int scf_linear(const float* x, const float* w, const float* bias, float* y, int B, int I, int O, int act,
                void* stream);

@@ -44,7 +44,7 @@ class TcSeg(C.Structure):
 class TcConvDesc(C.Structure):
     _fields_ = [
         ('seg', TcSeg * 3), ('nseg', C.c_int),
-        ('B', C.c_int), ('H', C.c_int), ('W', C.c_int), ('kh', C.c_int), ('kw', C.c_int),
+        ('B', C.c_int), ('H', C.c_int), ('W', C.c_int), ('kh', C.c_int), ('kw', C.c_int), ('stride', C.c_int),
         ('w', c_void_p), ('cin_pad', C.c_int), ('cout_pad', C.c_int), ('cout', C.c_int), ('w_batched', C.c_int),
         ('bias', c_void_p), ('scale', C.c_float), ('epi', C.c_int), ('act', C.c_int),
         ('out_f32', c_void_p), ('out_f32_stride', C.c_int), ('out_f32_coff', C.c_int),
@@ -124,6 +124,8 @@ _SIGNATURES = {
                                   C.c_int, C.c_int, C.c_int, c_void_p]),
     'scf_corr_lookup_taps': (C.c_int, [C.c_int, C.c_int, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p]),
     'scf_group_norm_relu': (C.c_int, [c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_void_p]),
+    'scf_group_norm_relu_split': (C.c_int, [c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_void_p,
+                                            C.c_longlong, c_void_p]),
     'scf_linear': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
     'scf_pose_project': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),

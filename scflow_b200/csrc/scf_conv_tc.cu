@@ -26,8 +26,9 @@ constexpr int TC_MAX_STAGES = 4;
 
 struct TcParams {
   int nseg, seg_chunks[3], seg_wcoff[3];
-  int B, H, W, kh, kw, ph, pw;
-  int TW, TH, tiles_x, tiles_y;
+  int B, H, W, kh, kw, ph, pw;   // H, W: OUTPUT spatial size
+  int stride;                    // 1 or 2 (input is sampled at stride*out + tap - pad)
+  int TW, TH, TB, tiles_x, tiles_y;   // tile = TW x TH pixels x TB samples = 128 rows
   int BN, cout, num_taps, w_batched, stages, tmem_cols;
   long long* dbg_times;        // optional [grid][8] globaltimer stamps (timing experiments only)
   int debug;                   // timing experiments only (SCFLOW_TC_DEBUG): 1 skip A loads, 2 skip W loads, 4 skip MMAs
@@ -123,8 +124,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   // ---- tile coordinates
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int b = blockIdx.x / tiles_per_img;
-  const int tr = blockIdx.x - b * tiles_per_img;
+  const int b = (blockIdx.x / tiles_per_img) * p.TB;      // first sample of the tile
+  const int tr = blockIdx.x % tiles_per_img;
   const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
   const int x0 = tx * p.TW, y0 = ty * p.TH;
   const int n0 = blockIdx.y * p.BN;
@@ -160,7 +161,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint32_t phase = 0;
       for (int tap = 0; tap < p.num_taps; ++tap) {
         const int ky = tap / p.kw, kx = tap - ky * p.kw;
-        const int cx = x0 + kx - p.pw, cy = y0 + ky - p.ph;
+        const int cx = x0 * p.stride + kx - p.pw, cy = y0 * p.stride + ky - p.ph;
         for (int s = 0; s < p.nseg; ++s) {
           const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
           for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
@@ -220,10 +221,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (threadIdx.x == 64) stamp(4);
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int h = row / p.TW, w = row - h * p.TW;
+    const int bb = row / (p.TW * p.TH), rr = row - bb * (p.TW * p.TH);
+    const int h = rr / p.TW, w = rr - h * p.TW;
     const int y = y0 + h, x = x0 + w;
-    const bool valid = y < p.H && x < p.W;
-    const long long pix = ((long long)b * p.H + y) * p.W + x;
+    const bool valid = y < p.H && x < p.W && b + bb < p.B;
+    const long long pix = ((long long)(b + bb) * p.H + y) * p.W + x;
     const int half = p.cout >> 1;
 #pragma unroll 1
     for (int g = 0; g < p.BN / 16; ++g) {
@@ -354,11 +356,12 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box) {
+                      const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr) {
   EncodeTiledFn fn = get_encode_fn();
   SCF_REQUIRE(fn != nullptr, SCF_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, ones,
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
+                  elem_strides ? elem_strides : ones,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SCF_REQUIRE(r == CUDA_SUCCESS, SCF_ERR_ARG, "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dims %llu %llu %llu, box %u %u %u)",
@@ -367,14 +370,16 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
   return 0;
 }
 
-static void pick_tile(int H, int W, int& TW, int& TH) {
-  // TW*TH = 128; minimise padded area, prefer wide tiles (longer contiguous runs)
+static void pick_tile(int B, int H, int W, bool one_sample, int& TW, int& TH, int& TB) {
+  // TW*TH*TB = 128 rows; minimise the padded volume, prefer wide tiles (longer contiguous runs), then tall ones
   long long best = -1;
-  for (int tw = 128; tw >= 4; tw >>= 1) {
-    const int th = 128 / tw;
-    if (tw > 256 || th > 256) continue;
-    const long long area = (long long)cdiv(W, tw) * tw * cdiv(H, th) * th;
-    if (best < 0 || area < best) { best = area; TW = tw; TH = th; }
+  for (int tw = 128; tw >= 2; tw >>= 1) {
+    for (int th = 128 / tw; th >= 1; th >>= 1) {
+      const int tb = 128 / (tw * th);
+      if (one_sample && tb != 1) continue;
+      const long long vol = (long long)cdiv(W, tw) * tw * cdiv(H, th) * th * cdiv(B, tb) * tb;
+      if (best < 0 || vol < best) { best = vol; TW = tw; TH = th; TB = tb; }
+    }
   }
 }
 
@@ -404,9 +409,14 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
 
   TcParams p = {};
   p.nseg = d.nseg;
-  p.B = d.B; p.H = d.H; p.W = d.W; p.kh = d.kh; p.kw = d.kw; p.ph = d.kh / 2; p.pw = d.kw / 2;
-  pick_tile(d.H, d.W, p.TW, p.TH);
-  p.tiles_x = cdiv(d.W, p.TW); p.tiles_y = cdiv(d.H, p.TH);
+  const int stride = d.stride == 2 ? 2 : 1;
+  SCF_REQUIRE(d.stride == 0 || d.stride == 1 || d.stride == 2, SCF_ERR_ARG, "scf_conv2d_tc: stride must be 1 or 2");
+  p.stride = stride;
+  p.kh = d.kh; p.kw = d.kw; p.ph = d.kh / 2; p.pw = d.kw / 2;
+  p.B = d.B; p.H = (d.H + 2 * p.ph - d.kh) / stride + 1; p.W = (d.W + 2 * p.pw - d.kw) / stride + 1;
+  pick_tile(d.B, p.H, p.W, d.w_batched != 0, p.TW, p.TH, p.TB);
+  p.tiles_x = cdiv(p.W, p.TW); p.tiles_y = cdiv(p.H, p.TH);
+  const int m_tiles = p.tiles_x * p.tiles_y * cdiv(d.B, p.TB);
   p.BN = d.cout_pad <= 256 ? d.cout_pad : 256;
   p.cout = d.cout;
   p.num_taps = d.kh * d.kw;
@@ -428,8 +438,8 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   {
     int cs = 1;
     const char* env = getenv("SCFLOW_TC_CLUSTER");
-    int want = env ? atoi(env) : 4;
-    const int mt = p.tiles_x * p.tiles_y * d.B;
+    int want = env ? atoi(env) : 1;   // multicast measured no gain on B200 for these shapes (profiles/r01_summary.md)
+    const int mt = m_tiles;
     for (int c = 8; c >= 2; c >>= 1) {
       if (c > want) continue;
       if (mt % c != 0 || (p.BN / c) % 8 != 0 || p.BN % c != 0) continue;
@@ -456,8 +466,10 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     cuuint64_t dims[5] = {(cuuint64_t)sg.nch, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B, 2};
     cuuint64_t str[4] = {(cuuint64_t)sg.stride * 2, (cuuint64_t)d.W * sg.stride * 2, (cuuint64_t)d.H * d.W * sg.stride * 2,
                          (cuuint64_t)sg.plane_stride * 2};
-    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1, 2};
-    SCF_TRY(encode_map(&tmA[s], base, 5, dims, str, box));
+    // box = elements TRAVERSED per dimension; with element strides (1,s,s,1,1) it deposits TW x TH x TB pixels
+    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TB, 2};
+    cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
+    SCF_TRY(encode_map(&tmA[s], base, 5, dims, str, box, estr));
     p.seg_chunks[s] = cdiv(sg.nch, TC_BK);
     p.seg_wcoff[s] = wcoff;
     wcoff += sg.nch;
@@ -500,7 +512,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   });
   SCF_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(attr_err));
   cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3(p.tiles_x * p.tiles_y * d.B, cdiv(d.cout_pad, p.BN));
+  lc.gridDim = dim3(m_tiles, cdiv(d.cout_pad, p.BN));
   lc.blockDim = dim3(TC_THREADS);
   lc.dynamicSmemBytes = smem;
   lc.stream = st;

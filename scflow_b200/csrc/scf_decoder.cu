@@ -98,7 +98,7 @@ static void build_arena(const scf_decoder_cfg& cfg, Arena& a) {
   size_t boff = (off * 4 + 1023) / 1024 * 1024;
   for (int i = 0; i < PC_COUNT; ++i) {
     PCInfo& p = a.pc[i];
-    p.tc = (cfg.precision == 1 && p.cin >= 8 && i < PC_PH0) ? 1 : 0;
+    p.tc = (cfg.precision == 1 && p.cin >= 8) ? 1 : 0;
     p.cin_pad = (p.cin + 7) / 8 * 8;
     p.cout_pad = (p.cout + 15) / 16 * 16;
     p.tc_off = 0;
@@ -147,7 +147,7 @@ struct Workspace {
   size_t corr_scratch, lvl[8], pts4, flow8, flowm, maskprev, corr, c1, cf, f1, h[2], cxt, motion, z, rh, hd, dflow,
       mask8, df1, df2, mf1, mf2, p1, p2, p3, fc0, fc1;
   // precision 1: split-bf16 planes [2][B*P][C] (byte offsets) and their plane strides in elements
-  size_t s_corr, s_c1, s_cf, s_f1, s_h[2], s_cxt, s_motion, s_rh, s_hd, s_df1, s_mf1;
+  size_t s_corr, s_c1, s_cf, s_f1, s_h[2], s_cxt, s_motion, s_rh, s_hd, s_df1, s_mf1, s_df2, s_mf2, s_p1, s_p2;
   int corr_stride_s;
   int hl[8], wl[8];
   int corr_stride;
@@ -185,7 +185,8 @@ static void build_workspace(const scf_decoder_cfg& cfg, int B, int H, int W, Wor
     auto split = [&](int ch) { return take(BP * ch * 2 * 2); };
     w.s_corr = split(w.corr_stride_s); w.s_c1 = split(256); w.s_cf = split(256); w.s_f1 = split(128);
     w.s_h[0] = split(128); w.s_h[1] = split(128); w.s_cxt = split(128); w.s_motion = split(128); w.s_rh = split(128);
-    w.s_hd = split(512); w.s_df1 = split(128); w.s_mf1 = split(64);
+    w.s_hd = split(512); w.s_df1 = split(128); w.s_mf1 = split(64); w.s_df2 = split(64); w.s_mf2 = split(32);
+    w.s_p1 = take((BP / 4 + 64) * 128 * 2 * 2); w.s_p2 = take((BP / 16 + 64) * 128 * 2 * 2);
   }
   w.total_bytes = off;
 }
@@ -366,16 +367,18 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
   };
   // tensor-core convolution on split-bf16 buffers: segs = {plane base, channels per pixel, first channel, channels}
   struct SSeg { void* ptr; int stride, coff, nch; };
+  int tc_hin = H8, tc_win = W8, tc_stride = 1;      // geometry of the next convtc call (pose head overrides it)
   auto convtc = [&](int id, std::initializer_list<SSeg> segs, int act, float* out_f32, int f32_stride, void* out_hl,
                     int hl_stride, int hl_coff, int epi = SCF_EPI_ACT, const float* aux0 = nullptr, const float* aux1 = nullptr,
                     void* out2_hl = nullptr) -> int {
     const PCInfo& p = a.pc[id];
     scf_tc_conv_desc d = {};
     int n = 0;
-    for (const SSeg& sg : segs) { d.seg[n].ptr = sg.ptr; d.seg[n].plane_stride = (long long)BP * sg.stride; d.seg[n].stride = sg.stride;
+    const long long in_pix = (long long)B * tc_hin * tc_win;
+    for (const SSeg& sg : segs) { d.seg[n].ptr = sg.ptr; d.seg[n].plane_stride = in_pix * sg.stride; d.seg[n].stride = sg.stride;
                                   d.seg[n].coff = sg.coff; d.seg[n].nch = sg.nch; ++n; }
     d.nseg = n;
-    d.B = B; d.H = H8; d.W = W8; d.kh = p.kh; d.kw = p.kw;
+    d.B = B; d.H = tc_hin; d.W = tc_win; d.kh = p.kh; d.kw = p.kw; d.stride = tc_stride;
     d.w = reinterpret_cast<const char*>(packed) + p.tc_off; d.cin_pad = p.cin_pad; d.cout_pad = p.cout_pad; d.cout = p.cout;
     d.w_batched = 0;
     d.bias = p.src_b[0] >= 0 ? pw + p.b_off : nullptr;
@@ -431,10 +434,10 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       if (cfg->pose_head) {
         SCF_TRY(conv(PC_DFE0, {{F(ws.dflow), 2, 0, 2}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, nullptr, 128, 0, SCF_EPI_ACT, nullptr, nullptr,
                      nullptr, S(ws.s_df1), 128));
-        SCF_TRY(convtc(PC_DFE1, {{S(ws.s_df1), 128, 0, 128}}, SCF_ACT_RELU, F(ws.df2), 64, nullptr, 0, 0));
+        SCF_TRY(convtc(PC_DFE1, {{S(ws.s_df1), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_df2), 64, 0));
         SCF_TRY(conv(PC_ME0, {{F(ws.mask8), 1, 0, 1}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, nullptr, 64, 0, SCF_EPI_ACT, nullptr, nullptr,
                      nullptr, S(ws.s_mf1), 64));
-        SCF_TRY(convtc(PC_ME1, {{S(ws.s_mf1), 64, 0, 64}}, SCF_ACT_RELU, F(ws.mf2), 32, nullptr, 0, 0));
+        SCF_TRY(convtc(PC_ME1, {{S(ws.s_mf1), 64, 0, 64}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_mf2), 32, 0));
       }
     } else {
       // lookup                                                              (:198-201)
@@ -476,6 +479,23 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       // pose regressor                                                    (:218-219, pose_head.py:201-211)
       const int h1 = (H8 - 1) / 2 + 1, w1 = (W8 - 1) / 2 + 1, h2 = (h1 - 1) / 2 + 1, w2 = (w1 - 1) / 2 + 1,
                 h3 = (h2 - 1) / 2 + 1, w3 = (w2 - 1) / 2 + 1;
+      if (tcp) {
+        // stride-2 convolutions on the tensor cores (TMA element strides), GroupNorm emits the next conv's split-bf16 input
+        tc_stride = 2;
+        tc_hin = H8; tc_win = W8;
+        SCF_TRY(convtc(PC_PH0, {{S(ws.s_h[0]), 128, 0, 128}, {S(ws.s_df2), 64, 0, 64}, {S(ws.s_mf2), 32, 0, 32}}, SCF_ACT_NONE,
+                       F(ws.p1), 128, nullptr, 0, 0));
+        SCF_TRY(scf_group_norm_relu_split(F(ws.p1), pw + a.gn_w[0], pw + a.gn_b[0], B, h1 * w1, 128, 32, 1e-5f, S(ws.s_p1),
+                                          (long long)B * h1 * w1 * 128, st));
+        tc_hin = h1; tc_win = w1;
+        SCF_TRY(convtc(PC_PH1, {{S(ws.s_p1), 128, 0, 128}}, SCF_ACT_NONE, F(ws.p2), 128, nullptr, 0, 0));
+        SCF_TRY(scf_group_norm_relu_split(F(ws.p2), pw + a.gn_w[1], pw + a.gn_b[1], B, h2 * w2, 128, 32, 1e-5f, S(ws.s_p2),
+                                          (long long)B * h2 * w2 * 128, st));
+        tc_hin = h2; tc_win = w2;
+        SCF_TRY(convtc(PC_PH2, {{S(ws.s_p2), 128, 0, 128}}, SCF_ACT_NONE, F(ws.p3), 128, nullptr, 0, 0));
+        SCF_TRY(scf_group_norm_relu(F(ws.p3), pw + a.gn_w[2], pw + a.gn_b[2], B, h3 * w3, 128, 32, 1e-5f, st));
+        tc_stride = 1; tc_hin = H8; tc_win = W8;
+      } else {
       SCF_TRY(conv(PC_PH0, {{h, 128, 0, 128}, {F(ws.df2), 64, 0, 64}, {F(ws.mf2), 32, 0, 32}}, H8, W8, h1, w1, 2, SCF_ACT_NONE,
                    F(ws.p1), 128, 0));
       SCF_TRY(scf_group_norm_relu(F(ws.p1), pw + a.gn_w[0], pw + a.gn_b[0], B, h1 * w1, 128, 32, 1e-5f, st));
@@ -483,6 +503,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       SCF_TRY(scf_group_norm_relu(F(ws.p2), pw + a.gn_w[1], pw + a.gn_b[1], B, h2 * w2, 128, 32, 1e-5f, st));
       SCF_TRY(conv(PC_PH2, {{F(ws.p2), 128, 0, 128}}, h2, w2, h3, w3, 2, SCF_ACT_NONE, F(ws.p3), 128, 0));
       SCF_TRY(scf_group_norm_relu(F(ws.p3), pw + a.gn_w[2], pw + a.gn_b[2], B, h3 * w3, 128, 32, 1e-5f, st));
+      }
       SCF_TRY(scf_linear(F(ws.p3), pw + a.fc0_w, pw + a.fc0_b, F(ws.fc0), B, 2048, 1024, SCF_ACT_RELU, st));
       SCF_TRY(scf_linear(F(ws.fc0), pw + a.fc1_w, pw + a.fc1_b, F(ws.fc1), B, 1024, 256, SCF_ACT_RELU, st));
       SCF_TRY(scf_pose_project(F(ws.fc1), pw + a.rot_w, pw + a.rot_b, pw + a.tr_w, pw + a.tr_b, io->label, drot_k, dtrs_k, B,

@@ -1,6 +1,7 @@
 // Pose-regressor tail (models/head/pose_head.py:201-211): GroupNorm+ReLU on NHWC maps, the FC chain and the
 // class-selected rotation/translation projection. All tiny, latency-bound; weights stay L2-resident.
 #include "scf_common.cuh"
+#include "scf_tc.cuh"
 
 namespace scf {
 
@@ -35,6 +36,103 @@ __global__ void __launch_bounds__(256) group_norm_relu_kernel(float* __restrict_
     float* p = base + (long long)(i / cpg) * C + c;
     const float y = (*p - mean) * rstd * gamma[g * cpg + c] + beta[g * cpg + c];
     *p = fmaxf(y, 0.f);
+  }
+}
+
+// Fast path for C == 4*G (one float4 = one group; the pose head: C=128, G=32): one 256-thread block per sample,
+// thread t owns group t%32 on pixels t/32 + 8j -> fully coalesced 512 B rows; two-pass statistics; optional
+// split-bf16 copy of the result for a following tensor-core convolution.
+__global__ void __launch_bounds__(256) group_norm_relu_c4_kernel(float* __restrict__ x, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, int HW, float eps,
+                                                                 __nv_bfloat16* __restrict__ out_hl, long long plane) {
+  __shared__ float red[8][33];
+  __shared__ float stat[2][32];
+  const int b = blockIdx.x, g = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int C = 128;
+  float4* base = reinterpret_cast<float4*>(x + (long long)b * HW * C) + g;
+  float s = 0.f;
+  for (int p = r; p < HW; p += 8) { const float4 v = base[(long long)p * 32]; s += (v.x + v.y) + (v.z + v.w); }
+  red[r][g] = s;
+  __syncthreads();
+  if (r == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i][g]; stat[0][g] = t / (float)(HW * 4); }
+  __syncthreads();
+  const float mean = stat[0][g];
+  float q = 0.f;
+  for (int p = r; p < HW; p += 8) {
+    const float4 v = base[(long long)p * 32];
+    const float a = v.x - mean, bq = v.y - mean, c = v.z - mean, d = v.w - mean;
+    q += (a * a + bq * bq) + (c * c + d * d);
+  }
+  __syncthreads();
+  red[r][g] = q;
+  __syncthreads();
+  if (r == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i][g]; stat[1][g] = rsqrtf(t / (float)(HW * 4) + eps); }
+  __syncthreads();
+  const float rstd = stat[1][g];
+  const float4 ga = reinterpret_cast<const float4*>(gamma)[g], be = reinterpret_cast<const float4*>(beta)[g];
+  for (int p = r; p < HW; p += 8) {
+    float4 v = base[(long long)p * 32];
+    v.x = fmaxf((v.x - mean) * rstd * ga.x + be.x, 0.f);
+    v.y = fmaxf((v.y - mean) * rstd * ga.y + be.y, 0.f);
+    v.z = fmaxf((v.z - mean) * rstd * ga.z + be.z, 0.f);
+    v.w = fmaxf((v.w - mean) * rstd * ga.w + be.w, 0.f);
+    base[(long long)p * 32] = v;
+    if (out_hl) {
+      __nv_bfloat16 hi[4], lo[4];
+      tc::split_bf16(v.x, hi[0], lo[0]); tc::split_bf16(v.y, hi[1], lo[1]);
+      tc::split_bf16(v.z, hi[2], lo[2]); tc::split_bf16(v.w, hi[3], lo[3]);
+      __nv_bfloat16* o = out_hl + ((long long)b * HW + p) * C + g * 4;
+      *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(o + plane) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
+}
+
+// y[b,o] = act(W[o,:] . x[b,:] + bias[o]).  Block = 8 warps = 8 output rows; x is staged through shared memory in
+// [32 samples x 256] chunks (coalesced, read once per block); each lane keeps 32 per-sample partial sums and the
+// weight row is read exactly once per batch chunk. Replaces a first version whose warps each re-read all of x.
+constexpr int LIN_KC = 256;
+__global__ void __launch_bounds__(256) linear_smem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ y, int B, int I,
+                                                          int O, int act) {
+  __shared__ __align__(16) float xs[32][LIN_KC];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int o = blockIdx.x * 8 + wid;
+  const float* wr = w + (long long)(o < O ? o : O - 1) * I;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    const int nb = B - b0 < 32 ? B - b0 : 32;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int k0 = 0; k0 < I; k0 += LIN_KC) {
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < 32 * (LIN_KC / 4); idx += 256) {
+        const int bb = idx / (LIN_KC / 4), c4 = idx - bb * (LIN_KC / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bb < nb && k0 + c4 * 4 < I) v = __ldg(reinterpret_cast<const float4*>(x + (long long)(b0 + bb) * I + k0) + c4);
+        reinterpret_cast<float4*>(&xs[bb][0])[c4] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int h = 0; h < LIN_KC / 128; ++h) {
+        const int k = h * 128 + lane * 4;
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + k < I) wv = __ldg(reinterpret_cast<const float4*>(wr + k0 + k));
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float4 xv = *reinterpret_cast<const float4*>(&xs[j][k]);
+          acc[j] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[j]))));
+        }
+      }
+    }
+    // lane j ends up with the full sum of sample j (butterfly transpose-reduce)
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float t = warp_sum(acc[j]);
+      if (lane == j) mine = t;
+    }
+    if (o < O && lane < nb) y[(long long)(b0 + lane) * O + o] = act_apply(mine + (bias ? bias[o] : 0.f), act);
   }
 }
 
@@ -104,10 +202,24 @@ __global__ void __launch_bounds__(256) pose_project_kernel(const float* __restri
 
 extern "C" {
 
+int scf_group_norm_relu_split(float* x, const float* gamma, const float* beta, int B, int HW, int C, int num_groups, float eps,
+                              void* out_hl, long long plane_stride, void* stream) {
+  SCF_REQUIRE(x && gamma && beta && B > 0 && HW > 0, SCF_ERR_ARG, "scf_group_norm_relu_split: bad args");
+  SCF_REQUIRE(C == 128 && num_groups == 32, SCF_ERR_UNSUPPORTED, "scf_group_norm_relu_split: C=128, 32 groups only");
+  SCF_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(gamma) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(beta) % 16 == 0, SCF_ERR_ALIGN, "scf_group_norm_relu_split: 16B alignment required");
+  scf::group_norm_relu_c4_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, HW, eps,
+                                                                     reinterpret_cast<__nv_bfloat16*>(out_hl), plane_stride);
+  return scf::check_launch("group_norm_relu_c4_kernel");
+}
+
 int scf_group_norm_relu(float* x, const float* gamma, const float* beta, int B, int HW, int C, int num_groups, float eps,
                         void* stream) {
   SCF_REQUIRE(x && gamma && beta && B > 0 && HW > 0 && C > 0 && num_groups > 0 && C % num_groups == 0, SCF_ERR_ARG,
               "scf_group_norm_relu: bad args");
+  if (C == 128 && num_groups == 32 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(gamma) % 16 == 0 &&
+      reinterpret_cast<uintptr_t>(beta) % 16 == 0)
+    return scf_group_norm_relu_split(x, gamma, beta, B, HW, C, num_groups, eps, nullptr, 0, stream);
   const int warps = B * num_groups;
   scf::group_norm_relu_kernel<<<scf::cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, B, HW, C, num_groups,
                                                                                     eps);
@@ -118,8 +230,8 @@ int scf_linear(const float* x, const float* w, const float* bias, float* y, int 
   SCF_REQUIRE(x && w && y && B > 0 && I > 0 && O > 0, SCF_ERR_ARG, "scf_linear: bad args");
   SCF_REQUIRE(I % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(w) % 16 == 0,
               SCF_ERR_ALIGN, "scf_linear: I must be a multiple of 4 and x/w 16B aligned");
-  scf::linear_kernel<<<scf::cdiv(O, 8), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, I, O, act);
-  return scf::check_launch("linear_kernel");
+  scf::linear_smem_kernel<<<scf::cdiv(O, 8), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, I, O, act);
+  return scf::check_launch("linear_smem_kernel");
 }
 
 int scf_pose_project(const float* x, const float* rot_w, const float* rot_b, const float* tr_w, const float* tr_b,

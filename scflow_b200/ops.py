@@ -273,7 +273,7 @@ def pack_conv_weight_tc(weights: Sequence[torch.Tensor], cin_pad: Optional[int] 
 def conv2d_tc(segs: Sequence, packed_w: torch.Tensor, bias: Optional[torch.Tensor], cout: int, kernel, act: str = 'none',
               out_f32: Optional[torch.Tensor] = None, out_f32_coff: int = 0, out_hl: Optional[torch.Tensor] = None,
               out_hl_coff: int = 0, epi: int = _lib.EPI_ACT, aux0=None, aux1=None, out2_hl=None, scale: float = 1.0,
-              w_batched: bool = False):
+              w_batched: bool = False, stride: int = 1):
     """tcgen05 convolution. ``segs`` = [(split tensor [2,B,H,W,stride], coff, nch), ...]."""
     kh, kw = (kernel, kernel) if isinstance(kernel, int) else kernel
     d = TcConvDesc()
@@ -282,7 +282,7 @@ def conv2d_tc(segs: Sequence, packed_w: torch.Tensor, bias: Optional[torch.Tenso
         d.seg[n] = TcSeg(t.data_ptr(), t[0].numel(), t.shape[-1], coff, nch)
     d.nseg = len(segs)
     _, b, h, w, _ = segs[0][0].shape
-    d.B, d.H, d.W, d.kh, d.kw = b, h, w, kh, kw
+    d.B, d.H, d.W, d.kh, d.kw, d.stride = b, h, w, kh, kw, stride
     _req(packed_w, 'packed_w', torch.bfloat16)
     d.w = packed_w.data_ptr()
     d.cin_pad, d.cout_pad, d.cout, d.w_batched = packed_w.shape[-1], packed_w.shape[-2], cout, int(w_batched)

@@ -60,6 +60,22 @@ def test_conv_tc_matches_fp64(S, cin, cout, k, hw, b, act):
     assert err_hl < 1e-4
 
 
+@pytest.mark.parametrize('cin,cout,hw,b,k', [(224, 128, (32, 32), 4, 3), (128, 128, (16, 16), 5, 3), (128, 128, (8, 8), 11, 3),
+                                            (64, 96, (64, 64), 2, 3), (64, 96, (64, 64), 2, 1), (96, 128, (30, 40), 2, 3)])
+def test_conv_tc_stride2(S, cin, cout, hw, b, k):
+    """Stride-2 convolutions (pose head, encoder down-sampling): TMA element strides; small maps pack several samples per tile."""
+    gen = torch.Generator().manual_seed(cin + cout + hw[0])
+    x = torch.randn(b, cin, *hw, generator=gen)
+    w = torch.randn(cout, cin, k, k, generator=gen) / math.sqrt(cin * k * k)
+    ref = F.conv2d(x.double(), w.double(), None, stride=2, padding=k // 2).float()
+    xs = S.ops.split_nchw(x.cuda())
+    ho, wo = ref.shape[-2:]
+    out = torch.full((b, ho, wo, cout), float('nan'), device='cuda')
+    S.ops.conv2d_tc([(xs, 0, cin)], S.ops.pack_conv_weight_tc([w.cuda()]), None, cout, k, out_f32=out, stride=2)
+    err = float((out.permute(0, 3, 1, 2).cpu() - ref).abs().max())
+    assert err < 5e-5, f'max err {err:.3e}'
+
+
 def test_conv_tc_segments_slices_and_gru_epilogues(S):
     from scflow_b200 import _lib
     gen = torch.Generator().manual_seed(3)
