@@ -125,7 +125,7 @@ typedef struct scf_tc_conv_desc {
   const float* bias; float scale; int epi, act;
   float* out_f32; int out_f32_stride, out_f32_coff;                     /* optional fp32 NHWC output */
   void* out_hl; long long out_hl_plane; int out_hl_stride, out_hl_coff; /* optional split-bf16 output */
-  const float* aux0; int aux0_stride; const float* aux1; int aux1_stride;
+  const float* aux0; int aux0_stride; const float* aux1; int aux1_stride;  /* EPI_ACT: aux0 = optional residual added before act */
   void* out2_hl; long long out2_hl_plane; int out2_hl_stride;           /* GRU_ZR: r*h as split-bf16 */
 } scf_tc_conv_desc;
 
@@ -193,6 +193,23 @@ int scf_reproject(const float* pts4, const float* K, const float* rot, const flo
 int scf_resize_bilinear(const float* src, const float* add, long long s_b, long long s_c, long long s_y, long long s_x,
                         int Hi, int Wi, float* dst, long long d_b, long long d_c, long long d_y, long long d_x, int Ho,
                         int Wo, int B, int C, float scale, void* stream);
+
+/* ---------------------------------------------------------------- RAFT encoder (feeds the loop) ----------- */
+/* RAFTEncoder 'Basic' (models/encoder/raft_encoder.py:286-314): 7x7/2 stem, three residual stages (64,96,128; strides
+ * 1,2,2; two BasicBlocks each, models/backbone/resnet.py:14-94), 1x1 to 256 channels at 1/8 resolution.
+ * 16 convolution units in network order: 0 conv1; 1-4 res_layer1.{0,1}.{conv1,conv2}; 5,6 res_layer2.0.{conv1,conv2};
+ * 7 res_layer2.0.downsample.0; 8,9 res_layer2.1.*; 10,11 res_layer3.0.*; 12 res_layer3.0.downsample.0; 13,14
+ * res_layer3.1.*; 15 conv2.  h_weights holds 6 device pointers per unit: conv weight (OIHW), conv bias, and - for
+ * norm = BN - the following BatchNorm's weight, bias, running_mean, running_var (NULL for IN / unit 15). */
+#define SCF_ENC_UNITS 16
+#define SCF_ENC_NORM_IN 0   /* InstanceNorm2d(affine=False), statistics computed per call */
+#define SCF_ENC_NORM_BN 1   /* BatchNorm2d in eval mode, folded into the packed weights */
+size_t scf_encoder_packed_bytes(void);
+size_t scf_encoder_workspace_bytes(int N, int H, int W);
+int scf_encoder_pack(int norm, const float* const* h_weights, void* packed, void* stream);
+/* images: NCHW fp32 [N,3,H,W]; out_nchw: fp32 [N,256,H/8,W/8] */
+int scf_encoder_forward(int norm, const void* packed, const float* images, int N, int H, int W, float* out_nchw,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- whole decoder loop --------------------- */
 enum scf_decoder_weight {

@@ -101,6 +101,18 @@ DECODER_WEIGHT_KEYS = [
 ]
 SCF_W_COUNT = len(DECODER_WEIGHT_KEYS)
 
+# RAFTEncoder conv units in the order of SCF_ENC_UNITS (include/scflow_b200.h): (conv module path, following norm path)
+ENCODER_UNITS = [('conv1', '{n}1')]
+for _stage in (1, 2, 3):
+    for _blk in (0, 1):
+        _q = f'res_layer{_stage}.{_blk}.'
+        ENCODER_UNITS.append((_q + 'conv1', _q + '{n}1'))
+        ENCODER_UNITS.append((_q + 'conv2', _q + '{n}2'))
+        if _blk == 0 and _stage > 1:
+            ENCODER_UNITS.append((_q + 'downsample.0', _q + 'downsample.1'))
+ENCODER_UNITS.append(('conv2', None))
+ENC_NORM_IN, ENC_NORM_BN = 0, 1
+
 _SIGNATURES = {
     'scf_abi_version': (C.c_int, []),
     'scf_last_error': (C.c_char_p, []),
@@ -135,6 +147,11 @@ _SIGNATURES = {
     'scf_resize_bilinear': (C.c_int, [c_void_p, c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
                                       C.c_int, c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_float, c_void_p]),
+    'scf_encoder_packed_bytes': (C.c_size_t, []),
+    'scf_encoder_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'scf_encoder_pack': (C.c_int, [C.c_int, C.POINTER(c_void_p), c_void_p, c_void_p]),
+    'scf_encoder_forward': (C.c_int, [C.c_int, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p, c_void_p, C.c_size_t,
+                                      c_void_p]),
     'scf_decoder_packed_bytes': (C.c_size_t, [C.POINTER(DecoderCfg)]),
     'scf_decoder_workspace_bytes': (C.c_size_t, [C.POINTER(DecoderCfg), C.c_int, C.c_int, C.c_int]),
     'scf_decoder_pack': (C.c_int, [C.POINTER(DecoderCfg), C.POINTER(c_void_p), c_void_p, c_void_p]),

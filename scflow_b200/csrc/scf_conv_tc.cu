@@ -245,6 +245,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int i = 0; i < 16; ++i) v[i] *= p.scale;
       }
       if (EPI == SCF_EPI_ACT) {
+        if (p.aux0) {                        // residual connection (encoder BasicBlock): added before the activation
+          float rv[16];
+          load16(p.aux0 + pix * p.aux0_stride + nb, rv);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += rv[i];
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = act_ct<ACT>(v[i]);
         if (p.out_f32) store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, nvalid);
@@ -395,7 +401,8 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     SCF_REQUIRE(d.out_f32 && d.aux0 && d.out2_hl && d.cout % 32 == 0, SCF_ERR_ARG, "scf_conv2d_tc: GRU_ZR needs out_f32 (z), aux0 (h), out2_hl (r*h)");
   if (d.epi == SCF_EPI_GRU_Q)
     SCF_REQUIRE(d.aux0 && d.aux1 && d.cout % 16 == 0, SCF_ERR_ARG, "scf_conv2d_tc: GRU_Q needs aux0 (h), aux1 (z), cout %% 16 == 0");
-  if (d.epi != SCF_EPI_ACT)
+  if (d.epi == SCF_EPI_ACT && d.aux0) SCF_REQUIRE(d.cout % 16 == 0, SCF_ERR_ARG, "scf_conv2d_tc: residual needs cout %% 16 == 0");
+  if (d.epi != SCF_EPI_ACT || d.aux0)
     SCF_REQUIRE(d.aux0_stride % 4 == 0 && reinterpret_cast<uintptr_t>(d.aux0) % 16 == 0 &&
                     (d.epi != SCF_EPI_GRU_Q || (d.aux1_stride % 4 == 0 && reinterpret_cast<uintptr_t>(d.aux1) % 16 == 0)),
                 SCF_ERR_ALIGN, "scf_conv2d_tc: aux buffers must be 16B aligned with strides %% 4 == 0");

@@ -1,0 +1,331 @@
+// RAFT 'Basic' feature / context encoder (models/encoder/raft_encoder.py:286-314, models/backbone/resnet.py:14-94,
+// 678-773) on the library's kernels: 7x7 stem on the fp32 CUDA-core conv (Cin=3), every 3x3 / 1x1 convolution on the
+// tcgen05 split-bf16 kernel (stride 2 through TMA element strides), InstanceNorm as deterministic two-stage
+// statistics + one fused normalise/ReLU/residual pass, eval-mode BatchNorm folded into the packed weights.
+// This is SURVEY.md §8(f) rank 1: the component feeding the refinement loop.
+#include "scf_common.cuh"
+#include "scf_tc.cuh"
+
+namespace scf {
+
+int conv2d_f32(const scf_conv_desc& d, cudaStream_t st);
+int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st);
+
+// ------------------------------------------------------------------ conv-unit table
+struct EncUnit { int cin, cout, k, stride; };
+static const EncUnit kUnits[SCF_ENC_UNITS] = {
+    {3, 64, 7, 2},                                                            // 0 stem conv1
+    {64, 64, 3, 1}, {64, 64, 3, 1}, {64, 64, 3, 1}, {64, 64, 3, 1},          // 1-4  res_layer1.{0,1}.{conv1,conv2}
+    {64, 96, 3, 2}, {96, 96, 3, 1}, {64, 96, 1, 2}, {96, 96, 3, 1}, {96, 96, 3, 1},      // 5-9  res_layer2 (7 = downsample)
+    {96, 128, 3, 2}, {128, 128, 3, 1}, {96, 128, 1, 2}, {128, 128, 3, 1}, {128, 128, 3, 1},  // 10-14 res_layer3 (12 = downsample)
+    {128, 256, 1, 1},                                                         // 15 conv2
+};
+
+struct EncArena {
+  size_t w_f32[SCF_ENC_UNITS];   // byte offsets: folded fp32 OIHW copy (source of both packings)
+  size_t bias[SCF_ENC_UNITS];    // folded bias, padded to a multiple of 16 floats
+  size_t packed[SCF_ENC_UNITS];  // unit 0: fp32 [K][ldw]; others: bf16 [2][taps][cout_pad][cin_pad]
+  int cin_pad[SCF_ENC_UNITS], cout_pad[SCF_ENC_UNITS], ldw0;
+  size_t total;
+};
+
+static void build_enc_arena(EncArena& a) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  for (int u = 0; u < SCF_ENC_UNITS; ++u) {
+    const EncUnit& e = kUnits[u];
+    a.cin_pad[u] = (e.cin + 7) / 8 * 8;
+    a.cout_pad[u] = (e.cout + 15) / 16 * 16;
+    a.w_f32[u] = take((size_t)e.cout * e.cin * e.k * e.k * 4);
+    a.bias[u] = take((size_t)a.cout_pad[u] * 4);
+    if (u == 0) { a.ldw0 = (e.cout + 3) / 4 * 4; a.packed[u] = take((size_t)e.k * e.k * e.cin * a.ldw0 * 4); }
+    else a.packed[u] = take((size_t)2 * e.k * e.k * a.cout_pad[u] * a.cin_pad[u] * 2);
+  }
+  a.total = off;
+}
+
+// w'[o,...] = w[o,...] * g[o] / sqrt(var[o] + eps) ; b'[o] = (b[o] - mean[o]) * g[o] / sqrt(var[o]+eps) + beta[o]
+__global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ g,
+                               const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ var,
+                               float eps, float* __restrict__ wo, float* __restrict__ bo, int O, int per_o) {
+  const int o = blockIdx.x;
+  const float s = g ? g[o] * rsqrtf(var[o] + eps) : 1.f;
+  for (int i = threadIdx.x; i < per_o; i += blockDim.x) wo[(long long)o * per_o + i] = w[(long long)o * per_o + i] * s;
+  if (threadIdx.x == 0) bo[o] = g ? ((b ? b[o] : 0.f) - mean[o]) * s + beta[o] : (b ? b[o] : 0.f);
+}
+
+// NCHW fp32 image -> NHWC fp32 (C=3)
+__global__ void image_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const long long r = idx / C;
+    const int p = (int)(r % HW);
+    const long long n = r / HW;
+    dst[idx] = src[(n * C + c) * HW + p];
+  }
+}
+
+// ---- InstanceNorm, stage 1: per (image, pixel-slice) partial sums of x and x^2 for every channel (deterministic)
+constexpr int IN_SLICES = 32;
+__global__ void __launch_bounds__(256) instnorm_partial_kernel(const float* __restrict__ x, float* __restrict__ part, int HW, int C) {
+  // grid (IN_SLICES, N); thread t owns channel quad (t % (C/4)) on pixels t/(C/4) + k*(256/(C/4))
+  __shared__ float4 rs[256], rq[256];
+  const int n = blockIdx.y, sl = blockIdx.x;
+  const int c4n = C >> 2, rows = 256 / c4n;
+  const int cq = threadIdx.x % c4n, r = threadIdx.x / c4n;
+  const int p0 = (int)((long long)HW * sl / IN_SLICES), p1 = (int)((long long)HW * (sl + 1) / IN_SLICES);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  if (r < rows)
+    for (int p = p0 + r; p < p1; p += rows) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((long long)n * HW + p) * C) + cq);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+    }
+  rs[threadIdx.x] = s; rq[threadIdx.x] = q;
+  __syncthreads();
+  if (r == 0) {
+    for (int i = 1; i < rows; ++i) {
+      const float4 a = rs[i * c4n + cq], b = rq[i * c4n + cq];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+    }
+    float* o = part + (((long long)n * IN_SLICES + sl) * 2) * C + cq * 4;
+    *reinterpret_cast<float4*>(o) = s;
+    *reinterpret_cast<float4*>(o + C) = q;
+  }
+}
+// stage 2: mean / rstd per (image, channel), combined in double
+__global__ void instnorm_finalize_kernel(const float* __restrict__ part, float* __restrict__ stat, int HW, int C, float eps, int N) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * C) return;
+  const int n = idx / C, c = idx - n * C;
+  double s = 0., q = 0.;
+  for (int sl = 0; sl < IN_SLICES; ++sl) {
+    s += part[(((long long)n * IN_SLICES + sl) * 2) * C + c];
+    q += part[(((long long)n * IN_SLICES + sl) * 2 + 1) * C + c];
+  }
+  const double mean = s / HW;
+  double var = q / HW - mean * mean;
+  if (var < 0.) var = 0.;
+  stat[(long long)idx * 2] = (float)mean;
+  stat[(long long)idx * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+// stage 3: y = [relu]( (x - mean) * rstd  [+ (r - rmean) * rrstd | + r] ) -> fp32 and/or split-bf16
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ stat,
+                                                             const float* __restrict__ res, const float* __restrict__ res_stat,
+                                                             int relu, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hl,
+                                                             long long plane, int HW, int C, long long total4) {
+  const int c4n = C >> 2;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
+    const int cq = (int)(idx % c4n);
+    const long long pix = idx / c4n;
+    const long long n = pix / HW;
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + idx);
+    float vv[4] = {v.x, v.y, v.z, v.w};
+    const float* st = stat + (n * C + cq * 4) * 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vv[i] = (vv[i] - st[2 * i]) * st[2 * i + 1];
+    if (res) {
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(res) + idx);
+      float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+      if (res_stat) {
+        const float* rt = res_stat + (n * C + cq * 4) * 2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rr[i] = (rr[i] - rt[2 * i]) * rt[2 * i + 1];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vv[i] += rr[i];
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vv[i] = fmaxf(vv[i], 0.f);
+    }
+    if (out_f32) reinterpret_cast<float4*>(out_f32)[idx] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    if (out_hl) {
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tc::split_bf16(vv[i], hi[i], lo[i]);
+      *reinterpret_cast<uint2*>(out_hl + idx * 4) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(out_hl + plane + idx * 4) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
+}
+
+struct EncWs {
+  size_t img, raw, raw2, xf[2], xs[2], ts, part, stat, stat2;
+  size_t total;
+};
+static void build_enc_ws(int N, int H, int W, EncWs& w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  const size_t p2 = (size_t)N * (H / 2) * (W / 2);
+  w.img = take((size_t)N * H * W * 3 * 4);
+  w.raw = take(p2 * 64 * 4); w.raw2 = take(p2 / 4 * 96 * 4 + 4096);
+  for (int i = 0; i < 2; ++i) { w.xf[i] = take(p2 * 64 * 4); w.xs[i] = take(p2 * 64 * 2 * 2); }
+  w.ts = take(p2 * 64 * 2 * 2);
+  w.part = take((size_t)N * IN_SLICES * 2 * 128 * 4); w.stat = take((size_t)N * 128 * 2 * 4); w.stat2 = take((size_t)N * 128 * 2 * 4);
+  w.total = off;
+}
+
+}  // namespace scf
+
+using namespace scf;
+
+extern "C" {
+
+size_t scf_encoder_packed_bytes(void) {
+  EncArena a;
+  build_enc_arena(a);
+  return a.total;
+}
+
+size_t scf_encoder_workspace_bytes(int N, int H, int W) {
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  EncWs w;
+  build_enc_ws(N, H, W, w);
+  return w.total;
+}
+
+int scf_encoder_pack(int norm, const float* const* h_weights, void* packed, void* stream) {
+  SCF_REQUIRE(h_weights && packed, SCF_ERR_ARG, "scf_encoder_pack: null pointer");
+  SCF_REQUIRE(norm == SCF_ENC_NORM_IN || norm == SCF_ENC_NORM_BN, SCF_ERR_ARG, "scf_encoder_pack: norm must be IN (0) or BN (1)");
+  cudaStream_t st = (cudaStream_t)stream;
+  EncArena a;
+  build_enc_arena(a);
+  char* base = reinterpret_cast<char*>(packed);
+  SCF_CUDA(cudaMemsetAsync(packed, 0, a.total, st));
+  for (int u = 0; u < SCF_ENC_UNITS; ++u) {
+    const EncUnit& e = kUnits[u];
+    const float* const* s = h_weights + u * 6;     // w, b, bn_weight, bn_bias, bn_mean, bn_var
+    SCF_REQUIRE(s[0] != nullptr, SCF_ERR_ARG, "scf_encoder_pack: conv weight of unit %d is null", u);
+    const bool fold = norm == SCF_ENC_NORM_BN && u != SCF_ENC_UNITS - 1;
+    if (fold) SCF_REQUIRE(s[2] && s[3] && s[4] && s[5], SCF_ERR_ARG, "scf_encoder_pack: BatchNorm parameters of unit %d missing", u);
+    float* wf = reinterpret_cast<float*>(base + a.w_f32[u]);
+    float* bf = reinterpret_cast<float*>(base + a.bias[u]);
+    fold_bn_kernel<<<e.cout, 128, 0, st>>>(s[0], s[1], fold ? s[2] : nullptr, s[3], s[4], s[5], 1e-5f, wf, bf, e.cout,
+                                           e.cin * e.k * e.k);
+    SCF_TRY(check_launch("fold_bn_kernel"));
+    if (u == 0) SCF_TRY(scf_pack_conv_weight(wf, reinterpret_cast<float*>(base + a.packed[u]), e.cout, e.cin, e.k, e.k, a.ldw0, 0, st));
+    else SCF_TRY(scf_pack_conv_weight_tc(wf, base + a.packed[u], e.cout, e.cin, e.k, e.k, a.cin_pad[u], a.cout_pad[u], 0, st));
+  }
+  return 0;
+}
+
+int scf_encoder_forward(int norm, const void* packed, const float* images, int N, int H, int W, float* out_nchw,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  SCF_REQUIRE(packed && images && out_nchw && workspace, SCF_ERR_ARG, "scf_encoder_forward: null pointer");
+  SCF_REQUIRE(norm == SCF_ENC_NORM_IN || norm == SCF_ENC_NORM_BN, SCF_ERR_ARG, "scf_encoder_forward: norm must be IN (0) or BN (1)");
+  SCF_REQUIRE(N > 0 && H >= 16 && W >= 16 && H % 8 == 0 && W % 8 == 0, SCF_ERR_ARG, "scf_encoder_forward: H, W must be multiples of 8");
+  SCF_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 256 == 0 && reinterpret_cast<uintptr_t>(packed) % 256 == 0, SCF_ERR_ALIGN,
+              "scf_encoder_forward: workspace / arena must be 256B aligned");
+  EncArena a;
+  build_enc_arena(a);
+  EncWs ws;
+  build_enc_ws(N, H, W, ws);
+  SCF_REQUIRE(workspace_bytes >= ws.total, SCF_ERR_ARG, "scf_encoder_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* wsb = reinterpret_cast<char*>(workspace);
+  const char* pk = reinterpret_cast<const char*>(packed);
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(wsb + off); };
+  auto S = [&](size_t off) { return reinterpret_cast<void*>(wsb + off); };
+  auto BIAS = [&](int u) { return reinterpret_cast<const float*>(pk + a.bias[u]); };
+  const bool inorm = norm == SCF_ENC_NORM_IN;
+
+  // ---- stem: NCHW image -> NHWC, 7x7 stride-2 conv on the fp32 cores
+  {
+    const long long total = (long long)N * H * W * 3;
+    image_to_nhwc_kernel<<<cdiv(total, 256) < 148 * 32 ? cdiv(total, 256) : 148 * 32, 256, 0, st>>>(images, F(ws.img), 3, H * W, total);
+    SCF_TRY(check_launch("image_to_nhwc_kernel"));
+  }
+  int h = H / 2, w = W / 2;
+  long long npix = (long long)N * h * w;
+  {
+    scf_conv_desc d = {};
+    d.seg[0] = {F(ws.img), 3, 0, 3};
+    d.nseg = 1;
+    d.B = N; d.Hi = H; d.Wi = W; d.Ho = h; d.Wo = w;
+    d.kh = d.kw = 7; d.sh = d.sw = 2; d.ph = d.pw = 3;
+    d.w = reinterpret_cast<const float*>(pk + a.packed[0]); d.ldw = a.ldw0; d.cout = 64;
+    d.bias = BIAS(0); d.scale = 1.f; d.epi = SCF_EPI_ACT;
+    if (inorm) { d.act = SCF_ACT_NONE; d.out = F(ws.raw); d.out_stride = 64; }
+    else {
+      d.act = SCF_ACT_RELU; d.out = F(ws.xf[0]); d.out_stride = 64;
+      d.out_hl = S(ws.xs[0]); d.out_hl_plane = npix * 64; d.out_hl_stride = 64;
+    }
+    SCF_TRY(conv2d_f32(d, st));
+  }
+  // InstanceNorm helpers
+  auto in_stats = [&](const float* x, float* stat, int hw, int C) -> int {
+    instnorm_partial_kernel<<<dim3(IN_SLICES, N), 256, 0, st>>>(x, F(ws.part), hw, C);
+    SCF_TRY(check_launch("instnorm_partial_kernel"));
+    instnorm_finalize_kernel<<<cdiv(N * C, 128), 128, 0, st>>>(F(ws.part), stat, hw, C, 1e-5f, N);
+    return check_launch("instnorm_finalize_kernel");
+  };
+  auto in_apply = [&](const float* x, const float* stat, const float* res, const float* res_stat, int relu, float* of32, void* ohl,
+                      long long pixels, int hw, int C) -> int {
+    const long long total4 = pixels * C / 4;
+    instnorm_apply_kernel<<<cdiv(total4, 256) < 148 * 32 ? cdiv(total4, 256) : 148 * 32, 256, 0, st>>>(
+        x, stat, res, res_stat, relu, of32, reinterpret_cast<__nv_bfloat16*>(ohl), pixels * C, hw, C, total4);
+    return check_launch("instnorm_apply_kernel");
+  };
+  // tensor-core conv unit u on split input (hin x win), stride from the table
+  auto tcconv = [&](int u, void* in_s, int hin, int win, int act, float* of32, void* ohl, const float* residual) -> int {
+    const EncUnit& e = kUnits[u];
+    scf_tc_conv_desc d = {};
+    const long long in_pix = (long long)N * hin * win;
+    d.seg[0].ptr = in_s; d.seg[0].plane_stride = in_pix * e.cin; d.seg[0].stride = e.cin; d.seg[0].coff = 0; d.seg[0].nch = e.cin;
+    d.nseg = 1;
+    d.B = N; d.H = hin; d.W = win; d.kh = d.kw = e.k; d.stride = e.stride;
+    d.w = pk + a.packed[u]; d.cin_pad = a.cin_pad[u]; d.cout_pad = a.cout_pad[u]; d.cout = e.cout;
+    d.bias = BIAS(u); d.scale = 1.f; d.epi = SCF_EPI_ACT; d.act = act;
+    const int ho = (hin + 2 * (e.k / 2) - e.k) / e.stride + 1, wo = (win + 2 * (e.k / 2) - e.k) / e.stride + 1;
+    d.out_f32 = of32; d.out_f32_stride = e.cout;
+    d.out_hl = ohl; d.out_hl_plane = (long long)N * ho * wo * e.cout; d.out_hl_stride = e.cout;
+    d.aux0 = residual; d.aux0_stride = e.cout;
+    return conv2d_tc(d, st);
+  };
+
+  int cur = 0;                         // block input lives in xf[cur] (fp32) and xs[cur] (split)
+  if (inorm) {
+    SCF_TRY(in_stats(F(ws.raw), F(ws.stat), h * w, 64));
+    SCF_TRY(in_apply(F(ws.raw), F(ws.stat), nullptr, nullptr, 1, F(ws.xf[0]), S(ws.xs[0]), npix, h * w, 64));
+  }
+  // ---- residual stages: units (c1, c2, ds) per block
+  const int blocks[6][3] = {{1, 2, -1}, {3, 4, -1}, {5, 6, 7}, {8, 9, -1}, {10, 11, 12}, {13, 14, -1}};
+  for (int bi = 0; bi < 6; ++bi) {
+    const int u1 = blocks[bi][0], u2 = blocks[bi][1], ud = blocks[bi][2];
+    const EncUnit& e1 = kUnits[u1];
+    const int ho = (h - 1) / e1.stride + 1, wo = (w - 1) / e1.stride + 1;
+    const long long opix = (long long)N * ho * wo;
+    const int C = e1.cout, nxt = cur ^ 1;
+    if (inorm) {
+      SCF_TRY(tcconv(u1, S(ws.xs[cur]), h, w, SCF_ACT_NONE, F(ws.raw), nullptr, nullptr));
+      SCF_TRY(in_stats(F(ws.raw), F(ws.stat), ho * wo, C));
+      SCF_TRY(in_apply(F(ws.raw), F(ws.stat), nullptr, nullptr, 1, nullptr, S(ws.ts), opix, ho * wo, C));
+      SCF_TRY(tcconv(u2, S(ws.ts), ho, wo, SCF_ACT_NONE, F(ws.raw), nullptr, nullptr));
+      SCF_TRY(in_stats(F(ws.raw), F(ws.stat), ho * wo, C));
+      if (ud >= 0) {
+        SCF_TRY(tcconv(ud, S(ws.xs[cur]), h, w, SCF_ACT_NONE, F(ws.raw2), nullptr, nullptr));
+        SCF_TRY(in_stats(F(ws.raw2), F(ws.stat2), ho * wo, C));
+        SCF_TRY(in_apply(F(ws.raw), F(ws.stat), F(ws.raw2), F(ws.stat2), 1, F(ws.xf[nxt]), S(ws.xs[nxt]), opix, ho * wo, C));
+      } else {
+        SCF_TRY(in_apply(F(ws.raw), F(ws.stat), F(ws.xf[cur]), nullptr, 1, F(ws.xf[nxt]), S(ws.xs[nxt]), opix, ho * wo, C));
+      }
+    } else {   // eval-mode BatchNorm folded into the convolutions: everything happens in the conv epilogues
+      SCF_TRY(tcconv(u1, S(ws.xs[cur]), h, w, SCF_ACT_RELU, nullptr, S(ws.ts), nullptr));
+      const float* identity = F(ws.xf[cur]);
+      if (ud >= 0) {
+        SCF_TRY(tcconv(ud, S(ws.xs[cur]), h, w, SCF_ACT_NONE, F(ws.raw2), nullptr, nullptr));
+        identity = F(ws.raw2);
+      }
+      SCF_TRY(tcconv(u2, S(ws.ts), ho, wo, SCF_ACT_RELU, F(ws.xf[nxt]), S(ws.xs[nxt]), identity));
+    }
+    cur = nxt; h = ho; w = wo;
+  }
+  // ---- conv2: 1x1 128 -> out channels, bias only; NHWC -> NCHW for the reference's output layout
+  SCF_TRY(tcconv(15, S(ws.xs[cur]), h, w, SCF_ACT_NONE, F(ws.raw), nullptr, nullptr));
+  SCF_TRY(scf_nhwc_to_nchw(F(ws.raw), 256, 0, out_nchw, N, 256, h, w, st));
+  return 0;
+}
+
+}  // extern "C"

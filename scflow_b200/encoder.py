@@ -1,16 +1,21 @@
-"""RAFTEncoder ('Basic' ResNet-ish feature / context encoder) with the reference's state-dict keys.
+"""RAFTEncoder ('Basic' ResNet-ish feature / context encoder) with the reference's state-dict keys
+(models/encoder/raft_encoder.py:286-314, models/backbone/resnet.py:14-94,678-773).
 
-NOT part of the replaced hot path: it feeds the decoder and runs as stock
-cuDNN convolutions through PyTorch, exactly like the reference (models/encoder/raft_encoder.py:286-314,
-models/backbone/resnet.py:14-94,678-773).  It exists so that ``SCFlowRefiner.get_pose`` is runnable end to end.
+SURVEY.md §8(f) rank 1 - the component feeding the refinement loop.  In inference (``eval()`` on a CUDA device,
+``norm_cfg`` IN or BN) ``forward`` is ONE call into the C ABI (``scf_encoder_forward``): tcgen05 split-bf16
+convolutions, fused InstanceNorm / folded BatchNorm.  In training mode (batch statistics, autograd) it falls through
+to the plain nn.Module graph below, which is also what defines the parameters / state-dict keys.
 """
 from typing import Optional, Sequence, Union
+
+import ctypes as C
 
 import torch
 import torch.nn as nn
 
+from . import _lib
 from .builder import ENCODERS
-from .cnn import BaseModule
+from .cnn import BaseModule, PackedCache
 
 
 def _norm(cfg: dict, channels: int, postfix=''):
@@ -92,6 +97,10 @@ class RAFTEncoder(BaseModule):
             self.res_layers.append(name)
             inplanes = planes
         self.conv2 = nn.Conv2d(inplanes, out_channels, 1)
+        self.norm_type = norm_cfg['type']
+        self.use_native = True            # set False to force the nn.Module graph (stock cuDNN) in eval mode too
+        self._arena = PackedCache()
+        self._ws = {}
         self.init_weights()
 
     def init_weights(self):
@@ -105,7 +114,48 @@ class RAFTEncoder(BaseModule):
                 nn.init.ones_(m.weight)
                 nn.init.zeros_(m.bias)
 
+    # ------------------------------------------------------------------ native (C ABI) inference path
+    def _native_ok(self, x: torch.Tensor) -> bool:
+        return (self.use_native and not self.training and x.is_cuda and not torch.is_grad_enabled()
+                and self.norm_type in ('IN', 'BN') and self.in_channels == 3 and self.out_channels == 256
+                and self.scale == 1 / 8 and x.shape[-2] % 8 == 0 and x.shape[-1] % 8 == 0)
+
+    def _forward_native(self, x: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        norm = _lib.ENC_NORM_IN if self.norm_type == 'IN' else _lib.ENC_NORM_BN
+        mods = dict(self.named_modules())
+        tensors = []
+        for conv_name, norm_name in _lib.ENCODER_UNITS:
+            conv = mods[conv_name]
+            unit = [conv.weight, conv.bias, None, None, None, None]
+            if norm == _lib.ENC_NORM_BN and norm_name is not None:
+                bn = mods[norm_name.format(n='bn')]
+                unit[2:] = [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+            tensors.extend(unit)
+        live = [t for t in tensors if t is not None]
+
+        def make():
+            arena = torch.empty(lib.scf_encoder_packed_bytes(), device=x.device, dtype=torch.uint8)
+            srcs = [None if t is None else t.detach().contiguous().float() for t in tensors]
+            arr = (C.c_void_p * len(srcs))(*[None if t is None else t.data_ptr() for t in srcs])
+            _lib.check(lib.scf_encoder_pack(norm, arr, _lib.ptr(arena), _lib.stream_ptr()), 'scf_encoder_pack')
+            return arena
+
+        arena = self._arena.get(live, make)
+        n, _, h, w = x.shape
+        key = (n, h, w, str(x.device))
+        ws = self._ws.get(key)
+        if ws is None:
+            self._ws = {key: torch.empty(lib.scf_encoder_workspace_bytes(n, h, w), device=x.device, dtype=torch.uint8)}
+            ws = self._ws[key]
+        out = torch.empty(n, self.out_channels, h // 8, w // 8, device=x.device, dtype=torch.float32)
+        _lib.check(lib.scf_encoder_forward(norm, _lib.ptr(arena), _lib.ptr(x.detach().contiguous().float()), n, h, w,
+                                           _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'scf_encoder_forward')
+        return out
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._native_ok(x):
+            return self._forward_native(x)
         x = self.relu(getattr(self, self.norm1_name)(self.conv1(x)))
         for name in self.res_layers:
             x = getattr(self, name)(x)

@@ -65,8 +65,13 @@ class SCFlowRefiner(BaseModule):
 
     def extract_feat(self, render_images, real_images) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
         """scflow_refiner.py:88-110."""
-        real_feat = self.real_encoder(real_images)
-        render_feat = self.render_encoder(render_images)
+        if self.real_encoder is self.render_encoder and not self.training and real_images.shape == render_images.shape:
+            # shared weights (seperate_encoder=False): one pass over both image sets (InstanceNorm is per sample)
+            both = self.real_encoder(torch.cat([real_images, render_images], dim=0))
+            real_feat, render_feat = both[:real_images.shape[0]], both[real_images.shape[0]:]
+        else:
+            real_feat = self.real_encoder(real_images)
+            render_feat = self.render_encoder(render_images)
         cxt_feat = self.context(render_images)
         h_feat, cxt_feat = torch.split(cxt_feat, [self.h_channels, self.cxt_channels], dim=1)
         return render_feat, real_feat, torch.tanh(h_feat), torch.relu(cxt_feat)

@@ -185,3 +185,35 @@ def test_mask_options_run():
     ref = _call(base, scene, f, b, 256, 256)
     assert torch.equal(outs[2][0], ref[2][0])            # first iteration: mask is all ones -> identical
     assert not torch.equal(outs[2][1], ref[2][1])        # second iteration: the predicted mask gates corr / flow
+
+
+@pytest.mark.parametrize('norm', ['IN', 'BN'])
+def test_native_encoder_matches_oracle(norm):
+    """RAFTEncoder through scf_encoder_forward (tcgen05 split-bf16) vs the fp32 CPU oracle."""
+    import scflow_b200 as S
+    enc = S.build_encoder(dict(type='RAFTEncoder', in_channels=3, out_channels=256, net_type='Basic', norm_cfg=dict(type=norm)))
+    sd = O.make_encoder_weights(5, norm)
+    enc.load_state_dict(sd, strict=False)
+    enc = enc.cuda().eval()
+    scene = O.make_scene(5, 3)
+    x = scene['real_images']
+    with torch.no_grad():
+        got = enc(x.cuda()).cpu()
+        ref = O.raft_encoder(sd, x, norm)
+        enc.use_native = False
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        stock = enc(x.cuda()).cpu()
+        torch.backends.cudnn.allow_tf32 = prev
+    assert got.shape == ref.shape == (3, 256, 32, 32)
+    scale = float(ref.abs().max())
+    err, err_stock = float((got - ref).abs().max()), float((stock - ref).abs().max())
+    print(f'encoder {norm}: max|native - oracle| {err:.2e}, max|cuDNN fp32 - oracle| {err_stock:.2e}, |ref|max {scale:.2f}')
+    assert err < 2e-4 * max(scale, 1.0)
+    # odd batch / non-square input
+    x2 = torch.rand(1, 3, 64, 96)
+    with torch.no_grad():
+        enc.use_native = True
+        g2 = enc(x2.cuda()).cpu()
+        r2 = O.raft_encoder(sd, x2, norm)
+    assert float((g2 - r2).abs().max()) < 2e-4 * max(float(r2.abs().max()), 1.0)
