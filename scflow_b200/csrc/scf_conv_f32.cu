@@ -225,8 +225,14 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int src_strid
   }
 }
 
+int conv2d_thin(const scf_conv_desc& d, int in_nchw, cudaStream_t st);
+
 int conv2d_f32(const scf_conv_desc& d, cudaStream_t st) {
   SCF_REQUIRE(d.nseg >= 1 && d.nseg <= 3, SCF_ERR_ARG, "scf_conv2d: nseg must be 1..3");
+  if (d.nseg == 1 && d.seg[0].nch <= 4 && d.seg[0].ptr && d.w && (d.out || d.out_hl) && d.B > 0 && d.cout > 0) {
+    const int rc = conv2d_thin(d, 0, st);       // register-tiled direct kernel for thin inputs
+    if (rc != -100) return rc;
+  }
   SCF_REQUIRE(d.w && (d.out || (d.out_hl && d.epi == SCF_EPI_ACT)) && d.B > 0 && d.cout > 0, SCF_ERR_ARG,
               "scf_conv2d: null pointer or empty shape");
   SCF_REQUIRE(d.ldw >= d.cout && d.ldw % 4 == 0, SCF_ERR_ARG, "scf_conv2d: ldw must be >= cout and a multiple of 4");

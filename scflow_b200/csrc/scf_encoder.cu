@@ -9,6 +9,7 @@
 namespace scf {
 
 int conv2d_f32(const scf_conv_desc& d, cudaStream_t st);
+int conv2d_thin(const scf_conv_desc& d, int in_nchw, cudaStream_t st);
 int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st);
 
 // ------------------------------------------------------------------ conv-unit table
@@ -231,17 +232,12 @@ int scf_encoder_forward(int norm, const void* packed, const float* images, int N
   auto BIAS = [&](int u) { return reinterpret_cast<const float*>(pk + a.bias[u]); };
   const bool inorm = norm == SCF_ENC_NORM_IN;
 
-  // ---- stem: NCHW image -> NHWC, 7x7 stride-2 conv on the fp32 cores
-  {
-    const long long total = (long long)N * H * W * 3;
-    image_to_nhwc_kernel<<<cdiv(total, 256) < 148 * 32 ? cdiv(total, 256) : 148 * 32, 256, 0, st>>>(images, F(ws.img), 3, H * W, total);
-    SCF_TRY(check_launch("image_to_nhwc_kernel"));
-  }
+  // ---- stem: 7x7 stride-2 conv on the fp32 cores, reading the NCHW image directly
   int h = H / 2, w = W / 2;
   long long npix = (long long)N * h * w;
   {
     scf_conv_desc d = {};
-    d.seg[0] = {F(ws.img), 3, 0, 3};
+    d.seg[0] = {images, 3, 0, 3};
     d.nseg = 1;
     d.B = N; d.Hi = H; d.Wi = W; d.Ho = h; d.Wo = w;
     d.kh = d.kw = 7; d.sh = d.sw = 2; d.ph = d.pw = 3;
@@ -252,7 +248,9 @@ int scf_encoder_forward(int norm, const void* packed, const float* images, int N
       d.act = SCF_ACT_RELU; d.out = F(ws.xf[0]); d.out_stride = 64;
       d.out_hl = S(ws.xs[0]); d.out_hl_plane = npix * 64; d.out_hl_stride = 64;
     }
-    SCF_TRY(conv2d_f32(d, st));
+    const int rc = conv2d_thin(d, /*in_nchw=*/1, st);
+    SCF_REQUIRE(rc != -100, SCF_ERR_UNSUPPORTED, "scf_encoder_forward: stem kernel rejected the shape");
+    SCF_TRY(rc);
   }
   // InstanceNorm helpers
   auto in_stats = [&](const float* x, float* stat, int hw, int C) -> int {
