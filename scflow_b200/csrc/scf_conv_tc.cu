@@ -32,6 +32,14 @@ struct TcParams {
   int BN, cout, num_taps, w_batched, stages, tmem_cols;
   long long* dbg_times;        // optional [grid][8] globaltimer stamps (timing experiments only)
   int debug;                   // timing experiments only (SCFLOW_TC_DEBUG): 1 skip A loads, 2 skip W loads, 4 skip MMAs
+  // halo mode (stride-1 multi-tap convs): the activation tile is fetched ONCE per channel chunk with its kh-1 / kw-1
+  // halo (PW x PH pixel rows) and every tap reads it through a row-shifted UMMA descriptor (tile = 8 x 16 pixels so
+  // that one 8-row core-matrix group = one tile row and the group stride is the halo pitch PW*128 B)
+  int halo, PW, PH, a_stages, b_stages;
+  // stacked-N mode (BN <= 128): the hi and lo weight planes are adjacent in shared memory, so ONE MMA with N = 2*BN
+  // forms A_hi*[W_hi;W_lo] into accumulator columns [0,BN) and [BN,2BN); a second MMA adds A_lo*W_hi into [0,BN).
+  // Two instructions per k-step instead of three (small-N MMAs are issue-bound); the epilogue adds the two halves.
+  int stackn;
   int cluster;                 // CTAs per cluster sharing one weight tile via TMA multicast (1 = none)
   const float* bias; float scale; int epi, act;
   float* out_f32; int out_f32_stride, out_f32_coff;
@@ -106,11 +114,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                const __grid_constant__ CUtensorMap tmWs, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024 B alignment
-  // [0,1024): barriers + TMEM pointer ; then `stages` x {A hi, A lo, W hi, W lo}
-  const uint32_t bar_full = smem_base, bar_empty = smem_base + 64, bar_tmem = smem_base + 128, tmem_slot = smem_base + 192;
+  // [0,1024): barriers + TMEM pointer. classic: `stages` x {A hi, A lo, W hi, W lo}; halo: A ring then W ring
+  const uint32_t bar_full = smem_base, bar_empty = smem_base + 64, bar_afull = smem_base + 128, bar_aempty = smem_base + 144,
+                 bar_tmem = smem_base + 160, tmem_slot = smem_base + 192;
   const uint32_t b_plane = (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;
+  const uint32_t stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;                    // classic mode
+  const uint32_t a_plane = (uint32_t)(p.PW * p.PH) * 128u;                      // halo mode
+  const uint32_t a_stage = (2 * a_plane + 1023u) & ~1023u;
   const uint32_t tiles0 = smem_base + 1024;
+  const uint32_t bring0 = tiles0 + (uint32_t)p.a_stages * a_stage;              // halo mode: start of the W ring
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto stamp = [&](int slot) {
@@ -137,9 +149,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (p.nseg > 1) prefetch_tmap(&tmA1);
     if (p.nseg > 2) prefetch_tmap(&tmA2);
     prefetch_tmap(p.cluster > 1 ? &tmWs : &tmW);
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < (p.halo ? p.b_stages : p.stages); ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, (uint32_t)p.cluster);   // every CTA of the cluster releases the stage
+    }
+    for (int s = 0; s < p.a_stages; ++s) {
+      mbar_init(bar_afull + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 1);
     }
     mbar_init(bar_tmem, 1);
     fence_barrier_init();
@@ -155,8 +171,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (threadIdx.x == 0) stamp(1);
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer
+    if (lane == 0 && !p.halo) {
+      // ================= TMA producer (classic: one {A tap tile, W tile} pair per stage)
       int stage = 0;
       uint32_t phase = 0;
       for (int tap = 0; tap < p.num_taps; ++tap) {
@@ -185,11 +201,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
       }
+    } else if (lane == 0) {
+      // ================= TMA producer (halo: one activation halo tile per channel chunk, one W tile per tap)
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
+        for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
+          mbar_wait(bar_aempty + 8 * sa, pa ^ 1u);
+          mbar_arrive_expect_tx(bar_afull + 8 * sa, 2 * a_plane);
+          tma_load_5d(tiles0 + sa * a_stage, tm, bar_afull + 8 * sa, cc * TC_BK, x0 - p.pw, y0 - p.ph, b, 0);
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+          const int wk = p.seg_wcoff[s] + cc * TC_BK;
+          for (int tap = 0; tap < p.num_taps; ++tap) {
+            mbar_wait(bar_empty + 8 * sb, pb ^ 1u);
+            const uint32_t full = bar_full + 8 * sb;
+            mbar_arrive_expect_tx(full, 2 * b_plane);
+            const uint32_t w_dst0 = bring0 + sb * 2 * b_plane;
+            if (p.cluster == 1) {
+              tma_load_4d(w_dst0, &tmW, full, wk, n0, tap, 0);
+            } else {
+              const int rows = p.BN / p.cluster;
+              const uint32_t w_dst = w_dst0 + crank * rows * 128;
+              tma_load_4d_mc(w_dst, &tmWs, full, wk, n0 + crank * rows, tap, 0, cmask);
+              tma_load_4d_mc(w_dst + b_plane, &tmWs, full, wk, n0 + crank * rows, tap, 1, cmask);
+            }
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1u; }
+          }
+        }
+      }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer
-      const uint32_t idesc = make_idesc_bf16(TC_BM, p.BN);
+    if (lane == 0 && !p.halo) {
+      // ================= MMA issuer (classic)
+      const uint32_t idesc = make_idesc_bf16(TC_BM, p.BN), idesc2 = make_idesc_bf16(TC_BM, 2 * p.BN);
       int stage = 0;
       uint32_t phase = 0;
       for (int c = 0; c < num_chunks; ++c) {
@@ -197,21 +242,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_after();
         if (c == 0) stamp(2);
         const uint32_t a_addr = tiles0 + stage * stage_bytes;
-        const uint64_t a_hi = make_smem_desc_sw128(a_addr), a_lo = make_smem_desc_sw128(a_addr + TC_A_PLANE);
-        const uint64_t b_hi = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE);
-        const uint64_t b_lo = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + b_plane);
+        const uint64_t a_hi = make_smem_desc_sw128(a_addr, 1024), a_lo = make_smem_desc_sw128(a_addr + TC_A_PLANE, 1024);
+        const uint64_t b_hi = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE, 1024);
+        const uint64_t b_lo = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + b_plane, 1024);
+        if (p.stackn) {
 #pragma unroll
-        for (int k = 0; k < ((p.debug & 4) ? 0 : TC_BK / 16); ++k) {
-          const uint64_t ko = (uint64_t)(k * 32 >> 4);     // 16 bf16 = 32 B along the swizzled 128 B row
-          umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, (c > 0 || k > 0) ? 1u : 0u);
-          umma_bf16(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
-          umma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t ko = (uint64_t)(k * 32 >> 4);
+            umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc2, (c > 0 || k > 0) ? 1u : 0u);   // N = 2*BN: [W_hi;W_lo]
+            umma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < ((p.debug & 4) ? 0 : TC_BK / 16); ++k) {
+            const uint64_t ko = (uint64_t)(k * 32 >> 4);     // 16 bf16 = 32 B along the swizzled 128 B row
+            umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, (c > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
+            umma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
+          }
         }
         if (p.cluster == 1) umma_commit(bar_empty + 8 * stage);   // frees the smem slot once these MMAs have read it
         else umma_commit_mc(bar_empty + 8 * stage, cmask);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
       umma_commit(bar_tmem);                      // accumulator complete
+      stamp(3);
+    } else if (lane == 0) {
+      // ================= MMA issuer (halo): tap (ky,kx) = the halo tile read from row offset ky*PW + kx; SWIZZLE_128B is
+      // a function of the absolute smem address for TMA and UMMA alike, so any 128 B row offset is a valid operand start
+      const uint32_t idesc = make_idesc_bf16(TC_BM, p.BN), idesc2 = make_idesc_bf16(TC_BM, 2 * p.BN);
+      const uint32_t a_sbo = (uint32_t)p.PW * 128u;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const int nchunk = chunks_per_tap;
+      for (int c = 0; c < nchunk; ++c) {
+        mbar_wait(bar_afull + 8 * sa, pa);
+        const uint32_t a_base = tiles0 + sa * a_stage;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          mbar_wait(bar_full + 8 * sb, pb);
+          tc_fence_after();
+          if (c == 0 && tap == 0) stamp(2);
+          const int ky = tap / p.kw, kx = tap - ky * p.kw;
+          const uint32_t a_addr = a_base + (uint32_t)(ky * p.PW + kx) * 128u;
+          const uint64_t a_hi = make_smem_desc_sw128(a_addr, a_sbo), a_lo = make_smem_desc_sw128(a_addr + a_plane, a_sbo);
+          const uint32_t w_addr = bring0 + sb * 2 * b_plane;
+          const uint64_t b_hi = make_smem_desc_sw128(w_addr, 1024), b_lo = make_smem_desc_sw128(w_addr + b_plane, 1024);
+          if (p.stackn) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t ko = (uint64_t)(k * 32 >> 4);
+              umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc2, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t ko = (uint64_t)(k * 32 >> 4);
+              umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
+            }
+          }
+          if (p.cluster == 1) umma_commit(bar_empty + 8 * sb);
+          else umma_commit_mc(bar_empty + 8 * sb, cmask);
+          if (++sb == p.b_stages) { sb = 0; pb ^= 1u; }
+        }
+        umma_commit(bar_aempty + 8 * sa);         // all taps of this chunk have read the halo tile
+        if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+      }
+      umma_commit(bar_tmem);
       stamp(3);
     }
   } else {
@@ -232,6 +331,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       float v[16];
       __syncwarp();
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 16), v);
+      if (p.stackn) {                        // second half of the stacked accumulator: A_hi * W_lo
+        float v2[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + g * 16), v2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += v2[i];
+      }
       const int nb = n0 + g * 16;
       if (!valid || nb >= p.cout) continue;
       const int nvalid = p.cout - nb < 16 ? p.cout - nb : 16;
@@ -423,7 +528,6 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.B = d.B; p.H = (d.H + 2 * p.ph - d.kh) / stride + 1; p.W = (d.W + 2 * p.pw - d.kw) / stride + 1;
   pick_tile(d.B, p.H, p.W, d.w_batched != 0, p.TW, p.TH, p.TB);
   p.tiles_x = cdiv(p.W, p.TW); p.tiles_y = cdiv(p.H, p.TH);
-  const int m_tiles = p.tiles_x * p.tiles_y * cdiv(d.B, p.TB);
   p.BN = d.cout_pad <= 256 ? d.cout_pad : 256;
   p.cout = d.cout;
   p.num_taps = d.kh * d.kw;
@@ -432,8 +536,40 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.stages = (232448 - 2048) / stage_bytes;
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
   SCF_REQUIRE(p.stages >= 2, SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: tile does not fit in shared memory");
+  {
+    // Small tiles (BN <= 64): keep two CTAs resident per SM (<= 113 KB each) so that one CTA's prologue / epilogue
+    // overlaps the other's main loop - the fixed per-tile cost is ~40 % of a 9-chunk tile's lifetime otherwise.
+    const char* ov = getenv("SCFLOW_TC_OCC2");
+    const bool occ2 = ov ? atoi(ov) != 0 : true;
+    if (occ2 && 2 * stage_bytes + 2048 <= 115712 && p.tiles_x * p.tiles_y * cdiv(d.B, p.TB) >= 4 * 148) p.stages = (115712 - 2048) / stage_bytes;
+  }
+  // halo mode for stride-1 multi-tap convolutions
+  p.halo = 0; p.PW = p.PH = 0; p.a_stages = 0; p.b_stages = 0;
+  int smem = 1024 + 1024 + p.stages * stage_bytes;
+  {
+    const char* hv = getenv("SCFLOW_TC_HALO");
+    const bool want = hv ? atoi(hv) != 0 : false;   // measured: no gain (small-N MMAs are issue-bound, not load-bound)
+    if (want && stride == 1 && p.num_taps > 1 && !d.w_batched) {
+      const int PW = 8 + d.kw - 1, PH = 16 + d.kh - 1;
+      const int a_stage = (2 * PW * PH * 128 + 1023) / 1024 * 1024;
+      const int b_stage = 2 * p.BN * 128;
+      int sb = (232448 - 2048 - 2 * a_stage) / b_stage;
+      if (sb > 8) sb = 8;
+      if (sb >= 2) {
+        p.halo = 1; p.PW = PW; p.PH = PH; p.a_stages = 2; p.b_stages = sb;
+        p.TW = 8; p.TH = 16; p.TB = 1;
+        p.tiles_x = cdiv(p.W, 8); p.tiles_y = cdiv(p.H, 16);
+        smem = 1024 + 1024 + 2 * a_stage + sb * b_stage;
+      }
+    }
+  }
+  const int m_tiles = p.tiles_x * p.tiles_y * cdiv(d.B, p.TB);
+  {
+    const char* sv = getenv("SCFLOW_TC_STACKN");
+    p.stackn = (p.BN <= 128 && (sv ? atoi(sv) != 0 : true)) ? 1 : 0;
+  }
   p.tmem_cols = 32;
-  while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+  while (p.tmem_cols < (p.stackn ? 2 * p.BN : p.BN)) p.tmem_cols <<= 1;
   p.bias = d.bias; p.scale = d.scale; p.epi = d.epi; p.act = d.act;
   p.out_f32 = d.out_f32; p.out_f32_stride = d.out_f32_stride; p.out_f32_coff = d.out_f32_coff;
   p.out_hl = reinterpret_cast<__nv_bfloat16*>(d.out_hl); p.out_hl_plane = d.out_hl_plane; p.out_hl_stride = d.out_hl_stride;
@@ -475,6 +611,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
                          (cuuint64_t)sg.plane_stride * 2};
     // box = elements TRAVERSED per dimension; with element strides (1,s,s,1,1) it deposits TW x TH x TB pixels
     cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TB, 2};
+    if (p.halo) { box[1] = (cuuint32_t)p.PW; box[2] = (cuuint32_t)p.PH; }
     cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
     SCF_TRY(encode_map(&tmA[s], base, 5, dims, str, box, estr));
     p.seg_chunks[s] = cdiv(sg.nch, TC_BK);
@@ -496,7 +633,6 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
       SCF_TRY(encode_map(&tmWs, d.w, 4, dims, str, boxs));
     }
   }
-  const int smem = 1024 + 1024 + p.stages * stage_bytes;
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
   KernelFn kernel = nullptr;
   if (d.epi == SCF_EPI_GRU_ZR) kernel = conv_tc_kernel<SCF_EPI_GRU_ZR, SCF_ACT_SIGMOID>;

@@ -121,11 +121,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 // Shared-memory matrix descriptor for a K-major tile whose rows are 128 B (64 bf16) with SWIZZLE_128B:
-// 8-row groups are 1024 B apart (SBO), LBO unused, descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+// 8-row groups are `sbo` bytes apart (1024 for a dense tile), LBO unused, descriptor version 1 (sm_100), layout
+// type 2 (SWIZZLE_128B).  Measured on B200: the swizzle is a function of the absolute shared-memory address for
+// both TMA writes and UMMA reads, so the start may sit at any 128 B row (base_offset stays 0).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t sbo) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
-  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset, bits [32,46)
+  d |= (uint64_t)(sbo >> 4) << 32;                    // stride byte offset, bits [32,46)
   d |= (uint64_t)1 << 46;                             // descriptor version
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
   return d;

@@ -6,17 +6,17 @@ import torch
 import scflow_b200 as S
 
 dev = 'cuda'
-b = 32
 g = torch.Generator().manual_seed(0)
-for name, cin, cout, k in [('gru_zr_1x5', 384, 256, (1, 5)), ('flow1_3x3', 128, 64, (3, 3)), ('mhp_1x1', 256, 1, (1, 1))]:
-    x = torch.randn(b, cin, 32, 32, generator=g).to(dev)
+for name, cin, cout, k, b, hw in [('gru_zr_1x5', 384, 256, (1, 5), 32, 32), ('flow1_3x3', 128, 64, (3, 3), 32, 32),
+                                  ('enc64_3x3', 64, 64, (3, 3), 8, 128), ('mhp_1x1', 256, 1, (1, 1), 32, 32)]:
+    x = torch.randn(b, cin, hw, hw, generator=g).to(dev)
     w = (torch.randn(cout, cin, *k, generator=g) / math.sqrt(cin * k[0] * k[1])).to(dev)
     xs = S.ops.split_nchw(x)
     pw = S.ops.pack_conv_weight_tc([w])
-    out = torch.zeros(2, b, 32, 32, (cout + 7) // 8 * 8, device=dev, dtype=torch.bfloat16)
-    ncta = 256 * ((cout + 255) // 256)
+    out = torch.zeros(2, b, hw, hw, (cout + 7) // 8 * 8, device=dev, dtype=torch.bfloat16)
+    ncta = (b * hw * hw // 128) * ((cout + 255) // 256)
     times = torch.zeros(ncta, 8, dtype=torch.int64, device=dev)
-    os.environ['SCFLOW_TC_CLUSTER'] = '1'
+    os.environ['SCFLOW_TC_CLUSTER'] = os.environ.get('SCFLOW_TC_CLUSTER', '1')
     fn = lambda: S.ops.conv2d_tc([(xs, 0, cin)], pw, None, cout, k, act='relu', out_hl=out)
     for _ in range(3):
         fn()
@@ -31,7 +31,7 @@ for name, cin, cout, k in [('gru_zr_1x5', 384, 256, (1, 5)), ('flow1_3x3', 128, 
     print(f'== {name}: kernel span {float((t[:, 6].max() - t0) / 1e3):.1f} us')
     names = ['start', 'prologue done', 'first data', 'last mma issued', 'accum ready', 'epilogue done', 'exit']
     order = torch.argsort(rel[:, 0])
-    for label, idx in (('first-wave CTA (earliest)', order[0]), ('first-wave CTA (median)', order[70]), ('second-wave CTA (median)', order[200]), ('last CTA', order[-1])):
+    for label, idx in (('first-wave CTA (earliest)', order[0]), ('first-wave CTA (median)', order[70]), ('last CTA', order[-1])):
         r = rel[idx]
         print(f'  {label:28s} ' + '  '.join(f'{n}={float(r[i]):7.2f}' for i, n in enumerate(names)))
     dur = rel[:, 6] - rel[:, 0]
