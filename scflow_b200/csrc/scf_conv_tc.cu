@@ -8,7 +8,8 @@
 //   * MMA     : per 16-channel k-step three tcgen05.mma (hi*hi, hi*lo, lo*hi), M=128, N=BN, issued by one thread.
 //   * epilogue: 4 warps read the accumulator with tcgen05.ld (one TMEM lane = one pixel per thread), apply
 //               bias/activation or the GRU gate math, and write fp32 and/or split-bf16 NHWC outputs.
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (coalesced through
+// a small shared-memory staging buffer).
 #include "scf_common.cuh"
 #include "scf_tc.cuh"
 #include <mutex>
@@ -20,7 +21,9 @@ using namespace tc;
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 192;   // warp 0 TMA, warp 1 MMA + TMEM allocator, warps 2-5 epilogue
+constexpr int TC_STAGE_ROW = 80;  // epilogue staging: 32 rows x 64 B per warp, rows padded to 80 B (conflict-free 16 B accesses)
+constexpr int TC_HEADER = 1024 + 4 * 32 * TC_STAGE_ROW + 1024;   // barriers + staging (+ pad to a multiple of 1024)
 constexpr uint32_t TC_A_PLANE = TC_BM * TC_BK * 2;   // 16 KB
 constexpr int TC_MAX_STAGES = 4;
 
@@ -40,6 +43,7 @@ struct TcParams {
   // forms A_hi*[W_hi;W_lo] into accumulator columns [0,BN) and [BN,2BN); a second MMA adds A_lo*W_hi into [0,BN).
   // Two instructions per k-step instead of three (small-N MMAs are issue-bound); the epilogue adds the two halves.
   int stackn;
+  int fast_epi;                // every global access of the epilogue is 16 B aligned: use the coalesced staged path
   int cluster;                 // CTAs per cluster sharing one weight tile via TMA multicast (1 = none)
   const float* bias; float scale; int epi, act;
   float* out_f32; int out_f32_stride, out_f32_coff;
@@ -67,6 +71,81 @@ __device__ __forceinline__ void load16(const float* src, float* d) {     // src 
     const float4 t = __ldg(reinterpret_cast<const float4*>(src) + i);
     d[4 * i] = t.x; d[4 * i + 1] = t.y; d[4 * i + 2] = t.z; d[4 * i + 3] = t.w;
   }
+}
+
+// ---- coalescing through shared memory.  In the accumulator layout a thread owns one pixel row, so direct 16 B stores
+// of a warp touch 32 different cache lines (measured: the epilogue of a 128x256 tile took 5.6 us, LSU-bound).  These
+// helpers move a [32 rows x 64 B] block between the warp's registers and global memory with 4 lanes per row, i.e.
+// 8 fully used 64 B row segments per instruction.  `mypix` = global pixel index of this thread's row, or -1.
+__device__ __forceinline__ void stage_store64(uint32_t sbuf, int lane, char* gbase, long long row_bytes, long long mypix,
+                                              const uint4 (&d)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + lane * TC_STAGE_ROW + i * 16), "r"(d[i].x), "r"(d[i].y),
+                 "r"(d[i].z), "r"(d[i].w) : "memory");
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2), seg = lane & 3;
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(sbuf + r * TC_STAGE_ROW + seg * 16) : "memory");
+    const long long pr = __shfl_sync(0xffffffffu, mypix, r);
+    if (pr >= 0) *reinterpret_cast<uint4*>(gbase + pr * row_bytes + seg * 16) = v;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void stage_load64(uint32_t sbuf, int lane, const char* gbase, long long row_bytes, long long mypix,
+                                             float (&out)[16]) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2), seg = lane & 3;
+    const long long pr = __shfl_sync(0xffffffffu, mypix, r);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (pr >= 0) v = __ldg(reinterpret_cast<const uint4*>(gbase + pr * row_bytes + seg * 16));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + r * TC_STAGE_ROW + seg * 16), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w) : "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(sbuf + lane * TC_STAGE_ROW + i * 16) : "memory");
+    out[4 * i] = __uint_as_float(v.x); out[4 * i + 1] = __uint_as_float(v.y);
+    out[4 * i + 2] = __uint_as_float(v.z); out[4 * i + 3] = __uint_as_float(v.w);
+  }
+  __syncwarp();
+}
+// 16 fp32 values of this thread's row -> one 64 B fp32 block
+__device__ __forceinline__ void stage_store_f32(uint32_t sbuf, int lane, float* gbase, int stride, long long mypix, const float* v) {
+  uint4 d[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    d[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+  stage_store64(sbuf, lane, reinterpret_cast<char*>(gbase), (long long)stride * 4, mypix, d);
+}
+// 32 fp32 values of this thread's row -> split-bf16: one 64 B block in the hi plane, one in the lo plane
+__device__ __forceinline__ void stage_store_split32(uint32_t sbuf, int lane, __nv_bfloat16* gbase, long long plane, int stride,
+                                                    long long mypix, const float* v) {
+  uint4 hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = v[8 * i + 2 * j], b = v[8 * i + 2 * j + 1];
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+      const float2 hf = __bfloat1622float2(h2);
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+      h[j] = *reinterpret_cast<const uint32_t*>(&h2);
+      l[j] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    hi[i] = make_uint4(h[0], h[1], h[2], h[3]);
+    lo[i] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+  stage_store64(sbuf, lane, reinterpret_cast<char*>(gbase), (long long)stride * 2, mypix, hi);
+  stage_store64(sbuf, lane, reinterpret_cast<char*>(gbase + plane), (long long)stride * 2, mypix, lo);
 }
 
 __device__ __forceinline__ void store_f32x16(float* dst, const float* v, int nvalid) {
@@ -121,7 +200,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;                    // classic mode
   const uint32_t a_plane = (uint32_t)(p.PW * p.PH) * 128u;                      // halo mode
   const uint32_t a_stage = (2 * a_plane + 1023u) & ~1023u;
-  const uint32_t tiles0 = smem_base + 1024;
+  const uint32_t stage0 = smem_base + 1024;                                     // epilogue staging, 4 warps x 2560 B
+  const uint32_t bias_s = smem_base + 1024 + 4 * 32 * TC_STAGE_ROW;             // this tile's bias (BN floats, zero if none)
+  const uint32_t tiles0 = smem_base + TC_HEADER;
   const uint32_t bring0 = tiles0 + (uint32_t)p.a_stages * a_stage;              // halo mode: start of the W ring
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,6 +242,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp >= 2) {        // stage the bias slice of this N tile (global-load latency would otherwise sit inside every slab)
+    for (int i = threadIdx.x - 64; i < p.BN; i += TC_THREADS - 64) {
+      const float bvl = (p.bias && blockIdx.y * p.BN + i < p.cout) ? __ldg(p.bias + blockIdx.y * p.BN + i) : 0.f;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4 * i), "f"(bvl) : "memory");
+    }
+  }
   tc_fence_before();
   if (p.cluster > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers must exist before any multicast
   tc_fence_after();
@@ -326,8 +413,87 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const bool valid = y < p.H && x < p.W && b + bb < p.B;
     const long long pix = ((long long)(b + bb) * p.H + y) * p.W + x;
     const int half = p.cout >> 1;
+    const int ngroups = p.BN / 16;
+    int g_begin = 0;
+    if (p.fast_epi) {
+      // ---- coalesced path: 32-column slabs, every global access staged through shared memory
+      const uint32_t sbuf = stage0 + (uint32_t)(warp - 2) * 32 * TC_STAGE_ROW;
+      const long long mypix = valid ? pix : -1;
+      const int nslab = (p.cout - n0 < p.BN ? p.cout - n0 : p.BN) / 32;      // full slabs only; the tail uses the plain path
 #pragma unroll 1
-    for (int g = 0; g < p.BN / 16; ++g) {
+      for (int sl = 0; sl < nslab; ++sl) {
+        float v[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sl * 32), v);
+        if (p.stackn) {
+          float v2[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + sl * 32), v2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += v2[i];
+        }
+        const int nb = n0 + sl * 32;
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {             // bias from shared memory (same address in every lane: broadcast)
+          float4 bq;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bq.x), "=f"(bq.y), "=f"(bq.z), "=f"(bq.w)
+                       : "r"(bias_s + (uint32_t)(sl * 32 + i4 * 4) * 4));
+          v[4 * i4] = fmaf(v[4 * i4], p.scale, bq.x); v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], p.scale, bq.y);
+          v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], p.scale, bq.z); v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], p.scale, bq.w);
+        }
+        if (EPI == SCF_EPI_ACT) {
+          if (p.aux0) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              float rv[16];
+              stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux0 + nb + hh * 16), (long long)p.aux0_stride * 4, mypix, rv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[hh * 16 + i] += rv[i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = act_ct<ACT>(v[i]);
+          if (p.out_f32) {
+            stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, mypix, v);
+            stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, mypix, v + 16);
+          }
+          if (p.out_hl) stage_store_split32(sbuf, lane, p.out_hl + p.out_hl_coff + nb, p.out_hl_plane, p.out_hl_stride, mypix, v);
+        } else if (EPI == SCF_EPI_GRU_ZR) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = sigmoid_fast(v[i]);
+          if (nb < half) {
+            stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, mypix, v);
+            stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, mypix, v + 16);
+          } else {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              float hv[16];
+              stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux0 + (nb - half) + hh * 16), (long long)p.aux0_stride * 4, mypix, hv);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[hh * 16 + i] *= hv[i];
+            }
+            stage_store_split32(sbuf, lane, p.out2_hl + (nb - half), p.out2_hl_plane, p.out2_hl_stride, mypix, v);
+          }
+        } else {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float hv[16], zv[16];
+            stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux0 + nb + hh * 16), (long long)p.aux0_stride * 4, mypix, hv);
+            stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux1 + nb + hh * 16), (long long)p.aux1_stride * 4, mypix, zv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[hh * 16 + i] = (1.f - zv[i]) * hv[i] + zv[i] * tanh_fast(v[hh * 16 + i]);
+          }
+          if (p.out_f32) {
+            stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, mypix, v);
+            stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, mypix, v + 16);
+          }
+          if (p.out_hl) stage_store_split32(sbuf, lane, p.out_hl + p.out_hl_coff + nb, p.out_hl_plane, p.out_hl_stride, mypix, v);
+        }
+      }
+      g_begin = nslab * 2;
+    }
+    const int g_end = ngroups;
+#pragma unroll 1
+    for (int g = g_begin; g < g_end; ++g) {
       float v[16];
       __syncwarp();
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 16), v);
@@ -533,7 +699,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.num_taps = d.kh * d.kw;
   p.w_batched = d.w_batched;
   const int stage_bytes = 2 * (int)TC_A_PLANE + 2 * p.BN * 128;
-  p.stages = (232448 - 2048) / stage_bytes;
+  p.stages = (232448 - 1024 - TC_HEADER) / stage_bytes;
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
   SCF_REQUIRE(p.stages >= 2, SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: tile does not fit in shared memory");
   {
@@ -541,11 +707,12 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     // overlaps the other's main loop - the fixed per-tile cost is ~40 % of a 9-chunk tile's lifetime otherwise.
     const char* ov = getenv("SCFLOW_TC_OCC2");
     const bool occ2 = ov ? atoi(ov) != 0 : true;
-    if (occ2 && 2 * stage_bytes + 2048 <= 115712 && p.tiles_x * p.tiles_y * cdiv(d.B, p.TB) >= 4 * 148) p.stages = (115712 - 2048) / stage_bytes;
+    if (occ2 && 2 * stage_bytes + 1024 + TC_HEADER <= 115712 && p.tiles_x * p.tiles_y * cdiv(d.B, p.TB) >= 4 * 148)
+      p.stages = (115712 - 1024 - TC_HEADER) / stage_bytes;
   }
   // halo mode for stride-1 multi-tap convolutions
   p.halo = 0; p.PW = p.PH = 0; p.a_stages = 0; p.b_stages = 0;
-  int smem = 1024 + 1024 + p.stages * stage_bytes;
+  int smem = 1024 + TC_HEADER + p.stages * stage_bytes;
   {
     const char* hv = getenv("SCFLOW_TC_HALO");
     const bool want = hv ? atoi(hv) != 0 : false;   // measured: no gain (small-N MMAs are issue-bound, not load-bound)
@@ -553,13 +720,13 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
       const int PW = 8 + d.kw - 1, PH = 16 + d.kh - 1;
       const int a_stage = (2 * PW * PH * 128 + 1023) / 1024 * 1024;
       const int b_stage = 2 * p.BN * 128;
-      int sb = (232448 - 2048 - 2 * a_stage) / b_stage;
+      int sb = (232448 - 1024 - TC_HEADER - 2 * a_stage) / b_stage;
       if (sb > 8) sb = 8;
       if (sb >= 2) {
         p.halo = 1; p.PW = PW; p.PH = PH; p.a_stages = 2; p.b_stages = sb;
         p.TW = 8; p.TH = 16; p.TB = 1;
         p.tiles_x = cdiv(p.W, 8); p.tiles_y = cdiv(p.H, 16);
-        smem = 1024 + 1024 + 2 * a_stage + sb * b_stage;
+        smem = 1024 + TC_HEADER + 2 * a_stage + sb * b_stage;
       }
     }
   }
@@ -632,6 +799,18 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
       cuuint32_t boxs[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.BN / p.cluster), 1, 1};
       SCF_TRY(encode_map(&tmWs, d.w, 4, dims, str, boxs));
     }
+  }
+  {
+    auto al16 = [](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0; };
+    bool ok = true;
+    if (d.out_f32) ok = ok && al16(d.out_f32) && d.out_f32_stride % 4 == 0 && d.out_f32_coff % 4 == 0;
+    if (d.out_hl) ok = ok && al16(d.out_hl) && d.out_hl_stride % 8 == 0 && d.out_hl_coff % 8 == 0 && (d.out_hl_plane * 2) % 16 == 0;
+    if (d.aux0) ok = ok && al16(d.aux0) && d.aux0_stride % 4 == 0;
+    if (d.aux1) ok = ok && al16(d.aux1) && d.aux1_stride % 4 == 0;
+    if (d.out2_hl) ok = ok && al16(d.out2_hl) && d.out2_hl_stride % 8 == 0 && (d.out2_hl_plane * 2) % 16 == 0;
+    if (d.epi == SCF_EPI_GRU_ZR) ok = ok && (d.cout / 2) % 32 == 0;
+    const char* fe = getenv("SCFLOW_TC_FASTEPI");
+    p.fast_epi = (ok && (fe ? atoi(fe) != 0 : true)) ? 1 : 0;
   }
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
   KernelFn kernel = nullptr;
