@@ -23,7 +23,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_THREADS = 192;   // warp 0 TMA, warp 1 MMA + TMEM allocator, warps 2-5 epilogue
 constexpr int TC_STAGE_ROW = 80;  // epilogue staging: 32 rows x 64 B per warp, rows padded to 80 B (conflict-free 16 B accesses)
-constexpr int TC_HEADER = 1024 + 4 * 32 * TC_STAGE_ROW + 1024;   // barriers + staging (+ pad to a multiple of 1024)
+constexpr int TC_HEADER = 1024 + 4 * 32 * TC_STAGE_ROW + 2048;   // barriers + staging + 2 bias buffers (multiple of 1024)
 constexpr uint32_t TC_A_PLANE = TC_BM * TC_BK * 2;   // 16 KB
 constexpr int TC_MAX_STAGES = 4;
 
@@ -32,19 +32,16 @@ struct TcParams {
   int B, H, W, kh, kw, ph, pw;   // H, W: OUTPUT spatial size
   int stride;                    // 1 or 2 (input is sampled at stride*out + tap - pad)
   int TW, TH, TB, tiles_x, tiles_y;   // tile = TW x TH pixels x TB samples = 128 rows
-  int BN, cout, num_taps, w_batched, stages, tmem_cols;
-  long long* dbg_times;        // optional [grid][8] globaltimer stamps (timing experiments only)
-  int debug;                   // timing experiments only (SCFLOW_TC_DEBUG): 1 skip A loads, 2 skip W loads, 4 skip MMAs
-  // halo mode (stride-1 multi-tap convs): the activation tile is fetched ONCE per channel chunk with its kh-1 / kw-1
-  // halo (PW x PH pixel rows) and every tap reads it through a row-shifted UMMA descriptor (tile = 8 x 16 pixels so
-  // that one 8-row core-matrix group = one tile row and the group stride is the halo pitch PW*128 B)
-  int halo, PW, PH, a_stages, b_stages;
+  int m_tiles, num_tiles;        // pixel tiles, pixel tiles x N tiles (tile t: n = t / m_tiles, m = t % m_tiles)
+  int BN, cout, num_taps, w_batched, stages;
+  int acc_cols, tmem_cols;       // TMEM columns of one accumulator buffer / allocated (two buffers)
+  long long* dbg_times;          // optional [grid][8] globaltimer stamps of each CTA's first tile (tools/trace_conv_tc.py)
   // stacked-N mode (BN <= 128): the hi and lo weight planes are adjacent in shared memory, so ONE MMA with N = 2*BN
   // forms A_hi*[W_hi;W_lo] into accumulator columns [0,BN) and [BN,2BN); a second MMA adds A_lo*W_hi into [0,BN).
-  // Two instructions per k-step instead of three (small-N MMAs are issue-bound); the epilogue adds the two halves.
+  // Two instructions per k-step instead of three (less shared-memory operand traffic per FLOP); the epilogue adds
+  // the two halves.
   int stackn;
-  int fast_epi;                // every global access of the epilogue is 16 B aligned: use the coalesced staged path
-  int cluster;                 // CTAs per cluster sharing one weight tile via TMA multicast (1 = none)
+  int fast_epi;                  // every global access of the epilogue is 16 B aligned: use the coalesced staged path
   const float* bias; float scale; int epi, act;
   float* out_f32; int out_f32_stride, out_f32_coff;
   __nv_bfloat16* out_hl; long long out_hl_plane; int out_hl_stride, out_hl_coff;
@@ -189,39 +186,30 @@ __device__ __forceinline__ void store_split16(__nv_bfloat16* hi_dst, long long p
 template <int EPI, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmWs, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024 B alignment
-  // [0,1024): barriers + TMEM pointer. classic: `stages` x {A hi, A lo, W hi, W lo}; halo: A ring then W ring
-  const uint32_t bar_full = smem_base, bar_empty = smem_base + 64, bar_afull = smem_base + 128, bar_aempty = smem_base + 144,
-                 bar_tmem = smem_base + 160, tmem_slot = smem_base + 192;
-  const uint32_t b_plane = (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;                    // classic mode
-  const uint32_t a_plane = (uint32_t)(p.PW * p.PH) * 128u;                      // halo mode
-  const uint32_t a_stage = (2 * a_plane + 1023u) & ~1023u;
-  const uint32_t stage0 = smem_base + 1024;                                     // epilogue staging, 4 warps x 2560 B
-  const uint32_t bias_s = smem_base + 1024 + 4 * 32 * TC_STAGE_ROW;             // this tile's bias (BN floats, zero if none)
+  // header: [0,256) barriers + TMEM pointer | [1024, 11264) epilogue staging | [11264, 13312) two bias buffers ; then the
+  // operand ring: `stages` x {A hi, A lo, W hi, W lo}
+  const uint32_t bar_full = smem_base, bar_empty = smem_base + 64, bar_tfull = smem_base + 128, bar_tempty = smem_base + 144,
+                 tmem_slot = smem_base + 192;
+  const uint32_t stage0 = smem_base + 1024;
+  const uint32_t bias0 = smem_base + 1024 + 4 * 32 * TC_STAGE_ROW;
   const uint32_t tiles0 = smem_base + TC_HEADER;
-  const uint32_t bring0 = tiles0 + (uint32_t)p.a_stages * a_stage;              // halo mode: start of the W ring
+  const uint32_t b_plane = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto stamp = [&](int slot) {
     if (p.dbg_times) {
       long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      p.dbg_times[((long long)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+      p.dbg_times[(long long)blockIdx.x * 8 + slot] = t;
     }
   };
   if (threadIdx.x == 0) stamp(0);
 
-  // ---- tile coordinates
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int b = (blockIdx.x / tiles_per_img) * p.TB;      // first sample of the tile
-  const int tr = blockIdx.x % tiles_per_img;
-  const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
-  const int x0 = tx * p.TW, y0 = ty * p.TH;
-  const int n0 = blockIdx.y * p.BN;
   const int chunks_per_tap = p.seg_chunks[0] + p.seg_chunks[1] + p.seg_chunks[2];
   const int num_chunks = p.num_taps * chunks_per_tap;
 
@@ -229,329 +217,267 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     prefetch_tmap(&tmA0);
     if (p.nseg > 1) prefetch_tmap(&tmA1);
     if (p.nseg > 2) prefetch_tmap(&tmA2);
-    prefetch_tmap(p.cluster > 1 ? &tmWs : &tmW);
-    for (int s = 0; s < (p.halo ? p.b_stages : p.stages); ++s) {
+    prefetch_tmap(&tmW);
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, (uint32_t)p.cluster);   // every CTA of the cluster releases the stage
+      mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int s = 0; s < p.a_stages; ++s) {
-      mbar_init(bar_afull + 8 * s, 1);
-      mbar_init(bar_aempty + 8 * s, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);     // MMA issuer -> epilogue: accumulator a complete
+      mbar_init(bar_tempty + 8 * a, 4);    // 4 epilogue warps -> MMA issuer: accumulator a drained
     }
-    mbar_init(bar_tmem, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  if (warp >= 2) {        // stage the bias slice of this N tile (global-load latency would otherwise sit inside every slab)
-    for (int i = threadIdx.x - 64; i < p.BN; i += TC_THREADS - 64) {
-      const float bvl = (p.bias && blockIdx.y * p.BN + i < p.cout) ? __ldg(p.bias + blockIdx.y * p.BN + i) : 0.f;
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4 * i), "f"(bvl) : "memory");
-    }
-  }
   tc_fence_before();
-  if (p.cluster > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers must exist before any multicast
+  __syncthreads();
   tc_fence_after();
-  const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0u;
-  const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (threadIdx.x == 0) stamp(1);
 
+  // Persistent CTA: tiles blockIdx.x, +gridDim.x, ...  The three roles walk the same tile sequence; the operand ring and
+  // the two TMEM accumulators run on, so tile i+1's loads and MMAs overlap tile i's epilogue.
   if (warp == 0) {
-    if (lane == 0 && !p.halo) {
-      // ================= TMA producer (classic: one {A tap tile, W tile} pair per stage)
+    if (lane == 0) {
+      // ================= TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int tap = 0; tap < p.num_taps; ++tap) {
-        const int ky = tap / p.kw, kx = tap - ky * p.kw;
-        const int cx = x0 * p.stride + kx - p.pw, cy = y0 * p.stride + ky - p.ph;
-        for (int s = 0; s < p.nseg; ++s) {
-          const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
-          for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            const uint32_t full = bar_full + 8 * stage;
-            mbar_arrive_expect_tx(full, ((p.debug & 1) ? 0u : 2 * TC_A_PLANE) + ((p.debug & 2) ? 0u : 2 * b_plane));
-            const uint32_t a_dst = tiles0 + stage * stage_bytes;
-            if (!(p.debug & 1)) tma_load_5d(a_dst, tm, full, cc * TC_BK, cx, cy, b, 0);
-            const int wk = p.seg_wcoff[s] + cc * TC_BK, wt = p.w_batched ? b : tap;
-            if (p.debug & 2) {
-            } else if (p.cluster == 1) {
-              tma_load_4d(a_dst + 2 * TC_A_PLANE, &tmW, full, wk, n0, wt, 0);
-            } else {
-              // this CTA fetches rows [crank*BN/cluster, +BN/cluster) of both planes and multicasts them to the cluster
-              const int rows = p.BN / p.cluster;
-              const uint32_t w_dst = a_dst + 2 * TC_A_PLANE + crank * rows * 128;
-              tma_load_4d_mc(w_dst, &tmWs, full, wk, n0 + crank * rows, wt, 0, cmask);
-              tma_load_4d_mc(w_dst + b_plane, &tmWs, full, wk, n0 + crank * rows, wt, 1, cmask);
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
+        const int b = (mt / tiles_per_img) * p.TB, tr = mt % tiles_per_img;
+        const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+        const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * p.BN;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const int ky = tap / p.kw, kx = tap - ky * p.kw;
+          const int cx = x0 * p.stride + kx - p.pw, cy = y0 * p.stride + ky - p.ph;
+          for (int s = 0; s < p.nseg; ++s) {
+            const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
+            for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+              const uint32_t full = bar_full + 8 * stage;
+              mbar_arrive_expect_tx(full, stage_bytes);
+              const uint32_t a_dst = tiles0 + stage * stage_bytes;
+              tma_load_5d(a_dst, tm, full, cc * TC_BK, cx, cy, b, 0);
+              tma_load_4d(a_dst + 2 * TC_A_PLANE, &tmW, full, p.seg_wcoff[s] + cc * TC_BK, n0, p.w_batched ? b : tap, 0);
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-          }
-        }
-      }
-    } else if (lane == 0) {
-      // ================= TMA producer (halo: one activation halo tile per channel chunk, one W tile per tap)
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
-        for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
-          mbar_wait(bar_aempty + 8 * sa, pa ^ 1u);
-          mbar_arrive_expect_tx(bar_afull + 8 * sa, 2 * a_plane);
-          tma_load_5d(tiles0 + sa * a_stage, tm, bar_afull + 8 * sa, cc * TC_BK, x0 - p.pw, y0 - p.ph, b, 0);
-          if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
-          const int wk = p.seg_wcoff[s] + cc * TC_BK;
-          for (int tap = 0; tap < p.num_taps; ++tap) {
-            mbar_wait(bar_empty + 8 * sb, pb ^ 1u);
-            const uint32_t full = bar_full + 8 * sb;
-            mbar_arrive_expect_tx(full, 2 * b_plane);
-            const uint32_t w_dst0 = bring0 + sb * 2 * b_plane;
-            if (p.cluster == 1) {
-              tma_load_4d(w_dst0, &tmW, full, wk, n0, tap, 0);
-            } else {
-              const int rows = p.BN / p.cluster;
-              const uint32_t w_dst = w_dst0 + crank * rows * 128;
-              tma_load_4d_mc(w_dst, &tmWs, full, wk, n0 + crank * rows, tap, 0, cmask);
-              tma_load_4d_mc(w_dst + b_plane, &tmWs, full, wk, n0 + crank * rows, tap, 1, cmask);
-            }
-            if (++sb == p.b_stages) { sb = 0; pb ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && !p.halo) {
-      // ================= MMA issuer (classic)
+    if (lane == 0) {
+      // ================= MMA issuer
       const uint32_t idesc = make_idesc_bf16(TC_BM, p.BN), idesc2 = make_idesc_bf16(TC_BM, 2 * p.BN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int c = 0; c < num_chunks; ++c) {
-        mbar_wait(bar_full + 8 * stage, phase);
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(bar_tempty + 8 * acc, (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue of tile it-2 has drained this buffer
         tc_fence_after();
-        if (c == 0) stamp(2);
-        const uint32_t a_addr = tiles0 + stage * stage_bytes;
-        const uint64_t a_hi = make_smem_desc_sw128(a_addr, 1024), a_lo = make_smem_desc_sw128(a_addr + TC_A_PLANE, 1024);
-        const uint64_t b_hi = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE, 1024);
-        const uint64_t b_lo = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + b_plane, 1024);
-        if (p.stackn) {
-#pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t ko = (uint64_t)(k * 32 >> 4);
-            umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc2, (c > 0 || k > 0) ? 1u : 0u);   // N = 2*BN: [W_hi;W_lo]
-            umma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < ((p.debug & 4) ? 0 : TC_BK / 16); ++k) {
-            const uint64_t ko = (uint64_t)(k * 32 >> 4);     // 16 bf16 = 32 B along the swizzled 128 B row
-            umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, (c > 0 || k > 0) ? 1u : 0u);
-            umma_bf16(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
-            umma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
-          }
-        }
-        if (p.cluster == 1) umma_commit(bar_empty + 8 * stage);   // frees the smem slot once these MMAs have read it
-        else umma_commit_mc(bar_empty + 8 * stage, cmask);
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-      }
-      umma_commit(bar_tmem);                      // accumulator complete
-      stamp(3);
-    } else if (lane == 0) {
-      // ================= MMA issuer (halo): tap (ky,kx) = the halo tile read from row offset ky*PW + kx; SWIZZLE_128B is
-      // a function of the absolute smem address for TMA and UMMA alike, so any 128 B row offset is a valid operand start
-      const uint32_t idesc = make_idesc_bf16(TC_BM, p.BN), idesc2 = make_idesc_bf16(TC_BM, 2 * p.BN);
-      const uint32_t a_sbo = (uint32_t)p.PW * 128u;
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      const int nchunk = chunks_per_tap;
-      for (int c = 0; c < nchunk; ++c) {
-        mbar_wait(bar_afull + 8 * sa, pa);
-        const uint32_t a_base = tiles0 + sa * a_stage;
-        for (int tap = 0; tap < p.num_taps; ++tap) {
-          mbar_wait(bar_full + 8 * sb, pb);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
+        for (int c = 0; c < num_chunks; ++c) {
+          mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          if (c == 0 && tap == 0) stamp(2);
-          const int ky = tap / p.kw, kx = tap - ky * p.kw;
-          const uint32_t a_addr = a_base + (uint32_t)(ky * p.PW + kx) * 128u;
-          const uint64_t a_hi = make_smem_desc_sw128(a_addr, a_sbo), a_lo = make_smem_desc_sw128(a_addr + a_plane, a_sbo);
-          const uint32_t w_addr = bring0 + sb * 2 * b_plane;
-          const uint64_t b_hi = make_smem_desc_sw128(w_addr, 1024), b_lo = make_smem_desc_sw128(w_addr + b_plane, 1024);
+          if (it == 0 && c == 0) stamp(2);
+          const uint32_t a_addr = tiles0 + stage * stage_bytes;
+          const uint64_t a_hi = make_smem_desc_sw128(a_addr, 1024), a_lo = make_smem_desc_sw128(a_addr + TC_A_PLANE, 1024);
+          const uint64_t b_hi = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE, 1024);
+          const uint64_t b_lo = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + b_plane, 1024);
           if (p.stackn) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
-              const uint64_t ko = (uint64_t)(k * 32 >> 4);
-              umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc2, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
-              umma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
+              const uint64_t ko = (uint64_t)(k * 32 >> 4);     // 16 bf16 = 32 B along the swizzled 128 B row
+              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc2, (c > 0 || k > 0) ? 1u : 0u);   // N = 2*BN: [W_hi;W_lo]
+              umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
             }
           } else {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
               const uint64_t ko = (uint64_t)(k * 32 >> 4);
-              umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
-              umma_bf16(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
-              umma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
+              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, (c > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
             }
           }
-          if (p.cluster == 1) umma_commit(bar_empty + 8 * sb);
-          else umma_commit_mc(bar_empty + 8 * sb, cmask);
-          if (++sb == p.b_stages) { sb = 0; pb ^= 1u; }
+          umma_commit(bar_empty + 8 * stage);     // frees the smem slot once these MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(bar_aempty + 8 * sa);         // all taps of this chunk have read the halo tile
-        if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+        umma_commit(bar_tfull + 8 * acc);         // accumulator complete
+        if (it == 0) stamp(3);
       }
-      umma_commit(bar_tmem);
-      stamp(3);
     }
   } else {
     // ================= epilogue: warp w owns TMEM lanes 32*(w%4)..+31 ; lane = pixel row of the tile
-    mbar_wait(bar_tmem, 0);
-    tc_fence_after();
-    if (threadIdx.x == 64) stamp(4);
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int bb = row / (p.TW * p.TH), rr = row - bb * (p.TW * p.TH);
     const int h = rr / p.TW, w = rr - h * p.TW;
-    const int y = y0 + h, x = x0 + w;
-    const bool valid = y < p.H && x < p.W && b + bb < p.B;
-    const long long pix = ((long long)(b + bb) * p.H + y) * p.W + x;
     const int half = p.cout >> 1;
     const int ngroups = p.BN / 16;
-    int g_begin = 0;
-    if (p.fast_epi) {
-      // ---- coalesced path: 32-column slabs, every global access staged through shared memory
-      const uint32_t sbuf = stage0 + (uint32_t)(warp - 2) * 32 * TC_STAGE_ROW;
-      const long long mypix = valid ? pix : -1;
-      const int nslab = (p.cout - n0 < p.BN ? p.cout - n0 : p.BN) / 32;      // full slabs only; the tail uses the plain path
+    const uint32_t sbuf = stage0 + (uint32_t)(warp - 2) * 32 * TC_STAGE_ROW;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
+      const int b = (mt / tiles_per_img) * p.TB, tr = mt % tiles_per_img;
+      const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+      const int y = ty * p.TH + h, x = tx * p.TW + w, n0 = nt * p.BN;
+      const bool valid = y < p.H && x < p.W && b + bb < p.B;
+      const long long pix = ((long long)(b + bb) * p.H + y) * p.W + x;
+      const uint32_t bias_s = bias0 + (uint32_t)acc * 1024u;
+      // stage this tile's bias slice (global-load latency would otherwise sit inside every column slab); the named barrier
+      // also orders it against the slowest warp still reading the buffer two tiles ago
+      for (int i = threadIdx.x - 64; i < p.BN; i += 128) {
+        const float bvl = (p.bias && n0 + i < p.cout) ? __ldg(p.bias + n0 + i) : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4 * i), "f"(bvl) : "memory");
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(bar_tfull + 8 * acc, ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      if (it == 0 && threadIdx.x == 64) stamp(4);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+      int g_begin = 0;
+      if (p.fast_epi) {
+        // ---- coalesced path: 32-column slabs, every global access staged through shared memory
+        const long long mypix = valid ? pix : -1;
+        const int nslab = (p.cout - n0 < p.BN ? p.cout - n0 : p.BN) / 32;    // full slabs only; the tail uses the plain path
 #pragma unroll 1
-      for (int sl = 0; sl < nslab; ++sl) {
-        float v[32];
-        __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sl * 32), v);
-        if (p.stackn) {
-          float v2[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + sl * 32), v2);
+        for (int sl = 0; sl < nslab; ++sl) {
+          float v[32];
+          __syncwarp();
+          tmem_ld32(t_addr + (uint32_t)(sl * 32), v);
+          if (p.stackn) {
+            float v2[32];
+            tmem_ld32(t_addr + (uint32_t)(p.BN + sl * 32), v2);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += v2[i];
-        }
-        const int nb = n0 + sl * 32;
+            for (int i = 0; i < 32; ++i) v[i] += v2[i];
+          }
+          const int nb = n0 + sl * 32;
 #pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {             // bias from shared memory (same address in every lane: broadcast)
-          float4 bq;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bq.x), "=f"(bq.y), "=f"(bq.z), "=f"(bq.w)
-                       : "r"(bias_s + (uint32_t)(sl * 32 + i4 * 4) * 4));
-          v[4 * i4] = fmaf(v[4 * i4], p.scale, bq.x); v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], p.scale, bq.y);
-          v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], p.scale, bq.z); v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], p.scale, bq.w);
-        }
-        if (EPI == SCF_EPI_ACT) {
-          if (p.aux0) {
+          for (int i4 = 0; i4 < 8; ++i4) {           // bias from shared memory (same address in every lane: broadcast)
+            float4 bq;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bq.x), "=f"(bq.y), "=f"(bq.z), "=f"(bq.w)
+                         : "r"(bias_s + (uint32_t)(sl * 32 + i4 * 4) * 4));
+            v[4 * i4] = fmaf(v[4 * i4], p.scale, bq.x); v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], p.scale, bq.y);
+            v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], p.scale, bq.z); v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], p.scale, bq.w);
+          }
+          if (EPI == SCF_EPI_ACT) {
+            if (p.aux0) {
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              float rv[16];
-              stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux0 + nb + hh * 16), (long long)p.aux0_stride * 4, mypix, rv);
+              for (int hh = 0; hh < 2; ++hh) {
+                float rv[16];
+                stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux0 + nb + hh * 16), (long long)p.aux0_stride * 4, mypix, rv);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[hh * 16 + i] += rv[i];
+                for (int i = 0; i < 16; ++i) v[hh * 16 + i] += rv[i];
+              }
             }
-          }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = act_ct<ACT>(v[i]);
-          if (p.out_f32) {
-            stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, mypix, v);
-            stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, mypix, v + 16);
-          }
-          if (p.out_hl) stage_store_split32(sbuf, lane, p.out_hl + p.out_hl_coff + nb, p.out_hl_plane, p.out_hl_stride, mypix, v);
-        } else if (EPI == SCF_EPI_GRU_ZR) {
+            for (int i = 0; i < 32; ++i) v[i] = act_ct<ACT>(v[i]);
+            if (p.out_f32) {
+              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, mypix, v);
+              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, mypix, v + 16);
+            }
+            if (p.out_hl) stage_store_split32(sbuf, lane, p.out_hl + p.out_hl_coff + nb, p.out_hl_plane, p.out_hl_stride, mypix, v);
+          } else if (EPI == SCF_EPI_GRU_ZR) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = sigmoid_fast(v[i]);
-          if (nb < half) {
-            stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, mypix, v);
-            stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, mypix, v + 16);
+            for (int i = 0; i < 32; ++i) v[i] = sigmoid_fast(v[i]);
+            if (nb < half) {
+              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, mypix, v);
+              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, mypix, v + 16);
+            } else {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                float hv[16];
+                stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux0 + (nb - half) + hh * 16), (long long)p.aux0_stride * 4, mypix, hv);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[hh * 16 + i] *= hv[i];
+              }
+              stage_store_split32(sbuf, lane, p.out2_hl + (nb - half), p.out2_hl_plane, p.out2_hl_stride, mypix, v);
+            }
           } else {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              float hv[16];
-              stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux0 + (nb - half) + hh * 16), (long long)p.aux0_stride * 4, mypix, hv);
+              float hv[16], zv[16];
+              stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux0 + nb + hh * 16), (long long)p.aux0_stride * 4, mypix, hv);
+              stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux1 + nb + hh * 16), (long long)p.aux1_stride * 4, mypix, zv);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[hh * 16 + i] *= hv[i];
+              for (int i = 0; i < 16; ++i) v[hh * 16 + i] = (1.f - zv[i]) * hv[i] + zv[i] * tanh_fast(v[hh * 16 + i]);
             }
-            stage_store_split32(sbuf, lane, p.out2_hl + (nb - half), p.out2_hl_plane, p.out2_hl_stride, mypix, v);
+            if (p.out_f32) {
+              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, mypix, v);
+              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, mypix, v + 16);
+            }
+            if (p.out_hl) stage_store_split32(sbuf, lane, p.out_hl + p.out_hl_coff + nb, p.out_hl_plane, p.out_hl_stride, mypix, v);
           }
-        } else {
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            float hv[16], zv[16];
-            stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux0 + nb + hh * 16), (long long)p.aux0_stride * 4, mypix, hv);
-            stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux1 + nb + hh * 16), (long long)p.aux1_stride * 4, mypix, zv);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[hh * 16 + i] = (1.f - zv[i]) * hv[i] + zv[i] * tanh_fast(v[hh * 16 + i]);
-          }
-          if (p.out_f32) {
-            stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, mypix, v);
-            stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, mypix, v + 16);
-          }
-          if (p.out_hl) stage_store_split32(sbuf, lane, p.out_hl + p.out_hl_coff + nb, p.out_hl_plane, p.out_hl_stride, mypix, v);
         }
+        g_begin = nslab * 2;
       }
-      g_begin = nslab * 2;
-    }
-    const int g_end = ngroups;
+      // ---- plain path (ragged channel tails, unaligned outputs): 16-column groups, direct per-thread stores
 #pragma unroll 1
-    for (int g = g_begin; g < g_end; ++g) {
-      float v[16];
+      for (int g = g_begin; g < ngroups; ++g) {
+        float v[16];
+        __syncwarp();
+        tmem_ld16(t_addr + (uint32_t)(g * 16), v);
+        if (p.stackn) {                        // second half of the stacked accumulator: A_hi * W_lo
+          float v2[16];
+          tmem_ld16(t_addr + (uint32_t)(p.BN + g * 16), v2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += v2[i];
+        }
+        const int nb = n0 + g * 16;
+        if (!valid || nb >= p.cout) continue;
+        const int nvalid = p.cout - nb < 16 ? p.cout - nb : 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float bq;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bq) : "r"(bias_s + (uint32_t)(g * 16 + i) * 4));
+          v[i] = fmaf(v[i], p.scale, bq);
+        }
+        if (EPI == SCF_EPI_ACT) {
+          if (p.aux0) {                        // residual connection (encoder BasicBlock): added before the activation
+            float rv[16];
+            load16(p.aux0 + pix * p.aux0_stride + nb, rv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += rv[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = act_ct<ACT>(v[i]);
+          if (p.out_f32) store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, nvalid);
+          if (p.out_hl) store_split16(p.out_hl + pix * p.out_hl_stride + p.out_hl_coff + nb, p.out_hl_plane, v, nvalid);
+        } else if (EPI == SCF_EPI_GRU_ZR) {    // cout = 2*Ch, Ch % 16 == 0: a group is entirely z or entirely r
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = sigmoid_fast(v[i]);
+          if (nb < half) {                     // z gate -> fp32 (read back by the q convolution's epilogue)
+            store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, 16);
+          } else {                             // r gate -> r*h as split-bf16, the q convolution's first input segment
+            float hv[16];
+            load16(p.aux0 + pix * p.aux0_stride + (nb - half), hv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= hv[i];
+            store_split16(p.out2_hl + pix * p.out2_hl_stride + (nb - half), p.out2_hl_plane, v, 16);
+          }
+        } else {                               // SCF_EPI_GRU_Q: h' = (1-z) h + z tanh(.)   (cout % 16 == 0)
+          float hv[16], zv[16];
+          load16(p.aux0 + pix * p.aux0_stride + nb, hv);
+          load16(p.aux1 + pix * p.aux1_stride + nb, zv);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (1.f - zv[i]) * hv[i] + zv[i] * tanh_fast(v[i]);
+          if (p.out_f32) store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, 16);
+          if (p.out_hl) store_split16(p.out_hl + pix * p.out_hl_stride + p.out_hl_coff + nb, p.out_hl_plane, v, 16);
+        }
+      }
+      // this warp has read everything it needs from accumulator `acc`: hand it back to the MMA issuer
+      tc_fence_before();
       __syncwarp();
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 16), v);
-      if (p.stackn) {                        // second half of the stacked accumulator: A_hi * W_lo
-        float v2[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + g * 16), v2);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += v2[i];
-      }
-      const int nb = n0 + g * 16;
-      if (!valid || nb >= p.cout) continue;
-      const int nvalid = p.cout - nb < 16 ? p.cout - nb : 16;
-      if (p.bias) {                          // bias buffers are readable up to cout_pad (multiple of 16)
-        float bv[16];
-        load16(p.bias + nb, bv);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], p.scale, bv[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= p.scale;
-      }
-      if (EPI == SCF_EPI_ACT) {
-        if (p.aux0) {                        // residual connection (encoder BasicBlock): added before the activation
-          float rv[16];
-          load16(p.aux0 + pix * p.aux0_stride + nb, rv);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += rv[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = act_ct<ACT>(v[i]);
-        if (p.out_f32) store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, nvalid);
-        if (p.out_hl) store_split16(p.out_hl + pix * p.out_hl_stride + p.out_hl_coff + nb, p.out_hl_plane, v, nvalid);
-      } else if (EPI == SCF_EPI_GRU_ZR) {    // cout = 2*Ch, Ch % 16 == 0: a group is entirely z or entirely r
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = sigmoid_fast(v[i]);
-        if (nb < half) {                     // z gate -> fp32 (read back by the q convolution's epilogue)
-          store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, 16);
-        } else {                             // r gate -> r*h as split-bf16, the q convolution's first input segment
-          float hv[16];
-          load16(p.aux0 + pix * p.aux0_stride + (nb - half), hv);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= hv[i];
-          store_split16(p.out2_hl + pix * p.out2_hl_stride + (nb - half), p.out2_hl_plane, v, 16);
-        }
-      } else {                               // SCF_EPI_GRU_Q: h' = (1-z) h + z tanh(.)   (cout % 16 == 0)
-        float hv[16], zv[16];
-        load16(p.aux0 + pix * p.aux0_stride + nb, hv);
-        load16(p.aux1 + pix * p.aux1_stride + nb, zv);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (1.f - zv[i]) * hv[i] + zv[i] * tanh_fast(v[i]);
-        if (p.out_f32) store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, 16);
-        if (p.out_hl) store_split16(p.out_hl + pix * p.out_hl_stride + p.out_hl_coff + nb, p.out_hl_plane, v, 16);
-      }
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (it == 0 && threadIdx.x == 64) stamp(5);
     }
   }
-  if (threadIdx.x == 64) stamp(5);
   tc_fence_before();
-  if (p.cluster > 1) cluster_sync_all(); else __syncthreads();   // no CTA may exit while peers can still signal it
+  __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   if (threadIdx.x == 32) stamp(6);
 }
@@ -698,72 +624,48 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.cout = d.cout;
   p.num_taps = d.kh * d.kw;
   p.w_batched = d.w_batched;
+  p.m_tiles = p.tiles_x * p.tiles_y * cdiv(d.B, p.TB);
+  p.num_tiles = p.m_tiles * cdiv(d.cout_pad, p.BN);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    SCF_CUDA(cudaGetDevice(&dev));
+    SCF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   const int stage_bytes = 2 * (int)TC_A_PLANE + 2 * p.BN * 128;
   p.stages = (232448 - 1024 - TC_HEADER) / stage_bytes;
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
   SCF_REQUIRE(p.stages >= 2, SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: tile does not fit in shared memory");
   {
-    // Small tiles (BN <= 64): keep two CTAs resident per SM (<= 113 KB each) so that one CTA's prologue / epilogue
-    // overlaps the other's main loop - the fixed per-tile cost is ~40 % of a 9-chunk tile's lifetime otherwise.
-    const char* ov = getenv("SCFLOW_TC_OCC2");
-    const bool occ2 = ov ? atoi(ov) != 0 : true;
-    if (occ2 && 2 * stage_bytes + 1024 + TC_HEADER <= 115712 && p.tiles_x * p.tiles_y * cdiv(d.B, p.TB) >= 4 * 148)
-      p.stages = (115712 - 1024 - TC_HEADER) / stage_bytes;
-  }
-  // halo mode for stride-1 multi-tap convolutions
-  p.halo = 0; p.PW = p.PH = 0; p.a_stages = 0; p.b_stages = 0;
-  int smem = 1024 + TC_HEADER + p.stages * stage_bytes;
-  {
-    const char* hv = getenv("SCFLOW_TC_HALO");
-    const bool want = hv ? atoi(hv) != 0 : false;   // measured: no gain (small-N MMAs are issue-bound, not load-bound)
-    if (want && stride == 1 && p.num_taps > 1 && !d.w_batched) {
-      const int PW = 8 + d.kw - 1, PH = 16 + d.kh - 1;
-      const int a_stage = (2 * PW * PH * 128 + 1023) / 1024 * 1024;
-      const int b_stage = 2 * p.BN * 128;
-      int sb = (232448 - 1024 - TC_HEADER - 2 * a_stage) / b_stage;
-      if (sb > 8) sb = 8;
-      if (sb >= 2) {
-        p.halo = 1; p.PW = PW; p.PH = PH; p.a_stages = 2; p.b_stages = sb;
-        p.TW = 8; p.TH = 16; p.TB = 1;
-        p.tiles_x = cdiv(p.W, 8); p.tiles_y = cdiv(p.H, 16);
-        smem = 1024 + TC_HEADER + 2 * a_stage + sb * b_stage;
-      }
-    }
-  }
-  const int m_tiles = p.tiles_x * p.tiles_y * cdiv(d.B, p.TB);
-  {
     const char* sv = getenv("SCFLOW_TC_STACKN");
     p.stackn = (p.BN <= 128 && (sv ? atoi(sv) != 0 : true)) ? 1 : 0;
   }
+  p.acc_cols = p.stackn ? 2 * p.BN : p.BN;
   p.tmem_cols = 32;
-  while (p.tmem_cols < (p.stackn ? 2 * p.BN : p.BN)) p.tmem_cols <<= 1;
+  while (p.tmem_cols < 2 * p.acc_cols) p.tmem_cols <<= 1;
+  int ctas_per_sm = 1;
+  {
+    // Small tiles: keep two CTAs resident per SM (<= 113 KB of shared memory and <= 256 TMEM columns each) so that the two
+    // CTAs' main loops interleave; larger tiles run one persistent CTA per SM with double-buffered accumulators.
+    const char* ov = getenv("SCFLOW_TC_OCC2");
+    const bool occ2 = ov ? atoi(ov) != 0 : true;
+    if (occ2 && 2 * stage_bytes + 1024 + TC_HEADER <= 115712 && p.tmem_cols <= 256 && p.num_tiles >= 4 * num_sms) {
+      p.stages = (115712 - 1024 - TC_HEADER) / stage_bytes;
+      ctas_per_sm = 2;
+    }
+  }
+  const int smem = 1024 + TC_HEADER + p.stages * stage_bytes;
   p.bias = d.bias; p.scale = d.scale; p.epi = d.epi; p.act = d.act;
   p.out_f32 = d.out_f32; p.out_f32_stride = d.out_f32_stride; p.out_f32_coff = d.out_f32_coff;
   p.out_hl = reinterpret_cast<__nv_bfloat16*>(d.out_hl); p.out_hl_plane = d.out_hl_plane; p.out_hl_stride = d.out_hl_stride;
   p.out_hl_coff = d.out_hl_coff;
   p.aux0 = d.aux0; p.aux0_stride = d.aux0_stride; p.aux1 = d.aux1; p.aux1_stride = d.aux1_stride;
   p.out2_hl = reinterpret_cast<__nv_bfloat16*>(d.out2_hl); p.out2_hl_plane = d.out2_hl_plane; p.out2_hl_stride = d.out2_hl_stride;
-
-  // cluster size: share the weight tile between CTAs of consecutive pixel tiles (same sample when weights are batched)
   {
-    int cs = 1;
-    const char* env = getenv("SCFLOW_TC_CLUSTER");
-    int want = env ? atoi(env) : 1;   // multicast measured no gain on B200 for these shapes (profiles/r01_summary.md)
-    const int mt = m_tiles;
-    for (int c = 8; c >= 2; c >>= 1) {
-      if (c > want) continue;
-      if (mt % c != 0 || (p.BN / c) % 8 != 0 || p.BN % c != 0) continue;
-      if (d.w_batched && (p.tiles_x * p.tiles_y) % c != 0) continue;
-      cs = c;
-      break;
-    }
-    p.cluster = cs;
-    const char* dbg = getenv("SCFLOW_TC_DEBUG");
-    p.debug = dbg ? atoi(dbg) : 0;
     const char* dt = getenv("SCFLOW_TC_DBG_TIMES");       // address of a device buffer, hex (timing experiments only)
     p.dbg_times = dt ? reinterpret_cast<long long*>(strtoull(dt, nullptr, 16)) : nullptr;
   }
-  CUtensorMap tmA[3], tmW, tmWs;
+  CUtensorMap tmA[3], tmW;
   int wcoff = 0;
   for (int s = 0; s < 3; ++s) {
     if (s >= d.nseg) { tmA[s] = tmA[0]; p.seg_chunks[s] = 0; p.seg_wcoff[s] = 0; continue; }
@@ -778,7 +680,6 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
                          (cuuint64_t)sg.plane_stride * 2};
     // box = elements TRAVERSED per dimension; with element strides (1,s,s,1,1) it deposits TW x TH x TB pixels
     cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TB, 2};
-    if (p.halo) { box[1] = (cuuint32_t)p.PW; box[2] = (cuuint32_t)p.PH; }
     cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
     SCF_TRY(encode_map(&tmA[s], base, 5, dims, str, box, estr));
     p.seg_chunks[s] = cdiv(sg.nch, TC_BK);
@@ -794,11 +695,6 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)p.BN, 1, 2};
     SCF_REQUIRE(reinterpret_cast<uintptr_t>(d.w) % 16 == 0, SCF_ERR_ALIGN, "scf_conv2d_tc: packed weight must be 16B aligned");
     SCF_TRY(encode_map(&tmW, d.w, 4, dims, str, box));
-    tmWs = tmW;
-    if (p.cluster > 1) {
-      cuuint32_t boxs[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.BN / p.cluster), 1, 1};
-      SCF_TRY(encode_map(&tmWs, d.w, 4, dims, str, boxs));
-    }
   }
   {
     auto al16 = [](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0; };
@@ -812,7 +708,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     const char* fe = getenv("SCFLOW_TC_FASTEPI");
     p.fast_epi = (ok && (fe ? atoi(fe) != 0 : true)) ? 1 : 0;
   }
-  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
   KernelFn kernel = nullptr;
   if (d.epi == SCF_EPI_GRU_ZR) kernel = conv_tc_kernel<SCF_EPI_GRU_ZR, SCF_ACT_SIGMOID>;
   else if (d.epi == SCF_EPI_GRU_Q) kernel = conv_tc_kernel<SCF_EPI_GRU_Q, SCF_ACT_TANH>;
@@ -833,17 +729,9 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     }
   });
   SCF_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(attr_err));
-  cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3(m_tiles, cdiv(d.cout_pad, p.BN));
-  lc.blockDim = dim3(TC_THREADS);
-  lc.dynamicSmemBytes = smem;
-  lc.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = p.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  lc.attrs = attr; lc.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&lc, kernel, tmA[0], tmA[1], tmA[2], tmW, tmWs, p);
-  if (le != cudaSuccess) { cudaGetLastError(); set_error("conv_tc_kernel launch (cluster %d): %s", p.cluster, cudaGetErrorString(le)); return (int)le; }
+  const int max_ctas = num_sms * ctas_per_sm;
+  const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
+  kernel<<<grid, TC_THREADS, smem, st>>>(tmA[0], tmA[1], tmA[2], tmW, p);
   return check_launch("conv_tc_kernel");
 }
 
