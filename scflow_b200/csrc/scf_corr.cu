@@ -90,6 +90,92 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) 
   }
 }
 
+// Specialised lookup for the shipped configuration (4 levels, radius 4): one warp per query.
+//  * the un-normalised coordinate of a tap depends on ONE window index per axis, so per level lanes 0-8 replay the
+//    reference's fp32 sequence for the 9 x-offsets and lanes 9-17 for the 9 y-offsets (18 instead of 162 divisions);
+//    taps fetch (floor, frac weights) by shuffle - neighbour indices stay bit-identical to the generic kernel;
+//  * all 12 (level, round) tap groups are unrolled and their 48 gathers issued before any is consumed, so a query
+//    pays one L2 latency instead of twelve.
+__global__ void __launch_bounds__(256) corr_lookup_l4r4_kernel(const LookupParams p) {
+  constexpr int R = 4, K = 9, KK = 81, L = 4, ROUNDS = 3;
+  const int lane = threadIdx.x & 31;
+  const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= p.nq) return;
+  const int P = p.H8 * p.W8;
+  const int pix = (int)(q % P);
+  const int y = pix / p.W8, x = pix - y * p.W8;
+  const float2 f = *reinterpret_cast<const float2*>(p.flow8 + q * 2);
+  const float gx0 = __fadd_rn((float)x, f.x), gy0 = __fadd_rn((float)y, f.y);
+  const float mval = p.mask ? p.mask[q] : 1.f;
+  // ---- per-axis coordinates: lane a (0..8) -> x axis offset a-R ; lane 9+b -> y axis offset b-R
+  int i0[L];
+  float w0[L], w1[L];
+  float inv = 1.f;
+#pragma unroll
+  for (int l = 0; l < L; ++l, inv *= 0.5f) {
+    const bool isx = lane < K;
+    const int off = (isx ? lane : lane - K) - R;
+    const float c = __fmul_rn(isx ? gx0 : gy0, inv);
+    const float ic = lookup_coord(c, off, isx ? p.wl[l] : p.hl[l]);
+    const float fl = floorf(ic);
+    i0[l] = (int)fl;
+    w1[l] = ic - fl;
+    w0[l] = (fl + 1.f) - ic;
+  }
+  // ---- gather: issue every load first
+  float v[L][ROUNDS][4], wgt[L][ROUNDS][4];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const int hl = p.hl[l], wl = p.wl[l];
+    const float* vol = p.lvl[l] + q * (long long)(hl * wl);
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const int tap = r * 32 + lane;
+      const int tc = tap < KK ? tap : KK - 1;          // lanes past the window replay the last tap (result discarded)
+      const int a = tc / K, b = tc - a * K;
+      const int x0 = __shfl_sync(0xffffffffu, i0[l], a), y0 = __shfl_sync(0xffffffffu, i0[l], K + b);
+      const float wx0 = __shfl_sync(0xffffffffu, w0[l], a), wx1 = __shfl_sync(0xffffffffu, w1[l], a);
+      const float wy0 = __shfl_sync(0xffffffffu, w0[l], K + b), wy1 = __shfl_sync(0xffffffffu, w1[l], K + b);
+      const bool xin0 = x0 >= 0 && x0 < wl, xin1 = x0 + 1 >= 0 && x0 + 1 < wl;
+      const bool yin0 = y0 >= 0 && y0 < hl, yin1 = y0 + 1 >= 0 && y0 + 1 < hl;
+      const float* r0 = vol + y0 * wl + x0;
+      v[l][r][0] = (yin0 && xin0) ? __ldg(r0) : 0.f;
+      v[l][r][1] = (yin0 && xin1) ? __ldg(r0 + 1) : 0.f;
+      v[l][r][2] = (yin1 && xin0) ? __ldg(r0 + wl) : 0.f;
+      v[l][r][3] = (yin1 && xin1) ? __ldg(r0 + wl + 1) : 0.f;
+      wgt[l][r][0] = wx0 * wy0; wgt[l][r][1] = wx1 * wy0; wgt[l][r][2] = wx0 * wy1; wgt[l][r][3] = wx1 * wy1;
+    }
+  }
+  float* outq = p.out ? p.out + q * p.out_stride + p.out_coff : nullptr;
+  __nv_bfloat16* outh = p.out_hl ? p.out_hl + q * p.out_stride : nullptr;
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const int tap = r * 32 + lane;
+      if (tap >= KK) continue;
+      // same accumulation order as the generic kernel / ATen: nw, ne, sw, se, skipping out-of-range taps
+      float acc = 0.f;
+      acc += v[l][r][0] * wgt[l][r][0];
+      acc += v[l][r][1] * wgt[l][r][1];
+      acc += v[l][r][2] * wgt[l][r][2];
+      acc += v[l][r][3] * wgt[l][r][3];
+      acc *= mval;
+      if (outq) outq[l * KK + tap] = acc;
+      if (outh) {
+        __nv_bfloat16 hi, lo;
+        tc::split_bf16(acc, hi, lo);
+        outh[l * KK + tap] = hi;
+        outh[p.out_hl_plane + l * KK + tap] = lo;
+      }
+    }
+  }
+  if (outh) {
+    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+    for (int c = L * KK + lane; c < p.out_stride; c += 32) { outh[c] = zero; outh[p.out_hl_plane + c] = zero; }
+  }
+}
+
 __global__ void corr_lookup_taps_kernel(int level, int radius, const float* __restrict__ flow8, int32_t* __restrict__ x0,
                                         int32_t* __restrict__ y0, int H8, int W8, long long nq) {
   const int k = 2 * radius + 1;
@@ -187,6 +273,10 @@ static int corr_lookup_impl(const float* const* h_levels, int num_levels, int ra
   p.out_hl = reinterpret_cast<__nv_bfloat16*>(out_hl); p.out_hl_plane = plane;
   p.out_stride = out_stride; p.out_coff = out_coff; p.H8 = H8; p.W8 = W8; p.nq = (long long)B * H8 * W8;
   const int wpb = 8;
+  if (num_levels == 4 && radius == 4) {
+    scf::corr_lookup_l4r4_kernel<<<scf::cdiv(p.nq, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(p);
+    return scf::check_launch("corr_lookup_l4r4_kernel");
+  }
   scf::corr_lookup_kernel<<<scf::cdiv(p.nq, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(p);
   return scf::check_launch("corr_lookup_kernel");
 }

@@ -104,6 +104,16 @@ __global__ void __launch_bounds__(256) linear_smem_kernel(const float* __restric
     float acc[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    // the warp's weight row is fetched up front (I <= 2048: 16 float4 per lane) so its latency overlaps the x staging
+    float4 wreg[16];
+    const bool wpre = I <= 2048;
+    if (wpre) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int k = u * 128 + lane * 4;
+        wreg[u] = k < I ? __ldg(reinterpret_cast<const float4*>(wr + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     for (int k0 = 0; k0 < I; k0 += LIN_KC) {
       __syncthreads();
       for (int idx = threadIdx.x; idx < 32 * (LIN_KC / 4); idx += 256) {
@@ -117,7 +127,13 @@ __global__ void __launch_bounds__(256) linear_smem_kernel(const float* __restric
       for (int h = 0; h < LIN_KC / 128; ++h) {
         const int k = h * 128 + lane * 4;
         float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k0 + k < I) wv = __ldg(reinterpret_cast<const float4*>(wr + k0 + k));
+        if (wpre) {
+          const int u = (k0 >> 7) + h;           // k0 / 128 + h  (LIN_KC = 256 -> two register slots per chunk)
+#pragma unroll
+          for (int uu = 0; uu < 16; ++uu) if (uu == u) wv = wreg[uu];
+        } else if (k0 + k < I) {
+          wv = __ldg(reinterpret_cast<const float4*>(wr + k0 + k));
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float4 xv = *reinterpret_cast<const float4*>(&xs[j][k]);
