@@ -127,7 +127,17 @@ typedef struct scf_tc_conv_desc {
   void* out_hl; long long out_hl_plane; int out_hl_stride, out_hl_coff; /* optional split-bf16 output */
   const float* aux0; int aux0_stride; const float* aux1; int aux1_stride;  /* EPI_ACT: aux0 = optional residual added before act */
   void* out2_hl; long long out2_hl_plane; int out2_hl_stride;           /* GRU_ZR: r*h as split-bf16 */
+  /* --- optional extensions (zero = off) --- */
+  const float* pre; int pre_stride;   /* GRU epilogues: fp32 NHWC map added to the accumulator before the gate non-linearity
+                                       * (the loop-invariant context contribution of the GRU convolutions, computed once) */
+  int stride_x, stride_y;             /* per-axis strides overriding `stride` when non-zero (1 or 2 each) */
+  float* stats;                       /* EPI_ACT: per (pixel tile, epilogue warp) partial sums of the fp32 output,
+                                       * [m_tiles][4][2][cout] floats (sum, then sum of squares), for InstanceNorm; needs
+                                       * one sample per 128-pixel tile and cout % 32 == 0 */
 } scf_tc_conv_desc;
+/* number of 128-pixel tiles scf_conv2d_tc uses for this geometry (size of the `stats` buffer = tiles*4*2*cout floats)
+ * and pixel tiles per sample (0 if a tile may span samples) */
+int scf_conv2d_tc_tiles(int B, int Hout, int Wout, int* tiles_per_sample);
 
 int scf_conv2d_tc(const scf_tc_conv_desc* d, void* stream);
 /* OIHW fp32 -> split-bf16 [2][kh*kw][cout_pad][cin_pad] (zero padded; caller memsets the buffer first).

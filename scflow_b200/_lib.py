@@ -51,6 +51,7 @@ class TcConvDesc(C.Structure):
         ('out_hl', c_void_p), ('out_hl_plane', C.c_longlong), ('out_hl_stride', C.c_int), ('out_hl_coff', C.c_int),
         ('aux0', c_void_p), ('aux0_stride', C.c_int), ('aux1', c_void_p), ('aux1_stride', C.c_int),
         ('out2_hl', c_void_p), ('out2_hl_plane', C.c_longlong), ('out2_hl_stride', C.c_int),
+        ('pre', c_void_p), ('pre_stride', C.c_int), ('stride_x', C.c_int), ('stride_y', C.c_int), ('stats', c_void_p),
     ]
 
 
@@ -123,6 +124,7 @@ _SIGNATURES = {
     'scf_pack_conv_weight': (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
     'scf_conv2d': (C.c_int, [C.POINTER(ConvDesc), c_void_p]),
     'scf_conv2d_tc': (C.c_int, [C.POINTER(TcConvDesc), c_void_p]),
+    'scf_conv2d_tc_tiles': (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     'scf_pack_conv_weight_tc': (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
     'scf_nchw_to_nhwc_split': (C.c_int, [c_void_p, c_void_p, C.c_longlong, C.c_int, C.c_int, c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_int, c_void_p]),

@@ -21,18 +21,21 @@ using namespace tc;
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 192;   // warp 0 TMA, warp 1 MMA + TMEM allocator, warps 2-5 epilogue
+// threads = 64 + 32*EW: warp 0 TMA, warp 1 MMA + TMEM allocator, EW (4 or 8) epilogue warps
 constexpr int TC_STAGE_ROW = 80;  // epilogue staging: 32 rows x 64 B per warp, rows padded to 80 B (conflict-free 16 B accesses)
-constexpr int TC_HEADER = 1024 + 4 * 32 * TC_STAGE_ROW + 2048;   // barriers + staging + 2 bias buffers (multiple of 1024)
+__host__ __device__ constexpr int tc_header(int ew) { return 1024 + ew * 32 * TC_STAGE_ROW + 2048; }   // barriers + staging + 2 bias buffers (multiple of 1024)
 constexpr uint32_t TC_A_PLANE = TC_BM * TC_BK * 2;   // 16 KB
 constexpr int TC_MAX_STAGES = 4;
 
 struct TcParams {
   int nseg, seg_chunks[3], seg_wcoff[3];
+  int seg_last_ks[3];            // 16-channel k-steps of a segment's last (possibly ragged) 64-channel chunk: 1..4
   int B, H, W, kh, kw, ph, pw;   // H, W: OUTPUT spatial size
-  int stride;                    // 1 or 2 (input is sampled at stride*out + tap - pad)
+  int sx, sy;                    // 1 or 2 per axis (input is sampled at stride*out + tap - pad)
   int TW, TH, TB, tiles_x, tiles_y;   // tile = TW x TH pixels x TB samples = 128 rows
   int m_tiles, num_tiles;        // pixel tiles, pixel tiles x N tiles (tile t: n = t / m_tiles, m = t % m_tiles)
+  int cluster;                   // CTAs per cluster (1, 2 or 4): consecutive pixel tiles of one N tile share each weight tile,
+                                 // every CTA fetching BN/cluster rows of it and multicasting them to its peers
   int BN, cout, num_taps, w_batched, stages;
   int acc_cols, tmem_cols;       // TMEM columns of one accumulator buffer / allocated (two buffers)
   long long* dbg_times;          // optional [grid][8] globaltimer stamps of each CTA's first tile (tools/trace_conv_tc.py)
@@ -47,6 +50,8 @@ struct TcParams {
   __nv_bfloat16* out_hl; long long out_hl_plane; int out_hl_stride, out_hl_coff;
   const float* aux0; int aux0_stride; const float* aux1; int aux1_stride;
   __nv_bfloat16* out2_hl; long long out2_hl_plane; int out2_hl_stride;
+  const float* pre; int pre_stride;   // GRU epilogues: fp32 map added before the gate non-linearity
+  float* stats;                       // EPI_ACT: [m_tiles][4 warps][2][cout] partial sums / sums of squares of the output
 };
 
 // ---- compact epilogue helpers (the whole epilogue loop body must stay well inside the instruction cache: a first
@@ -70,11 +75,12 @@ __device__ __forceinline__ void load16(const float* src, float* d) {     // src 
   }
 }
 
-// ---- coalescing through shared memory.  In the accumulator layout a thread owns one pixel row, so direct 16 B stores
+// ---- coalescing through shared memory.  In the accumulator layout a thread owns one pixel row, so direct 16 B accesses
 // of a warp touch 32 different cache lines (measured: the epilogue of a 128x256 tile took 5.6 us, LSU-bound).  These
 // helpers move a [32 rows x 64 B] block between the warp's registers and global memory with 4 lanes per row, i.e.
-// 8 fully used 64 B row segments per instruction.  `mypix` = global pixel index of this thread's row, or -1.
-__device__ __forceinline__ void stage_store64(uint32_t sbuf, int lane, char* gbase, long long row_bytes, long long mypix,
+// 8 fully used 64 B row segments per instruction.  rp[it] = global pixel index of row it*8 + (lane>>2) of this warp's
+// 32 rows, or -1 (row outside the image).
+__device__ __forceinline__ void stage_store64(uint32_t sbuf, int lane, char* gbase, long long row_bytes, const int (&rp)[4],
                                               const uint4 (&d)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -87,22 +93,49 @@ __device__ __forceinline__ void stage_store64(uint32_t sbuf, int lane, char* gba
     uint4 v;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "r"(sbuf + r * TC_STAGE_ROW + seg * 16) : "memory");
-    const long long pr = __shfl_sync(0xffffffffu, mypix, r);
-    if (pr >= 0) *reinterpret_cast<uint4*>(gbase + pr * row_bytes + seg * 16) = v;
+    if (rp[it] >= 0) *reinterpret_cast<uint4*>(gbase + rp[it] * row_bytes + seg * 16) = v;
   }
   __syncwarp();
 }
-__device__ __forceinline__ void stage_load64(uint32_t sbuf, int lane, const char* gbase, long long row_bytes, long long mypix,
-                                             float (&out)[16]) {
+// Same for an fp32 block, additionally accumulating per-column sums and sums of squares of the valid rows:
+// after the call lane l holds (in s, q) the partial sums of columns (l&3)*4..+3 over rows (l>>2) + 8*it.
+__device__ __forceinline__ void stage_store64_stats(uint32_t sbuf, int lane, char* gbase, long long row_bytes, const int (&rp)[4],
+                                                    const uint4 (&d)[4], float (&s)[4], float (&q)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + lane * TC_STAGE_ROW + i * 16), "r"(d[i].x), "r"(d[i].y),
+                 "r"(d[i].z), "r"(d[i].w) : "memory");
+  __syncwarp();
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int r = it * 8 + (lane >> 2), seg = lane & 3;
-    const long long pr = __shfl_sync(0xffffffffu, mypix, r);
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (pr >= 0) v = __ldg(reinterpret_cast<const uint4*>(gbase + pr * row_bytes + seg * 16));
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + r * TC_STAGE_ROW + seg * 16), "r"(v.x), "r"(v.y), "r"(v.z),
-                 "r"(v.w) : "memory");
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(sbuf + r * TC_STAGE_ROW + seg * 16) : "memory");
+    if (rp[it] >= 0) {
+      *reinterpret_cast<uint4*>(gbase + rp[it] * row_bytes + seg * 16) = v;
+      const float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y), f2 = __uint_as_float(v.z), f3 = __uint_as_float(v.w);
+      s[0] += f0; s[1] += f1; s[2] += f2; s[3] += f3;
+      q[0] = fmaf(f0, f0, q[0]); q[1] = fmaf(f1, f1, q[1]); q[2] = fmaf(f2, f2, q[2]); q[3] = fmaf(f3, f3, q[3]);
+    }
   }
+  __syncwarp();
+}
+// Loads are split in two so that a block can be in flight while the previous one is consumed (the epilogue warps have
+// nothing else to hide global-memory latency with): stage_issue64 starts the 4 coalesced 16 B loads of a
+// [32 rows x 64 B] fp32 block, stage_commit64 transposes them through shared memory into this thread's row.
+__device__ __forceinline__ void stage_issue64(const float* gbase, int row_floats, const int (&rp)[4], int lane, uint4 (&r)[4]) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    r[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (rp[it] >= 0) r[it] = __ldg(reinterpret_cast<const uint4*>(gbase + (long long)rp[it] * row_floats) + (lane & 3));
+  }
+}
+__device__ __forceinline__ void stage_commit64(uint32_t sbuf, int lane, const uint4 (&r)[4], float (&out)[16]) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + (it * 8 + (lane >> 2)) * TC_STAGE_ROW + (lane & 3) * 16),
+                 "r"(r[it].x), "r"(r[it].y), "r"(r[it].z), "r"(r[it].w) : "memory");
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -115,16 +148,16 @@ __device__ __forceinline__ void stage_load64(uint32_t sbuf, int lane, const char
   __syncwarp();
 }
 // 16 fp32 values of this thread's row -> one 64 B fp32 block
-__device__ __forceinline__ void stage_store_f32(uint32_t sbuf, int lane, float* gbase, int stride, long long mypix, const float* v) {
+__device__ __forceinline__ void stage_store_f32(uint32_t sbuf, int lane, float* gbase, int stride, const int (&rp)[4], const float* v) {
   uint4 d[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     d[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
-  stage_store64(sbuf, lane, reinterpret_cast<char*>(gbase), (long long)stride * 4, mypix, d);
+  stage_store64(sbuf, lane, reinterpret_cast<char*>(gbase), (long long)stride * 4, rp, d);
 }
 // 32 fp32 values of this thread's row -> split-bf16: one 64 B block in the hi plane, one in the lo plane
 __device__ __forceinline__ void stage_store_split32(uint32_t sbuf, int lane, __nv_bfloat16* gbase, long long plane, int stride,
-                                                    long long mypix, const float* v) {
+                                                    const int (&rp)[4], const float* v) {
   uint4 hi[4], lo[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -141,8 +174,8 @@ __device__ __forceinline__ void stage_store_split32(uint32_t sbuf, int lane, __n
     hi[i] = make_uint4(h[0], h[1], h[2], h[3]);
     lo[i] = make_uint4(l[0], l[1], l[2], l[3]);
   }
-  stage_store64(sbuf, lane, reinterpret_cast<char*>(gbase), (long long)stride * 2, mypix, hi);
-  stage_store64(sbuf, lane, reinterpret_cast<char*>(gbase + plane), (long long)stride * 2, mypix, lo);
+  stage_store64(sbuf, lane, reinterpret_cast<char*>(gbase), (long long)stride * 2, rp, hi);
+  stage_store64(sbuf, lane, reinterpret_cast<char*>(gbase + plane), (long long)stride * 2, rp, lo);
 }
 
 __device__ __forceinline__ void store_f32x16(float* dst, const float* v, int nvalid) {
@@ -183,23 +216,24 @@ __device__ __forceinline__ void store_split16(__nv_bfloat16* hi_dst, long long p
   }
 }
 
-template <int EPI, int ACT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int EPI, int ACT, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024 B alignment
-  // header: [0,256) barriers + TMEM pointer | [1024, 11264) epilogue staging | [11264, 13312) two bias buffers ; then the
-  // operand ring: `stages` x {A hi, A lo, W hi, W lo}
+  // header: [0,256) barriers + TMEM pointer | [1024, ..) epilogue staging, 2560 B per epilogue warp | two 1 KB bias buffers ;
+  // then the operand ring: `stages` x {A hi, A lo, W hi, W lo}
   const uint32_t bar_full = smem_base, bar_empty = smem_base + 64, bar_tfull = smem_base + 128, bar_tempty = smem_base + 144,
                  tmem_slot = smem_base + 192;
   const uint32_t stage0 = smem_base + 1024;
-  const uint32_t bias0 = smem_base + 1024 + 4 * 32 * TC_STAGE_ROW;
-  const uint32_t tiles0 = smem_base + TC_HEADER;
+  const uint32_t bias0 = smem_base + 1024 + EW * 32 * TC_STAGE_ROW;
+  const uint32_t tiles0 = smem_base + tc_header(EW);
   const uint32_t b_plane = (uint32_t)p.BN * 128u;
   const uint32_t stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  griddep_launch_dependents();   // the next kernel's prologue may overlap this grid's tail (it waits before touching memory)
   auto stamp = [&](int slot) {
     if (p.dbg_times) {
       long long t;
@@ -210,8 +244,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (threadIdx.x == 0) stamp(0);
 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int chunks_per_tap = p.seg_chunks[0] + p.seg_chunks[1] + p.seg_chunks[2];
-  const int num_chunks = p.num_taps * chunks_per_tap;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0);
@@ -220,21 +252,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     prefetch_tmap(&tmW);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, (uint32_t)p.cluster);   // every CTA of the cluster releases the stage (peers write into it)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);     // MMA issuer -> epilogue: accumulator a complete
-      mbar_init(bar_tempty + 8 * a, 4);    // 4 epilogue warps -> MMA issuer: accumulator a drained
+      mbar_init(bar_tempty + 8 * a, EW);   // epilogue warps -> MMA issuer: accumulator a drained
     }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
-  __syncthreads();
+  if (p.cluster > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers must exist before any multicast reaches them
   tc_fence_after();
+  const int crank = p.cluster > 1 ? (int)cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
+  // tile walk: cluster c takes tile groups c, c + #clusters, ...; group g = tiles g*cluster .. +cluster-1 (same N tile)
+  const int tile0 = (int)(blockIdx.x / p.cluster) * p.cluster + crank, tile_step = (int)gridDim.x;
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (threadIdx.x == 0) stamp(1);
+  griddep_wait();                // everything above overlapped the previous kernel; its results are visible from here on
 
   // Persistent CTA: tiles blockIdx.x, +gridDim.x, ...  The three roles walk the same tile sequence; the operand ring and
   // the two TMEM accumulators run on, so tile i+1's loads and MMAs overlap tile i's epilogue.
@@ -243,14 +280,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // ================= TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const int w_rows = p.BN / p.cluster;
+      for (int t = tile0; t < p.num_tiles; t += tile_step) {
         const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
         const int b = (mt / tiles_per_img) * p.TB, tr = mt % tiles_per_img;
         const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
         const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * p.BN;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
-          const int cx = x0 * p.stride + kx - p.pw, cy = y0 * p.stride + ky - p.ph;
+          const int cx = x0 * p.sx + kx - p.pw, cy = y0 * p.sy + ky - p.ph;
           for (int s = 0; s < p.nseg; ++s) {
             const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
             for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
@@ -259,7 +297,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               mbar_arrive_expect_tx(full, stage_bytes);
               const uint32_t a_dst = tiles0 + stage * stage_bytes;
               tma_load_5d(a_dst, tm, full, cc * TC_BK, cx, cy, b, 0);
-              tma_load_4d(a_dst + 2 * TC_A_PLANE, &tmW, full, p.seg_wcoff[s] + cc * TC_BK, n0, p.w_batched ? b : tap, 0);
+              const uint32_t w_dst = a_dst + 2 * TC_A_PLANE;
+              const int wk = p.seg_wcoff[s] + cc * TC_BK, wt = p.w_batched ? b : tap;
+              if (p.cluster == 1) {
+                tma_load_4d(w_dst, &tmW, full, wk, n0, wt, 0);
+                tma_load_4d(w_dst + b_plane, &tmW, full, wk, n0, wt, 1);
+              } else {       // this CTA's share of both weight planes, delivered to every CTA of the cluster
+                const uint32_t off = (uint32_t)(crank * w_rows) * 128u;
+                tma_load_4d_mc(w_dst + off, &tmW, full, wk, n0 + crank * w_rows, wt, 0, cmask);
+                tma_load_4d_mc(w_dst + b_plane + off, &tmW, full, wk, n0 + crank * w_rows, wt, 1, cmask);
+              }
               if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
           }
@@ -273,45 +320,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      for (int t = tile0; t < p.num_tiles; t += tile_step, ++it) {
         const int acc = it & 1;
         mbar_wait(bar_tempty + 8 * acc, (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue of tile it-2 has drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
-        for (int c = 0; c < num_chunks; ++c) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          if (it == 0 && c == 0) stamp(2);
-          const uint32_t a_addr = tiles0 + stage * stage_bytes;
-          const uint64_t a_hi = make_smem_desc_sw128(a_addr, 1024), a_lo = make_smem_desc_sw128(a_addr + TC_A_PLANE, 1024);
-          const uint64_t b_hi = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE, 1024);
-          const uint64_t b_lo = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + b_plane, 1024);
-          if (p.stackn) {
+        int c = 0;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          for (int sg = 0; sg < p.nseg; ++sg) {
+            for (int cc = 0; cc < p.seg_chunks[sg]; ++cc, ++c) {
+              const int ks = (cc == p.seg_chunks[sg] - 1) ? p.seg_last_ks[sg] : TC_BK / 16;   // skip all-zero k-steps of a ragged chunk
+              mbar_wait(bar_full + 8 * stage, phase);
+              tc_fence_after();
+              if (it == 0 && c == 0) stamp(2);
+              const uint32_t a_addr = tiles0 + stage * stage_bytes;
+              const uint64_t a_hi = make_smem_desc_sw128(a_addr, 1024), a_lo = make_smem_desc_sw128(a_addr + TC_A_PLANE, 1024);
+              const uint64_t b_hi = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE, 1024);
+              const uint64_t b_lo = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + b_plane, 1024);
+              if (p.stackn) {
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              const uint64_t ko = (uint64_t)(k * 32 >> 4);     // 16 bf16 = 32 B along the swizzled 128 B row
-              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc2, (c > 0 || k > 0) ? 1u : 0u);   // N = 2*BN: [W_hi;W_lo]
-              umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
-            }
-          } else {
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                  if (k < ks) {
+                    const uint64_t ko = (uint64_t)(k * 32 >> 4);     // 16 bf16 = 32 B along the swizzled 128 B row
+                    umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc2, (c > 0 || k > 0) ? 1u : 0u);   // N = 2*BN: [W_hi;W_lo]
+                    umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
+                  }
+                }
+              } else {
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              const uint64_t ko = (uint64_t)(k * 32 >> 4);
-              umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, (c > 0 || k > 0) ? 1u : 0u);
-              umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-              umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                  if (k < ks) {
+                    const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                    umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                    umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
+                  }
+                }
+              }
+              if (p.cluster == 1) umma_commit(bar_empty + 8 * stage);     // frees the smem slot once these MMAs have read it
+              else umma_commit_mc(bar_empty + 8 * stage, cmask);          // ... in every CTA of the cluster
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
           }
-          umma_commit(bar_empty + 8 * stage);     // frees the smem slot once these MMAs have read it
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(bar_tfull + 8 * acc);         // accumulator complete
         if (it == 0) stamp(3);
       }
     }
   } else {
-    // ================= epilogue: warp w owns TMEM lanes 32*(w%4)..+31 ; lane = pixel row of the tile
-    const int q = warp & 3;
+    // ================= epilogue: warp w may touch TMEM lanes 32*(w%4)..+31 ; lane = pixel row of the tile.  With EW = 8 two
+    // warps share a lane quarter and take alternate 32-column slabs.
+    constexpr int NPAR = EW / 4;
+    const int q = warp & 3, par = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int bb = row / (p.TW * p.TH), rr = row - bb * (p.TW * p.TH);
     const int h = rr / p.TW, w = rr - h * p.TW;
@@ -319,7 +379,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int ngroups = p.BN / 16;
     const uint32_t sbuf = stage0 + (uint32_t)(warp - 2) * 32 * TC_STAGE_ROW;
     int it = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+    for (int t = tile0; t < p.num_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
       const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
       const int b = (mt / tiles_per_img) * p.TB, tr = mt % tiles_per_img;
@@ -327,25 +387,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int y = ty * p.TH + h, x = tx * p.TW + w, n0 = nt * p.BN;
       const bool valid = y < p.H && x < p.W && b + bb < p.B;
       const long long pix = ((long long)(b + bb) * p.H + y) * p.W + x;
+      int rp[4];                         // pixel index of staging row it*8 + (lane>>2), or -1
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rp[i] = __shfl_sync(0xffffffffu, valid ? (int)pix : -1, i * 8 + (lane >> 2));
       const uint32_t bias_s = bias0 + (uint32_t)acc * 1024u;
       // stage this tile's bias slice (global-load latency would otherwise sit inside every column slab); the named barrier
       // also orders it against the slowest warp still reading the buffer two tiles ago
-      for (int i = threadIdx.x - 64; i < p.BN; i += 128) {
+      for (int i = threadIdx.x - 64; i < p.BN; i += 32 * EW) {
         const float bvl = (p.bias && n0 + i < p.cout) ? __ldg(p.bias + n0 + i) : 0.f;
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4 * i), "f"(bvl) : "memory");
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(bar_tfull + 8 * acc, ((uint32_t)it >> 1) & 1u);
-      tc_fence_after();
-      if (it == 0 && threadIdx.x == 64) stamp(4);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_cols);
       int g_begin = 0;
       if (p.fast_epi) {
-        // ---- coalesced path: 32-column slabs, every global access staged through shared memory
-        const long long mypix = valid ? pix : -1;
+        // ---- coalesced path: 32-column slabs, every global access staged through shared memory.  The epilogue's inputs
+        // (GRU: context term, h, z; ACT: residual) are prefetched one 16-column block ahead into registers (XA..YC).
         const int nslab = (p.cout - n0 < p.BN ? p.cout - n0 : p.BN) / 32;    // full slabs only; the tail uses the plain path
+        uint4 XA[4], XB[4], XC[4], YA[4], YB[4], YC[4];
+        auto issue = [&](int nb16, uint4 (&A)[4], uint4 (&B)[4], uint4 (&C)[4]) {
+          if (EPI == SCF_EPI_ACT) {
+            if (p.aux0) stage_issue64(p.aux0 + nb16, p.aux0_stride, rp, lane, B);
+          } else {
+            if (p.pre) stage_issue64(p.pre + nb16, p.pre_stride, rp, lane, A);
+            if (EPI == SCF_EPI_GRU_ZR) {
+              if (nb16 >= half) stage_issue64(p.aux0 + (nb16 - half), p.aux0_stride, rp, lane, B);
+            } else {
+              stage_issue64(p.aux0 + nb16, p.aux0_stride, rp, lane, B);
+              stage_issue64(p.aux1 + nb16, p.aux1_stride, rp, lane, C);
+            }
+          }
+        };
+        // applies the epilogue math to 16 accumulator columns (bias already added) using a prefetched block
+        auto consume = [&](int nb16, float* v16, const uint4 (&A)[4], const uint4 (&B)[4], const uint4 (&C)[4]) {
+          float t0[16];
+          if (EPI == SCF_EPI_ACT) {
+            if (p.aux0) {                      // residual connection (encoder BasicBlock): added before the activation
+              stage_commit64(sbuf, lane, B, t0);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v16[i] += t0[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v16[i] = act_ct<ACT>(v16[i]);
+          } else {
+            if (p.pre) {                       // loop-invariant context contribution (bias folded in), computed once per forward
+              stage_commit64(sbuf, lane, A, t0);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v16[i] += t0[i];
+            }
+            if (EPI == SCF_EPI_GRU_ZR) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v16[i] = sigmoid_fast(v16[i]);
+              if (nb16 >= half) {              // r gate: r * h feeds the q convolution
+                stage_commit64(sbuf, lane, B, t0);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v16[i] *= t0[i];
+              }
+            } else {                           // h' = (1 - z) h + z tanh(.)
+              float t1[16];
+              stage_commit64(sbuf, lane, B, t0);
+              stage_commit64(sbuf, lane, C, t1);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v16[i] = (1.f - t1[i]) * t0[i] + t1[i] * tanh_fast(v16[i]);
+            }
+          }
+        };
+        if (par < nslab) issue(n0 + par * 32, XA, XB, XC);       // overlaps the wait for the accumulator
+        mbar_wait(bar_tfull + 8 * acc, ((uint32_t)it >> 1) & 1u);
+        tc_fence_after();
+        if (it == 0 && threadIdx.x == 64) stamp(4);
 #pragma unroll 1
-        for (int sl = 0; sl < nslab; ++sl) {
+        for (int sl = par; sl < nslab; sl += NPAR) {
           float v[32];
           __syncwarp();
           tmem_ld32(t_addr + (uint32_t)(sl * 32), v);
@@ -364,60 +476,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             v[4 * i4] = fmaf(v[4 * i4], p.scale, bq.x); v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], p.scale, bq.y);
             v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], p.scale, bq.z); v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], p.scale, bq.w);
           }
-          if (EPI == SCF_EPI_ACT) {
-            if (p.aux0) {
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                float rv[16];
-                stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux0 + nb + hh * 16), (long long)p.aux0_stride * 4, mypix, rv);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[hh * 16 + i] += rv[i];
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = act_ct<ACT>(v[i]);
-            if (p.out_f32) {
-              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, mypix, v);
-              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, mypix, v + 16);
-            }
-            if (p.out_hl) stage_store_split32(sbuf, lane, p.out_hl + p.out_hl_coff + nb, p.out_hl_plane, p.out_hl_stride, mypix, v);
-          } else if (EPI == SCF_EPI_GRU_ZR) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = sigmoid_fast(v[i]);
-            if (nb < half) {
-              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, mypix, v);
-              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, mypix, v + 16);
+          issue(nb + 16, YA, YB, YC);
+          consume(nb, v, XA, XB, XC);
+          if (sl + NPAR < nslab) issue(nb + NPAR * 32, XA, XB, XC);
+          consume(nb + 16, v + 16, YA, YB, YC);
+          // ---- stores of the finished 32-column slab
+          if (EPI == SCF_EPI_GRU_ZR) {
+            if (nb < half) {                   // z gate -> fp32 (read back by the q convolution's epilogue)
+              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, rp, v);
+              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, rp, v + 16);
             } else {
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                float hv[16];
-                stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux0 + (nb - half) + hh * 16), (long long)p.aux0_stride * 4, mypix, hv);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[hh * 16 + i] *= hv[i];
-              }
-              stage_store_split32(sbuf, lane, p.out2_hl + (nb - half), p.out2_hl_plane, p.out2_hl_stride, mypix, v);
+              stage_store_split32(sbuf, lane, p.out2_hl + (nb - half), p.out2_hl_plane, p.out2_hl_stride, rp, v);
             }
           } else {
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              float hv[16], zv[16];
-              stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux0 + nb + hh * 16), (long long)p.aux0_stride * 4, mypix, hv);
-              stage_load64(sbuf, lane, reinterpret_cast<const char*>(p.aux1 + nb + hh * 16), (long long)p.aux1_stride * 4, mypix, zv);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[hh * 16 + i] = (1.f - zv[i]) * hv[i] + zv[i] * tanh_fast(v[hh * 16 + i]);
-            }
             if (p.out_f32) {
-              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, mypix, v);
-              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, mypix, v + 16);
+              if (EPI == SCF_EPI_ACT && p.stats) {
+                // InstanceNorm statistics of the map being written: per-column partial sums over this warp's 32 rows
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  uint4 d[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    d[i] = make_uint4(__float_as_uint(v[hh * 16 + 4 * i]), __float_as_uint(v[hh * 16 + 4 * i + 1]),
+                                      __float_as_uint(v[hh * 16 + 4 * i + 2]), __float_as_uint(v[hh * 16 + 4 * i + 3]));
+                  float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+                  stage_store64_stats(sbuf, lane, reinterpret_cast<char*>(p.out_f32 + p.out_f32_coff + nb + hh * 16),
+                                      (long long)p.out_f32_stride * 4, rp, d, s4, q4);
+#pragma unroll
+                  for (int off = 4; off < 32; off <<= 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      s4[j] += __shfl_xor_sync(0xffffffffu, s4[j], off);
+                      q4[j] += __shfl_xor_sync(0xffffffffu, q4[j], off);
+                    }
+                  }
+                  if (lane < 4) {
+                    float* o = p.stats + ((long long)(mt * 4 + q) * 2) * p.cout + nb + hh * 16 + lane * 4;
+                    *reinterpret_cast<float4*>(o) = make_float4(s4[0], s4[1], s4[2], s4[3]);
+                    *reinterpret_cast<float4*>(o + p.cout) = make_float4(q4[0], q4[1], q4[2], q4[3]);
+                  }
+                }
+              } else {
+                stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, rp, v);
+                stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, rp, v + 16);
+              }
             }
-            if (p.out_hl) stage_store_split32(sbuf, lane, p.out_hl + p.out_hl_coff + nb, p.out_hl_plane, p.out_hl_stride, mypix, v);
+            if (p.out_hl) stage_store_split32(sbuf, lane, p.out_hl + p.out_hl_coff + nb, p.out_hl_plane, p.out_hl_stride, rp, v);
           }
         }
         g_begin = nslab * 2;
+      } else {
+        mbar_wait(bar_tfull + 8 * acc, ((uint32_t)it >> 1) & 1u);
+        tc_fence_after();
+        if (it == 0 && threadIdx.x == 64) stamp(4);
       }
       // ---- plain path (ragged channel tails, unaligned outputs): 16-column groups, direct per-thread stores
 #pragma unroll 1
-      for (int g = g_begin; g < ngroups; ++g) {
+      for (int g = g_begin + par; g < ngroups; g += NPAR) {
         float v[16];
         __syncwarp();
         tmem_ld16(t_addr + (uint32_t)(g * 16), v);
@@ -448,6 +563,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (p.out_f32) store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, nvalid);
           if (p.out_hl) store_split16(p.out_hl + pix * p.out_hl_stride + p.out_hl_coff + nb, p.out_hl_plane, v, nvalid);
         } else if (EPI == SCF_EPI_GRU_ZR) {    // cout = 2*Ch, Ch % 16 == 0: a group is entirely z or entirely r
+          if (p.pre) {
+            float pv[16];
+            load16(p.pre + pix * p.pre_stride + nb, pv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += pv[i];
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = sigmoid_fast(v[i]);
           if (nb < half) {                     // z gate -> fp32 (read back by the q convolution's epilogue)
@@ -461,6 +582,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         } else {                               // SCF_EPI_GRU_Q: h' = (1-z) h + z tanh(.)   (cout % 16 == 0)
           float hv[16], zv[16];
+          if (p.pre) {
+            load16(p.pre + pix * p.pre_stride + nb, hv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += hv[i];
+          }
           load16(p.aux0 + pix * p.aux0_stride + nb, hv);
           load16(p.aux1 + pix * p.aux1_stride + nb, zv);
 #pragma unroll
@@ -477,14 +603,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (p.cluster > 1) cluster_sync_all(); else __syncthreads();   // no CTA may exit while peers can still signal or write into it
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   if (threadIdx.x == 32) stamp(6);
 }
 
 // ------------------------------------------------------------------ prep kernels
+// input channels [i_begin, i_begin + I) of a weight with I_total input channels land at packed channels i_dst ..
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, int O, int I, int taps,
-                                      int cin_pad, int cout_pad, int o_off) {
+                                      int cin_pad, int cout_pad, int o_off, int I_total, int i_begin, int i_dst) {
   const long long total = (long long)O * I * taps;
   const long long plane = (long long)taps * cout_pad * cin_pad;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -494,8 +621,8 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16
     const int o = (int)(r % O);
     const int tap = (int)(r / O);
     __nv_bfloat16 hi, lo;
-    split_bf16(w[((long long)o * I + i) * taps + tap], hi, lo);
-    const long long dst = ((long long)tap * cout_pad + o_off + o) * cin_pad + i;
+    split_bf16(w[((long long)o * I_total + i_begin + i) * taps + tap], hi, lo);
+    const long long dst = ((long long)tap * cout_pad + o_off + o) * cin_pad + i_dst + i;
     packed[dst] = hi;
     packed[plane + dst] = lo;
   }
@@ -615,9 +742,12 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.nseg = d.nseg;
   const int stride = d.stride == 2 ? 2 : 1;
   SCF_REQUIRE(d.stride == 0 || d.stride == 1 || d.stride == 2, SCF_ERR_ARG, "scf_conv2d_tc: stride must be 1 or 2");
-  p.stride = stride;
+  SCF_REQUIRE(d.stride_x >= 0 && d.stride_x <= 2 && d.stride_y >= 0 && d.stride_y <= 2, SCF_ERR_ARG,
+              "scf_conv2d_tc: stride_x / stride_y must be 0 (= stride), 1 or 2");
+  p.sx = d.stride_x ? d.stride_x : stride;
+  p.sy = d.stride_y ? d.stride_y : stride;
   p.kh = d.kh; p.kw = d.kw; p.ph = d.kh / 2; p.pw = d.kw / 2;
-  p.B = d.B; p.H = (d.H + 2 * p.ph - d.kh) / stride + 1; p.W = (d.W + 2 * p.pw - d.kw) / stride + 1;
+  p.B = d.B; p.H = (d.H + 2 * p.ph - d.kh) / p.sy + 1; p.W = (d.W + 2 * p.pw - d.kw) / p.sx + 1;
   pick_tile(d.B, p.H, p.W, d.w_batched != 0, p.TW, p.TH, p.TB);
   p.tiles_x = cdiv(p.W, p.TW); p.tiles_y = cdiv(p.H, p.TH);
   p.BN = d.cout_pad <= 256 ? d.cout_pad : 256;
@@ -633,7 +763,14 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     SCF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int stage_bytes = 2 * (int)TC_A_PLANE + 2 * p.BN * 128;
-  p.stages = (232448 - 1024 - TC_HEADER) / stage_bytes;
+  // epilogue warps: 8 (two per TMEM lane quarter) for the one-CTA-per-SM configuration - the epilogue's global loads
+  // (GRU gates, residuals) need the extra memory-level parallelism - and 4 for the small-tile two-CTAs-per-SM mode
+  int ew = 8;
+  {
+    const char* ev = getenv("SCFLOW_TC_EW");
+    if (ev && atoi(ev) == 4) ew = 4;
+  }
+  p.stages = (232448 - 1024 - tc_header(ew)) / stage_bytes;
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
   SCF_REQUIRE(p.stages >= 2, SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: tile does not fit in shared memory");
   {
@@ -643,24 +780,83 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.acc_cols = p.stackn ? 2 * p.BN : p.BN;
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.acc_cols) p.tmem_cols <<= 1;
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
+  static const KernelFn table[2][6] = {
+      {conv_tc_kernel<SCF_EPI_GRU_ZR, SCF_ACT_SIGMOID, 4>, conv_tc_kernel<SCF_EPI_GRU_Q, SCF_ACT_TANH, 4>,
+       conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_NONE, 4>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_RELU, 4>,
+       conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_SIGMOID, 4>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_TANH, 4>},
+      {conv_tc_kernel<SCF_EPI_GRU_ZR, SCF_ACT_SIGMOID, 8>, conv_tc_kernel<SCF_EPI_GRU_Q, SCF_ACT_TANH, 8>,
+       conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_NONE, 8>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_RELU, 8>,
+       conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_SIGMOID, 8>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_TANH, 8>}};
+  int ki = -1;
+  if (d.epi == SCF_EPI_GRU_ZR) ki = 0;
+  else if (d.epi == SCF_EPI_GRU_Q) ki = 1;
+  else if (d.epi == SCF_EPI_ACT && d.act >= SCF_ACT_NONE && d.act <= SCF_ACT_TANH) ki = 2 + d.act;
+  SCF_REQUIRE(ki >= 0, SCF_ERR_ARG, "scf_conv2d_tc: bad epilogue / activation");
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    for (int a = 0; a < 2; ++a)
+      for (int i = 0; i < 6; ++i) {
+        cudaError_t e = cudaFuncSetAttribute(table[a][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) attr_err = e;
+      }
+  });
+  SCF_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(attr_err));
   int ctas_per_sm = 1;
   {
     // Small tiles: keep two CTAs resident per SM (<= 113 KB of shared memory and <= 256 TMEM columns each) so that the two
     // CTAs' main loops interleave; larger tiles run one persistent CTA per SM with double-buffered accumulators.
     const char* ov = getenv("SCFLOW_TC_OCC2");
     const bool occ2 = ov ? atoi(ov) != 0 : true;
-    if (occ2 && 2 * stage_bytes + 1024 + TC_HEADER <= 115712 && p.tmem_cols <= 256 && p.num_tiles >= 4 * num_sms) {
-      p.stages = (115712 - 1024 - TC_HEADER) / stage_bytes;
+    if (occ2 && 2 * stage_bytes + 1024 + tc_header(4) <= 115712 && p.tmem_cols <= 256 && p.num_tiles >= 4 * num_sms) {
+      ew = 4;
+      p.stages = (115712 - 1024 - tc_header(4)) / stage_bytes;
       ctas_per_sm = 2;
     }
   }
-  const int smem = 1024 + TC_HEADER + p.stages * stage_bytes;
+  const int smem = 1024 + tc_header(ew) + p.stages * stage_bytes;
+  KernelFn kernel = table[ew == 8 ? 1 : 0][ki];
+  // ---- cluster size: CTAs of consecutive pixel tiles (same N tile, same sample when the weights are batched) share each
+  // weight tile through TMA multicast, which divides the weight share of the L2 -> shared-memory operand traffic - the
+  // resource this kernel saturates first (ncu: 8-9 TB/s) - by the cluster size
+  p.cluster = 1;
+  int max_clusters = 0;
+  if (ctas_per_sm == 1) {
+    const char* ce = getenv("SCFLOW_TC_CLUSTER");
+    const int want = ce ? atoi(ce) : 1;   // measured on B200 (tools/trace_gru.py, bench_conv_tc.py): no gain from 2 or 4 - the main
+                                          // loop is MMA-bound at the power-capped clock, not operand-delivery-bound - so off by default
+    for (int cs = want >= 4 ? 4 : (want >= 2 ? 2 : 1); cs > 1; cs >>= 1) {
+      if (p.m_tiles % cs != 0 || (p.BN / cs) % 8 != 0 || p.num_tiles < 2 * cs) continue;
+      if (d.w_batched && (p.tiles_x * p.tiles_y) % cs != 0) continue;
+      static std::mutex mu;
+      static int cache[2][6][5][8];      // [ew][kernel][cluster][stages] -> max co-resident clusters (+1; 0 = not queried)
+      std::lock_guard<std::mutex> lock(mu);
+      int& slot = cache[ew == 8 ? 1 : 0][ki][cs][p.stages];
+      if (slot == 0) {
+        cudaLaunchConfig_t qc = {};
+        qc.gridDim = dim3(num_sms / cs * cs); qc.blockDim = dim3(64 + 32 * ew); qc.dynamicSmemBytes = smem;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = cs; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+        qc.attrs = qa; qc.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &qc) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        slot = n + 1;
+      }
+      if (slot - 1 >= 1) { p.cluster = cs; max_clusters = slot - 1; break; }
+    }
+  }
   p.bias = d.bias; p.scale = d.scale; p.epi = d.epi; p.act = d.act;
   p.out_f32 = d.out_f32; p.out_f32_stride = d.out_f32_stride; p.out_f32_coff = d.out_f32_coff;
   p.out_hl = reinterpret_cast<__nv_bfloat16*>(d.out_hl); p.out_hl_plane = d.out_hl_plane; p.out_hl_stride = d.out_hl_stride;
   p.out_hl_coff = d.out_hl_coff;
   p.aux0 = d.aux0; p.aux0_stride = d.aux0_stride; p.aux1 = d.aux1; p.aux1_stride = d.aux1_stride;
   p.out2_hl = reinterpret_cast<__nv_bfloat16*>(d.out2_hl); p.out2_hl_plane = d.out2_hl_plane; p.out2_hl_stride = d.out2_hl_stride;
+  p.pre = d.pre; p.pre_stride = d.pre_stride; p.stats = d.stats;
+  if (d.pre)
+    SCF_REQUIRE(d.epi != SCF_EPI_ACT && d.pre_stride % 4 == 0 && reinterpret_cast<uintptr_t>(d.pre) % 16 == 0, SCF_ERR_ALIGN,
+                "scf_conv2d_tc: pre needs a GRU epilogue, 16B alignment and stride %% 4 == 0");
   {
     const char* dt = getenv("SCFLOW_TC_DBG_TIMES");       // address of a device buffer, hex (timing experiments only)
     p.dbg_times = dt ? reinterpret_cast<long long*>(strtoull(dt, nullptr, 16)) : nullptr;
@@ -668,7 +864,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   CUtensorMap tmA[3], tmW;
   int wcoff = 0;
   for (int s = 0; s < 3; ++s) {
-    if (s >= d.nseg) { tmA[s] = tmA[0]; p.seg_chunks[s] = 0; p.seg_wcoff[s] = 0; continue; }
+    if (s >= d.nseg) { tmA[s] = tmA[0]; p.seg_chunks[s] = 0; p.seg_wcoff[s] = 0; p.seg_last_ks[s] = 0; continue; }
     const scf_tc_seg& sg = d.seg[s];
     SCF_REQUIRE(sg.ptr && sg.nch > 0 && sg.nch % 8 == 0 && sg.coff % 8 == 0 && sg.stride % 8 == 0, SCF_ERR_ALIGN,
                 "scf_conv2d_tc: segment %d channels/offset/stride must be multiples of 8", s);
@@ -679,10 +875,11 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     cuuint64_t str[4] = {(cuuint64_t)sg.stride * 2, (cuuint64_t)d.W * sg.stride * 2, (cuuint64_t)d.H * d.W * sg.stride * 2,
                          (cuuint64_t)sg.plane_stride * 2};
     // box = elements TRAVERSED per dimension; with element strides (1,s,s,1,1) it deposits TW x TH x TB pixels
-    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), (cuuint32_t)p.TB, 2};
-    cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.TW * p.sx), (cuuint32_t)(p.TH * p.sy), (cuuint32_t)p.TB, 2};
+    cuuint32_t estr[5] = {1, (cuuint32_t)p.sx, (cuuint32_t)p.sy, 1, 1};
     SCF_TRY(encode_map(&tmA[s], base, 5, dims, str, box, estr));
     p.seg_chunks[s] = cdiv(sg.nch, TC_BK);
+    p.seg_last_ks[s] = cdiv(sg.nch - (p.seg_chunks[s] - 1) * TC_BK, 16);
     p.seg_wcoff[s] = wcoff;
     wcoff += sg.nch;
   }
@@ -692,7 +889,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     cuuint64_t dims[4] = {(cuuint64_t)d.cin_pad, (cuuint64_t)d.cout_pad, (cuuint64_t)third, 2};
     cuuint64_t str[3] = {(cuuint64_t)d.cin_pad * 2, (cuuint64_t)d.cout_pad * d.cin_pad * 2,
                          (cuuint64_t)third * d.cout_pad * d.cin_pad * 2};
-    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)p.BN, 1, 2};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.BN / p.cluster), 1, 1};
     SCF_REQUIRE(reinterpret_cast<uintptr_t>(d.w) % 16 == 0, SCF_ERR_ALIGN, "scf_conv2d_tc: packed weight must be 16B aligned");
     SCF_TRY(encode_map(&tmW, d.w, 4, dims, str, box));
   }
@@ -708,30 +905,40 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     const char* fe = getenv("SCFLOW_TC_FASTEPI");
     p.fast_epi = (ok && (fe ? atoi(fe) != 0 : true)) ? 1 : 0;
   }
-  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
-  KernelFn kernel = nullptr;
-  if (d.epi == SCF_EPI_GRU_ZR) kernel = conv_tc_kernel<SCF_EPI_GRU_ZR, SCF_ACT_SIGMOID>;
-  else if (d.epi == SCF_EPI_GRU_Q) kernel = conv_tc_kernel<SCF_EPI_GRU_Q, SCF_ACT_TANH>;
-  else if (d.act == SCF_ACT_NONE) kernel = conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_NONE>;
-  else if (d.act == SCF_ACT_RELU) kernel = conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_RELU>;
-  else if (d.act == SCF_ACT_SIGMOID) kernel = conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_SIGMOID>;
-  else if (d.act == SCF_ACT_TANH) kernel = conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_TANH>;
-  SCF_REQUIRE(kernel != nullptr, SCF_ERR_ARG, "scf_conv2d_tc: bad epilogue / activation");
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    KernelFn all[6] = {conv_tc_kernel<SCF_EPI_GRU_ZR, SCF_ACT_SIGMOID>, conv_tc_kernel<SCF_EPI_GRU_Q, SCF_ACT_TANH>,
-                       conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_NONE>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_RELU>,
-                       conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_SIGMOID>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_TANH>};
-    for (KernelFn f : all) {
-      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-      if (e != cudaSuccess) attr_err = e;
+  if (d.stats)
+    SCF_REQUIRE(p.fast_epi && p.TB == 1 && d.cout % 32 == 0 && d.out_f32 && d.epi == SCF_EPI_ACT &&
+                    reinterpret_cast<uintptr_t>(d.stats) % 16 == 0,
+                SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: stats need an aligned fp32 output, cout %% 32 == 0 and one sample per tile");
+  int grid;
+  if (p.cluster > 1) {
+    const int groups = p.num_tiles / p.cluster;
+    grid = (groups < max_clusters ? groups : max_clusters) * p.cluster;
+  } else {
+    const int max_ctas = num_sms * ctas_per_sm;
+    grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
+  }
+  {
+    // programmatic dependent launch: this kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) may overlap
+    // the tail of the previous kernel on the stream; the kernel executes griddepcontrol.wait before it touches memory
+    static const bool pdl = [] { const char* e = getenv("SCFLOW_PDL"); return e ? atoi(e) != 0 : true; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * ew); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
     }
-  });
-  SCF_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(attr_err));
-  const int max_ctas = num_sms * ctas_per_sm;
-  const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
-  kernel<<<grid, TC_THREADS, smem, st>>>(tmA[0], tmA[1], tmA[2], tmW, p);
+    if (p.cluster > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = p.cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, tmA[0], tmA[1], tmA[2], tmW, p);
+    if (le != cudaSuccess) { cudaGetLastError(); set_error("conv_tc_kernel launch: %s", cudaGetErrorString(le)); g_launches++; return (int)le; }
+  }
   return check_launch("conv_tc_kernel");
 }
 
@@ -744,15 +951,39 @@ int scf_conv2d_tc(const scf_tc_conv_desc* d, void* stream) {
   return scf::conv2d_tc(*d, (cudaStream_t)stream);
 }
 
+}  // extern "C"
+
+namespace scf {
+// packs input channels [i_begin, i_begin + i_count) of an OIHW weight with I_total input channels at packed channels i_dst..
+int pack_conv_weight_tc_range(const float* w_oihw, void* packed, int O, int I_total, int i_begin, int i_count, int i_dst, int kh,
+                              int kw, int cin_pad, int cout_pad, int o_off, cudaStream_t st) {
+  SCF_REQUIRE(w_oihw && packed && O > 0 && i_count > 0 && kh > 0 && kw > 0, SCF_ERR_ARG, "pack_conv_weight_tc_range: bad args");
+  SCF_REQUIRE(i_begin >= 0 && i_begin + i_count <= I_total && cin_pad >= i_dst + i_count && cout_pad >= o_off + O, SCF_ERR_ARG,
+              "pack_conv_weight_tc_range: range outside the weight / padding");
+  const long long total = (long long)O * i_count * kh * kw;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  pack_weight_tc_kernel<<<blocks, 256, 0, st>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(packed), O, i_count, kh * kw, cin_pad,
+                                                cout_pad, o_off, I_total, i_begin, i_dst);
+  return check_launch("pack_weight_tc_kernel");
+}
+}  // namespace scf
+
+extern "C" {
+
+int scf_conv2d_tc_tiles(int B, int Hout, int Wout, int* tiles_per_sample) {
+  if (B <= 0 || Hout <= 0 || Wout <= 0) return 0;
+  int TW = 0, TH = 0, TB = 0;
+  scf::pick_tile(B, Hout, Wout, false, TW, TH, TB);
+  const int per = scf::cdiv(Wout, TW) * scf::cdiv(Hout, TH);
+  if (tiles_per_sample) *tiles_per_sample = TB == 1 ? per : 0;
+  return per * scf::cdiv(B, TB);
+}
+
 int scf_pack_conv_weight_tc(const float* w_oihw, void* packed, int O, int I, int kh, int kw, int cin_pad, int cout_pad,
                             int o_off, void* stream) {
   SCF_REQUIRE(w_oihw && packed && O > 0 && I > 0 && kh > 0 && kw > 0, SCF_ERR_ARG, "scf_pack_conv_weight_tc: bad args");
   SCF_REQUIRE(cin_pad >= I && cout_pad >= o_off + O, SCF_ERR_ARG, "scf_pack_conv_weight_tc: padding smaller than the weight");
-  const long long total = (long long)O * I * kh * kw;
-  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  scf::pack_weight_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(packed), O, I,
-                                                                      kh * kw, cin_pad, cout_pad, o_off);
-  return scf::check_launch("pack_weight_tc_kernel");
+  return scf::pack_conv_weight_tc_range(w_oihw, packed, O, I, 0, I, 0, kh, kw, cin_pad, cout_pad, o_off, (cudaStream_t)stream);
 }
 
 int scf_nchw_to_nhwc_split(const float* src, void* dst_hl, long long plane_stride, int dst_stride, int dst_coff,

@@ -10,6 +10,8 @@ namespace scf {
 int conv2d_f32(const scf_conv_desc& d, cudaStream_t st);
 int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st);
 int avgpool2(const float* in, float* out, long long nq, int hi, int wi, cudaStream_t st);
+int pack_conv_weight_tc_range(const float* w_oihw, void* packed, int O, int I_total, int i_begin, int i_count, int i_dst, int kh,
+                              int kw, int cin_pad, int cout_pad, int o_off, cudaStream_t st);
 int corr_build_dispatch(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
                         float* const* levels, void* scratch, int precision, cudaStream_t st);
 
@@ -24,7 +26,9 @@ void set_error(const char* fmt, ...) {
 
 // ------------------------------------------------------------------ packed convolution table
 enum PC {
-  PC_CORR0, PC_CORR1, PC_FLOW0, PC_FLOW1, PC_OUT0, PC_ZR0, PC_Q0, PC_ZR1, PC_Q1, PC_HEADS, PC_FHP, PC_MHP,
+  PC_CORR0, PC_CORR1, PC_FLOW0, PC_FLOW1, PC_OUT0, PC_ZR0, PC_Q0, PC_ZR1, PC_Q1,
+  PC_CZR0, PC_CQ0, PC_CZR1, PC_CQ1,   // tensor-core only: the context-feature columns of the GRU convolutions (loop invariant)
+  PC_HEADS, PC_FHP, PC_MHP,
   PC_DFE0, PC_DFE1, PC_ME0, PC_ME1, PC_PH0, PC_PH1, PC_PH2, PC_COUNT
 };
 struct PCInfo {
@@ -37,6 +41,8 @@ struct PCInfo {
   // tensor-core copy (precision 1): bf16 [2][taps][cout_pad][cin_pad] at byte offset tc_off (0 = layer stays on fp32 cores)
   int tc, cin_pad, cout_pad;
   size_t tc_off;
+  int tc_only;                // no fp32 copy (exists for the tensor-core path only)
+  int tc_nr, tc_src[2], tc_cnt[2];   // input-channel ranges of the source weight that the tensor-core copy holds, packed densely
 };
 
 struct Arena {
@@ -58,6 +64,7 @@ static void build_arena(const scf_decoder_cfg& cfg, Arena& a) {
     p.src_w[1] = w1; p.src_b[1] = b1; p.src_cout[1] = c1;
     p.cout = c0 + c1;
     p.ldw = (p.cout + 3) / 4 * 4;
+    p.tc_only = 0; p.tc_nr = 1; p.tc_src[0] = 0; p.tc_cnt[0] = cin; p.tc_src[1] = p.tc_cnt[1] = 0;
   };
   set(PC_CORR0, corr_ch, 1, 1, SCF_W_CORR0_W, SCF_W_CORR0_B, 256);
   set(PC_CORR1, 256, 3, 3, SCF_W_CORR1_W, SCF_W_CORR1_B, 192);
@@ -68,6 +75,18 @@ static void build_arena(const scf_decoder_cfg& cfg, Arena& a) {
   set(PC_Q0, 384, 1, 5, SCF_W_GRU_Q0_W, SCF_W_GRU_Q0_B, 128);
   set(PC_ZR1, 384, 5, 1, SCF_W_GRU_Z1_W, SCF_W_GRU_Z1_B, 128, SCF_W_GRU_R1_W, SCF_W_GRU_R1_B, 128);
   set(PC_Q1, 384, 5, 1, SCF_W_GRU_Q1_W, SCF_W_GRU_Q1_B, 128);
+  // precision 1: the GRU input is [h | cxt | motion]; the cxt columns never change inside the loop, so their contribution
+  // (plus the bias) is evaluated once per forward (PC_C*) and the per-iteration convolutions keep [h | motion] only
+  set(PC_CZR0, 384, 1, 5, SCF_W_GRU_Z0_W, SCF_W_GRU_Z0_B, 128, SCF_W_GRU_R0_W, SCF_W_GRU_R0_B, 128);
+  set(PC_CQ0, 384, 1, 5, SCF_W_GRU_Q0_W, SCF_W_GRU_Q0_B, 128);
+  set(PC_CZR1, 384, 5, 1, SCF_W_GRU_Z1_W, SCF_W_GRU_Z1_B, 128, SCF_W_GRU_R1_W, SCF_W_GRU_R1_B, 128);
+  set(PC_CQ1, 384, 5, 1, SCF_W_GRU_Q1_W, SCF_W_GRU_Q1_B, 128);
+  for (int id : {PC_CZR0, PC_CQ0, PC_CZR1, PC_CQ1}) { a.pc[id].tc_only = 1; a.pc[id].tc_src[0] = 128; a.pc[id].tc_cnt[0] = 128; }
+  if (cfg.precision == 1)
+    for (int id : {PC_ZR0, PC_Q0, PC_ZR1, PC_Q1}) {
+      PCInfo& p = a.pc[id];
+      p.tc_nr = 2; p.tc_src[0] = 0; p.tc_cnt[0] = 128; p.tc_src[1] = 256; p.tc_cnt[1] = 128;
+    }
   set(PC_HEADS, 128, 3, 3, SCF_W_FH0_W, SCF_W_FH0_B, 256, SCF_W_MH0_W, SCF_W_MH0_B, 256);
   set(PC_FHP, 256, 3, 3, SCF_W_FHP_W, SCF_W_FHP_B, 2);
   set(PC_MHP, 256, 1, 1, SCF_W_MHP_W, SCF_W_MHP_B, 1);
@@ -82,7 +101,7 @@ static void build_arena(const scf_decoder_cfg& cfg, Arena& a) {
   auto take = [&](size_t n) { size_t o = off; off += (n + 63) / 64 * 64; return o; };   // 256B-aligned slots
   for (int i = 0; i < PC_COUNT; ++i) {
     PCInfo& p = a.pc[i];
-    p.w_off = take((size_t)p.kh * p.kw * p.cin * p.ldw);
+    p.w_off = take(p.tc_only ? 0 : (size_t)p.kh * p.kw * p.cin * p.ldw);
     p.b_off = take(p.ldw);
   }
   for (int i = 0; i < 3; ++i) { a.gn_w[i] = take(128); a.gn_b[i] = take(128); }
@@ -99,7 +118,7 @@ static void build_arena(const scf_decoder_cfg& cfg, Arena& a) {
   for (int i = 0; i < PC_COUNT; ++i) {
     PCInfo& p = a.pc[i];
     p.tc = (cfg.precision == 1 && p.cin >= 8) ? 1 : 0;
-    p.cin_pad = (p.cin + 7) / 8 * 8;
+    p.cin_pad = (p.tc_cnt[0] + p.tc_cnt[1] + 7) / 8 * 8;
     p.cout_pad = (p.cout + 15) / 16 * 16;
     p.tc_off = 0;
     if (p.tc) {
@@ -148,6 +167,7 @@ struct Workspace {
       mask8, df1, df2, mf1, mf2, p1, p2, p3, fc0, fc1;
   // precision 1: split-bf16 planes [2][B*P][C] (byte offsets) and their plane strides in elements
   size_t s_corr, s_c1, s_cf, s_f1, s_h[2], s_cxt, s_motion, s_rh, s_hd, s_df1, s_mf1, s_df2, s_mf2, s_p1, s_p2;
+  size_t pre_zr[2], pre_q[2];   // fp32 [B*P][256] / [B*P][128]: context contribution + bias of the GRU convolutions, per pass
   int corr_stride_s;
   int hl[8], wl[8];
   int corr_stride;
@@ -187,6 +207,7 @@ static void build_workspace(const scf_decoder_cfg& cfg, int B, int H, int W, Wor
     w.s_h[0] = split(128); w.s_h[1] = split(128); w.s_cxt = split(128); w.s_motion = split(128); w.s_rh = split(128);
     w.s_hd = split(512); w.s_df1 = split(128); w.s_mf1 = split(64); w.s_df2 = split(64); w.s_mf2 = split(32);
     w.s_p1 = take((BP / 4 + 64) * 128 * 2 * 2); w.s_p2 = take((BP / 16 + 64) * 128 * 2 * 2);
+    for (int i = 0; i < 2; ++i) { w.pre_zr[i] = take(BP * 256 * 4); w.pre_q[i] = take(BP * 128 * 4); }
   }
   w.total_bytes = off;
 }
@@ -248,10 +269,16 @@ int scf_decoder_pack(const scf_decoder_cfg* cfg, const float* const* h_weights, 
     int o_off = 0;
     for (int s = 0; s < p.nsrc; ++s) {
       SCF_REQUIRE(h_weights[p.src_w[s]] != nullptr, SCF_ERR_ARG, "scf_decoder_pack: weight %d is null", p.src_w[s]);
-      SCF_TRY(scf_pack_conv_weight(h_weights[p.src_w[s]], base + p.w_off, p.src_cout[s], p.cin, p.kh, p.kw, p.ldw, o_off, st));
-      if (p.tc)
-        SCF_TRY(scf_pack_conv_weight_tc(h_weights[p.src_w[s]], reinterpret_cast<char*>(packed) + p.tc_off, p.src_cout[s], p.cin,
-                                        p.kh, p.kw, p.cin_pad, p.cout_pad, o_off, st));
+      if (!p.tc_only)
+        SCF_TRY(scf_pack_conv_weight(h_weights[p.src_w[s]], base + p.w_off, p.src_cout[s], p.cin, p.kh, p.kw, p.ldw, o_off, st));
+      if (p.tc) {
+        int i_dst = 0;
+        for (int r = 0; r < p.tc_nr; ++r) {
+          SCF_TRY(pack_conv_weight_tc_range(h_weights[p.src_w[s]], reinterpret_cast<char*>(packed) + p.tc_off, p.src_cout[s], p.cin,
+                                            p.tc_src[r], p.tc_cnt[r], i_dst, p.kh, p.kw, p.cin_pad, p.cout_pad, o_off, st));
+          i_dst += p.tc_cnt[r];
+        }
+      }
       if (p.src_b[s] >= 0) {
         SCF_REQUIRE(h_weights[p.src_b[s]] != nullptr, SCF_ERR_ARG, "scf_decoder_pack: bias %d is null", p.src_b[s]);
         SCF_CUDA(cudaMemcpyAsync(base + p.b_off + o_off, h_weights[p.src_b[s]], (size_t)p.src_cout[s] * 4,
@@ -370,7 +397,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
   int tc_hin = H8, tc_win = W8, tc_stride = 1;      // geometry of the next convtc call (pose head overrides it)
   auto convtc = [&](int id, std::initializer_list<SSeg> segs, int act, float* out_f32, int f32_stride, void* out_hl,
                     int hl_stride, int hl_coff, int epi = SCF_EPI_ACT, const float* aux0 = nullptr, const float* aux1 = nullptr,
-                    void* out2_hl = nullptr) -> int {
+                    void* out2_hl = nullptr, const float* pre = nullptr, int pre_stride = 0) -> int {
     const PCInfo& p = a.pc[id];
     scf_tc_conv_desc d = {};
     int n = 0;
@@ -387,9 +414,17 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
     d.out_hl = out_hl; d.out_hl_plane = (long long)BP * hl_stride; d.out_hl_stride = hl_stride; d.out_hl_coff = hl_coff;
     d.aux0 = aux0; d.aux0_stride = 128; d.aux1 = aux1; d.aux1_stride = 128;
     d.out2_hl = out2_hl; d.out2_hl_plane = (long long)BP * 128; d.out2_hl_stride = 128;
+    if (pre) { d.pre = pre; d.pre_stride = pre_stride; d.bias = nullptr; }   // the bias is part of the precomputed map
     return conv2d_tc(d, st);
   };
 
+  if (tcp) {
+    // loop-invariant part of the SepConvGRU: W[:, cxt columns] * cxt + bias for z|r and q of both passes (raft_decoder.py:235-253)
+    for (int pass = 0; pass < 2; ++pass) {
+      SCF_TRY(convtc(pass == 0 ? PC_CZR0 : PC_CZR1, {{S(ws.s_cxt), 128, 0, 128}}, SCF_ACT_NONE, F(ws.pre_zr[pass]), 256, nullptr, 0, 0));
+      SCF_TRY(convtc(pass == 0 ? PC_CQ0 : PC_CQ1, {{S(ws.s_cxt), 128, 0, 128}}, SCF_ACT_NONE, F(ws.pre_q[pass]), 128, nullptr, 0, 0));
+    }
+  }
   const float* flow_full = io->init_flow;
   for (int it = 0; it < iters; ++it) {
     float* flow_pose_k = io->flow_from_pose + (size_t)it * B * 2 * HW;
@@ -423,10 +458,12 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       SCF_TRY(convtc(PC_FLOW1, {{S(ws.s_f1), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_cf), 256, 192));
       SCF_TRY(convtc(PC_OUT0, {{S(ws.s_cf), 256, 0, 256}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_motion), 128, 0));
       for (int pass = 0; pass < 2; ++pass) {
-        SCF_TRY(convtc(pass == 0 ? PC_ZR0 : PC_ZR1, {{S(ws.s_h[pass]), 128, 0, 128}, {S(ws.s_cxt), 128, 0, 128}, {S(ws.s_motion), 128, 0, 128}},
-                       SCF_ACT_SIGMOID, F(ws.z), 128, nullptr, 0, 0, SCF_EPI_GRU_ZR, F(ws.h[pass]), nullptr, S(ws.s_rh)));
-        SCF_TRY(convtc(pass == 0 ? PC_Q0 : PC_Q1, {{S(ws.s_rh), 128, 0, 128}, {S(ws.s_cxt), 128, 0, 128}, {S(ws.s_motion), 128, 0, 128}},
-                       SCF_ACT_TANH, F(ws.h[pass ^ 1]), 128, S(ws.s_h[pass ^ 1]), 128, 0, SCF_EPI_GRU_Q, F(ws.h[pass]), F(ws.z), nullptr));
+        SCF_TRY(convtc(pass == 0 ? PC_ZR0 : PC_ZR1, {{S(ws.s_h[pass]), 128, 0, 128}, {S(ws.s_motion), 128, 0, 128}},
+                       SCF_ACT_SIGMOID, F(ws.z), 128, nullptr, 0, 0, SCF_EPI_GRU_ZR, F(ws.h[pass]), nullptr, S(ws.s_rh),
+                       F(ws.pre_zr[pass]), 256));
+        SCF_TRY(convtc(pass == 0 ? PC_Q0 : PC_Q1, {{S(ws.s_rh), 128, 0, 128}, {S(ws.s_motion), 128, 0, 128}},
+                       SCF_ACT_TANH, F(ws.h[pass ^ 1]), 128, S(ws.s_h[pass ^ 1]), 128, 0, SCF_EPI_GRU_Q, F(ws.h[pass]), F(ws.z), nullptr,
+                       F(ws.pre_q[pass]), 128));
       }
       SCF_TRY(convtc(PC_HEADS, {{S(ws.s_h[0]), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_hd), 512, 0));
       SCF_TRY(convtc(PC_FHP, {{S(ws.s_hd), 512, 0, 256}}, SCF_ACT_NONE, F(ws.dflow), 2, nullptr, 0, 0));
@@ -533,7 +570,7 @@ int scf_decoder_launch_count(const scf_decoder_cfg* cfg, int iters) {
   per_iter += cfg->pose_head ? 4 + 6 + 3 : 1;
   per_iter += cfg->mask_flow ? 1 : 0;
   int once = (cfg->precision == 1 ? 3 : 2) /*layout change of the feature maps + level 0*/ + (cfg->num_levels - 1) + 1 /*unproject*/ +
-             2 /*h, cxt*/;
+             2 /*h, cxt*/ + (cfg->precision == 1 ? 4 : 0) /*GRU context terms*/;
   if (cfg->mask_corr || cfg->mask_flow) once += 1;
   return once + per_iter * iters;
 }

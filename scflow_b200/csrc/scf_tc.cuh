@@ -64,6 +64,13 @@ __device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* 
       : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// launch_dependents: lets the next kernel on the stream (launched with the programmatic-serialization attribute) start
+// its prologue while this grid is still running; wait: blocks until every prerequisite grid has completed and its
+// memory is visible.  Both are no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

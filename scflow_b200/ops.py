@@ -273,8 +273,11 @@ def pack_conv_weight_tc(weights: Sequence[torch.Tensor], cin_pad: Optional[int] 
 def conv2d_tc(segs: Sequence, packed_w: torch.Tensor, bias: Optional[torch.Tensor], cout: int, kernel, act: str = 'none',
               out_f32: Optional[torch.Tensor] = None, out_f32_coff: int = 0, out_hl: Optional[torch.Tensor] = None,
               out_hl_coff: int = 0, epi: int = _lib.EPI_ACT, aux0=None, aux1=None, out2_hl=None, scale: float = 1.0,
-              w_batched: bool = False, stride: int = 1):
-    """tcgen05 convolution. ``segs`` = [(split tensor [2,B,H,W,stride], coff, nch), ...]."""
+              w_batched: bool = False, stride: int = 1, pre: Optional[torch.Tensor] = None, stride_xy=None,
+              stats: Optional[torch.Tensor] = None):
+    """tcgen05 convolution. ``segs`` = [(split tensor [2,B,H,W,stride], coff, nch), ...].
+    ``pre``: fp32 NHWC map added before the GRU gate non-linearity; ``stride_xy``: per-axis strides; ``stats``: fp32
+    [tiles*4*2*cout] buffer receiving per-tile InstanceNorm partial sums (see include/scflow_b200.h)."""
     kh, kw = (kernel, kernel) if isinstance(kernel, int) else kernel
     d = TcConvDesc()
     for n, (t, coff, nch) in enumerate(segs):
@@ -303,21 +306,43 @@ def conv2d_tc(segs: Sequence, packed_w: torch.Tensor, bias: Optional[torch.Tenso
     if out2_hl is not None:
         _req_split(out2_hl, 'out2_hl')
         d.out2_hl, d.out2_hl_plane, d.out2_hl_stride = out2_hl.data_ptr(), out2_hl[0].numel(), out2_hl.shape[-1]
+    if pre is not None:
+        _req(pre, 'pre')
+        d.pre, d.pre_stride = pre.data_ptr(), pre.shape[-1]
+    if stride_xy is not None:
+        d.stride_x, d.stride_y = stride_xy
+    if stats is not None:
+        _req(stats, 'stats')
+        d.stats = stats.data_ptr()
     check(_lib.load().scf_conv2d_tc(C.byref(d), stream_ptr()), 'scf_conv2d_tc')
     return out_f32 if out_f32 is not None else out_hl
 
 
+def conv2d_tc_tiles(b: int, hout: int, wout: int):
+    """(number of 128-pixel tiles, tiles per sample or 0) of scf_conv2d_tc for this output geometry."""
+    per = C.c_int(0)
+    n = _lib.load().scf_conv2d_tc_tiles(b, hout, wout, C.byref(per))
+    return n, per.value
+
+
 def make_tc_gru_zr_bench(h, cxt, mot, wz, wr, bias, z, rh):
-    """bench.py helper: a closure launching the GRU z|r tensor-core convolution (the dominant kernel) on prepared
-    buffers. h/cxt/mot: fp32 NHWC [B,H,W,128]; wz/wr: OIHW; returns (launch, kernel name, mma passes)."""
+    """bench.py helper: a closure launching the GRU z|r tensor-core convolution (the dominant kernel) exactly as
+    scf_decoder_forward issues it: input [h | motion] (K = taps*256), the loop-invariant context contribution + bias
+    (computed here once, as the decoder does once per forward) added in the epilogue.
+    h/cxt/mot: fp32 NHWC [B,H,W,128]; wz/wr: OIHW [128,384,kh,kw]; returns (launch, kernel name, mma passes, K)."""
     hs = split_nchw(h.permute(0, 3, 1, 2).contiguous())
     cs = split_nchw(cxt.permute(0, 3, 1, 2).contiguous())
     ms = split_nchw(mot.permute(0, 3, 1, 2).contiguous())
-    pw = pack_conv_weight_tc([wz, wr])
-    rhs = torch.zeros(2, *rh.shape, device=rh.device, dtype=torch.bfloat16)
     kernel = (int(wz.shape[2]), int(wz.shape[3]))
+    hm = [torch.cat([w[:, :128], w[:, 256:]], 1).contiguous() for w in (wz, wr)]
+    cx = [w[:, 128:256].contiguous() for w in (wz, wr)]
+    pw = pack_conv_weight_tc(hm)
+    pre = torch.empty(*h.shape[:3], 256, device=h.device, dtype=torch.float32)
+    conv2d_tc([(cs, 0, 128)], pack_conv_weight_tc(cx), bias, 256, kernel, act='none', out_f32=pre)
+    rhs = torch.zeros(2, *rh.shape, device=rh.device, dtype=torch.bfloat16)
 
     def launch():
-        conv2d_tc([(hs, 0, 128), (cs, 0, 128), (ms, 0, 128)], pw, bias, 256, kernel, act='sigmoid', out_f32=z,
-                  epi=_lib.EPI_GRU_ZR, aux0=h, out2_hl=rhs)
-    return launch, 'conv_tc_kernel (GRU z|r 1x5, tcgen05 split-bf16, N=256, K=1920)', 3
+        conv2d_tc([(hs, 0, 128), (ms, 0, 128)], pw, None, 256, kernel, act='sigmoid', out_f32=z,
+                  epi=_lib.EPI_GRU_ZR, aux0=h, out2_hl=rhs, pre=pre)
+    k = kernel[0] * kernel[1] * 256
+    return launch, f'conv_tc_kernel (GRU z|r 1x5, tcgen05 split-bf16, N=256, K={k}; context term hoisted out of the loop)', 3, k
