@@ -667,6 +667,80 @@ __global__ void split_copy_kernel(const float* __restrict__ src, int src_stride,
   }
 }
 
+// ------------------------------------------------------------------ thin-input convolutions on the tensor cores
+// A k x k convolution over very few input channels (RGB stem 7x7x3, flow encoders 7x7x2) has K = k*k*Cin <= 147: too
+// thin per tap for a 64-channel k-chunk.  The kernel row is therefore folded into the channel axis first:
+//   T[n, y, xo, kx*Cin + c] = in[n, c, y, xo*sx + kx - k/2]      (zero outside the image; channels padded to 16 or 32:
+//   a power-of-two pixel pitch - measured: the 48 B pitch of 24 channels makes the TMA tile loads 2.3x slower)
+// written as split-bf16 NHWC, after which the layer is a k x 1 convolution (stride sy vertically) over KW*Cin channels
+// that conv_tc_kernel runs with one ragged k-chunk per tap.
+template <int CIN, int KW, bool NCHW>
+__global__ void __launch_bounds__(256) im2col_x_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long plane,
+                                                             int N, int H, int Wi, int Wo, int sx, long long total) {
+  constexpr int KC = KW * CIN <= 16 ? 16 : 32;
+  static_assert(KW * CIN <= 32, "folded row must fit 32 channels");
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int xo = (int)(idx % Wo);
+    const long long r = idx / Wo;
+    const int y = (int)(r % H);
+    const long long n = r / H;
+    __nv_bfloat16 hi[KC], lo[KC];
+#pragma unroll
+    for (int kx = 0; kx < KW; ++kx) {
+      const int ix = xo * sx + kx - KW / 2;
+      const bool ok = ix >= 0 && ix < Wi;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        float v = 0.f;
+        if (ok) v = NCHW ? __ldg(in + ((n * CIN + c) * H + y) * Wi + ix) : __ldg(in + ((n * H + y) * Wi + ix) * CIN + c);
+        split_bf16(v, hi[kx * CIN + c], lo[kx * CIN + c]);
+      }
+    }
+#pragma unroll
+    for (int i = KW * CIN; i < KC; ++i) { hi[i] = __float2bfloat16_rn(0.f); lo[i] = hi[i]; }
+    uint4* oh = reinterpret_cast<uint4*>(out + idx * KC);
+    uint4* ol = reinterpret_cast<uint4*>(out + plane + idx * KC);
+#pragma unroll
+    for (int i = 0; i < KC / 8; ++i) {
+      oh[i] = *reinterpret_cast<const uint4*>(hi + 8 * i);
+      ol[i] = *reinterpret_cast<const uint4*>(lo + 8 * i);
+    }
+  }
+}
+
+// OIHW [O, C, KH, KW] -> [O, KW*C, KH, 1] with channel kx*C + c (the weight of the folded convolution above)
+__global__ void fold_kx_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int O, int C, int KH, int KW) {
+  const int total = O * C * KH * KW;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int kx = idx % KW;
+    int r = idx / KW;
+    const int ky = r % KH; r /= KH;
+    const int c = r % C;
+    const int o = r / C;
+    out[((long long)o * (KW * C) + kx * C + c) * KH + ky] = w[idx];
+  }
+}
+
+// in: NCHW fp32 [N,cin,H,Wi] (nchw) or NHWC fp32 [N,H,Wi,cin]; out: split-bf16 [2][N,H,Wo,KC], KC = 16 (kw*cin <= 16) or 32,
+// Wo = (Wi-1)/sx + 1
+int im2col_x_split(const float* in, int nchw, int cin, int kw, void* out_hl, long long plane, int N, int H, int Wi, int sx,
+                   cudaStream_t st) {
+  SCF_REQUIRE(in && out_hl && N > 0 && H > 0 && Wi > 0 && (sx == 1 || sx == 2), SCF_ERR_ARG, "im2col_x_split: bad args");
+  const int Wo = (Wi - 1) / sx + 1;
+  const long long total = (long long)N * H * Wo;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_hl);
+  if (cin == 3 && kw == 7 && nchw) im2col_x_split_kernel<3, 7, true><<<blocks, 256, 0, st>>>(in, o, plane, N, H, Wi, Wo, sx, total);
+  else if (cin == 2 && kw == 7 && !nchw) im2col_x_split_kernel<2, 7, false><<<blocks, 256, 0, st>>>(in, o, plane, N, H, Wi, Wo, sx, total);
+  else SCF_REQUIRE(false, SCF_ERR_UNSUPPORTED, "im2col_x_split: unsupported (cin %d, kw %d, nchw %d)", cin, kw, nchw);
+  return check_launch("im2col_x_split_kernel");
+}
+
+// packs an OIHW [O,C,KH,KW] weight for the folded k x 1 convolution: bf16 [2][KH][cout_pad][cin_pad], cin_pad >= pad8(KW*C).
+// `scratch` needs O*C*KH*KW floats.
+int pack_conv_weight_tc_foldx(const float* w_oihw, float* scratch, void* packed, int O, int C, int KH, int KW, int cin_pad,
+                              int cout_pad, int o_off, cudaStream_t st);
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -875,8 +949,10 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     cuuint64_t str[4] = {(cuuint64_t)sg.stride * 2, (cuuint64_t)d.W * sg.stride * 2, (cuuint64_t)d.H * d.W * sg.stride * 2,
                          (cuuint64_t)sg.plane_stride * 2};
     // box = elements TRAVERSED per dimension; with element strides (1,s,s,1,1) it deposits TW x TH x TB pixels
-    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.TW * p.sx), (cuuint32_t)(p.TH * p.sy), (cuuint32_t)p.TB, 2};
-    cuuint32_t estr[5] = {1, (cuuint32_t)p.sx, (cuuint32_t)p.sy, 1, 1};
+    // a one-row (one-column) tile needs no element stride along that axis: the producer's coordinate already carries it
+    const int bsx = p.TW == 1 ? 1 : p.sx, bsy = p.TH == 1 ? 1 : p.sy;
+    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.TW * bsx), (cuuint32_t)(p.TH * bsy), (cuuint32_t)p.TB, 2};
+    cuuint32_t estr[5] = {1, (cuuint32_t)bsx, (cuuint32_t)bsy, 1, 1};
     SCF_TRY(encode_map(&tmA[s], base, 5, dims, str, box, estr));
     p.seg_chunks[s] = cdiv(sg.nch, TC_BK);
     p.seg_last_ks[s] = cdiv(sg.nch - (p.seg_chunks[s] - 1) * TC_BK, 16);
@@ -965,6 +1041,14 @@ int pack_conv_weight_tc_range(const float* w_oihw, void* packed, int O, int I_to
   pack_weight_tc_kernel<<<blocks, 256, 0, st>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(packed), O, i_count, kh * kw, cin_pad,
                                                 cout_pad, o_off, I_total, i_begin, i_dst);
   return check_launch("pack_weight_tc_kernel");
+}
+
+int pack_conv_weight_tc_foldx(const float* w_oihw, float* scratch, void* packed, int O, int C, int KH, int KW, int cin_pad,
+                              int cout_pad, int o_off, cudaStream_t st) {
+  SCF_REQUIRE(w_oihw && scratch && packed, SCF_ERR_ARG, "pack_conv_weight_tc_foldx: null pointer");
+  fold_kx_weight_kernel<<<cdiv((long long)O * C * KH * KW, 256), 256, 0, st>>>(w_oihw, scratch, O, C, KH, KW);
+  SCF_TRY(check_launch("fold_kx_weight_kernel"));
+  return pack_conv_weight_tc_range(scratch, packed, O, KW * C, 0, KW * C, 0, KH, 1, cin_pad, cout_pad, o_off, st);
 }
 }  // namespace scf
 

@@ -12,6 +12,12 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st);
 int avgpool2(const float* in, float* out, long long nq, int hi, int wi, cudaStream_t st);
 int pack_conv_weight_tc_range(const float* w_oihw, void* packed, int O, int I_total, int i_begin, int i_count, int i_dst, int kh,
                               int kw, int cin_pad, int cout_pad, int o_off, cudaStream_t st);
+int heads_predict(const void* hd_hl, long long plane, int stride, int hidden, const float* wf, int ldwf, const float* bf,
+                  const float* wm, int ldwm, const float* bm, float* dflow, float* mask8, int B, int H, int W, cudaStream_t st);
+int im2col_x_split(const float* in, int nchw, int cin, int kw, void* out_hl, long long plane, int N, int H, int Wi, int sx,
+                   cudaStream_t st);
+int pack_conv_weight_tc_foldx(const float* w_oihw, float* scratch, void* packed, int O, int C, int KH, int KW, int cin_pad,
+                              int cout_pad, int o_off, cudaStream_t st);
 int corr_build_dispatch(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
                         float* const* levels, void* scratch, int precision, cudaStream_t st);
 
@@ -43,12 +49,15 @@ struct PCInfo {
   size_t tc_off;
   int tc_only;                // no fp32 copy (exists for the tensor-core path only)
   int tc_nr, tc_src[2], tc_cnt[2];   // input-channel ranges of the source weight that the tensor-core copy holds, packed densely
+  int foldx;                  // thin input: the tensor-core copy is the kh x 1 convolution over kx*cin + c channels (x-im2col)
+  int tc_kh, tc_kw;           // kernel size the tensor-core convolution runs with
 };
 
 struct Arena {
   PCInfo pc[PC_COUNT];
   size_t gn_w[3], gn_b[3];
   size_t fc0_w, fc0_b, fc1_w, fc1_b, rot_w, rot_b, tr_w, tr_b;
+  size_t fold_scratch;        // floats: staging of a folded thin-input weight while packing
   size_t total_floats;
   size_t total_bytes;         // fp32 section + tensor-core section
   int nc, rot_rows, tr_rows;
@@ -65,6 +74,7 @@ static void build_arena(const scf_decoder_cfg& cfg, Arena& a) {
     p.cout = c0 + c1;
     p.ldw = (p.cout + 3) / 4 * 4;
     p.tc_only = 0; p.tc_nr = 1; p.tc_src[0] = 0; p.tc_cnt[0] = cin; p.tc_src[1] = p.tc_cnt[1] = 0;
+    p.foldx = 0; p.tc_kh = kh; p.tc_kw = kw;
   };
   set(PC_CORR0, corr_ch, 1, 1, SCF_W_CORR0_W, SCF_W_CORR0_B, 256);
   set(PC_CORR1, 256, 3, 3, SCF_W_CORR1_W, SCF_W_CORR1_B, 192);
@@ -112,6 +122,7 @@ static void build_arena(const scf_decoder_cfg& cfg, Arena& a) {
   a.fc1_w = take((size_t)256 * 1024); a.fc1_b = take(256);
   a.rot_w = take((size_t)a.rot_rows * 256); a.rot_b = take(a.rot_rows);
   a.tr_w = take((size_t)a.tr_rows * 256); a.tr_b = take(a.tr_rows);
+  a.fold_scratch = take((size_t)128 * 2 * 7 * 7);
   a.total_floats = off;
   // tensor-core section: every stride-1 convolution with >= 8 input channels
   size_t boff = (off * 4 + 1023) / 1024 * 1024;
@@ -119,11 +130,15 @@ static void build_arena(const scf_decoder_cfg& cfg, Arena& a) {
     PCInfo& p = a.pc[i];
     p.tc = (cfg.precision == 1 && p.cin >= 8) ? 1 : 0;
     p.cin_pad = (p.tc_cnt[0] + p.tc_cnt[1] + 7) / 8 * 8;
+    if (cfg.precision == 1 && (i == PC_FLOW0 || i == PC_DFE0)) {     // 7x7 over 2 channels -> 7x1 over 14 (padded to 16)
+      p.tc = 1; p.foldx = 1; p.tc_kh = p.kh; p.tc_kw = 1;
+      p.cin_pad = (p.kw * p.cin + 7) / 8 * 8;
+    }
     p.cout_pad = (p.cout + 15) / 16 * 16;
     p.tc_off = 0;
     if (p.tc) {
       p.tc_off = boff;
-      boff += ((size_t)2 * p.kh * p.kw * p.cout_pad * p.cin_pad * 2 + 1023) / 1024 * 1024;
+      boff += ((size_t)2 * p.tc_kh * p.tc_kw * p.cout_pad * p.cin_pad * 2 + 1023) / 1024 * 1024;
     }
   }
   a.total_bytes = boff;
@@ -167,6 +182,7 @@ struct Workspace {
       mask8, df1, df2, mf1, mf2, p1, p2, p3, fc0, fc1;
   // precision 1: split-bf16 planes [2][B*P][C] (byte offsets) and their plane strides in elements
   size_t s_corr, s_c1, s_cf, s_f1, s_h[2], s_cxt, s_motion, s_rh, s_hd, s_df1, s_mf1, s_df2, s_mf2, s_p1, s_p2;
+  size_t s_t7;                  // x-folded 2-channel flow map [2][B*P][16] feeding the 7x1 tensor-core form of the 7x7 flow encoders
   size_t pre_zr[2], pre_q[2];   // fp32 [B*P][256] / [B*P][128]: context contribution + bias of the GRU convolutions, per pass
   int corr_stride_s;
   int hl[8], wl[8];
@@ -208,6 +224,7 @@ static void build_workspace(const scf_decoder_cfg& cfg, int B, int H, int W, Wor
     w.s_hd = split(512); w.s_df1 = split(128); w.s_mf1 = split(64); w.s_df2 = split(64); w.s_mf2 = split(32);
     w.s_p1 = take((BP / 4 + 64) * 128 * 2 * 2); w.s_p2 = take((BP / 16 + 64) * 128 * 2 * 2);
     for (int i = 0; i < 2; ++i) { w.pre_zr[i] = take(BP * 256 * 4); w.pre_q[i] = take(BP * 128 * 4); }
+    w.s_t7 = split(16);
   }
   w.total_bytes = off;
 }
@@ -271,7 +288,10 @@ int scf_decoder_pack(const scf_decoder_cfg* cfg, const float* const* h_weights, 
       SCF_REQUIRE(h_weights[p.src_w[s]] != nullptr, SCF_ERR_ARG, "scf_decoder_pack: weight %d is null", p.src_w[s]);
       if (!p.tc_only)
         SCF_TRY(scf_pack_conv_weight(h_weights[p.src_w[s]], base + p.w_off, p.src_cout[s], p.cin, p.kh, p.kw, p.ldw, o_off, st));
-      if (p.tc) {
+      if (p.tc && p.foldx) {
+        SCF_TRY(pack_conv_weight_tc_foldx(h_weights[p.src_w[s]], base + a.fold_scratch, reinterpret_cast<char*>(packed) + p.tc_off,
+                                          p.src_cout[s], p.cin, p.kh, p.kw, p.cin_pad, p.cout_pad, o_off, st));
+      } else if (p.tc) {
         int i_dst = 0;
         for (int r = 0; r < p.tc_nr; ++r) {
           SCF_TRY(pack_conv_weight_tc_range(h_weights[p.src_w[s]], reinterpret_cast<char*>(packed) + p.tc_off, p.src_cout[s], p.cin,
@@ -405,7 +425,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
     for (const SSeg& sg : segs) { d.seg[n].ptr = sg.ptr; d.seg[n].plane_stride = in_pix * sg.stride; d.seg[n].stride = sg.stride;
                                   d.seg[n].coff = sg.coff; d.seg[n].nch = sg.nch; ++n; }
     d.nseg = n;
-    d.B = B; d.H = tc_hin; d.W = tc_win; d.kh = p.kh; d.kw = p.kw; d.stride = tc_stride;
+    d.B = B; d.H = tc_hin; d.W = tc_win; d.kh = p.tc_kh; d.kw = p.tc_kw; d.stride = tc_stride;
     d.w = reinterpret_cast<const char*>(packed) + p.tc_off; d.cin_pad = p.cin_pad; d.cout_pad = p.cout_pad; d.cout = p.cout;
     d.w_batched = 0;
     d.bias = p.src_b[0] >= 0 ? pw + p.b_off : nullptr;
@@ -453,8 +473,8 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
                                     S(ws.s_corr), (long long)BP * ws.corr_stride_s, ws.corr_stride_s, B, H8, W8, st));
       SCF_TRY(convtc(PC_CORR0, {{S(ws.s_corr), ws.corr_stride_s, 0, ws.corr_stride_s}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_c1), 256, 0));
       SCF_TRY(convtc(PC_CORR1, {{S(ws.s_c1), 256, 0, 256}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_cf), 256, 0));
-      SCF_TRY(conv(PC_FLOW0, {{menc_flow, 2, 0, 2}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, nullptr, 128, 0, SCF_EPI_ACT, nullptr, nullptr,
-                   nullptr, S(ws.s_f1), 128));
+      SCF_TRY(im2col_x_split(menc_flow, 0, 2, 7, S(ws.s_t7), (long long)BP * 16, B, H8, W8, 1, st));
+      SCF_TRY(convtc(PC_FLOW0, {{S(ws.s_t7), 16, 0, 16}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_f1), 128, 0));
       SCF_TRY(convtc(PC_FLOW1, {{S(ws.s_f1), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_cf), 256, 192));
       SCF_TRY(convtc(PC_OUT0, {{S(ws.s_cf), 256, 0, 256}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_motion), 128, 0));
       for (int pass = 0; pass < 2; ++pass) {
@@ -466,11 +486,12 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
                        F(ws.pre_q[pass]), 128));
       }
       SCF_TRY(convtc(PC_HEADS, {{S(ws.s_h[0]), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_hd), 512, 0));
-      SCF_TRY(convtc(PC_FHP, {{S(ws.s_hd), 512, 0, 256}}, SCF_ACT_NONE, F(ws.dflow), 2, nullptr, 0, 0));
-      SCF_TRY(convtc(PC_MHP, {{S(ws.s_hd), 512, 256, 256}}, SCF_ACT_SIGMOID, F(ws.mask8), 1, nullptr, 0, 0));
+      // both predict layers (3x3 256->2, 1x1 256->1 + sigmoid) in one streaming fp32 kernel over the split hidden map
+      SCF_TRY(heads_predict(S(ws.s_hd), (long long)BP * 512, 512, 256, pw + a.pc[PC_FHP].w_off, a.pc[PC_FHP].ldw, pw + a.pc[PC_FHP].b_off,
+                            pw + a.pc[PC_MHP].w_off, a.pc[PC_MHP].ldw, pw + a.pc[PC_MHP].b_off, F(ws.dflow), F(ws.mask8), B, H8, W8, st));
       if (cfg->pose_head) {
-        SCF_TRY(conv(PC_DFE0, {{F(ws.dflow), 2, 0, 2}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, nullptr, 128, 0, SCF_EPI_ACT, nullptr, nullptr,
-                     nullptr, S(ws.s_df1), 128));
+        SCF_TRY(im2col_x_split(F(ws.dflow), 0, 2, 7, S(ws.s_t7), (long long)BP * 16, B, H8, W8, 1, st));
+        SCF_TRY(convtc(PC_DFE0, {{S(ws.s_t7), 16, 0, 16}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_df1), 128, 0));
         SCF_TRY(convtc(PC_DFE1, {{S(ws.s_df1), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_df2), 64, 0));
         SCF_TRY(conv(PC_ME0, {{F(ws.mask8), 1, 0, 1}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, nullptr, 64, 0, SCF_EPI_ACT, nullptr, nullptr,
                      nullptr, S(ws.s_mf1), 64));
@@ -566,7 +587,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
 
 int scf_decoder_launch_count(const scf_decoder_cfg* cfg, int iters) {
   if (check_cfg(cfg) != 0) return -1;
-  int per_iter = 1 /*down8*/ + 1 /*lookup*/ + 6 /*menc*/ + 4 /*gru*/ + 3 /*heads*/ + 2 /*up8*/ + 2 /*pose upd + reproject*/;
+  int per_iter = 1 /*down8*/ + 1 /*lookup*/ + 6 /*menc*/ - (cfg->precision == 1 ? 1 : 0) /*merged predict layers*/ + (cfg->precision == 1 ? (cfg->pose_head ? 2 : 1) : 0) /*x-folding of the flow maps*/ + 4 /*gru*/ + 3 /*heads*/ + 2 /*up8*/ + 2 /*pose upd + reproject*/;
   per_iter += cfg->pose_head ? 4 + 6 + 3 : 1;
   per_iter += cfg->mask_flow ? 1 : 0;
   int once = (cfg->precision == 1 ? 3 : 2) /*layout change of the feature maps + level 0*/ + (cfg->num_levels - 1) + 1 /*unproject*/ +

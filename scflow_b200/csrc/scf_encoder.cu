@@ -11,6 +11,10 @@ namespace scf {
 int conv2d_f32(const scf_conv_desc& d, cudaStream_t st);
 int conv2d_thin(const scf_conv_desc& d, int in_nchw, cudaStream_t st);
 int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st);
+int im2col_x_split(const float* in, int nchw, int cin, int kw, void* out_hl, long long plane, int N, int H, int Wi, int sx,
+                   cudaStream_t st);
+int pack_conv_weight_tc_foldx(const float* w_oihw, float* scratch, void* packed, int O, int C, int KH, int KW, int cin_pad,
+                              int cout_pad, int o_off, cudaStream_t st);
 
 // ------------------------------------------------------------------ conv-unit table
 struct EncUnit { int cin, cout, k, stride; };
@@ -25,8 +29,9 @@ static const EncUnit kUnits[SCF_ENC_UNITS] = {
 struct EncArena {
   size_t w_f32[SCF_ENC_UNITS];   // byte offsets: folded fp32 OIHW copy (source of both packings)
   size_t bias[SCF_ENC_UNITS];    // folded bias, padded to a multiple of 16 floats
-  size_t packed[SCF_ENC_UNITS];  // unit 0: fp32 [K][ldw]; others: bf16 [2][taps][cout_pad][cin_pad]
-  int cin_pad[SCF_ENC_UNITS], cout_pad[SCF_ENC_UNITS], ldw0;
+  size_t packed[SCF_ENC_UNITS];  // bf16 [2][taps][cout_pad][cin_pad]; unit 0 (7x7 stem) is folded to 7x1 over kx*3+c channels
+  size_t fold0;                  // scratch for the folded stem weight
+  int cin_pad[SCF_ENC_UNITS], cout_pad[SCF_ENC_UNITS];
   size_t total;
 };
 
@@ -39,8 +44,11 @@ static void build_enc_arena(EncArena& a) {
     a.cout_pad[u] = (e.cout + 15) / 16 * 16;
     a.w_f32[u] = take((size_t)e.cout * e.cin * e.k * e.k * 4);
     a.bias[u] = take((size_t)a.cout_pad[u] * 4);
-    if (u == 0) { a.ldw0 = (e.cout + 3) / 4 * 4; a.packed[u] = take((size_t)e.k * e.k * e.cin * a.ldw0 * 4); }
-    else a.packed[u] = take((size_t)2 * e.k * e.k * a.cout_pad[u] * a.cin_pad[u] * 2);
+    if (u == 0) {
+      a.cin_pad[u] = 32;       // 7 taps x 3 channels = 21, padded to a power-of-two pixel pitch
+      a.packed[u] = take((size_t)2 * e.k * a.cout_pad[u] * a.cin_pad[u] * 2);
+      a.fold0 = take((size_t)e.cout * e.cin * e.k * e.k * 4);
+    } else a.packed[u] = take((size_t)2 * e.k * e.k * a.cout_pad[u] * a.cin_pad[u] * 2);
   }
   a.total = off;
 }
@@ -111,6 +119,39 @@ __global__ void instnorm_finalize_kernel(const float* __restrict__ part, float* 
   stat[(long long)idx * 2] = (float)mean;
   stat[(long long)idx * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
+// stage 2 for statistics gathered by the convolution's own epilogue (scf_conv2d_tc `stats`): part is
+// [N * tiles_per_img][4 warps][2][C]; one block per image, deterministic double-precision combine
+__global__ void __launch_bounds__(256) instnorm_finalize_tiles_kernel(const float* __restrict__ part, float* __restrict__ stat,
+                                                                      int HW, int C, float eps, int tiles_per_img) {
+  // grid (N, C/32): thread = (channel c of 32, row group g of 8); 8 independent loads in flight per thread
+  __shared__ double ss[256], sq[256];
+  const int n = blockIdx.x;
+  const int c = blockIdx.y * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+  const int rows = tiles_per_img * 4;
+  const float* base = part + (long long)n * rows * 2 * C + c;
+  double s = 0., q = 0.;
+  for (int r0 = g; r0 < rows; r0 += 64) {
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = r0 + 8 * j;
+      a[j] = r < rows ? base[(long long)r * 2 * C] : 0.f;
+      b[j] = r < rows ? base[(long long)r * 2 * C + C] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += a[j]; q += b[j]; }
+  }
+  ss[threadIdx.x] = s; sq[threadIdx.x] = q;
+  __syncthreads();
+  if (g == 0) {
+    for (int i = 1; i < 8; ++i) { s += ss[i * 32 + (threadIdx.x & 31)]; q += sq[i * 32 + (threadIdx.x & 31)]; }
+    const double mean = s / HW;
+    double var = q / HW - mean * mean;
+    if (var < 0.) var = 0.;
+    stat[((long long)n * C + c) * 2] = (float)mean;
+    stat[((long long)n * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
 // stage 3: y = [relu]( (x - mean) * rstd  [+ (r - rmean) * rrstd | + r] ) -> fp32 and/or split-bf16
 __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ stat,
                                                              const float* __restrict__ res, const float* __restrict__ res_stat,
@@ -153,18 +194,30 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __rest
 }
 
 struct EncWs {
-  size_t img, raw, raw2, xf[2], xs[2], ts, part, stat, stat2;
+  size_t t0, raw, raw2, xf[2], xs[2], ts, part, stat, stat2;
   size_t total;
 };
 static void build_enc_ws(int N, int H, int W, EncWs& w) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
   const size_t p2 = (size_t)N * (H / 2) * (W / 2);
-  w.img = take((size_t)N * H * W * 3 * 4);
+  w.t0 = take((size_t)N * H * (W / 2) * 32 * 2 * 2);     // x-folded image, split-bf16 [2][N,H,W/2,32]
   w.raw = take(p2 * 64 * 4); w.raw2 = take(p2 / 4 * 96 * 4 + 4096);
   for (int i = 0; i < 2; ++i) { w.xf[i] = take(p2 * 64 * 4); w.xs[i] = take(p2 * 64 * 2 * 2); }
   w.ts = take(p2 * 64 * 2 * 2);
-  w.part = take((size_t)N * IN_SLICES * 2 * 128 * 4); w.stat = take((size_t)N * 128 * 2 * 4); w.stat2 = take((size_t)N * 128 * 2 * 4);
+  {
+    // partial sums: either IN_SLICES per image (separate pass) or one row per (128-pixel tile, epilogue warp) of a convolution
+    size_t part = (size_t)N * IN_SLICES * 2 * 128 * 4;
+    int hh = H / 2, ww = W / 2;
+    const int chans[3] = {64, 96, 128};
+    for (int l = 0; l < 3; ++l) {
+      const size_t need = (size_t)scf_conv2d_tc_tiles(N, hh, ww, nullptr) * 4 * 2 * chans[l] * 4;
+      if (need > part) part = need;
+      hh = (hh - 1) / 2 + 1; ww = (ww - 1) / 2 + 1;
+    }
+    w.part = take(part);
+  }
+  w.stat = take((size_t)N * 128 * 2 * 4); w.stat2 = take((size_t)N * 128 * 2 * 4);
   w.total = off;
 }
 
@@ -206,7 +259,8 @@ int scf_encoder_pack(int norm, const float* const* h_weights, void* packed, void
     fold_bn_kernel<<<e.cout, 128, 0, st>>>(s[0], s[1], fold ? s[2] : nullptr, s[3], s[4], s[5], 1e-5f, wf, bf, e.cout,
                                            e.cin * e.k * e.k);
     SCF_TRY(check_launch("fold_bn_kernel"));
-    if (u == 0) SCF_TRY(scf_pack_conv_weight(wf, reinterpret_cast<float*>(base + a.packed[u]), e.cout, e.cin, e.k, e.k, a.ldw0, 0, st));
+    if (u == 0) SCF_TRY(pack_conv_weight_tc_foldx(wf, reinterpret_cast<float*>(base + a.fold0), base + a.packed[u], e.cout, e.cin, e.k,
+                                                  e.k, a.cin_pad[u], a.cout_pad[u], 0, st));
     else SCF_TRY(scf_pack_conv_weight_tc(wf, base + a.packed[u], e.cout, e.cin, e.k, e.k, a.cin_pad[u], a.cout_pad[u], 0, st));
   }
   return 0;
@@ -232,26 +286,24 @@ int scf_encoder_forward(int norm, const void* packed, const float* images, int N
   auto BIAS = [&](int u) { return reinterpret_cast<const float*>(pk + a.bias[u]); };
   const bool inorm = norm == SCF_ENC_NORM_IN;
 
-  // ---- stem: 7x7 stride-2 conv on the fp32 cores, reading the NCHW image directly
+  // ---- stem: 7x7 stride-2 convolution on the tensor cores: kernel rows folded into the channel axis (x-im2col with
+  // stride 2 -> 21 channels), then a 7x1 convolution with vertical stride 2 (see scf_conv_tc.cu)
   int h = H / 2, w = W / 2;
   long long npix = (long long)N * h * w;
-  {
-    scf_conv_desc d = {};
-    d.seg[0] = {images, 3, 0, 3};
+  SCF_TRY(im2col_x_split(images, /*nchw=*/1, 3, 7, S(ws.t0), (long long)N * H * w * a.cin_pad[0], N, H, W, 2, st));
+  auto stem_conv = [&](int act, float* of32, void* ohl, float* stats) -> int {
+    scf_tc_conv_desc d = {};
+    d.seg[0].ptr = S(ws.t0); d.seg[0].plane_stride = (long long)N * H * w * a.cin_pad[0]; d.seg[0].stride = a.cin_pad[0];
+    d.seg[0].coff = 0; d.seg[0].nch = a.cin_pad[0];
     d.nseg = 1;
-    d.B = N; d.Hi = H; d.Wi = W; d.Ho = h; d.Wo = w;
-    d.kh = d.kw = 7; d.sh = d.sw = 2; d.ph = d.pw = 3;
-    d.w = reinterpret_cast<const float*>(pk + a.packed[0]); d.ldw = a.ldw0; d.cout = 64;
-    d.bias = BIAS(0); d.scale = 1.f; d.epi = SCF_EPI_ACT;
-    if (inorm) { d.act = SCF_ACT_NONE; d.out = F(ws.raw); d.out_stride = 64; }
-    else {
-      d.act = SCF_ACT_RELU; d.out = F(ws.xf[0]); d.out_stride = 64;
-      d.out_hl = S(ws.xs[0]); d.out_hl_plane = npix * 64; d.out_hl_stride = 64;
-    }
-    const int rc = conv2d_thin(d, /*in_nchw=*/1, st);
-    SCF_REQUIRE(rc != -100, SCF_ERR_UNSUPPORTED, "scf_encoder_forward: stem kernel rejected the shape");
-    SCF_TRY(rc);
-  }
+    d.B = N; d.H = H; d.W = w; d.kh = 7; d.kw = 1; d.stride_x = 1; d.stride_y = 2;
+    d.w = pk + a.packed[0]; d.cin_pad = a.cin_pad[0]; d.cout_pad = a.cout_pad[0]; d.cout = 64;
+    d.bias = BIAS(0); d.scale = 1.f; d.epi = SCF_EPI_ACT; d.act = act;
+    d.out_f32 = of32; d.out_f32_stride = 64;
+    d.out_hl = ohl; d.out_hl_plane = npix * 64; d.out_hl_stride = 64;
+    d.stats = stats;
+    return conv2d_tc(d, st);
+  };
   // InstanceNorm helpers
   auto in_stats = [&](const float* x, float* stat, int hw, int C) -> int {
     instnorm_partial_kernel<<<dim3(IN_SLICES, N), 256, 0, st>>>(x, F(ws.part), hw, C);
@@ -267,7 +319,8 @@ int scf_encoder_forward(int norm, const void* packed, const float* images, int N
     return check_launch("instnorm_apply_kernel");
   };
   // tensor-core conv unit u on split input (hin x win), stride from the table
-  auto tcconv = [&](int u, void* in_s, int hin, int win, int act, float* of32, void* ohl, const float* residual) -> int {
+  auto tcconv = [&](int u, void* in_s, int hin, int win, int act, float* of32, void* ohl, const float* residual,
+                    float* stats = nullptr) -> int {
     const EncUnit& e = kUnits[u];
     scf_tc_conv_desc d = {};
     const long long in_pix = (long long)N * hin * win;
@@ -280,12 +333,39 @@ int scf_encoder_forward(int norm, const void* packed, const float* images, int N
     d.out_f32 = of32; d.out_f32_stride = e.cout;
     d.out_hl = ohl; d.out_hl_plane = (long long)N * ho * wo * e.cout; d.out_hl_stride = e.cout;
     d.aux0 = residual; d.aux0_stride = e.cout;
+    d.stats = stats;
     return conv2d_tc(d, st);
+  };
+  // convolution + InstanceNorm statistics of its output: the conv epilogue emits per-tile partial sums when a tile never
+  // spans two images (always, except for tiny maps), otherwise a separate statistics pass reads the map back
+  auto tcconv_stats = [&](int u, void* in_s, int hin, int win, float* raw, float* stat) -> int {
+    const EncUnit& e = kUnits[u];
+    const int ho = (hin + 2 * (e.k / 2) - e.k) / e.stride + 1, wo = (win + 2 * (e.k / 2) - e.k) / e.stride + 1;
+    int per_img = 0;
+    scf_conv2d_tc_tiles(N, ho, wo, &per_img);
+    if (per_img > 0 && e.cout % 32 == 0) {
+      SCF_TRY(tcconv(u, in_s, hin, win, SCF_ACT_NONE, raw, nullptr, nullptr, F(ws.part)));
+      instnorm_finalize_tiles_kernel<<<dim3(N, e.cout / 32), 256, 0, st>>>(F(ws.part), stat, ho * wo, e.cout, 1e-5f, per_img);
+      return check_launch("instnorm_finalize_tiles_kernel");
+    }
+    SCF_TRY(tcconv(u, in_s, hin, win, SCF_ACT_NONE, raw, nullptr, nullptr));
+    return in_stats(raw, stat, ho * wo, e.cout);
   };
 
   int cur = 0;                         // block input lives in xf[cur] (fp32) and xs[cur] (split)
-  if (inorm) {
-    SCF_TRY(in_stats(F(ws.raw), F(ws.stat), h * w, 64));
+  if (!inorm) {
+    SCF_TRY(stem_conv(SCF_ACT_RELU, F(ws.xf[0]), S(ws.xs[0]), nullptr));
+  } else {
+    int per_img = 0;
+    scf_conv2d_tc_tiles(N, h, w, &per_img);
+    if (per_img > 0) {
+      SCF_TRY(stem_conv(SCF_ACT_NONE, F(ws.raw), nullptr, F(ws.part)));
+      instnorm_finalize_tiles_kernel<<<dim3(N, 2), 256, 0, st>>>(F(ws.part), F(ws.stat), h * w, 64, 1e-5f, per_img);
+      SCF_TRY(check_launch("instnorm_finalize_tiles_kernel"));
+    } else {
+      SCF_TRY(stem_conv(SCF_ACT_NONE, F(ws.raw), nullptr, nullptr));
+      SCF_TRY(in_stats(F(ws.raw), F(ws.stat), h * w, 64));
+    }
     SCF_TRY(in_apply(F(ws.raw), F(ws.stat), nullptr, nullptr, 1, F(ws.xf[0]), S(ws.xs[0]), npix, h * w, 64));
   }
   // ---- residual stages: units (c1, c2, ds) per block
@@ -297,14 +377,11 @@ int scf_encoder_forward(int norm, const void* packed, const float* images, int N
     const long long opix = (long long)N * ho * wo;
     const int C = e1.cout, nxt = cur ^ 1;
     if (inorm) {
-      SCF_TRY(tcconv(u1, S(ws.xs[cur]), h, w, SCF_ACT_NONE, F(ws.raw), nullptr, nullptr));
-      SCF_TRY(in_stats(F(ws.raw), F(ws.stat), ho * wo, C));
+      SCF_TRY(tcconv_stats(u1, S(ws.xs[cur]), h, w, F(ws.raw), F(ws.stat)));
       SCF_TRY(in_apply(F(ws.raw), F(ws.stat), nullptr, nullptr, 1, nullptr, S(ws.ts), opix, ho * wo, C));
-      SCF_TRY(tcconv(u2, S(ws.ts), ho, wo, SCF_ACT_NONE, F(ws.raw), nullptr, nullptr));
-      SCF_TRY(in_stats(F(ws.raw), F(ws.stat), ho * wo, C));
+      SCF_TRY(tcconv_stats(u2, S(ws.ts), ho, wo, F(ws.raw), F(ws.stat)));
       if (ud >= 0) {
-        SCF_TRY(tcconv(ud, S(ws.xs[cur]), h, w, SCF_ACT_NONE, F(ws.raw2), nullptr, nullptr));
-        SCF_TRY(in_stats(F(ws.raw2), F(ws.stat2), ho * wo, C));
+        SCF_TRY(tcconv_stats(ud, S(ws.xs[cur]), h, w, F(ws.raw2), F(ws.stat2)));
         SCF_TRY(in_apply(F(ws.raw), F(ws.stat), F(ws.raw2), F(ws.stat2), 1, F(ws.xf[nxt]), S(ws.xs[nxt]), opix, ho * wo, C));
       } else {
         SCF_TRY(in_apply(F(ws.raw), F(ws.stat), F(ws.xf[cur]), nullptr, 1, F(ws.xf[nxt]), S(ws.xs[nxt]), opix, ho * wo, C));
