@@ -283,6 +283,11 @@ typedef struct scf_decoder_io {
   float* delta_rotation;   /* [iters,B,rot_dim] */
   float* delta_translation;/* [iters,B,3] */
   float* h_out;            /* optional [B,128,H/8,W/8] NCHW final hidden state (may be NULL) */
+  /* Sub-batch calls: when out_batch_total > 0 the seven outputs are [iters, out_batch_total, ...] tensors shared by several
+   * calls and this call (B samples) writes samples out_batch_offset .. out_batch_offset + B - 1 of every iteration. The
+   * Python module uses it to run two half batches on two streams (the tail of one chain overlaps the other's kernels).
+   * `label` may then point at the FULL batch's labels: only label[0] is read (pose_head.py:201-211 class-selection quirk). */
+  int out_batch_total, out_batch_offset;
 } scf_decoder_io;
 
 int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const scf_decoder_io* io, int B, int H, int W,

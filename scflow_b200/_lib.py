@@ -67,6 +67,7 @@ class DecoderIO(C.Structure):
         ('label', c_void_p), ('init_flow', c_void_p), ('invalid_flow_num', C.c_float),
         ('flow_from_pose', c_void_p), ('flow_from_pred', c_void_p), ('rotation', c_void_p), ('translation', c_void_p),
         ('mask', c_void_p), ('delta_rotation', c_void_p), ('delta_translation', c_void_p), ('h_out', c_void_p),
+        ('out_batch_total', C.c_int), ('out_batch_offset', C.c_int),
     ]
 
 

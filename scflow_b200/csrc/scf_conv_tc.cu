@@ -36,8 +36,13 @@ struct TcParams {
   int m_tiles, num_tiles;        // pixel tiles, pixel tiles x N tiles (tile t: n = t / m_tiles, m = t % m_tiles)
   int cluster;                   // CTAs per cluster (1, 2 or 4): consecutive pixel tiles of one N tile share each weight tile,
                                  // every CTA fetching BN/cluster rows of it and multicasting them to its peers
+  int pair;                      // 1 (with cluster == 2): the two CTAs run ONE cta_group::2 MMA of M = 256 - each keeps its
+                                 // own 128 A rows and only HALF of the weight rows in shared memory (no multicast), which cuts
+                                 // the shared-memory traffic per FLOP (operand reads + TMA fills), the resource a single-CTA
+                                 // tile saturates first
   int BN, cout, num_taps, w_batched, stages;
   int acc_cols, tmem_cols;       // TMEM columns of one accumulator buffer / allocated (two buffers)
+  int dbg_epi;                   // timing experiments only (SCFLOW_TC_DBG_EPI): 1 = skip epilogue loads, 2 = skip stores
   long long* dbg_times;          // optional [grid][8] globaltimer stamps of each CTA's first tile (tools/trace_conv_tc.py)
   // stacked-N mode (BN <= 128): the hi and lo weight planes are adjacent in shared memory, so ONE MMA with N = 2*BN
   // forms A_hi*[W_hi;W_lo] into accumulator columns [0,BN) and [BN,2BN); a second MMA adds A_lo*W_hi into [0,BN).
@@ -121,31 +126,25 @@ __device__ __forceinline__ void stage_store64_stats(uint32_t sbuf, int lane, cha
   }
   __syncwarp();
 }
-// Loads are split in two so that a block can be in flight while the previous one is consumed (the epilogue warps have
-// nothing else to hide global-memory latency with): stage_issue64 starts the 4 coalesced 16 B loads of a
-// [32 rows x 64 B] fp32 block, stage_commit64 transposes them through shared memory into this thread's row.
-__device__ __forceinline__ void stage_issue64(const float* gbase, int row_floats, const int (&rp)[4], int lane, uint4 (&r)[4]) {
+// Epilogue INPUTS (GRU: context term, h, z; ACT: residual) are read straight into the accumulator layout: a thread owns one
+// pixel row, so it loads its own 64 B (16 fp32 columns) with four 16 B loads.  A warp-wide load touches 32 rows, but every
+// 32 B sector is used completely by two consecutive loads of the same thread (merged in the L1 miss queue), and - unlike the
+// staged stores below - no shared-memory bandwidth is taken from the tensor core, which runs the next tile's MMAs out of
+// shared memory while this epilogue executes.  row_issue starts the loads (they stay in flight while the previous block is
+// processed); the registers are consumed as fp32 later.
+__device__ __forceinline__ void row_issue(const float* row_ptr, bool valid, uint4 (&r)[4]) {
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    r[it] = make_uint4(0u, 0u, 0u, 0u);
-    if (rp[it] >= 0) r[it] = __ldg(reinterpret_cast<const uint4*>(gbase + (long long)rp[it] * row_floats) + (lane & 3));
+  for (int j = 0; j < 4; ++j) {
+    r[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (valid) r[j] = __ldg(reinterpret_cast<const uint4*>(row_ptr) + j);
   }
 }
-__device__ __forceinline__ void stage_commit64(uint32_t sbuf, int lane, const uint4 (&r)[4], float (&out)[16]) {
+__device__ __forceinline__ void row_values(const uint4 (&r)[4], float (&out)[16]) {
 #pragma unroll
-  for (int it = 0; it < 4; ++it)
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + (it * 8 + (lane >> 2)) * TC_STAGE_ROW + (lane & 3) * 16),
-                 "r"(r[it].x), "r"(r[it].y), "r"(r[it].z), "r"(r[it].w) : "memory");
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "r"(sbuf + lane * TC_STAGE_ROW + i * 16) : "memory");
-    out[4 * i] = __uint_as_float(v.x); out[4 * i + 1] = __uint_as_float(v.y);
-    out[4 * i + 2] = __uint_as_float(v.z); out[4 * i + 3] = __uint_as_float(v.w);
+  for (int j = 0; j < 4; ++j) {
+    out[4 * j] = __uint_as_float(r[j].x); out[4 * j + 1] = __uint_as_float(r[j].y);
+    out[4 * j + 2] = __uint_as_float(r[j].z); out[4 * j + 3] = __uint_as_float(r[j].w);
   }
-  __syncwarp();
 }
 // 16 fp32 values of this thread's row -> one 64 B fp32 block
 __device__ __forceinline__ void stage_store_f32(uint32_t sbuf, int lane, float* gbase, int stride, const int (&rp)[4], const float* v) {
@@ -216,7 +215,9 @@ __device__ __forceinline__ void store_split16(__nv_bfloat16* hi_dst, long long p
   }
 }
 
-template <int EPI, int ACT, int EW>
+// PAIR is a template parameter because a kernel that contains cta_group::2 instructions can only be launched as a cluster of
+// two (cudaErrorInvalidClusterSize otherwise): the single-CTA variants must not contain them.
+template <int EPI, int ACT, int EW, bool PAIR>
 __global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
@@ -229,7 +230,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t stage0 = smem_base + 1024;
   const uint32_t bias0 = smem_base + 1024 + EW * 32 * TC_STAGE_ROW;
   const uint32_t tiles0 = smem_base + tc_header(EW);
-  const uint32_t b_plane = (uint32_t)p.BN * 128u;
+  const uint32_t b_plane = (uint32_t)(PAIR ? p.BN / 2 : p.BN) * 128u;    // weight rows held by this CTA
   const uint32_t stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -252,15 +253,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     prefetch_tmap(&tmW);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, (uint32_t)p.cluster);   // every CTA of the cluster releases the stage (peers write into it)
+      // multicast mode: every CTA of the cluster releases the stage (peers write into it); pair mode: one multicast commit
+      mbar_init(bar_empty + 8 * s, PAIR ? 1u : (uint32_t)p.cluster);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);     // MMA issuer -> epilogue: accumulator a complete
-      mbar_init(bar_tempty + 8 * a, EW);   // epilogue warps -> MMA issuer: accumulator a drained
+      mbar_init(bar_tempty + 8 * a, PAIR ? 2 * EW : EW);   // epilogue warps (of both CTAs of a pair) -> MMA issuer
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2cta(tmem_slot, (uint32_t)p.tmem_cols); else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
   tc_fence_before();
   if (p.cluster > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers must exist before any multicast reaches them
   tc_fence_after();
@@ -294,11 +298,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
               mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
               const uint32_t full = bar_full + 8 * stage;
-              mbar_arrive_expect_tx(full, stage_bytes);
               const uint32_t a_dst = tiles0 + stage * stage_bytes;
-              tma_load_5d(a_dst, tm, full, cc * TC_BK, cx, cy, b, 0);
               const uint32_t w_dst = a_dst + 2 * TC_A_PLANE;
               const int wk = p.seg_wcoff[s] + cc * TC_BK, wt = p.w_batched ? b : tap;
+              if (PAIR) {
+                // both CTAs' loads complete on the LEADER's barrier (it issues the pair's MMAs); each brings its A tile and
+                // its half of the weight rows
+                const uint32_t lfull = mapa_shared(full, 0);
+                if (crank == 0) mbar_arrive_expect_tx(full, 2 * stage_bytes);
+                tma_load_5d_2cta(a_dst, tm, lfull, cc * TC_BK, cx, cy, b, 0);
+                tma_load_4d_2cta(w_dst, &tmW, lfull, wk, n0 + crank * w_rows, wt, 0);
+                tma_load_4d_2cta(w_dst + b_plane, &tmW, lfull, wk, n0 + crank * w_rows, wt, 1);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                continue;
+              }
+              mbar_arrive_expect_tx(full, stage_bytes);
+              tma_load_5d(a_dst, tm, full, cc * TC_BK, cx, cy, b, 0);
               if (p.cluster == 1) {
                 tma_load_4d(w_dst, &tmW, full, wk, n0, wt, 0);
                 tma_load_4d(w_dst + b_plane, &tmW, full, wk, n0, wt, 1);
@@ -314,9 +329,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer
-      const uint32_t idesc = make_idesc_bf16(TC_BM, p.BN), idesc2 = make_idesc_bf16(TC_BM, 2 * p.BN);
+    if (lane == 0 && !(PAIR && crank != 0)) {
+      // ================= MMA issuer (pair mode: the leader CTA issues for both)
+      const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, p.BN), idesc2 = make_idesc_bf16(TC_BM, 2 * p.BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -337,7 +352,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const uint64_t a_hi = make_smem_desc_sw128(a_addr, 1024), a_lo = make_smem_desc_sw128(a_addr + TC_A_PLANE, 1024);
               const uint64_t b_hi = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE, 1024);
               const uint64_t b_lo = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + b_plane, 1024);
-              if (p.stackn) {
+              if (PAIR) {
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                  if (k < ks) {
+                    const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                    umma_bf16_2cta(d_tmem, a_hi + ko, b_hi + ko, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16_2cta(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                    umma_bf16_2cta(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
+                  }
+                }
+              } else if (p.stackn) {
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k) {
                   if (k < ks) {
@@ -357,13 +382,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                   }
                 }
               }
-              if (p.cluster == 1) umma_commit(bar_empty + 8 * stage);     // frees the smem slot once these MMAs have read it
+              if (PAIR) umma_commit_2cta(bar_empty + 8 * stage);        // frees the slot in both CTAs of the pair
+              else if (p.cluster == 1) umma_commit(bar_empty + 8 * stage);     // frees the smem slot once these MMAs have read it
               else umma_commit_mc(bar_empty + 8 * stage, cmask);          // ... in every CTA of the cluster
               if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
           }
         }
-        umma_commit(bar_tfull + 8 * acc);         // accumulator complete
+        if (PAIR) umma_commit_2cta(bar_tfull + 8 * acc); else umma_commit(bar_tfull + 8 * acc);   // accumulator complete
         if (it == 0) stamp(3);
       }
     }
@@ -406,15 +432,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int nslab = (p.cout - n0 < p.BN ? p.cout - n0 : p.BN) / 32;    // full slabs only; the tail uses the plain path
         uint4 XA[4], XB[4], XC[4], YA[4], YB[4], YC[4];
         auto issue = [&](int nb16, uint4 (&A)[4], uint4 (&B)[4], uint4 (&C)[4]) {
+          if (p.dbg_epi & 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) A[j] = B[j] = C[j] = make_uint4(0u, 0u, 0u, 0u);
+            return;
+          }
           if (EPI == SCF_EPI_ACT) {
-            if (p.aux0) stage_issue64(p.aux0 + nb16, p.aux0_stride, rp, lane, B);
+            if (p.aux0) row_issue(p.aux0 + pix * p.aux0_stride + nb16, valid, B);
           } else {
-            if (p.pre) stage_issue64(p.pre + nb16, p.pre_stride, rp, lane, A);
+            if (p.pre) row_issue(p.pre + pix * p.pre_stride + nb16, valid, A);
             if (EPI == SCF_EPI_GRU_ZR) {
-              if (nb16 >= half) stage_issue64(p.aux0 + (nb16 - half), p.aux0_stride, rp, lane, B);
+              if (nb16 >= half) row_issue(p.aux0 + pix * p.aux0_stride + (nb16 - half), valid, B);
             } else {
-              stage_issue64(p.aux0 + nb16, p.aux0_stride, rp, lane, B);
-              stage_issue64(p.aux1 + nb16, p.aux1_stride, rp, lane, C);
+              row_issue(p.aux0 + pix * p.aux0_stride + nb16, valid, B);
+              row_issue(p.aux1 + pix * p.aux1_stride + nb16, valid, C);
             }
           }
         };
@@ -423,7 +454,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           float t0[16];
           if (EPI == SCF_EPI_ACT) {
             if (p.aux0) {                      // residual connection (encoder BasicBlock): added before the activation
-              stage_commit64(sbuf, lane, B, t0);
+              row_values(B, t0);
 #pragma unroll
               for (int i = 0; i < 16; ++i) v16[i] += t0[i];
             }
@@ -431,7 +462,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int i = 0; i < 16; ++i) v16[i] = act_ct<ACT>(v16[i]);
           } else {
             if (p.pre) {                       // loop-invariant context contribution (bias folded in), computed once per forward
-              stage_commit64(sbuf, lane, A, t0);
+              row_values(A, t0);
 #pragma unroll
               for (int i = 0; i < 16; ++i) v16[i] += t0[i];
             }
@@ -439,14 +470,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 16; ++i) v16[i] = sigmoid_fast(v16[i]);
               if (nb16 >= half) {              // r gate: r * h feeds the q convolution
-                stage_commit64(sbuf, lane, B, t0);
+                row_values(B, t0);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v16[i] *= t0[i];
               }
             } else {                           // h' = (1 - z) h + z tanh(.)
               float t1[16];
-              stage_commit64(sbuf, lane, B, t0);
-              stage_commit64(sbuf, lane, C, t1);
+              row_values(B, t0);
+              row_values(C, t1);
 #pragma unroll
               for (int i = 0; i < 16; ++i) v16[i] = (1.f - t1[i]) * t0[i] + t1[i] * tanh_fast(v16[i]);
             }
@@ -481,7 +512,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (sl + NPAR < nslab) issue(nb + NPAR * 32, XA, XB, XC);
           consume(nb + 16, v + 16, YA, YB, YC);
           // ---- stores of the finished 32-column slab
-          if (EPI == SCF_EPI_GRU_ZR) {
+          if (p.dbg_epi & 2) {
+            float acc_ = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc_ += v[i];
+            if (acc_ == 123.456f) p.out_f32[0] = acc_;
+          } else if (EPI == SCF_EPI_GRU_ZR) {
             if (nb < half) {                   // z gate -> fp32 (read back by the q convolution's epilogue)
               stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, rp, v);
               stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, rp, v + 16);
@@ -598,13 +634,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // this warp has read everything it needs from accumulator `acc`: hand it back to the MMA issuer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (lane == 0) {
+        if (PAIR && crank != 0) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0));   // the leader's issuer waits for both
+        else mbar_arrive(bar_tempty + 8 * acc);
+      }
       if (it == 0 && threadIdx.x == 64) stamp(5);
     }
   }
   tc_fence_before();
   if (p.cluster > 1) cluster_sync_all(); else __syncthreads();   // no CTA may exit while peers can still signal or write into it
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
   if (threadIdx.x == 32) stamp(6);
 }
 
@@ -836,7 +877,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     SCF_CUDA(cudaGetDevice(&dev));
     SCF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int stage_bytes = 2 * (int)TC_A_PLANE + 2 * p.BN * 128;
+  int stage_bytes = 2 * (int)TC_A_PLANE + 2 * p.BN * 128;
   // epilogue warps: 8 (two per TMEM lane quarter) for the one-CTA-per-SM configuration - the epilogue's global loads
   // (GRU gates, residuals) need the extra memory-level parallelism - and 4 for the small-tile two-CTAs-per-SM mode
   int ew = 8;
@@ -855,13 +896,12 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.acc_cols) p.tmem_cols <<= 1;
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
-  static const KernelFn table[2][6] = {
-      {conv_tc_kernel<SCF_EPI_GRU_ZR, SCF_ACT_SIGMOID, 4>, conv_tc_kernel<SCF_EPI_GRU_Q, SCF_ACT_TANH, 4>,
-       conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_NONE, 4>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_RELU, 4>,
-       conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_SIGMOID, 4>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_TANH, 4>},
-      {conv_tc_kernel<SCF_EPI_GRU_ZR, SCF_ACT_SIGMOID, 8>, conv_tc_kernel<SCF_EPI_GRU_Q, SCF_ACT_TANH, 8>,
-       conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_NONE, 8>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_RELU, 8>,
-       conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_SIGMOID, 8>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_TANH, 8>}};
+#define SCF_TC_ROW(EW_, PAIR_)                                                                                        \
+  {conv_tc_kernel<SCF_EPI_GRU_ZR, SCF_ACT_SIGMOID, EW_, PAIR_>, conv_tc_kernel<SCF_EPI_GRU_Q, SCF_ACT_TANH, EW_, PAIR_>,  \
+   conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_NONE, EW_, PAIR_>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_RELU, EW_, PAIR_>,         \
+   conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_SIGMOID, EW_, PAIR_>, conv_tc_kernel<SCF_EPI_ACT, SCF_ACT_TANH, EW_, PAIR_>}
+  static const KernelFn table[3][6] = {SCF_TC_ROW(4, false), SCF_TC_ROW(8, false), SCF_TC_ROW(8, true)};   // [variant][epilogue]
+#undef SCF_TC_ROW
   int ki = -1;
   if (d.epi == SCF_EPI_GRU_ZR) ki = 0;
   else if (d.epi == SCF_EPI_GRU_Q) ki = 1;
@@ -870,7 +910,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 3; ++a)
       for (int i = 0; i < 6; ++i) {
         cudaError_t e = cudaFuncSetAttribute(table[a][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) attr_err = e;
@@ -889,8 +929,30 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
       ctas_per_sm = 2;
     }
   }
+  // ---- CTA pair: two CTAs (one TPC) run one cta_group::2 MMA of M = 256; each stages its own A tile and half of the weight
+  // rows, so the shared-memory traffic per FLOP (operand reads by the tensor core + TMA fills) drops by a third for
+  // BN = 256.  Used for every large-tile layer with an even number of pixel tiles.
+  p.pair = 0;
+  if (ctas_per_sm == 1) {
+    const char* pe = getenv("SCFLOW_TC_PAIR");
+    const bool want_pair = pe ? atoi(pe) != 0 : true;
+    const char* pm = getenv("SCFLOW_TC_PAIR_MIN_BN");
+    const int pair_min_bn = pm ? atoi(pm) : 192;      // BN <= 128 keeps the single-CTA stacked-N form (measured faster there)
+    if (want_pair && p.m_tiles % 2 == 0 && p.BN % 16 == 0 && p.BN >= pair_min_bn && p.num_tiles >= 4 &&
+        (!d.w_batched || (p.tiles_x * p.tiles_y) % 2 == 0)) {
+      p.pair = 1;
+      ew = 8;
+      stage_bytes = 2 * (int)TC_A_PLANE + p.BN * 128;           // A (hi, lo) + BN/2 weight rows (hi, lo)
+      p.stages = (232448 - 1024 - tc_header(ew)) / stage_bytes;
+      if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+      p.stackn = 0;                                              // three MMAs of N = BN (the stacked-N trick splits B unevenly)
+      p.acc_cols = p.BN;
+      p.tmem_cols = 32;
+      while (p.tmem_cols < 2 * p.acc_cols) p.tmem_cols <<= 1;
+    }
+  }
   const int smem = 1024 + tc_header(ew) + p.stages * stage_bytes;
-  KernelFn kernel = table[ew == 8 ? 1 : 0][ki];
+  KernelFn kernel = table[p.pair ? 2 : (ew == 8 ? 1 : 0)][ki];
   // ---- cluster size: CTAs of consecutive pixel tiles (same N tile, same sample when the weights are batched) share each
   // weight tile through TMA multicast, which divides the weight share of the L2 -> shared-memory operand traffic - the
   // resource this kernel saturates first (ncu: 8-9 TB/s) - by the cluster size
@@ -898,15 +960,15 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   int max_clusters = 0;
   if (ctas_per_sm == 1) {
     const char* ce = getenv("SCFLOW_TC_CLUSTER");
-    const int want = ce ? atoi(ce) : 1;   // measured on B200 (tools/trace_gru.py, bench_conv_tc.py): no gain from 2 or 4 - the main
+    const int want = p.pair ? 2 : (ce ? atoi(ce) : 1);   // measured on B200 (tools/trace_gru.py, bench_conv_tc.py): no gain from 2 or 4 - the main
                                           // loop is MMA-bound at the power-capped clock, not operand-delivery-bound - so off by default
     for (int cs = want >= 4 ? 4 : (want >= 2 ? 2 : 1); cs > 1; cs >>= 1) {
       if (p.m_tiles % cs != 0 || (p.BN / cs) % 8 != 0 || p.num_tiles < 2 * cs) continue;
       if (d.w_batched && (p.tiles_x * p.tiles_y) % cs != 0) continue;
       static std::mutex mu;
-      static int cache[2][6][5][8];      // [ew][kernel][cluster][stages] -> max co-resident clusters (+1; 0 = not queried)
+      static int cache[3][6][5][8];      // [variant][kernel][cluster][stages] -> max co-resident clusters (+1; 0 = not queried)
       std::lock_guard<std::mutex> lock(mu);
-      int& slot = cache[ew == 8 ? 1 : 0][ki][cs][p.stages];
+      int& slot = cache[p.pair ? 2 : (ew == 8 ? 1 : 0)][ki][cs][p.stages];
       if (slot == 0) {
         cudaLaunchConfig_t qc = {};
         qc.gridDim = dim3(num_sms / cs * cs); qc.blockDim = dim3(64 + 32 * ew); qc.dynamicSmemBytes = smem;
@@ -920,6 +982,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
       }
       if (slot - 1 >= 1) { p.cluster = cs; max_clusters = slot - 1; break; }
     }
+    SCF_REQUIRE(!p.pair || p.cluster == 2, SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: CTA pairs cannot be scheduled on this device");
   }
   p.bias = d.bias; p.scale = d.scale; p.epi = d.epi; p.act = d.act;
   p.out_f32 = d.out_f32; p.out_f32_stride = d.out_f32_stride; p.out_f32_coff = d.out_f32_coff;
@@ -934,6 +997,8 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   {
     const char* dt = getenv("SCFLOW_TC_DBG_TIMES");       // address of a device buffer, hex (timing experiments only)
     p.dbg_times = dt ? reinterpret_cast<long long*>(strtoull(dt, nullptr, 16)) : nullptr;
+    const char* de = getenv("SCFLOW_TC_DBG_EPI");
+    p.dbg_epi = de ? atoi(de) : 0;
   }
   CUtensorMap tmA[3], tmW;
   int wcoff = 0;

@@ -445,17 +445,21 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       SCF_TRY(convtc(pass == 0 ? PC_CQ0 : PC_CQ1, {{S(ws.s_cxt), 128, 0, 128}}, SCF_ACT_NONE, F(ws.pre_q[pass]), 128, nullptr, 0, 0));
     }
   }
+  const size_t Btot = io->out_batch_total > 0 ? (size_t)io->out_batch_total : (size_t)B;
+  const size_t boff = io->out_batch_total > 0 ? (size_t)io->out_batch_offset : 0;
+  SCF_REQUIRE(io->out_batch_offset >= 0 && boff + B <= Btot, SCF_ERR_ARG, "scf_decoder_forward: output batch window out of range");
   const float* flow_full = io->init_flow;
   for (int it = 0; it < iters; ++it) {
-    float* flow_pose_k = io->flow_from_pose + (size_t)it * B * 2 * HW;
-    float* flow_pred_k = io->flow_from_pred + (size_t)it * B * 2 * HW;
-    float* mask_k = io->mask + (size_t)it * B * HW;
-    float* rot_k = io->rotation + (size_t)it * B * 9;
-    float* trs_k = io->translation + (size_t)it * B * 3;
-    float* drot_k = io->delta_rotation + (size_t)it * B * cfg->rot_dim;
-    float* dtrs_k = io->delta_translation + (size_t)it * B * 3;
-    const float* rot_prev = it == 0 ? io->ref_rotation : io->rotation + (size_t)(it - 1) * B * 9;
-    const float* trs_prev = it == 0 ? io->ref_translation : io->translation + (size_t)(it - 1) * B * 3;
+    const size_t ob = (size_t)it * Btot + boff;          // first output sample of this call in iteration `it`
+    float* flow_pose_k = io->flow_from_pose + ob * 2 * HW;
+    float* flow_pred_k = io->flow_from_pred + ob * 2 * HW;
+    float* mask_k = io->mask + ob * HW;
+    float* rot_k = io->rotation + ob * 9;
+    float* trs_k = io->translation + ob * 3;
+    float* drot_k = io->delta_rotation + ob * cfg->rot_dim;
+    float* dtrs_k = io->delta_translation + ob * 3;
+    const float* rot_prev = it == 0 ? io->ref_rotation : io->rotation + (ob - Btot) * 9;
+    const float* trs_prev = it == 0 ? io->ref_translation : io->translation + (ob - Btot) * 3;
 
     // flow8 = 1/8 * down8(flow)                                          (scflow_decoder.py:196-197)
     SCF_TRY(scf_resize_bilinear(flow_full, nullptr, 2 * HW, HW, W, 1, H, W, F(ws.flow8), (long long)P * 2, 1,

@@ -49,9 +49,12 @@ def run(name, cout, epi, act):
     t = times.cpu().double()
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
+    span = float((t[:, 6].max() - t0) / 1e3)
+    ncta = t.shape[0]
+    t = t[t[:, 2] > 0]          # CTA-pair mode: only the leader CTA issues MMAs and stamps the main loop
     rel = (t - t0) / 1e3
     tf = 2.0 * b * 1024 * cout * 1280 / (us * 1e-6) / 1e12
-    print(f'== {name}: {us:.1f} us by CUDA events ({tf:.0f} TFLOP/s algorithmic); span by stamps {float((t[:, 6].max() - t0) / 1e3):.1f} us; {t.shape[0]} CTAs')
+    print(f'== {name}: {us:.1f} us by CUDA events ({tf:.0f} TFLOP/s algorithmic); span by stamps {span:.1f} us; {ncta} CTAs ({t.shape[0]} issuing)')
     print(f'   first tile of each CTA: prologue {float((rel[:,1]-rel[:,0]).mean()):.2f}  wait-first-data {float((rel[:,2]-rel[:,1]).mean()):.2f}  '
           f'mainloop {float((rel[:,4]-rel[:,2]).mean()):.2f}  epilogue {float((rel[:,5]-rel[:,4]).mean()):.2f} (max {float((rel[:,5]-rel[:,4]).max()):.2f})  '
           f'CTA lifetime mean {float((rel[:,6]-rel[:,0]).mean()):.2f} max {float((rel[:,6]-rel[:,0]).max()):.2f}')
