@@ -295,6 +295,37 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
 /* number of kernel launches one scf_decoder_forward call issues (for bench.py's gpu_launches) */
 int scf_decoder_launch_count(const scf_decoder_cfg* cfg, int iters);
 
+/* ---------------------------------------------------------------- training loss (forward) ---------------- */
+/* models/utils/flow.py:6-26 filter_flow_by_mask, in place: flow [B,2,H,W] is set to `invalid` where it already is
+ * (both components >= invalid) or where the bilinear sample (zeros padding, align_corners=False) of gt_mask [B,H,W] at
+ * the flow target is < 0.9. */
+int scf_filter_flow_by_mask(float* flow, const float* gt_mask, float invalid, int B, int H, int W, void* stream);
+
+/* SCFlowRefiner.loss after get_pose (models/refiner/scflow_refiner.py:204-258) with the shipped loss configuration
+ * (configs/refine_models/scflow.py:75-104): SequenceLoss(gamma) over RAFTLoss (flow), L1Loss (mask) and
+ * DisentanglePointMatchingLoss (loss_type 'l1', disentangle_z=True, no scale factors). Forward only. */
+typedef struct scf_loss_desc {
+  const float* flow_pred;      /* [iters,B,2,H,W] sequence_flow_from_pred                                  */
+  const float* mask_pred;      /* [iters,B,1,H,W] sequence_masks                                           */
+  const float* rotation;       /* [iters,B,3,3]                                                            */
+  const float* translation;    /* [iters,B,3]                                                              */
+  const float* gt_flow;        /* [B,2,H,W] ground-truth flow, invalid pixels hold max_flow (already filtered) */
+  const float* valid;          /* [B,H,W] rendered mask                                                    */
+  const float* gt_rotation; const float* gt_translation;   /* [B,3,3], [B,3]                              */
+  const int64_t* label;        /* [B]                                                                      */
+  const float* points;         /* [num_class, max_points, 3] model points, zero padded                     */
+  const int* num_points;       /* [num_class]                                                              */
+  const unsigned char* symmetric; /* [num_class] 1 = nearest-neighbour matching (symmetry_types)           */
+  const float* diameter;       /* [num_class] mesh_diameter                                                */
+  int iters, B, H, W, num_class, max_points;
+  float max_flow, gamma, w_flow, w_pose, w_mask, eps;     /* 400, 0.8, 0.1, 10, 10, 1e-10 in the shipped config */
+  void* scratch; size_t scratch_bytes;                    /* >= scf_refiner_loss_scratch_bytes(iters, B), 256B aligned */
+  float* out;                  /* [4 + 3*iters]: loss, loss_pose, loss_flow, loss_mask, then the per-iteration (weighted)
+                                * pose, flow and mask losses - the reference's seq_*_loss_list */
+} scf_loss_desc;
+size_t scf_refiner_loss_scratch_bytes(int iters, int B);
+int scf_refiner_loss(const scf_loss_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

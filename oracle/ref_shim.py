@@ -158,6 +158,16 @@ def _dummy(name):
 _INSTALLED = False
 
 
+def _knn_points(p1, p2, K=1, **kwargs):
+    """Stand-in for pytorch3d.ops.knn_points (pytorch3d is not installed; the reference depends on the fork
+    YangHai-1218/pytorch3d, README.md:29, unpinned): brute-force K=1 nearest neighbour under the squared L2 distance,
+    which is the published semantics of knn_points(norm=2). Returns an object with .dists [N,P1,K] and .idx [N,P1,K]."""
+    assert K == 1
+    d = ((p1[:, :, None, :] - p2[:, None, :, :]) ** 2).sum(-1)
+    dists, idx = d.min(dim=2)
+    return types.SimpleNamespace(dists=dists[..., None], idx=idx[..., None], knn=None)
+
+
 def install():
     """Register stand-in third-party modules and namespace packages for the reference."""
     global _INSTALLED
@@ -182,7 +192,7 @@ def install():
     _mod('kornia.geometry.conversions')
     _mod('kornia.augmentation', AugmentationSequential=_dummy('AugmentationSequential'))
     _mod('pytorch3d')
-    _mod('pytorch3d.ops', knn_points=None)
+    _mod('pytorch3d.ops', knn_points=_knn_points)
     _mod('pytorch3d.structures', join_meshes_as_batch=None)
     names = ['PointLights', 'PerspectiveCameras', 'BlendParams', 'MeshRasterizer', 'RasterizationSettings',
              'HardPhongShader', 'SoftPhongShader', 'HardGouraudShader', 'SoftGouraudShader',
@@ -214,7 +224,11 @@ def load_reference():
     from models.utils import pose as pose_mod
     from models.head.pose_head import MultiClassPoseHead, SingleClassPoseHead
     from models.encoder.raft_encoder import RAFTEncoder
+    from models.utils import flow as flow_mod
+    from models.loss import sequence_loss as seq_loss_mod
+    from models.loss import point_matching_loss as pm_loss_mod
     return types.SimpleNamespace(
+        flow=flow_mod, sequence_loss=seq_loss_mod, point_matching_loss=pm_loss_mod,
         SCFlowDecoder=SCFlowDecoder, CorrelationPyramid=CorrelationPyramid, MotionEncoder=MotionEncoder,
         ConvGRU=ConvGRU, XHead=XHead, CorrLookup=CorrLookup, pose=pose_mod,
         MultiClassPoseHead=MultiClassPoseHead, SingleClassPoseHead=SingleClassPoseHead,

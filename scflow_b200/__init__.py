@@ -9,6 +9,7 @@ from .pose_head import MultiClassPoseHead, SingleClassPoseHead
 from .decoder import SCFlowDecoder, CorrelationPyramid, MotionEncoder, ConvGRU, XHead
 from .encoder import RAFTEncoder
 from .refiner import SCFlowRefiner
+from .loss import SequenceLoss, RAFTLoss, L1Loss, DisentanglePointMatchingLoss, filter_flow_by_mask, refiner_loss
 from .pose import (get_pose_from_delta_pose, cal_3d_2d_corr, get_flow_from_delta_pose_and_points, unproject_dense,
                    get_flow_from_delta_pose_dense)
 from . import ops
@@ -21,4 +22,5 @@ __all__ = ['Registry', 'build_from_cfg', 'Config', 'ConfigDict', 'REFINERS', 'DE
            'ConvModule', 'BaseModule', 'CorrLookup', 'coords_grid', 'MultiClassPoseHead', 'SingleClassPoseHead',
            'SCFlowDecoder', 'CorrelationPyramid', 'MotionEncoder', 'ConvGRU', 'XHead', 'RAFTEncoder', 'SCFlowRefiner',
            'get_pose_from_delta_pose', 'cal_3d_2d_corr', 'get_flow_from_delta_pose_and_points', 'unproject_dense',
-           'get_flow_from_delta_pose_dense', 'ops', 'ScfError']
+           'get_flow_from_delta_pose_dense', 'ops', 'ScfError', 'SequenceLoss', 'RAFTLoss', 'L1Loss',
+           'DisentanglePointMatchingLoss', 'filter_flow_by_mask', 'refiner_loss']

@@ -71,6 +71,17 @@ class DecoderIO(C.Structure):
     ]
 
 
+class LossDesc(C.Structure):
+    _fields_ = [
+        ('flow_pred', c_void_p), ('mask_pred', c_void_p), ('rotation', c_void_p), ('translation', c_void_p),
+        ('gt_flow', c_void_p), ('valid', c_void_p), ('gt_rotation', c_void_p), ('gt_translation', c_void_p),
+        ('label', c_void_p), ('points', c_void_p), ('num_points', c_void_p), ('symmetric', c_void_p), ('diameter', c_void_p),
+        ('iters', C.c_int), ('B', C.c_int), ('H', C.c_int), ('W', C.c_int), ('num_class', C.c_int), ('max_points', C.c_int),
+        ('max_flow', C.c_float), ('gamma', C.c_float), ('w_flow', C.c_float), ('w_pose', C.c_float), ('w_mask', C.c_float),
+        ('eps', C.c_float), ('scratch', c_void_p), ('scratch_bytes', C.c_size_t), ('out', c_void_p),
+    ]
+
+
 ACT = {'none': 0, None: 0, 'relu': 1, 'sigmoid': 2, 'tanh': 3}
 EPI_ACT, EPI_GRU_ZR, EPI_GRU_Q = 0, 1, 2
 
@@ -150,6 +161,9 @@ _SIGNATURES = {
     'scf_resize_bilinear': (C.c_int, [c_void_p, c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
                                       C.c_int, c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_float, c_void_p]),
+    'scf_filter_flow_by_mask': (C.c_int, [c_void_p, c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, c_void_p]),
+    'scf_refiner_loss_scratch_bytes': (C.c_size_t, [C.c_int, C.c_int]),
+    'scf_refiner_loss': (C.c_int, [C.POINTER(LossDesc), c_void_p]),
     'scf_encoder_packed_bytes': (C.c_size_t, []),
     'scf_encoder_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'scf_encoder_pack': (C.c_int, [C.c_int, C.POINTER(c_void_p), c_void_p, c_void_p]),

@@ -10,7 +10,7 @@ from typing import Callable, Dict, Optional, Tuple, Union
 import torch
 import torch.nn as nn
 
-from .builder import REFINERS, build_decoder, build_encoder
+from .builder import REFINERS, build_decoder, build_encoder, build_loss
 from .cnn import BaseModule
 
 
@@ -43,6 +43,8 @@ class SCFlowRefiner(BaseModule):
         self.train_cfg = train_cfg or {}
         self.test_cfg = test_cfg or {}
         self.loss_cfgs = dict(pose=pose_loss_cfg, flow=flow_loss_cfg, mask=mask_loss_cfg)
+        # built lazily (the point-matching loss reads the model point clouds from mesh_path)
+        self._loss_funcs = None
         self.filter_invalid_flow = filter_invalid_flow
         self.test_by_flow = self.test_cfg.get('by_flow', False)
         self.test_iter_num = self.test_cfg.get('iters') if 'iters' in self.test_cfg else self.decoder.iters
@@ -117,7 +119,47 @@ class SCFlowRefiner(BaseModule):
         raise NotImplementedError('dataset-format batches (mmcv DataContainer collation) are outside the replaced hot path')
 
     def train_step(self, data_batch, optimizer, **kwargs):
-        raise NotImplementedError('training (loss + backward) is not implemented in this round; see DESIGN.md "what comes next"')
+        raise NotImplementedError('training needs the backward pass of the refinement loop, which is not built yet (the forward '
+                                  'value of the loss is available as SCFlowRefiner.loss under torch.no_grad()); see DESIGN.md')
 
-    def loss(self, data_batch):
-        raise NotImplementedError('training (loss + backward) is not implemented in this round; see DESIGN.md "what comes next"')
+    def loss_functions(self):
+        """(pose, flow, mask) SequenceLoss modules built from the reference's config keys (scflow_refiner.py:61-63)."""
+        if self._loss_funcs is None:
+            if any(v is None for v in self.loss_cfgs.values()):
+                raise RuntimeError('SCFlowRefiner: pose_loss_cfg / flow_loss_cfg / mask_loss_cfg were not given')
+            from . import loss as _loss  # noqa: F401  (registers the loss classes)
+            self._loss_funcs = tuple(build_loss(self.loss_cfgs[k]) for k in ('pose', 'flow', 'mask'))
+        return self._loss_funcs
+
+    def loss(self, data: Dict):
+        """Forward value of the training loss (scflow_refiner.py:184-258) for a pre-formatted batch: keys ``gt_rotations,
+        gt_translations, ref_rotations, ref_translations, real_images, rendered_images, rendered_depths, rendered_masks,
+        gt_masks, internel_k, labels`` (what ``format_data_train_sup`` produces; the renderer is not part of this package).
+        Returns ``(loss, log_vars, seq_rotations, seq_translations)``.  FORWARD ONLY: the value carries no autograd graph
+        (the backward pass of the loop is not built yet), so it must be called under ``torch.no_grad()``."""
+        if torch.is_grad_enabled():
+            raise NotImplementedError('SCFlowRefiner.loss computes the forward value only (no backward yet): call it under torch.no_grad()')
+        from . import loss as L
+        from . import ops
+        pose_f, flow_f, mask_f = self.loss_functions()
+        outs = self.get_pose(data['rendered_images'], data['real_images'], data['ref_rotations'], data['ref_translations'],
+                             data['rendered_depths'], data['internel_k'], data['labels'])
+        flow_from_pose, flow_from_pred, seq_rot, seq_trs, seq_masks = outs[0], outs[1], outs[2], outs[3], outs[4]
+        depth = data['rendered_depths'].float().contiguous()
+        k = data['internel_k'].float().contiguous()
+        # GT flow (models/utils/pose.py:92-121): lift with the reference pose, project with the ground-truth pose
+        pts4 = ops.unproject(depth, k, data['ref_rotations'].float().contiguous(), data['ref_translations'].float().contiguous())
+        gt_flow = ops.reproject(pts4, k, data['gt_rotations'].float().contiguous(), data['gt_translations'].float().contiguous(),
+                                float(self.max_flow))
+        if self.filter_invalid_flow:
+            gt_flow = L.filter_flow_by_mask(gt_flow, data['gt_masks'].float().contiguous(), float(self.max_flow))
+        out, iters = L.refiner_loss(flow_from_pred, seq_masks, seq_rot, seq_trs, gt_flow, data['rendered_masks'], data['gt_rotations'],
+                                    data['gt_translations'], data['labels'], pose_f, flow_f, mask_f)
+        vals = out.tolist()            # one device->host read for the whole log (the reference does 3*iters + 4 .item() calls)
+        log_vars = {}
+        for i in range(iters):
+            log_vars[f'seq_{i}_pose_loss'] = vals[4 + i]
+            log_vars[f'seq_{i}_flow_loss'] = vals[4 + iters + i]
+            log_vars[f'seq_{i}_mask_loss'] = vals[4 + 2 * iters + i]
+        log_vars.update(loss_mask=vals[3], loss_flow=vals[2], loss_pose=vals[1], loss=vals[0])
+        return out[0], log_vars, seq_rot, seq_trs
