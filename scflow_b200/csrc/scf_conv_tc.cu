@@ -133,10 +133,17 @@ __device__ __forceinline__ void stage_store64_stats(uint32_t sbuf, int lane, cha
 // shared memory while this epilogue executes.  row_issue starts the loads (they stay in flight while the previous block is
 // processed); the registers are consumed as fp32 later.
 __device__ __forceinline__ void row_issue(const float* row_ptr, bool valid, uint4 (&r)[4]) {
+  // two 256-bit loads (sm_100): every 32 B sector is requested exactly once.  volatile asm: ptxas otherwise sinks the loads
+  // down to their first use (to save registers), which turns the software prefetch into a load-and-wait per block
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    r[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (valid) r[j] = __ldg(reinterpret_cast<const uint4*>(row_ptr) + j);
+  for (int j = 0; j < 2; ++j) {
+    r[2 * j] = make_uint4(0u, 0u, 0u, 0u);
+    r[2 * j + 1] = make_uint4(0u, 0u, 0u, 0u);
+    if (valid)
+      asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(r[2 * j].x), "=r"(r[2 * j].y), "=r"(r[2 * j].z), "=r"(r[2 * j].w), "=r"(r[2 * j + 1].x), "=r"(r[2 * j + 1].y),
+                     "=r"(r[2 * j + 1].z), "=r"(r[2 * j + 1].w)
+                   : "l"(reinterpret_cast<const char*>(row_ptr) + 32 * j));
   }
 }
 __device__ __forceinline__ void row_values(const uint4 (&r)[4], float (&out)[16]) {
