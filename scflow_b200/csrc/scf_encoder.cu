@@ -152,43 +152,55 @@ __global__ void __launch_bounds__(256) instnorm_finalize_tiles_kernel(const floa
     stat[((long long)n * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
   }
 }
-// stage 3: y = [relu]( (x - mean) * rstd  [+ (r - rmean) * rrstd | + r] ) -> fp32 and/or split-bf16
+// stage 3: y = [relu]( (x - mean) * rstd  [+ (r - rmean) * rrstd | + r] ) -> fp32 and/or split-bf16.  HBM-streaming: a thread
+// owns 8 consecutive channels (two 16 B loads per input, one 16 B store per bf16 plane), two pixels in flight per iteration.
 __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ stat,
                                                              const float* __restrict__ res, const float* __restrict__ res_stat,
                                                              int relu, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hl,
-                                                             long long plane, int HW, int C, long long total4) {
-  const int c4n = C >> 2;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
-    const int cq = (int)(idx % c4n);
-    const long long pix = idx / c4n;
+                                                             long long plane, int HW, int C, long long total8) {
+  const int c8n = C >> 3;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total8; idx += (long long)gridDim.x * blockDim.x) {
+    const int cq = (int)(idx % c8n);
+    const long long pix = idx / c8n;
     const long long n = pix / HW;
-    float4 v = __ldg(reinterpret_cast<const float4*>(x) + idx);
-    float vv[4] = {v.x, v.y, v.z, v.w};
-    const float* st = stat + (n * C + cq * 4) * 2;
+    const float4 v0 = __ldcs(reinterpret_cast<const float4*>(x) + 2 * idx), v1 = __ldcs(reinterpret_cast<const float4*>(x) + 2 * idx + 1);
+    float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const float4* st = reinterpret_cast<const float4*>(stat + (n * C + cq * 8) * 2);     // (mean, rstd) pairs
 #pragma unroll
-    for (int i = 0; i < 4; ++i) vv[i] = (vv[i] - st[2 * i]) * st[2 * i + 1];
+    for (int i = 0; i < 4; ++i) {
+      const float4 s2 = __ldg(st + i);
+      vv[2 * i] = (vv[2 * i] - s2.x) * s2.y;
+      vv[2 * i + 1] = (vv[2 * i + 1] - s2.z) * s2.w;
+    }
     if (res) {
-      const float4 rv = __ldg(reinterpret_cast<const float4*>(res) + idx);
-      float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+      const float4 r0 = __ldcs(reinterpret_cast<const float4*>(res) + 2 * idx), r1 = __ldcs(reinterpret_cast<const float4*>(res) + 2 * idx + 1);
+      float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
       if (res_stat) {
-        const float* rt = res_stat + (n * C + cq * 4) * 2;
+        const float4* rt = reinterpret_cast<const float4*>(res_stat + (n * C + cq * 8) * 2);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rr[i] = (rr[i] - rt[2 * i]) * rt[2 * i + 1];
+        for (int i = 0; i < 4; ++i) {
+          const float4 s2 = __ldg(rt + i);
+          rr[2 * i] = (rr[2 * i] - s2.x) * s2.y;
+          rr[2 * i + 1] = (rr[2 * i + 1] - s2.z) * s2.w;
+        }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) vv[i] += rr[i];
+      for (int i = 0; i < 8; ++i) vv[i] += rr[i];
     }
     if (relu) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) vv[i] = fmaxf(vv[i], 0.f);
+      for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
     }
-    if (out_f32) reinterpret_cast<float4*>(out_f32)[idx] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    if (out_f32) {
+      reinterpret_cast<float4*>(out_f32)[2 * idx] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      reinterpret_cast<float4*>(out_f32)[2 * idx + 1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+    }
     if (out_hl) {
-      __nv_bfloat16 hi[4], lo[4];
+      __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) tc::split_bf16(vv[i], hi[i], lo[i]);
-      *reinterpret_cast<uint2*>(out_hl + idx * 4) = *reinterpret_cast<const uint2*>(hi);
-      *reinterpret_cast<uint2*>(out_hl + plane + idx * 4) = *reinterpret_cast<const uint2*>(lo);
+      for (int i = 0; i < 8; ++i) tc::split_bf16(vv[i], hi[i], lo[i]);
+      *reinterpret_cast<uint4*>(out_hl + idx * 8) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(out_hl + plane + idx * 8) = *reinterpret_cast<const uint4*>(lo);
     }
   }
 }
@@ -313,9 +325,9 @@ int scf_encoder_forward(int norm, const void* packed, const float* images, int N
   };
   auto in_apply = [&](const float* x, const float* stat, const float* res, const float* res_stat, int relu, float* of32, void* ohl,
                       long long pixels, int hw, int C) -> int {
-    const long long total4 = pixels * C / 4;
-    instnorm_apply_kernel<<<cdiv(total4, 256) < 148 * 32 ? cdiv(total4, 256) : 148 * 32, 256, 0, st>>>(
-        x, stat, res, res_stat, relu, of32, reinterpret_cast<__nv_bfloat16*>(ohl), pixels * C, hw, C, total4);
+    const long long total8 = pixels * C / 8;
+    instnorm_apply_kernel<<<cdiv(total8, 256) < 148 * 16 ? cdiv(total8, 256) : 148 * 16, 256, 0, st>>>(
+        x, stat, res, res_stat, relu, of32, reinterpret_cast<__nv_bfloat16*>(ohl), pixels * C, hw, C, total8);
     return check_launch("instnorm_apply_kernel");
   };
   // tensor-core conv unit u on split input (hin x win), stride from the table
