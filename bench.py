@@ -216,16 +216,44 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = world * b / (ms_step * 1e-3)
 
-    # ---- e2e: pinned host inputs -> H2D -> get_pose -> D2H of the refined poses, all inside the timed region
-    def e2e_step():
-        inp = {k: host[k].to(dev, non_blocking=True) for k in keys}
-        rot, trs = step(inp)
-        lo = rank * b if world > 1 else 0
-        out_host[:, :9].copy_(rot[lo:lo + b].reshape(b, 9), non_blocking=True)
-        out_host[:, 9:].copy_(trs[lo:lo + b], non_blocking=True)
-    for _ in range(2):
-        e2e_step()
-    e2e_ms = D.max_over_ranks(timed(e2e_step, args.steps), dev) / args.steps
+    # ---- e2e: pinned host inputs -> H2D -> get_pose -> D2H of the refined poses, all inside ONE timed region of K steps.
+    # Every step copies its own inputs from pinned host memory and reads its own poses back; like any serving loop the
+    # copy of step i+1 runs on a copy stream while step i computes (two device input buffers), L2 is flushed every step.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    bufs = [{k: torch.empty_like(resident[k]) for k in keys} for _ in range(2)]
+
+    def e2e_run(steps):
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0.record(main_stream)
+        copy_stream.wait_stream(main_stream)
+
+        def upload(i):
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(done[i % 2])          # the step that last used this buffer has finished
+                for k in keys:
+                    bufs[i % 2][k].copy_(host[k], non_blocking=True)
+                ready[i % 2].record(copy_stream)
+        upload(0)
+        for i in range(steps):
+            if i + 1 < steps:
+                upload(i + 1)
+            flush.zero_()
+            main_stream.wait_event(ready[i % 2])
+            rot, trs = step(bufs[i % 2])
+            lo = rank * b if world > 1 else 0
+            out_host[:, :9].copy_(rot[lo:lo + b].reshape(b, 9), non_blocking=True)
+            out_host[:, 9:].copy_(trs[lo:lo + b], non_blocking=True)
+            done[i % 2].record(main_stream)
+        t1.record(main_stream)
+        barrier()
+        return t0.elapsed_time(t1)
+    e2e_run(2)
+    e2e_ms = D.max_over_ranks(e2e_run(args.steps), dev) / args.steps
     h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
     d2h = out_host.numel() * 4
 
@@ -271,6 +299,9 @@ def run_ours(args):
             'config': {'workload': f'YCB-V-like 256x256 crop pairs, batch={b} per GPU, {iters} iters, inference (BASELINE config 2); '
                                    'step = get_pose (3 RAFT encoder passes + corr build + refinement loop), all on scflow_b200 kernels',
                        'l2': 'L2 flushed (256 MB write) before every timed step', 'cuda_graph': not args.no_graph,
+                       'e2e': 'one timed region of K steps; per step: pinned-host -> device copy of that step\'s inputs (copy stream, '
+                              'double-buffered so it overlaps the previous step\'s compute), L2 flush, get_pose, device -> pinned-host '
+                              'read of the poses',
                        'precision': args.precision, 'parallelism': f'batch-sharded x{world}, no data-path collective'},
             'e2e': {'value': world * b / (e2e_ms * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_ms},
