@@ -36,6 +36,12 @@ struct TcParams {
   int m_tiles, num_tiles;        // pixel tiles, pixel tiles x N tiles (tile t: n = t / m_tiles, m = t % m_tiles)
   int cluster;                   // CTAs per cluster (1, 2 or 4): consecutive pixel tiles of one N tile share each weight tile,
                                  // every CTA fetching BN/cluster rows of it and multicasting them to its peers
+  // halo mode (stride-1 multi-tap convolutions, one sample per tile): the activation tile is fetched ONCE per channel chunk
+  // together with its (kw-1) x (kh-1) halo - PW x PH pixel rows of 128 B - and every tap reads it through a row-shifted
+  // UMMA descriptor.  The tile is 8 x 16 pixels so that one 8-row core-matrix group = one tile row and the group stride
+  // (SBO) is the halo pitch PW*128 B.  Cuts the activation bytes a CTA ingests per chunk from taps*32 KB to ~46 KB; the
+  // weight tiles (one per tap) go through their own, deeper ring.
+  int halo, PW, PH, a_stages, b_stages;
   int pair;                      // 1 (with cluster == 2): the two CTAs run ONE cta_group::2 MMA of M = 256 - each keeps its
                                  // own 128 A rows and only HALF of the weight rows in shared memory (no multicast), which cuts
                                  // the shared-memory traffic per FLOP (operand reads + TMA fills), the resource a single-CTA
@@ -50,6 +56,7 @@ struct TcParams {
   // the two halves.
   int stackn;
   int fast_epi;                  // every global access of the epilogue is 16 B aligned: use the coalesced staged path
+  int direct_st;                 // ... and every 32-column output block is 32 B aligned: 256-bit row stores, no staging
   const float* bias; float scale; int epi, act;
   float* out_f32; int out_f32_stride, out_f32_coff;
   __nv_bfloat16* out_hl; long long out_hl_plane; int out_hl_stride, out_hl_coff;
@@ -153,6 +160,43 @@ __device__ __forceinline__ void row_values(const uint4 (&r)[4], float (&out)[16]
     out[4 * j + 2] = __uint_as_float(r[j].z); out[4 * j + 3] = __uint_as_float(r[j].w);
   }
 }
+// Direct row stores with 256-bit instructions (sm_100): the thread writes whole 32 B sectors of its own pixel row, so no
+// shared-memory transpose (and none of the tensor core's shared-memory bandwidth) is needed.  Require 32 B alignment.
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+// 32 fp32 values of this thread's row -> 128 B
+__device__ __forceinline__ void row_store_f32x32(float* row_ptr, const float* v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = __float_as_uint(v[8 * i + j]);
+    st_global_256(row_ptr + 8 * i, w);
+  }
+}
+// 32 fp32 values of this thread's row -> split-bf16: 64 B in the hi plane, 64 B in the lo plane
+__device__ __forceinline__ void row_store_split32(__nv_bfloat16* row_ptr, long long plane, const float* v) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float a = v[2 * i], b = v[2 * i + 1];
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint32_t wh[8], wl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { wh[j] = hi[8 * i + j]; wl[j] = lo[8 * i + j]; }
+    st_global_256(row_ptr + 16 * i, wh);
+    st_global_256(row_ptr + plane + 16 * i, wl);
+  }
+}
 // 16 fp32 values of this thread's row -> one 64 B fp32 block
 __device__ __forceinline__ void stage_store_f32(uint32_t sbuf, int lane, float* gbase, int stride, const int (&rp)[4], const float* v) {
   uint4 d[4];
@@ -233,12 +277,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // header: [0,256) barriers + TMEM pointer | [1024, ..) epilogue staging, 2560 B per epilogue warp | two 1 KB bias buffers ;
   // then the operand ring: `stages` x {A hi, A lo, W hi, W lo}
   const uint32_t bar_full = smem_base, bar_empty = smem_base + 64, bar_tfull = smem_base + 128, bar_tempty = smem_base + 144,
-                 tmem_slot = smem_base + 192;
+                 bar_afull = smem_base + 160, bar_aempty = smem_base + 176, tmem_slot = smem_base + 192;
   const uint32_t stage0 = smem_base + 1024;
   const uint32_t bias0 = smem_base + 1024 + EW * 32 * TC_STAGE_ROW;
   const uint32_t tiles0 = smem_base + tc_header(EW);
   const uint32_t b_plane = (uint32_t)(PAIR ? p.BN / 2 : p.BN) * 128u;    // weight rows held by this CTA
   const uint32_t stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;
+  const uint32_t a_plane = (uint32_t)(p.PW * p.PH) * 128u;                        // halo mode: one bf16 plane of the halo tile
+  const uint32_t a_stage = (2u * a_plane + 1023u) & ~1023u;
+  const uint32_t bring0 = tiles0 + (uint32_t)p.a_stages * a_stage;                // halo mode: start of the weight ring
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   griddep_launch_dependents();   // the next kernel's prologue may overlap this grid's tail (it waits before touching memory)
@@ -258,7 +305,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (p.nseg > 1) prefetch_tmap(&tmA1);
     if (p.nseg > 2) prefetch_tmap(&tmA2);
     prefetch_tmap(&tmW);
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < p.a_stages; ++s) {
+      mbar_init(bar_afull + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 1);
+    }
+    for (int s = 0; s < (p.halo ? p.b_stages : p.stages); ++s) {
       mbar_init(bar_full + 8 * s, 1);
       // multicast mode: every CTA of the cluster releases the stage (peers write into it); pair mode: one multicast commit
       mbar_init(bar_empty + 8 * s, PAIR ? 1u : (uint32_t)p.cluster);
@@ -289,14 +340,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       // ================= TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, hsa = 0;
+      uint32_t phase = 0, hpa = 0;
       const int w_rows = p.BN / p.cluster;
       for (int t = tile0; t < p.num_tiles; t += tile_step) {
         const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
         const int b = (mt / tiles_per_img) * p.TB, tr = mt % tiles_per_img;
         const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
         const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * p.BN;
+        if (p.halo) {
+          // one halo tile per channel chunk, then one weight tile per tap (own ring)
+          for (int s = 0; s < p.nseg; ++s) {
+            const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
+            for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
+              mbar_wait(bar_aempty + 8 * hsa, hpa ^ 1u);
+              mbar_arrive_expect_tx(bar_afull + 8 * hsa, 2 * a_plane);
+              tma_load_5d(tiles0 + hsa * a_stage, tm, bar_afull + 8 * hsa, cc * TC_BK, x0 - p.pw, y0 - p.ph, b, 0);
+              if (++hsa == p.a_stages) { hsa = 0; hpa ^= 1u; }
+              const int wk = p.seg_wcoff[s] + cc * TC_BK;
+              for (int tap = 0; tap < p.num_taps; ++tap) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                const uint32_t full = bar_full + 8 * stage;
+                mbar_arrive_expect_tx(full, 2 * b_plane);
+                const uint32_t w_dst = bring0 + stage * 2 * b_plane;
+                tma_load_4d(w_dst, &tmW, full, wk, n0, tap, 0);
+                tma_load_4d(w_dst + b_plane, &tmW, full, wk, n0, tap, 1);
+                if (++stage == p.b_stages) { stage = 0; phase ^= 1u; }
+              }
+            }
+          }
+          continue;
+        }
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
           const int cx = x0 * p.sx + kx - p.pw, cy = y0 * p.sy + ky - p.ph;
@@ -339,14 +413,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (lane == 0 && !(PAIR && crank != 0)) {
       // ================= MMA issuer (pair mode: the leader CTA issues for both)
       const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, p.BN), idesc2 = make_idesc_bf16(TC_BM, 2 * p.BN);
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, hsa = 0;
+      uint32_t phase = 0, hpa = 0;
       int it = 0;
       for (int t = tile0; t < p.num_tiles; t += tile_step, ++it) {
         const int acc = it & 1;
         mbar_wait(bar_tempty + 8 * acc, (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue of tile it-2 has drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
+        if (p.halo) {
+          // tap (ky, kx) = the halo tile read from row offset ky*PW + kx; SWIZZLE_128B is a function of the absolute shared-
+          // memory address for TMA and UMMA alike, so any 128 B row offset is a valid operand start
+          const uint32_t a_sbo = (uint32_t)p.PW * 128u;
+          bool first = true;
+          for (int sg = 0; sg < p.nseg; ++sg) {
+            for (int cc = 0; cc < p.seg_chunks[sg]; ++cc) {
+              const int ks = (cc == p.seg_chunks[sg] - 1) ? p.seg_last_ks[sg] : TC_BK / 16;
+              mbar_wait(bar_afull + 8 * hsa, hpa);
+              const uint32_t a_base = tiles0 + hsa * a_stage;
+              for (int tap = 0; tap < p.num_taps; ++tap) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                if (it == 0 && first) stamp(2);
+                const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                const uint32_t a_addr = a_base + (uint32_t)(ky * p.PW + kx) * 128u;
+                const uint64_t a_hi = make_smem_desc_sw128(a_addr, a_sbo), a_lo = make_smem_desc_sw128(a_addr + a_plane, a_sbo);
+                const uint32_t w_addr = bring0 + stage * 2 * b_plane;
+                const uint64_t b_hi = make_smem_desc_sw128(w_addr, 1024), b_lo = make_smem_desc_sw128(w_addr + b_plane, 1024);
+                if (p.stackn) {
+#pragma unroll
+                  for (int k = 0; k < TC_BK / 16; ++k) {
+                    if (k < ks) {
+                      const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                      umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc2, (!first || k > 0) ? 1u : 0u);
+                      umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < TC_BK / 16; ++k) {
+                    if (k < ks) {
+                      const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                      umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, (!first || k > 0) ? 1u : 0u);
+                      umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                      umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
+                    }
+                  }
+                }
+                first = false;
+                umma_commit(bar_empty + 8 * stage);
+                if (++stage == p.b_stages) { stage = 0; phase ^= 1u; }
+              }
+              umma_commit(bar_aempty + 8 * hsa);      // every tap of this chunk has read the halo tile
+              if (++hsa == p.a_stages) { hsa = 0; hpa ^= 1u; }
+            }
+          }
+          umma_commit(bar_tfull + 8 * acc);
+          if (it == 0) stamp(3);
+          continue;
+        }
         int c = 0;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           for (int sg = 0; sg < p.nseg; ++sg) {
@@ -525,7 +650,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int i = 0; i < 32; ++i) acc_ += v[i];
             if (acc_ == 123.456f) p.out_f32[0] = acc_;
           } else if (EPI == SCF_EPI_GRU_ZR) {
-            if (nb < half) {                   // z gate -> fp32 (read back by the q convolution's epilogue)
+            if (p.direct_st) {
+              if (valid) {
+                if (nb < half) row_store_f32x32(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v);
+                else row_store_split32(p.out2_hl + pix * p.out2_hl_stride + (nb - half), p.out2_hl_plane, v);
+              }
+            } else if (nb < half) {            // z gate -> fp32 (read back by the q convolution's epilogue)
               stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, rp, v);
               stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, rp, v + 16);
             } else {
@@ -559,12 +689,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     *reinterpret_cast<float4*>(o + p.cout) = make_float4(q4[0], q4[1], q4[2], q4[3]);
                   }
                 }
+              } else if (p.direct_st) {
+                if (valid) row_store_f32x32(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v);
               } else {
                 stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, rp, v);
                 stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, rp, v + 16);
               }
             }
-            if (p.out_hl) stage_store_split32(sbuf, lane, p.out_hl + p.out_hl_coff + nb, p.out_hl_plane, p.out_hl_stride, rp, v);
+            if (p.out_hl) {
+              if (p.direct_st) {
+                if (valid) row_store_split32(p.out_hl + pix * p.out_hl_stride + p.out_hl_coff + nb, p.out_hl_plane, v);
+              } else {
+                stage_store_split32(sbuf, lane, p.out_hl + p.out_hl_coff + nb, p.out_hl_plane, p.out_hl_stride, rp, v);
+              }
+            }
           }
         }
         g_begin = nslab * 2;
@@ -835,6 +973,20 @@ static void pick_tile(int B, int H, int W, bool one_sample, int& TW, int& TH, in
   }
 }
 
+// tiling of the calling thread's most recent scf_conv2d_tc launch (the `stats` buffer is indexed by its pixel tiles)
+thread_local int g_last_m_tiles = 0, g_last_tiles_per_img = 0;
+void conv2d_tc_last_tiles(int* m_tiles, int* per_img) {
+  if (m_tiles) *m_tiles = g_last_m_tiles;
+  if (per_img) *per_img = g_last_tiles_per_img;
+}
+// upper bound of the number of pixel tiles any tiling of a [B, Hout, Wout] output can have (sizes the `stats` buffer)
+int conv2d_tc_max_tiles(int B, int Hout, int Wout) {
+  int TW = 0, TH = 0, TB = 0;
+  pick_tile(B, Hout, Wout, false, TW, TH, TB);
+  const int a = cdiv(Wout, TW) * cdiv(Hout, TH) * cdiv(B, TB), h = cdiv(Wout, 8) * cdiv(Hout, 16) * B;
+  return a > h ? a : h;
+}
+
 int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   SCF_REQUIRE(d.nseg >= 1 && d.nseg <= 3, SCF_ERR_ARG, "scf_conv2d_tc: nseg must be 1..3");
   SCF_REQUIRE(d.w && d.B > 0 && d.H > 0 && d.W > 0 && d.cout > 0, SCF_ERR_ARG, "scf_conv2d_tc: null pointer or empty shape");
@@ -958,7 +1110,33 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
       while (p.tmem_cols < 2 * p.acc_cols) p.tmem_cols <<= 1;
     }
   }
-  const int smem = 1024 + tc_header(ew) + p.stages * stage_bytes;
+  // ---- halo mode: stride-1 multi-tap convolutions fetch the activation tile once per channel chunk (see TcParams)
+  p.halo = 0; p.PW = p.PH = 0; p.a_stages = 0; p.b_stages = 0;
+  int smem = 1024 + tc_header(ew) + p.stages * stage_bytes;
+  {
+    const char* hv = getenv("SCFLOW_TC_HALO");
+    const int want = hv ? atoi(hv) : 1;               // 0 off, 1 on for single-CTA one-CTA-per-SM tiles, 2 also instead of two-CTAs-per-SM
+    const bool eligible = p.sx == 1 && p.sy == 1 && p.num_taps > 1 && !d.w_batched && !p.pair && p.H * p.W >= 128 &&
+                          (ctas_per_sm == 1 || want >= 2);
+    if (want && eligible) {
+      const int PW = 8 + d.kw - 1, PH = 16 + d.kh - 1;
+      const int a_stage = (2 * PW * PH * 128 + 1023) / 1024 * 1024;
+      const int b_stage = 2 * p.BN * 128;
+      int sb = (232448 - 1024 - tc_header(8) - 2 * a_stage) / b_stage;
+      if (sb > 8) sb = 8;
+      if (sb >= 2) {
+        p.halo = 1; p.PW = PW; p.PH = PH; p.a_stages = 2; p.b_stages = sb;
+        p.TW = 8; p.TH = 16; p.TB = 1;
+        p.tiles_x = cdiv(p.W, 8); p.tiles_y = cdiv(p.H, 16);
+        p.m_tiles = p.tiles_x * p.tiles_y * d.B;
+        p.num_tiles = p.m_tiles * cdiv(d.cout_pad, p.BN);
+        ew = 8; ctas_per_sm = 1;
+        smem = 1024 + tc_header(8) + 2 * a_stage + sb * b_stage;
+      }
+    }
+  }
+  g_last_m_tiles = p.m_tiles;
+  g_last_tiles_per_img = p.TB == 1 ? p.tiles_x * p.tiles_y : 0;
   KernelFn kernel = table[p.pair ? 2 : (ew == 8 ? 1 : 0)][ki];
   // ---- cluster size: CTAs of consecutive pixel tiles (same N tile, same sample when the weights are batched) share each
   // weight tile through TMA multicast, which divides the weight share of the L2 -> shared-memory operand traffic - the
@@ -1024,6 +1202,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     // a one-row (one-column) tile needs no element stride along that axis: the producer's coordinate already carries it
     const int bsx = p.TW == 1 ? 1 : p.sx, bsy = p.TH == 1 ? 1 : p.sy;
     cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.TW * bsx), (cuuint32_t)(p.TH * bsy), (cuuint32_t)p.TB, 2};
+    if (p.halo) { box[1] = (cuuint32_t)p.PW; box[2] = (cuuint32_t)p.PH; }
     cuuint32_t estr[5] = {1, (cuuint32_t)bsx, (cuuint32_t)bsy, 1, 1};
     SCF_TRY(encode_map(&tmA[s], base, 5, dims, str, box, estr));
     p.seg_chunks[s] = cdiv(sg.nch, TC_BK);
@@ -1052,6 +1231,16 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     if (d.epi == SCF_EPI_GRU_ZR) ok = ok && (d.cout / 2) % 32 == 0;
     const char* fe = getenv("SCFLOW_TC_FASTEPI");
     p.fast_epi = (ok && (fe ? atoi(fe) != 0 : true)) ? 1 : 0;
+  }
+  {
+    // 256-bit direct stores need 32 B alignment of every 32-column block of every output
+    auto al32 = [](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % 32 == 0; };
+    bool ok = p.fast_epi != 0;
+    if (d.out_f32) ok = ok && al32(d.out_f32) && d.out_f32_stride % 8 == 0 && d.out_f32_coff % 8 == 0;
+    if (d.out_hl) ok = ok && al32(d.out_hl) && d.out_hl_stride % 16 == 0 && d.out_hl_coff % 16 == 0 && (d.out_hl_plane * 2) % 32 == 0;
+    if (d.out2_hl) ok = ok && al32(d.out2_hl) && d.out2_hl_stride % 16 == 0 && (d.out2_hl_plane * 2) % 32 == 0;
+    const char* ds = getenv("SCFLOW_TC_DIRECT_ST");
+    p.direct_st = (ok && (ds ? atoi(ds) != 0 : false)) ? 1 : 0;   // measured: no gain over the staged stores, off by default
   }
   if (d.stats)
     SCF_REQUIRE(p.fast_epi && p.TB == 1 && d.cout % 32 == 0 && d.out_f32 && d.epi == SCF_EPI_ACT &&

@@ -11,6 +11,8 @@ namespace scf {
 int conv2d_f32(const scf_conv_desc& d, cudaStream_t st);
 int conv2d_thin(const scf_conv_desc& d, int in_nchw, cudaStream_t st);
 int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st);
+void conv2d_tc_last_tiles(int* m_tiles, int* per_img);
+int conv2d_tc_max_tiles(int B, int Hout, int Wout);
 int im2col_x_split(const float* in, int nchw, int cin, int kw, void* out_hl, long long plane, int N, int H, int Wi, int sx,
                    cudaStream_t st);
 int pack_conv_weight_tc_foldx(const float* w_oihw, float* scratch, void* packed, int O, int C, int KH, int KW, int cin_pad,
@@ -223,7 +225,7 @@ static void build_enc_ws(int N, int H, int W, EncWs& w) {
     int hh = H / 2, ww = W / 2;
     const int chans[3] = {64, 96, 128};
     for (int l = 0; l < 3; ++l) {
-      const size_t need = (size_t)scf_conv2d_tc_tiles(N, hh, ww, nullptr) * 4 * 2 * chans[l] * 4;
+      const size_t need = (size_t)conv2d_tc_max_tiles(N, hh, ww) * 4 * 2 * chans[l] * 4;
       if (need > part) part = need;
       hh = (hh - 1) / 2 + 1; ww = (ww - 1) / 2 + 1;
     }
@@ -355,8 +357,10 @@ int scf_encoder_forward(int norm, const void* packed, const float* images, int N
     const int ho = (hin + 2 * (e.k / 2) - e.k) / e.stride + 1, wo = (win + 2 * (e.k / 2) - e.k) / e.stride + 1;
     int per_img = 0;
     scf_conv2d_tc_tiles(N, ho, wo, &per_img);
-    if (per_img > 0 && e.cout % 32 == 0) {
+    if (per_img > 0 && e.cout % 32 == 0 && ho * wo >= 128) {
       SCF_TRY(tcconv(u, in_s, hin, win, SCF_ACT_NONE, raw, nullptr, nullptr, F(ws.part)));
+      conv2d_tc_last_tiles(nullptr, &per_img);      // the tiling the launch actually used (halo mode: 8 x 16 pixel tiles)
+      SCF_REQUIRE(per_img > 0, SCF_ERR_UNSUPPORTED, "scf_encoder_forward: statistics need one sample per tile");
       instnorm_finalize_tiles_kernel<<<dim3(N, e.cout / 32), 256, 0, st>>>(F(ws.part), stat, ho * wo, e.cout, 1e-5f, per_img);
       return check_launch("instnorm_finalize_tiles_kernel");
     }
@@ -372,6 +376,7 @@ int scf_encoder_forward(int norm, const void* packed, const float* images, int N
     scf_conv2d_tc_tiles(N, h, w, &per_img);
     if (per_img > 0) {
       SCF_TRY(stem_conv(SCF_ACT_NONE, F(ws.raw), nullptr, F(ws.part)));
+      conv2d_tc_last_tiles(nullptr, &per_img);
       instnorm_finalize_tiles_kernel<<<dim3(N, 2), 256, 0, st>>>(F(ws.part), F(ws.stat), h * w, 64, 1e-5f, per_img);
       SCF_TRY(check_launch("instnorm_finalize_tiles_kernel"));
     } else {
