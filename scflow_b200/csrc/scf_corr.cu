@@ -5,6 +5,7 @@
 //   g = c*2/(W_l-1) - 1 ; i = ((g+1)*0.5)*(W_l-1)        -- replayed with round-to-nearest intrinsics, no FMA
 //   bilinear taps floor(i), floor(i)+1 ; out-of-range taps contribute 0 (padding_mode='zeros').
 #include "scf_common.cuh"
+#include <stdlib.h>
 #include "scf_tc.cuh"
 
 namespace scf {
@@ -176,6 +177,105 @@ __global__ void __launch_bounds__(256) corr_lookup_l4r4_kernel(const LookupParam
   }
 }
 
+// Same lookup, with each level's window region staged in shared memory first.  The 81 taps of a level touch a region of
+// at most 11 x 11 texels; gathering them straight from global memory costs 4 scattered loads per tap (the LSU, not HBM, is
+// the limit: ~48 warp-wide gathers per query).  Here a warp copies the bounding box of every level with row-contiguous
+// loads (zeros outside the map = the reference's zeros padding), then the taps read shared memory.  Values, weights and
+// accumulation order are unchanged, so the output is bit-identical to the kernel above.
+constexpr int LK_RS = 12, LK_ROWS = 12;      // staged region: up to 12 x 12 texels per level
+__global__ void __launch_bounds__(256) corr_lookup_l4r4_smem_kernel(const LookupParams p) {
+  constexpr int R = 4, K = 9, KK = 81, L = 4, ROUNDS = 3;
+  __shared__ float reg[8][L][LK_ROWS * LK_RS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
+  if (q >= p.nq) return;
+  const int P = p.H8 * p.W8;
+  const int pix = (int)(q % P);
+  const int y = pix / p.W8, x = pix - y * p.W8;
+  const float2 f = *reinterpret_cast<const float2*>(p.flow8 + q * 2);
+  const float gx0 = __fadd_rn((float)x, f.x), gy0 = __fadd_rn((float)y, f.y);
+  const float mval = p.mask ? p.mask[q] : 1.f;
+  int i0[L], xlo[L], ylo[L];
+  float w0[L], w1[L];
+  float inv = 1.f;
+#pragma unroll
+  for (int l = 0; l < L; ++l, inv *= 0.5f) {
+    const bool isx = lane < K;
+    const int off = (isx ? lane : lane - K) - R;
+    const float c = __fmul_rn(isx ? gx0 : gy0, inv);
+    const float ic = lookup_coord(c, off, isx ? p.wl[l] : p.hl[l]);
+    const float fl = floorf(ic);
+    // clamp far-away coordinates (huge flows) so that the int conversion and the region arithmetic stay defined; a tap
+    // that far outside the map reads zeros either way
+    i0[l] = (int)fminf(fmaxf(fl, -65536.f), 65536.f);
+    w1[l] = ic - fl;
+    w0[l] = (fl + 1.f) - ic;
+    // the per-axis floor coordinates increase with the window index: the region starts at index 0 of each axis
+    xlo[l] = __shfl_sync(0xffffffffu, i0[l], 0);
+    ylo[l] = __shfl_sync(0xffffffffu, i0[l], K);
+  }
+  // ---- stage the regions (coalesced along x), all loads issued before the first use
+  float st[L][(LK_ROWS * LK_RS + 31) / 32];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const int hl = p.hl[l], wl = p.wl[l];
+    const float* vol = p.lvl[l] + q * (long long)(hl * wl);
+#pragma unroll
+    for (int j = 0; j < (LK_ROWS * LK_RS + 31) / 32; ++j) {
+      const int idx = j * 32 + lane;
+      const int r = idx / LK_RS, c = idx - r * LK_RS;
+      const int yy = ylo[l] + r, xx = xlo[l] + c;
+      st[l][j] = (idx < LK_ROWS * LK_RS && yy >= 0 && yy < hl && xx >= 0 && xx < wl) ? __ldg(vol + yy * wl + xx) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < L; ++l)
+#pragma unroll
+    for (int j = 0; j < (LK_ROWS * LK_RS + 31) / 32; ++j) {
+      const int idx = j * 32 + lane;
+      if (idx < LK_ROWS * LK_RS) reg[wid][l][idx] = st[l][j];
+    }
+  __syncwarp();
+  float* outq = p.out ? p.out + q * p.out_stride + p.out_coff : nullptr;
+  __nv_bfloat16* outh = p.out_hl ? p.out_hl + q * p.out_stride : nullptr;
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const int tap = r * 32 + lane;
+      const int tc = tap < KK ? tap : KK - 1;
+      const int a = tc / K, b = tc - a * K;
+      const int x0 = __shfl_sync(0xffffffffu, i0[l], a), y0 = __shfl_sync(0xffffffffu, i0[l], K + b);
+      const float wx0 = __shfl_sync(0xffffffffu, w0[l], a), wx1 = __shfl_sync(0xffffffffu, w1[l], a);
+      const float wy0 = __shfl_sync(0xffffffffu, w0[l], K + b), wy1 = __shfl_sync(0xffffffffu, w1[l], K + b);
+      if (tap >= KK) continue;
+      const int rx = x0 - xlo[l], ry = y0 - ylo[l];
+      float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
+      if (rx >= 0 && rx + 1 < LK_RS && ry >= 0 && ry + 1 < LK_ROWS) {      // always true for finite coordinates
+        const float* s0 = &reg[wid][l][ry * LK_RS + rx];
+        v00 = s0[0]; v01 = s0[1]; v10 = s0[LK_RS]; v11 = s0[LK_RS + 1];
+      }
+      float acc = 0.f;
+      acc += v00 * (wx0 * wy0);
+      acc += v01 * (wx1 * wy0);
+      acc += v10 * (wx0 * wy1);
+      acc += v11 * (wx1 * wy1);
+      acc *= mval;
+      if (outq) outq[l * KK + tap] = acc;
+      if (outh) {
+        __nv_bfloat16 hi, lo;
+        tc::split_bf16(acc, hi, lo);
+        outh[l * KK + tap] = hi;
+        outh[p.out_hl_plane + l * KK + tap] = lo;
+      }
+    }
+  }
+  if (outh) {
+    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+    for (int c = L * KK + lane; c < p.out_stride; c += 32) { outh[c] = zero; outh[p.out_hl_plane + c] = zero; }
+  }
+}
+
 __global__ void corr_lookup_taps_kernel(int level, int radius, const float* __restrict__ flow8, int32_t* __restrict__ x0,
                                         int32_t* __restrict__ y0, int H8, int W8, long long nq) {
   const int k = 2 * radius + 1;
@@ -274,6 +374,11 @@ static int corr_lookup_impl(const float* const* h_levels, int num_levels, int ra
   p.out_stride = out_stride; p.out_coff = out_coff; p.H8 = H8; p.W8 = W8; p.nq = (long long)B * H8 * W8;
   const int wpb = 8;
   if (num_levels == 4 && radius == 4) {
+    static const bool staged = [] { const char* e = getenv("SCFLOW_LOOKUP_SMEM"); return e ? atoi(e) != 0 : true; }();
+    if (staged) {
+      scf::corr_lookup_l4r4_smem_kernel<<<scf::cdiv(p.nq, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(p);
+      return scf::check_launch("corr_lookup_l4r4_smem_kernel");
+    }
     scf::corr_lookup_l4r4_kernel<<<scf::cdiv(p.nq, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(p);
     return scf::check_launch("corr_lookup_l4r4_kernel");
   }
