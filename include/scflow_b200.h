@@ -131,6 +131,7 @@ typedef struct scf_tc_conv_desc {
   const float* pre; int pre_stride;   /* GRU epilogues: fp32 NHWC map added to the accumulator before the gate non-linearity
                                        * (the loop-invariant context contribution of the GRU convolutions, computed once) */
   int stride_x, stride_y;             /* per-axis strides overriding `stride` when non-zero (1 or 2 each) */
+  long long w_plane_stride;           /* elements from the hi to the lo plane of `w` (0 = tightly packed) */
   float* stats;                       /* EPI_ACT: per (pixel tile, epilogue warp) partial sums of the fp32 output,
                                        * [m_tiles][4][2][cout] floats (sum, then sum of squares), for InstanceNorm; needs
                                        * one sample per 128-pixel tile and cout % 32 == 0 */
@@ -221,6 +222,18 @@ int scf_encoder_pack(int norm, const float* const* h_weights, void* packed, void
 int scf_encoder_forward(int norm, const void* packed, const float* images, int N, int H, int W, float* out_nchw,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same network, but the final 1x1 convolution writes the consumer's layout directly (no NCHW round trip): pixel-major
+ * split-bf16 planes and / or fp32 NHWC, with an optional activation per channel block.  split = 256: one block of 256
+ * channels (feature encoder: hl0 = [2][N*P][256]); split = 128: channels [0,128) -> block 0, [128,256) -> block 1 (context
+ * encoder: block 0 = tanh -> hidden state, block 1 = relu -> context; scflow_refiner.py:101-108). */
+typedef struct scf_encoder_out {
+  void* hl0; long long plane0; int stride0; float* f32_0; int f32_stride0; int act0;
+  void* hl1; long long plane1; int stride1; float* f32_1; int f32_stride1; int act1;
+  int split;
+} scf_encoder_out;
+int scf_encoder_forward_ex(int norm, const void* packed, const float* images, int N, int H, int W, const scf_encoder_out* out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- whole decoder loop --------------------- */
 enum scf_decoder_weight {
   SCF_W_CORR0_W = 0, SCF_W_CORR0_B,   /* encoder.corr_net.0.conv   [256,324,1,1] */
@@ -288,7 +301,14 @@ typedef struct scf_decoder_io {
    * Python module uses it to run two half batches on two streams (the tail of one chain overlaps the other's kernels).
    * `label` may then point at the FULL batch's labels: only label[0] is read (pose_head.py:201-211 class-selection quirk). */
   int out_batch_total, out_batch_offset;
+  /* native_inputs = 1: feat_render / feat_real / h_feat / cxt_feat are ignored; the caller (scf_encoder_forward_ex) has already
+   * written them in the loop's own layout into the workspace slots reported by scf_decoder_workspace_slots (precision 1). */
+  int native_inputs;
 } scf_decoder_io;
+/* Byte offsets into the decoder workspace (precision 1) of the buffers an encoder can fill directly:
+ *   slots[0] feature maps, split-bf16 [2][2*B*P][256]: samples [0,B) = feat_real, [B,2B) = feat_render (plane stride 2*B*P*256)
+ *   slots[1] hidden state h, split-bf16 [2][B*P][128] ; slots[2] h, fp32 [B*P][128] ; slots[3] context, split-bf16 [2][B*P][128] */
+int scf_decoder_workspace_slots(const scf_decoder_cfg* cfg, int B, int H, int W, size_t* slots4);
 
 int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const scf_decoder_io* io, int B, int H, int W,
                         int iters, void* workspace, size_t workspace_bytes, void* stream);

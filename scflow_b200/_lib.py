@@ -51,7 +51,7 @@ class TcConvDesc(C.Structure):
         ('out_hl', c_void_p), ('out_hl_plane', C.c_longlong), ('out_hl_stride', C.c_int), ('out_hl_coff', C.c_int),
         ('aux0', c_void_p), ('aux0_stride', C.c_int), ('aux1', c_void_p), ('aux1_stride', C.c_int),
         ('out2_hl', c_void_p), ('out2_hl_plane', C.c_longlong), ('out2_hl_stride', C.c_int),
-        ('pre', c_void_p), ('pre_stride', C.c_int), ('stride_x', C.c_int), ('stride_y', C.c_int), ('stats', c_void_p),
+        ('pre', c_void_p), ('pre_stride', C.c_int), ('stride_x', C.c_int), ('stride_y', C.c_int), ('w_plane_stride', C.c_longlong), ('stats', c_void_p),
     ]
 
 
@@ -67,7 +67,15 @@ class DecoderIO(C.Structure):
         ('label', c_void_p), ('init_flow', c_void_p), ('invalid_flow_num', C.c_float),
         ('flow_from_pose', c_void_p), ('flow_from_pred', c_void_p), ('rotation', c_void_p), ('translation', c_void_p),
         ('mask', c_void_p), ('delta_rotation', c_void_p), ('delta_translation', c_void_p), ('h_out', c_void_p),
-        ('out_batch_total', C.c_int), ('out_batch_offset', C.c_int),
+        ('out_batch_total', C.c_int), ('out_batch_offset', C.c_int), ('native_inputs', C.c_int),
+    ]
+
+
+class EncoderOut(C.Structure):
+    _fields_ = [
+        ('hl0', c_void_p), ('plane0', C.c_longlong), ('stride0', C.c_int), ('f32_0', c_void_p), ('f32_stride0', C.c_int), ('act0', C.c_int),
+        ('hl1', c_void_p), ('plane1', C.c_longlong), ('stride1', C.c_int), ('f32_1', c_void_p), ('f32_stride1', C.c_int), ('act1', C.c_int),
+        ('split', C.c_int),
     ]
 
 
@@ -169,6 +177,9 @@ _SIGNATURES = {
     'scf_encoder_pack': (C.c_int, [C.c_int, C.POINTER(c_void_p), c_void_p, c_void_p]),
     'scf_encoder_forward': (C.c_int, [C.c_int, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p, c_void_p, C.c_size_t,
                                       c_void_p]),
+    'scf_encoder_forward_ex': (C.c_int, [C.c_int, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(EncoderOut), c_void_p,
+                                         C.c_size_t, c_void_p]),
+    'scf_decoder_workspace_slots': (C.c_int, [C.POINTER(DecoderCfg), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     'scf_decoder_packed_bytes': (C.c_size_t, [C.POINTER(DecoderCfg)]),
     'scf_decoder_workspace_bytes': (C.c_size_t, [C.POINTER(DecoderCfg), C.c_int, C.c_int, C.c_int]),
     'scf_decoder_pack': (C.c_int, [C.POINTER(DecoderCfg), C.POINTER(c_void_p), c_void_p, c_void_p]),

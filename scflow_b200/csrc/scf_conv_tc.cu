@@ -1215,7 +1215,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     const int third = d.w_batched ? d.B : p.num_taps;
     cuuint64_t dims[4] = {(cuuint64_t)d.cin_pad, (cuuint64_t)d.cout_pad, (cuuint64_t)third, 2};
     cuuint64_t str[3] = {(cuuint64_t)d.cin_pad * 2, (cuuint64_t)d.cout_pad * d.cin_pad * 2,
-                         (cuuint64_t)third * d.cout_pad * d.cin_pad * 2};
+                         d.w_plane_stride > 0 ? (cuuint64_t)d.w_plane_stride * 2 : (cuuint64_t)third * d.cout_pad * d.cin_pad * 2};
     cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.BN / p.cluster), 1, 1};
     SCF_REQUIRE(reinterpret_cast<uintptr_t>(d.w) % 16 == 0, SCF_ERR_ALIGN, "scf_conv2d_tc: packed weight must be 16B aligned");
     SCF_TRY(encode_map(&tmW, d.w, 4, dims, str, box));

@@ -3,6 +3,7 @@
 // hands in a packed-weight arena (scf_decoder_pack) and a workspace (scf_decoder_workspace_bytes), so the whole
 // call is CUDA-graph capturable.
 #include "scf_common.cuh"
+#include <cuda_bf16.h>
 #include <string.h>
 
 namespace scf {
@@ -20,6 +21,7 @@ int pack_conv_weight_tc_foldx(const float* w_oihw, float* scratch, void* packed,
                               int cout_pad, int o_off, cudaStream_t st);
 int corr_build_dispatch(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
                         float* const* levels, void* scratch, int precision, cudaStream_t st);
+int corr_build_presplit(void* scratch, int B, int C, int H8, int W8, int num_levels, float* const* levels, cudaStream_t st);
 
 thread_local char g_err[512] = {0};
 thread_local long long g_launches = 0;
@@ -271,6 +273,15 @@ size_t scf_decoder_workspace_bytes(const scf_decoder_cfg* cfg, int B, int H, int
   return w.total_bytes;
 }
 
+int scf_decoder_workspace_slots(const scf_decoder_cfg* cfg, int B, int H, int W, size_t* slots4) {
+  SCF_TRY(check_cfg(cfg));
+  SCF_REQUIRE(slots4 && B > 0 && H > 0 && W > 0 && cfg->precision == 1, SCF_ERR_ARG, "scf_decoder_workspace_slots: bad args (precision 1 only)");
+  Workspace w;
+  build_workspace(*cfg, B, H, W, w);
+  slots4[0] = w.corr_scratch; slots4[1] = w.s_h[0]; slots4[2] = w.h[0]; slots4[3] = w.s_cxt;
+  return 0;
+}
+
 int scf_decoder_pack(const scf_decoder_cfg* cfg, const float* const* h_weights, void* packed, void* stream) {
   SCF_TRY(check_cfg(cfg));
   SCF_REQUIRE(h_weights && packed, SCF_ERR_ARG, "scf_decoder_pack: null pointer");
@@ -347,8 +358,8 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
   const int scale = 1 << (cfg->num_levels - 1);
   SCF_REQUIRE(H % scale == 0 && W % scale == 0 && H >= 2 * scale && W >= 2 * scale, SCF_ERR_ARG,
               "scf_decoder_forward: H, W must be multiples of %d", scale);
-  SCF_REQUIRE(io->feat_render && io->feat_real && io->h_feat && io->cxt_feat && io->ref_rotation && io->ref_translation &&
-                  io->depth && io->internel_k && io->init_flow,
+  SCF_REQUIRE((io->native_inputs || (io->feat_render && io->feat_real && io->h_feat && io->cxt_feat)) && io->ref_rotation &&
+                  io->ref_translation && io->depth && io->internel_k && io->init_flow,
               SCF_ERR_ARG, "scf_decoder_forward: null input");
   SCF_REQUIRE(io->flow_from_pose && io->flow_from_pred && io->rotation && io->translation && io->mask &&
                   io->delta_rotation && io->delta_translation,
@@ -377,12 +388,17 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
   // ---- once per forward: pyramid, point map, layout conversion of h / context
   float* levels[8];
   for (int l = 0; l < cfg->num_levels; ++l) levels[l] = F(ws.lvl[l]);
-  SCF_TRY(corr_build_dispatch(io->feat_render, io->feat_real, B, 256, H8, W8, cfg->num_levels, levels, wsb + ws.corr_scratch,
-                              cfg->precision, st));
+  const bool native = io->native_inputs != 0;
+  SCF_REQUIRE(!native || cfg->precision == 1, SCF_ERR_ARG, "scf_decoder_forward: native_inputs needs precision 1");
+  if (native) SCF_TRY(corr_build_presplit(wsb + ws.corr_scratch, B, 256, H8, W8, cfg->num_levels, levels, st));
+  else SCF_TRY(corr_build_dispatch(io->feat_render, io->feat_real, B, 256, H8, W8, cfg->num_levels, levels, wsb + ws.corr_scratch,
+                                   cfg->precision, st));
   SCF_TRY(scf_unproject(io->depth, io->internel_k, io->ref_rotation, io->ref_translation, F(ws.pts4), B, H, W, st));
   const bool tcp = cfg->precision == 1;
   auto S = [&](size_t off) { return reinterpret_cast<void*>(wsb + off); };
-  if (tcp) {
+  if (native) {
+    // h (split + fp32) and the context map were written into their workspace slots by scf_encoder_forward_ex
+  } else if (tcp) {
     SCF_TRY(scf_nchw_to_nhwc_split(io->h_feat, S(ws.s_h[0]), (long long)BP * 128, 128, 0, F(ws.h[0]), 128, B, 128, H8, W8, st));
     SCF_TRY(scf_nchw_to_nhwc_split(io->cxt_feat, S(ws.s_cxt), (long long)BP * 128, 128, 0, nullptr, 0, B, 128, H8, W8, st));
   } else {
@@ -609,6 +625,26 @@ int corr_build_f32(const float* feat_render, const float* feat_real, int B, int 
 // tcgen05 build: both feature maps are transposed to pixel-major split-bf16 ([2][B][P][C], K-major for both GEMM
 // operands); level 0 = batched GEMM  f1[b] (P x C) * f2[b]^T (C x P) / sqrt(C)  on the tensor cores, written once as
 // fp32; levels 1.. are the reference's successive floor 2x2 means.
+// level 0 from pixel-major split-bf16 feature maps f1s (render) / f2s (real), both with hi->lo plane stride `plane`
+static int corr_gemm_and_pool(const void* f1s, const void* f2s, long long plane, int B, int C, int H8, int W8, int num_levels,
+                              float* const* levels, cudaStream_t st) {
+  const int P = H8 * W8;
+  scf_tc_conv_desc d = {};
+  d.seg[0].ptr = f1s; d.seg[0].plane_stride = plane; d.seg[0].stride = C; d.seg[0].coff = 0; d.seg[0].nch = C;
+  d.nseg = 1;
+  d.B = B; d.H = H8; d.W = W8; d.kh = d.kw = 1;
+  d.w = f2s; d.cin_pad = C; d.cout_pad = P; d.cout = P; d.w_batched = 1; d.w_plane_stride = plane;
+  d.bias = nullptr; d.scale = 1.0f / sqrtf((float)C); d.epi = SCF_EPI_ACT; d.act = SCF_ACT_NONE;
+  d.out_f32 = levels[0]; d.out_f32_stride = P; d.out_f32_coff = 0;
+  SCF_TRY(conv2d_tc(d, st));
+  int hl = H8, wl = W8;
+  for (int l = 1; l < num_levels; ++l) {
+    SCF_TRY(avgpool2(levels[l - 1], levels[l], (long long)B * P, hl, wl, st));
+    hl /= 2; wl /= 2;
+  }
+  return 0;
+}
+
 static int corr_build_tc(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
                          float* const* levels, void* scratch, cudaStream_t st) {
   const int P = H8 * W8;
@@ -619,20 +655,16 @@ static int corr_build_tc(const float* feat_render, const float* feat_real, int B
   void* f2s = sc + (size_t)plane * 2 * 2;
   SCF_TRY(scf_nchw_to_nhwc_split(feat_render, f1s, plane, C, 0, nullptr, 0, B, C, H8, W8, st));
   SCF_TRY(scf_nchw_to_nhwc_split(feat_real, f2s, plane, C, 0, nullptr, 0, B, C, H8, W8, st));
-  scf_tc_conv_desc d = {};
-  d.seg[0].ptr = f1s; d.seg[0].plane_stride = plane; d.seg[0].stride = C; d.seg[0].coff = 0; d.seg[0].nch = C;
-  d.nseg = 1;
-  d.B = B; d.H = H8; d.W = W8; d.kh = d.kw = 1;
-  d.w = f2s; d.cin_pad = C; d.cout_pad = P; d.cout = P; d.w_batched = 1;
-  d.bias = nullptr; d.scale = 1.0f / sqrtf((float)C); d.epi = SCF_EPI_ACT; d.act = SCF_ACT_NONE;
-  d.out_f32 = levels[0]; d.out_f32_stride = P; d.out_f32_coff = 0;
-  SCF_TRY(conv2d_tc(d, st));
-  int hl = H8, wl = W8;
-  for (int l = 1; l < num_levels; ++l) {
-    SCF_TRY(avgpool2(levels[l - 1], levels[l], (long long)B * P, hl, wl, st));
-    hl /= 2; wl /= 2;
-  }
-  return 0;
+  return corr_gemm_and_pool(f1s, f2s, plane, B, C, H8, W8, num_levels, levels, st);
+}
+
+// feature maps already in the scratch as ONE split tensor [2][2*B*P][C]: samples [0,B) real, [B,2B) render
+int corr_build_presplit(void* scratch, int B, int C, int H8, int W8, int num_levels, float* const* levels, cudaStream_t st) {
+  const int P = H8 * W8;
+  SCF_REQUIRE(C % 8 == 0 && P % 16 == 0, SCF_ERR_UNSUPPORTED, "scf_corr_build(tc): C %% 8 and H8*W8 %% 16 required");
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(scratch);
+  const long long plane = 2LL * B * P * C;
+  return corr_gemm_and_pool(base + (long long)B * P * C, base, plane, B, C, H8, W8, num_levels, levels, st);
 }
 
 int corr_build_dispatch(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,

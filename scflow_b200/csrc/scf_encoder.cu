@@ -33,6 +33,7 @@ struct EncArena {
   size_t bias[SCF_ENC_UNITS];    // folded bias, padded to a multiple of 16 floats
   size_t packed[SCF_ENC_UNITS];  // bf16 [2][taps][cout_pad][cin_pad]; unit 0 (7x7 stem) is folded to 7x1 over kx*3+c channels
   size_t fold0;                  // scratch for the folded stem weight
+  size_t packed15_half[2];       // unit 15 (conv2) once more as two 128-output-channel halves (h / context heads of the context encoder)
   int cin_pad[SCF_ENC_UNITS], cout_pad[SCF_ENC_UNITS];
   size_t total;
 };
@@ -52,6 +53,7 @@ static void build_enc_arena(EncArena& a) {
       a.fold0 = take((size_t)e.cout * e.cin * e.k * e.k * 4);
     } else a.packed[u] = take((size_t)2 * e.k * e.k * a.cout_pad[u] * a.cin_pad[u] * 2);
   }
+  for (int i = 0; i < 2; ++i) a.packed15_half[i] = take((size_t)2 * 128 * 128 * 2);
   a.total = off;
 }
 
@@ -276,13 +278,16 @@ int scf_encoder_pack(int norm, const float* const* h_weights, void* packed, void
     if (u == 0) SCF_TRY(pack_conv_weight_tc_foldx(wf, reinterpret_cast<float*>(base + a.fold0), base + a.packed[u], e.cout, e.cin, e.k,
                                                   e.k, a.cin_pad[u], a.cout_pad[u], 0, st));
     else SCF_TRY(scf_pack_conv_weight_tc(wf, base + a.packed[u], e.cout, e.cin, e.k, e.k, a.cin_pad[u], a.cout_pad[u], 0, st));
+    if (u == SCF_ENC_UNITS - 1)
+      for (int i = 0; i < 2; ++i)
+        SCF_TRY(scf_pack_conv_weight_tc(wf + (size_t)i * 128 * e.cin, base + a.packed15_half[i], 128, e.cin, 1, 1, 128, 128, 0, st));
   }
   return 0;
 }
 
-int scf_encoder_forward(int norm, const void* packed, const float* images, int N, int H, int W, float* out_nchw,
-                        void* workspace, size_t workspace_bytes, void* stream) {
-  SCF_REQUIRE(packed && images && out_nchw && workspace, SCF_ERR_ARG, "scf_encoder_forward: null pointer");
+static int encoder_forward_impl(int norm, const void* packed, const float* images, int N, int H, int W, float* out_nchw,
+                                const scf_encoder_out* ex, void* workspace, size_t workspace_bytes, void* stream) {
+  SCF_REQUIRE(packed && images && (out_nchw || ex) && workspace, SCF_ERR_ARG, "scf_encoder_forward: null pointer");
   SCF_REQUIRE(norm == SCF_ENC_NORM_IN || norm == SCF_ENC_NORM_BN, SCF_ERR_ARG, "scf_encoder_forward: norm must be IN (0) or BN (1)");
   SCF_REQUIRE(N > 0 && H >= 16 && W >= 16 && H % 8 == 0 && W % 8 == 0, SCF_ERR_ARG, "scf_encoder_forward: H, W must be multiples of 8");
   SCF_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 256 == 0 && reinterpret_cast<uintptr_t>(packed) % 256 == 0, SCF_ERR_ALIGN,
@@ -414,10 +419,44 @@ int scf_encoder_forward(int norm, const void* packed, const float* images, int N
     }
     cur = nxt; h = ho; w = wo;
   }
+  if (ex) {
+    // ---- conv2 writing the consumer's layout directly (pixel-major split-bf16 / fp32, optional activation per channel half):
+    // no NCHW round trip between the encoder and the refinement loop
+    SCF_REQUIRE(ex->split == 256 || ex->split == 128, SCF_ERR_ARG, "scf_encoder_forward_ex: split must be 128 or 256");
+    const long long opix = (long long)N * h * w;
+    for (int part = 0; part < (ex->split == 256 ? 1 : 2); ++part) {
+      scf_tc_conv_desc d = {};
+      d.seg[0].ptr = S(ws.xs[cur]); d.seg[0].plane_stride = opix * 128; d.seg[0].stride = 128; d.seg[0].coff = 0; d.seg[0].nch = 128;
+      d.nseg = 1;
+      d.B = N; d.H = h; d.W = w; d.kh = d.kw = 1; d.stride = 1;
+      const int cout = ex->split == 256 ? 256 : 128;
+      d.w = ex->split == 256 ? pk + a.packed[15] : pk + a.packed15_half[part];
+      d.cin_pad = 128; d.cout_pad = cout; d.cout = cout;
+      d.bias = BIAS(15) + part * 128; d.scale = 1.f; d.epi = SCF_EPI_ACT;
+      d.act = part == 0 ? ex->act0 : ex->act1;
+      d.out_f32 = part == 0 ? ex->f32_0 : ex->f32_1; d.out_f32_stride = part == 0 ? ex->f32_stride0 : ex->f32_stride1;
+      d.out_hl = part == 0 ? ex->hl0 : ex->hl1; d.out_hl_plane = part == 0 ? ex->plane0 : ex->plane1;
+      d.out_hl_stride = part == 0 ? ex->stride0 : ex->stride1;
+      SCF_REQUIRE(d.out_f32 || d.out_hl, SCF_ERR_ARG, "scf_encoder_forward_ex: output %d has no destination", part);
+      SCF_TRY(conv2d_tc(d, st));
+    }
+    return 0;
+  }
   // ---- conv2: 1x1 128 -> out channels, bias only; NHWC -> NCHW for the reference's output layout
   SCF_TRY(tcconv(15, S(ws.xs[cur]), h, w, SCF_ACT_NONE, F(ws.raw), nullptr, nullptr));
   SCF_TRY(scf_nhwc_to_nchw(F(ws.raw), 256, 0, out_nchw, N, 256, h, w, st));
   return 0;
+}
+
+int scf_encoder_forward(int norm, const void* packed, const float* images, int N, int H, int W, float* out_nchw,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  SCF_REQUIRE(out_nchw != nullptr, SCF_ERR_ARG, "scf_encoder_forward: null output");
+  return encoder_forward_impl(norm, packed, images, N, H, W, out_nchw, nullptr, workspace, workspace_bytes, stream);
+}
+int scf_encoder_forward_ex(int norm, const void* packed, const float* images, int N, int H, int W, const scf_encoder_out* out,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  SCF_REQUIRE(out != nullptr, SCF_ERR_ARG, "scf_encoder_forward_ex: null output descriptor");
+  return encoder_forward_impl(norm, packed, images, N, H, W, nullptr, out, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -266,9 +266,12 @@ class SCFlowDecoder(BaseModule):
     def _run_one(self, cfg, arena, ws, ins, outs, b, h, w, iters, invalid, lo=0, total=0):
         """One scf_decoder_forward call on the current stream for samples lo..lo+b-1 of the batch."""
         io = _lib.DecoderIO()
+        io.native_inputs = 1 if ins.get('feat_render') is None else 0
         for k in ('feat_render', 'feat_real', 'h_feat', 'cxt_feat', 'ref_rotation', 'ref_translation', 'depth', 'internel_k',
                   'init_flow'):
-            t = ins[k]
+            t = ins.get(k)
+            if t is None:
+                continue
             io_ptr = t.data_ptr() + lo * t.stride(0) * t.element_size()
             setattr(io, k, io_ptr)
         io.label = ins['label'].data_ptr()        # full batch: only label[0] is read (pose_head.py:201-211 quirk)
@@ -353,8 +356,46 @@ class SCFlowDecoder(BaseModule):
         order = ('flow_from_pose', 'flow_from_pred', 'rotation', 'translation', 'mask', 'delta_rotation', 'delta_translation')
         return tuple([outs[k][i] for i in range(iters)] for k in order)
 
+    # ------------------------------------------------------------------ encoder -> loop without the NCHW round trip
+    def native_slots(self, b: int, h: int, w: int, device):
+        """(cfg, workspace tensor, byte offsets of the feature / h split / h fp32 / context slots) for encoders that write the
+        loop's inputs directly (scf_encoder_forward_ex); None when this configuration cannot take them."""
+        if int(self.precision) != 1 or self._splits(b) != 1:
+            return None
+        cfg = self._cfg()
+        ws = self._workspace(cfg, b, h, w, device)[0]
+        slots = (C.c_size_t * 4)()
+        _lib.check(_lib.load().scf_decoder_workspace_slots(C.byref(cfg), b, h, w, slots), 'scf_decoder_workspace_slots')
+        return cfg, ws, [int(v) for v in slots]
+
+    def forward_prepared(self, ref_rotation, ref_translation, depth, internel_k, label, init_flow, invalid_flow_num):
+        """Same as ``forward`` when the feature maps, hidden state and context already sit in the workspace slots
+        (``native_slots``), written there by the encoders in the loop's own layout."""
+        ins = dict(ref_rotation=ref_rotation, ref_translation=ref_translation, depth=depth, internel_k=internel_k, init_flow=init_flow)
+        for k, t in ins.items():
+            if not t.is_cuda:
+                raise RuntimeError(f'SCFlowDecoder: {k} must be a CUDA tensor (scflow_b200 has no CPU path)')
+            ins[k] = t.detach().contiguous().float()
+        if label is None:
+            label = torch.zeros(depth.shape[0], dtype=torch.int64, device=depth.device)
+        ins['label'] = label.detach().to(torch.int64).contiguous()
+        b, h, w = depth.shape
+        iters = int(self.iters)
+        cfg = self._cfg()
+        dev = depth.device
+        arena = self._packed_arena(cfg)
+        ws = self._workspace(cfg, b, h, w, dev)
+        if self.use_cuda_graph:
+            outs = self._forward_graph(cfg, arena, ws, ins, b, h, w, iters, invalid_flow_num, cfg.rot_dim, dev)
+        else:
+            outs = self._alloc_outputs(iters, b, h, w, cfg.rot_dim, dev)
+            self._run(cfg, arena, ws, ins, outs, b, h, w, iters, invalid_flow_num)
+        order = ('flow_from_pose', 'flow_from_pred', 'rotation', 'translation', 'mask', 'delta_rotation', 'delta_translation')
+        return tuple([outs[k][i] for i in range(iters)] for k in order)
+
     def _forward_graph(self, cfg, arena, ws, ins, b, h, w, iters, invalid, rot_dim, dev):
-        key = (b, h, w, iters, float(invalid), int(cfg.precision), int(cfg.pose_head), arena.data_ptr(), ws[0].data_ptr(), len(ws))
+        key = (b, h, w, iters, float(invalid), int(cfg.precision), int(cfg.pose_head), arena.data_ptr(), ws[0].data_ptr(), len(ws),
+               'feat_render' in ins)
         entry = self._graphs.get(key)
         if entry is None:
             static_in = {k: torch.empty_like(v) for k, v in ins.items()}

@@ -120,7 +120,9 @@ class RAFTEncoder(BaseModule):
                 and self.norm_type in ('IN', 'BN') and self.in_channels == 3 and self.out_channels == 256
                 and self.scale == 1 / 8 and x.shape[-2] % 8 == 0 and x.shape[-1] % 8 == 0)
 
-    def _forward_native(self, x: torch.Tensor) -> torch.Tensor:
+    def _forward_native(self, x: torch.Tensor, ex: Optional['_lib.EncoderOut'] = None) -> Optional[torch.Tensor]:
+        """One scf_encoder_forward call; with ``ex`` the final convolution writes the consumer's buffers described by the
+        ``EncoderOut`` structure (scf_encoder_forward_ex) and nothing is returned."""
         lib = _lib.load()
         norm = _lib.ENC_NORM_IN if self.norm_type == 'IN' else _lib.ENC_NORM_BN
         mods = dict(self.named_modules())
@@ -148,6 +150,11 @@ class RAFTEncoder(BaseModule):
         if ws is None:
             self._ws = {key: torch.empty(lib.scf_encoder_workspace_bytes(n, h, w), device=x.device, dtype=torch.uint8)}
             ws = self._ws[key]
+        xin = x.detach().contiguous().float()
+        if ex is not None:
+            _lib.check(lib.scf_encoder_forward_ex(norm, _lib.ptr(arena), _lib.ptr(xin), n, h, w, C.byref(ex), _lib.ptr(ws), ws.numel(),
+                                                  _lib.stream_ptr()), 'scf_encoder_forward_ex')
+            return None
         out = torch.empty(n, self.out_channels, h // 8, w // 8, device=x.device, dtype=torch.float32)
         _lib.check(lib.scf_encoder_forward(norm, _lib.ptr(arena), _lib.ptr(x.detach().contiguous().float()), n, h, w,
                                            _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'scf_encoder_forward')

@@ -45,6 +45,8 @@ class SCFlowRefiner(BaseModule):
         self.loss_cfgs = dict(pose=pose_loss_cfg, flow=flow_loss_cfg, mask=mask_loss_cfg)
         # built lazily (the point-matching loss reads the model point clouds from mesh_path)
         self._loss_funcs = None
+        self.native_feature_path = True   # inference: encoders write the loop's inputs directly (no NCHW round trip)
+        self._zero_flow = None
         self.filter_invalid_flow = filter_invalid_flow
         self.test_by_flow = self.test_cfg.get('by_flow', False)
         self.test_iter_num = self.test_cfg.get('iters') if 'iters' in self.test_cfg else self.decoder.iters
@@ -78,9 +80,51 @@ class SCFlowRefiner(BaseModule):
         h_feat, cxt_feat = torch.split(cxt_feat, [self.h_channels, self.cxt_channels], dim=1)
         return render_feat, real_feat, torch.tanh(h_feat), torch.relu(cxt_feat)
 
+    def _get_pose_native(self, render_images, real_images, ref_rotation, ref_translation, depth, internel_k, label, init_flow):
+        """Inference fast path: the three encoder passes write the loop's inputs (pixel-major split-bf16 feature maps, tanh'ed
+        hidden state, relu'ed context) straight into the decoder workspace - no NCHW tensors between encoder and loop.
+        Returns None when the configuration does not allow it (the generic path below is used then)."""
+        from . import _lib
+        import ctypes as C
+        enc, ctx, dec = self.real_encoder, self.context, self.decoder
+        if (self.training or torch.is_grad_enabled() or enc is not self.render_encoder or real_images.shape != render_images.shape
+                or not (enc._native_ok(real_images) and ctx._native_ok(render_images)) or not hasattr(dec, 'native_slots')):
+            return None
+        b, _, h, w = real_images.shape
+        if tuple(depth.shape) != (b, h, w):
+            return None
+        prep = dec.native_slots(b, h, w, real_images.device)
+        if prep is None:
+            return None
+        _, ws, (s_feat, s_h, s_hf32, s_cxt) = prep
+        p8 = (h // 8) * (w // 8)
+        base = ws.data_ptr()
+        ex = _lib.EncoderOut()
+        ex.split = 256
+        ex.hl0, ex.plane0, ex.stride0, ex.act0 = base + s_feat, 2 * b * p8 * 256, 256, _lib.ACT['none']
+        enc._forward_native(torch.cat([real_images, render_images], dim=0), ex)      # samples [0,b) real, [b,2b) render
+        ex = _lib.EncoderOut()
+        ex.split = 128
+        ex.hl0, ex.plane0, ex.stride0, ex.act0 = base + s_h, b * p8 * 128, 128, _lib.ACT['tanh']
+        ex.f32_0, ex.f32_stride0 = base + s_hf32, 128
+        ex.hl1, ex.plane1, ex.stride1, ex.act1 = base + s_cxt, b * p8 * 128, 128, _lib.ACT['relu']
+        ctx._forward_native(render_images, ex)
+        return dec.forward_prepared(ref_rotation, ref_translation, depth, internel_k, label, init_flow, 0.)
+
     def get_pose(self, render_images, real_images, ref_rotation, ref_translation, depth, internel_k, label,
                  init_flow=None):
         """scflow_refiner.py:112-142: encoders -> decoder loop; returns the decoder's 7 lists."""
+        if self.native_feature_path:
+            if init_flow is None:
+                n, _, h, w = real_images.shape
+                key = (n, h, w, str(real_images.device))
+                if self._zero_flow is None or self._zero_flow[0] != key:
+                    self._zero_flow = (key, torch.zeros((n, 2, h, w), device=real_images.device, dtype=torch.float32))
+                zero = self._zero_flow[1]
+            outs = self._get_pose_native(render_images, real_images, ref_rotation, ref_translation, depth, internel_k, label,
+                                         zero if init_flow is None else init_flow)
+            if outs is not None:
+                return outs
         feat_render, feat_real, h_feat, cxt_feat = self.extract_feat(render_images, real_images)
         if init_flow is None:
             n, _, h, w = real_images.shape

@@ -217,3 +217,33 @@ def test_native_encoder_matches_oracle(norm):
         g2 = enc(x2.cuda()).cpu()
         r2 = O.raft_encoder(sd, x2, norm)
     assert float((g2 - r2).abs().max()) < 2e-4 * max(float(r2.abs().max()), 1.0)
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_native_feature_path_matches_generic_path_and_oracle(graph):
+    """get_pose with the encoders writing the loop's inputs straight into the decoder workspace (no NCHW round trip) against
+    the generic module-by-module path and against the CPU oracle (flow EPE < 1e-3 px, the stated tolerance)."""
+    import scflow_b200 as S
+    seed, b, iters = 4, 2, 3
+    model = S.build_refiner(scflow_model_cfg(iters=iters, precision=1, use_cuda_graph=graph))
+    sd = O.make_model_weights(seed)
+    model.load_state_dict(sd, strict=False)
+    model = model.cuda().eval()
+    scene = O.make_scene(seed, b)
+    c = {k: v.cuda() for k, v in scene.items()}
+    args = (c['render_images'], c['real_images'], c['ref_rotation'], c['ref_translation'], c['depth'], c['internel_k'], c['label'])
+    with torch.no_grad():
+        assert model.native_feature_path
+        for _ in range(2):                      # second call replays the captured graph when graph=True
+            fast = [[t.clone() for t in lst] for lst in model.get_pose(*args)]
+        model.native_feature_path = False
+        slow = model.get_pose(*args)
+        ref = O.get_pose(sd, scene['render_images'], scene['real_images'], scene['ref_rotation'], scene['ref_translation'],
+                         scene['depth'], scene['internel_k'], scene['label'], iters=iters)
+    for k in (0, 1):
+        for i in range(iters):
+            d = float((fast[k][i] - slow[k][i]).pow(2).sum(1).sqrt().mean())
+            e = float((fast[k][i].cpu() - ref[k][i]).pow(2).sum(1).sqrt().mean())
+            assert d < 1e-4, f'native vs generic path: list {k} iter {i} EPE {d:.3e}'
+            assert e < 1e-3, f'native path vs oracle: list {k} iter {i} EPE {e:.3e}'
+    assert float((fast[2][-1] - slow[2][-1]).abs().max()) < 1e-5
