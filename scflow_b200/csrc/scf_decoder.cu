@@ -5,6 +5,7 @@
 #include "scf_common.cuh"
 #include <cuda_bf16.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace scf {
 
@@ -30,6 +31,36 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ------------------------------------------------------------------ side stream for work off the critical path
+// The pose regressor is a chain of small, latency-bound kernels that leaves most SMs idle; the x8 up-sampling of the flow /
+// mask outputs of the same iteration does not depend on it, so it runs on a library-owned side stream (fork / join through
+// events: capturable into the caller's CUDA graph, still no host synchronisation).
+struct SideStream { cudaStream_t s; cudaEvent_t fork, join, join_a, join_b; int dev; bool ok; };
+static thread_local SideStream g_side = {nullptr, nullptr, nullptr, nullptr, nullptr, -1, false};
+// SCFLOW_DEC_OVERLAP bit mask: 1 = output up-sampling, 2 = flow branch of the motion encoder, 4 = mask encoder
+static int overlap_mask() {
+  static const int m = [] { const char* e = getenv("SCFLOW_DEC_OVERLAP"); return e ? atoi(e) : 7; }();
+  return m;
+}
+static SideStream* side_stream() {
+  if (!overlap_mask()) return nullptr;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (g_side.ok && g_side.dev == dev) return &g_side;
+  SideStream n = {nullptr, nullptr, nullptr, nullptr, nullptr, dev, false};
+  if (cudaStreamCreateWithFlags(&n.s, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n.join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n.join_a, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n.join_b, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  n.ok = true;
+  g_side = n;          // (a previous device's stream is deliberately leaked: one process drives one GPU)
+  return &g_side;
 }
 
 // ------------------------------------------------------------------ packed convolution table
@@ -410,6 +441,9 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
     SCF_TRY(check_launch("fill_kernel"));
   }
 
+  cudaStream_t lst = st;       // stream the conv / convtc helpers launch on (switched to the side stream for parallel branches)
+  SideStream* const side_all = cfg->pose_head && tcp ? side_stream() : nullptr;
+  const int ovl = side_all ? overlap_mask() : 0;
   auto conv = [&](int id, std::initializer_list<scf_conv_seg> segs, int Hi, int Wi, int Ho, int Wo, int stride, int act,
                   float* out, int out_stride, int out_coff, int epi = SCF_EPI_ACT, const float* aux0 = nullptr,
                   const float* aux1 = nullptr, float* out2 = nullptr, void* out_hl = nullptr, int out_hl_stride = 0) -> int {
@@ -426,7 +460,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
     d.out = out; d.out_stride = out_stride; d.out_coff = out_coff;
     d.aux0 = aux0; d.aux0_stride = 128; d.aux1 = aux1; d.aux1_stride = 128; d.out2 = out2; d.out2_stride = 128;
     d.out_hl = out_hl; d.out_hl_plane = (long long)BP * out_hl_stride; d.out_hl_stride = out_hl_stride; d.out_hl_coff = 0;
-    return conv2d_f32(d, st);
+    return conv2d_f32(d, lst);
   };
   // tensor-core convolution on split-bf16 buffers: segs = {plane base, channels per pixel, first channel, channels}
   struct SSeg { void* ptr; int stride, coff, nch; };
@@ -451,7 +485,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
     d.aux0 = aux0; d.aux0_stride = 128; d.aux1 = aux1; d.aux1_stride = 128;
     d.out2_hl = out2_hl; d.out2_hl_plane = (long long)BP * 128; d.out2_hl_stride = 128;
     if (pre) { d.pre = pre; d.pre_stride = pre_stride; d.bias = nullptr; }   // the bias is part of the precomputed map
-    return conv2d_tc(d, st);
+    return conv2d_tc(d, lst);
   };
 
   if (tcp) {
@@ -488,14 +522,25 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
     }
     if (tcp) {
       // ---------------- tensor-core path: activations live as split-bf16 planes
-      SCF_TRY(scf_split_copy(menc_flow, 2, 0, S(ws.s_motion), (long long)BP * 128, 128, 126, (long long)BP, 2, st));
+      // flow branch of the motion encoder (flow_net) on the side stream, parallel to the lookup + corr_net branch
+      if (ovl & 2) {
+        SCF_CUDA(cudaEventRecord(side_all->fork, st));
+        SCF_CUDA(cudaStreamWaitEvent(side_all->s, side_all->fork, 0));
+        lst = side_all->s;
+      }
+      SCF_TRY(scf_split_copy(menc_flow, 2, 0, S(ws.s_motion), (long long)BP * 128, 128, 126, (long long)BP, 2, lst));
+      SCF_TRY(im2col_x_split(menc_flow, 0, 2, 7, S(ws.s_t7), (long long)BP * 16, B, H8, W8, 1, lst));
+      SCF_TRY(convtc(PC_FLOW0, {{S(ws.s_t7), 16, 0, 16}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_f1), 128, 0));
+      SCF_TRY(convtc(PC_FLOW1, {{S(ws.s_f1), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_cf), 256, 192));
+      if (ovl & 2) {
+        SCF_CUDA(cudaEventRecord(side_all->join_a, side_all->s));
+        lst = st;
+      }
       SCF_TRY(scf_corr_lookup_split(levels, cfg->num_levels, cfg->radius, F(ws.flow8), cfg->mask_corr ? F(ws.maskprev) : nullptr,
                                     S(ws.s_corr), (long long)BP * ws.corr_stride_s, ws.corr_stride_s, B, H8, W8, st));
       SCF_TRY(convtc(PC_CORR0, {{S(ws.s_corr), ws.corr_stride_s, 0, ws.corr_stride_s}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_c1), 256, 0));
       SCF_TRY(convtc(PC_CORR1, {{S(ws.s_c1), 256, 0, 256}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_cf), 256, 0));
-      SCF_TRY(im2col_x_split(menc_flow, 0, 2, 7, S(ws.s_t7), (long long)BP * 16, B, H8, W8, 1, st));
-      SCF_TRY(convtc(PC_FLOW0, {{S(ws.s_t7), 16, 0, 16}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_f1), 128, 0));
-      SCF_TRY(convtc(PC_FLOW1, {{S(ws.s_f1), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_cf), 256, 192));
+      if (ovl & 2) SCF_CUDA(cudaStreamWaitEvent(st, side_all->join_a, 0));
       SCF_TRY(convtc(PC_OUT0, {{S(ws.s_cf), 256, 0, 256}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_motion), 128, 0));
       for (int pass = 0; pass < 2; ++pass) {
         SCF_TRY(convtc(pass == 0 ? PC_ZR0 : PC_ZR1, {{S(ws.s_h[pass]), 128, 0, 128}, {S(ws.s_motion), 128, 0, 128}},
@@ -510,12 +555,23 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       SCF_TRY(heads_predict(S(ws.s_hd), (long long)BP * 512, 512, 256, pw + a.pc[PC_FHP].w_off, a.pc[PC_FHP].ldw, pw + a.pc[PC_FHP].b_off,
                             pw + a.pc[PC_MHP].w_off, a.pc[PC_MHP].ldw, pw + a.pc[PC_MHP].b_off, F(ws.dflow), F(ws.mask8), B, H8, W8, st));
       if (cfg->pose_head) {
-        SCF_TRY(im2col_x_split(F(ws.dflow), 0, 2, 7, S(ws.s_t7), (long long)BP * 16, B, H8, W8, 1, st));
-        SCF_TRY(convtc(PC_DFE0, {{S(ws.s_t7), 16, 0, 16}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_df1), 128, 0));
-        SCF_TRY(convtc(PC_DFE1, {{S(ws.s_df1), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_df2), 64, 0));
+        // mask encoder on the side stream, parallel to the delta-flow encoder
+        if (ovl & 4) {
+          SCF_CUDA(cudaEventRecord(side_all->fork, st));
+          SCF_CUDA(cudaStreamWaitEvent(side_all->s, side_all->fork, 0));
+          lst = side_all->s;
+        }
         SCF_TRY(conv(PC_ME0, {{F(ws.mask8), 1, 0, 1}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, nullptr, 64, 0, SCF_EPI_ACT, nullptr, nullptr,
                      nullptr, S(ws.s_mf1), 64));
         SCF_TRY(convtc(PC_ME1, {{S(ws.s_mf1), 64, 0, 64}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_mf2), 32, 0));
+        if (ovl & 4) {
+          SCF_CUDA(cudaEventRecord(side_all->join_b, side_all->s));
+          lst = st;
+        }
+        SCF_TRY(im2col_x_split(F(ws.dflow), 0, 2, 7, S(ws.s_t7), (long long)BP * 16, B, H8, W8, 1, st));
+        SCF_TRY(convtc(PC_DFE0, {{S(ws.s_t7), 16, 0, 16}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_df1), 128, 0));
+        SCF_TRY(convtc(PC_DFE1, {{S(ws.s_df1), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_df2), 64, 0));
+        if (ovl & 4) SCF_CUDA(cudaStreamWaitEvent(st, side_all->join_b, 0));
       }
     } else {
       // lookup                                                              (:198-201)
@@ -552,6 +608,18 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
         SCF_TRY(conv(PC_ME1, {{F(ws.mf1), 64, 0, 64}}, H8, W8, H8, W8, 1, SCF_ACT_RELU, F(ws.mf2), 32, 0));
       }
     }
+    // flow_pred = 8 * up8(flow8 + dflow) ; mask_up = up8(mask)            (:222-227)  - outputs only: off the critical path
+    SideStream* side = (cfg->pose_head && (overlap_mask() & 1)) ? side_stream() : nullptr;
+    cudaStream_t up_st = st;
+    if (side) {
+      SCF_CUDA(cudaEventRecord(side->fork, st));
+      SCF_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+      up_st = side->s;
+    }
+    SCF_TRY(scf_resize_bilinear(F(ws.flow8), F(ws.dflow), (long long)P * 2, 1, (long long)W8 * 2, 2, H8, W8, flow_pred_k, 2 * HW,
+                                HW, W, 1, H, W, B, 2, (float)scale, up_st));
+    SCF_TRY(scf_resize_bilinear(F(ws.mask8), nullptr, P, 0, W8, 1, H8, W8, mask_k, HW, 0, W, 1, H, W, B, 1, 1.f, up_st));
+    if (side) SCF_CUDA(cudaEventRecord(side->join, side->s));
     float* h = F(ws.h[0]);
     if (cfg->pose_head) {
       // pose regressor                                                    (:218-219, pose_head.py:201-211)
@@ -590,14 +658,11 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       identity_delta_kernel<<<cdiv(B, 64), 64, 0, st>>>(drot_k, dtrs_k, B, cfg->rot_dim);
       SCF_TRY(check_launch("identity_delta_kernel"));
     }
-    // flow_pred = 8 * up8(flow8 + dflow) ; mask_up = up8(mask)            (:222-227)
-    SCF_TRY(scf_resize_bilinear(F(ws.flow8), F(ws.dflow), (long long)P * 2, 1, (long long)W8 * 2, 2, H8, W8, flow_pred_k, 2 * HW,
-                                HW, W, 1, H, W, B, 2, (float)scale, st));
-    SCF_TRY(scf_resize_bilinear(F(ws.mask8), nullptr, P, 0, W8, 1, H8, W8, mask_k, HW, 0, W, 1, H, W, B, 1, 1.f, st));
     // pose update + pose-induced flow                                     (:230-243)
     SCF_TRY(scf_pose_update(drot_k, dtrs_k, rot_prev, trs_prev, rot_k, trs_k, B, st));
     SCF_TRY(scf_reproject(F(ws.pts4), io->internel_k, rot_k, trs_k, io->invalid_flow_num, flow_pose_k, B, H, W, st));
     flow_full = flow_pose_k;
+    if (side) SCF_CUDA(cudaStreamWaitEvent(st, side->join, 0));    // flow8 / dflow / mask8 are rewritten by the next iteration
     if (cfg->mask_corr || cfg->mask_flow)
       SCF_CUDA(cudaMemcpyAsync(F(ws.maskprev), F(ws.mask8), BP * 4, cudaMemcpyDeviceToDevice, st));
   }
