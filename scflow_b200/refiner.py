@@ -5,6 +5,7 @@ of the hot path.  The renderer (pytorch3d), the losses and the OpenCV pose re-ma
 path; the refiner accepts their config keys so the reference's config dicts build unchanged, takes an injected
 ``renderer`` callable, and raises a clear error where an out-of-scope component would be needed.
 """
+import os
 from typing import Callable, Dict, Optional, Tuple, Union
 
 import torch
@@ -47,6 +48,8 @@ class SCFlowRefiner(BaseModule):
         self._loss_funcs = None
         self.native_feature_path = True   # inference: encoders write the loop's inputs directly (no NCHW round trip)
         self._zero_flow = None
+        self.overlap_encoders = os.environ.get('SCFLOW_ENC_OVERLAP', '1') != '0'
+        self._side_stream = None
         self.filter_invalid_flow = filter_invalid_flow
         self.test_by_flow = self.test_cfg.get('by_flow', False)
         self.test_iter_num = self.test_cfg.get('iters') if 'iters' in self.test_cfg else self.decoder.iters
@@ -102,13 +105,26 @@ class SCFlowRefiner(BaseModule):
         ex = _lib.EncoderOut()
         ex.split = 256
         ex.hl0, ex.plane0, ex.stride0, ex.act0 = base + s_feat, 2 * b * p8 * 256, 256, _lib.ACT['none']
-        enc._forward_native(torch.cat([real_images, render_images], dim=0), ex)      # samples [0,b) real, [b,2b) render
-        ex = _lib.EncoderOut()
-        ex.split = 128
-        ex.hl0, ex.plane0, ex.stride0, ex.act0 = base + s_h, b * p8 * 128, 128, _lib.ACT['tanh']
-        ex.f32_0, ex.f32_stride0 = base + s_hf32, 128
-        ex.hl1, ex.plane1, ex.stride1, ex.act1 = base + s_cxt, b * p8 * 128, 128, _lib.ACT['relu']
-        ctx._forward_native(render_images, ex)
+        ex2 = _lib.EncoderOut()
+        ex2.split = 128
+        ex2.hl0, ex2.plane0, ex2.stride0, ex2.act0 = base + s_h, b * p8 * 128, 128, _lib.ACT['tanh']
+        ex2.f32_0, ex2.f32_stride0 = base + s_hf32, 128
+        ex2.hl1, ex2.plane1, ex2.stride1, ex2.act1 = base + s_cxt, b * p8 * 128, 128, _lib.ACT['relu']
+        if self.overlap_encoders:
+            # the context encoder is independent of the feature encoder: run it on a side stream so that its tensor-core
+            # convolutions fill the feature encoder's HBM-bound InstanceNorm passes (and vice versa)
+            cur = torch.cuda.current_stream(real_images.device)
+            if self._side_stream is None or self._side_stream.device != real_images.device:
+                self._side_stream = torch.cuda.Stream(device=real_images.device)
+            side = self._side_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                ctx._forward_native(render_images, ex2)
+            enc._forward_native(torch.cat([real_images, render_images], dim=0), ex)  # samples [0,b) real, [b,2b) render
+            cur.wait_stream(side)
+        else:
+            enc._forward_native(torch.cat([real_images, render_images], dim=0), ex)  # samples [0,b) real, [b,2b) render
+            ctx._forward_native(render_images, ex2)
         return dec.forward_prepared(ref_rotation, ref_translation, depth, internel_k, label, init_flow, 0.)
 
     def get_pose(self, render_images, real_images, ref_rotation, ref_translation, depth, internel_k, label,
