@@ -39,48 +39,62 @@ __global__ void __launch_bounds__(256) group_norm_relu_kernel(float* __restrict_
   }
 }
 
-// Fast path for C == 4*G (one float4 = one group; the pose head: C=128, G=32): one 256-thread block per sample,
-// thread t owns group t%32 on pixels t/32 + 8j -> fully coalesced 512 B rows; two-pass statistics; optional
-// split-bf16 copy of the result for a following tensor-core convolution.
+// Fast path for C == 4*G (one float4 = one group; the pose head: C=128, G=32): grid (B, 4), a 256-thread block owns 8
+// groups of one sample: thread t = (group t%8, pixel lane t/8), pixels lane + 32j -> 128 B contiguous per pixel; the
+// sample's values stay in registers between the three steps (mean, variance about the mean, normalise), so the map is
+// read once.  Optional split-bf16 copy of the result for a following tensor-core convolution.  HW <= 32*GN_MAXP.
+constexpr int GN_MAXP = 8;
 __global__ void __launch_bounds__(256) group_norm_relu_c4_kernel(float* __restrict__ x, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, int HW, float eps,
                                                                  __nv_bfloat16* __restrict__ out_hl, long long plane) {
-  __shared__ float red[8][33];
-  __shared__ float stat[2][32];
-  const int b = blockIdx.x, g = threadIdx.x & 31, r = threadIdx.x >> 5;
+  __shared__ float red[32][9];
+  __shared__ float stat[8];
+  const int b = blockIdx.x, gl = threadIdx.x & 7, r = threadIdx.x >> 3;
+  const int g = blockIdx.y * 8 + gl;
   const int C = 128;
   float4* base = reinterpret_cast<float4*>(x + (long long)b * HW * C) + g;
+  float4 v[GN_MAXP];
   float s = 0.f;
-  for (int p = r; p < HW; p += 8) { const float4 v = base[(long long)p * 32]; s += (v.x + v.y) + (v.z + v.w); }
-  red[r][g] = s;
+#pragma unroll
+  for (int j = 0; j < GN_MAXP; ++j) {
+    const int p = r + 32 * j;
+    v[j] = p < HW ? base[(long long)p * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  red[r][gl] = s;
   __syncthreads();
-  if (r == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i][g]; stat[0][g] = t / (float)(HW * 4); }
+  if (r == 0) { float t = 0.f; for (int i = 0; i < 32; ++i) t += red[i][gl]; stat[gl] = t / (float)(HW * 4); }
   __syncthreads();
-  const float mean = stat[0][g];
+  const float mean = stat[gl];
   float q = 0.f;
-  for (int p = r; p < HW; p += 8) {
-    const float4 v = base[(long long)p * 32];
-    const float a = v.x - mean, bq = v.y - mean, c = v.z - mean, d = v.w - mean;
-    q += (a * a + bq * bq) + (c * c + d * d);
+#pragma unroll
+  for (int j = 0; j < GN_MAXP; ++j) {
+    if (r + 32 * j < HW) {
+      const float a = v[j].x - mean, bq = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += (a * a + bq * bq) + (c * c + d * d);
+    }
   }
   __syncthreads();
-  red[r][g] = q;
+  red[r][gl] = q;
   __syncthreads();
-  if (r == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i][g]; stat[1][g] = rsqrtf(t / (float)(HW * 4) + eps); }
+  if (r == 0) { float t = 0.f; for (int i = 0; i < 32; ++i) t += red[i][gl]; stat[gl] = rsqrtf(t / (float)(HW * 4) + eps); }
   __syncthreads();
-  const float rstd = stat[1][g];
+  const float rstd = stat[gl];
   const float4 ga = reinterpret_cast<const float4*>(gamma)[g], be = reinterpret_cast<const float4*>(beta)[g];
-  for (int p = r; p < HW; p += 8) {
-    float4 v = base[(long long)p * 32];
-    v.x = fmaxf((v.x - mean) * rstd * ga.x + be.x, 0.f);
-    v.y = fmaxf((v.y - mean) * rstd * ga.y + be.y, 0.f);
-    v.z = fmaxf((v.z - mean) * rstd * ga.z + be.z, 0.f);
-    v.w = fmaxf((v.w - mean) * rstd * ga.w + be.w, 0.f);
-    base[(long long)p * 32] = v;
+#pragma unroll
+  for (int j = 0; j < GN_MAXP; ++j) {
+    const int p = r + 32 * j;
+    if (p >= HW) continue;
+    float4 o4;
+    o4.x = fmaxf((v[j].x - mean) * rstd * ga.x + be.x, 0.f);
+    o4.y = fmaxf((v[j].y - mean) * rstd * ga.y + be.y, 0.f);
+    o4.z = fmaxf((v[j].z - mean) * rstd * ga.z + be.z, 0.f);
+    o4.w = fmaxf((v[j].w - mean) * rstd * ga.w + be.w, 0.f);
+    base[(long long)p * 32] = o4;
     if (out_hl) {
       __nv_bfloat16 hi[4], lo[4];
-      tc::split_bf16(v.x, hi[0], lo[0]); tc::split_bf16(v.y, hi[1], lo[1]);
-      tc::split_bf16(v.z, hi[2], lo[2]); tc::split_bf16(v.w, hi[3], lo[3]);
+      tc::split_bf16(o4.x, hi[0], lo[0]); tc::split_bf16(o4.y, hi[1], lo[1]);
+      tc::split_bf16(o4.z, hi[2], lo[2]); tc::split_bf16(o4.w, hi[3], lo[3]);
       __nv_bfloat16* o = out_hl + ((long long)b * HW + p) * C + g * 4;
       *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
       *reinterpret_cast<uint2*>(o + plane) = *reinterpret_cast<const uint2*>(lo);
@@ -224,7 +238,13 @@ int scf_group_norm_relu_split(float* x, const float* gamma, const float* beta, i
   SCF_REQUIRE(C == 128 && num_groups == 32, SCF_ERR_UNSUPPORTED, "scf_group_norm_relu_split: C=128, 32 groups only");
   SCF_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(gamma) % 16 == 0 &&
                   reinterpret_cast<uintptr_t>(beta) % 16 == 0, SCF_ERR_ALIGN, "scf_group_norm_relu_split: 16B alignment required");
-  scf::group_norm_relu_c4_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, HW, eps,
+  if (HW > 32 * scf::GN_MAXP) {     // large maps: the generic one-warp-per-(sample, group) kernel (no split copy available)
+    SCF_REQUIRE(out_hl == nullptr, SCF_ERR_UNSUPPORTED, "scf_group_norm_relu_split: maps above %d pixels are not supported", 32 * scf::GN_MAXP);
+    const int warps = B * num_groups;
+    scf::group_norm_relu_kernel<<<scf::cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, B, HW, C, num_groups, eps);
+    return scf::check_launch("group_norm_relu_kernel");
+  }
+  scf::group_norm_relu_c4_kernel<<<dim3(B, 4), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, HW, eps,
                                                                      reinterpret_cast<__nv_bfloat16*>(out_hl), plane_stride);
   return scf::check_launch("group_norm_relu_c4_kernel");
 }
