@@ -309,7 +309,9 @@ def run_ours(args):
             'clocks': clocks.summary(),
             'roofline': roof,
             'cpu_baseline': cpu,
-            'breakdown': {'encoders_ms': enc_ms, 'decoder_ms': dec_ms, 'per_iter_ms': per_iter_ms,
+            'breakdown': {'note': 'module-by-module on the generic API path (NCHW feature maps between encoder and decoder, no '
+                                  'encoder overlap); the step itself uses the fused path, so encoders + decoder > ms_per_step',
+                          'encoders_ms': enc_ms, 'decoder_ms': dec_ms, 'per_iter_ms': per_iter_ms,
                           'decoder_pairs_per_s': world * b / (dec_ms * 1e-3), 'launches_per_step': int(launches_per_step)},
         }
         print(json.dumps(line))
