@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(256) instnorm_finalize_tiles_kernel(const floa
 // owns 8 consecutive channels (two 16 B loads per input, one 16 B store per bf16 plane), two pixels in flight per iteration.
 __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ stat,
                                                              const float* __restrict__ res, const float* __restrict__ res_stat,
+                                                             const __nv_bfloat16* __restrict__ res_hl,
                                                              int relu, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hl,
                                                              long long plane, int HW, int C, long long total8) {
   const int c8n = C >> 3;
@@ -190,6 +191,18 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __rest
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) vv[i] += rr[i];
+    } else if (res_hl) {
+      // identity branch of a BasicBlock read from the block input's split-bf16 planes (hi + lo carries 16 mantissa bits), so no
+      // separate fp32 copy of every block output has to be written and read back
+      const uint4 h4 = __ldcs(reinterpret_cast<const uint4*>(res_hl + idx * 8)), l4 = __ldcs(reinterpret_cast<const uint4*>(res_hl + plane + idx * 8));
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h4);
+      const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 a = __bfloat1622float2(hp[i]), b2 = __bfloat1622float2(lp[i]);
+        vv[2 * i] += a.x + b2.x;
+        vv[2 * i + 1] += a.y + b2.y;
+      }
     }
     if (relu) {
 #pragma unroll
@@ -331,10 +344,11 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
     return check_launch("instnorm_finalize_kernel");
   };
   auto in_apply = [&](const float* x, const float* stat, const float* res, const float* res_stat, int relu, float* of32, void* ohl,
-                      long long pixels, int hw, int C) -> int {
+                      long long pixels, int hw, int C, const void* res_hl = nullptr) -> int {
     const long long total8 = pixels * C / 8;
     instnorm_apply_kernel<<<cdiv(total8, 256) < 148 * 16 ? cdiv(total8, 256) : 148 * 16, 256, 0, st>>>(
-        x, stat, res, res_stat, relu, of32, reinterpret_cast<__nv_bfloat16*>(ohl), pixels * C, hw, C, total8);
+        x, stat, res, res_stat, reinterpret_cast<const __nv_bfloat16*>(res_hl), relu, of32, reinterpret_cast<__nv_bfloat16*>(ohl),
+        pixels * C, hw, C, total8);
     return check_launch("instnorm_apply_kernel");
   };
   // tensor-core conv unit u on split input (hin x win), stride from the table
@@ -388,7 +402,7 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
       SCF_TRY(stem_conv(SCF_ACT_NONE, F(ws.raw), nullptr, nullptr));
       SCF_TRY(in_stats(F(ws.raw), F(ws.stat), h * w, 64));
     }
-    SCF_TRY(in_apply(F(ws.raw), F(ws.stat), nullptr, nullptr, 1, F(ws.xf[0]), S(ws.xs[0]), npix, h * w, 64));
+    SCF_TRY(in_apply(F(ws.raw), F(ws.stat), nullptr, nullptr, 1, nullptr, S(ws.xs[0]), npix, h * w, 64));
   }
   // ---- residual stages: units (c1, c2, ds) per block
   const int blocks[6][3] = {{1, 2, -1}, {3, 4, -1}, {5, 6, 7}, {8, 9, -1}, {10, 11, 12}, {13, 14, -1}};
@@ -404,9 +418,9 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
       SCF_TRY(tcconv_stats(u2, S(ws.ts), ho, wo, F(ws.raw), F(ws.stat)));
       if (ud >= 0) {
         SCF_TRY(tcconv_stats(ud, S(ws.xs[cur]), h, w, F(ws.raw2), F(ws.stat2)));
-        SCF_TRY(in_apply(F(ws.raw), F(ws.stat), F(ws.raw2), F(ws.stat2), 1, F(ws.xf[nxt]), S(ws.xs[nxt]), opix, ho * wo, C));
+        SCF_TRY(in_apply(F(ws.raw), F(ws.stat), F(ws.raw2), F(ws.stat2), 1, nullptr, S(ws.xs[nxt]), opix, ho * wo, C));
       } else {
-        SCF_TRY(in_apply(F(ws.raw), F(ws.stat), F(ws.xf[cur]), nullptr, 1, F(ws.xf[nxt]), S(ws.xs[nxt]), opix, ho * wo, C));
+        SCF_TRY(in_apply(F(ws.raw), F(ws.stat), nullptr, nullptr, 1, nullptr, S(ws.xs[nxt]), opix, ho * wo, C, S(ws.xs[cur])));
       }
     } else {   // eval-mode BatchNorm folded into the convolutions: everything happens in the conv epilogues
       SCF_TRY(tcconv(u1, S(ws.xs[cur]), h, w, SCF_ACT_RELU, nullptr, S(ws.ts), nullptr));
