@@ -1,7 +1,8 @@
 // RAFT 'Basic' feature / context encoder (models/encoder/raft_encoder.py:286-314, models/backbone/resnet.py:14-94,
-// 678-773) on the library's kernels: 7x7 stem on the fp32 CUDA-core conv (Cin=3), every 3x3 / 1x1 convolution on the
-// tcgen05 split-bf16 kernel (stride 2 through TMA element strides), InstanceNorm as deterministic two-stage
-// statistics + one fused normalise/ReLU/residual pass, eval-mode BatchNorm folded into the packed weights.
+// 678-773) on the library's kernels: the 7x7 stride-2 stem as an x-folded 7x1 tcgen05 convolution, every 3x3 / 1x1
+// convolution on the tcgen05 split-bf16 kernel (stride 2 through TMA element strides), InstanceNorm as deterministic
+// per-tile statistics emitted by the convolution's epilogue + one fused normalise/ReLU/residual pass, eval-mode BatchNorm
+// folded into the packed weights.
 // This is SURVEY.md §8(f) rank 1: the component feeding the refinement loop.
 #include "scf_common.cuh"
 #include "scf_tc.cuh"
@@ -65,17 +66,6 @@ __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restr
   const float s = g ? g[o] * rsqrtf(var[o] + eps) : 1.f;
   for (int i = threadIdx.x; i < per_o; i += blockDim.x) wo[(long long)o * per_o + i] = w[(long long)o * per_o + i] * s;
   if (threadIdx.x == 0) bo[o] = g ? ((b ? b[o] : 0.f) - mean[o]) * s + beta[o] : (b ? b[o] : 0.f);
-}
-
-// NCHW fp32 image -> NHWC fp32 (C=3)
-__global__ void image_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, long long total) {
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C);
-    const long long r = idx / C;
-    const int p = (int)(r % HW);
-    const long long n = r / HW;
-    dst[idx] = src[(n * C + c) * HW + p];
-  }
 }
 
 // ---- InstanceNorm, stage 1: per (image, pixel-slice) partial sums of x and x^2 for every channel (deterministic)
