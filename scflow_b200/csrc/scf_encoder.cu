@@ -117,18 +117,18 @@ __global__ void instnorm_finalize_kernel(const float* __restrict__ part, float* 
 // [N * tiles_per_img][4 warps][2][C]; one block per image, deterministic double-precision combine
 __global__ void __launch_bounds__(256) instnorm_finalize_tiles_kernel(const float* __restrict__ part, float* __restrict__ stat,
                                                                       int HW, int C, float eps, int tiles_per_img) {
-  // grid (N, C/32): thread = (channel c of 32, row group g of 8); 8 independent loads in flight per thread
+  // grid (N, C/8): thread = (channel c of 8, row group g of 32); 8 independent loads in flight per thread; fixed combine order
   __shared__ double ss[256], sq[256];
   const int n = blockIdx.x;
-  const int c = blockIdx.y * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+  const int cl = threadIdx.x & 7, c = blockIdx.y * 8 + cl, g = threadIdx.x >> 3;
   const int rows = tiles_per_img * 4;
   const float* base = part + (long long)n * rows * 2 * C + c;
   double s = 0., q = 0.;
-  for (int r0 = g; r0 < rows; r0 += 64) {
+  for (int r0 = g; r0 < rows; r0 += 256) {
     float a[8], b[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int r = r0 + 8 * j;
+      const int r = r0 + 32 * j;
       a[j] = r < rows ? base[(long long)r * 2 * C] : 0.f;
       b[j] = r < rows ? base[(long long)r * 2 * C + C] : 0.f;
     }
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) instnorm_finalize_tiles_kernel(const floa
   ss[threadIdx.x] = s; sq[threadIdx.x] = q;
   __syncthreads();
   if (g == 0) {
-    for (int i = 1; i < 8; ++i) { s += ss[i * 32 + (threadIdx.x & 31)]; q += sq[i * 32 + (threadIdx.x & 31)]; }
+    for (int i = 1; i < 32; ++i) { s += ss[i * 8 + cl]; q += sq[i * 8 + cl]; }
     const double mean = s / HW;
     double var = q / HW - mean * mean;
     if (var < 0.) var = 0.;
@@ -370,7 +370,7 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
       SCF_TRY(tcconv(u, in_s, hin, win, SCF_ACT_NONE, raw, nullptr, nullptr, F(ws.part)));
       conv2d_tc_last_tiles(nullptr, &per_img);      // the tiling the launch actually used (halo mode: 8 x 16 pixel tiles)
       SCF_REQUIRE(per_img > 0, SCF_ERR_UNSUPPORTED, "scf_encoder_forward: statistics need one sample per tile");
-      instnorm_finalize_tiles_kernel<<<dim3(N, e.cout / 32), 256, 0, st>>>(F(ws.part), stat, ho * wo, e.cout, 1e-5f, per_img);
+      instnorm_finalize_tiles_kernel<<<dim3(N, e.cout / 8), 256, 0, st>>>(F(ws.part), stat, ho * wo, e.cout, 1e-5f, per_img);
       return check_launch("instnorm_finalize_tiles_kernel");
     }
     SCF_TRY(tcconv(u, in_s, hin, win, SCF_ACT_NONE, raw, nullptr, nullptr));
@@ -386,7 +386,7 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
     if (per_img > 0) {
       SCF_TRY(stem_conv(SCF_ACT_NONE, F(ws.raw), nullptr, F(ws.part)));
       conv2d_tc_last_tiles(nullptr, &per_img);
-      instnorm_finalize_tiles_kernel<<<dim3(N, 2), 256, 0, st>>>(F(ws.part), F(ws.stat), h * w, 64, 1e-5f, per_img);
+      instnorm_finalize_tiles_kernel<<<dim3(N, 8), 256, 0, st>>>(F(ws.part), F(ws.stat), h * w, 64, 1e-5f, per_img);
       SCF_TRY(check_launch("instnorm_finalize_tiles_kernel"));
     } else {
       SCF_TRY(stem_conv(SCF_ACT_NONE, F(ws.raw), nullptr, nullptr));
