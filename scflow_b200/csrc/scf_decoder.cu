@@ -552,6 +552,11 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       }
       SCF_TRY(convtc(PC_HEADS, {{S(ws.s_h[0]), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_hd), 512, 0));
       // both predict layers (3x3 256->2, 1x1 256->1 + sigmoid) in one streaming fp32 kernel over the split hidden map
+      static const bool predict_tc = [] { const char* e = getenv("SCFLOW_PREDICT_TC"); return e ? atoi(e) != 0 : false; }();
+      if (predict_tc) {   // the two predict layers as tensor-core convolutions (N padded to 16; halo mode for the 3x3)
+        SCF_TRY(convtc(PC_FHP, {{S(ws.s_hd), 512, 0, 256}}, SCF_ACT_NONE, F(ws.dflow), 2, nullptr, 0, 0));
+        SCF_TRY(convtc(PC_MHP, {{S(ws.s_hd), 512, 256, 256}}, SCF_ACT_SIGMOID, F(ws.mask8), 1, nullptr, 0, 0));
+      } else
       SCF_TRY(heads_predict(S(ws.s_hd), (long long)BP * 512, 512, 256, pw + a.pc[PC_FHP].w_off, a.pc[PC_FHP].ldw, pw + a.pc[PC_FHP].b_off,
                             pw + a.pc[PC_MHP].w_off, a.pc[PC_MHP].ldw, pw + a.pc[PC_MHP].b_off, F(ws.dflow), F(ws.mask8), B, H8, W8, st));
       if (cfg->pose_head) {

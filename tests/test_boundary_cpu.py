@@ -118,3 +118,26 @@ def test_shard_helpers():
     s1 = D.shard_batch(data, 1, 2)
     assert s1['labels'].tolist() == [9, 4] and s1['depth'][:, 0, 0].tolist() == [3., 4.] and s1['tag'] == 'x'
     assert D.shard_batch(data, 1, 2, keep_global_label0=False)['labels'].tolist() == [3, 4]
+
+
+def test_host_only_layout_queries():
+    """Workspace slots (encoder -> loop hand-over), tiling and loss-scratch queries are host-only and consistent."""
+    lib = _lib.load()
+    cfg = _lib.DecoderCfg(4, 4, 21, 6, 0, 0, 1, 1)
+    total = lib.scf_decoder_workspace_bytes(ctypes.byref(cfg), 32, 256, 256)
+    slots = (ctypes.c_size_t * 4)()
+    assert lib.scf_decoder_workspace_slots(ctypes.byref(cfg), 32, 256, 256, slots) == 0
+    feat, sh, hf32, scxt = [int(v) for v in slots]
+    bp = 32 * 1024
+    sizes = [2 * 2 * bp * 256 * 2, 2 * bp * 128 * 2, bp * 128 * 4, 2 * bp * 128 * 2]
+    spans = sorted(zip([feat, sh, hf32, scxt], sizes))
+    for (o, n), (o2, _) in zip(spans, spans[1:]):
+        assert o % 256 == 0 and o + n <= o2, 'slots must be aligned and must not overlap'
+    assert spans[-1][0] + spans[-1][1] <= total
+    cfg0 = _lib.DecoderCfg(4, 4, 21, 6, 0, 0, 1, 0)             # the fp32 path has no native slots
+    assert lib.scf_decoder_workspace_slots(ctypes.byref(cfg0), 32, 256, 256, slots) != 0
+    per = ctypes.c_int(0)
+    assert lib.scf_conv2d_tc_tiles(32, 32, 32, ctypes.byref(per)) == 256 and per.value == 8
+    assert lib.scf_conv2d_tc_tiles(2, 8, 8, ctypes.byref(per)) == 1 and per.value == 0      # a tile spans both samples
+    assert lib.scf_refiner_loss_scratch_bytes(8, 32) >= 8 * 296 * 3 * 8 + 8 * 32 * 4
+    assert lib.scf_refiner_loss_scratch_bytes(0, 32) == 0
