@@ -282,7 +282,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t bias0 = smem_base + 1024 + EW * 32 * TC_STAGE_ROW;
   const uint32_t tiles0 = smem_base + tc_header(EW);
   const uint32_t b_plane = (uint32_t)(PAIR ? p.BN / 2 : p.BN) * 128u;    // weight rows held by this CTA
-  const uint32_t stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;
+  // pair + stacked-N: region X = one whole weight plane (hi in the leader, lo in the peer: together the stacked [W_hi; W_lo]
+  // operand of the N = 2*BN MMA), region Y = this CTA's half of W_hi (the B operand of the A_lo * W_hi MMA)
+  const bool pstack = PAIR && p.stackn;
+  const uint32_t stage_bytes = 2 * TC_A_PLANE + (pstack ? 3 * b_plane : 2 * b_plane);
   const uint32_t a_plane = (uint32_t)(p.PW * p.PH) * 128u;                        // halo mode: one bf16 plane of the halo tile
   const uint32_t a_stage = (2u * a_plane + 1023u) & ~1023u;
   const uint32_t bring0 = tiles0 + (uint32_t)p.a_stages * a_stage;                // halo mode: start of the weight ring
@@ -388,8 +391,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const uint32_t lfull = mapa_shared(full, 0);
                 if (crank == 0) mbar_arrive_expect_tx(full, 2 * stage_bytes);
                 tma_load_5d_2cta(a_dst, tm, lfull, cc * TC_BK, cx, cy, b, 0);
-                tma_load_4d_2cta(w_dst, &tmW, lfull, wk, n0 + crank * w_rows, wt, 0);
-                tma_load_4d_2cta(w_dst + b_plane, &tmW, lfull, wk, n0 + crank * w_rows, wt, 1);
+                if (pstack) {
+                  tma_load_4d_2cta(w_dst, &tmW, lfull, wk, n0, wt, crank);                          // X: plane `crank`, rows [0, BN/2)
+                  tma_load_4d_2cta(w_dst + b_plane, &tmW, lfull, wk, n0 + w_rows, wt, crank);       //    ... rows [BN/2, BN)
+                  tma_load_4d_2cta(w_dst + 2 * b_plane, &tmW, lfull, wk, n0 + crank * w_rows, wt, 0);   // Y: my half of W_hi
+                } else {
+                  tma_load_4d_2cta(w_dst, &tmW, lfull, wk, n0 + crank * w_rows, wt, 0);
+                  tma_load_4d_2cta(w_dst + b_plane, &tmW, lfull, wk, n0 + crank * w_rows, wt, 1);
+                }
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 continue;
               }
@@ -412,7 +421,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0 && !(PAIR && crank != 0)) {
       // ================= MMA issuer (pair mode: the leader CTA issues for both)
-      const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, p.BN), idesc2 = make_idesc_bf16(TC_BM, 2 * p.BN);
+      const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, p.BN),
+                     idesc2 = make_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, 2 * p.BN);
       int stage = 0, hsa = 0;
       uint32_t phase = 0, hpa = 0;
       int it = 0;
@@ -484,7 +494,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const uint64_t a_hi = make_smem_desc_sw128(a_addr, 1024), a_lo = make_smem_desc_sw128(a_addr + TC_A_PLANE, 1024);
               const uint64_t b_hi = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE, 1024);
               const uint64_t b_lo = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + b_plane, 1024);
-              if (PAIR) {
+              if (PAIR && pstack) {
+                const uint64_t b_y = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + 2 * b_plane, 1024);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                  if (k < ks) {
+                    const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                    umma_bf16_2cta(d_tmem, a_hi + ko, b_hi + ko, idesc2, (c > 0 || k > 0) ? 1u : 0u);   // A_hi * [W_hi; W_lo]
+                    umma_bf16_2cta(d_tmem, a_lo + ko, b_y + ko, idesc, 1u);                             // A_lo * W_hi
+                  }
+                }
+              } else if (PAIR) {
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k) {
                   if (k < ks) {
@@ -1101,11 +1121,12 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
         (!d.w_batched || (p.tiles_x * p.tiles_y) % 2 == 0)) {
       p.pair = 1;
       ew = 8;
-      stage_bytes = 2 * (int)TC_A_PLANE + p.BN * 128;           // A (hi, lo) + BN/2 weight rows (hi, lo)
+      // BN > 128: three MMAs of N = BN, each CTA holds BN/2 rows of both weight planes.  BN <= 128 (stacked-N): the leader
+      // holds W_hi, the peer W_lo (= the two halves of the stacked [W_hi; W_lo] operand) plus half of W_hi each
+      stage_bytes = 2 * (int)TC_A_PLANE + (p.stackn ? 3 : 2) * (p.BN / 2) * 128;
       p.stages = (232448 - 1024 - tc_header(ew)) / stage_bytes;
       if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
-      p.stackn = 0;                                              // three MMAs of N = BN (the stacked-N trick splits B unevenly)
-      p.acc_cols = p.BN;
+      p.acc_cols = p.stackn ? 2 * p.BN : p.BN;
       p.tmem_cols = 32;
       while (p.tmem_cols < 2 * p.acc_cols) p.tmem_cols <<= 1;
     }
