@@ -55,6 +55,8 @@ struct TcParams {
   // Two instructions per k-step instead of three (less shared-memory operand traffic per FLOP); the epilogue adds
   // the two halves.
   int stackn;
+  int splitacc;                  // experiment (SCFLOW_TC_SPLITACC, single-CTA stacked-N): the A_lo*W_hi MMA accumulates into its own
+                                 // TMEM columns [2BN, 3BN) instead of [0, BN), so consecutive MMAs never depend on each other
   int fast_epi;                  // every global access of the epilogue is 16 B aligned: use the coalesced staged path
   int direct_st;                 // ... and every 32-column output block is 32 B aligned: 256-bit row stores, no staging
   const float* bias; float scale; int epi, act;
@@ -277,7 +279,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // header: [0,256) barriers + TMEM pointer | [1024, ..) epilogue staging, 2560 B per epilogue warp | two 1 KB bias buffers ;
   // then the operand ring: `stages` x {A hi, A lo, W hi, W lo}
   const uint32_t bar_full = smem_base, bar_empty = smem_base + 64, bar_tfull = smem_base + 128, bar_tempty = smem_base + 144,
-                 bar_afull = smem_base + 160, bar_aempty = smem_base + 176, tmem_slot = smem_base + 192;
+                 bar_afull = smem_base + 256, bar_aempty = smem_base + 320, tmem_slot = smem_base + 192;
   const uint32_t stage0 = smem_base + 1024;
   const uint32_t bias0 = smem_base + 1024 + EW * 32 * TC_STAGE_ROW;
   const uint32_t tiles0 = smem_base + tc_header(EW);
@@ -357,17 +359,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
             for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
               mbar_wait(bar_aempty + 8 * hsa, hpa ^ 1u);
-              mbar_arrive_expect_tx(bar_afull + 8 * hsa, 2 * a_plane);
-              tma_load_5d(tiles0 + hsa * a_stage, tm, bar_afull + 8 * hsa, cc * TC_BK, x0 - p.pw, y0 - p.ph, b, 0);
+              if (p.dbg_epi & 8) mbar_arrive(bar_afull + 8 * hsa);     // timing experiment: no activation loads
+              else {
+                mbar_arrive_expect_tx(bar_afull + 8 * hsa, 2 * a_plane);
+                tma_load_5d(tiles0 + hsa * a_stage, tm, bar_afull + 8 * hsa, cc * TC_BK, x0 - p.pw, y0 - p.ph, b, 0);
+              }
               if (++hsa == p.a_stages) { hsa = 0; hpa ^= 1u; }
               const int wk = p.seg_wcoff[s] + cc * TC_BK;
               for (int tap = 0; tap < p.num_taps; ++tap) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
                 const uint32_t full = bar_full + 8 * stage;
-                mbar_arrive_expect_tx(full, 2 * b_plane);
                 const uint32_t w_dst = bring0 + stage * 2 * b_plane;
-                tma_load_4d(w_dst, &tmW, full, wk, n0, tap, 0);
-                tma_load_4d(w_dst + b_plane, &tmW, full, wk, n0, tap, 1);
+                if (p.dbg_epi & 16) mbar_arrive(full);                 // timing experiment: no weight loads
+                else {
+                  mbar_arrive_expect_tx(full, 2 * b_plane);
+                  tma_load_4d(w_dst, &tmW, full, wk, n0, tap, 0);
+                  tma_load_4d(w_dst + b_plane, &tmW, full, wk, n0, tap, 1);
+                }
                 if (++stage == p.b_stages) { stage = 0; phase ^= 1u; }
               }
             }
@@ -450,15 +458,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const uint64_t a_hi = make_smem_desc_sw128(a_addr, a_sbo), a_lo = make_smem_desc_sw128(a_addr + a_plane, a_sbo);
                 const uint32_t w_addr = bring0 + stage * 2 * b_plane;
                 const uint64_t b_hi = make_smem_desc_sw128(w_addr, 1024), b_lo = make_smem_desc_sw128(w_addr + b_plane, 1024);
-                if (p.stackn) {
+                if (p.dbg_epi & 4) {
+                  // timing experiment: no MMAs issued (barrier / load pipeline only)
+                } else if (p.stackn) {
+                  // MMAs of equal shape are issued back to back: measured (tools/trace_mma_rate.py) 61 ns per MMA when
+                  // consecutive instructions share the instruction descriptor, 104 ns when the shape alternates
 #pragma unroll
-                  for (int k = 0; k < TC_BK / 16; ++k) {
+                  for (int k = 0; k < TC_BK / 16; ++k)
+                    if (k < ks) umma_bf16(d_tmem, a_hi + (uint64_t)(k * 32 >> 4), b_hi + (uint64_t)(k * 32 >> 4), idesc2, (!first || k > 0) ? 1u : 0u);
+#pragma unroll
+                  for (int k = 0; k < TC_BK / 16; ++k)
                     if (k < ks) {
                       const uint64_t ko = (uint64_t)(k * 32 >> 4);
-                      umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc2, (!first || k > 0) ? 1u : 0u);
-                      umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
+                      if (p.splitacc) umma_bf16(d_tmem + 2 * p.BN, a_lo + ko, b_hi + ko, idesc, (!first || k > 0) ? 1u : 0u);
+                      else umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
                     }
-                  }
                 } else {
 #pragma unroll
                   for (int k = 0; k < TC_BK / 16; ++k) {
@@ -497,13 +511,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               if (PAIR && pstack) {
                 const uint64_t b_y = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + 2 * b_plane, 1024);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
-                  if (k < ks) {
-                    const uint64_t ko = (uint64_t)(k * 32 >> 4);
-                    umma_bf16_2cta(d_tmem, a_hi + ko, b_hi + ko, idesc2, (c > 0 || k > 0) ? 1u : 0u);   // A_hi * [W_hi; W_lo]
-                    umma_bf16_2cta(d_tmem, a_lo + ko, b_y + ko, idesc, 1u);                             // A_lo * W_hi
-                  }
-                }
+                for (int k = 0; k < TC_BK / 16; ++k)
+                  if (k < ks) umma_bf16_2cta(d_tmem, a_hi + (uint64_t)(k * 32 >> 4), b_hi + (uint64_t)(k * 32 >> 4), idesc2, (c > 0 || k > 0) ? 1u : 0u);   // A_hi * [W_hi; W_lo]
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)
+                  if (k < ks) umma_bf16_2cta(d_tmem, a_lo + (uint64_t)(k * 32 >> 4), b_y + (uint64_t)(k * 32 >> 4), idesc, 1u);   // A_lo * W_hi
               } else if (PAIR) {
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k) {
@@ -515,14 +527,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                   }
                 }
               } else if (p.stackn) {
+                // equal-shape MMAs back to back (see the halo path): first all A_hi * [W_hi; W_lo] (N = 2*BN), then all A_lo * W_hi
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
+                for (int k = 0; k < TC_BK / 16; ++k)    // 16 bf16 = 32 B along the swizzled 128 B row
+                  if (k < ks) umma_bf16(d_tmem, a_hi + (uint64_t)(k * 32 >> 4), b_hi + (uint64_t)(k * 32 >> 4), idesc2, (c > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)
                   if (k < ks) {
-                    const uint64_t ko = (uint64_t)(k * 32 >> 4);     // 16 bf16 = 32 B along the swizzled 128 B row
-                    umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc2, (c > 0 || k > 0) ? 1u : 0u);   // N = 2*BN: [W_hi;W_lo]
-                    umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
+                    const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                    if (p.splitacc) umma_bf16(d_tmem + 2 * p.BN, a_lo + ko, b_hi + ko, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    else umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
                   }
-                }
               } else {
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k) {
@@ -649,6 +664,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tmem_ld32(t_addr + (uint32_t)(p.BN + sl * 32), v2);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += v2[i];
+            if (p.splitacc) {
+              tmem_ld32(t_addr + (uint32_t)(2 * p.BN + sl * 32), v2);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += v2[i];
+            }
           }
           const int nb = n0 + sl * 32;
 #pragma unroll
@@ -742,6 +762,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tmem_ld16(t_addr + (uint32_t)(p.BN + g * 16), v2);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += v2[i];
+          if (p.splitacc) {
+            tmem_ld16(t_addr + (uint32_t)(2 * p.BN + g * 16), v2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += v2[i];
+          }
         }
         const int nb = n0 + g * 16;
         if (!valid || nb >= p.cout) continue;
@@ -1069,9 +1094,15 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   SCF_REQUIRE(p.stages >= 2, SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: tile does not fit in shared memory");
   {
     const char* sv = getenv("SCFLOW_TC_STACKN");
-    p.stackn = (p.BN <= 128 && (sv ? atoi(sv) != 0 : true)) ? 1 : 0;
+    // off by default: measured without any loads (tools/trace_mma_rate.py) an MMA of N <= 128 takes 61 ns when the three
+    // products are three equal-shape instructions, but ~100 ns each in the stacked two-instruction form
+    p.stackn = (p.BN <= 128 && (sv ? atoi(sv) != 0 : false)) ? 1 : 0;
   }
-  p.acc_cols = p.stackn ? 2 * p.BN : p.BN;
+  {
+    const char* sa = getenv("SCFLOW_TC_SPLITACC");
+    p.splitacc = (p.stackn && p.BN <= 64 && sa && atoi(sa) != 0) ? 1 : 0;     // 3*BN columns x 2 buffers must fit 512
+  }
+  p.acc_cols = p.stackn ? (p.splitacc ? 3 : 2) * p.BN : p.BN;
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.acc_cols) p.tmem_cols <<= 1;
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
@@ -1116,7 +1147,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     const char* pe = getenv("SCFLOW_TC_PAIR");
     const bool want_pair = pe ? atoi(pe) != 0 : true;
     const char* pm = getenv("SCFLOW_TC_PAIR_MIN_BN");
-    const int pair_min_bn = pm ? atoi(pm) : 192;      // BN <= 128 keeps the single-CTA stacked-N form (measured faster there)
+    const int pair_min_bn = pm ? atoi(pm) : 64;
     if (want_pair && p.m_tiles % 2 == 0 && p.BN % 16 == 0 && p.BN >= pair_min_bn && p.num_tiles >= 4 &&
         (!d.w_batched || (p.tiles_x * p.tiles_y) % 2 == 0)) {
       p.pair = 1;
@@ -1126,6 +1157,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
       stage_bytes = 2 * (int)TC_A_PLANE + (p.stackn ? 3 : 2) * (p.BN / 2) * 128;
       p.stages = (232448 - 1024 - tc_header(ew)) / stage_bytes;
       if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+      p.splitacc = 0;
       p.acc_cols = p.stackn ? 2 * p.BN : p.BN;
       p.tmem_cols = 32;
       while (p.tmem_cols < 2 * p.acc_cols) p.tmem_cols <<= 1;
@@ -1143,16 +1175,20 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
       const int PW = 8 + d.kw - 1, PH = 16 + d.kh - 1;
       const int a_stage = (2 * PW * PH * 128 + 1023) / 1024 * 1024;
       const int b_stage = 2 * p.BN * 128;
-      int sb = (232448 - 1024 - tc_header(8) - 2 * a_stage) / b_stage;
+      const char* as = getenv("SCFLOW_TC_HALO_ASTAGES");
+      int sa = as ? atoi(as) : 2;
+      if (sa < 2) sa = 2;
+      if (sa > 2 && (232448 - 1024 - tc_header(8) - sa * a_stage) / b_stage < 3) sa = 2;
+      int sb = (232448 - 1024 - tc_header(8) - sa * a_stage) / b_stage;
       if (sb > 8) sb = 8;
       if (sb >= 2) {
-        p.halo = 1; p.PW = PW; p.PH = PH; p.a_stages = 2; p.b_stages = sb;
+        p.halo = 1; p.PW = PW; p.PH = PH; p.a_stages = sa; p.b_stages = sb;
         p.TW = 8; p.TH = 16; p.TB = 1;
         p.tiles_x = cdiv(p.W, 8); p.tiles_y = cdiv(p.H, 16);
         p.m_tiles = p.tiles_x * p.tiles_y * d.B;
         p.num_tiles = p.m_tiles * cdiv(d.cout_pad, p.BN);
         ew = 8; ctas_per_sm = 1;
-        smem = 1024 + tc_header(8) + 2 * a_stage + sb * b_stage;
+        smem = 1024 + tc_header(8) + sa * a_stage + sb * b_stage;
       }
     }
   }
