@@ -55,6 +55,8 @@ struct TcParams {
   // Two instructions per k-step instead of three (less shared-memory operand traffic per FLOP); the epilogue adds
   // the two halves.
   int stackn;
+  int dualacc;                   // single-CTA, non-stacked, BN <= 128: the k-steps alternate between two accumulators (columns [0,BN)
+                                 // and [BN,2BN), summed by the epilogue) so that consecutive MMAs do not form one dependent chain
   int splitacc;                  // experiment (SCFLOW_TC_SPLITACC, single-CTA stacked-N): the A_lo*W_hi MMA accumulates into its own
                                  // TMEM columns [2BN, 3BN) instead of [0, BN), so consecutive MMAs never depend on each other
   int fast_epi;                  // every global access of the epilogue is 16 B aligned: use the coalesced staged path
@@ -443,7 +445,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           // tap (ky, kx) = the halo tile read from row offset ky*PW + kx; SWIZZLE_128B is a function of the absolute shared-
           // memory address for TMA and UMMA alike, so any 128 B row offset is a valid operand start
           const uint32_t a_sbo = (uint32_t)p.PW * 128u;
-          bool first = true;
+          bool first = true, init0 = true, init1 = true;
           for (int sg = 0; sg < p.nseg; ++sg) {
             for (int cc = 0; cc < p.seg_chunks[sg]; ++cc) {
               const int ks = (cc == p.seg_chunks[sg] - 1) ? p.seg_last_ks[sg] : TC_BK / 16;
@@ -473,6 +475,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                       if (p.splitacc) umma_bf16(d_tmem + 2 * p.BN, a_lo + ko, b_hi + ko, idesc, (!first || k > 0) ? 1u : 0u);
                       else umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
                     }
+                } else if (p.dualacc) {
+                  // two independent accumulation chains, alternating with every instruction
+#pragma unroll
+                  for (int kp = 0; kp < TC_BK / 16; kp += 2) {
+                    const uint64_t k0 = (uint64_t)(kp * 32 >> 4), k1 = (uint64_t)((kp + 1) * 32 >> 4);
+                    const bool on0 = kp < ks, on1 = kp + 1 < ks;
+                    if (on0) umma_bf16(d_tmem, a_hi + k0, b_hi + k0, idesc, init0 ? 0u : 1u);
+                    if (on1) umma_bf16(d_tmem + p.BN, a_hi + k1, b_hi + k1, idesc, init1 ? 0u : 1u);
+                    if (on0) { umma_bf16(d_tmem, a_hi + k0, b_lo + k0, idesc, 1u); init0 = false; }
+                    if (on1) { umma_bf16(d_tmem + p.BN, a_hi + k1, b_lo + k1, idesc, 1u); init1 = false; }
+                    if (on0) umma_bf16(d_tmem, a_lo + k0, b_hi + k0, idesc, 1u);
+                    if (on1) umma_bf16(d_tmem + p.BN, a_lo + k1, b_hi + k1, idesc, 1u);
+                  }
                 } else {
 #pragma unroll
                   for (int k = 0; k < TC_BK / 16; ++k) {
@@ -497,6 +512,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           continue;
         }
         int c = 0;
+        bool ninit0 = true, ninit1 = true;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           for (int sg = 0; sg < p.nseg; ++sg) {
             for (int cc = 0; cc < p.seg_chunks[sg]; ++cc, ++c) {
@@ -538,6 +554,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     if (p.splitacc) umma_bf16(d_tmem + 2 * p.BN, a_lo + ko, b_hi + ko, idesc, (c > 0 || k > 0) ? 1u : 0u);
                     else umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1u);
                   }
+              } else if (p.dualacc) {
+#pragma unroll
+                for (int kp = 0; kp < TC_BK / 16; kp += 2) {
+                  const uint64_t k0 = (uint64_t)(kp * 32 >> 4), k1 = (uint64_t)((kp + 1) * 32 >> 4);
+                  const bool on0 = kp < ks, on1 = kp + 1 < ks;
+                  if (on0) umma_bf16(d_tmem, a_hi + k0, b_hi + k0, idesc, ninit0 ? 0u : 1u);
+                  if (on1) umma_bf16(d_tmem + p.BN, a_hi + k1, b_hi + k1, idesc, ninit1 ? 0u : 1u);
+                  if (on0) { umma_bf16(d_tmem, a_hi + k0, b_lo + k0, idesc, 1u); ninit0 = false; }
+                  if (on1) { umma_bf16(d_tmem + p.BN, a_hi + k1, b_lo + k1, idesc, 1u); ninit1 = false; }
+                  if (on0) umma_bf16(d_tmem, a_lo + k0, b_hi + k0, idesc, 1u);
+                  if (on1) umma_bf16(d_tmem + p.BN, a_lo + k1, b_hi + k1, idesc, 1u);
+                }
               } else {
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k) {
@@ -659,7 +687,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           float v[32];
           __syncwarp();
           tmem_ld32(t_addr + (uint32_t)(sl * 32), v);
-          if (p.stackn) {
+          if (p.stackn || p.dualacc) {
             float v2[32];
             tmem_ld32(t_addr + (uint32_t)(p.BN + sl * 32), v2);
 #pragma unroll
@@ -757,7 +785,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         float v[16];
         __syncwarp();
         tmem_ld16(t_addr + (uint32_t)(g * 16), v);
-        if (p.stackn) {                        // second half of the stacked accumulator: A_hi * W_lo
+        if (p.stackn || p.dualacc) {           // second half of the stacked accumulator (A_hi * W_lo) / second accumulation chain
           float v2[16];
           tmem_ld16(t_addr + (uint32_t)(p.BN + g * 16), v2);
 #pragma unroll
@@ -1102,7 +1130,11 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     const char* sa = getenv("SCFLOW_TC_SPLITACC");
     p.splitacc = (p.stackn && p.BN <= 64 && sa && atoi(sa) != 0) ? 1 : 0;     // 3*BN columns x 2 buffers must fit 512
   }
-  p.acc_cols = p.stackn ? (p.splitacc ? 3 : 2) * p.BN : p.BN;
+  {
+    const char* da = getenv("SCFLOW_TC_DUALACC");
+    p.dualacc = (!p.stackn && p.BN <= 128 && (da ? atoi(da) != 0 : false)) ? 1 : 0;
+  }
+  p.acc_cols = p.stackn ? (p.splitacc ? 3 : 2) * p.BN : (p.dualacc ? 2 * p.BN : p.BN);
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.acc_cols) p.tmem_cols <<= 1;
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
@@ -1157,7 +1189,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
       stage_bytes = 2 * (int)TC_A_PLANE + (p.stackn ? 3 : 2) * (p.BN / 2) * 128;
       p.stages = (232448 - 1024 - tc_header(ew)) / stage_bytes;
       if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
-      p.splitacc = 0;
+      p.splitacc = 0; p.dualacc = 0;
       p.acc_cols = p.stackn ? 2 * p.BN : p.BN;
       p.tmem_cols = 32;
       while (p.tmem_cols < 2 * p.acc_cols) p.tmem_cols <<= 1;

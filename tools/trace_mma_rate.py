@@ -25,6 +25,6 @@ for cout in (16, 64, 128, 256):
     t = times.cpu().double(); t = t[t[:, 2] > 0]; rel = (t - t[:, 0].min()) / 1e3
     ml = float((rel[:, 3] - rel[:, 2]).mean())       # first data -> last MMA issued
     ml2 = float((rel[:, 4] - rel[:, 2]).mean())      # first data -> accumulator ready
-    stack = os.environ.get('SCFLOW_TC_STACKN', '1') != '0' and cout <= 128
+    stack = os.environ.get('SCFLOW_TC_STACKN', '0') != '0' and cout <= 128
     nmma = 72 * (2 if stack else 3)
     print(f'cout={cout:3d} stackn={int(stack)}: issue loop {ml:.2f} us, until accumulator ready {ml2:.2f} us -> {ml2 * 1e3 / nmma:.1f} ns per MMA ({nmma} MMAs)')
