@@ -25,9 +25,9 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = 'image-pairs/sec at 256x256, 8 GRU iters'
-# DRAM bytes of one GRU z|r launch (B=32) from the committed ncu --set full capture (profiles/r01g_summary.md): 85.6 MB read
-# + 11.1 MB written; the algorithmic minimum is 117 MB when nothing is L2-resident (inputs 83.9 MB, outputs 33.5 MB)
-ZR_TRAFFIC_BYTES = 96.7e6
+# DRAM bytes of one GRU z|r launch (B=32) from the committed ncu --set full capture (profiles/r01i_summary.md): 85.6 MB read
+# + 10.2 MB written; the algorithmic minimum is 117 MB when nothing is L2-resident (inputs 83.9 MB, outputs 33.5 MB)
+ZR_TRAFFIC_BYTES = 95.8e6
 
 
 def parse():
@@ -357,7 +357,7 @@ def dominant_kernel_roofline(S, args, b, dev, flush, peaks):
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks['bf16_burst']
     return {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-            'traffic': ZR_TRAFFIC_BYTES if passes == 3 and b == 32 else None, 'traffic_source': 'ncu --set full, profiles/r01g_summary.md '
+            'traffic': ZR_TRAFFIC_BYTES if passes == 3 and b == 32 else None, 'traffic_source': 'ncu --set full, profiles/r01i_summary.md '
             '(dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=32; bytes)', 'ms_per_launch': ms, 'algorithmic_flops_per_launch': flops, 'mma_passes': passes,
             'peak_source': f"{peaks['source']} bf16 dense burst (kernel timed alone)"}
 
