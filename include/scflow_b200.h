@@ -135,6 +135,9 @@ typedef struct scf_tc_conv_desc {
   float* stats;                       /* EPI_ACT: per (pixel tile, epilogue warp) partial sums of the fp32 output,
                                        * [m_tiles][4][2][cout] floats (sum, then sum of squares), for InstanceNorm; needs
                                        * one sample per 128-pixel tile and cout % 32 == 0 */
+  int out_pad_writable;               /* non-zero: the outputs' padding channels [cout, round_up(cout, 8)) may be overwritten
+                                       * (with act(0)); lets layers with cout % 8 != 0 leave through TMA stores, which clip
+                                       * the channel axis at 16 B granularity */
 } scf_tc_conv_desc;
 /* number of 128-pixel tiles scf_conv2d_tc uses for this geometry (size of the `stats` buffer = tiles*4*2*cout floats)
  * and pixel tiles per sample (0 if a tile may span samples) */

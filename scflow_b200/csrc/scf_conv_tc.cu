@@ -867,6 +867,242 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (threadIdx.x == 32) stamp(6);
 }
 
+// ================================================================== transposed tile (layers of <= 128 output channels)
+// Measured (tools/trace_mma_rate.py): one tcgen05.mma of M = 128 costs ~61 ns for every N <= 128 and ~88 ns for N = 256, so a
+// pixels-as-rows tile of a 64/96/128-channel layer pays the full instruction time for a fraction of the tensor core's width.
+// Here the roles are swapped: the (zero-padded) 128 weight rows are the MMA's M side and 256 pixels its N side - twice the
+// pixels per instruction at 1.44x the instruction time.  Accumulator lane = output channel, accumulator column = pixel, so
+// in the epilogue a warp's 32 lanes hold 32 consecutive channels of ONE pixel: every NHWC access is naturally coalesced, the
+// bias is a per-thread scalar and the InstanceNorm partial sums need no cross-lane reduction.
+struct TctParams {
+  int nseg, seg_chunks[3], seg_wcoff[3], seg_last_ks[3];
+  int B, H, W, kh, kw, ph, pw, sx, sy;      // H, W: output size
+  int tw_sh, th_sh;                         // tile = 2^tw_sh x 2^th_sh pixels x (256 >> (tw_sh + th_sh)) samples
+  int tiles_x, tiles_y, num_tiles, num_taps, stages, cout;
+  const float* bias; float scale;
+  float* out_f32; int out_f32_stride, out_f32_coff;
+  __nv_bfloat16* out_hl; long long out_hl_plane; int out_hl_stride, out_hl_coff;
+  const float* aux0; int aux0_stride;
+  float* stats;                             // [num_tiles][2 warp parities][2][cout]
+  int dbg;                                  // timing experiments (SCFLOW_TCT_DBG): 1 no epilogue global accesses, 2 no MMAs, 4 no
+                                            // activation loads, 8 no weight loads
+};
+constexpr int TCT_PIX = 256;
+constexpr uint32_t TCT_W_PLANE = 128 * 128, TCT_P_PLANE = TCT_PIX * 128;
+constexpr uint32_t TCT_STAGE = 2 * TCT_W_PLANE + 2 * TCT_P_PLANE;      // 96 KB
+constexpr int TCT_EW = 8;
+constexpr uint32_t TCT_STAGING = 4096;     // per epilogue warp: [16 px][32 ch] fp32 | [2 planes][16 px][32 ch] bf16
+
+template <int ACT>
+__global__ void __launch_bounds__(64 + 32 * TCT_EW, 1)
+conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
+                const __grid_constant__ CUtensorMap tmP2, const __grid_constant__ CUtensorMap tmW,
+                const __grid_constant__ CUtensorMap tmOF, const __grid_constant__ CUtensorMap tmOH, const TctParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_base, bar_empty = smem_base + 64, bar_tfull = smem_base + 128, bar_tempty = smem_base + 144,
+                 tmem_slot = smem_base + 192;
+  const uint32_t staging0 = smem_base + 1024;                         // 4 KB per epilogue warp (TMA store source)
+  const uint32_t tiles0 = staging0 + TCT_EW * TCT_STAGING;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  griddep_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmP0);
+    if (p.nseg > 1) prefetch_tmap(&tmP1);
+    if (p.nseg > 2) prefetch_tmap(&tmP2);
+    prefetch_tmap(&tmW);
+    if (p.out_f32) prefetch_tmap(&tmOF);
+    if (p.out_hl) prefetch_tmap(&tmOH);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, TCT_EW);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512u);       // two accumulators of 256 columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  griddep_wait();
+
+  const int TW = 1 << p.tw_sh, TH = 1 << p.th_sh, TB = TCT_PIX >> (p.tw_sh + p.th_sh);
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int b = (t / tiles_per_img) * TB, tr = t % tiles_per_img;
+        const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+        const int x0 = tx * TW, y0 = ty * TH;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const int ky = tap / p.kw, kx = tap - ky * p.kw;
+          const int cx = x0 * p.sx + kx - p.pw, cy = y0 * p.sy + ky - p.ph;
+          for (int s = 0; s < p.nseg; ++s) {
+            const CUtensorMap* tm = s == 0 ? &tmP0 : (s == 1 ? &tmP1 : &tmP2);
+            for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+              const uint32_t full = bar_full + 8 * stage;
+              const uint32_t w_dst = tiles0 + stage * TCT_STAGE, p_dst = w_dst + 2 * TCT_W_PLANE;
+              const int wk = p.seg_wcoff[s] + cc * TC_BK;
+              const uint32_t txb = ((p.dbg & 4) ? 0u : 2 * TCT_P_PLANE) + ((p.dbg & 8) ? 0u : 2 * TCT_W_PLANE);
+              if (txb) mbar_arrive_expect_tx(full, txb); else mbar_arrive(full);
+              if (!(p.dbg & 4)) tma_load_5d(p_dst, tm, full, cc * TC_BK, cx, cy, b, 0);
+              if (!(p.dbg & 8)) {
+                tma_load_4d(w_dst, &tmW, full, wk, 0, tap, 0);
+                tma_load_4d(w_dst + TCT_W_PLANE, &tmW, full, wk, 0, tap, 1);
+              }
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer: D[channel][pixel] += W[channel][k] * P[pixel][k]  (split-bf16: hi*hi + hi*lo + lo*hi)
+      const uint32_t idesc = make_idesc_bf16(128, TCT_PIX);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(bar_tempty + 8 * acc, (((uint32_t)it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TCT_PIX);
+        int c = 0;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          for (int sg = 0; sg < p.nseg; ++sg) {
+            for (int cc = 0; cc < p.seg_chunks[sg]; ++cc, ++c) {
+              const int ks = (cc == p.seg_chunks[sg] - 1) ? p.seg_last_ks[sg] : TC_BK / 16;
+              mbar_wait(bar_full + 8 * stage, phase);
+              tc_fence_after();
+              const uint32_t w_addr = tiles0 + stage * TCT_STAGE, p_addr = w_addr + 2 * TCT_W_PLANE;
+              const uint64_t w_hi = make_smem_desc_sw128(w_addr, 1024), w_lo = make_smem_desc_sw128(w_addr + TCT_W_PLANE, 1024);
+              const uint64_t p_hi = make_smem_desc_sw128(p_addr, 1024), p_lo = make_smem_desc_sw128(p_addr + TCT_P_PLANE, 1024);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                if (k < ks && !(p.dbg & 2)) {
+                  const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                  umma_bf16(d_tmem, w_hi + ko, p_hi + ko, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                  umma_bf16(d_tmem, w_hi + ko, p_lo + ko, idesc, 1u);
+                  umma_bf16(d_tmem, w_lo + ko, p_hi + ko, idesc, 1u);
+                }
+              }
+              umma_commit(bar_empty + 8 * stage);
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+        umma_commit(bar_tfull + 8 * acc);
+      }
+    }
+  } else {
+    // ================= epilogue: thread = output channel (TMEM lane), accumulator columns = the tile's pixels; the two warps
+    // of a lane quarter take alternate 32-pixel slabs
+    const int q = warp & 3, par = (warp - 2) >> 2;
+    const int c = q * 32 + lane;
+    const bool cvalid = c < p.cout;
+    const bool warp_active = q * 32 < p.cout;
+    const float bias_c = (p.bias && cvalid) ? __ldg(p.bias + c) : 0.f;
+    const int tw_mask = TW - 1, th_mask = TH - 1, b_sh = p.tw_sh + p.th_sh, odd = lane & 1;
+    const uint32_t stg = staging0 + (uint32_t)(warp - 2) * TCT_STAGING;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int b = (t / tiles_per_img) * TB, tr = t % tiles_per_img;
+      const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+      const int x0 = tx * TW, y0 = ty * TH;
+      mbar_wait(bar_tfull + 8 * acc, ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      float ssum = 0.f, qsum = 0.f;
+      if (warp_active && !(p.dbg & 1)) {
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TCT_PIX);
+#pragma unroll 1
+        for (int ch = par; ch < TCT_PIX / 16; ch += TCT_EW / 4) {
+          float v[16];
+          __syncwarp();
+          tmem_ld16(t_addr + (uint32_t)(ch * 16), v);
+          // The tile is at least 32 pixels wide, so a 16-column chunk is a run of one tile row.  The warp writes its
+          // [16 pixels][32 channels] block to shared memory in NHWC order (conflict-free: lanes = consecutive channels, constant
+          // offsets) and one TMA store per output moves it out; the tensor map clips pixels beyond the row / image / batch and
+          // channels beyond cout, so the stores need no predicates.  (A first version with per-thread global stores spent
+          // ~70 instructions per pixel pair on 64-bit addressing and predicates and was issue-bound at 1.6 TB/s.)
+          const int col0 = ch * 16;
+          const int xb = x0 + (col0 & tw_mask), y = y0 + ((col0 >> p.tw_sh) & th_mask), bi = b + (col0 >> b_sh);
+          int nvalid = p.W - xb;
+          nvalid = (y < p.H && bi < p.B) ? (nvalid < 16 ? nvalid : 16) : 0;      // negative = none
+          if (p.aux0 && cvalid) {                                                  // residual, added before the activation
+            const float* ax = p.aux0 + (((long long)bi * p.H + y) * p.W + xb) * p.aux0_stride + c;
+            float rv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rv[j] = j < nvalid ? __ldg(ax + (long long)j * p.aux0_stride) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = act_ct<ACT>(fmaf(v[j], p.scale, bias_c) + rv[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = act_ct<ACT>(fmaf(v[j], p.scale, bias_c));
+          }
+          if (p.stats) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < nvalid) { ssum += v[j]; qsum = fmaf(v[j], v[j], qsum); }
+          }
+          if (lane == 0) bulk_wait_group_read0();       // the previous chunk's TMA stores have read the staging block
+          __syncwarp();
+          if (p.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg + (uint32_t)(j * 128 + lane * 4)), "f"(v[j]) : "memory");
+          }
+          if (p.out_hl) {
+            // lanes 2i, 2i+1 trade values: the even lane stores channels (c, c+1) of pixel j as one 32-bit word per plane, the
+            // odd lane channels (c-1, c) of pixel j + 1
+            const uint32_t hbase = stg + 2048u + (uint32_t)(odd * 64 + (lane & ~1) * 2);
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(v[j]), h1 = __float2bfloat16_rn(v[j + 1]);
+              const __nv_bfloat16 l0 = __float2bfloat16_rn(v[j] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[j + 1] - __bfloat162float(h1));
+              const uint32_t hl0 = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(l0) << 16);
+              const uint32_t hl1 = (uint32_t)__bfloat16_as_ushort(h1) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? hl0 : hl1, 1);
+              const uint32_t mine = odd ? hl1 : hl0;
+              const uint32_t lo_ch = odd ? recv : mine, hi_ch = odd ? mine : recv;      // lower / upper channel of the pair
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(hbase + (uint32_t)(j * 64)), "r"((lo_ch & 0xffffu) | (hi_ch << 16)) : "memory");
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(hbase + 1024u + (uint32_t)(j * 64)), "r"((lo_ch >> 16) | (hi_ch & 0xffff0000u)) : "memory");
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.out_f32) tma_store_4d(&tmOF, stg, q * 32, xb, y, bi);
+            if (p.out_hl) tma_store_5d(&tmOH, stg + 2048u, q * 32, xb, y, bi, 0);
+            bulk_commit_group();
+          }
+        }
+      }
+      if (p.stats && cvalid) {
+        float* o = p.stats + ((long long)(t * (TCT_EW / 4) + par) * 2) * p.cout + c;
+        o[0] = ssum;
+        o[p.cout] = qsum;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+    if (lane == 0) bulk_wait_group0();       // shared memory must outlive the last TMA stores
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
 // ------------------------------------------------------------------ prep kernels
 // input channels [i_begin, i_begin + I) of a weight with I_total input channels land at packed channels i_dst ..
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, int O, int I, int taps,
@@ -1019,13 +1255,14 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr) {
+                      const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr,
+                      CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   SCF_REQUIRE(fn != nullptr, SCF_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
                   elem_strides ? elem_strides : ones,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SCF_REQUIRE(r == CUDA_SUCCESS, SCF_ERR_ARG, "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dims %llu %llu %llu, box %u %u %u)",
               (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1],
@@ -1048,9 +1285,12 @@ static void pick_tile(int B, int H, int W, bool one_sample, int& TW, int& TH, in
 
 // tiling of the calling thread's most recent scf_conv2d_tc launch (the `stats` buffer is indexed by its pixel tiles)
 thread_local int g_last_m_tiles = 0, g_last_tiles_per_img = 0;
-void conv2d_tc_last_tiles(int* m_tiles, int* per_img) {
+extern thread_local int g_last_stat_rows_per_img;
+// per_img: pixel tiles per sample (0 when a tile spans samples); stat_rows: rows of [2][cout] partial sums per sample in `stats`
+void conv2d_tc_last_tiles(int* m_tiles, int* per_img, int* stat_rows) {
   if (m_tiles) *m_tiles = g_last_m_tiles;
   if (per_img) *per_img = g_last_tiles_per_img;
+  if (stat_rows) *stat_rows = g_last_stat_rows_per_img;
 }
 // upper bound of the number of pixel tiles any tiling of a [B, Hout, Wout] output can have (sizes the `stats` buffer)
 int conv2d_tc_max_tiles(int B, int Hout, int Wout) {
@@ -1058,6 +1298,160 @@ int conv2d_tc_max_tiles(int B, int Hout, int Wout) {
   pick_tile(B, Hout, Wout, false, TW, TH, TB);
   const int a = cdiv(Wout, TW) * cdiv(Hout, TH) * cdiv(B, TB), h = cdiv(Wout, 8) * cdiv(Hout, 16) * B;
   return a > h ? a : h;
+}
+
+// ---- transposed-tile variant (conv_tct_kernel): plain-activation layers of <= 128 output channels
+static bool tct_pick_tile(int B, int H, int W, int sx, int sy, bool one_sample, int& tw_sh, int& th_sh) {
+  long long best = -1;
+  for (int a = 8; a >= 5; --a) {          // >= 32 pixels wide: the epilogue's 32-column slabs must not cross tile rows
+    for (int b = 8 - a; b >= 0; --b) {
+      const int tw = 1 << a, th = 1 << b, tb = TCT_PIX >> (a + b);
+      if (one_sample && tb != 1) continue;
+      if ((tw > 1 ? tw * sx : 1) > 256 || (th > 1 ? th * sy : 1) > 256) continue;      // TMA box limit
+      const long long vol = (long long)cdiv(W, tw) * tw * cdiv(H, th) * th * cdiv(B, tb) * tb;
+      if (best < 0 || vol < best) { best = vol; tw_sh = a; th_sh = b; }
+    }
+  }
+  return best >= 0;
+}
+
+thread_local int g_last_stat_rows_per_img = 0;
+
+static bool tct_eligible(const scf_tc_conv_desc& d) {
+  // SCFLOW_TC_T: 0 never, 1 (default) where it measured faster than the pixels-as-rows tiling (tools/bench_tct.py: every
+  // layer except the 64-channel ones with a short reduction, whose main loop is no longer than the 256-pixel epilogue),
+  // 2 every eligible layer
+  const char* e = getenv("SCFLOW_TC_T");
+  const int mode = e ? atoi(e) : 1;
+  if (!mode) return false;
+  if (mode == 1) {
+    int cin = 0;
+    for (int s = 0; s < d.nseg; ++s) cin += d.seg[s].nch;
+    if (d.cout <= 64 && cin * d.kh * d.kw < 1024) return false;
+  }
+  if (d.epi != SCF_EPI_ACT || d.w_batched || d.pre || d.cout_pad > 128 || d.act < SCF_ACT_NONE || d.act > SCF_ACT_TANH) return false;
+  {
+    const int sx = d.stride_x ? d.stride_x : (d.stride == 2 ? 2 : 1);
+    if ((d.W + 2 * (d.kw / 2) - d.kw) / sx + 1 < 24) return false;      // tiles are at least 32 pixels wide
+  }
+  // the epilogue leaves through TMA stores: 16 B aligned bases and pitches
+  // ... and they clip the channel axis at 16 B granularity
+  if (!d.out_pad_writable && ((d.out_hl && d.cout % 8) || (d.out_f32 && d.cout % 4))) return false;
+  if (d.out_pad_writable && ((d.cout + 7) / 8 * 8 > d.cout_pad)) return false;
+  if (d.out_hl && (d.cout % 2 || d.out_hl_stride % 8 || d.out_hl_coff % 8 || d.out_hl_plane % 8 || reinterpret_cast<uintptr_t>(d.out_hl) % 16))
+    return false;
+  if (d.out_f32 && (d.out_f32_stride % 4 || d.out_f32_coff % 4 || reinterpret_cast<uintptr_t>(d.out_f32) % 16)) return false;
+  return true;
+}
+
+static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
+  TctParams p = {};
+  p.nseg = d.nseg;
+  const int stride = d.stride == 2 ? 2 : 1;
+  p.sx = d.stride_x ? d.stride_x : stride;
+  p.sy = d.stride_y ? d.stride_y : stride;
+  p.kh = d.kh; p.kw = d.kw; p.ph = d.kh / 2; p.pw = d.kw / 2;
+  p.B = d.B; p.H = (d.H + 2 * p.ph - d.kh) / p.sy + 1; p.W = (d.W + 2 * p.pw - d.kw) / p.sx + 1;
+  SCF_REQUIRE(tct_pick_tile(d.B, p.H, p.W, p.sx, p.sy, d.stats != nullptr, p.tw_sh, p.th_sh), SCF_ERR_UNSUPPORTED,
+              "scf_conv2d_tc: no transposed tiling");
+  const int TW = 1 << p.tw_sh, TH = 1 << p.th_sh, TB = TCT_PIX >> (p.tw_sh + p.th_sh);
+  p.tiles_x = cdiv(p.W, TW); p.tiles_y = cdiv(p.H, TH);
+  p.num_tiles = p.tiles_x * p.tiles_y * cdiv(d.B, TB);
+  p.num_taps = d.kh * d.kw;
+  p.cout = d.cout;
+  p.stages = 2;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    SCF_CUDA(cudaGetDevice(&dev));
+    SCF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TctParams);
+  static const KernelFn table[4] = {conv_tct_kernel<SCF_ACT_NONE>, conv_tct_kernel<SCF_ACT_RELU>, conv_tct_kernel<SCF_ACT_SIGMOID>,
+                                    conv_tct_kernel<SCF_ACT_TANH>};
+  const int smem = 1024 + 1024 + TCT_EW * (int)TCT_STAGING + p.stages * (int)TCT_STAGE;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [smem] {
+    for (int i = 0; i < 4; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) attr_err = e;
+    }
+  });
+  SCF_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "cudaFuncSetAttribute(conv_tct_kernel): %s", cudaGetErrorString(attr_err));
+  p.bias = d.bias; p.scale = d.scale;
+  p.out_f32 = d.out_f32; p.out_f32_stride = d.out_f32_stride; p.out_f32_coff = d.out_f32_coff;
+  p.out_hl = reinterpret_cast<__nv_bfloat16*>(d.out_hl); p.out_hl_plane = d.out_hl_plane; p.out_hl_stride = d.out_hl_stride;
+  p.out_hl_coff = d.out_hl_coff;
+  p.aux0 = d.aux0; p.aux0_stride = d.aux0_stride;
+  p.stats = d.stats;
+  { const char* de = getenv("SCFLOW_TCT_DBG"); p.dbg = de ? atoi(de) : 0; }
+  if (d.stats) SCF_REQUIRE(TB == 1, SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: stats need one sample per tile");
+  CUtensorMap tmP[3], tmW;
+  int wcoff = 0;
+  for (int s = 0; s < 3; ++s) {
+    if (s >= d.nseg) { tmP[s] = tmP[0]; continue; }
+    const scf_tc_seg& sg = d.seg[s];
+    SCF_REQUIRE(sg.ptr && sg.nch > 0 && sg.nch % 8 == 0 && sg.coff % 8 == 0 && sg.stride % 8 == 0, SCF_ERR_ALIGN,
+                "scf_conv2d_tc: segment %d channels/offset/stride must be multiples of 8", s);
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(sg.ptr) + sg.coff;
+    SCF_REQUIRE(reinterpret_cast<uintptr_t>(base) % 16 == 0 && (sg.plane_stride * 2) % 16 == 0, SCF_ERR_ALIGN,
+                "scf_conv2d_tc: segment %d must be 16B aligned", s);
+    cuuint64_t dims[5] = {(cuuint64_t)sg.nch, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B, 2};
+    cuuint64_t str[4] = {(cuuint64_t)sg.stride * 2, (cuuint64_t)d.W * sg.stride * 2, (cuuint64_t)d.H * d.W * sg.stride * 2,
+                         (cuuint64_t)sg.plane_stride * 2};
+    const int bsx = TW == 1 ? 1 : p.sx, bsy = TH == 1 ? 1 : p.sy;
+    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)(TW * bsx), (cuuint32_t)(TH * bsy), (cuuint32_t)TB, 2};
+    cuuint32_t estr[5] = {1, (cuuint32_t)bsx, (cuuint32_t)bsy, 1, 1};
+    SCF_TRY(encode_map(&tmP[s], base, 5, dims, str, box, estr));
+    p.seg_chunks[s] = cdiv(sg.nch, TC_BK);
+    p.seg_last_ks[s] = cdiv(sg.nch - (p.seg_chunks[s] - 1) * TC_BK, 16);
+    p.seg_wcoff[s] = wcoff;
+    wcoff += sg.nch;
+  }
+  SCF_REQUIRE(wcoff <= d.cin_pad, SCF_ERR_ARG, "scf_conv2d_tc: segments carry %d channels but the packed weight has cin_pad %d", wcoff, d.cin_pad);
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d.cin_pad, (cuuint64_t)d.cout_pad, (cuuint64_t)p.num_taps, 2};
+    cuuint64_t str[3] = {(cuuint64_t)d.cin_pad * 2, (cuuint64_t)d.cout_pad * d.cin_pad * 2,
+                         d.w_plane_stride > 0 ? (cuuint64_t)d.w_plane_stride * 2 : (cuuint64_t)p.num_taps * d.cout_pad * d.cin_pad * 2};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BK, 128, 1, 1};       // rows >= cout_pad: zero fill
+    SCF_REQUIRE(reinterpret_cast<uintptr_t>(d.w) % 16 == 0, SCF_ERR_ALIGN, "scf_conv2d_tc: packed weight must be 16B aligned");
+    SCF_TRY(encode_map(&tmW, d.w, 4, dims, str, box));
+  }
+  // output maps of the epilogue's TMA stores: box = 32 channels x 16 pixels of one row (both bf16 planes in one store)
+  CUtensorMap tmOF = tmW, tmOH = tmW;
+  if (d.out_f32) {
+    cuuint64_t dims[4] = {(cuuint64_t)d.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)d.B};
+    cuuint64_t str[3] = {(cuuint64_t)d.out_f32_stride * 4, (cuuint64_t)p.W * d.out_f32_stride * 4, (cuuint64_t)p.H * p.W * d.out_f32_stride * 4};
+    cuuint32_t box[4] = {32, 16, 1, 1};
+    SCF_TRY(encode_map(&tmOF, d.out_f32 + d.out_f32_coff, 4, dims, str, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  }
+  if (d.out_hl) {
+    cuuint64_t dims[5] = {(cuuint64_t)d.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)d.B, 2};
+    cuuint64_t str[4] = {(cuuint64_t)d.out_hl_stride * 2, (cuuint64_t)p.W * d.out_hl_stride * 2, (cuuint64_t)p.H * p.W * d.out_hl_stride * 2,
+                         (cuuint64_t)d.out_hl_plane * 2};
+    cuuint32_t box[5] = {32, 16, 1, 1, 2};
+    SCF_TRY(encode_map(&tmOH, reinterpret_cast<const __nv_bfloat16*>(d.out_hl) + d.out_hl_coff, 5, dims, str, box, nullptr,
+                       CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_NONE));
+  }
+  g_last_m_tiles = p.num_tiles;
+  g_last_tiles_per_img = TB == 1 ? p.tiles_x * p.tiles_y : 0;
+  g_last_stat_rows_per_img = g_last_tiles_per_img * (TCT_EW / 4);
+  static const bool pdl = [] { const char* e = getenv("SCFLOW_PDL"); return e ? atoi(e) != 0 : true; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.num_tiles < num_sms ? p.num_tiles : num_sms); cfg.blockDim = dim3(64 + 32 * TCT_EW);
+  cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, table[d.act], tmP[0], tmP[1], tmP[2], tmW, tmOF, tmOH, p);
+  if (le != cudaSuccess) { cudaGetLastError(); set_error("conv_tct_kernel launch: %s", cudaGetErrorString(le)); g_launches++; return (int)le; }
+  return check_launch("conv_tct_kernel");
 }
 
 int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
@@ -1085,12 +1479,16 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     SCF_REQUIRE(d.out_f32_stride % 4 == 0 && d.out_f32_coff % 4 == 0 && reinterpret_cast<uintptr_t>(d.out_f32) % 16 == 0,
                 SCF_ERR_ALIGN, "scf_conv2d_tc: GRU epilogues need 16B-aligned fp32 outputs");
 
-  TcParams p = {};
-  p.nseg = d.nseg;
-  const int stride = d.stride == 2 ? 2 : 1;
   SCF_REQUIRE(d.stride == 0 || d.stride == 1 || d.stride == 2, SCF_ERR_ARG, "scf_conv2d_tc: stride must be 1 or 2");
   SCF_REQUIRE(d.stride_x >= 0 && d.stride_x <= 2 && d.stride_y >= 0 && d.stride_y <= 2, SCF_ERR_ARG,
               "scf_conv2d_tc: stride_x / stride_y must be 0 (= stride), 1 or 2");
+  if (d.stats)
+    SCF_REQUIRE(d.cout % 32 == 0 && d.out_f32 && d.epi == SCF_EPI_ACT && reinterpret_cast<uintptr_t>(d.stats) % 16 == 0,
+                SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: stats need an fp32 output, cout %% 32 == 0 and the plain epilogue");
+  if (tct_eligible(d)) return conv2d_tct(d, st);
+  TcParams p = {};
+  p.nseg = d.nseg;
+  const int stride = d.stride == 2 ? 2 : 1;
   p.sx = d.stride_x ? d.stride_x : stride;
   p.sy = d.stride_y ? d.stride_y : stride;
   p.kh = d.kh; p.kw = d.kw; p.ph = d.kh / 2; p.pw = d.kw / 2;
@@ -1226,6 +1624,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   }
   g_last_m_tiles = p.m_tiles;
   g_last_tiles_per_img = p.TB == 1 ? p.tiles_x * p.tiles_y : 0;
+  g_last_stat_rows_per_img = g_last_tiles_per_img * 4;
   KernelFn kernel = table[p.pair ? 2 : (ew == 8 ? 1 : 0)][ki];
   // ---- cluster size: CTAs of consecutive pixel tiles (same N tile, same sample when the weights are batched) share each
   // weight tile through TMA multicast, which divides the weight share of the L2 -> shared-memory operand traffic - the

@@ -465,6 +465,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
   // tensor-core convolution on split-bf16 buffers: segs = {plane base, channels per pixel, first channel, channels}
   struct SSeg { void* ptr; int stride, coff, nch; };
   int tc_hin = H8, tc_win = W8, tc_stride = 1;      // geometry of the next convtc call (pose head overrides it)
+  int pad_writable = 0;
   auto convtc = [&](int id, std::initializer_list<SSeg> segs, int act, float* out_f32, int f32_stride, void* out_hl,
                     int hl_stride, int hl_coff, int epi = SCF_EPI_ACT, const float* aux0 = nullptr, const float* aux1 = nullptr,
                     void* out2_hl = nullptr, const float* pre = nullptr, int pre_stride = 0) -> int {
@@ -485,6 +486,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
     d.aux0 = aux0; d.aux0_stride = 128; d.aux1 = aux1; d.aux1_stride = 128;
     d.out2_hl = out2_hl; d.out2_hl_plane = (long long)BP * 128; d.out2_hl_stride = 128;
     if (pre) { d.pre = pre; d.pre_stride = pre_stride; d.bias = nullptr; }   // the bias is part of the precomputed map
+    d.out_pad_writable = pad_writable;
     return conv2d_tc(d, lst);
   };
 
@@ -528,7 +530,6 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
         SCF_CUDA(cudaStreamWaitEvent(side_all->s, side_all->fork, 0));
         lst = side_all->s;
       }
-      SCF_TRY(scf_split_copy(menc_flow, 2, 0, S(ws.s_motion), (long long)BP * 128, 128, 126, (long long)BP, 2, lst));
       SCF_TRY(im2col_x_split(menc_flow, 0, 2, 7, S(ws.s_t7), (long long)BP * 16, B, H8, W8, 1, lst));
       SCF_TRY(convtc(PC_FLOW0, {{S(ws.s_t7), 16, 0, 16}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_f1), 128, 0));
       SCF_TRY(convtc(PC_FLOW1, {{S(ws.s_f1), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_cf), 256, 192));
@@ -541,7 +542,12 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       SCF_TRY(convtc(PC_CORR0, {{S(ws.s_corr), ws.corr_stride_s, 0, ws.corr_stride_s}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_c1), 256, 0));
       SCF_TRY(convtc(PC_CORR1, {{S(ws.s_c1), 256, 0, 256}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_cf), 256, 0));
       if (ovl & 2) SCF_CUDA(cudaStreamWaitEvent(st, side_all->join_a, 0));
+      // motion features = [conv output (126) | flow (2)] (raft_decoder.py MotionEncoder: cat([out, flow])); the flow channels
+      // are written after the convolution, which may clear its output's padding channels (out_pad_writable)
+      pad_writable = 1;
       SCF_TRY(convtc(PC_OUT0, {{S(ws.s_cf), 256, 0, 256}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_motion), 128, 0));
+      pad_writable = 0;
+      SCF_TRY(scf_split_copy(menc_flow, 2, 0, S(ws.s_motion), (long long)BP * 128, 128, 126, (long long)BP, 2, lst));
       for (int pass = 0; pass < 2; ++pass) {
         SCF_TRY(convtc(pass == 0 ? PC_ZR0 : PC_ZR1, {{S(ws.s_h[pass]), 128, 0, 128}, {S(ws.s_motion), 128, 0, 128}},
                        SCF_ACT_SIGMOID, F(ws.z), 128, nullptr, 0, 0, SCF_EPI_GRU_ZR, F(ws.h[pass]), nullptr, S(ws.s_rh),

@@ -12,7 +12,7 @@ namespace scf {
 int conv2d_f32(const scf_conv_desc& d, cudaStream_t st);
 int conv2d_thin(const scf_conv_desc& d, int in_nchw, cudaStream_t st);
 int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st);
-void conv2d_tc_last_tiles(int* m_tiles, int* per_img);
+void conv2d_tc_last_tiles(int* m_tiles, int* per_img, int* stat_rows);
 int conv2d_tc_max_tiles(int B, int Hout, int Wout);
 int im2col_x_split(const float* in, int nchw, int cin, int kw, void* out_hl, long long plane, int N, int H, int Wi, int sx,
                    cudaStream_t st);
@@ -114,14 +114,13 @@ __global__ void instnorm_finalize_kernel(const float* __restrict__ part, float* 
   stat[(long long)idx * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 // stage 2 for statistics gathered by the convolution's own epilogue (scf_conv2d_tc `stats`): part is
-// [N * tiles_per_img][4 warps][2][C]; one block per image, deterministic double-precision combine
+// [N][rows][2][C] (rows = partial-sum rows per image, see conv2d_tc_last_tiles); one block per image, deterministic double-precision combine
 __global__ void __launch_bounds__(256) instnorm_finalize_tiles_kernel(const float* __restrict__ part, float* __restrict__ stat,
-                                                                      int HW, int C, float eps, int tiles_per_img) {
+                                                                      int HW, int C, float eps, int rows) {
   // grid (N, C/8): thread = (channel c of 8, row group g of 32); 8 independent loads in flight per thread; fixed combine order
   __shared__ double ss[256], sq[256];
   const int n = blockIdx.x;
   const int cl = threadIdx.x & 7, c = blockIdx.y * 8 + cl, g = threadIdx.x >> 3;
-  const int rows = tiles_per_img * 4;
   const float* base = part + (long long)n * rows * 2 * C + c;
   double s = 0., q = 0.;
   for (int r0 = g; r0 < rows; r0 += 256) {
@@ -368,9 +367,10 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
     scf_conv2d_tc_tiles(N, ho, wo, &per_img);
     if (per_img > 0 && e.cout % 32 == 0 && ho * wo >= 128) {
       SCF_TRY(tcconv(u, in_s, hin, win, SCF_ACT_NONE, raw, nullptr, nullptr, F(ws.part)));
-      conv2d_tc_last_tiles(nullptr, &per_img);      // the tiling the launch actually used (halo mode: 8 x 16 pixel tiles)
+      int rows = 0;
+      conv2d_tc_last_tiles(nullptr, &per_img, &rows);      // the tiling the launch actually used (halo / transposed tiles differ)
       SCF_REQUIRE(per_img > 0, SCF_ERR_UNSUPPORTED, "scf_encoder_forward: statistics need one sample per tile");
-      instnorm_finalize_tiles_kernel<<<dim3(N, e.cout / 8), 256, 0, st>>>(F(ws.part), stat, ho * wo, e.cout, 1e-5f, per_img);
+      instnorm_finalize_tiles_kernel<<<dim3(N, e.cout / 8), 256, 0, st>>>(F(ws.part), stat, ho * wo, e.cout, 1e-5f, rows);
       return check_launch("instnorm_finalize_tiles_kernel");
     }
     SCF_TRY(tcconv(u, in_s, hin, win, SCF_ACT_NONE, raw, nullptr, nullptr));
@@ -385,8 +385,9 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
     scf_conv2d_tc_tiles(N, h, w, &per_img);
     if (per_img > 0) {
       SCF_TRY(stem_conv(SCF_ACT_NONE, F(ws.raw), nullptr, F(ws.part)));
-      conv2d_tc_last_tiles(nullptr, &per_img);
-      instnorm_finalize_tiles_kernel<<<dim3(N, 8), 256, 0, st>>>(F(ws.part), F(ws.stat), h * w, 64, 1e-5f, per_img);
+      int rows = 0;
+      conv2d_tc_last_tiles(nullptr, &per_img, &rows);
+      instnorm_finalize_tiles_kernel<<<dim3(N, 8), 256, 0, st>>>(F(ws.part), F(ws.stat), h * w, 64, 1e-5f, rows);
       SCF_TRY(check_launch("instnorm_finalize_tiles_kernel"));
     } else {
       SCF_TRY(stem_conv(SCF_ACT_NONE, F(ws.raw), nullptr, nullptr));

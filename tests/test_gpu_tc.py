@@ -108,3 +108,53 @@ def test_conv_tc_segments_slices_and_gru_epilogues(S):
                     act='tanh', out_f32=hn32, out_hl=hns, epi=_lib.EPI_GRU_Q, aux0=h32, aux1=zbuf)
     assert float((hn32.permute(0, 3, 1, 2).cpu() - hn).abs().max()) < 3e-5
     assert float((S.ops.unsplit(hns).cpu() - hn).abs().max()) < 3e-5
+
+
+T_CASES = [
+    # cin, cout, kernel, (H, W), B, stride, residual, stats
+    (64, 64, (3, 3), (64, 64), 1, 1, True, True),       # encoder residual block: raw fp32 + InstanceNorm partial sums
+    (64, 96, (3, 3), (64, 64), 1, 2, False, True),      # down-sampling
+    (128, 128, (3, 3), (30, 40), 1, 1, True, True),     # ragged rows and columns
+    (96, 128, (1, 1), (32, 32), 3, 2, False, False),    # 16-wide output: stays on the pixels-as-rows kernel
+    (16, 128, (7, 1), (32, 32), 2, 1, False, False),    # x-folded thin input (cin_pad 16, one ragged chunk per tap)
+    (256, 126, (3, 3), (32, 32), 2, 1, False, False),   # cout % 8 != 0 (motion encoder output)
+]
+
+
+@pytest.mark.parametrize('transposed', ['0', '2'])
+@pytest.mark.parametrize('cin,cout,k,hw,b,stride,residual,stats', T_CASES)
+def test_conv_tc_small_n_variants(S, monkeypatch, transposed, cin, cout, k, hw, b, stride, residual, stats):
+    """Layers of <= 128 output channels through both tilings (SCFLOW_TC_T: weights or pixels as the MMA's rows): same
+    results, including the residual input, the InstanceNorm partial sums and untouched neighbouring channels."""
+    monkeypatch.setenv('SCFLOW_TC_T', transposed)
+    gen = torch.Generator().manual_seed(cin + 3 * cout + hw[1])
+    x = torch.randn(b, cin, *hw, generator=gen)
+    w = torch.randn(cout, cin, *k, generator=gen) / math.sqrt(cin * k[0] * k[1])
+    bias = 0.1 * torch.randn(cout, generator=gen)
+    pad = (k[0] // 2, k[1] // 2)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), stride=stride, padding=pad)
+    ho, wo = ref.shape[-2:]
+    res = torch.randn(b, ho, wo, cout, generator=gen) if residual else None
+    if residual:
+        ref = ref + res.permute(0, 3, 1, 2).double()
+    ref = torch.relu(ref).float()
+    xs = S.ops.split_nchw(x.cuda())
+    pw = S.ops.pack_conv_weight_tc([w.cuda()])
+    cpad = (cout + 7) // 8 * 8
+    out_f32 = torch.full((b, ho, wo, cpad + 8), 7.0, device='cuda')
+    out_hl = torch.full((2, b, ho, wo, cpad + 16), 7.0, device='cuda', dtype=torch.bfloat16)
+    n_tiles, _ = S.ops.conv2d_tc_tiles(b, ho, wo)
+    st = torch.zeros(n_tiles * 4 * 2 * cout, device='cuda') if stats else None
+    S.ops.conv2d_tc([(xs, 0, cin)], pw, bias.cuda(), cout, k, act='relu', out_f32=out_f32, out_hl=out_hl, out_hl_coff=8,
+                    stride=stride, aux0=None if res is None else res.cuda(), stats=st, out_pad_writable=cout % 8 != 0)
+    torch.cuda.synchronize()
+    got = out_f32[..., :cout].permute(0, 3, 1, 2).cpu()
+    got_hl = S.ops.unsplit(out_hl)[:, 8:8 + cout].cpu()
+    assert float((got - ref).abs().max()) < 5e-5
+    assert float((got_hl - ref).abs().max()) < 1e-4
+    # channels outside [coff, coff + round_up(cout, 8)) keep their contents
+    assert bool((out_f32[..., cpad:] == 7.0).all()) and bool((out_hl[..., :8] == 7.0).all()) and bool((out_hl[..., 8 + cpad:] == 7.0).all())
+    if stats:
+        rows = st.view(-1, 2, cout).double().sum(0).cpu()
+        assert float((rows[0] - ref.double().sum((0, 2, 3))).abs().max()) < 1e-2
+        assert float((rows[1] - ref.double().pow(2).sum((0, 2, 3))).abs().max()) < 2e-2
