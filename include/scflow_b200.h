@@ -132,9 +132,11 @@ typedef struct scf_tc_conv_desc {
                                        * (the loop-invariant context contribution of the GRU convolutions, computed once) */
   int stride_x, stride_y;             /* per-axis strides overriding `stride` when non-zero (1 or 2 each) */
   long long w_plane_stride;           /* elements from the hi to the lo plane of `w` (0 = tightly packed) */
-  float* stats;                       /* EPI_ACT: per (pixel tile, epilogue warp) partial sums of the fp32 output,
-                                       * [m_tiles][4][2][cout] floats (sum, then sum of squares), for InstanceNorm; needs
-                                       * one sample per 128-pixel tile and cout % 32 == 0 */
+  float* stats;                       /* EPI_ACT: per (pixel tile, epilogue warp group) partial sums of the fp32 output,
+                                       * rows of [2][cout] floats (sum, then sum of squares), for InstanceNorm: 4 rows per
+                                       * 128-pixel tile, or 2 rows per 256-pixel tile when the transposed tiling is used
+                                       * (rows of one sample are contiguous; zero-initialised rows beyond the used ones add
+                                       * nothing).  Needs one sample per tile and cout % 32 == 0 */
   int out_pad_writable;               /* non-zero: the outputs' padding channels [cout, round_up(cout, 8)) may be overwritten
                                        * (with act(0)); lets layers with cout % 8 != 0 leave through TMA stores, which clip
                                        * the channel axis at 16 B granularity */

@@ -1013,6 +1013,8 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
     const float bias_c = (p.bias && cvalid) ? __ldg(p.bias + c) : 0.f;
     const int tw_mask = TW - 1, th_mask = TH - 1, b_sh = p.tw_sh + p.th_sh, odd = lane & 1;
     const uint32_t stg = staging0 + (uint32_t)(warp - 2) * TCT_STAGING;
+    const bool both = p.out_f32 && p.out_hl;
+    uint32_t kc = 0;                      // chunks staged so far (staging block parity)
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -1054,17 +1056,31 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
             for (int j = 0; j < 16; ++j)
               if (j < nvalid) { ssum += v[j]; qsum = fmaf(v[j], v[j], qsum); }
           }
-          if (lane == 0) bulk_wait_group_read0();       // the previous chunk's TMA stores have read the staging block
+          // Staging: 4 KB per warp.  One output kind: two 2 KB blocks used alternately; both kinds: the fp32 block and the
+          // bf16 block each go out as their own bulk group.  Either way a block is rewritten only after the group that read it
+          // two groups ago has completed (wait_group.read 1), so one store is always in flight behind the shared-memory writes.
+          const uint32_t blk_f = stg + ((!both && (kc & 1)) ? 2048u : 0u);
+          const uint32_t blk_h = stg + ((both || (kc & 1)) ? 2048u : 0u);
+          ++kc;
+          if (lane == 0) bulk_wait_group_read1();
           __syncwarp();
           if (p.out_f32) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg + (uint32_t)(j * 128 + lane * 4)), "f"(v[j]) : "memory");
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(blk_f + (uint32_t)(j * 128 + lane * 4)), "f"(v[j]) : "memory");
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmOF, blk_f, q * 32, xb, y, bi);
+              bulk_commit_group();
+              if (both) bulk_wait_group_read1();
+            }
+            __syncwarp();
           }
           if (p.out_hl) {
             // lanes 2i, 2i+1 trade values: the even lane stores channels (c, c+1) of pixel j as one 32-bit word per plane, the
             // odd lane channels (c-1, c) of pixel j + 1
-            const uint32_t hbase = stg + 2048u + (uint32_t)(odd * 64 + (lane & ~1) * 2);
+            const uint32_t hbase = blk_h + (uint32_t)(odd * 64 + (lane & ~1) * 2);
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               const __nv_bfloat16 h0 = __float2bfloat16_rn(v[j]), h1 = __float2bfloat16_rn(v[j + 1]);
@@ -1077,13 +1093,12 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
               asm volatile("st.shared.u32 [%0], %1;" ::"r"(hbase + (uint32_t)(j * 64)), "r"((lo_ch & 0xffffu) | (hi_ch << 16)) : "memory");
               asm volatile("st.shared.u32 [%0], %1;" ::"r"(hbase + 1024u + (uint32_t)(j * 64)), "r"((lo_ch >> 16) | (hi_ch & 0xffff0000u)) : "memory");
             }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            if (p.out_f32) tma_store_4d(&tmOF, stg, q * 32, xb, y, bi);
-            if (p.out_hl) tma_store_5d(&tmOH, stg + 2048u, q * 32, xb, y, bi, 0);
-            bulk_commit_group();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_5d(&tmOH, blk_h, q * 32, xb, y, bi, 0);
+              bulk_commit_group();
+            }
           }
         }
       }
