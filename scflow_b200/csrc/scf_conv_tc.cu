@@ -884,6 +884,8 @@ struct TctParams {
   __nv_bfloat16* out_hl; long long out_hl_plane; int out_hl_stride, out_hl_coff;
   const float* aux0; int aux0_stride;
   float* stats;                             // [num_tiles][2 warp parities][2][cout]
+  int bk;                                   // channels per stage: 64 (SWIZZLE_128B rows, 2 x 96 KB stages) or 32 (SWIZZLE_64B rows,
+                                            // 4 x 48 KB stages: same bytes in the ring, finer hand-over between TMA and MMA)
   int dbg;                                  // timing experiments (SCFLOW_TCT_DBG): 1 no epilogue global accesses, 2 no MMAs, 4 no
                                             // activation loads, 8 no weight loads
 };
@@ -904,6 +906,8 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
                  tmem_slot = smem_base + 192;
   const uint32_t staging0 = smem_base + 1024;                         // 4 KB per epilogue warp (TMA store source)
   const uint32_t tiles0 = staging0 + TCT_EW * TCT_STAGING;
+  const uint32_t row_bytes = (uint32_t)p.bk * 2u;                     // one K-major operand row of a stage
+  const uint32_t w_plane = 128u * row_bytes, p_plane = (uint32_t)TCT_PIX * row_bytes, stage_bytes = 2u * (w_plane + p_plane);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   griddep_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -950,14 +954,14 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
             for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
               mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
               const uint32_t full = bar_full + 8 * stage;
-              const uint32_t w_dst = tiles0 + stage * TCT_STAGE, p_dst = w_dst + 2 * TCT_W_PLANE;
-              const int wk = p.seg_wcoff[s] + cc * TC_BK;
-              const uint32_t txb = ((p.dbg & 4) ? 0u : 2 * TCT_P_PLANE) + ((p.dbg & 8) ? 0u : 2 * TCT_W_PLANE);
+              const uint32_t w_dst = tiles0 + stage * stage_bytes, p_dst = w_dst + 2 * w_plane;
+              const int wk = p.seg_wcoff[s] + cc * p.bk;
+              const uint32_t txb = ((p.dbg & 4) ? 0u : 2 * p_plane) + ((p.dbg & 8) ? 0u : 2 * w_plane);
               if (txb) mbar_arrive_expect_tx(full, txb); else mbar_arrive(full);
-              if (!(p.dbg & 4)) tma_load_5d(p_dst, tm, full, cc * TC_BK, cx, cy, b, 0);
+              if (!(p.dbg & 4)) tma_load_5d(p_dst, tm, full, cc * p.bk, cx, cy, b, 0);
               if (!(p.dbg & 8)) {
                 tma_load_4d(w_dst, &tmW, full, wk, 0, tap, 0);
-                tma_load_4d(w_dst + TCT_W_PLANE, &tmW, full, wk, 0, tap, 1);
+                tma_load_4d(w_dst + w_plane, &tmW, full, wk, 0, tap, 1);
               }
               if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
@@ -980,12 +984,15 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
         for (int tap = 0; tap < p.num_taps; ++tap) {
           for (int sg = 0; sg < p.nseg; ++sg) {
             for (int cc = 0; cc < p.seg_chunks[sg]; ++cc, ++c) {
-              const int ks = (cc == p.seg_chunks[sg] - 1) ? p.seg_last_ks[sg] : TC_BK / 16;
+              const int ks = (cc == p.seg_chunks[sg] - 1) ? p.seg_last_ks[sg] : p.bk / 16;
               mbar_wait(bar_full + 8 * stage, phase);
               tc_fence_after();
-              const uint32_t w_addr = tiles0 + stage * TCT_STAGE, p_addr = w_addr + 2 * TCT_W_PLANE;
-              const uint64_t w_hi = make_smem_desc_sw128(w_addr, 1024), w_lo = make_smem_desc_sw128(w_addr + TCT_W_PLANE, 1024);
-              const uint64_t p_hi = make_smem_desc_sw128(p_addr, 1024), p_lo = make_smem_desc_sw128(p_addr + TCT_P_PLANE, 1024);
+              const uint32_t w_addr = tiles0 + stage * stage_bytes, p_addr = w_addr + 2 * w_plane;
+              const bool sw64 = p.bk == 32;
+              const uint64_t w_hi = sw64 ? make_smem_desc_sw64(w_addr, 512) : make_smem_desc_sw128(w_addr, 1024);
+              const uint64_t w_lo = sw64 ? make_smem_desc_sw64(w_addr + w_plane, 512) : make_smem_desc_sw128(w_addr + w_plane, 1024);
+              const uint64_t p_hi = sw64 ? make_smem_desc_sw64(p_addr, 512) : make_smem_desc_sw128(p_addr, 1024);
+              const uint64_t p_lo = sw64 ? make_smem_desc_sw64(p_addr + p_plane, 512) : make_smem_desc_sw128(p_addr + p_plane, 1024);
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k) {
                 if (k < ks && !(p.dbg & 2)) {
@@ -1374,7 +1381,11 @@ static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.num_tiles = p.tiles_x * p.tiles_y * cdiv(d.B, TB);
   p.num_taps = d.kh * d.kw;
   p.cout = d.cout;
-  p.stages = 2;
+  {
+    const char* be = getenv("SCFLOW_TCT_BK");
+    p.bk = (be && atoi(be) == 64) ? 64 : 32;      // measured: four 48 KB stages beat two 96 KB stages by 3 % of the whole step
+  }
+  p.stages = p.bk == 32 ? 4 : 2;
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -1384,7 +1395,7 @@ static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TctParams);
   static const KernelFn table[4] = {conv_tct_kernel<SCF_ACT_NONE>, conv_tct_kernel<SCF_ACT_RELU>, conv_tct_kernel<SCF_ACT_SIGMOID>,
                                     conv_tct_kernel<SCF_ACT_TANH>};
-  const int smem = 1024 + 1024 + TCT_EW * (int)TCT_STAGING + p.stages * (int)TCT_STAGE;
+  const int smem = 1024 + 1024 + TCT_EW * (int)TCT_STAGING + 2 * (int)TCT_STAGE;     // ring = 192 KB for both stage sizes
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [smem] {
@@ -1416,11 +1427,12 @@ static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
     cuuint64_t str[4] = {(cuuint64_t)sg.stride * 2, (cuuint64_t)d.W * sg.stride * 2, (cuuint64_t)d.H * d.W * sg.stride * 2,
                          (cuuint64_t)sg.plane_stride * 2};
     const int bsx = TW == 1 ? 1 : p.sx, bsy = TH == 1 ? 1 : p.sy;
-    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)(TW * bsx), (cuuint32_t)(TH * bsy), (cuuint32_t)TB, 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.bk, (cuuint32_t)(TW * bsx), (cuuint32_t)(TH * bsy), (cuuint32_t)TB, 2};
     cuuint32_t estr[5] = {1, (cuuint32_t)bsx, (cuuint32_t)bsy, 1, 1};
-    SCF_TRY(encode_map(&tmP[s], base, 5, dims, str, box, estr));
-    p.seg_chunks[s] = cdiv(sg.nch, TC_BK);
-    p.seg_last_ks[s] = cdiv(sg.nch - (p.seg_chunks[s] - 1) * TC_BK, 16);
+    SCF_TRY(encode_map(&tmP[s], base, 5, dims, str, box, estr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                       p.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
+    p.seg_chunks[s] = cdiv(sg.nch, p.bk);
+    p.seg_last_ks[s] = cdiv(sg.nch - (p.seg_chunks[s] - 1) * p.bk, 16);
     p.seg_wcoff[s] = wcoff;
     wcoff += sg.nch;
   }
@@ -1429,9 +1441,10 @@ static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
     cuuint64_t dims[4] = {(cuuint64_t)d.cin_pad, (cuuint64_t)d.cout_pad, (cuuint64_t)p.num_taps, 2};
     cuuint64_t str[3] = {(cuuint64_t)d.cin_pad * 2, (cuuint64_t)d.cout_pad * d.cin_pad * 2,
                          d.w_plane_stride > 0 ? (cuuint64_t)d.w_plane_stride * 2 : (cuuint64_t)p.num_taps * d.cout_pad * d.cin_pad * 2};
-    cuuint32_t box[4] = {(cuuint32_t)TC_BK, 128, 1, 1};       // rows >= cout_pad: zero fill
+    cuuint32_t box[4] = {(cuuint32_t)p.bk, 128, 1, 1};       // rows >= cout_pad: zero fill
     SCF_REQUIRE(reinterpret_cast<uintptr_t>(d.w) % 16 == 0, SCF_ERR_ALIGN, "scf_conv2d_tc: packed weight must be 16B aligned");
-    SCF_TRY(encode_map(&tmW, d.w, 4, dims, str, box));
+    SCF_TRY(encode_map(&tmW, d.w, 4, dims, str, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                       p.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
   }
   // output maps of the epilogue's TMA stores: box = 32 channels x 16 pixels of one row (both bf16 planes in one store)
   CUtensorMap tmOF = tmW, tmOH = tmW;

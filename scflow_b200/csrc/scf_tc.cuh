@@ -228,6 +228,16 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 
+// Same for SWIZZLE_64B tiles (rows of 64 B = 32 bf16, 8-row groups 512 B apart when dense): layout type 4.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                             // SWIZZLE_64B
+  return d;
+}
+
 // Instruction descriptor, kind::f16: D=F32, A=B=BF16, both K-major, dense, no negate.
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

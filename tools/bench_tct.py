@@ -15,8 +15,10 @@ LAYERS = [  # name, batch, size, cin, cout, kernel, stride
     ('enc128_s2', 64, 64, 96, 128, (3, 3), 2), ('enc128_3x3', 64, 32, 128, 128, (3, 3), 1), ('enc_1x1', 64, 32, 128, 128, (1, 1), 1),
     ('out_3x3', 32, 32, 256, 126, (3, 3), 1), ('flow2_3x3', 32, 32, 128, 64, (3, 3), 1),
 ]
-VARIANTS = [('rows', {'SCFLOW_TC_T': '0'}), ('T', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '0'}),
-            ('T noepi', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '1'}), ('T nomma', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '3'}),
+VARIANTS = [('rows', {'SCFLOW_TC_T': '0'}), ('T', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '0', 'SCFLOW_TCT_BK': '64'}),
+            ('T bk32', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '0', 'SCFLOW_TCT_BK': '32'}),
+            ('bk32 noepi', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '1', 'SCFLOW_TCT_BK': '32'}),
+            ('T noepi', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '1', 'SCFLOW_TCT_BK': '64'}), ('T nomma', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '3'}),
             ('T noload', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '13'}), ('T epi only', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '14'})]
 dev = 'cuda'
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -40,7 +42,7 @@ for name, b, hw, cin, cout, k, stride in LAYERS:
             fn()
         torch.cuda.synchronize()
         tag = ''
-        if vn in ('rows', 'T'):
+        if vn in ('rows', 'T', 'T bk32'):
             cur = (S.ops.unsplit(out).clone(), of.clone())
             if ref is None:
                 ref = cur
