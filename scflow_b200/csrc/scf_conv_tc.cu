@@ -25,7 +25,7 @@ constexpr int TC_BK = 64;
 constexpr int TC_STAGE_ROW = 80;  // epilogue staging: 32 rows x 64 B per warp, rows padded to 80 B (conflict-free 16 B accesses)
 __host__ __device__ constexpr int tc_header(int ew) { return 1024 + ew * 32 * TC_STAGE_ROW + 2048; }   // barriers + staging + 2 bias buffers (multiple of 1024)
 constexpr uint32_t TC_A_PLANE = TC_BM * TC_BK * 2;   // 16 KB
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_STAGES = 4;      // 64-channel stages; 32-channel stages: 7
 
 struct TcParams {
   int nseg, seg_chunks[3], seg_wcoff[3];
@@ -47,6 +47,8 @@ struct TcParams {
                                  // the shared-memory traffic per FLOP (operand reads + TMA fills), the resource a single-CTA
                                  // tile saturates first
   int BN, cout, num_taps, w_batched, stages;
+  int bk;                        // channels per stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows; twice the stages in the same
+                                 // ring, finer hand-over between TMA and the MMA issuer); halo mode is always 64
   int acc_cols, tmem_cols;       // TMEM columns of one accumulator buffer / allocated (two buffers)
   int dbg_epi;                   // timing experiments only (SCFLOW_TC_DBG_EPI): 1 = skip epilogue loads, 2 = skip stores
   long long* dbg_times;          // optional [grid][8] globaltimer stamps of each CTA's first tile (tools/trace_conv_tc.py)
@@ -285,11 +287,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t stage0 = smem_base + 1024;
   const uint32_t bias0 = smem_base + 1024 + EW * 32 * TC_STAGE_ROW;
   const uint32_t tiles0 = smem_base + tc_header(EW);
-  const uint32_t b_plane = (uint32_t)(PAIR ? p.BN / 2 : p.BN) * 128u;    // weight rows held by this CTA
+  const uint32_t rowb = (uint32_t)p.bk * 2u;                              // bytes of one K-major operand row of a stage (128 or 64)
+  const uint32_t ta_plane = 128u * rowb;                                  // one bf16 plane of the activation tile
+  const uint32_t b_plane = (uint32_t)(PAIR ? p.BN / 2 : p.BN) * rowb;     // weight rows held by this CTA
   // pair + stacked-N: region X = one whole weight plane (hi in the leader, lo in the peer: together the stacked [W_hi; W_lo]
   // operand of the N = 2*BN MMA), region Y = this CTA's half of W_hi (the B operand of the A_lo * W_hi MMA)
   const bool pstack = PAIR && p.stackn;
-  const uint32_t stage_bytes = 2 * TC_A_PLANE + (pstack ? 3 * b_plane : 2 * b_plane);
+  const uint32_t stage_bytes = 2 * ta_plane + (pstack ? 3 * b_plane : 2 * b_plane);
   const uint32_t a_plane = (uint32_t)(p.PW * p.PH) * 128u;                        // halo mode: one bf16 plane of the halo tile
   const uint32_t a_stage = (2u * a_plane + 1023u) & ~1023u;
   const uint32_t bring0 = tiles0 + (uint32_t)p.a_stages * a_stage;                // halo mode: start of the weight ring
@@ -393,14 +397,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
               const uint32_t full = bar_full + 8 * stage;
               const uint32_t a_dst = tiles0 + stage * stage_bytes;
-              const uint32_t w_dst = a_dst + 2 * TC_A_PLANE;
-              const int wk = p.seg_wcoff[s] + cc * TC_BK, wt = p.w_batched ? b : tap;
+              const uint32_t w_dst = a_dst + 2 * ta_plane;
+              const int wk = p.seg_wcoff[s] + cc * p.bk, wt = p.w_batched ? b : tap;
               if (PAIR) {
                 // both CTAs' loads complete on the LEADER's barrier (it issues the pair's MMAs); each brings its A tile and
                 // its half of the weight rows
                 const uint32_t lfull = mapa_shared(full, 0);
                 if (crank == 0) mbar_arrive_expect_tx(full, 2 * stage_bytes);
-                tma_load_5d_2cta(a_dst, tm, lfull, cc * TC_BK, cx, cy, b, 0);
+                tma_load_5d_2cta(a_dst, tm, lfull, cc * p.bk, cx, cy, b, 0);
                 if (pstack) {
                   tma_load_4d_2cta(w_dst, &tmW, lfull, wk, n0, wt, crank);                          // X: plane `crank`, rows [0, BN/2)
                   tma_load_4d_2cta(w_dst + b_plane, &tmW, lfull, wk, n0 + w_rows, wt, crank);       //    ... rows [BN/2, BN)
@@ -413,12 +417,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 continue;
               }
               mbar_arrive_expect_tx(full, stage_bytes);
-              tma_load_5d(a_dst, tm, full, cc * TC_BK, cx, cy, b, 0);
+              tma_load_5d(a_dst, tm, full, cc * p.bk, cx, cy, b, 0);
               if (p.cluster == 1) {
                 tma_load_4d(w_dst, &tmW, full, wk, n0, wt, 0);
                 tma_load_4d(w_dst + b_plane, &tmW, full, wk, n0, wt, 1);
               } else {       // this CTA's share of both weight planes, delivered to every CTA of the cluster
-                const uint32_t off = (uint32_t)(crank * w_rows) * 128u;
+                const uint32_t off = (uint32_t)(crank * w_rows) * rowb;
                 tma_load_4d_mc(w_dst + off, &tmW, full, wk, n0 + crank * w_rows, wt, 0, cmask);
                 tma_load_4d_mc(w_dst + b_plane + off, &tmW, full, wk, n0 + crank * w_rows, wt, 1, cmask);
               }
@@ -516,16 +520,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int tap = 0; tap < p.num_taps; ++tap) {
           for (int sg = 0; sg < p.nseg; ++sg) {
             for (int cc = 0; cc < p.seg_chunks[sg]; ++cc, ++c) {
-              const int ks = (cc == p.seg_chunks[sg] - 1) ? p.seg_last_ks[sg] : TC_BK / 16;   // skip all-zero k-steps of a ragged chunk
+              const int ks = (cc == p.seg_chunks[sg] - 1) ? p.seg_last_ks[sg] : p.bk / 16;   // skip all-zero k-steps of a ragged chunk
               mbar_wait(bar_full + 8 * stage, phase);
               tc_fence_after();
               if (it == 0 && c == 0) stamp(2);
               const uint32_t a_addr = tiles0 + stage * stage_bytes;
-              const uint64_t a_hi = make_smem_desc_sw128(a_addr, 1024), a_lo = make_smem_desc_sw128(a_addr + TC_A_PLANE, 1024);
-              const uint64_t b_hi = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE, 1024);
-              const uint64_t b_lo = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + b_plane, 1024);
+              // 64-channel stages: SWIZZLE_128B rows; 32-channel stages (twice as many, same ring bytes): SWIZZLE_64B rows
+              auto mk = [&](uint32_t addr) { return p.bk == 32 ? make_smem_desc_sw64(addr, 512) : make_smem_desc_sw128(addr, 1024); };
+              const uint64_t a_hi = mk(a_addr), a_lo = mk(a_addr + ta_plane);
+              const uint64_t b_hi = mk(a_addr + 2 * ta_plane);
+              const uint64_t b_lo = mk(a_addr + 2 * ta_plane + b_plane);
               if (PAIR && pstack) {
-                const uint64_t b_y = make_smem_desc_sw128(a_addr + 2 * TC_A_PLANE + 2 * b_plane, 1024);
+                const uint64_t b_y = mk(a_addr + 2 * ta_plane + 2 * b_plane);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k)
                   if (k < ks) umma_bf16_2cta(d_tmem, a_hi + (uint64_t)(k * 32 >> 4), b_hi + (uint64_t)(k * 32 >> 4), idesc2, (c > 0 || k > 0) ? 1u : 0u);   // A_hi * [W_hi; W_lo]
@@ -1535,7 +1541,12 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     SCF_CUDA(cudaGetDevice(&dev));
     SCF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  int stage_bytes = 2 * (int)TC_A_PLANE + 2 * p.BN * 128;
+  {
+    const char* be = getenv("SCFLOW_TC_BK");
+    p.bk = (be && atoi(be) == 32) ? 32 : 64;
+  }
+  const int rowb = p.bk * 2, max_stages = p.bk == 32 ? 7 : TC_MAX_STAGES;
+  int stage_bytes = 2 * 128 * rowb + 2 * p.BN * rowb;
   // epilogue warps: 8 (two per TMEM lane quarter) for the one-CTA-per-SM configuration - the epilogue's global loads
   // (GRU gates, residuals) need the extra memory-level parallelism - and 4 for the small-tile two-CTAs-per-SM mode
   int ew = 8;
@@ -1544,7 +1555,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     if (ev && atoi(ev) == 4) ew = 4;
   }
   p.stages = (232448 - 1024 - tc_header(ew)) / stage_bytes;
-  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  if (p.stages > max_stages) p.stages = max_stages;
   SCF_REQUIRE(p.stages >= 2, SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: tile does not fit in shared memory");
   {
     const char* sv = getenv("SCFLOW_TC_STACKN");
@@ -1591,9 +1602,11 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     // CTAs' main loops interleave; larger tiles run one persistent CTA per SM with double-buffered accumulators.
     const char* ov = getenv("SCFLOW_TC_OCC2");
     const bool occ2 = ov ? atoi(ov) != 0 : true;
-    if (occ2 && 2 * stage_bytes + 1024 + tc_header(4) <= 115712 && p.tmem_cols <= 256 && p.num_tiles >= 4 * num_sms) {
+    // (the decision is made on the 64-channel stage size so that the stage granularity does not change the mode)
+    if (occ2 && 2 * (stage_bytes * 128 / rowb) + 1024 + tc_header(4) <= 115712 && p.tmem_cols <= 256 && p.num_tiles >= 4 * num_sms) {
       ew = 4;
       p.stages = (115712 - 1024 - tc_header(4)) / stage_bytes;
+      if (p.stages > max_stages) p.stages = max_stages;
       ctas_per_sm = 2;
     }
   }
@@ -1612,9 +1625,9 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
       ew = 8;
       // BN > 128: three MMAs of N = BN, each CTA holds BN/2 rows of both weight planes.  BN <= 128 (stacked-N): the leader
       // holds W_hi, the peer W_lo (= the two halves of the stacked [W_hi; W_lo] operand) plus half of W_hi each
-      stage_bytes = 2 * (int)TC_A_PLANE + (p.stackn ? 3 : 2) * (p.BN / 2) * 128;
+      stage_bytes = 2 * 128 * rowb + (p.stackn ? 3 : 2) * (p.BN / 2) * rowb;
       p.stages = (232448 - 1024 - tc_header(ew)) / stage_bytes;
-      if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+      if (p.stages > max_stages) p.stages = max_stages;
       p.splitacc = 0; p.dualacc = 0;
       p.acc_cols = p.stackn ? 2 * p.BN : p.BN;
       p.tmem_cols = 32;
@@ -1641,6 +1654,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
       if (sb > 8) sb = 8;
       if (sb >= 2) {
         p.halo = 1; p.PW = PW; p.PH = PH; p.a_stages = sa; p.b_stages = sb;
+        p.bk = 64;
         p.TW = 8; p.TH = 16; p.TB = 1;
         p.tiles_x = cdiv(p.W, 8); p.tiles_y = cdiv(p.H, 16);
         p.m_tiles = p.tiles_x * p.tiles_y * d.B;
@@ -1717,12 +1731,13 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     // box = elements TRAVERSED per dimension; with element strides (1,s,s,1,1) it deposits TW x TH x TB pixels
     // a one-row (one-column) tile needs no element stride along that axis: the producer's coordinate already carries it
     const int bsx = p.TW == 1 ? 1 : p.sx, bsy = p.TH == 1 ? 1 : p.sy;
-    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.TW * bsx), (cuuint32_t)(p.TH * bsy), (cuuint32_t)p.TB, 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.bk, (cuuint32_t)(p.TW * bsx), (cuuint32_t)(p.TH * bsy), (cuuint32_t)p.TB, 2};
     if (p.halo) { box[1] = (cuuint32_t)p.PW; box[2] = (cuuint32_t)p.PH; }
     cuuint32_t estr[5] = {1, (cuuint32_t)bsx, (cuuint32_t)bsy, 1, 1};
-    SCF_TRY(encode_map(&tmA[s], base, 5, dims, str, box, estr));
-    p.seg_chunks[s] = cdiv(sg.nch, TC_BK);
-    p.seg_last_ks[s] = cdiv(sg.nch - (p.seg_chunks[s] - 1) * TC_BK, 16);
+    const CUtensorMapSwizzle swz = p.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    SCF_TRY(encode_map(&tmA[s], base, 5, dims, str, box, estr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, swz));
+    p.seg_chunks[s] = cdiv(sg.nch, p.bk);
+    p.seg_last_ks[s] = cdiv(sg.nch - (p.seg_chunks[s] - 1) * p.bk, 16);
     p.seg_wcoff[s] = wcoff;
     wcoff += sg.nch;
   }
@@ -1732,9 +1747,10 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     cuuint64_t dims[4] = {(cuuint64_t)d.cin_pad, (cuuint64_t)d.cout_pad, (cuuint64_t)third, 2};
     cuuint64_t str[3] = {(cuuint64_t)d.cin_pad * 2, (cuuint64_t)d.cout_pad * d.cin_pad * 2,
                          d.w_plane_stride > 0 ? (cuuint64_t)d.w_plane_stride * 2 : (cuuint64_t)third * d.cout_pad * d.cin_pad * 2};
-    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(p.BN / p.cluster), 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)p.bk, (cuuint32_t)(p.BN / p.cluster), 1, 1};
     SCF_REQUIRE(reinterpret_cast<uintptr_t>(d.w) % 16 == 0, SCF_ERR_ALIGN, "scf_conv2d_tc: packed weight must be 16B aligned");
-    SCF_TRY(encode_map(&tmW, d.w, 4, dims, str, box));
+    SCF_TRY(encode_map(&tmW, d.w, 4, dims, str, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                       p.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
   }
   {
     auto al16 = [](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0; };
