@@ -889,7 +889,14 @@ struct TctParams {
   float* out_f32; int out_f32_stride, out_f32_coff;
   __nv_bfloat16* out_hl; long long out_hl_plane; int out_hl_stride, out_hl_coff;
   const float* aux0; int aux0_stride;
+  int gru_q;                                // GRU state update epilogue: h' = (1 - z) h + z tanh(acc + pre), aux0 = h, aux1 = z
+  const float* aux1; int aux1_stride; const float* pre; int pre_stride;
   float* stats;                             // [num_tiles][2 warp parities][2][cout]
+  // halo mode (stride-1 multi-tap layers, one sample per tile): the tile is 8 x 32 pixels, its activations are fetched ONCE per
+  // channel chunk together with the (kw-1) x (kh-1) halo - PW x PH pixel rows - and every tap reads them through a row-shifted
+  // UMMA descriptor (one 8-row core-matrix group = one tile row, group stride = PW rows); weights run through their own ring
+  int halo, PW, PH, p_stages, w_stages;
+  int cw_sh;                                // log2 of the pixels per row of an epilogue chunk (16 columns = 1 x 16 or 2 x 8 pixels)
   int bk;                                   // channels per stage: 64 (SWIZZLE_128B rows, 2 x 96 KB stages) or 32 (SWIZZLE_64B rows,
                                             // 4 x 48 KB stages: same bytes in the ring, finer hand-over between TMA and MMA)
   int dbg;                                  // timing experiments (SCFLOW_TCT_DBG): 1 no epilogue global accesses, 2 no MMAs, 4 no
@@ -909,11 +916,14 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = smem_base, bar_empty = smem_base + 64, bar_tfull = smem_base + 128, bar_tempty = smem_base + 144,
-                 tmem_slot = smem_base + 192;
+                 tmem_slot = smem_base + 192, bar_pfull = smem_base + 256, bar_pempty = smem_base + 320;
   const uint32_t staging0 = smem_base + 1024;                         // 4 KB per epilogue warp (TMA store source)
   const uint32_t tiles0 = staging0 + TCT_EW * TCT_STAGING;
   const uint32_t row_bytes = (uint32_t)p.bk * 2u;                     // one K-major operand row of a stage
   const uint32_t w_plane = 128u * row_bytes, p_plane = (uint32_t)TCT_PIX * row_bytes, stage_bytes = 2u * (w_plane + p_plane);
+  const uint32_t hp_plane = (uint32_t)(p.PW * p.PH) * row_bytes;      // halo mode: one bf16 plane of the halo tile
+  const uint32_t hp_stage = (2u * hp_plane + 1023u) & ~1023u;
+  const uint32_t wring0 = tiles0 + (uint32_t)p.p_stages * hp_stage;   // halo mode: weight ring behind the activation ring
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   griddep_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -923,9 +933,13 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
     prefetch_tmap(&tmW);
     if (p.out_f32) prefetch_tmap(&tmOF);
     if (p.out_hl) prefetch_tmap(&tmOH);
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < (p.halo ? p.w_stages : p.stages); ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < p.p_stages; ++s) {
+      mbar_init(bar_pfull + 8 * s, 1);
+      mbar_init(bar_pempty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
@@ -946,12 +960,40 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       // ================= TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, hs = 0;
+      uint32_t phase = 0, hph = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const int b = (t / tiles_per_img) * TB, tr = t % tiles_per_img;
         const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
         const int x0 = tx * TW, y0 = ty * TH;
+        if (p.halo) {
+          for (int s = 0; s < p.nseg; ++s) {
+            const CUtensorMap* tm = s == 0 ? &tmP0 : (s == 1 ? &tmP1 : &tmP2);
+            for (int cc = 0; cc < p.seg_chunks[s]; ++cc) {
+              mbar_wait(bar_pempty + 8 * hs, hph ^ 1u);
+              if (p.dbg & 4) mbar_arrive(bar_pfull + 8 * hs);
+              else {
+                mbar_arrive_expect_tx(bar_pfull + 8 * hs, 2 * hp_plane);
+                tma_load_5d(tiles0 + hs * hp_stage, tm, bar_pfull + 8 * hs, cc * p.bk, x0 - p.pw, y0 - p.ph, b, 0);
+              }
+              if (++hs == p.p_stages) { hs = 0; hph ^= 1u; }
+              const int wk = p.seg_wcoff[s] + cc * p.bk;
+              for (int tap = 0; tap < p.num_taps; ++tap) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                const uint32_t full = bar_full + 8 * stage;
+                const uint32_t w_dst = wring0 + stage * 2 * w_plane;
+                if (p.dbg & 8) mbar_arrive(full);
+                else {
+                  mbar_arrive_expect_tx(full, 2 * w_plane);
+                  tma_load_4d(w_dst, &tmW, full, wk, 0, tap, 0);
+                  tma_load_4d(w_dst + w_plane, &tmW, full, wk, 0, tap, 1);
+                }
+                if (++stage == p.w_stages) { stage = 0; phase ^= 1u; }
+              }
+            }
+          }
+          continue;
+        }
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
           const int cx = x0 * p.sx + kx - p.pw, cy = y0 * p.sy + ky - p.ph;
@@ -979,13 +1021,51 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
     if (lane == 0) {
       // ================= MMA issuer: D[channel][pixel] += W[channel][k] * P[pixel][k]  (split-bf16: hi*hi + hi*lo + lo*hi)
       const uint32_t idesc = make_idesc_bf16(128, TCT_PIX);
-      int stage = 0, it = 0;
-      uint32_t phase = 0;
+      int stage = 0, it = 0, hs = 0;
+      uint32_t phase = 0, hph = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
         const int acc = it & 1;
         mbar_wait(bar_tempty + 8 * acc, (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TCT_PIX);
+        if (p.halo) {
+          // tap (ky, kx) = the halo tile read from pixel-row offset ky*PW + kx (the swizzle is a function of the absolute
+          // shared-memory address for TMA and UMMA alike, so any row offset is a valid operand start)
+          const uint32_t p_sbo = (uint32_t)p.PW * row_bytes;
+          bool first = true;
+          for (int sg = 0; sg < p.nseg; ++sg) {
+            for (int cc = 0; cc < p.seg_chunks[sg]; ++cc) {
+              const int ks = (cc == p.seg_chunks[sg] - 1) ? p.seg_last_ks[sg] : p.bk / 16;
+              mbar_wait(bar_pfull + 8 * hs, hph);
+              const uint32_t p_base = tiles0 + hs * hp_stage;
+              for (int tap = 0; tap < p.num_taps; ++tap) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                const uint32_t p_addr = p_base + (uint32_t)(ky * p.PW + kx) * row_bytes;
+                const uint32_t w_addr = wring0 + stage * 2 * w_plane;
+                const uint64_t w_hi = make_smem_desc_sw64(w_addr, 512), w_lo = make_smem_desc_sw64(w_addr + w_plane, 512);
+                const uint64_t p_hi = make_smem_desc_sw64(p_addr, p_sbo), p_lo = make_smem_desc_sw64(p_addr + hp_plane, p_sbo);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  if (k < ks && !(p.dbg & 2)) {
+                    const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                    umma_bf16(d_tmem, w_hi + ko, p_hi + ko, idesc, (!first || k > 0) ? 1u : 0u);
+                    umma_bf16(d_tmem, w_hi + ko, p_lo + ko, idesc, 1u);
+                    umma_bf16(d_tmem, w_lo + ko, p_hi + ko, idesc, 1u);
+                  }
+                }
+                first = false;
+                umma_commit(bar_empty + 8 * stage);
+                if (++stage == p.w_stages) { stage = 0; phase ^= 1u; }
+              }
+              umma_commit(bar_pempty + 8 * hs);        // every tap of this chunk has read the halo tile
+              if (++hs == p.p_stages) { hs = 0; hph ^= 1u; }
+            }
+          }
+          umma_commit(bar_tfull + 8 * acc);
+          continue;
+        }
         int c = 0;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           for (int sg = 0; sg < p.nseg; ++sg) {
@@ -1024,7 +1104,7 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
     const bool cvalid = c < p.cout;
     const bool warp_active = q * 32 < p.cout;
     const float bias_c = (p.bias && cvalid) ? __ldg(p.bias + c) : 0.f;
-    const int tw_mask = TW - 1, th_mask = TH - 1, b_sh = p.tw_sh + p.th_sh, odd = lane & 1;
+    const int tw_mask = TW - 1, th_mask = TH - 1, b_sh = p.tw_sh + p.th_sh, odd = lane & 1, cwm = (1 << p.cw_sh) - 1;
     const uint32_t stg = staging0 + (uint32_t)(warp - 2) * TCT_STAGING;
     const bool both = p.out_f32 && p.out_hl;
     uint32_t kc = 0;                      // chunks staged so far (staging block parity)
@@ -1042,22 +1122,45 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
 #pragma unroll 1
         for (int ch = par; ch < TCT_PIX / 16; ch += TCT_EW / 4) {
           float v[16];
-          __syncwarp();
-          tmem_ld16(t_addr + (uint32_t)(ch * 16), v);
-          // The tile is at least 32 pixels wide, so a 16-column chunk is a run of one tile row.  The warp writes its
+          if (!(ACT == SCF_ACT_TANH && p.gru_q)) {
+            __syncwarp();
+            tmem_ld16(t_addr + (uint32_t)(ch * 16), v);
+          }
+          // A 16-column chunk is a run of 16 pixels of one tile row (tiles >= 32 wide) or two rows of an 8-wide halo-mode
+          // tile.  The warp writes its
           // [16 pixels][32 channels] block to shared memory in NHWC order (conflict-free: lanes = consecutive channels, constant
           // offsets) and one TMA store per output moves it out; the tensor map clips pixels beyond the row / image / batch and
           // channels beyond cout, so the stores need no predicates.  (A first version with per-thread global stores spent
           // ~70 instructions per pixel pair on 64-bit addressing and predicates and was issue-bound at 1.6 TB/s.)
           const int col0 = ch * 16;
           const int xb = x0 + (col0 & tw_mask), y = y0 + ((col0 >> p.tw_sh) & th_mask), bi = b + (col0 >> b_sh);
-          int nvalid = p.W - xb;
-          nvalid = (y < p.H && bi < p.B) ? (nvalid < 16 ? nvalid : 16) : 0;      // negative = none
-          if (p.aux0 && cvalid) {                                                  // residual, added before the activation
+          const int nvx = p.W - xb, nvy = bi < p.B ? p.H - y : 0;                // valid pixels per chunk row / valid chunk rows
+          auto okj = [&](int j) { return (j & cwm) < nvx && (j >> p.cw_sh) < nvy; };
+          auto offj = [&](int j) { return (long long)((j >> p.cw_sh) * p.W + (j & cwm)); };   // pixel offset inside the chunk
+          if (ACT == SCF_ACT_TANH && p.gru_q) {
+            // SepConvGRU state update (raft_decoder.py:235-253): all inputs of the chunk are requested before the accumulator
+            // is read so that their latencies overlap
+            const long long pix0 = ((long long)bi * p.H + y) * p.W + xb;
+            const float* hp = p.aux0 + pix0 * p.aux0_stride + c;
+            const float* zp = p.aux1 + pix0 * p.aux1_stride + c;
+            const float* pp = p.pre + pix0 * p.pre_stride + c;
+            float hv[16], zv[16], pv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const bool ok = okj(j) && cvalid;
+              hv[j] = ok ? __ldg(hp + offj(j) * p.aux0_stride) : 0.f;
+              zv[j] = ok ? __ldg(zp + offj(j) * p.aux1_stride) : 0.f;
+              pv[j] = (ok && p.pre) ? __ldg(pp + offj(j) * p.pre_stride) : 0.f;
+            }
+            __syncwarp();
+            tmem_ld16(t_addr + (uint32_t)(ch * 16), v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = (1.f - zv[j]) * hv[j] + zv[j] * tanh_fast(fmaf(v[j], p.scale, bias_c) + pv[j]);
+          } else if (p.aux0 && cvalid) {                                           // residual, added before the activation
             const float* ax = p.aux0 + (((long long)bi * p.H + y) * p.W + xb) * p.aux0_stride + c;
             float rv[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) rv[j] = j < nvalid ? __ldg(ax + (long long)j * p.aux0_stride) : 0.f;
+            for (int j = 0; j < 16; ++j) rv[j] = okj(j) ? __ldg(ax + offj(j) * p.aux0_stride) : 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = act_ct<ACT>(fmaf(v[j], p.scale, bias_c) + rv[j]);
           } else {
@@ -1067,7 +1170,7 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
           if (p.stats) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (j < nvalid) { ssum += v[j]; qsum = fmaf(v[j], v[j], qsum); }
+              if (okj(j)) { ssum += v[j]; qsum = fmaf(v[j], v[j], qsum); }
           }
           // Staging: 4 KB per warp.  One output kind: two 2 KB blocks used alternately; both kinds: the fp32 block and the
           // bf16 block each go out as their own bulk group.  Either way a block is rewritten only after the group that read it
@@ -1355,9 +1458,22 @@ static bool tct_eligible(const scf_tc_conv_desc& d) {
   if (mode == 1) {
     int cin = 0;
     for (int s = 0; s < d.nseg; ++s) cin += d.seg[s].nch;
-    if (d.cout <= 64 && cin * d.kh * d.kw < 1024) return false;
+    if (d.cout <= 64 && cin * d.kh * d.kw < 1024) {
+      // SCFLOW_TCT_SMALL64=1: take them anyway when the halo form applies on a large map (measured alone 289 us against
+      // 302 us on the 64-channel 128 x 128 encoder layers, but +0.05 ms on the whole step: off)
+      const char* he = getenv("SCFLOW_TCT_HALO");
+      const bool halo = (he ? atoi(he) != 0 : true) && d.kh * d.kw > 1 && d.stride != 2 && d.stride_x != 2 && d.stride_y != 2;
+      const char* s64 = getenv("SCFLOW_TCT_SMALL64");
+      if (!(halo && (s64 ? atoi(s64) != 0 : false) && (long long)d.B * d.H * d.W >= 4LL * 148 * 256)) return false;
+    }
   }
-  if (d.epi != SCF_EPI_ACT || d.w_batched || d.pre || d.cout_pad > 128 || d.act < SCF_ACT_NONE || d.act > SCF_ACT_TANH) return false;
+  if (d.w_batched || d.cout_pad > 128 || d.act < SCF_ACT_NONE || d.act > SCF_ACT_TANH) return false;
+  if (d.epi == SCF_EPI_GRU_Q) {
+    const char* qe = getenv("SCFLOW_TC_T_GRUQ");
+    if (!(qe ? atoi(qe) != 0 : true) || d.act != SCF_ACT_TANH || !d.aux0 || !d.aux1 || d.stats) return false;
+  } else if (d.epi != SCF_EPI_ACT || d.pre) {
+    return false;
+  }
   {
     const int sx = d.stride_x ? d.stride_x : (d.stride == 2 ? 2 : 1);
     if ((d.W + 2 * (d.kw / 2) - d.kw) / sx + 1 < 24) return false;      // tiles are at least 32 pixels wide
@@ -1382,16 +1498,32 @@ static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.B = d.B; p.H = (d.H + 2 * p.ph - d.kh) / p.sy + 1; p.W = (d.W + 2 * p.pw - d.kw) / p.sx + 1;
   SCF_REQUIRE(tct_pick_tile(d.B, p.H, p.W, p.sx, p.sy, d.stats != nullptr, p.tw_sh, p.th_sh), SCF_ERR_UNSUPPORTED,
               "scf_conv2d_tc: no transposed tiling");
-  const int TW = 1 << p.tw_sh, TH = 1 << p.th_sh, TB = TCT_PIX >> (p.tw_sh + p.th_sh);
-  p.tiles_x = cdiv(p.W, TW); p.tiles_y = cdiv(p.H, TH);
-  p.num_tiles = p.tiles_x * p.tiles_y * cdiv(d.B, TB);
-  p.num_taps = d.kh * d.kw;
-  p.cout = d.cout;
   {
     const char* be = getenv("SCFLOW_TCT_BK");
     p.bk = (be && atoi(be) == 64) ? 64 : 32;      // measured: four 48 KB stages beat two 96 KB stages by 3 % of the whole step
   }
   p.stages = p.bk == 32 ? 4 : 2;
+  {
+    // halo mode: 8 x 32 pixel tiles (one sample each), activations once per channel chunk, weights per tap in their own ring
+    const char* he = getenv("SCFLOW_TCT_HALO");
+    const bool want = he ? atoi(he) != 0 : true;       // measured: +1 % of the step (encoder layers 2-15 % each)
+    if (want && p.bk == 32 && p.sx == 1 && p.sy == 1 && d.kh * d.kw > 1) {
+      const int PW = 8 + d.kw - 1, PH = 32 + d.kh - 1;
+      const int hp_stage = (2 * PW * PH * 64 + 1023) / 1024 * 1024;
+      int ws = (2 * (int)TCT_STAGE - 2 * hp_stage) / (2 * 128 * 64);
+      if (ws > 8) ws = 8;
+      if (ws >= 3) {
+        p.halo = 1; p.PW = PW; p.PH = PH; p.p_stages = 2; p.w_stages = ws;
+        p.tw_sh = 3; p.th_sh = 5;
+      }
+    }
+  }
+  p.cw_sh = p.tw_sh < 4 ? p.tw_sh : 4;
+  const int TW = 1 << p.tw_sh, TH = 1 << p.th_sh, TB = TCT_PIX >> (p.tw_sh + p.th_sh);
+  p.tiles_x = cdiv(p.W, TW); p.tiles_y = cdiv(p.H, TH);
+  p.num_tiles = p.tiles_x * p.tiles_y * cdiv(d.B, TB);
+  p.num_taps = d.kh * d.kw;
+  p.cout = d.cout;
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -1416,6 +1548,8 @@ static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.out_hl = reinterpret_cast<__nv_bfloat16*>(d.out_hl); p.out_hl_plane = d.out_hl_plane; p.out_hl_stride = d.out_hl_stride;
   p.out_hl_coff = d.out_hl_coff;
   p.aux0 = d.aux0; p.aux0_stride = d.aux0_stride;
+  p.gru_q = d.epi == SCF_EPI_GRU_Q ? 1 : 0;
+  p.aux1 = d.aux1; p.aux1_stride = d.aux1_stride; p.pre = d.pre; p.pre_stride = d.pre_stride;
   p.stats = d.stats;
   { const char* de = getenv("SCFLOW_TCT_DBG"); p.dbg = de ? atoi(de) : 0; }
   if (d.stats) SCF_REQUIRE(TB == 1, SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: stats need one sample per tile");
@@ -1434,6 +1568,7 @@ static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
                          (cuuint64_t)sg.plane_stride * 2};
     const int bsx = TW == 1 ? 1 : p.sx, bsy = TH == 1 ? 1 : p.sy;
     cuuint32_t box[5] = {(cuuint32_t)p.bk, (cuuint32_t)(TW * bsx), (cuuint32_t)(TH * bsy), (cuuint32_t)TB, 2};
+    if (p.halo) { box[1] = (cuuint32_t)p.PW; box[2] = (cuuint32_t)p.PH; }
     cuuint32_t estr[5] = {1, (cuuint32_t)bsx, (cuuint32_t)bsy, 1, 1};
     SCF_TRY(encode_map(&tmP[s], base, 5, dims, str, box, estr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                        p.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
@@ -1457,14 +1592,14 @@ static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
   if (d.out_f32) {
     cuuint64_t dims[4] = {(cuuint64_t)d.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)d.B};
     cuuint64_t str[3] = {(cuuint64_t)d.out_f32_stride * 4, (cuuint64_t)p.W * d.out_f32_stride * 4, (cuuint64_t)p.H * p.W * d.out_f32_stride * 4};
-    cuuint32_t box[4] = {32, 16, 1, 1};
+    cuuint32_t box[4] = {32, (cuuint32_t)(1 << p.cw_sh), (cuuint32_t)(16 >> p.cw_sh), 1};
     SCF_TRY(encode_map(&tmOF, d.out_f32 + d.out_f32_coff, 4, dims, str, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE));
   }
   if (d.out_hl) {
     cuuint64_t dims[5] = {(cuuint64_t)d.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)d.B, 2};
     cuuint64_t str[4] = {(cuuint64_t)d.out_hl_stride * 2, (cuuint64_t)p.W * d.out_hl_stride * 2, (cuuint64_t)p.H * p.W * d.out_hl_stride * 2,
                          (cuuint64_t)d.out_hl_plane * 2};
-    cuuint32_t box[5] = {32, 16, 1, 1, 2};
+    cuuint32_t box[5] = {32, (cuuint32_t)(1 << p.cw_sh), (cuuint32_t)(16 >> p.cw_sh), 1, 2};
     SCF_TRY(encode_map(&tmOH, reinterpret_cast<const __nv_bfloat16*>(d.out_hl) + d.out_hl_coff, 5, dims, str, box, nullptr,
                        CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_NONE));
   }

@@ -16,10 +16,12 @@ LAYERS = [  # name, batch, size, cin, cout, kernel, stride
     ('out_3x3', 32, 32, 256, 126, (3, 3), 1), ('flow2_3x3', 32, 32, 128, 64, (3, 3), 1),
 ]
 VARIANTS = [('rows', {'SCFLOW_TC_T': '0'}), ('T', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '0', 'SCFLOW_TCT_BK': '64'}),
-            ('T bk32', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '0', 'SCFLOW_TCT_BK': '32'}),
-            ('bk32 noepi', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '1', 'SCFLOW_TCT_BK': '32'}),
+            ('T bk32', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '0', 'SCFLOW_TCT_BK': '32', 'SCFLOW_TCT_HALO': '0'}),
+            ('T halo', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '0', 'SCFLOW_TCT_BK': '32', 'SCFLOW_TCT_HALO': '1'}),
+            ('halo noepi', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '1', 'SCFLOW_TCT_BK': '32', 'SCFLOW_TCT_HALO': '1'}),
+            ('bk32 noepi', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '1', 'SCFLOW_TCT_BK': '32', 'SCFLOW_TCT_HALO': '0'}),
             ('T noepi', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '1', 'SCFLOW_TCT_BK': '64'}), ('T nomma', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '3'}),
-            ('T noload', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '13'}), ('T epi only', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '14'})]
+            ('T noload', {'SCFLOW_TC_T': '2', 'SCFLOW_TCT_DBG': '13'})]
 dev = 'cuda'
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 g = torch.Generator().manual_seed(0)
@@ -42,7 +44,7 @@ for name, b, hw, cin, cout, k, stride in LAYERS:
             fn()
         torch.cuda.synchronize()
         tag = ''
-        if vn in ('rows', 'T', 'T bk32'):
+        if vn in ('rows', 'T', 'T bk32', 'T halo'):
             cur = (S.ops.unsplit(out).clone(), of.clone())
             if ref is None:
                 ref = cur
