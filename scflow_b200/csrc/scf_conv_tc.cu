@@ -1114,6 +1114,27 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
       const int b = (t / tiles_per_img) * TB, tr = t % tiles_per_img;
       const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
       const int x0 = tx * TW, y0 = ty * TH;
+      // GRU q: h, z and the context term of a chunk are requested one chunk ahead (the first one before the accumulator is
+      // complete), so their latency hides behind the main loop's tail / the previous chunk's stores
+      float nh[16], nz[16], npre[16];
+      auto gru_issue = [&](int ch) {
+        const int col0 = ch * 16;
+        const int xb = x0 + (col0 & tw_mask), y = y0 + ((col0 >> p.tw_sh) & th_mask), bi = b + (col0 >> b_sh);
+        const int nvx = p.W - xb, nvy = bi < p.B ? p.H - y : 0;
+        const long long pix0 = ((long long)bi * p.H + y) * p.W + xb;
+        const float* hp = p.aux0 + pix0 * p.aux0_stride + c;
+        const float* zp = p.aux1 + pix0 * p.aux1_stride + c;
+        const float* pp = p.pre + pix0 * p.pre_stride + c;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const bool ok = (j & cwm) < nvx && (j >> p.cw_sh) < nvy && cvalid;
+          const long long off = (long long)((j >> p.cw_sh) * p.W + (j & cwm));
+          nh[j] = ok ? __ldg(hp + off * p.aux0_stride) : 0.f;
+          nz[j] = ok ? __ldg(zp + off * p.aux1_stride) : 0.f;
+          npre[j] = (ok && p.pre) ? __ldg(pp + off * p.pre_stride) : 0.f;
+        }
+      };
+      if (ACT == SCF_ACT_TANH && p.gru_q && warp_active) gru_issue(par);
       mbar_wait(bar_tfull + 8 * acc, ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
       float ssum = 0.f, qsum = 0.f;
@@ -1138,20 +1159,11 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
           auto okj = [&](int j) { return (j & cwm) < nvx && (j >> p.cw_sh) < nvy; };
           auto offj = [&](int j) { return (long long)((j >> p.cw_sh) * p.W + (j & cwm)); };   // pixel offset inside the chunk
           if (ACT == SCF_ACT_TANH && p.gru_q) {
-            // SepConvGRU state update (raft_decoder.py:235-253): all inputs of the chunk are requested before the accumulator
-            // is read so that their latencies overlap
-            const long long pix0 = ((long long)bi * p.H + y) * p.W + xb;
-            const float* hp = p.aux0 + pix0 * p.aux0_stride + c;
-            const float* zp = p.aux1 + pix0 * p.aux1_stride + c;
-            const float* pp = p.pre + pix0 * p.pre_stride + c;
+            // SepConvGRU state update (raft_decoder.py:235-253)
             float hv[16], zv[16], pv[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const bool ok = okj(j) && cvalid;
-              hv[j] = ok ? __ldg(hp + offj(j) * p.aux0_stride) : 0.f;
-              zv[j] = ok ? __ldg(zp + offj(j) * p.aux1_stride) : 0.f;
-              pv[j] = (ok && p.pre) ? __ldg(pp + offj(j) * p.pre_stride) : 0.f;
-            }
+            for (int j = 0; j < 16; ++j) { hv[j] = nh[j]; zv[j] = nz[j]; pv[j] = npre[j]; }
+            if (ch + TCT_EW / 4 < TCT_PIX / 16) gru_issue(ch + TCT_EW / 4);
             __syncwarp();
             tmem_ld16(t_addr + (uint32_t)(ch * 16), v);
 #pragma unroll
@@ -1507,7 +1519,10 @@ static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
     // halo mode: 8 x 32 pixel tiles (one sample each), activations once per channel chunk, weights per tap in their own ring
     const char* he = getenv("SCFLOW_TCT_HALO");
     const bool want = he ? atoi(he) != 0 : true;       // measured: +1 % of the step (encoder layers 2-15 % each)
-    if (want && p.bk == 32 && p.sx == 1 && p.sy == 1 && d.kh * d.kw > 1) {
+    // (1-D taps - the GRU's 1x5 / 5x1 - measured slower with the halo form: 58 us against 52 us)
+    const char* h1 = getenv("SCFLOW_TCT_HALO_1D");
+    const bool two_d = (d.kh > 1 && d.kw > 1) || (h1 && atoi(h1) != 0);
+    if (want && p.bk == 32 && p.sx == 1 && p.sy == 1 && d.kh * d.kw > 1 && two_d) {
       const int PW = 8 + d.kw - 1, PH = 32 + d.kh - 1;
       const int hp_stage = (2 * PW * PH * 64 + 1023) / 1024 * 1024;
       int ws = (2 * (int)TCT_STAGE - 2 * hp_stage) / (2 * 128 * 64);
