@@ -1468,6 +1468,13 @@ static bool tct_eligible(const scf_tc_conv_desc& d) {
   const int mode = e ? atoi(e) : 1;
   if (!mode) return false;
   if (mode == 1) {
+    // fewer than ~100 tiles of 256 pixels would leave a third of the SMs idle where the 128-pixel tiling still fills them
+    // (measured: config 4's B = 16 shard 9.3 -> 9.7 ms without this rule)
+    {
+      const int sx = d.stride_x ? d.stride_x : (d.stride == 2 ? 2 : 1), sy = d.stride_y ? d.stride_y : (d.stride == 2 ? 2 : 1);
+      const long long wo = (d.W + 2 * (d.kw / 2) - d.kw) / sx + 1, ho = (d.H + 2 * (d.kh / 2) - d.kh) / sy + 1;
+      if ((long long)d.B * ho * wo < 100LL * TCT_PIX) return false;
+    }
     int cin = 0;
     for (int s = 0; s < d.nseg; ++s) cin += d.seg[s].nch;
     if (d.cout <= 64 && cin * d.kh * d.kw < 1024) {
