@@ -54,6 +54,9 @@ extern "C" {
 #define SCF_EPI_GRU_Q 2   /* q = tanh(.) ; out[n] = (1-aux1[n])*aux0[n] + aux1[n]*q   (aux0 = h, aux1 = z)  */
 
 int scf_abi_version(void);
+/* sizeof() of a descriptor struct as this library was compiled, so that a binding can verify its mirror of the layout:
+ * 0 scf_conv_desc, 1 scf_tc_conv_desc, 2 scf_decoder_cfg, 3 scf_decoder_io, 4 scf_encoder_out, 5 scf_loss_desc; -1 otherwise */
+int scf_struct_size(int which);
 const char* scf_last_error(void);
 /* 1 if the tcgen05/TMA code paths are usable on the current device (compute capability 10.x), else 0 */
 int scf_device_supported(void);

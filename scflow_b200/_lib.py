@@ -137,6 +137,7 @@ ENC_NORM_IN, ENC_NORM_BN = 0, 1
 
 _SIGNATURES = {
     'scf_abi_version': (C.c_int, []),
+    'scf_struct_size': (C.c_int, [C.c_int]),
     'scf_last_error': (C.c_char_p, []),
     'scf_device_supported': (C.c_int, []),
     'scf_launch_counter': (C.c_longlong, []),
@@ -226,6 +227,10 @@ def load():
             fn.argtypes = args
         if lib.scf_abi_version() != 1:
             raise ScfError('libscflow_sm100a.so ABI version mismatch')
+        for which, cls in enumerate((ConvDesc, TcConvDesc, DecoderCfg, DecoderIO, EncoderOut, LossDesc)):
+            if lib.scf_struct_size(which) != C.sizeof(cls):
+                raise ScfError(f'libscflow_sm100a.so was built with a different {cls.__name__} layout '
+                               f'({lib.scf_struct_size(which)} bytes, binding {C.sizeof(cls)}): rebuild the library')
         _lib = lib
     return _lib
 

@@ -278,6 +278,17 @@ using namespace scf;
 extern "C" {
 
 int scf_abi_version(void) { return SCF_ABI_VERSION; }
+int scf_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(scf_conv_desc);
+    case 1: return (int)sizeof(scf_tc_conv_desc);
+    case 2: return (int)sizeof(scf_decoder_cfg);
+    case 3: return (int)sizeof(scf_decoder_io);
+    case 4: return (int)sizeof(scf_encoder_out);
+    case 5: return (int)sizeof(scf_loss_desc);
+    default: return -1;
+  }
+}
 const char* scf_last_error(void) { return scf::g_err; }
 
 int scf_device_supported(void) {

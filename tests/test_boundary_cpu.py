@@ -99,6 +99,15 @@ def test_library_exports_every_declared_symbol():
     assert len(re.findall(r'SCF_W_[A-Z0-9_]+', enum_body)) == len(keys)
 
 
+def test_ctypes_mirrors_match_the_compiled_struct_layouts():
+    """The ctypes mirrors in scflow_b200/_lib.py have the size the library was compiled with (ABI drift guard)."""
+    lib = _lib.load()
+    mirrors = [_lib.ConvDesc, _lib.TcConvDesc, _lib.DecoderCfg, _lib.DecoderIO, _lib.EncoderOut, _lib.LossDesc]
+    for which, cls in enumerate(mirrors):
+        assert lib.scf_struct_size(which) == ctypes.sizeof(cls), cls.__name__
+    assert lib.scf_struct_size(len(mirrors)) == -1
+
+
 def test_config_fromfile_with_base(tmp_path):
     (tmp_path / 'base.py').write_text("a = 1\nmodel = dict(type='X', k=dict(p=1, q=2))\n")
     (tmp_path / 'child.py').write_text("_base_ = './base.py'\nmodel = dict(k=dict(q=3), z=5)\nb = 'x'\n")
