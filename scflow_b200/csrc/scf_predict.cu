@@ -38,29 +38,85 @@ __global__ void __launch_bounds__(256) heads_predict_kernel(const __nv_bfloat16*
   const int x = x0 + px, y = y0 + py;
   const bool valid = x < W && y < H;
   float a0 = 0.f, a1 = 0.f, am = 0.f;
-  for (int c0 = 0; c0 < hidden; c0 += HP_CH) {
-    __syncthreads();
-    // stage the (8+2)^2 pixel patch of channels [c0, c0+64) as fp32 (hi + lo), zero outside the image
-    for (int idx = threadIdx.x; idx < HP_HALO * HP_HALO * (HP_CH / 8); idx += 256) {
+  // Per 64-channel chunk every global load (patch, weights, the mask head's own pixel) is issued before the first use, and the
+  // next chunk's loads are issued before the current chunk's arithmetic: the kernel is latency-bound (0.3 GFLOP, 67 MB from
+  // L2), so what matters is the number of serialised L2 round trips - one per chunk instead of ~7.
+  constexpr int NT = (HP_HALO * HP_HALO * (HP_CH / 8) + 255) / 256;      // patch items per thread (4)
+  constexpr int NW = (9 * HP_CH + 255) / 256;                            // weight rows per thread (3)
+  uint4 th[NT], tl[NT], mh[2], ml[2];
+  float w0[NW], w1[NW], mw[16];
+  auto issue = [&](int c0) {
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+      const int idx = threadIdx.x + k * 256;
       const int c8 = idx % (HP_CH / 8), pp = idx / (HP_CH / 8);
       const int ty = pp / HP_HALO, tx = pp - ty * HP_HALO;
       const int iy = y0 + ty - 1, ix = x0 + tx - 1;
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      th[k] = tl[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (idx < HP_HALO * HP_HALO * (HP_CH / 8) && iy >= 0 && iy < H && ix >= 0 && ix < W) {
         const __nv_bfloat16* src = hd + (((long long)b * H + iy) * W + ix) * stride + c0 + c8 * 8;
-        bf16x8_sum(__ldg(reinterpret_cast<const uint4*>(src)), __ldg(reinterpret_cast<const uint4*>(src + plane)), v);
+        th[k] = __ldg(reinterpret_cast<const uint4*>(src));
+        tl[k] = __ldg(reinterpret_cast<const uint4*>(src + plane));
       }
-      float4* dst = reinterpret_cast<float4*>(tile + pp * HP_RS + (c8 >> 1) * HP_QS + (c8 & 1) * 8);
-      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      const int idx = threadIdx.x + k * 256;
+      w0[k] = w1[k] = 0.f;
+      if (idx < 9 * HP_CH) {
+        const int tap = idx / HP_CH, c = idx - tap * HP_CH;
+        const float* src = wf + (long long)(tap * hidden + c0 + c) * ldwf;
+        w0[k] = __ldg(src); w1[k] = __ldg(src + 1);
+      }
+    }
+    if (valid) {
+      const __nv_bfloat16* src = hd + (((long long)b * H + y) * W + x) * stride + hidden + c0 + quarter * 16;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        mh[j] = __ldg(reinterpret_cast<const uint4*>(src + 8 * j));
+        ml[j] = __ldg(reinterpret_cast<const uint4*>(src + plane + 8 * j));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mw[i] = __ldg(wm + (long long)(c0 + quarter * 16 + i) * ldwm);
+  };
+  issue(0);
+  for (int c0 = 0; c0 < hidden; c0 += HP_CH) {
+    __syncthreads();                       // the previous chunk's arithmetic has finished reading the shared-memory patch
+    // stage the (8+2)^2 pixel patch of channels [c0, c0+64) as fp32 (hi + lo), zero outside the image
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+      const int idx = threadIdx.x + k * 256;
+      if (idx < HP_HALO * HP_HALO * (HP_CH / 8)) {
+        const int c8 = idx % (HP_CH / 8), pp = idx / (HP_CH / 8);
+        float v[8];
+        bf16x8_sum(th[k], tl[k], v);
+        float4* dst = reinterpret_cast<float4*>(tile + pp * HP_RS + (c8 >> 1) * HP_QS + (c8 & 1) * 8);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
     }
     // weights of this chunk: wsm[tap][quarter][(c % 16) * 2 + o]
-    for (int idx = threadIdx.x; idx < 9 * HP_CH; idx += 256) {
-      const int tap = idx / HP_CH, c = idx - tap * HP_CH;
-      const float* src = wf + (long long)(tap * hidden + c0 + c) * ldwf;
-      float* dst = wsm + tap * HP_WT + (c >> 4) * HP_WQ + (c & 15) * 2;
-      dst[0] = __ldg(src); dst[1] = __ldg(src + 1);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      const int idx = threadIdx.x + k * 256;
+      if (idx < 9 * HP_CH) {
+        const int tap = idx / HP_CH, c = idx - tap * HP_CH;
+        float* dst = wsm + tap * HP_WT + (c >> 4) * HP_WQ + (c & 15) * 2;
+        dst[0] = w0[k]; dst[1] = w1[k];
+      }
     }
+    // mask head: 1x1 over channels hidden + [c0, c0+64) of the same pixel (this thread: 16 of them)
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float v[8];
+        bf16x8_sum(mh[j], ml[j], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) am = fmaf(v[i], mw[8 * j + i], am);
+      }
+    }
+    if (c0 + HP_CH < hidden) issue(c0 + HP_CH);       // in flight during this chunk's arithmetic
     __syncthreads();
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
@@ -70,22 +126,11 @@ __global__ void __launch_bounds__(256) heads_predict_kernel(const __nv_bfloat16*
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 v = *reinterpret_cast<const float4*>(tp + 4 * j);
-        const float4 w0 = *reinterpret_cast<const float4*>(wp + 8 * j), w1 = *reinterpret_cast<const float4*>(wp + 8 * j + 4);
-        a0 = fmaf(v.x, w0.x, a0); a1 = fmaf(v.x, w0.y, a1);
-        a0 = fmaf(v.y, w0.z, a0); a1 = fmaf(v.y, w0.w, a1);
-        a0 = fmaf(v.z, w1.x, a0); a1 = fmaf(v.z, w1.y, a1);
-        a0 = fmaf(v.w, w1.z, a0); a1 = fmaf(v.w, w1.w, a1);
-      }
-    }
-    // mask head: 1x1 over channels hidden + [c0, c0+64) of the same pixel (this thread: 16 of them)
-    if (valid) {
-      const __nv_bfloat16* src = hd + (((long long)b * H + y) * W + x) * stride + hidden + c0 + quarter * 16;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        float v[8];
-        bf16x8_sum(__ldg(reinterpret_cast<const uint4*>(src + 8 * j)), __ldg(reinterpret_cast<const uint4*>(src + plane + 8 * j)), v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) am = fmaf(v[i], __ldg(wm + (long long)(c0 + quarter * 16 + 8 * j + i) * ldwm), am);
+        const float4 w0v = *reinterpret_cast<const float4*>(wp + 8 * j), w1v = *reinterpret_cast<const float4*>(wp + 8 * j + 4);
+        a0 = fmaf(v.x, w0v.x, a0); a1 = fmaf(v.x, w0v.y, a1);
+        a0 = fmaf(v.y, w0v.z, a0); a1 = fmaf(v.y, w0v.w, a1);
+        a0 = fmaf(v.z, w1v.x, a0); a1 = fmaf(v.z, w1v.y, a1);
+        a0 = fmaf(v.w, w1v.z, a0); a1 = fmaf(v.w, w1v.w, a1);
       }
     }
   }
