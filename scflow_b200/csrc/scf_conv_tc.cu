@@ -889,6 +889,8 @@ struct TctParams {
   float* out_f32; int out_f32_stride, out_f32_coff;
   __nv_bfloat16* out_hl; long long out_hl_plane; int out_hl_stride, out_hl_coff;
   const float* aux0; int aux0_stride;
+  int gru_zr;                               // GRU gates (cout = 256): tile t = (pixel tile t >> 1, gate t & 1); gate 0: z = sigmoid(acc + pre)
+                                            // -> out_f32, gate 1: r = sigmoid(acc + pre[128 + c]) -> r * h (aux0) -> out_hl
   int gru_q;                                // GRU state update epilogue: h' = (1 - z) h + z tanh(acc + pre), aux0 = h, aux1 = z
   const float* aux1; int aux1_stride; const float* pre; int pre_stride;
   float* stats;                             // [num_tiles][2 warp parities][2][cout]
@@ -963,7 +965,8 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
       int stage = 0, hs = 0;
       uint32_t phase = 0, hph = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const int b = (t / tiles_per_img) * TB, tr = t % tiles_per_img;
+        const int pt = p.gru_zr ? (t >> 1) : t, wrow = p.gru_zr ? (t & 1) * 128 : 0;      // pixel tile, first weight row
+        const int b = (pt / tiles_per_img) * TB, tr = pt % tiles_per_img;
         const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
         const int x0 = tx * TW, y0 = ty * TH;
         if (p.halo) {
@@ -985,8 +988,8 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
                 if (p.dbg & 8) mbar_arrive(full);
                 else {
                   mbar_arrive_expect_tx(full, 2 * w_plane);
-                  tma_load_4d(w_dst, &tmW, full, wk, 0, tap, 0);
-                  tma_load_4d(w_dst + w_plane, &tmW, full, wk, 0, tap, 1);
+                  tma_load_4d(w_dst, &tmW, full, wk, wrow, tap, 0);
+                  tma_load_4d(w_dst + w_plane, &tmW, full, wk, wrow, tap, 1);
                 }
                 if (++stage == p.w_stages) { stage = 0; phase ^= 1u; }
               }
@@ -1008,8 +1011,8 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
               if (txb) mbar_arrive_expect_tx(full, txb); else mbar_arrive(full);
               if (!(p.dbg & 4)) tma_load_5d(p_dst, tm, full, cc * p.bk, cx, cy, b, 0);
               if (!(p.dbg & 8)) {
-                tma_load_4d(w_dst, &tmW, full, wk, 0, tap, 0);
-                tma_load_4d(w_dst + w_plane, &tmW, full, wk, 0, tap, 1);
+                tma_load_4d(w_dst, &tmW, full, wk, wrow, tap, 0);
+                tma_load_4d(w_dst + w_plane, &tmW, full, wk, wrow, tap, 1);
               }
               if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
@@ -1101,17 +1104,20 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
     // of a lane quarter take alternate 32-pixel slabs
     const int q = warp & 3, par = (warp - 2) >> 2;
     const int c = q * 32 + lane;
-    const bool cvalid = c < p.cout;
-    const bool warp_active = q * 32 < p.cout;
-    const float bias_c = (p.bias && cvalid) ? __ldg(p.bias + c) : 0.f;
+    const bool cvalid = p.gru_zr || c < p.cout;
+    const bool warp_active = p.gru_zr || q * 32 < p.cout;
+    float bias_c = (p.bias && cvalid) ? __ldg(p.bias + c) : 0.f;
     const int tw_mask = TW - 1, th_mask = TH - 1, b_sh = p.tw_sh + p.th_sh, odd = lane & 1, cwm = (1 << p.cw_sh) - 1;
     const uint32_t stg = staging0 + (uint32_t)(warp - 2) * TCT_STAGING;
-    const bool both = p.out_f32 && p.out_hl;
+    const bool both = p.out_f32 && p.out_hl && !p.gru_zr;
     uint32_t kc = 0;                      // chunks staged so far (staging block parity)
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
-      const int b = (t / tiles_per_img) * TB, tr = t % tiles_per_img;
+      const int pt = p.gru_zr ? (t >> 1) : t, gate = p.gru_zr ? (t & 1) : 0;
+      const bool do_f32 = p.gru_zr ? gate == 0 : p.out_f32 != nullptr, do_hl = p.gru_zr ? gate == 1 : p.out_hl != nullptr;
+      if (p.gru_zr && p.bias) bias_c = __ldg(p.bias + gate * 128 + c);
+      const int b = (pt / tiles_per_img) * TB, tr = pt % tiles_per_img;
       const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
       const int x0 = tx * TW, y0 = ty * TH;
       // GRU q: h, z and the context term of a chunk are requested one chunk ahead (the first one before the accumulator is
@@ -1124,17 +1130,17 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
         const long long pix0 = ((long long)bi * p.H + y) * p.W + xb;
         const float* hp = p.aux0 + pix0 * p.aux0_stride + c;
         const float* zp = p.aux1 + pix0 * p.aux1_stride + c;
-        const float* pp = p.pre + pix0 * p.pre_stride + c;
+        const float* pp = p.pre + pix0 * p.pre_stride + gate * 128 + c;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const bool ok = (j & cwm) < nvx && (j >> p.cw_sh) < nvy && cvalid;
           const long long off = (long long)((j >> p.cw_sh) * p.W + (j & cwm));
-          nh[j] = ok ? __ldg(hp + off * p.aux0_stride) : 0.f;
-          nz[j] = ok ? __ldg(zp + off * p.aux1_stride) : 0.f;
+          nh[j] = (ok && (p.gru_q || gate == 1)) ? __ldg(hp + off * p.aux0_stride) : 0.f;
+          nz[j] = (ok && p.gru_q) ? __ldg(zp + off * p.aux1_stride) : 0.f;
           npre[j] = (ok && p.pre) ? __ldg(pp + off * p.pre_stride) : 0.f;
         }
       };
-      if (ACT == SCF_ACT_TANH && p.gru_q && warp_active) gru_issue(par);
+      if (((ACT == SCF_ACT_TANH && p.gru_q) || (ACT == SCF_ACT_SIGMOID && p.gru_zr)) && warp_active) gru_issue(par);
       mbar_wait(bar_tfull + 8 * acc, ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
       float ssum = 0.f, qsum = 0.f;
@@ -1143,7 +1149,7 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
 #pragma unroll 1
         for (int ch = par; ch < TCT_PIX / 16; ch += TCT_EW / 4) {
           float v[16];
-          if (!(ACT == SCF_ACT_TANH && p.gru_q)) {
+          if (!((ACT == SCF_ACT_TANH && p.gru_q) || (ACT == SCF_ACT_SIGMOID && p.gru_zr))) {
             __syncwarp();
             tmem_ld16(t_addr + (uint32_t)(ch * 16), v);
           }
@@ -1168,6 +1174,19 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
             tmem_ld16(t_addr + (uint32_t)(ch * 16), v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = (1.f - zv[j]) * hv[j] + zv[j] * tanh_fast(fmaf(v[j], p.scale, bias_c) + pv[j]);
+          } else if (ACT == SCF_ACT_SIGMOID && p.gru_zr) {
+            // SepConvGRU gates: z = sigmoid(.) ; r = sigmoid(.), stored as r * h, the q convolution's first input segment
+            float hv[16], pv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { hv[j] = nh[j]; pv[j] = npre[j]; }
+            if (ch + TCT_EW / 4 < TCT_PIX / 16) gru_issue(ch + TCT_EW / 4);
+            __syncwarp();
+            tmem_ld16(t_addr + (uint32_t)(ch * 16), v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float g = sigmoid_fast(fmaf(v[j], p.scale, bias_c) + pv[j]);
+              v[j] = gate ? g * hv[j] : g;
+            }
           } else if (p.aux0 && cvalid) {                                           // residual, added before the activation
             const float* ax = p.aux0 + (((long long)bi * p.H + y) * p.W + xb) * p.aux0_stride + c;
             float rv[16];
@@ -1192,7 +1211,7 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
           ++kc;
           if (lane == 0) bulk_wait_group_read1();
           __syncwarp();
-          if (p.out_f32) {
+          if (do_f32) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               asm volatile("st.shared.f32 [%0], %1;" ::"r"(blk_f + (uint32_t)(j * 128 + lane * 4)), "f"(v[j]) : "memory");
@@ -1205,7 +1224,7 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant_
             }
             __syncwarp();
           }
-          if (p.out_hl) {
+          if (do_hl) {
             // lanes 2i, 2i+1 trade values: the even lane stores channels (c, c+1) of pixel j as one 32-bit word per plane, the
             // odd lane channels (c-1, c) of pixel j + 1
             const uint32_t hbase = blk_h + (uint32_t)(odd * 64 + (lane & ~1) * 2);
@@ -1486,10 +1505,25 @@ static bool tct_eligible(const scf_tc_conv_desc& d) {
       if (!(halo && (s64 ? atoi(s64) != 0 : false) && (long long)d.B * d.H * d.W >= 4LL * 148 * 256)) return false;
     }
   }
+  if (d.epi == SCF_EPI_GRU_ZR) {
+    // the GRU's gate convolution: two 128-channel weight-row tiles (z, r) per pixel tile
+    const char* ze = getenv("SCFLOW_TC_T_GRUZR");
+    const char* e = getenv("SCFLOW_TC_T");
+    if ((e && atoi(e) == 0) || !(ze ? atoi(ze) != 0 : false)) return false;
+    if (d.w_batched || d.cout != 256 || d.cout_pad != 256 || d.act != SCF_ACT_SIGMOID || !d.aux0 || !d.out_f32 || !d.out2_hl || d.stats)
+      return false;
+    if (d.out2_hl_stride % 8 || d.out2_hl_plane % 8 || reinterpret_cast<uintptr_t>(d.out2_hl) % 16) return false;
+    if (d.out_f32_stride % 4 || d.out_f32_coff % 4 || reinterpret_cast<uintptr_t>(d.out_f32) % 16) return false;
+    const int sx = d.stride_x ? d.stride_x : (d.stride == 2 ? 2 : 1), sy = d.stride_y ? d.stride_y : (d.stride == 2 ? 2 : 1);
+    const long long wo = (d.W + 2 * (d.kw / 2) - d.kw) / sx + 1, ho = (d.H + 2 * (d.kh / 2) - d.kh) / sy + 1;
+    return wo >= 24 && (long long)d.B * ho * wo >= 100LL * TCT_PIX;
+  }
   if (d.w_batched || d.cout_pad > 128 || d.act < SCF_ACT_NONE || d.act > SCF_ACT_TANH) return false;
   if (d.epi == SCF_EPI_GRU_Q) {
     const char* qe = getenv("SCFLOW_TC_T_GRUQ");
     if (!(qe ? atoi(qe) != 0 : true) || d.act != SCF_ACT_TANH || !d.aux0 || !d.aux1 || d.stats) return false;
+  } else if (d.epi == SCF_EPI_GRU_ZR) {
+    return false;      // handled by tct_eligible_zr (two 128-channel gates)
   } else if (d.epi != SCF_EPI_ACT || d.pre) {
     return false;
   }
@@ -1571,6 +1605,13 @@ static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.out_hl_coff = d.out_hl_coff;
   p.aux0 = d.aux0; p.aux0_stride = d.aux0_stride;
   p.gru_q = d.epi == SCF_EPI_GRU_Q ? 1 : 0;
+  p.gru_zr = d.epi == SCF_EPI_GRU_ZR ? 1 : 0;
+  if (p.gru_zr) {                      // z -> out_f32 (128 channels), r * h -> out2_hl (128 channels); tile = (pixel tile, gate)
+    p.cout = 128;
+    p.out_hl = reinterpret_cast<__nv_bfloat16*>(d.out2_hl); p.out_hl_plane = d.out2_hl_plane; p.out_hl_stride = d.out2_hl_stride;
+    p.out_hl_coff = 0;
+    p.num_tiles *= 2;
+  }
   p.aux1 = d.aux1; p.aux1_stride = d.aux1_stride; p.pre = d.pre; p.pre_stride = d.pre_stride;
   p.stats = d.stats;
   { const char* de = getenv("SCFLOW_TCT_DBG"); p.dbg = de ? atoi(de) : 0; }
@@ -1612,17 +1653,17 @@ static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
   // output maps of the epilogue's TMA stores: box = 32 channels x 16 pixels of one row (both bf16 planes in one store)
   CUtensorMap tmOF = tmW, tmOH = tmW;
   if (d.out_f32) {
-    cuuint64_t dims[4] = {(cuuint64_t)d.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)d.B};
+    cuuint64_t dims[4] = {(cuuint64_t)p.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)d.B};
     cuuint64_t str[3] = {(cuuint64_t)d.out_f32_stride * 4, (cuuint64_t)p.W * d.out_f32_stride * 4, (cuuint64_t)p.H * p.W * d.out_f32_stride * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)(1 << p.cw_sh), (cuuint32_t)(16 >> p.cw_sh), 1};
     SCF_TRY(encode_map(&tmOF, d.out_f32 + d.out_f32_coff, 4, dims, str, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE));
   }
-  if (d.out_hl) {
-    cuuint64_t dims[5] = {(cuuint64_t)d.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)d.B, 2};
-    cuuint64_t str[4] = {(cuuint64_t)d.out_hl_stride * 2, (cuuint64_t)p.W * d.out_hl_stride * 2, (cuuint64_t)p.H * p.W * d.out_hl_stride * 2,
-                         (cuuint64_t)d.out_hl_plane * 2};
+  if (p.out_hl) {
+    cuuint64_t dims[5] = {(cuuint64_t)p.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)d.B, 2};
+    cuuint64_t str[4] = {(cuuint64_t)p.out_hl_stride * 2, (cuuint64_t)p.W * p.out_hl_stride * 2, (cuuint64_t)p.H * p.W * p.out_hl_stride * 2,
+                         (cuuint64_t)p.out_hl_plane * 2};
     cuuint32_t box[5] = {32, (cuuint32_t)(1 << p.cw_sh), (cuuint32_t)(16 >> p.cw_sh), 1, 2};
-    SCF_TRY(encode_map(&tmOH, reinterpret_cast<const __nv_bfloat16*>(d.out_hl) + d.out_hl_coff, 5, dims, str, box, nullptr,
+    SCF_TRY(encode_map(&tmOH, p.out_hl + p.out_hl_coff, 5, dims, str, box, nullptr,
                        CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_NONE));
   }
   g_last_m_tiles = p.num_tiles;
