@@ -329,6 +329,14 @@ int scf_decoder_launch_count(const scf_decoder_cfg* cfg, int iters);
  * the flow target is < 0.9. */
 int scf_filter_flow_by_mask(float* flow, const float* gt_mask, float invalid, int B, int H, int W, void* stream);
 
+/* ---- input formatting next to the path ------------------------------------------------------
+ * models/refiner/base_refiner.py:96-107 (BaseRefiner.format_data_test after the renderer call): images [B,H,W,cin>=3]
+ * (renderer output, RGB(A) in [0,1]) -> out_images [B,3,H,W] = (rgb - mean) / std ; zbuf [B,H,W,zk] -> out_depth [B,H,W]
+ * = zbuf[...,0], out_mask = (depth > 0).  mean3 / std3 are HOST arrays (already divided by 255 as the reference does).
+ * Bit-exact with the reference's fp32 arithmetic. */
+int scf_format_rendered(const float* images, int cin, const float* zbuf, int zk, const float* mean3, const float* std3,
+                        float* out_images, float* out_depth, float* out_mask, int B, int H, int W, void* stream);
+
 /* SCFlowRefiner.loss after get_pose (models/refiner/scflow_refiner.py:204-258) with the shipped loss configuration
  * (configs/refine_models/scflow.py:75-104): SequenceLoss(gamma) over RAFTLoss (flow), L1Loss (mask) and
  * DisentanglePointMatchingLoss (loss_type 'l1', disentangle_z=True, no scale factors). Forward only. */

@@ -347,3 +347,25 @@ def make_tc_gru_zr_bench(h, cxt, mot, wz, wr, bias, z, rh):
                   epi=_lib.EPI_GRU_ZR, aux0=h, out2_hl=rhs, pre=pre)
     k = kernel[0] * kernel[1] * 256
     return launch, f'conv_tc_kernel (GRU z|r 1x5, tcgen05 split-bf16, N=256, K={k}; context term hoisted out of the loop)', 3, k
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# input formatting next to the path
+# ----------------------------------------------------------------------------------------------------------------------
+def format_rendered(images: torch.Tensor, zbuf: torch.Tensor, mean: Sequence[float], std: Sequence[float]):
+    """Renderer output -> network input (base_refiner.py:96-107): ``images`` [B,H,W,C>=3] in [0,1], ``zbuf`` [B,H,W,K];
+    ``mean`` / ``std`` are the three fp32 values the reference subtracts / divides by (dataset values already / 255).
+    Returns (rendered_images [B,3,H,W], rendered_depths [B,H,W], rendered_masks [B,H,W])."""
+    _req(images, 'images')
+    _req(zbuf, 'zbuf')
+    if images.dim() != 4 or zbuf.dim() != 4 or images.shape[:3] != zbuf.shape[:3] or images.shape[-1] < 3:
+        raise ValueError(f'format_rendered: images [B,H,W,C>=3] and zbuf [B,H,W,K] expected, got {tuple(images.shape)} {tuple(zbuf.shape)}')
+    b, h, w, cin = images.shape
+    out = torch.empty(b, 3, h, w, device=images.device, dtype=torch.float32)
+    depth = torch.empty(b, h, w, device=images.device, dtype=torch.float32)
+    mask = torch.empty(b, h, w, device=images.device, dtype=torch.float32)
+    m3 = (C.c_float * 3)(*[float(v) for v in mean])
+    s3 = (C.c_float * 3)(*[float(v) for v in std])
+    check(_lib.load().scf_format_rendered(ptr(images), cin, ptr(zbuf), zbuf.shape[-1], m3, s3, ptr(out), ptr(depth), ptr(mask), b, h, w,
+                                          stream_ptr()), 'scf_format_rendered')
+    return out, depth, mask

@@ -176,7 +176,18 @@ class SCFlowRefiner(BaseModule):
         if self.renderer is None:
             raise NotImplementedError('SCFlowRefiner.forward(data_batch) needs a renderer: assign a callable to '
                                       '`model.renderer` or pass a pre-formatted dict with `rendered_images` / `rendered_depths`.')
-        raise NotImplementedError('dataset-format batches (mmcv DataContainer collation) are outside the replaced hot path')
+        return self.forward_single_pass(self.format_data_test(data_batch), data_batch)
+
+    def set_renderer(self, renderer: Callable):
+        """Plug in the renderer (reference interface: ``renderer(rotations, translations, internel_k, labels)`` returning
+        ``{'images': [N,H,W,4], 'fragments': obj with .zbuf [N,H,W,K]}``, models/utils/renderer.py)."""
+        self.renderer = renderer
+
+    def format_data_test(self, data_batch: Dict) -> Dict:
+        """base_refiner.py:79-133: flatten the per-image patch lists, render the reference poses, format the render
+        (one CUDA pass, scflow_b200/formatting.py)."""
+        from . import formatting
+        return formatting.format_data_test(data_batch, self.renderer)
 
     def train_step(self, data_batch, optimizer, **kwargs):
         raise NotImplementedError('training needs the backward pass of the refinement loop, which is not built yet (the forward '
