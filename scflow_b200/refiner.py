@@ -149,8 +149,8 @@ class SCFlowRefiner(BaseModule):
                             init_flow=init_flow, label=label, invalid_flow_num=0.)
 
     def forward_single_pass(self, data: Dict, data_batch: Optional[Dict] = None, return_loss: bool = False):
-        """scflow_refiner.py:146-179 without the OpenCV re-mapping to the original image resolution
-        (remap_pose_to_origin_resoluaion is host-side cv2.solvePnP, out of scope): poses are returned in the crop frame."""
+        """scflow_refiner.py:146-179.  The re-mapping to the original image resolution is the identity for the shipped
+        'adapt_intrinsic' pipelines; the cv2.solvePnP modes raise (see below)."""
         labels = data['labels']
         per_img_patch_num = data.get('per_img_patch_num', [len(labels)])
         iters = self.decoder.iters
@@ -161,6 +161,14 @@ class SCFlowRefiner(BaseModule):
         finally:
             self.decoder.iters = iters
         seq_rotations, seq_translations = outs[2], outs[3]
+        # remap_pose_to_origin_resoluaion (models/utils/pose.py:264-309): with the shipped pipelines (RemapPose(keep_intrinsic=
+        # False) without dst_k => 'adapt_intrinsic', datasets/pipelines/geometry_transform.py:35-45) the poses are returned
+        # unchanged (:276-279); the other two modes re-solve the pose with cv2.solvePnP on the host, which is not built
+        for meta in (data_batch or {}).get('img_metas', []):
+            mode = meta.get('geometry_transform_mode', 'adapt_intrinsic') if isinstance(meta, dict) else 'adapt_intrinsic'
+            if mode != 'adapt_intrinsic':
+                raise NotImplementedError(f"geometry_transform_mode '{mode}' needs the OpenCV PnP re-mapping (pose.py:280-305), "
+                                          "which is outside this package; the shipped configs use 'adapt_intrinsic'")
         return dict(
             rotations=torch.split(seq_rotations[-1], per_img_patch_num),
             translations=torch.split(seq_translations[-1], per_img_patch_num),

@@ -103,3 +103,11 @@ def test_refiner_forward_formats_and_refines_a_dataset_batch():
         out = model(data_batch)
     assert [r.shape for r in out['rotations']] == [(2, 3, 3), (1, 3, 3)]
     assert all(torch.isfinite(t).all() for t in out['translations'])
+    # 'adapt_intrinsic' (shipped pipelines): poses are returned as predicted; the cv2.solvePnP modes are refused loudly
+    data_batch['img_metas'] = [dict(m, geometry_transform_mode='adapt_intrinsic') for m in batch['img_metas']]
+    with torch.no_grad():
+        again = model(data_batch)
+    assert all(torch.equal(a, b) for a, b in zip(again['rotations'], out['rotations']))
+    data_batch['img_metas'] = [dict(m, geometry_transform_mode='target_intrinsic') for m in batch['img_metas']]
+    with pytest.raises(NotImplementedError, match='PnP'), torch.no_grad():
+        model(data_batch)
