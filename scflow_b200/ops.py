@@ -369,3 +369,16 @@ def format_rendered(images: torch.Tensor, zbuf: torch.Tensor, mean: Sequence[flo
     check(_lib.load().scf_format_rendered(ptr(images), cin, ptr(zbuf), zbuf.shape[-1], m3, s3, ptr(out), ptr(depth), ptr(mask), b, h, w,
                                           stream_ptr()), 'scf_format_rendered')
     return out, depth, mask
+
+
+def convex_upsample(flow: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """RAFTDecoder._upsample with a predicted mask (raft_decoder.py:381-416): flow [B,2,H,W], mask [B,576,H,W] ->
+    [B,2,8H,8W] (softmax over the 3x3 neighbourhood, x8 flow scaling)."""
+    _req(flow, 'flow')
+    _req(mask, 'mask')
+    b, c, h, w = flow.shape
+    if c != 2 or tuple(mask.shape) != (b, 576, h, w):
+        raise ValueError(f'convex_upsample: flow [B,2,H,W] and mask [B,576,H,W] expected, got {tuple(flow.shape)} {tuple(mask.shape)}')
+    out = torch.empty(b, 2, 8 * h, 8 * w, device=flow.device, dtype=torch.float32)
+    check(_lib.load().scf_convex_upsample(ptr(flow), ptr(mask), ptr(out), b, h, w, stream_ptr()), 'scf_convex_upsample')
+    return out
