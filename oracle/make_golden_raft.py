@@ -23,6 +23,24 @@ def main():
     assert torch.equal(ref, mine), 'restatement differs from the reference'
     np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'convex_upsample_b2_6x9.npz'), out=ref.numpy())
     print('restatement == reference; fixture written', tuple(ref.shape))
+    # ---- the whole RAFTDecoder
+    dec = RAFTDecoder(net_type='Basic', num_levels=4, radius=4, iters=3, corr_lookup_cfg=dict(align_corners=True),
+                      gru_type='SeqConv', act_cfg=dict(type='ReLU'))
+    sd = RO.make_raft_decoder_weights(2)
+    missing, unexpected = dec.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    dec.eval()
+    inputs = RO.make_raft_inputs(2, 2, 16, 16)
+    with torch.no_grad():
+        ref_preds = dec(*inputs)
+        my_preds = RO.raft_decoder_forward(sd, *inputs, iters=3)
+    out = {}
+    for i, (a, b) in enumerate(zip(ref_preds, my_preds)):
+        err = float((a - b).abs().max())
+        assert err < 1e-4, f'iteration {i}: restatement differs from the reference by {err:.3e}'
+        out[f'upflow_{i}'] = a.numpy()
+        print(f'iteration {i}: |restatement - reference| max {err:.2e}, |flow| max {float(a.abs().max()):.2f}')
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'raft_decoder_b2_16x16_it3.npz'), **out)
 
 
 if __name__ == '__main__':

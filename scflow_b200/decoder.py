@@ -150,14 +150,82 @@ class XHead(BaseModule):
             raise ValueError(f'x must be \'flow\' or \'mask\', but got {x}')
         self._pred = PackedCache()
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        """``scale`` multiplies the prediction inside the convolution's epilogue (RAFTDecoder's ``.25 * mask_pred(h)``; for a
+        power of two ``scale * acc + scale * bias`` equals ``scale * (acc + bias)`` exactly)."""
         y = ops.nchw_to_nhwc(x.contiguous())
         for layer in self.layers:
             y = layer.forward_nhwc([(y, 0, layer.in_channels)])
         p = self.predict_layer
         w = self._pred.get([p.weight], lambda: ops.pack_conv_weight([p.weight.detach()]))
-        out = ops.conv2d_nhwc([(y, 0, y.shape[-1])], w, p.bias.detach(), p.out_channels, p.kernel_size, 1, p.padding)
+        bias = p.bias.detach() if scale == 1.0 else p.bias.detach() * scale
+        out = ops.conv2d_nhwc([(y, 0, y.shape[-1])], w, bias, p.out_channels, p.kernel_size, 1, p.padding, scale=scale)
         return ops.nhwc_to_nchw(out)
+
+
+@DECODERS.register_module()
+class RAFTDecoder(BaseModule):
+    """The RAFT baseline decoder (models/decoder/raft_decoder.py:296-457): same constructor kwargs,
+    parameter names and return value (the list of x8 up-sampled flow predictions).  Assembled from the same native
+    operators as ``SCFlowDecoder`` - correlation pyramid, pyramid lookup, motion encoder, SepConvGRU, flow head - plus the
+    mask head's 576-channel prediction and the convex up-sampling kernel; runs module by module (exact-fp32 convolutions),
+    not as the fused loop, because it is a baseline next to the path rather than the path."""
+    _h_channels = {'Basic': 128, 'Small': 96}
+    _cxt_channels = {'Basic': 128, 'Small': 64}
+
+    def __init__(self, net_type: str, num_levels: int, radius: int, iters: int,
+                 corr_lookup_cfg: dict = dict(type='CorrLookup', align_corners=True), gru_type: str = 'SeqConv',
+                 feat_channels: Union[int, Sequence[int]] = 256, mask_channels: int = 64, convex_unsample_flow: bool = True,
+                 conv_cfg: Optional[dict] = None, norm_cfg: Optional[dict] = None, act_cfg: Optional[dict] = None) -> None:
+        super().__init__()
+        assert net_type in ['Basic', 'Small']
+        assert type(feat_channels) in (int, tuple, list)
+        if net_type != 'Basic' or gru_type != 'SeqConv' or num_levels != 4 or radius != 4:
+            raise NotImplementedError('RAFTDecoder: net_type="Basic", gru_type="SeqConv", num_levels=4, radius=4 (the shipped '
+                                      'configuration: x8 up-sampling over a 3x3 neighbourhood) is implemented')
+        self.corr_block = CorrelationPyramid(num_levels=num_levels)
+        feat_channels = [feat_channels]         # the reference's `isinstance(tuple, list)` quirk (raft_decoder.py:343-344)
+        self.net_type, self.num_levels, self.radius = net_type, num_levels, radius
+        self.h_channels = self._h_channels[net_type]
+        self.cxt_channels = self._cxt_channels[net_type]
+        self.iters = iters
+        self.mask_channels = mask_channels * (2 * radius + 1)
+        corr_lookup_cfg = {k: v for k, v in corr_lookup_cfg.items() if k != 'type'}
+        corr_lookup_cfg['radius'] = radius
+        self.corr_lookup = CorrLookup(**corr_lookup_cfg)
+        self.encoder = MotionEncoder(num_levels=num_levels, radius=radius, net_type=net_type, conv_cfg=conv_cfg,
+                                     norm_cfg=norm_cfg, act_cfg=act_cfg)
+        self.gru_type = gru_type
+        self.gru = ConvGRU(self.h_channels, self.encoder.out_channels[0] + 2 + self.cxt_channels, net_type=gru_type)
+        self.flow_pred = XHead(self.h_channels, feat_channels, 2, x='flow')
+        self.mask_pred = XHead(self.h_channels, feat_channels, self.mask_channels, x='mask')
+        self.convex_upsample_flow = convex_unsample_flow
+
+    def _upsample(self, flow: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """raft_decoder.py:381-416."""
+        scale = 2 ** (self.num_levels - 1)
+        if mask is None:
+            return ops.resize_bilinear_nchw(flow.contiguous(), scale * flow.shape[2], scale * flow.shape[3], scale=float(scale))
+        return ops.convex_upsample(flow.contiguous(), mask.contiguous())
+
+    def forward(self, feat1: torch.Tensor, feat2: torch.Tensor, flow: torch.Tensor, h_feat: torch.Tensor,
+                cxt_feat: torch.Tensor) -> Sequence[torch.Tensor]:
+        """raft_decoder.py:418-457 (inference: the reference's ``flow.detach()`` is a no-op without autograd)."""
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (feat1, feat2, flow, h_feat, cxt_feat)):
+            raise NotImplementedError('RAFTDecoder: forward only (no backward yet); call under torch.no_grad()')
+        corr_pyramid = self.corr_block(feat1, feat2)
+        upflow_preds = []
+        b, _, h, w = flow.shape
+        flow = flow.contiguous()
+        for _ in range(self.iters):
+            corr = self.corr_lookup(corr_pyramid, flow)
+            motion_feat = self.encoder(corr, flow)
+            h_feat = self.gru(h_feat, torch.cat([cxt_feat, motion_feat], dim=1))
+            delta_flow = self.flow_pred(h_feat)
+            flow = ops.resize_bilinear_nchw(delta_flow, h, w, scale=1.0, add=flow)        # flow + delta_flow (identity resize)
+            mask = self.mask_pred(h_feat, scale=0.25) if self.convex_upsample_flow else None
+            upflow_preds.append(self._upsample(flow, mask))
+        return upflow_preds
 
 
 @DECODERS.register_module()

@@ -40,3 +40,59 @@ def test_convex_upsample_rejects_bad_shapes_and_cpu_tensors():
         S.ops.convex_upsample(flow, mask)
     with pytest.raises(ValueError, match='576'):
         S.ops.convex_upsample(flow.cuda(), mask[:, :64].contiguous().cuda())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the whole RAFT baseline decoder
+# ---------------------------------------------------------------------------------------------------------------------
+RAFT_CFG = dict(type='RAFTDecoder', net_type='Basic', num_levels=4, radius=4, iters=3, corr_lookup_cfg=dict(type='CorrLookup', align_corners=True),
+                gru_type='SeqConv', act_cfg=dict(type='ReLU'))
+
+
+def test_raft_decoder_oracle_matches_reference_golden():
+    g = load_golden('raft_decoder_b2_16x16_it3')
+    sd = RO.make_raft_decoder_weights(2)
+    with torch.no_grad():
+        preds = RO.raft_decoder_forward(sd, *RO.make_raft_inputs(2, 2, 16, 16), iters=3)
+    assert len(preds) == 3
+    for i, p in enumerate(preds):
+        assert p.shape == (2, 2, 128, 128)
+        assert float(np.abs(p.numpy() - g[f'upflow_{i}']).max()) < 1e-4
+
+
+def test_raft_decoder_registers_with_reference_keys():
+    import scflow_b200 as S
+    from scflow_b200.builder import DECODERS, build_decoder
+    assert DECODERS.get('RAFTDecoder') is S.RAFTDecoder
+    dec = build_decoder(dict(RAFT_CFG))
+    assert set(dec.state_dict().keys()) == set(RO.make_raft_decoder_weights(0).keys())
+    assert dec.mask_channels == 576 and dec.iters == 3
+    with pytest.raises(NotImplementedError):
+        build_decoder(dict(RAFT_CFG, net_type='Small'))
+
+
+@pytest.mark.gpu
+def test_raft_decoder_matches_oracle():
+    from scflow_b200.builder import build_decoder
+    sd = RO.make_raft_decoder_weights(2)
+    inputs = RO.make_raft_inputs(2, 2, 16, 16)
+    with torch.no_grad():
+        ref = RO.raft_decoder_forward(sd, *inputs, iters=3)
+    dec = build_decoder(dict(RAFT_CFG))
+    dec.load_state_dict(sd)
+    dec = dec.cuda().eval()
+    with torch.no_grad():
+        got = dec(*[t.cuda() for t in inputs])
+    g = load_golden('raft_decoder_b2_16x16_it3')
+    assert len(got) == 3
+    for i, (a, b) in enumerate(zip(got, ref)):
+        err = float((a.cpu() - b).abs().max())
+        epe = float((a.cpu() - b).pow(2).sum(1).sqrt().mean())
+        print(f'RAFTDecoder iteration {i}: max err {err:.3e}, EPE {epe:.3e}')
+        assert err < 2e-3 and epe < 1e-4           # fp32 both sides; x8 flow scale; three recurrent iterations
+        assert float(np.abs(a.cpu().numpy() - g[f'upflow_{i}']).max()) < 2e-3
+    # without the mask head's convex combination the reference falls back to x8 bilinear up-sampling (raft_decoder.py:398-401)
+    dec.convex_upsample_flow = False
+    with torch.no_grad():
+        plain = dec(*[t.cuda() for t in inputs])
+    assert plain[0].shape == (2, 2, 128, 128) and not torch.equal(plain[0], got[0])
