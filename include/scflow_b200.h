@@ -331,10 +331,11 @@ int scf_filter_flow_by_mask(float* flow, const float* gt_mask, float invalid, in
 
 /* ---- RAFT baseline decoders: convex x8 up-sampling -------------------------------------------
  * models/decoder/raft_decoder.py:381-416 RAFTDecoder._upsample with a mask (num_levels = 4 => scale 8, radius = 4 => 3x3
- * grid): flow [B,2,H,W], mask [B,576,H,W] (channel = k*64 + i*8 + j) -> out [B,2,8H,8W],
- * out[b,c,8h+i,8w+j] = sum_k softmax_k(mask) * 8*flow[b,c,h+ky-1,w+kx-1] (zero padding).  fp32; agrees with the reference to
+ * grid) and raft_decoder_mask.py:143-162 upsample_mask: x [B,C,H,W] (C = 2 flow with mul = 8, C = 1 occlusion with mul = 1),
+ * mask [B,576,H,W] (channel = k*64 + i*8 + j) -> out [B,C,8H,8W],
+ * out[b,c,8h+i,8w+j] = sum_k softmax_k(mask) * mul*x[b,c,h+ky-1,w+kx-1] (zero padding).  fp32; agrees with the reference to
  * summation order (a few ulp). */
-int scf_convex_upsample(const float* flow, const float* mask, float* out, int B, int H, int W, void* stream);
+int scf_convex_upsample(const float* x, const float* mask, float* out, int B, int C, int H, int W, float mul, void* stream);
 
 /* ---- input formatting next to the path ------------------------------------------------------
  * models/refiner/base_refiner.py:96-107 (BaseRefiner.format_data_test after the renderer call): images [B,H,W,cin>=3]

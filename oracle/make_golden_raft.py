@@ -41,6 +41,26 @@ def main():
         out[f'upflow_{i}'] = a.numpy()
         print(f'iteration {i}: |restatement - reference| max {err:.2e}, |flow| max {float(a.abs().max()):.2f}')
     np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'raft_decoder_b2_16x16_it3.npz'), **out)
+    # ---- RAFTDecoderMask
+    from models.decoder.raft_decoder_mask import RAFTDecoderMask
+    decm = RAFTDecoderMask(net_type='Basic', num_levels=4, radius=4, iters=2, corr_lookup_cfg=dict(align_corners=True),
+                           gru_type='SeqConv', act_cfg=dict(type='ReLU'))
+    sdm = RO.make_raft_decoder_mask_weights(3)
+    missing, unexpected = decm.load_state_dict(sdm, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    decm.eval()
+    inputs = RO.make_raft_inputs(3, 2, 16, 16)
+    with torch.no_grad():
+        ref_f, ref_o = decm(*inputs)
+        my_f, my_o = RO.raft_decoder_mask_forward(sdm, *inputs, iters=2)
+    outm = {}
+    for i in range(2):
+        ef, eo = float((ref_f[i] - my_f[i]).abs().max()), float((ref_o[i] - my_o[i]).abs().max())
+        assert ef < 1e-4 and eo < 1e-5, (i, ef, eo)
+        outm[f'upflow_{i}'] = ref_f[i].numpy()
+        outm[f'upocc_{i}'] = ref_o[i].numpy()
+        print(f'RAFTDecoderMask iteration {i}: |restatement - reference| flow {ef:.2e}, occlusion {eo:.2e}')
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'raft_decoder_mask_b2_16x16_it2.npz'), **outm)
 
 
 if __name__ == '__main__':

@@ -6,7 +6,7 @@ from .builder import (REFINERS, DECODERS, ENCODERS, HEAD, LOSSES, BACKBONES, bui
 from .cnn import ConvModule, BaseModule
 from .corr_lookup import CorrLookup, coords_grid
 from .pose_head import MultiClassPoseHead, SingleClassPoseHead
-from .decoder import SCFlowDecoder, RAFTDecoder, CorrelationPyramid, MotionEncoder, ConvGRU, XHead
+from .decoder import SCFlowDecoder, RAFTDecoder, RAFTDecoderMask, CorrelationPyramid, MotionEncoder, ConvGRU, XHead
 from .encoder import RAFTEncoder
 from .refiner import SCFlowRefiner
 from .loss import SequenceLoss, RAFTLoss, L1Loss, DisentanglePointMatchingLoss, filter_flow_by_mask, refiner_loss
@@ -20,7 +20,7 @@ __version__ = '0.1.0'
 __all__ = ['Registry', 'build_from_cfg', 'Config', 'ConfigDict', 'REFINERS', 'DECODERS', 'ENCODERS', 'HEAD', 'LOSSES',
            'BACKBONES', 'build_refiner', 'build_decoder', 'build_encoder', 'build_head', 'build_loss', 'build_backbone',
            'ConvModule', 'BaseModule', 'CorrLookup', 'coords_grid', 'MultiClassPoseHead', 'SingleClassPoseHead',
-           'SCFlowDecoder', 'RAFTDecoder', 'CorrelationPyramid', 'MotionEncoder', 'ConvGRU', 'XHead', 'RAFTEncoder', 'SCFlowRefiner',
+           'SCFlowDecoder', 'RAFTDecoder', 'RAFTDecoderMask', 'CorrelationPyramid', 'MotionEncoder', 'ConvGRU', 'XHead', 'RAFTEncoder', 'SCFlowRefiner',
            'get_pose_from_delta_pose', 'cal_3d_2d_corr', 'get_flow_from_delta_pose_and_points', 'unproject_dense',
            'get_flow_from_delta_pose_dense', 'ops', 'ScfError', 'SequenceLoss', 'RAFTLoss', 'L1Loss',
            'DisentanglePointMatchingLoss', 'filter_flow_by_mask', 'refiner_loss']

@@ -138,7 +138,7 @@ ENC_NORM_IN, ENC_NORM_BN = 0, 1
 _SIGNATURES = {
     'scf_abi_version': (C.c_int, []),
     'scf_struct_size': (C.c_int, [C.c_int]),
-    'scf_convex_upsample': (C.c_int, [c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p]),
+    'scf_convex_upsample': (C.c_int, [c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_void_p]),
     'scf_format_rendered': (C.c_int, [c_void_p, C.c_int, c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), c_void_p, c_void_p,
                                       c_void_p, C.c_int, C.c_int, C.c_int, c_void_p]),
     'scf_last_error': (C.c_char_p, []),

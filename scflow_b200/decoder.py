@@ -150,16 +150,17 @@ class XHead(BaseModule):
             raise ValueError(f'x must be \'flow\' or \'mask\', but got {x}')
         self._pred = PackedCache()
 
-    def forward(self, x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, scale: float = 1.0, act: str = 'none') -> torch.Tensor:
         """``scale`` multiplies the prediction inside the convolution's epilogue (RAFTDecoder's ``.25 * mask_pred(h)``; for a
-        power of two ``scale * acc + scale * bias`` equals ``scale * (acc + bias)`` exactly)."""
+        power of two ``scale * acc + scale * bias`` equals ``scale * (acc + bias)`` exactly); ``act`` is applied there too
+        (RAFTDecoderMask's ``sigmoid(occlusion_pred(h))``)."""
         y = ops.nchw_to_nhwc(x.contiguous())
         for layer in self.layers:
             y = layer.forward_nhwc([(y, 0, layer.in_channels)])
         p = self.predict_layer
         w = self._pred.get([p.weight], lambda: ops.pack_conv_weight([p.weight.detach()]))
         bias = p.bias.detach() if scale == 1.0 else p.bias.detach() * scale
-        out = ops.conv2d_nhwc([(y, 0, y.shape[-1])], w, bias, p.out_channels, p.kernel_size, 1, p.padding, scale=scale)
+        out = ops.conv2d_nhwc([(y, 0, y.shape[-1])], w, bias, p.out_channels, p.kernel_size, 1, p.padding, scale=scale, act=act)
         return ops.nhwc_to_nchw(out)
 
 
@@ -226,6 +227,50 @@ class RAFTDecoder(BaseModule):
             mask = self.mask_pred(h_feat, scale=0.25) if self.convex_upsample_flow else None
             upflow_preds.append(self._upsample(flow, mask))
         return upflow_preds
+
+
+@DECODERS.register_module()
+class RAFTDecoderMask(RAFTDecoder):
+    """models/decoder/raft_decoder_mask.py:21-208: RAFTDecoder plus an occlusion head whose sigmoid output is up-sampled with
+    the same convex combination (without the x8 factor); returns ``(upflow_preds, upocclusion_preds)``."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        # same parameter order as the reference (flow_pred, occlusion_pred, mask_pred)
+        mask_pred = self.mask_pred
+        del self.mask_pred
+        self.occlusion_pred = XHead(self.h_channels, [256], 1, x='mask')
+        self.mask_pred = mask_pred
+
+    def upsample_flow(self, flow: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self._upsample(flow, mask)
+
+    def upsample_mask(self, occlusion: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """raft_decoder_mask.py:143-162."""
+        scale = 2 ** (self.num_levels - 1)
+        if mask is None:
+            return ops.resize_bilinear_nchw(occlusion.contiguous(), scale * occlusion.shape[2], scale * occlusion.shape[3])
+        return ops.convex_upsample(occlusion.contiguous(), mask.contiguous(), mul=1.0)
+
+    def forward(self, feat1: torch.Tensor, feat2: torch.Tensor, flow: torch.Tensor, h_feat: torch.Tensor, cxt_feat: torch.Tensor):
+        """raft_decoder_mask.py:165-208."""
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (feat1, feat2, flow, h_feat, cxt_feat)):
+            raise NotImplementedError('RAFTDecoderMask: forward only (no backward yet); call under torch.no_grad()')
+        corr_pyramid = self.corr_block(feat1, feat2)
+        upflow_preds, upocclusion_preds = [], []
+        b, _, h, w = flow.shape
+        flow = flow.contiguous()
+        for _ in range(self.iters):
+            corr = self.corr_lookup(corr_pyramid, flow)
+            motion_feat = self.encoder(corr, flow)
+            h_feat = self.gru(h_feat, torch.cat([cxt_feat, motion_feat], dim=1))
+            delta_flow = self.flow_pred(h_feat)
+            flow = ops.resize_bilinear_nchw(delta_flow, h, w, scale=1.0, add=flow)        # flow + delta_flow
+            occlusion = self.occlusion_pred(h_feat, act='sigmoid')
+            mask = self.mask_pred(h_feat, scale=0.25) if self.convex_upsample_flow else None
+            upflow_preds.append(self.upsample_flow(flow, mask))
+            upocclusion_preds.append(self.upsample_mask(occlusion, mask))
+        return upflow_preds, upocclusion_preds
 
 
 @DECODERS.register_module()

@@ -371,14 +371,15 @@ def format_rendered(images: torch.Tensor, zbuf: torch.Tensor, mean: Sequence[flo
     return out, depth, mask
 
 
-def convex_upsample(flow: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-    """RAFTDecoder._upsample with a predicted mask (raft_decoder.py:381-416): flow [B,2,H,W], mask [B,576,H,W] ->
-    [B,2,8H,8W] (softmax over the 3x3 neighbourhood, x8 flow scaling)."""
-    _req(flow, 'flow')
+def convex_upsample(x: torch.Tensor, mask: torch.Tensor, mul: float = 8.0) -> torch.Tensor:
+    """RAFTDecoder._upsample with a predicted mask (raft_decoder.py:381-416; ``mul`` = 8) or RAFTDecoderMask.upsample_mask
+    (raft_decoder_mask.py:143-162; ``mul`` = 1): x [B,C<=2,H,W], mask [B,576,H,W] -> [B,C,8H,8W] (softmax over the 3x3
+    neighbourhood)."""
+    _req(x, 'x')
     _req(mask, 'mask')
-    b, c, h, w = flow.shape
-    if c != 2 or tuple(mask.shape) != (b, 576, h, w):
-        raise ValueError(f'convex_upsample: flow [B,2,H,W] and mask [B,576,H,W] expected, got {tuple(flow.shape)} {tuple(mask.shape)}')
-    out = torch.empty(b, 2, 8 * h, 8 * w, device=flow.device, dtype=torch.float32)
-    check(_lib.load().scf_convex_upsample(ptr(flow), ptr(mask), ptr(out), b, h, w, stream_ptr()), 'scf_convex_upsample')
+    b, c, h, w = x.shape
+    if c not in (1, 2) or tuple(mask.shape) != (b, 576, h, w):
+        raise ValueError(f'convex_upsample: x [B,1|2,H,W] and mask [B,576,H,W] expected, got {tuple(x.shape)} {tuple(mask.shape)}')
+    out = torch.empty(b, c, 8 * h, 8 * w, device=x.device, dtype=torch.float32)
+    check(_lib.load().scf_convex_upsample(ptr(x), ptr(mask), ptr(out), b, c, h, w, float(mul), stream_ptr()), 'scf_convex_upsample')
     return out

@@ -96,3 +96,51 @@ def test_raft_decoder_matches_oracle():
     with torch.no_grad():
         plain = dec(*[t.cuda() for t in inputs])
     assert plain[0].shape == (2, 2, 128, 128) and not torch.equal(plain[0], got[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# RAFTDecoderMask (flow + occlusion)
+# ---------------------------------------------------------------------------------------------------------------------
+RAFTM_CFG = dict(RAFT_CFG, type='RAFTDecoderMask', iters=2)
+
+
+def test_raft_decoder_mask_oracle_matches_reference_golden():
+    g = load_golden('raft_decoder_mask_b2_16x16_it2')
+    sd = RO.make_raft_decoder_mask_weights(3)
+    with torch.no_grad():
+        flows, occs = RO.raft_decoder_mask_forward(sd, *RO.make_raft_inputs(3, 2, 16, 16), iters=2)
+    for i in range(2):
+        assert float(np.abs(flows[i].numpy() - g[f'upflow_{i}']).max()) < 1e-4
+        assert float(np.abs(occs[i].numpy() - g[f'upocc_{i}']).max()) < 1e-5
+        assert occs[i].shape == (2, 1, 128, 128) and float(occs[i].min()) >= 0. and float(occs[i].max()) <= 1.
+
+
+def test_raft_decoder_mask_registers_with_reference_keys():
+    from scflow_b200.builder import build_decoder
+    dec = build_decoder(dict(RAFTM_CFG))
+    assert set(dec.state_dict().keys()) == set(RO.make_raft_decoder_mask_weights(0).keys())
+
+
+@pytest.mark.gpu
+def test_raft_decoder_mask_matches_oracle():
+    from scflow_b200.builder import build_decoder
+    sd = RO.make_raft_decoder_mask_weights(3)
+    inputs = RO.make_raft_inputs(3, 2, 16, 16)
+    with torch.no_grad():
+        ref_f, ref_o = RO.raft_decoder_mask_forward(sd, *inputs, iters=2)
+    dec = build_decoder(dict(RAFTM_CFG))
+    dec.load_state_dict(sd)
+    dec = dec.cuda().eval()
+    with torch.no_grad():
+        got_f, got_o = dec(*[t.cuda() for t in inputs])
+    for i in range(2):
+        ef = float((got_f[i].cpu() - ref_f[i]).abs().max())
+        eo = float((got_o[i].cpu() - ref_o[i]).abs().max())
+        print(f'RAFTDecoderMask iteration {i}: flow max err {ef:.3e}, occlusion max err {eo:.3e}')
+        assert ef < 2e-3 and eo < 2e-5
+    # one-channel convex combination without the x8 factor, directly
+    import scflow_b200 as S
+    occ = torch.rand(2, 1, 5, 37)
+    _, mask = RO.make_upsample_case(9, 2, 5, 37)
+    err = float((S.ops.convex_upsample(occ.cuda(), mask.cuda(), mul=1.0).cpu() - RO.convex_upsample_mask(occ, mask)).abs().max())
+    assert err < 2e-6
