@@ -91,3 +91,45 @@ def format_data_test(data_batch: Dict, renderer) -> Dict:
 
 TENSOR_KEYS = ('real_images', 'rendered_images', 'labels', 'ori_k', 'transform_matrix', 'internel_k', 'ref_rotations',
                'ref_translations', 'rendered_masks', 'rendered_depths', 'real_depths', 'gt_rotations', 'gt_translations', 'gt_masks')
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BaseRefiner.format_data_train_sup (base_refiner.py:136-191), pinned like format_data_test (fixture format_train_b5.npz)
+# ----------------------------------------------------------------------------------------------------------------------
+def make_train_batch(seed: int, patch_nums=(2, 3), height: int = 48, width: int = 64) -> Dict:
+    batch = make_data_batch(seed, patch_nums, height, width, with_gt=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    n = sum(patch_nums)
+    batch['annots'].update(init_add_error=30. * torch.rand(n, generator=g), init_rot_error=20. * torch.rand(n, generator=g),
+                           init_trans_error=40. * torch.rand(n, generator=g))
+    return batch
+
+
+def format_data_train_sup(data_batch: Dict, renderer) -> Dict:
+    """base_refiner.py:136-191 with render_augmentation = None (every shipped config)."""
+    real_images, annots, meta_infos = data_batch['img'], data_batch['annots'], data_batch['img_metas']
+    out = {}
+    for name in ('add', 'rot', 'trans'):
+        std, mean = torch.std_mean(annots[f'init_{name}_error'], unbiased=False)
+        out[f'init_{name}_error_mean'], out[f'init_{name}_error_std'] = mean, std
+    ref_rotations, ref_translations = torch.cat(annots['ref_rotations'], 0), torch.cat(annots['ref_translations'], 0)
+    labels, internel_k = torch.cat(annots['labels']), torch.cat(annots['k'])
+    out.update(real_images=torch.cat(real_images), ref_rotations=ref_rotations, ref_translations=ref_translations,
+               gt_rotations=torch.cat(annots['gt_rotations'], 0), gt_translations=torch.cat(annots['gt_translations'], 0),
+               labels=labels, internel_k=internel_k)
+    ro = renderer(ref_rotations, ref_translations, internel_k, labels)
+    images = ro['images'][..., :3].permute(0, 3, 1, 2).contiguous()
+    depths = ro['fragments'].zbuf[..., 0]
+    cfg = meta_infos[0]['img_norm_cfg']
+    mean = torch.Tensor(cfg['mean']).view(1, 3, 1, 1) / 255.
+    std = torch.Tensor(cfg['std']).view(1, 3, 1, 1) / 255.
+    out.update(rendered_images=(images - mean) / std, rendered_depths=depths, rendered_masks=(depths > 0).to(torch.float32))
+    if 'gt_masks' in annots:
+        out['gt_masks'] = torch.cat([m.to_tensor(dtype=torch.bool, device=labels.device) if hasattr(m, 'to_tensor') else m
+                                     for m in annots['gt_masks']], 0)
+    return out
+
+
+TRAIN_KEYS = ('ref_rotations', 'ref_translations', 'gt_rotations', 'gt_translations', 'labels', 'internel_k', 'rendered_images',
+              'real_images', 'rendered_masks', 'rendered_depths', 'init_add_error_mean', 'init_add_error_std', 'init_rot_error_mean',
+              'init_rot_error_std', 'init_trans_error_mean', 'init_trans_error_std', 'gt_masks')

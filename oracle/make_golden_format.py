@@ -40,6 +40,19 @@ def main():
     out['per_img_patch_num'] = np.asarray(ref['per_img_patch_num'])
     np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'format_test_b5.npz'), **out)
     print('restatement == reference on', len(FO.TENSOR_KEYS), 'tensors; fixture written')
+    # ---- format_data_train_sup
+    tb = FO.make_train_batch(5)
+    ref_tb = dict(tb, annots=dict(tb['annots'], gt_masks=[_Mask(m) for m in tb['annots']['gt_masks']]))
+    fake_self = types.SimpleNamespace(renderer=FO.fake_renderer(), render_augmentation=None)
+    ref = base_refiner.BaseRefiner.format_data_train_sup(fake_self, ref_tb)
+    mine = FO.format_data_train_sup(tb, FO.fake_renderer())
+    assert set(ref.keys()) == set(mine.keys()) == set(FO.TRAIN_KEYS), set(ref.keys()) ^ set(mine.keys())
+    out = {}
+    for k in FO.TRAIN_KEYS:
+        assert torch.equal(ref[k], mine[k]), f'{k}: restatement differs from the reference'
+        out[k] = ref[k].numpy()
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'format_train_b5.npz'), **out)
+    print('format_data_train_sup: restatement == reference on', len(FO.TRAIN_KEYS), 'tensors; fixture written')
 
 
 if __name__ == '__main__':

@@ -54,3 +54,38 @@ def format_data_test(data_batch: Dict, renderer: Callable) -> Dict:
                  for m in annots['gt_masks']]
         output.update(gt_masks=torch.cat(masks, dim=0))
     return output
+
+
+def format_data_train_sup(data_batch: Dict, renderer: Callable, render_augmentation=None) -> Dict:
+    """base_refiner.py:136-191: the supervised-training counterpart of ``format_data_test`` (adds the ground-truth poses and
+    the statistics of the initial pose error; no ``ori_k`` / ``transform_matrix``).  ``render_augmentation`` (kornia in the
+    reference, ``None`` in every shipped config) is not part of this package."""
+    if renderer is None:
+        raise RuntimeError('format_data_train_sup needs a renderer (see format_data_test)')
+    if render_augmentation is not None:
+        raise NotImplementedError('render augmentations (kornia AugmentationSequential, base_refiner.py:50-62) are outside this '
+                                  'package; the shipped configs use none')
+    real_images, annots, meta_infos = data_batch['img'], data_batch['annots'], data_batch['img_metas']
+    stats = {}
+    for name in ('add', 'rot', 'trans'):
+        std, mean = torch.std_mean(annots[f'init_{name}_error'], unbiased=False)          # :142-144
+        stats[f'init_{name}_error_mean'], stats[f'init_{name}_error_std'] = mean, std
+    real_images = torch.cat(list(real_images))
+    ref_rotations = torch.cat(list(annots['ref_rotations']), dim=0)
+    ref_translations = torch.cat(list(annots['ref_translations']), dim=0)
+    gt_rotations = torch.cat(list(annots['gt_rotations']), dim=0)
+    gt_translations = torch.cat(list(annots['gt_translations']), dim=0)
+    labels, internel_k = torch.cat(list(annots['labels'])), torch.cat(list(annots['k']))
+    render_outputs = renderer(ref_rotations, ref_translations, internel_k, labels)
+    mean, std = norm_constants(meta_infos[0]['img_norm_cfg'])
+    rendered_images, rendered_depths, rendered_masks = ops.format_rendered(
+        render_outputs['images'].float().contiguous(), render_outputs['fragments'].zbuf.float().contiguous(), mean, std)
+    output = dict(ref_rotations=ref_rotations, ref_translations=ref_translations, gt_rotations=gt_rotations,
+                  gt_translations=gt_translations, labels=labels, internel_k=internel_k, rendered_images=rendered_images,
+                  real_images=real_images, rendered_masks=rendered_masks, rendered_depths=rendered_depths, **stats)
+    if 'gt_masks' in annots:
+        dev = gt_rotations.device
+        masks = [m.to_tensor(dtype=torch.bool, device=dev) if hasattr(m, 'to_tensor') else m.to(device=dev, dtype=torch.bool)
+                 for m in annots['gt_masks']]
+        output['gt_masks'] = torch.cat(masks, dim=0)
+    return output

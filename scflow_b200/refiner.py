@@ -191,6 +191,11 @@ class SCFlowRefiner(BaseModule):
         ``{'images': [N,H,W,4], 'fragments': obj with .zbuf [N,H,W,K]}``, models/utils/renderer.py)."""
         self.renderer = renderer
 
+    def format_data_train_sup(self, data_batch: Dict) -> Dict:
+        """base_refiner.py:136-191 (render augmentations: none, as in every shipped config)."""
+        from . import formatting
+        return formatting.format_data_train_sup(data_batch, self.renderer, getattr(self, 'render_augmentation', None))
+
     def format_data_test(self, data_batch: Dict) -> Dict:
         """base_refiner.py:79-133: flatten the per-image patch lists, render the reference poses, format the render
         (one CUDA pass, scflow_b200/formatting.py)."""
@@ -211,7 +216,8 @@ class SCFlowRefiner(BaseModule):
         return self._loss_funcs
 
     def loss(self, data: Dict):
-        """Forward value of the training loss (scflow_refiner.py:184-258) for a pre-formatted batch: keys ``gt_rotations,
+        """Forward value of the training loss (scflow_refiner.py:184-258) for a collated training batch (formatted through
+        ``format_data_train_sup`` when a renderer is plugged in) or an already formatted one: keys ``gt_rotations,
         gt_translations, ref_rotations, ref_translations, real_images, rendered_images, rendered_depths, rendered_masks,
         gt_masks, internel_k, labels`` (what ``format_data_train_sup`` produces; the renderer is not part of this package).
         Returns ``(loss, log_vars, seq_rotations, seq_translations)``.  FORWARD ONLY: the value carries no autograd graph
@@ -220,6 +226,8 @@ class SCFlowRefiner(BaseModule):
             raise NotImplementedError('SCFlowRefiner.loss computes the forward value only (no backward yet): call it under torch.no_grad()')
         from . import loss as L
         from . import ops
+        if 'rendered_images' not in data:         # a collated training batch: format it first (scflow_refiner.py:186)
+            data = self.format_data_train_sup(data)
         pose_f, flow_f, mask_f = self.loss_functions()
         outs = self.get_pose(data['rendered_images'], data['real_images'], data['ref_rotations'], data['ref_translations'],
                              data['rendered_depths'], data['internel_k'], data['labels'])

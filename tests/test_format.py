@@ -111,3 +111,38 @@ def test_refiner_forward_formats_and_refines_a_dataset_batch():
     data_batch['img_metas'] = [dict(m, geometry_transform_mode='target_intrinsic') for m in batch['img_metas']]
     with pytest.raises(NotImplementedError, match='PnP'), torch.no_grad():
         model(data_batch)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# format_data_train_sup
+# ---------------------------------------------------------------------------------------------------------------------
+def test_format_train_oracle_matches_reference_golden():
+    g = load_golden('format_train_b5')
+    out = FO.format_data_train_sup(FO.make_train_batch(5), FO.fake_renderer())
+    assert set(out.keys()) == set(FO.TRAIN_KEYS)
+    for k in FO.TRAIN_KEYS:
+        assert np.array_equal(out[k].numpy(), g[k]), k
+
+
+def test_product_train_formatting_refuses_augmentations_and_cpu():
+    from scflow_b200 import formatting
+    with pytest.raises(NotImplementedError, match='augment'):
+        formatting.format_data_train_sup(FO.make_train_batch(5), FO.fake_renderer(), render_augmentation=object())
+    with pytest.raises(RuntimeError, match='CUDA'):
+        formatting.format_data_train_sup(FO.make_train_batch(5), FO.fake_renderer())
+
+
+@pytest.mark.gpu
+def test_format_data_train_sup_matches_oracle_bit_exact():
+    from scflow_b200 import formatting
+    batch = FO.make_train_batch(6, patch_nums=(3, 1, 2))
+    ref = FO.format_data_train_sup(batch, FO.fake_renderer())
+    got = formatting.format_data_train_sup(dict(img=_to(batch['img'], 'cuda'), annots=_to(batch['annots'], 'cuda'),
+                                                img_metas=batch['img_metas']), _cuda_renderer())
+    assert set(got.keys()) == set(ref.keys())
+    for k in FO.TRAIN_KEYS:
+        assert got[k].is_cuda and got[k].shape == ref[k].shape and got[k].dtype == ref[k].dtype, k
+        if k.startswith('init_'):          # torch.std_mean on the GPU vs the CPU: reduction order
+            assert float((got[k].cpu() - ref[k]).abs()) < 1e-4 * max(1.0, float(ref[k].abs())), k
+        else:
+            assert torch.equal(got[k].cpu(), ref[k]), k
