@@ -144,8 +144,9 @@ typedef struct scf_tc_conv_desc {
                                        * (with act(0)); lets layers with cout % 8 != 0 leave through TMA stores, which clip
                                        * the channel axis at 16 B granularity */
 } scf_tc_conv_desc;
-/* number of 128-pixel tiles scf_conv2d_tc uses for this geometry (size of the `stats` buffer = tiles*4*2*cout floats)
- * and pixel tiles per sample (0 if a tile may span samples) */
+/* upper bound, in 128-pixel-tile units, of the pixel tiles scf_conv2d_tc may use for this output geometry whichever tiling it
+ * chooses (size of the `stats` buffer = tiles*4*2*cout floats, zero-initialised), and the 128-pixel tiles per sample (0 if a
+ * tile may span samples: then `stats` cannot be used) */
 int scf_conv2d_tc_tiles(int B, int Hout, int Wout, int* tiles_per_sample);
 
 int scf_conv2d_tc(const scf_tc_conv_desc* d, void* stream);

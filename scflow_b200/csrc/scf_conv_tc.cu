@@ -1455,11 +1455,20 @@ void conv2d_tc_last_tiles(int* m_tiles, int* per_img, int* stat_rows) {
   if (stat_rows) *stat_rows = g_last_stat_rows_per_img;
 }
 // upper bound of the number of pixel tiles any tiling of a [B, Hout, Wout] output can have (sizes the `stats` buffer)
+static bool tct_pick_tile(int B, int H, int W, int sx, int sy, bool one_sample, int& tw_sh, int& th_sh);
 int conv2d_tc_max_tiles(int B, int Hout, int Wout) {
   int TW = 0, TH = 0, TB = 0;
   pick_tile(B, Hout, Wout, false, TW, TH, TB);
   const int a = cdiv(Wout, TW) * cdiv(Hout, TH) * cdiv(B, TB), h = cdiv(Wout, 8) * cdiv(Hout, 16) * B;
-  return a > h ? a : h;
+  int best = a > h ? a : h;
+  // transposed tiling: 2 rows of partial sums per 256-pixel tile (its 8 x 32 halo form never has more rows than the 8 x 16 one)
+  int tw_sh = 0, th_sh = 0;
+  if (tct_pick_tile(B, Hout, Wout, 1, 1, true, tw_sh, th_sh)) {
+    const int t = cdiv(Wout, 1 << tw_sh) * cdiv(Hout, 1 << th_sh) * B;
+    const int eq = (2 * t + 3) / 4;
+    if (eq > best) best = eq;
+  }
+  return best;
 }
 
 // ---- transposed-tile variant (conv_tct_kernel): plain-activation layers of <= 128 output channels
@@ -2051,7 +2060,7 @@ int scf_conv2d_tc_tiles(int B, int Hout, int Wout, int* tiles_per_sample) {
   scf::pick_tile(B, Hout, Wout, false, TW, TH, TB);
   const int per = scf::cdiv(Wout, TW) * scf::cdiv(Hout, TH);
   if (tiles_per_sample) *tiles_per_sample = TB == 1 ? per : 0;
-  return per * scf::cdiv(B, TB);
+  return scf::conv2d_tc_max_tiles(B, Hout, Wout);      // upper bound over every tiling the library may choose
 }
 
 int scf_pack_conv_weight_tc(const float* w_oihw, void* packed, int O, int I, int kh, int kw, int cin_pad, int cout_pad,
