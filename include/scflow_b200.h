@@ -9,7 +9,7 @@
  *   models/decoder/raft_decoder.py:152-166    MotionEncoder.forward           -> scf_conv2d (x5) / scf_decoder_forward
  *   models/decoder/raft_decoder.py:235-253    ConvGRU.forward                 -> scf_conv2d (GRU epilogues)
  *   models/decoder/raft_decoder.py:292-294    XHead.forward                   -> scf_conv2d
- *   models/head/pose_head.py:201-211          MultiClassPoseHead.forward      -> scf_group_norm_relu, scf_pose_fc
+ *   models/head/pose_head.py:201-211          MultiClassPoseHead.forward      -> scf_group_norm_relu, scf_linear, scf_pose_project
  *   models/utils/pose.py:124-169              get_pose_from_delta_pose        -> scf_pose_update
  *   models/utils/pose.py:26-64                cal_3d_2d_corr / lift_2d_to_3d  -> scf_unproject
  *   models/utils/pose.py:66-88                get_flow_from_delta_pose_and_points -> scf_reproject

@@ -249,6 +249,9 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """torch's current stream on ``device`` (default: the current device).  Callers that take tensors pass the tensors'
+    device and run the C call under ``torch.cuda.device(device)`` so that kernels, tensor maps and the library's side streams
+    are issued on the device that owns the memory."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

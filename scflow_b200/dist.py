@@ -6,8 +6,10 @@ pose are private, so inference needs NO data-path collective - only a final gath
 (test.py:121-126, tools/eval.py:185-215).
 
 One reference quirk couples samples: ``MultiClassPoseHead`` selects the class row of ``label[0]`` for the whole batch
-(pose_head.py:209-210).  ``shard_batch`` therefore plants the GLOBAL first label at position 0 of every shard's
-label tensor (only element 0 is ever read), which makes an N-rank run reproduce the 1-rank result exactly.
+(pose_head.py:209-210).  ``shard_batch`` therefore adds a ``pose_head_label`` entry holding the GLOBAL first label; the
+refiner / decoder use it as the pose head's class selector, which makes an N-rank run reproduce the 1-rank result exactly.
+The per-sample ``labels`` are left untouched (they pick meshes, diameters and symmetry flags in the loss and are returned
+per image by ``forward_single_pass``).
 """
 import os
 from typing import Dict, Optional, Sequence, Tuple
@@ -48,7 +50,8 @@ _BATCH_KEYS = ('real_images', 'rendered_images', 'render_images', 'ref_rotations
 
 
 def shard_batch(data: Dict[str, torch.Tensor], rank: int, world: int, keep_global_label0: bool = True) -> Dict[str, torch.Tensor]:
-    """Slice every per-sample tensor of `data` to this rank's shard. Non-tensor entries are passed through."""
+    """Slice every per-sample tensor of `data` to this rank's shard. Non-tensor entries are passed through.  With
+    ``keep_global_label0`` the shard carries ``pose_head_label`` = the global batch's first label (1-element tensor)."""
     label_key = 'labels' if 'labels' in data else ('label' if 'label' in data else None)
     n = None
     for k in _BATCH_KEYS:
@@ -64,10 +67,8 @@ def shard_batch(data: Dict[str, torch.Tensor], rank: int, world: int, keep_globa
             out[k] = v[lo:hi].contiguous()
         else:
             out[k] = v
-    if keep_global_label0 and label_key is not None and hi > lo:
-        lab = out[label_key].clone()
-        lab[0] = data[label_key][0]
-        out[label_key] = lab
+    if keep_global_label0 and label_key is not None:
+        out['pose_head_label'] = data[label_key][:1].clone()
     return out
 
 

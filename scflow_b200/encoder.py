@@ -98,6 +98,7 @@ class RAFTEncoder(BaseModule):
             inplanes = planes
         self.conv2 = nn.Conv2d(inplanes, out_channels, 1)
         self.norm_type = norm_cfg['type']
+        self.norm_eps = float(norm_cfg.get('eps', 1e-5))
         self.use_native = True            # set False to force the nn.Module graph (stock cuDNN) in eval mode too
         self._arena = PackedCache()
         self._ws = {}
@@ -115,10 +116,23 @@ class RAFTEncoder(BaseModule):
                 nn.init.zeros_(m.bias)
 
     # ------------------------------------------------------------------ native (C ABI) inference path
+    def _native_refusal(self, x: torch.Tensor) -> Optional[str]:
+        """Why the native (C ABI) path cannot take this call, or None when it can."""
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return ('autograd is enabled with tensors that require grad; the native encoder is inference-only - call it under '
+                    'torch.no_grad(), or put the module in train() mode to use the differentiable nn.Module graph')
+        if not x.is_cuda:
+            return 'the input is not a CUDA tensor (scflow_b200 has no CPU path)'
+        if self.norm_type not in ('IN', 'BN') or self.in_channels != 3 or self.out_channels != 256 or self.scale != 1 / 8:
+            return 'only the shipped configuration (3 -> 256 channels, scale 1/8, IN or BN) is implemented natively'
+        if self.norm_eps != 1e-5:
+            return f'norm eps {self.norm_eps} != 1e-5 (the native kernels fold the default eps)'
+        if x.shape[-2] % 8 or x.shape[-1] % 8:
+            return f'input size {tuple(x.shape[-2:])} is not a multiple of 8'
+        return None
+
     def _native_ok(self, x: torch.Tensor) -> bool:
-        return (self.use_native and not self.training and x.is_cuda and not torch.is_grad_enabled()
-                and self.norm_type in ('IN', 'BN') and self.in_channels == 3 and self.out_channels == 256
-                and self.scale == 1 / 8 and x.shape[-2] % 8 == 0 and x.shape[-1] % 8 == 0)
+        return self.use_native and not self.training and self._native_refusal(x) is None
 
     def _forward_native(self, x: torch.Tensor, ex: Optional['_lib.EncoderOut'] = None) -> Optional[torch.Tensor]:
         """One scf_encoder_forward call; with ``ex`` the final convolution writes the consumer's buffers described by the
@@ -161,8 +175,15 @@ class RAFTEncoder(BaseModule):
         return out
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if self._native_ok(x):
-            return self._forward_native(x)
+        """eval(): ONE C-ABI call, or an error saying why not - never a silent switch to stock PyTorch kernels.  train(): the
+        differentiable nn.Module graph below (batch statistics, autograd).  ``use_native = False`` is the explicit opt-out used
+        by the tests that compare the native path with cuDNN."""
+        if not self.training and self.use_native:
+            why = self._native_refusal(x)
+            if why is not None:
+                raise RuntimeError(f'RAFTEncoder (eval): {why}')
+            with torch.cuda.device(x.device):
+                return self._forward_native(x)
         x = self.relu(getattr(self, self.norm1_name)(self.conv1(x)))
         for name in self.res_layers:
             x = getattr(self, name)(x)

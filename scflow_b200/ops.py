@@ -24,6 +24,9 @@ def _req(t: torch.Tensor, name: str, dtype=torch.float32):
         raise TypeError(f'{name} must be {dtype}, got {t.dtype}')
     if not t.is_contiguous():
         raise ValueError(f'{name} must be contiguous')
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f'{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: call '
+                           f'scflow_b200.ops under torch.cuda.device({t.device.index}) (the modules do this themselves)')
     return t
 
 

@@ -50,6 +50,8 @@ class SCFlowRefiner(BaseModule):
         self._zero_flow = None
         self.overlap_encoders = os.environ.get('SCFLOW_ENC_OVERLAP', '1') != '0'
         self._side_stream = None
+        self._graphs = {}
+        self._last_key = None
         self.filter_invalid_flow = filter_invalid_flow
         self.test_by_flow = self.test_cfg.get('by_flow', False)
         self.test_iter_num = self.test_cfg.get('iters') if 'iters' in self.test_cfg else self.decoder.iters
@@ -83,23 +85,26 @@ class SCFlowRefiner(BaseModule):
         h_feat, cxt_feat = torch.split(cxt_feat, [self.h_channels, self.cxt_channels], dim=1)
         return render_feat, real_feat, torch.tanh(h_feat), torch.relu(cxt_feat)
 
-    def _get_pose_native(self, render_images, real_images, ref_rotation, ref_translation, depth, internel_k, label, init_flow):
-        """Inference fast path: the three encoder passes write the loop's inputs (pixel-major split-bf16 feature maps, tanh'ed
-        hidden state, relu'ed context) straight into the decoder workspace - no NCHW tensors between encoder and loop.
-        Returns None when the configuration does not allow it (the generic path below is used then)."""
-        from . import _lib
-        import ctypes as C
+    def _native_plan(self, render_images, real_images, depth):
+        """(b, h, w) when the fused inference path applies to these inputs, else None (the generic path is used then)."""
         enc, ctx, dec = self.real_encoder, self.context, self.decoder
         if (self.training or torch.is_grad_enabled() or enc is not self.render_encoder or real_images.shape != render_images.shape
                 or not (enc._native_ok(real_images) and ctx._native_ok(render_images)) or not hasattr(dec, 'native_slots')):
             return None
         b, _, h, w = real_images.shape
-        if tuple(depth.shape) != (b, h, w):
+        if tuple(depth.shape) != (b, h, w) or dec.native_slots(b, h, w, real_images.device) is None:
             return None
-        prep = dec.native_slots(b, h, w, real_images.device)
-        if prep is None:
-            return None
-        _, ws, (s_feat, s_h, s_hf32, s_cxt) = prep
+        return b, h, w
+
+    def _native_eager(self, images2, ref_rotation, ref_translation, depth, internel_k, label, init_flow):
+        """Enqueues the whole step on the current stream: the three encoder passes write the loop's inputs (pixel-major
+        split-bf16 feature maps, tanh'ed hidden state, relu'ed context) straight into the decoder workspace - no NCHW tensors
+        between encoder and loop - then the loop runs.  ``images2`` = [real ; rendered] images stacked along the batch."""
+        from . import _lib
+        enc, ctx, dec = self.real_encoder, self.context, self.decoder
+        b2, _, h, w = images2.shape
+        b = b2 // 2
+        _, ws, (s_feat, s_h, s_hf32, s_cxt) = dec.native_slots(b, h, w, images2.device)
         p8 = (h // 8) * (w // 8)
         base = ws.data_ptr()
         ex = _lib.EncoderOut()
@@ -110,26 +115,80 @@ class SCFlowRefiner(BaseModule):
         ex2.hl0, ex2.plane0, ex2.stride0, ex2.act0 = base + s_h, b * p8 * 128, 128, _lib.ACT['tanh']
         ex2.f32_0, ex2.f32_stride0 = base + s_hf32, 128
         ex2.hl1, ex2.plane1, ex2.stride1, ex2.act1 = base + s_cxt, b * p8 * 128, 128, _lib.ACT['relu']
+        render_images = images2[b:]
         if self.overlap_encoders:
             # the context encoder is independent of the feature encoder: run it on a side stream so that its tensor-core
             # convolutions fill the feature encoder's HBM-bound InstanceNorm passes (and vice versa)
-            cur = torch.cuda.current_stream(real_images.device)
-            if self._side_stream is None or self._side_stream.device != real_images.device:
-                self._side_stream = torch.cuda.Stream(device=real_images.device)
+            cur = torch.cuda.current_stream(images2.device)
+            if self._side_stream is None or self._side_stream.device != images2.device:
+                self._side_stream = torch.cuda.Stream(device=images2.device)
             side = self._side_stream
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 ctx._forward_native(render_images, ex2)
-            enc._forward_native(torch.cat([real_images, render_images], dim=0), ex)  # samples [0,b) real, [b,2b) render
+            enc._forward_native(images2, ex)            # samples [0,b) real, [b,2b) rendered
             cur.wait_stream(side)
         else:
-            enc._forward_native(torch.cat([real_images, render_images], dim=0), ex)  # samples [0,b) real, [b,2b) render
+            enc._forward_native(images2, ex)
             ctx._forward_native(render_images, ex2)
-        return dec.forward_prepared(ref_rotation, ref_translation, depth, internel_k, label, init_flow, 0.)
+        return dec.forward_prepared(ref_rotation, ref_translation, depth, internel_k, label, init_flow, 0., allow_graph=False)
+
+    def _get_pose_native(self, render_images, real_images, ref_rotation, ref_translation, depth, internel_k, label, init_flow):
+        """Inference fast path (see ``_native_eager``).  With ``decoder.use_cuda_graph`` the WHOLE step - encoders and loop -
+        is captured once per shape and replayed; the outputs are then views of static buffers that the next call overwrites.
+        Returns None when the configuration does not allow the fused path."""
+        plan = self._native_plan(render_images, real_images, depth)
+        if plan is None:
+            return None
+        b, h, w = plan
+        dev = real_images.device
+        dec = self.decoder
+        ins = dict(ref_rotation=ref_rotation, ref_translation=ref_translation, depth=depth, internel_k=internel_k, init_flow=init_flow)
+        for k, t in ins.items():
+            if not t.is_cuda:
+                raise RuntimeError(f'SCFlowRefiner: {k} must be a CUDA tensor (scflow_b200 has no CPU path)')
+            ins[k] = t.detach().contiguous().float()
+        if label is None:
+            label = torch.zeros(1, dtype=torch.int64, device=dev)
+        ins['label'] = label.detach().to(torch.int64).reshape(-1)[:1].contiguous()       # only label[0] is read (pose_head.py:209-210)
+        real_images, render_images = real_images.detach().float(), render_images.detach().float()
+        with torch.cuda.device(dev):
+            if not getattr(dec, 'use_cuda_graph', False) or torch.cuda.is_current_stream_capturing():
+                return self._native_eager(torch.cat([real_images, render_images], dim=0), **ins)
+            _, ws, _ = dec.native_slots(b, h, w, dev)
+            key = (b, h, w, int(dec.iters), str(dev), ws.data_ptr(), int(dec.identity_pose_head), self.overlap_encoders)
+            entry = self._graphs.get(key)
+            if entry is None:
+                # Cache miss: this call's result comes from ONE eager run (also the warm-up that loads modules and sets function
+                # attributes); the capture itself enqueues nothing.  A shape is captured only when it repeats - test-time batches
+                # with a different patch count every call would otherwise pay a capture per call for nothing.
+                static = {k: v.clone() for k, v in ins.items()}
+                static['images2'] = torch.cat([real_images, render_images], dim=0)
+                outs = self._native_eager(**static)
+                seen, self._last_key = self._last_key == key, key
+                if not seen:
+                    return outs
+                torch.cuda.current_stream(dev).synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    replay_outs = self._native_eager(**static)
+                self._graphs = {key: (graph, static, replay_outs)}      # keep only the latest shape
+                return outs                                             # (the eager run's; replay_outs are filled by replays)
+            graph, static, outs = entry
+            static['images2'][:b].copy_(real_images, non_blocking=True)
+            static['images2'][b:].copy_(render_images, non_blocking=True)
+            for k, v in ins.items():
+                static[k].copy_(v, non_blocking=True)
+            graph.replay()
+            return outs
 
     def get_pose(self, render_images, real_images, ref_rotation, ref_translation, depth, internel_k, label,
-                 init_flow=None):
-        """scflow_refiner.py:112-142: encoders -> decoder loop; returns the decoder's 7 lists."""
+                 init_flow=None, pose_head_label=None):
+        """scflow_refiner.py:112-142: encoders -> decoder loop; returns the decoder's 7 lists.  ``pose_head_label`` (not in the
+        reference): class selector of the pose head when this batch is a shard of a larger one (the reference's head uses the
+        GLOBAL ``label[0]`` for every row, pose_head.py:209-210; see scflow_b200/dist.py)."""
+        if pose_head_label is not None:
+            label = pose_head_label.reshape(-1)[:1]
         if self.native_feature_path:
             if init_flow is None:
                 n, _, h, w = real_images.shape
@@ -157,7 +216,7 @@ class SCFlowRefiner(BaseModule):
         self.decoder.iters = self.test_iter_num
         try:
             outs = self.get_pose(data['rendered_images'], data['real_images'], data['ref_rotations'], data['ref_translations'],
-                                 data['rendered_depths'], data['internel_k'], labels)
+                                 data['rendered_depths'], data['internel_k'], labels, pose_head_label=data.get('pose_head_label'))
         finally:
             self.decoder.iters = iters
         seq_rotations, seq_translations = outs[2], outs[3]

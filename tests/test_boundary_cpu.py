@@ -125,8 +125,11 @@ def test_shard_helpers():
         assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
     data = dict(labels=torch.tensor([9, 1, 2, 3, 4]), depth=torch.arange(5.)[:, None, None].repeat(1, 2, 2), tag='x')
     s1 = D.shard_batch(data, 1, 2)
-    assert s1['labels'].tolist() == [9, 4] and s1['depth'][:, 0, 0].tolist() == [3., 4.] and s1['tag'] == 'x'
-    assert D.shard_batch(data, 1, 2, keep_global_label0=False)['labels'].tolist() == [3, 4]
+    # per-sample labels stay the shard's own (they select meshes / symmetry in the loss and are returned per image); the pose
+    # head's class selector - the GLOBAL label[0], pose_head.py:209-210 - travels separately
+    assert s1['labels'].tolist() == [3, 4] and s1['pose_head_label'].tolist() == [9]
+    assert s1['depth'][:, 0, 0].tolist() == [3., 4.] and s1['tag'] == 'x'
+    assert 'pose_head_label' not in D.shard_batch(data, 1, 2, keep_global_label0=False)
 
 
 def test_host_only_layout_queries():
@@ -150,3 +153,19 @@ def test_host_only_layout_queries():
     assert lib.scf_conv2d_tc_tiles(2, 8, 8, ctypes.byref(per)) in (1, 2) and per.value == 0      # a 128-pixel tile spans both samples (the count is an upper bound over the tilings)
     assert lib.scf_refiner_loss_scratch_bytes(8, 32) >= 8 * 296 * 3 * 8 + 8 * 32 * 4
     assert lib.scf_refiner_loss_scratch_bytes(0, 32) == 0
+
+
+def test_encoder_never_falls_back_silently():
+    """eval(): the encoder is ONE C-ABI call or an error that says why - no silent switch to stock PyTorch kernels
+    (north_star: no CPU fallback).  train() keeps the differentiable nn.Module graph."""
+    import pytest
+    enc = S.build_encoder(dict(scflow_model_cfg()['encoder']))
+    x = torch.rand(1, 3, 32, 32)
+    enc.eval()
+    with pytest.raises(RuntimeError, match='autograd is enabled'):
+        enc(x)                                   # grad-enabled eval call
+    with torch.no_grad(), pytest.raises(RuntimeError, match='not a CUDA tensor'):
+        enc(x)                                   # CPU tensor
+    enc.train()
+    y = enc(x)                                   # training graph: plain nn.Module ops with autograd
+    assert y.shape == (1, 256, 4, 4) and y.requires_grad

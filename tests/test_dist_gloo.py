@@ -36,7 +36,7 @@ def _run(data, sd):
     with torch.no_grad():
         outs = O.decoder_forward(sd, data['feat_render'], data['feat_real'], data['h_feat'], data['cxt_feat'],
                                  data['ref_rotation'], data['ref_translation'], data['depth'], data['internel_k'],
-                                 data['label'], torch.zeros(n, 2, 256, 256), 0., iters=ITERS)
+                                 data.get('pose_head_label', data['label']), torch.zeros(n, 2, 256, 256), 0., iters=ITERS)
     return outs[2][-1], outs[3][-1]
 
 

@@ -222,7 +222,9 @@ def test_native_encoder_matches_oracle(norm):
 @pytest.mark.parametrize('graph', [False, True])
 def test_native_feature_path_matches_generic_path_and_oracle(graph):
     """get_pose with the encoders writing the loop's inputs straight into the decoder workspace (no NCHW round trip) against
-    the generic module-by-module path and against the CPU oracle (flow EPE < 1e-3 px, the stated tolerance)."""
+    the generic module-by-module path and against the CPU oracle (flow EPE < 1e-3 px, the stated tolerance).  EVERY call is
+    checked: the first (eager), the second (eager + graph capture) and the third (graph replay) - a replay-only comparison
+    would hide a capture call that consumed the encoder-written hidden state twice."""
     import scflow_b200 as S
     seed, b, iters = 4, 2, 3
     model = S.build_refiner(scflow_model_cfg(iters=iters, precision=1, use_cuda_graph=graph))
@@ -234,16 +236,67 @@ def test_native_feature_path_matches_generic_path_and_oracle(graph):
     args = (c['render_images'], c['real_images'], c['ref_rotation'], c['ref_translation'], c['depth'], c['internel_k'], c['label'])
     with torch.no_grad():
         assert model.native_feature_path
-        for _ in range(2):                      # second call replays the captured graph when graph=True
-            fast = [[t.clone() for t in lst] for lst in model.get_pose(*args)]
+        calls = []
+        for _ in range(3):
+            calls.append([[t.clone() for t in lst] for lst in model.get_pose(*args)])
+        assert bool(model._graphs) == graph, 'the whole step must be captured once the shape repeats (and only then)'
         model.native_feature_path = False
-        slow = model.get_pose(*args)
+        slow = [[t.clone() for t in lst] for lst in model.get_pose(*args)]
         ref = O.get_pose(sd, scene['render_images'], scene['real_images'], scene['ref_rotation'], scene['ref_translation'],
                          scene['depth'], scene['internel_k'], scene['label'], iters=iters)
-    for k in (0, 1):
-        for i in range(iters):
-            d = float((fast[k][i] - slow[k][i]).pow(2).sum(1).sqrt().mean())
-            e = float((fast[k][i].cpu() - ref[k][i]).pow(2).sum(1).sqrt().mean())
-            assert d < 1e-4, f'native vs generic path: list {k} iter {i} EPE {d:.3e}'
-            assert e < 1e-3, f'native path vs oracle: list {k} iter {i} EPE {e:.3e}'
-    assert float((fast[2][-1] - slow[2][-1]).abs().max()) < 1e-5
+    for n, fast in enumerate(calls):
+        for k in (0, 1):
+            for i in range(iters):
+                d = float((fast[k][i] - slow[k][i]).pow(2).sum(1).sqrt().mean())
+                e = float((fast[k][i].cpu() - ref[k][i]).pow(2).sum(1).sqrt().mean())
+                assert d < 1e-4, f'call {n}: native vs generic path: list {k} iter {i} EPE {d:.3e}'
+                assert e < 1e-3, f'call {n}: native path vs oracle: list {k} iter {i} EPE {e:.3e}'
+        assert float((fast[2][-1] - slow[2][-1]).abs().max()) < 1e-5
+        for k in range(7):                       # eager, capture and replay calls agree bit for bit
+            assert all(torch.equal(a, b_) for a, b_ in zip(fast[k], calls[0][k])), f'call {n} differs from call 0 in list {k}'
+
+
+def test_graph_survives_shape_changes():
+    """Patch counts change from batch to batch at test time: A, A, A (captured, replayed), B, A, A, B must each give the
+    result of an eager model, whatever the graph cache holds."""
+    import scflow_b200 as S
+    seed, iters = 6, 2
+    sd = O.make_model_weights(seed)
+    models = {}
+    for graph in (False, True):
+        m = S.build_refiner(scflow_model_cfg(iters=iters, precision=1, use_cuda_graph=graph))
+        m.load_state_dict(sd, strict=False)
+        models[graph] = m.cuda().eval()
+    scenes = {b: {k: v.cuda() for k, v in O.make_scene(seed + b, b).items()} for b in (2, 3)}
+
+    def run(m, b):
+        c = scenes[b]
+        with torch.no_grad():
+            outs = m.get_pose(c['render_images'], c['real_images'], c['ref_rotation'], c['ref_translation'], c['depth'],
+                              c['internel_k'], c['label'])
+        return [outs[k][-1].clone() for k in (0, 1, 2, 3, 4)]
+    want = {b: run(models[False], b) for b in (2, 3)}
+    for n, b in enumerate((2, 2, 2, 3, 2, 2, 3, 3, 3)):
+        got = run(models[True], b)
+        for g, w_ in zip(got, want[b]):
+            assert torch.equal(g, w_), f'call {n} (batch {b}) differs from the eager model'
+
+
+def test_decoder_graph_every_call_matches_eager():
+    """SCFlowDecoder's own graph (generic API): eager first call, capture on the repeat, replay afterwards - all identical."""
+    seed, b, iters = 8, 2, 2
+    scene, f = O.make_scene(seed, b), O.make_features(seed, b)
+    outs = {}
+    for graph in (False, True):
+        dec, _ = build_decoder_from_oracle_weights(seed, iters, precision=1, use_cuda_graph=graph)
+        res = []
+        with torch.no_grad():
+            for _ in range(3):
+                o = dec(f['feat_render'].cuda(), f['feat_real'].cuda(), f['h_feat'].cuda(), f['cxt_feat'].cuda(),
+                        scene['ref_rotation'].cuda(), scene['ref_translation'].cuda(), scene['depth'].cuda(), scene['internel_k'].cuda(),
+                        label=scene['label'].cuda(), init_flow=torch.zeros(b, 2, 256, 256, device='cuda'), invalid_flow_num=0.)
+                res.append([o[k][-1].clone() for k in range(7)])
+        outs[graph] = res
+    for n in range(3):
+        for a, b_ in zip(outs[True][n], outs[False][0]):
+            assert torch.equal(a, b_), f'graph call {n} differs from the eager decoder'
