@@ -55,7 +55,8 @@ extern "C" {
 
 int scf_abi_version(void);
 /* sizeof() of a descriptor struct as this library was compiled, so that a binding can verify its mirror of the layout:
- * 0 scf_conv_desc, 1 scf_tc_conv_desc, 2 scf_decoder_cfg, 3 scf_decoder_io, 4 scf_encoder_out, 5 scf_loss_desc; -1 otherwise */
+ * 0 scf_conv_desc, 1 scf_tc_conv_desc, 2 scf_decoder_cfg, 3 scf_decoder_io, 4 scf_encoder_out, 5 scf_loss_desc,
+ * 6 scf_gru_pass_desc, 7 scf_lookup_conv_desc; -1 otherwise */
 int scf_struct_size(int which);
 const char* scf_last_error(void);
 /* 1 if the tcgen05/TMA code paths are usable on the current device (compute capability 10.x), else 0 */
@@ -160,6 +161,28 @@ int scf_nchw_to_nhwc_split(const float* src, void* dst_hl, long long plane_strid
 /* NHWC fp32 channels [src_coff, src_coff+nch) -> split-bf16 planes at dst_coff */
 int scf_split_copy(const float* src, int src_stride, int src_coff, void* dst_hl, long long plane_stride, int dst_stride,
                    int dst_coff, long long npix, int nch, void* stream);
+
+/* ---------------------------------------------------------------- SepConvGRU pass, one kernel ----------- */
+/* ConvGRU.forward, one pass (models/decoder/raft_decoder.py:245-253): z, r gates, r*h, q and the state update of a 256-pixel
+ * tile (whole rows for the 1x5 pass, whole columns for the 5x1 pass) on one SM - z and r accumulate side by side in TMEM, r*h
+ * becomes the q convolution's operand in shared memory, h' leaves as fp32 + split-bf16.  The context columns of the GRU's input
+ * are loop invariant: their contribution (+ bias) arrives as fp32 maps pre_zr / pre_q, the kernel contracts over [h | motion].
+ * Needs 32 positions along the taps (W == 32 for the horizontal pass, H == 32 for the vertical one) and a multiple of 8 across. */
+typedef struct scf_gru_pass_desc {
+  const void* h_hl; long long h_plane;    /* state, split-bf16 NHWC [2][B*H*W][128] (lo plane h_plane elements after hi) */
+  const float* h_f32;                     /* state, fp32 NHWC [B*H*W][128] */
+  const void* m_hl; long long m_plane;    /* motion features, split-bf16 NHWC [2][B*H*W][128] */
+  const void* w_zr;                       /* packed bf16 [2][5][256][256]: rows z (0..127) | r (128..255), columns [h | motion] */
+  const void* w_q;                        /* packed bf16 [2][5][128][256]: columns [r*h | motion] */
+  const float* pre_zr;                    /* fp32 [B*H*W][256] */
+  const float* pre_q;                     /* fp32 [B*H*W][128] */
+  float* z_scratch;                       /* fp32 [B*H*W][128] */
+  float* out_f32;                         /* h' fp32 NHWC [B*H*W][128] (not in place) */
+  void* out_hl; long long out_plane;      /* h' split-bf16 */
+  int B, H, W;
+  int vertical;                           /* 0: 1x5 pass (taps along x), 1: 5x1 pass (taps along y) */
+} scf_gru_pass_desc;
+int scf_gru_pass_fused(const scf_gru_pass_desc* d, void* stream);
 
 /* ---------------------------------------------------------------- correlation pyramid -------------------- */
 /* feat_render / feat_real: NCHW fp32 [B,C,H8,W8]. levels[l]: fp32 [B*H8*W8, Hl*Wl] (the reference's

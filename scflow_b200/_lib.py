@@ -80,6 +80,16 @@ class EncoderOut(C.Structure):
     ]
 
 
+class GruPassDesc(C.Structure):
+    """scf_gru_pass_desc (include/scflow_b200.h)."""
+    _fields_ = [
+        ('h_hl', c_void_p), ('h_plane', C.c_longlong), ('h_f32', c_void_p), ('m_hl', c_void_p), ('m_plane', C.c_longlong),
+        ('w_zr', c_void_p), ('w_q', c_void_p), ('pre_zr', c_void_p), ('pre_q', c_void_p), ('z_scratch', c_void_p),
+        ('out_f32', c_void_p), ('out_hl', c_void_p), ('out_plane', C.c_longlong), ('B', C.c_int), ('H', C.c_int), ('W', C.c_int),
+        ('vertical', C.c_int),
+    ]
+
+
 class LossDesc(C.Structure):
     _fields_ = [
         ('flow_pred', c_void_p), ('mask_pred', c_void_p), ('rotation', c_void_p), ('translation', c_void_p),
@@ -177,6 +187,7 @@ _SIGNATURES = {
     'scf_filter_flow_by_mask': (C.c_int, [c_void_p, c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, c_void_p]),
     'scf_refiner_loss_scratch_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'scf_refiner_loss': (C.c_int, [C.POINTER(LossDesc), c_void_p]),
+    'scf_gru_pass_fused': (C.c_int, [C.POINTER(GruPassDesc), c_void_p]),
     'scf_encoder_packed_bytes': (C.c_size_t, []),
     'scf_encoder_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'scf_encoder_pack': (C.c_int, [C.c_int, C.POINTER(c_void_p), c_void_p, c_void_p]),
@@ -230,7 +241,7 @@ def load():
             fn.argtypes = args
         if lib.scf_abi_version() != 1:
             raise ScfError('libscflow_sm100a.so ABI version mismatch')
-        for which, cls in enumerate((ConvDesc, TcConvDesc, DecoderCfg, DecoderIO, EncoderOut, LossDesc)):
+        for which, cls in enumerate((ConvDesc, TcConvDesc, DecoderCfg, DecoderIO, EncoderOut, LossDesc, GruPassDesc)):
             if lib.scf_struct_size(which) != C.sizeof(cls):
                 raise ScfError(f'libscflow_sm100a.so was built with a different {cls.__name__} layout '
                                f'({lib.scf_struct_size(which)} bytes, binding {C.sizeof(cls)}): rebuild the library')

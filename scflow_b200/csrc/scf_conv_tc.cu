@@ -1399,6 +1399,9 @@ int pack_conv_weight_tc_foldx(const float* w_oihw, float* scratch, void* packed,
                               int cout_pad, int o_off, cudaStream_t st);
 
 // ------------------------------------------------------------------ host side
+int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr,
+               CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B);
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1416,9 +1419,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr,
-                      CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box, const cuuint32_t* elem_strides, CUtensorMapDataType dtype, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   SCF_REQUIRE(fn != nullptr, SCF_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};

@@ -22,6 +22,7 @@ int pack_conv_weight_tc_foldx(const float* w_oihw, float* scratch, void* packed,
                               int cout_pad, int o_off, cudaStream_t st);
 int corr_build_dispatch(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
                         float* const* levels, void* scratch, int precision, cudaStream_t st);
+int gru_pass_fused(const scf_gru_pass_desc& d, cudaStream_t st);
 int corr_build_presplit(void* scratch, int B, int C, int H8, int W8, int num_levels, float* const* levels, cudaStream_t st);
 
 thread_local char g_err[512] = {0};
@@ -286,6 +287,7 @@ int scf_struct_size(int which) {
     case 3: return (int)sizeof(scf_decoder_io);
     case 4: return (int)sizeof(scf_encoder_out);
     case 5: return (int)sizeof(scf_loss_desc);
+    case 6: return (int)sizeof(scf_gru_pass_desc);
     default: return -1;
   }
 }
@@ -559,7 +561,21 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       SCF_TRY(convtc(PC_OUT0, {{S(ws.s_cf), 256, 0, 256}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_motion), 128, 0));
       pad_writable = 0;
       SCF_TRY(scf_split_copy(menc_flow, 2, 0, S(ws.s_motion), (long long)BP * 128, 128, 126, (long long)BP, 2, lst));
+      // SepConvGRU: one kernel per pass where the map allows whole-row / whole-column tiles (SCFLOW_GRU_FUSED=0: two kernels)
+      static const bool gru_fused = [] { const char* e = getenv("SCFLOW_GRU_FUSED"); return e ? atoi(e) != 0 : true; }();
       for (int pass = 0; pass < 2; ++pass) {
+        if (gru_fused && H8 == 32 && W8 == 32) {
+          scf_gru_pass_desc g = {};
+          g.h_hl = S(ws.s_h[pass]); g.h_plane = (long long)BP * 128; g.h_f32 = F(ws.h[pass]);
+          g.m_hl = S(ws.s_motion); g.m_plane = (long long)BP * 128;
+          g.w_zr = reinterpret_cast<const char*>(packed) + a.pc[pass == 0 ? PC_ZR0 : PC_ZR1].tc_off;
+          g.w_q = reinterpret_cast<const char*>(packed) + a.pc[pass == 0 ? PC_Q0 : PC_Q1].tc_off;
+          g.pre_zr = F(ws.pre_zr[pass]); g.pre_q = F(ws.pre_q[pass]); g.z_scratch = F(ws.z);
+          g.out_f32 = F(ws.h[pass ^ 1]); g.out_hl = S(ws.s_h[pass ^ 1]); g.out_plane = (long long)BP * 128;
+          g.B = B; g.H = H8; g.W = W8; g.vertical = pass;
+          SCF_TRY(gru_pass_fused(g, lst));
+          continue;
+        }
         SCF_TRY(convtc(pass == 0 ? PC_ZR0 : PC_ZR1, {{S(ws.s_h[pass]), 128, 0, 128}, {S(ws.s_motion), 128, 0, 128}},
                        SCF_ACT_SIGMOID, F(ws.z), 128, nullptr, 0, 0, SCF_EPI_GRU_ZR, F(ws.h[pass]), nullptr, S(ws.s_rh),
                        F(ws.pre_zr[pass]), 256));

@@ -352,6 +352,54 @@ def make_tc_gru_zr_bench(h, cxt, mot, wz, wr, bias, z, rh):
     return launch, f'conv_tc_kernel (GRU z|r 1x5, tcgen05 split-bf16, N=256, K={k}; context term hoisted out of the loop)', 3, k
 
 
+class GruPassFused:
+    """One SepConvGRU pass as ONE kernel (scf_gru_pass_fused; raft_decoder.py:245-253).  Built from the reference's weights
+    ``conv_z/r/q.{pass}.conv.weight`` [128,384,kh,kw] and biases; the context columns' contribution (loop invariant) is
+    evaluated once per context map with ``precompute`` and then every ``__call__(h, motion)`` is one launch.
+    h / cxt / motion: fp32 NHWC [B,H,W,128]."""
+
+    def __init__(self, wz, wr, wq, bz, br, bq):
+        self.kernel = (int(wz.shape[2]), int(wz.shape[3]))
+        if self.kernel not in ((1, 5), (5, 1)):
+            raise ValueError('GruPassFused: SepConvGRU kernels are 1x5 or 5x1')
+        self.vertical = int(self.kernel == (5, 1))
+        hm = lambda w: torch.cat([w[:, :128], w[:, 256:]], 1).contiguous()      # [h | motion] columns
+        self.w_zr = pack_conv_weight_tc([hm(wz), hm(wr)])
+        self.w_q = pack_conv_weight_tc([hm(wq)])
+        self.w_czr = pack_conv_weight_tc([wz[:, 128:256].contiguous(), wr[:, 128:256].contiguous()])
+        self.w_cq = pack_conv_weight_tc([wq[:, 128:256].contiguous()])
+        self.b_zr, self.b_q = torch.cat([bz, br]).contiguous(), bq.contiguous()
+        self.pre_zr = self.pre_q = None
+
+    def precompute(self, cxt: torch.Tensor):
+        cs = split_nchw(cxt.permute(0, 3, 1, 2).contiguous())
+        self.pre_zr = torch.empty(*cxt.shape[:3], 256, device=cxt.device, dtype=torch.float32)
+        self.pre_q = torch.empty(*cxt.shape[:3], 128, device=cxt.device, dtype=torch.float32)
+        conv2d_tc([(cs, 0, 128)], self.w_czr, self.b_zr, 256, self.kernel, act='none', out_f32=self.pre_zr)
+        conv2d_tc([(cs, 0, 128)], self.w_cq, self.b_q, 128, self.kernel, act='none', out_f32=self.pre_q)
+
+    def __call__(self, h: torch.Tensor, motion: torch.Tensor):
+        """Returns (h' fp32 NHWC [B,H,W,128], h' split-bf16 [2,B,H,W,128])."""
+        _req(h, 'h')
+        _req(motion, 'motion')
+        b, hh, ww, _ = h.shape
+        hs = split_nchw(h.permute(0, 3, 1, 2).contiguous())
+        ms = split_nchw(motion.permute(0, 3, 1, 2).contiguous())
+        z = torch.empty_like(h)
+        out = torch.empty_like(h)
+        out_hl = torch.empty(2, b, hh, ww, 128, device=h.device, dtype=torch.bfloat16)
+        d = _lib.GruPassDesc()
+        d.h_hl, d.h_plane, d.h_f32 = hs.data_ptr(), hs[0].numel(), h.data_ptr()
+        d.m_hl, d.m_plane = ms.data_ptr(), ms[0].numel()
+        d.w_zr, d.w_q = self.w_zr.data_ptr(), self.w_q.data_ptr()
+        d.pre_zr, d.pre_q, d.z_scratch = self.pre_zr.data_ptr(), self.pre_q.data_ptr(), z.data_ptr()
+        d.out_f32, d.out_hl, d.out_plane = out.data_ptr(), out_hl.data_ptr(), out_hl[0].numel()
+        d.B, d.H, d.W, d.vertical = b, hh, ww, self.vertical
+        self._keep = (hs, ms, z)
+        check(_lib.load().scf_gru_pass_fused(C.byref(d), stream_ptr()), 'scf_gru_pass_fused')
+        return out, out_hl
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # input formatting next to the path (SURVEY.md §8f rank 3)
 # ----------------------------------------------------------------------------------------------------------------------
