@@ -167,7 +167,7 @@ int scf_split_copy(const float* src, int src_stride, int src_coff, void* dst_hl,
  * tile (whole rows for the 1x5 pass, whole columns for the 5x1 pass) on one SM - z and r accumulate side by side in TMEM, r*h
  * becomes the q convolution's operand in shared memory, h' leaves as fp32 + split-bf16.  The context columns of the GRU's input
  * are loop invariant: their contribution (+ bias) arrives as fp32 maps pre_zr / pre_q, the kernel contracts over [h | motion].
- * Needs 32 positions along the taps (W == 32 for the horizontal pass, H == 32 for the vertical one) and a multiple of 8 across. */
+ * Needs a 32 x 32 map (256x256 crops at 1/8 resolution); other sizes keep the two-convolution form (scf_conv2d_tc). */
 typedef struct scf_gru_pass_desc {
   const void* h_hl; long long h_plane;    /* state, split-bf16 NHWC [2][B*H*W][128] (lo plane h_plane elements after hi) */
   const float* h_f32;                     /* state, fp32 NHWC [B*H*W][128] */
@@ -176,7 +176,6 @@ typedef struct scf_gru_pass_desc {
   const void* w_q;                        /* packed bf16 [2][5][128][256]: columns [r*h | motion] */
   const float* pre_zr;                    /* fp32 [B*H*W][256] */
   const float* pre_q;                     /* fp32 [B*H*W][128] */
-  float* z_scratch;                       /* fp32 [B*H*W][128] */
   float* out_f32;                         /* h' fp32 NHWC [B*H*W][128] (not in place) */
   void* out_hl; long long out_plane;      /* h' split-bf16 */
   int B, H, W;

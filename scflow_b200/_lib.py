@@ -84,7 +84,7 @@ class GruPassDesc(C.Structure):
     """scf_gru_pass_desc (include/scflow_b200.h)."""
     _fields_ = [
         ('h_hl', c_void_p), ('h_plane', C.c_longlong), ('h_f32', c_void_p), ('m_hl', c_void_p), ('m_plane', C.c_longlong),
-        ('w_zr', c_void_p), ('w_q', c_void_p), ('pre_zr', c_void_p), ('pre_q', c_void_p), ('z_scratch', c_void_p),
+        ('w_zr', c_void_p), ('w_q', c_void_p), ('pre_zr', c_void_p), ('pre_q', c_void_p),
         ('out_f32', c_void_p), ('out_hl', c_void_p), ('out_plane', C.c_longlong), ('B', C.c_int), ('H', C.c_int), ('W', C.c_int),
         ('vertical', C.c_int),
     ]

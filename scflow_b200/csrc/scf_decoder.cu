@@ -570,7 +570,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
           g.m_hl = S(ws.s_motion); g.m_plane = (long long)BP * 128;
           g.w_zr = reinterpret_cast<const char*>(packed) + a.pc[pass == 0 ? PC_ZR0 : PC_ZR1].tc_off;
           g.w_q = reinterpret_cast<const char*>(packed) + a.pc[pass == 0 ? PC_Q0 : PC_Q1].tc_off;
-          g.pre_zr = F(ws.pre_zr[pass]); g.pre_q = F(ws.pre_q[pass]); g.z_scratch = F(ws.z);
+          g.pre_zr = F(ws.pre_zr[pass]); g.pre_q = F(ws.pre_q[pass]);
           g.out_f32 = F(ws.h[pass ^ 1]); g.out_hl = S(ws.s_h[pass ^ 1]); g.out_plane = (long long)BP * 128;
           g.B = B; g.H = H8; g.W = W8; g.vertical = pass;
           SCF_TRY(gru_pass_fused(g, lst));

@@ -385,17 +385,16 @@ class GruPassFused:
         b, hh, ww, _ = h.shape
         hs = split_nchw(h.permute(0, 3, 1, 2).contiguous())
         ms = split_nchw(motion.permute(0, 3, 1, 2).contiguous())
-        z = torch.empty_like(h)
         out = torch.empty_like(h)
         out_hl = torch.empty(2, b, hh, ww, 128, device=h.device, dtype=torch.bfloat16)
         d = _lib.GruPassDesc()
         d.h_hl, d.h_plane, d.h_f32 = hs.data_ptr(), hs[0].numel(), h.data_ptr()
         d.m_hl, d.m_plane = ms.data_ptr(), ms[0].numel()
         d.w_zr, d.w_q = self.w_zr.data_ptr(), self.w_q.data_ptr()
-        d.pre_zr, d.pre_q, d.z_scratch = self.pre_zr.data_ptr(), self.pre_q.data_ptr(), z.data_ptr()
+        d.pre_zr, d.pre_q = self.pre_zr.data_ptr(), self.pre_q.data_ptr()
         d.out_f32, d.out_hl, d.out_plane = out.data_ptr(), out_hl.data_ptr(), out_hl[0].numel()
         d.B, d.H, d.W, d.vertical = b, hh, ww, self.vertical
-        self._keep = (hs, ms, z)
+        self._keep = (hs, ms)
         check(_lib.load().scf_gru_pass_fused(C.byref(d), stream_ptr()), 'scf_gru_pass_fused')
         return out, out_hl
 
