@@ -230,6 +230,11 @@ int scf_unproject(const float* depth, const float* K, const float* rot, const fl
 /* flow NCHW [B,2,H,W]: projected flow at depth>0, `invalid` elsewhere */
 int scf_reproject(const float* pts4, const float* K, const float* rot, const float* trs, float invalid, float* flow,
                   int B, int H, int W, void* stream);
+/* Same, and in the same launch the NEXT iteration's coarse flow  flow8 = (H8/H) * F.interpolate(flow, H8/H, bilinear,
+ * align_corners=True)  (scflow_decoder.py:196-197) as NHWC [B,H8,W8,2]: each coarse pixel blends the pose-induced flow of its
+ * four full-resolution taps, so the dense map is not read back and no separate resize is launched. */
+int scf_reproject_down(const float* pts4, const float* K, const float* rot, const float* trs, float invalid, float* flow,
+                       int B, int H, int W, float* flow8, int H8, int W8, void* stream);
 /* bilinear, align_corners=True. src element (b,c,y,x) at b*s_b + c*s_c + y*s_y + x*s_x (floats); same for dst.
  * dst = scale * interp(src (+ add, same strides as src, optional)). */
 int scf_resize_bilinear(const float* src, const float* add, long long s_b, long long s_c, long long s_y, long long s_x,

@@ -181,6 +181,8 @@ _SIGNATURES = {
     'scf_pose_update': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, c_void_p]),
     'scf_unproject': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p]),
     'scf_reproject': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_float, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p]),
+    'scf_reproject_down': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_float, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p,
+                                     C.c_int, C.c_int, c_void_p]),
     'scf_resize_bilinear': (C.c_int, [c_void_p, c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
                                       C.c_int, c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_float, c_void_p]),
@@ -205,6 +207,8 @@ _SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)
+# ctypes mirrors in the order of scf_struct_size(which)
+STRUCT_MIRRORS = (ConvDesc, TcConvDesc, DecoderCfg, DecoderIO, EncoderOut, LossDesc, GruPassDesc)
 
 _lib = None
 _lock = threading.Lock()
@@ -241,7 +245,7 @@ def load():
             fn.argtypes = args
         if lib.scf_abi_version() != 1:
             raise ScfError('libscflow_sm100a.so ABI version mismatch')
-        for which, cls in enumerate((ConvDesc, TcConvDesc, DecoderCfg, DecoderIO, EncoderOut, LossDesc, GruPassDesc)):
+        for which, cls in enumerate(STRUCT_MIRRORS):
             if lib.scf_struct_size(which) != C.sizeof(cls):
                 raise ScfError(f'libscflow_sm100a.so was built with a different {cls.__name__} layout '
                                f'({lib.scf_struct_size(which)} bytes, binding {C.sizeof(cls)}): rebuild the library')

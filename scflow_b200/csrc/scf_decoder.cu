@@ -212,7 +212,7 @@ __global__ void identity_delta_kernel(float* d_rot, float* d_trs, int B, int rot
 
 // ------------------------------------------------------------------ workspace
 struct Workspace {
-  size_t corr_scratch, lvl[8], pts4, flow8, flowm, maskprev, corr, c1, cf, f1, h[2], cxt, motion, z, rh, hd, dflow,
+  size_t corr_scratch, lvl[8], pts4, flow8, flow8b, flowm, maskprev, corr, c1, cf, f1, h[2], cxt, motion, z, rh, hd, dflow,
       mask8, df1, df2, mf1, mf2, p1, p2, p3, fc0, fc1;
   // precision 1: split-bf16 planes [2][B*P][C] (byte offsets) and their plane strides in elements
   size_t s_corr, s_c1, s_cf, s_f1, s_h[2], s_cxt, s_motion, s_rh, s_hd, s_df1, s_mf1, s_df2, s_mf2, s_p1, s_p2;
@@ -240,7 +240,7 @@ static void build_workspace(const scf_decoder_cfg& cfg, int B, int H, int W, Wor
   const int k = 2 * cfg.radius + 1;
   w.corr_stride = (cfg.num_levels * k * k + 3) / 4 * 4;
   w.pts4 = take((size_t)B * H * W * 16);
-  w.flow8 = take(BP * 8); w.flowm = take(BP * 8); w.maskprev = take(BP * 4);
+  w.flow8 = take(BP * 8); w.flow8b = take(BP * 8); w.flowm = take(BP * 8); w.maskprev = take(BP * 4);
   w.corr = take(BP * w.corr_stride * 4);
   w.c1 = take(BP * 256 * 4); w.cf = take(BP * 256 * 4); w.f1 = take(BP * 128 * 4);
   w.h[0] = take(BP * 128 * 4); w.h[1] = take(BP * 128 * 4);
@@ -527,11 +527,16 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
     const float* trs_prev = it == 0 ? io->ref_translation : io->translation + (ob - Btot) * 3;
 
     // flow8 = 1/8 * down8(flow)                                          (scflow_decoder.py:196-197)
-    SCF_TRY(scf_resize_bilinear(flow_full, nullptr, 2 * HW, HW, W, 1, H, W, F(ws.flow8), (long long)P * 2, 1,
-                                (long long)W8 * 2, 2, H8, W8, B, 2, 1.0f / scale, st));
-    const float* menc_flow = F(ws.flow8);
+    // iteration 0 resamples the caller's init_flow; later iterations receive flow8 from the previous iteration's re-projection
+    // launch (two buffers: the side stream's x8 up-sampling of iteration `it` still reads flow8[it] while flow8[it+1] is written)
+    float* const flow8 = F((it & 1) ? ws.flow8b : ws.flow8);
+    float* const flow8_next = F((it & 1) ? ws.flow8 : ws.flow8b);
+    if (it == 0)
+      SCF_TRY(scf_resize_bilinear(flow_full, nullptr, 2 * HW, HW, W, 1, H, W, flow8, (long long)P * 2, 1,
+                                  (long long)W8 * 2, 2, H8, W8, B, 2, 1.0f / scale, st));
+    const float* menc_flow = flow8;
     if (cfg->mask_flow) {
-      mul_mask_kernel<<<cdiv(BP, 256), 256, 0, st>>>(F(ws.flow8), F(ws.maskprev), F(ws.flowm), (long long)BP);
+      mul_mask_kernel<<<cdiv(BP, 256), 256, 0, st>>>(flow8, F(ws.maskprev), F(ws.flowm), (long long)BP);
       SCF_TRY(check_launch("mul_mask_kernel"));
       menc_flow = F(ws.flowm);
     }
@@ -550,7 +555,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
         SCF_CUDA(cudaEventRecord(side_all->join_a, side_all->s));
         lst = st;
       }
-      SCF_TRY(scf_corr_lookup_split(levels, cfg->num_levels, cfg->radius, F(ws.flow8), cfg->mask_corr ? F(ws.maskprev) : nullptr,
+      SCF_TRY(scf_corr_lookup_split(levels, cfg->num_levels, cfg->radius, flow8, cfg->mask_corr ? F(ws.maskprev) : nullptr,
                                     S(ws.s_corr), (long long)BP * ws.corr_stride_s, ws.corr_stride_s, B, H8, W8, st));
       SCF_TRY(convtc(PC_CORR0, {{S(ws.s_corr), ws.corr_stride_s, 0, ws.corr_stride_s}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_c1), 256, 0));
       SCF_TRY(convtc(PC_CORR1, {{S(ws.s_c1), 256, 0, 256}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_cf), 256, 0));
@@ -613,7 +618,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       }
     } else {
       // lookup                                                              (:198-201)
-      SCF_TRY(scf_corr_lookup(levels, cfg->num_levels, cfg->radius, F(ws.flow8), cfg->mask_corr ? F(ws.maskprev) : nullptr,
+      SCF_TRY(scf_corr_lookup(levels, cfg->num_levels, cfg->radius, flow8, cfg->mask_corr ? F(ws.maskprev) : nullptr,
                               F(ws.corr), ws.corr_stride, 0, B, H8, W8, st));
       // motion encoder                                                      (raft_decoder.py:152-166)
       const int corr_ch = a.pc[PC_CORR0].cin;
@@ -654,7 +659,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       SCF_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
       up_st = side->s;
     }
-    SCF_TRY(scf_resize_bilinear(F(ws.flow8), F(ws.dflow), (long long)P * 2, 1, (long long)W8 * 2, 2, H8, W8, flow_pred_k, 2 * HW,
+    SCF_TRY(scf_resize_bilinear(flow8, F(ws.dflow), (long long)P * 2, 1, (long long)W8 * 2, 2, H8, W8, flow_pred_k, 2 * HW,
                                 HW, W, 1, H, W, B, 2, (float)scale, up_st));
     SCF_TRY(scf_resize_bilinear(F(ws.mask8), nullptr, P, 0, W8, 1, H8, W8, mask_k, HW, 0, W, 1, H, W, B, 1, 1.f, up_st));
     if (side) SCF_CUDA(cudaEventRecord(side->join, side->s));
@@ -698,7 +703,10 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
     }
     // pose update + pose-induced flow                                     (:230-243)
     SCF_TRY(scf_pose_update(drot_k, dtrs_k, rot_prev, trs_prev, rot_k, trs_k, B, st));
-    SCF_TRY(scf_reproject(F(ws.pts4), io->internel_k, rot_k, trs_k, io->invalid_flow_num, flow_pose_k, B, H, W, st));
+    if (it + 1 < iters)
+      SCF_TRY(scf_reproject_down(F(ws.pts4), io->internel_k, rot_k, trs_k, io->invalid_flow_num, flow_pose_k, B, H, W, flow8_next, H8, W8, st));
+    else
+      SCF_TRY(scf_reproject(F(ws.pts4), io->internel_k, rot_k, trs_k, io->invalid_flow_num, flow_pose_k, B, H, W, st));
     flow_full = flow_pose_k;
     if (side) SCF_CUDA(cudaStreamWaitEvent(st, side->join, 0));    // flow8 / dflow / mask8 are rewritten by the next iteration
     if (cfg->mask_corr || cfg->mask_flow)
@@ -710,13 +718,13 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
 
 int scf_decoder_launch_count(const scf_decoder_cfg* cfg, int iters) {
   if (check_cfg(cfg) != 0) return -1;
-  int per_iter = 1 /*down8*/ + 1 /*lookup*/ + 6 /*menc*/ - (cfg->precision == 1 ? 1 : 0) /*merged predict layers*/ + (cfg->precision == 1 ? (cfg->pose_head ? 2 : 1) : 0) /*x-folding of the flow maps*/ + 4 /*gru*/ + 3 /*heads*/ + 2 /*up8*/ + 2 /*pose upd + reproject*/;
+  int per_iter = 1 /*lookup*/ + 6 /*menc*/ - (cfg->precision == 1 ? 1 : 0) /*merged predict layers*/ + (cfg->precision == 1 ? (cfg->pose_head ? 2 : 1) : 0) /*x-folding of the flow maps*/ + 4 /*gru*/ + 3 /*heads*/ + 2 /*up8*/ + 2 /*pose upd + reproject*/;
   per_iter += cfg->pose_head ? 4 + 6 + 3 : 1;
   per_iter += cfg->mask_flow ? 1 : 0;
   int once = (cfg->precision == 1 ? 3 : 2) /*layout change of the feature maps + level 0*/ + (cfg->num_levels - 1) + 1 /*unproject*/ +
              2 /*h, cxt*/ + (cfg->precision == 1 ? 4 : 0) /*GRU context terms*/;
   if (cfg->mask_corr || cfg->mask_flow) once += 1;
-  return once + per_iter * iters;
+  return once + 1 /*down8 of init_flow*/ + per_iter * iters;
 }
 
 }  // extern "C"

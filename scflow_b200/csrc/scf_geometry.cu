@@ -49,34 +49,63 @@ __global__ void __launch_bounds__(256) unproject_kernel(const float* __restrict_
   }
 }
 
-// pose.py:79-87: u = K (R X + t) ; flow = (u_x/u_z - x, u_y/u_z - y) on depth>0, `invalid` elsewhere
+// pose.py:79-87 for one pixel: u = K (R X + t) ; flow = (u_x/u_z - x, u_y/u_z - y) on depth>0, `invalid` elsewhere
+__device__ __forceinline__ float2 pose_flow_at(const float4 p, const float* k, const float* r, const float* t, int x, int y, float invalid) {
+  float2 o = make_float2(invalid, invalid);
+  if (p.w > 0.f) {
+    const float vx = r[0] * p.x + r[1] * p.y + r[2] * p.z + t[0];
+    const float vy = r[3] * p.x + r[4] * p.y + r[5] * p.z + t[1];
+    const float vz = r[6] * p.x + r[7] * p.y + r[8] * p.z + t[2];
+    const float ux = k[0] * vx + k[1] * vy + k[2] * vz;
+    const float uy = k[3] * vx + k[4] * vy + k[5] * vz;
+    const float uz = k[6] * vx + k[7] * vy + k[8] * vz;
+    o.x = ux / uz - (float)x;
+    o.y = uy / uz - (float)y;
+  }
+  return o;
+}
+
+// Pose-induced flow at full resolution (NCHW) and, in the trailing blocks of the same launch, the next iteration's 1/8-resolution
+// flow  flow8 = 1/s * F.interpolate(flow, 1/s, bilinear, align_corners=True)  (scflow_decoder.py:196-197) as NHWC [B,H8,W8,2]:
+// each coarse pixel blends the flows of its four full-resolution taps, evaluated with the same function as the dense map
+// (same values as interpolating the stored map, without re-reading it and without a second launch).
 __global__ void __launch_bounds__(256) reproject_kernel(const float4* __restrict__ pts4, const float* __restrict__ K,
                                                         const float* __restrict__ rot, const float* __restrict__ trs,
-                                                        float invalid, float* __restrict__ flow, int H, int W) {
+                                                        float invalid, float* __restrict__ flow, int H, int W, int full_blocks,
+                                                        float* __restrict__ flow8, int H8, int W8, float ry, float rx, float scale8) {
   __shared__ float k[9], r[9], t[3];
   const int b = blockIdx.y;
   if (threadIdx.x < 9) { k[threadIdx.x] = K[b * 9 + threadIdx.x]; r[threadIdx.x] = rot[b * 9 + threadIdx.x]; }
   if (threadIdx.x < 3) t[threadIdx.x] = trs[b * 3 + threadIdx.x];
   __syncthreads();
   const int HW = H * W;
+  const float4* pb = pts4 + (long long)b * HW;
+  if ((int)blockIdx.x >= full_blocks) {
+    const int P8 = H8 * W8;
+    for (int q = ((int)blockIdx.x - full_blocks) * blockDim.x + threadIdx.x; q < P8; q += ((int)gridDim.x - full_blocks) * blockDim.x) {
+      const int yo = q / W8, xo = q - yo * W8;
+      const float sy = ry * (float)yo, sx = rx * (float)xo;
+      const int y0 = (int)sy, x0 = (int)sx;
+      const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+      const float ly1 = sy - (float)y0, ly0 = 1.f - ly1, lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+      const float2 v00 = pose_flow_at(__ldg(pb + y0 * W + x0), k, r, t, x0, y0, invalid);
+      const float2 v01 = pose_flow_at(__ldg(pb + y0 * W + x1), k, r, t, x1, y0, invalid);
+      const float2 v10 = pose_flow_at(__ldg(pb + y1 * W + x0), k, r, t, x0, y1, invalid);
+      const float2 v11 = pose_flow_at(__ldg(pb + y1 * W + x1), k, r, t, x1, y1, invalid);
+      float2 o;
+      o.x = scale8 * (ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x));
+      o.y = scale8 * (ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y));
+      reinterpret_cast<float2*>(flow8)[(long long)b * P8 + q] = o;
+    }
+    return;
+  }
   float* fx = flow + (long long)b * 2 * HW;
   float* fy = fx + HW;
-  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
-    const float4 p = __ldg(pts4 + (long long)b * HW + pix);
-    float ox = invalid, oy = invalid;
-    if (p.w > 0.f) {
-      const int y = pix / W, x = pix - y * W;
-      const float vx = r[0] * p.x + r[1] * p.y + r[2] * p.z + t[0];
-      const float vy = r[3] * p.x + r[4] * p.y + r[5] * p.z + t[1];
-      const float vz = r[6] * p.x + r[7] * p.y + r[8] * p.z + t[2];
-      const float ux = k[0] * vx + k[1] * vy + k[2] * vz;
-      const float uy = k[3] * vx + k[4] * vy + k[5] * vz;
-      const float uz = k[6] * vx + k[7] * vy + k[8] * vz;
-      ox = ux / uz - (float)x;
-      oy = uy / uz - (float)y;
-    }
-    fx[pix] = ox;
-    fy[pix] = oy;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += full_blocks * blockDim.x) {
+    const int y = pix / W, x = pix - y * W;
+    const float2 o = pose_flow_at(__ldg(pb + pix), k, r, t, x, y, invalid);
+    fx[pix] = o.x;
+    fy[pix] = o.y;
   }
 }
 
@@ -194,14 +223,32 @@ int scf_unproject(const float* depth, const float* K, const float* rot, const fl
   return scf::check_launch("unproject_kernel");
 }
 
-int scf_reproject(const float* pts4, const float* K, const float* rot, const float* trs, float invalid, float* flow,
-                  int B, int H, int W, void* stream) {
+static int reproject_launch(const float* pts4, const float* K, const float* rot, const float* trs, float invalid, float* flow,
+                            int B, int H, int W, float* flow8, int H8, int W8, void* stream) {
   SCF_REQUIRE(pts4 && K && rot && trs && flow && B > 0 && H > 0 && W > 0, SCF_ERR_ARG, "scf_reproject: bad args");
   SCF_REQUIRE(reinterpret_cast<uintptr_t>(pts4) % 16 == 0, SCF_ERR_ALIGN, "scf_reproject: pts4 must be 16B aligned");
-  dim3 grid(scf::cdiv(H * W, 256 * 4), B);
-  scf::reproject_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(pts4), K, rot, trs,
-                                                               invalid, flow, H, W);
+  SCF_REQUIRE(!flow8 || (H8 > 0 && W8 > 0 && H8 <= H && W8 <= W && reinterpret_cast<uintptr_t>(flow8) % 8 == 0), SCF_ERR_ARG,
+              "scf_reproject_down: bad coarse size / alignment");
+  const int full_blocks = scf::cdiv(H * W, 256 * 4), coarse_blocks = flow8 ? scf::cdiv(H8 * W8, 256) : 0;
+  dim3 grid(full_blocks + coarse_blocks, B);
+  // ATen area_pixel_compute_scale(align_corners=True): (in-1)/(out-1) in fp32, 0 when out == 1 (as scf_resize_bilinear)
+  const float ry = H8 > 1 ? (float)(H - 1) / (float)(H8 - 1) : 0.f, rx = W8 > 1 ? (float)(W - 1) / (float)(W8 - 1) : 0.f;
+  const float scale8 = flow8 ? 1.0f / (float)(H / H8) : 1.f;
+  scf::reproject_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(pts4), K, rot, trs, invalid, flow, H, W,
+                                                               full_blocks, flow8, H8, W8, ry, rx, scale8);
   return scf::check_launch("reproject_kernel");
+}
+
+int scf_reproject(const float* pts4, const float* K, const float* rot, const float* trs, float invalid, float* flow,
+                  int B, int H, int W, void* stream) {
+  return reproject_launch(pts4, K, rot, trs, invalid, flow, B, H, W, nullptr, 0, 0, stream);
+}
+
+int scf_reproject_down(const float* pts4, const float* K, const float* rot, const float* trs, float invalid, float* flow,
+                       int B, int H, int W, float* flow8, int H8, int W8, void* stream) {
+  SCF_REQUIRE(flow8 != nullptr && H8 > 0 && H % H8 == 0 && W8 > 0 && W / W8 == H / H8, SCF_ERR_ARG,
+              "scf_reproject_down: the coarse map must be the full one divided by one integer factor");
+  return reproject_launch(pts4, K, rot, trs, invalid, flow, B, H, W, flow8, H8, W8, stream);
 }
 
 int scf_pose_update(const float* d_rot, const float* d_trs, const float* rot_in, const float* trs_in, float* rot_out,

@@ -218,6 +218,19 @@ def reproject(pts4, k, rot, trs, invalid: float = 0.0):
     return flow
 
 
+def reproject_down(pts4, k, rot, trs, factor: int = 8, invalid: float = 0.0):
+    """``reproject`` plus, from the same launch, the next iteration's coarse flow (scflow_decoder.py:196-197):
+    ``1/factor * F.interpolate(flow, 1/factor, bilinear, align_corners=True)`` as NHWC [B, H/factor, W/factor, 2]."""
+    for n, t in (('pts4', pts4), ('k', k), ('rot', rot), ('trs', trs)):
+        _req(t, n)
+    b, h, w, _ = pts4.shape
+    flow = torch.empty(b, 2, h, w, device=pts4.device, dtype=torch.float32)
+    flow8 = torch.empty(b, h // factor, w // factor, 2, device=pts4.device, dtype=torch.float32)
+    check(_lib.load().scf_reproject_down(ptr(pts4), ptr(k), ptr(rot), ptr(trs), float(invalid), ptr(flow), b, h, w, ptr(flow8),
+                                         h // factor, w // factor, stream_ptr()), 'scf_reproject_down')
+    return flow, flow8
+
+
 def resize_bilinear_nchw(x: torch.Tensor, out_h: int, out_w: int, scale: float = 1.0, add: Optional[torch.Tensor] = None):
     """F.interpolate(mode='bilinear', align_corners=True) on NCHW, times ``scale``."""
     _req(x, 'x')

@@ -53,3 +53,27 @@ def test_gru_pass_fused_rejects_other_shapes():
     op.precompute(x)
     with pytest.raises(ScfError, match='32 x 32 map'):
         op(x, x)
+
+
+@pytest.mark.parametrize('size', [(256, 256), (480, 640)])
+def test_reproject_emits_the_next_coarse_flow(size):
+    """K3: the re-projection launch also writes flow8 = 1/8 * interpolate(flow, 1/8, bilinear, align_corners=True)
+    (scflow_decoder.py:196-197) - against torch on the dense flow the same launch wrote."""
+    import scflow_b200 as S
+    from oracle import scflow_oracle as O
+    h, w = size
+    scene = O.make_scene(31, 2, h, w)
+    c = {k: v.cuda() for k, v in scene.items()}
+    pts4 = S.ops.unproject(c['depth'], c['internel_k'], c['ref_rotation'], c['ref_translation'])
+    g = torch.Generator().manual_seed(3)
+    rot = (scene['ref_rotation'] + 0.01 * torch.randn(2, 3, 3, generator=g)).cuda()
+    trs = (scene['ref_translation'] + torch.randn(2, 3, generator=g)).cuda()
+    flow, flow8 = S.ops.reproject_down(pts4, c['internel_k'], rot, trs)
+    assert torch.equal(flow, S.ops.reproject(pts4, c['internel_k'], rot, trs))
+    want = F.interpolate(flow.cpu(), scale_factor=1 / 8, mode='bilinear', align_corners=True) / 8
+    got = flow8.permute(0, 3, 1, 2).cpu()
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) < 1e-5 * max(1.0, float(want.abs().max()))
+    # and it is what the separate resize kernel produced (same taps, same blend)
+    sep = S.ops.resize_bilinear_nchw(flow, h // 8, w // 8, scale=1 / 8)
+    assert float((got - sep.cpu()).abs().max()) < 2e-6 * max(1.0, float(want.abs().max()))
