@@ -737,8 +737,14 @@ int corr_build_f32(const float* feat_render, const float* feat_real, int B, int 
 // operands); level 0 = batched GEMM  f1[b] (P x C) * f2[b]^T (C x P) / sqrt(C)  on the tensor cores, written once as
 // fp32; levels 1.. are the reference's successive floor 2x2 means.
 // level 0 from pixel-major split-bf16 feature maps f1s (render) / f2s (real), both with hi->lo plane stride `plane`
+bool corr_pyramid_fused_ok(int C, int H8, int W8, int num_levels);
+int corr_pyramid_fused(const void* f1s, const void* f2s, long long plane, int B, int C, int H8, int W8, float* const* levels,
+                       cudaStream_t st);
+
 static int corr_gemm_and_pool(const void* f1s, const void* f2s, long long plane, int B, int C, int H8, int W8, int num_levels,
                               float* const* levels, cudaStream_t st) {
+  // 32-wide maps (256x256 crops): volume and pooled levels from one kernel (scf_corr_fused.cu); other sizes: GEMM + pools
+  if (corr_pyramid_fused_ok(C, H8, W8, num_levels)) return corr_pyramid_fused(f1s, f2s, plane, B, C, H8, W8, levels, st);
   const int P = H8 * W8;
   scf_tc_conv_desc d = {};
   d.seg[0].ptr = f1s; d.seg[0].plane_stride = plane; d.seg[0].stride = C; d.seg[0].coff = 0; d.seg[0].nch = C;

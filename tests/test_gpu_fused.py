@@ -77,3 +77,21 @@ def test_reproject_emits_the_next_coarse_flow(size):
     # and it is what the separate resize kernel produced (same taps, same blend)
     sep = S.ops.resize_bilinear_nchw(flow, h // 8, w // 8, scale=1 / 8)
     assert float((got - sep.cpu()).abs().max()) < 2e-6 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize('b,h8', [(2, 32), (5, 8), (1, 16)])
+def test_corr_pyramid_one_kernel_matches_build_plus_pools(b, h8, monkeypatch):
+    """K2: volume + pooled pyramid from one kernel vs (a) the fp32 oracle and (b) the GEMM + three floor-pool launches -
+    same accumulation order and the reference's summation order in the pools, so (b) must agree bit for bit."""
+    import scflow_b200 as S
+    from oracle import scflow_oracle as O
+    f = O.make_features(21, b, h8, 32, channels=256)
+    ref = O.correlation_pyramid(f['feat_render'], f['feat_real'], 4)
+    monkeypatch.setenv('SCFLOW_CORR_FUSED', '1')
+    fused = S.ops.corr_build(f['feat_render'].cuda(), f['feat_real'].cuda(), 4, precision=1)
+    monkeypatch.setenv('SCFLOW_CORR_FUSED', '0')
+    split = S.ops.corr_build(f['feat_render'].cuda(), f['feat_real'].cuda(), 4, precision=1)
+    for l, (r, a, c) in enumerate(zip(ref, fused, split)):
+        assert a.shape == r.shape == c.shape
+        assert float((a.cpu() - r).abs().max()) < 2e-4, f'level {l} vs oracle'
+        assert torch.equal(a, c), f'level {l}: fused and GEMM + pool forms differ (max {float((a - c).abs().max()):.2e})'
