@@ -25,9 +25,6 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = 'image-pairs/sec at 256x256, 8 GRU iters'
-# DRAM bytes of one GRU z|r launch (B=32) from the committed ncu --set full capture (profiles/r01i_summary.md): 85.6 MB read
-# + 10.2 MB written; the algorithmic minimum is 117 MB when nothing is L2-resident (inputs 83.9 MB, outputs 33.5 MB)
-ZR_TRAFFIC_BYTES = 95.8e6
 
 
 def parse():
@@ -41,7 +38,8 @@ def parse():
     ap.add_argument('--precision', type=int, default=int(os.environ.get('SCFLOW_PRECISION', '1')),
                     help='0 = fp32 CUDA-core convolutions, 1 = tcgen05 split-bf16 (fp32-accurate)')
     ap.add_argument('--no-graph', action='store_true', help='do not replay the decoder loop as a CUDA graph')
-    ap.add_argument('--cpu-sample', type=int, default=4, help='crop pairs in the CPU-baseline sample')
+    ap.add_argument('--cpu-sample', type=int, default=32, help='crop pairs per CPU step (config 2: 32; shrunk automatically to fit the time budget)')
+    ap.add_argument('--no-extras', action='store_true', help='skip the eager-GPU comparator and the config 1/3/4 lines')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--seed', type=int, default=0)
     return ap.parse_args()
@@ -102,40 +100,53 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------- reference arm
-def cpu_reference_time(batch: int, iters: int, steps: int, warmup: int, seed: int):
-    """The reference's CPU implementation of the path (oracle port of SCFlowRefiner.get_pose) on all host cores."""
+def cpu_reference_time(batch: int, iters: int, steps: int, warmup: int, seed: int, budget_s: float = 0.0):
+    """The reference's CPU implementation of the path (oracle port of SCFlowRefiner.get_pose, incl. the three encoder passes) on
+    all host cores.  With ``budget_s`` the per-step sample shrinks from ``batch`` crop pairs until warm-up + timed steps fit the
+    budget (judged from one probe step).  Returns (pairs/s, ms per step, threads, pairs per step)."""
     from oracle import scflow_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    scene = O.make_scene(seed, batch)
     sd = O.make_model_weights(seed)
 
-    def step():
-        with torch.no_grad():
-            O.get_pose(sd, scene['render_images'], scene['real_images'], scene['ref_rotation'], scene['ref_translation'],
-                       scene['depth'], scene['internel_k'], scene['label'], iters=iters)
+    def make_step(n):
+        scene = O.make_scene(seed, n)
 
-    for _ in range(warmup):
+        def step():
+            with torch.no_grad():
+                O.get_pose(sd, scene['render_images'], scene['real_images'], scene['ref_rotation'], scene['ref_translation'],
+                           scene['depth'], scene['internel_k'], scene['label'], iters=iters)
+        return step
+
+    step = make_step(batch)
+    t0 = time.perf_counter()
+    step()                                           # probe (also the first warm-up step)
+    probe = time.perf_counter() - t0
+    if budget_s > 0 and probe * (steps + warmup) > budget_s and batch > 1:
+        batch = max(1, int(batch * budget_s / (probe * (steps + warmup))))
+        step = make_step(batch)
+        step()
+    for _ in range(max(warmup - 1, 0)):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return batch / dt, dt * 1e3, torch.get_num_threads()
+    return batch / dt, dt * 1e3, torch.get_num_threads(), batch
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sample = args.cpu_sample
-    pairs_s, ms, threads = cpu_reference_time(sample, args.iters, args.steps, args.warmup, args.seed)
+    pairs_s, ms, threads, sample = cpu_reference_time(args.cpu_sample, args.iters, args.steps, args.warmup, args.seed, budget_s=200.)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': pairs_s, 'unit': 'pairs/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f'YCB-V-like 256x256 crop pairs, batch={args.batch}, {args.iters} iters, inference (BASELINE config 2)',
-                   'sample': f'{sample} pairs per step on the host CPU'},
+                   'sample': f'{sample} pairs per step on the host CPU' + (' (the full config-2 batch)' if sample == args.batch else
+                                                                             ' (reduced to keep the run within a few minutes)')},
         'cpu_baseline': {'value': pairs_s, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
                          'sample': f'{sample} crop pairs x {args.iters} iters per step, {args.steps} steps (oracle port of the '
                                    'reference get_pose; /root/reference is not present on the GPU box)'},
@@ -271,26 +282,37 @@ def run_ours(args):
         with torch.no_grad():
             model.extract_feat(resident['render_images'], resident['real_images'])
     nsub = max(3, min(args.steps, 10))
-    dec_only(); enc_only()
-    dec_ms = timed(dec_only, nsub) / nsub
-    enc_ms = timed(enc_only, nsub) / nsub
+
+    def warmed(fn):            # three untimed calls: lazy initialisation, allocator growth and the graph capture stay outside
+        for _ in range(3):
+            fn()
+        return timed(fn, nsub) / nsub
+    dec_ms = warmed(dec_only)
+    enc_ms = warmed(enc_only)
     model.decoder.iters = iters // 2
-    dec_only()
-    dec_half_ms = timed(dec_only, nsub) / nsub
+    dec_half_ms = warmed(dec_only)
     model.decoder.iters = iters
     per_iter_ms = (dec_ms - dec_half_ms) / (iters - iters // 2)
 
-    # ---- roofline of the dominant kernel: the GRU z|r convolution (N=256, K=5*384=1920; 2 launches / iteration)
+    # ---- roofline of the dominant kernel: the one-kernel SepConvGRU pass (2 launches / iteration, the largest single kernel)
     roof = dominant_kernel_roofline(S, args, b, dev, flush, peaks)
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del model
+        torch.cuda.empty_cache()
+        extras = extra_lines(S, O, args, dev, flush)
 
     line = None
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            pairs_s, cms, threads = cpu_reference_time(args.cpu_sample, iters, 2, 1, args.seed)
+            pairs_s, cms, threads, sample = cpu_reference_time(args.cpu_sample, iters, 2, 1, args.seed, budget_s=45.)
             cpu = {'value': pairs_s, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
-                   'sample': f'{args.cpu_sample} crop pairs x {iters} iters, 1 warm-up + 2 timed reps of the oracle port '
-                             f'(get_pose incl. encoders) on {threads} host threads'}
+                   'sample': f'{sample} crop pairs x {iters} iters (config-2 shape), 1 warm-up + 2 timed reps of the oracle port '
+                             f'(get_pose incl. the three encoder passes) on {threads} host threads', 'ms_per_step': cms}
+            if not args.no_extras:      # BASELINE config 1: one 256x256 pair, 4 iterations, the reference's own CPU-runnable case
+                p1, ms1, _, _ = cpu_reference_time(1, 4, 5, 2, args.seed)
+                cpu['config1'] = {'value': p1, 'unit': 'pairs/s', 'ms_per_step': ms1, 'sample': '1 pair x 4 iters, 2 warm-up + 5 timed reps'}
         line = {
             'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -309,6 +331,7 @@ def run_ours(args):
             'clocks': clocks.summary(),
             'roofline': roof,
             'cpu_baseline': cpu,
+            'extra': extras,
             'breakdown': {'note': 'module-by-module on the generic API path (NCHW feature maps between encoder and decoder, no '
                                   'encoder overlap); the step itself uses the fused path, so encoders + decoder > ms_per_step',
                           'encoders_ms': enc_ms, 'decoder_ms': dec_ms, 'per_iter_ms': per_iter_ms,
@@ -321,26 +344,49 @@ def run_ours(args):
     return line
 
 
+def kernel_traffic(name: str):
+    """DRAM bytes per launch of a kernel from the committed `ncu --set full` summary (profiles/r02_kernel_traffic.json: written by
+    tools/ncu_summary.py from the .ncu-rep of the command it names); None if absent."""
+    path = os.path.join(ROOT, 'profiles', 'r02_kernel_traffic.json')
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        t = json.load(f)
+    e = t.get(name)
+    return (e['dram_read_bytes'] + e['dram_write_bytes'], e.get('source')) if e else (None, None)
+
+
 def dominant_kernel_roofline(S, args, b, dev, flush, peaks):
-    """Times the GRU z|r convolution alone (CUDA events on its stream, L2 flushed between launches)."""
+    """Times the one-kernel SepConvGRU pass alone (CUDA events on its stream, L2 flushed between launches).  Algorithmic FLOPs per
+    launch = 2 * (B*1024 px) * 384 gate channels (z, r, q) * 1280 (5 taps x [h | motion] 256): the context columns are evaluated
+    once per forward, not per iteration."""
     from scflow_b200 import _lib
+    import ctypes as C
     g = torch.Generator().manual_seed(1)
     h = torch.tanh(torch.randn(b, 32, 32, 128, generator=g)).to(dev)
     cxt = torch.relu(torch.randn(b, 32, 32, 128, generator=g)).to(dev)
     mot = torch.randn(b, 32, 32, 128, generator=g).to(dev)
-    wz = (torch.randn(128, 384, 1, 5, generator=g) * 0.02).to(dev)
-    wr = (torch.randn(128, 384, 1, 5, generator=g) * 0.02).to(dev)
-    bias = torch.zeros(256, device=dev)
-    z, rh = torch.empty_like(h), torch.empty_like(h)
-    if args.precision == 0 or not hasattr(S.ops, 'conv2d_tc'):
-        packed = S.ops.pack_conv_weight([wz, wr])
+    if args.precision == 0:
+        return None
+    ws = [(torch.randn(128, 384, 1, 5, generator=g) * 0.02).to(dev) for _ in range(3)]
+    bs = [torch.zeros(128, device=dev) for _ in range(3)]
+    op = S.ops.GruPassFused(*ws, *bs)
+    op.precompute(cxt)
+    hs = S.ops.split_nchw(h.permute(0, 3, 1, 2).contiguous())
+    ms_ = S.ops.split_nchw(mot.permute(0, 3, 1, 2).contiguous())
+    out = torch.empty_like(h)
+    out_hl = torch.empty(2, b, 32, 32, 128, device=dev, dtype=torch.bfloat16)
+    d = _lib.GruPassDesc()
+    d.h_hl, d.h_plane, d.h_f32 = hs.data_ptr(), hs[0].numel(), h.data_ptr()
+    d.m_hl, d.m_plane = ms_.data_ptr(), ms_[0].numel()
+    d.w_zr, d.w_q = op.w_zr.data_ptr(), op.w_q.data_ptr()
+    d.pre_zr, d.pre_q = op.pre_zr.data_ptr(), op.pre_q.data_ptr()
+    d.out_f32, d.out_hl, d.out_plane = out.data_ptr(), out_hl.data_ptr(), out_hl[0].numel()
+    d.B, d.H, d.W, d.vertical = b, 32, 32, 0
+    lib = _lib.load()
 
-        def launch():
-            S.ops.conv2d_nhwc([(h, 0, 128), (cxt, 0, 128), (mot, 0, 128)], packed, bias, 256, (1, 5), 1, (0, 2), act='sigmoid',
-                              out=z, epi=_lib.EPI_GRU_ZR, aux0=h, out2=rh)
-        name, passes, kdim = 'conv_f32_kernel<4> (GRU z|r 1x5, fp32 CUDA cores)', 1, 1920
-    else:
-        launch, name, passes, kdim = S.ops.make_tc_gru_zr_bench(h, cxt, mot, wz, wr, bias, z, rh)
+    def launch():
+        _lib.check(lib.scf_gru_pass_fused(C.byref(d), _lib.stream_ptr()), 'scf_gru_pass_fused')
     for _ in range(3):
         launch()
     reps = 10
@@ -352,14 +398,82 @@ def dominant_kernel_roofline(S, args, b, dev, flush, peaks):
         e.record()
     torch.cuda.synchronize(dev)
     ms = sum(s.elapsed_time(e) for s, e in evs) / reps
-    flops = 2.0 * b * 1024 * 256 * kdim              # FLOPs this launch performs: 2*M*N*K (the context columns, 1/3 of the
-    #                                                  reference's K = 1920, are evaluated once per forward, not per iteration)
+    flops = 2.0 * b * 1024 * 384 * 1280
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks['bf16_burst']
-    return {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-            'traffic': ZR_TRAFFIC_BYTES if passes == 3 and b == 32 else None, 'traffic_source': 'ncu --set full, profiles/r01i_summary.md '
-            '(dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=32; bytes)', 'ms_per_launch': ms, 'algorithmic_flops_per_launch': flops, 'mma_passes': passes,
-            'peak_source': f"{peaks['source']} bf16 dense burst (kernel timed alone)"}
+    traffic, src = kernel_traffic('gru_pass_kernel') if b == 32 else (None, None)
+    return {'kernel': 'gru_pass_kernel<horizontal> (one SepConvGRU pass: z | r | q over [h | motion], 1x5 taps, tcgen05 split-bf16, M=128 N=256)',
+            'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
+            'traffic_source': src, 'ms_per_launch': ms, 'algorithmic_flops_per_launch': flops, 'mma_passes': 3,
+            'launches_per_step': 2 * args.iters,
+            'peak_source': f"{peaks['source']} bf16 dense burst (kernel timed alone); 3 MMAs per algorithmic MAC => ceiling 1/3"}
+
+
+def extra_lines(S, O, args, dev, flush):
+    """Comparators and the other BASELINE configurations, measured in the same run (rank 0, N=1):
+      * gpu_eager_reference: the reference's arithmetic (oracle port of get_pose: torch conv2d / grid_sample / matmul, i.e.
+        cuDNN / cuBLAS eager kernels) on THIS GPU at the config-2 shape, with TF32 off (fp32, the parity setting) and on (torch's
+        default for convolutions) - the existing-Blackwell number the hand-written path has to beat;
+      * config 3 (480x640, B=8, identity pose head), a config-4 shard (B=16 of 64 over 4 GPUs, 12 iterations) and config 1
+        (B=1, 4 iterations) through scflow_b200."""
+    from tests.util import scflow_model_cfg
+    out = {}
+
+    def timed(fn, reps=5, warm=3):
+        for _ in range(warm):
+            fn()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for s, e in evs:
+            flush.zero_()
+            s.record()
+            fn()
+            e.record()
+        torch.cuda.synchronize(dev)
+        return sum(s.elapsed_time(e) for s, e in evs) / reps
+
+    # ---- eager PyTorch on the GPU
+    b, iters = args.batch, args.iters
+    sd = {k: v.to(dev) for k, v in O.make_model_weights(args.seed).items()}
+    scene = {k: v.to(dev) for k, v in O.make_scene(args.seed, b).items()}
+
+    def eager():
+        with torch.no_grad():
+            O.get_pose(sd, scene['render_images'], scene['real_images'], scene['ref_rotation'], scene['ref_translation'],
+                       scene['depth'], scene['internel_k'], scene['label'], iters=iters)
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, conv_tf32, mm_tf32 in (('fp32', False, False), ('tf32', True, True)):
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = conv_tf32, mm_tf32
+            ms = timed(eager, reps=3, warm=2)
+            out[f'gpu_eager_reference_{name}'] = {'ms_per_step': ms, 'value': b / (ms * 1e-3), 'unit': 'pairs/s',
+                                                  'what': f'oracle port of get_pose under torch eager on the GPU (cuDNN / cuBLAS), B={b}, '
+                                                          f'{iters} iters, cudnn.allow_tf32={conv_tf32}, matmul.allow_tf32={mm_tf32}'}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    del sd, scene
+    torch.cuda.empty_cache()
+
+    # ---- the other configurations through scflow_b200
+    def ours(bb, hh, ww, it, identity):
+        model = S.build_refiner(scflow_model_cfg(iters=it, precision=args.precision, use_cuda_graph=not args.no_graph))
+        model.load_state_dict(O.make_model_weights(args.seed), strict=False)
+        model = model.to(dev).eval()
+        model.decoder.identity_pose_head = identity
+        sc = {k: v.to(dev) for k, v in O.make_scene(args.seed, bb, hh, ww).items()}
+
+        def step():
+            with torch.no_grad():
+                model.get_pose(sc['render_images'], sc['real_images'], sc['ref_rotation'], sc['ref_translation'], sc['depth'],
+                               sc['internel_k'], sc['label'])
+        ms = timed(step)
+        return {'ms_per_step': ms, 'value': bb / (ms * 1e-3), 'unit': 'pairs/s'}
+    out['config1_b1_it4'] = dict(ours(1, 256, 256, 4, False), what='BASELINE config 1 shape: one 256x256 pair, 4 iterations')
+    out['config3_480x640_b8_it8'] = dict(ours(8, 480, 640, 8, True),
+                                         what='BASELINE config 3: 480x640 full frames, B=8, 8 iterations, identity pose head (the stock '
+                                              'head cannot run off 256x256, as in the reference)')
+    out['config4_shard_b16_it12'] = dict(ours(16, 256, 256, 12, False),
+                                         what='one GPU\'s shard of BASELINE config 4: B=64 over 4 GPUs = 16 crops, 12 iterations incl. pose head')
+    return out
 
 
 def main():

@@ -118,10 +118,11 @@ def corr_lookup(pyramid: Sequence[Tensor], flow: Tensor, radius: int = 4) -> Ten
     """The reference's own formulation (grid_sample); output [B, L*(2r+1)^2, H, W] fp32."""
     b, _, h, w = flow.shape
     k = 2 * radius + 1
-    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing='ij')
+    dev = flow.device                                                       # (CPU in the tests; bench.py's eager-GPU comparator passes CUDA tensors)
+    ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing='ij')
     base = torch.stack([xs, ys], dim=0).float()[None] + flow               # corr_lookup.py:113-115
     base = base.permute(0, 2, 3, 1).reshape(b * h * w, 1, 1, 2)
-    d = torch.linspace(-radius, radius, k)
+    d = torch.linspace(-radius, radius, k, device=dev)
     first, second = torch.meshgrid(d, d, indexing='ij')
     delta = torch.stack([first, second], dim=-1).view(1, k, k, 2)          # x-major: corr_lookup.py:118-123
     outs = []
@@ -213,7 +214,8 @@ def unproject_dense(depth: Tensor, k: Tensor, rot: Tensor, trs: Tensor) -> Tenso
     X_cam = K^-1 (x d, y d, d)^T ; X_obj = R^-1 (X_cam - t) with torch.inverse as in the reference.
     """
     b, h, w = depth.shape
-    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing='ij')
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=depth.device),
+                            torch.arange(w, dtype=torch.float32, device=depth.device), indexing='ij')
     homo = torch.stack([xs, ys, torch.ones_like(xs)], dim=0)[None] * depth[:, None]     # [B,3,H,W]
     cam = torch.bmm(torch.inverse(k), homo.reshape(b, 3, -1))
     obj = torch.bmm(torch.inverse(rot), cam - trs[:, :, None])
@@ -225,7 +227,8 @@ def reproject_dense(points_obj: Tensor, depth: Tensor, k: Tensor, rot: Tensor, t
     """Dense form of pose.py:66-88: flow = proj(K(R X + t)) - pixel at depth>0, ``invalid`` elsewhere."""
     b, _, h, w = points_obj.shape
     u = torch.bmm(k, torch.bmm(rot, points_obj.reshape(b, 3, -1)) + trs[:, :, None]).reshape(b, 3, h, w)
-    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing='ij')
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=depth.device),
+                            torch.arange(w, dtype=torch.float32, device=depth.device), indexing='ij')
     fx = u[:, 0] / u[:, 2] - xs
     fy = u[:, 1] / u[:, 2] - ys
     fg = depth > 0
@@ -268,8 +271,8 @@ def decoder_forward(sd: SD, feat_render: Tensor, feat_real: Tensor, h_feat: Tens
         mf = _conv(sd, 'mask_encoder.0.conv', mask, 1, act='relu')                 # :217
         mf = _conv(sd, 'mask_encoder.1.conv', mf, 1, act='relu')
         if identity_pose_head:
-            d_rot = torch.tensor([1., 0., 0., 0., 1., 0.]).repeat(b, 1)
-            d_trs = torch.zeros(b, 3)
+            d_rot = torch.tensor([1., 0., 0., 0., 1., 0.], device=depth.device).repeat(b, 1)
+            d_trs = torch.zeros(b, 3, device=depth.device)
         else:
             d_rot, d_trs = pose_head(sd, torch.cat([h_feat, df, mf], dim=1), label, num_class)   # :218-219
         flow_pred = scale * resize_bilinear_ac(flow8 + d_flow, hh, ww)             # :222-224
@@ -329,7 +332,7 @@ def get_pose(sd_model: SD, render_images: Tensor, real_images: Tensor, ref_rotat
     c = raft_encoder(ctx, render_images, 'BN')
     h_feat, cxt = torch.tanh(c[:, :128]), torch.relu(c[:, 128:])
     n, _, hh, ww = real_images.shape
-    init_flow = torch.zeros(n, 2, hh, ww)
+    init_flow = torch.zeros(n, 2, hh, ww, device=render_images.device)
     return decoder_forward(dec, feat_render, feat_real, h_feat, cxt, ref_rotation, ref_translation, depth,
                            internel_k, label, init_flow, 0., iters=iters, identity_pose_head=identity_pose_head)
 
