@@ -56,7 +56,7 @@ extern "C" {
 int scf_abi_version(void);
 /* sizeof() of a descriptor struct as this library was compiled, so that a binding can verify its mirror of the layout:
  * 0 scf_conv_desc, 1 scf_tc_conv_desc, 2 scf_decoder_cfg, 3 scf_decoder_io, 4 scf_encoder_out, 5 scf_loss_desc,
- * 6 scf_gru_pass_desc, 7 scf_lookup_conv_desc; -1 otherwise */
+ * 6 scf_gru_pass_desc; -1 otherwise */
 int scf_struct_size(int which);
 const char* scf_last_error(void);
 /* 1 if the tcgen05/TMA code paths are usable on the current device (compute capability 10.x), else 0 */
@@ -397,6 +397,16 @@ typedef struct scf_loss_desc {
 } scf_loss_desc;
 size_t scf_refiner_loss_scratch_bytes(int iters, int B);
 int scf_refiner_loss(const scf_loss_desc* d, void* stream);
+
+/* ---------------------------------------------------------------- training: optimizer step -------------- */
+/* Global-norm gradient clipping + AdamW over flat fp32 buffers of n elements (n % 4 == 0, 16B aligned): what mmcv's
+ * OptimizerHook(grad_clip=dict(max_norm=10.)) + torch.optim.AdamW do per step (configs/refine_models/scflow.py:117-125).
+ * grads are first multiplied by grad_scale (1 / world size after an all-reduce SUM); the norm of the scaled gradient and the clip
+ * coefficient are written to stats2[0..1]; max_norm <= 0 disables clipping.  scratch: >= min(4*SMs, n/1024) floats.
+ * step = 1 for the first update (bias correction). */
+int scf_clip_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, float max_norm, float grad_scale, float* scratch,
+                   int scratch_floats, float* stats2, void* stream);
 
 #ifdef __cplusplus
 }

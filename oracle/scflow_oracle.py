@@ -199,12 +199,15 @@ def ortho6d_to_matrix(o6: Tensor) -> Tensor:
     return torch.stack([x, y, z], dim=2)
 
 
-def update_pose(d_rot: Tensor, d_trs: Tensor, rot: Tensor, trs: Tensor, weight: float = 10.) -> Tuple[Tensor, Tensor]:
-    """pose.py:124-149 with depth_transform='exp': R' = dR R; tz' = tz/exp(dz); txy' = tz'(dxy/10 + txy/tz)."""
+def update_pose(d_rot: Tensor, d_trs: Tensor, rot: Tensor, trs: Tensor, weight: float = 10.,
+                detach_depth_for_xy: bool = False) -> Tuple[Tensor, Tensor]:
+    """pose.py:124-149 with depth_transform='exp': R' = dR R; tz' = tz/exp(dz); txy' = tz'(dxy/10 + txy/tz).
+    ``detach_depth_for_xy`` (pose.py:143-145; True in the shipped config) changes gradients only."""
     r_new = torch.bmm(ortho6d_to_matrix(d_rot), rot)
     tz = trs[:, 2] / torch.exp(d_trs[:, 2])
-    tx = tz * (d_trs[:, 0] / weight + trs[:, 0] / trs[:, 2])
-    ty = tz * (d_trs[:, 1] / weight + trs[:, 1] / trs[:, 2])
+    tzx = tz.detach() if detach_depth_for_xy else tz
+    tx = tzx * (d_trs[:, 0] / weight + trs[:, 0] / trs[:, 2])
+    ty = tzx * (d_trs[:, 1] / weight + trs[:, 1] / trs[:, 2])
     return r_new, torch.stack([tx, ty, tz], dim=-1)
 
 
@@ -248,7 +251,7 @@ def decoder_forward(sd: SD, feat_render: Tensor, feat_real: Tensor, h_feat: Tens
                     ref_rotation: Tensor, ref_translation: Tensor, depth: Tensor, internel_k: Tensor,
                     label: Tensor, init_flow: Tensor, invalid_flow_num: float = 0., iters: int = 8,
                     num_levels: int = 4, radius: int = 4, num_class: int = 21, identity_pose_head: bool = False,
-                    trace: dict = None):
+                    trace: dict = None, detach: bool = False):
     """Returns the reference's 7 lists. ``identity_pose_head`` = config-3 mode (stock head cannot run at
     480x640): delta pose is the zero-init head's output (identity) in oracle and candidate."""
     scale = 2 ** (num_levels - 1)
@@ -260,6 +263,8 @@ def decoder_forward(sd: SD, feat_render: Tensor, feat_real: Tensor, h_feat: Tens
     flow = init_flow
     outs = ([], [], [], [], [], [], [])
     for it in range(iters):
+        if detach:        # detach_flow / detach_pose / detach_depth_for_xy = True in the shipped config (scflow.py:57-60; scflow_decoder.py:192-195, 232-233):
+            flow, rot, trs = flow.detach(), rot.detach(), trs.detach()            # changes gradients only, never forward values
         flow8 = (1.0 / scale) * resize_bilinear_ac(flow, h8, w8)                  # :196-197
         corr = corr_lookup(pyramid, flow8, radius)                                 # :198
         motion = motion_encoder(sd, corr, flow8)                                   # :206
@@ -277,7 +282,7 @@ def decoder_forward(sd: SD, feat_render: Tensor, feat_real: Tensor, h_feat: Tens
             d_rot, d_trs = pose_head(sd, torch.cat([h_feat, df, mf], dim=1), label, num_class)   # :218-219
         flow_pred = scale * resize_bilinear_ac(flow8 + d_flow, hh, ww)             # :222-224
         mask_up = resize_bilinear_ac(mask, hh, ww)                                 # :226-227
-        rot, trs = update_pose(d_rot, d_trs, rot, trs)                             # :230-236
+        rot, trs = update_pose(d_rot, d_trs, rot, trs, detach_depth_for_xy=detach)  # :230-236
         flow = reproject_dense(pts, depth, internel_k, rot, trs, invalid_flow_num)  # :239-243
         if trace is not None:
             trace.setdefault('flow8', []).append(flow8)

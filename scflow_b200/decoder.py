@@ -460,8 +460,10 @@ class SCFlowDecoder(BaseModule):
         translation_preds, mask_preds, delta_rotation_preds, delta_translation_preds), each a list of ``iters`` tensors."""
         if torch.is_grad_enabled() and (feat_render.requires_grad or any(p.requires_grad for p in self.parameters())):
             if feat_render.requires_grad or self.training:
-                raise NotImplementedError('scflow_b200.SCFlowDecoder: backward is not implemented yet; call under '
-                                          'torch.no_grad() / model.eval() (inference path)')
+                # training: the differentiable graph (native forward for the gradient-free kernels, torch-composed backward)
+                from . import training
+                return training.decoder_forward_train(self, feat_render, feat_real, h_feat, cxt_feat, ref_rotation, ref_translation,
+                                                      depth, internel_k, label, init_flow, invalid_flow_num)
         ins = dict(feat_render=feat_render, feat_real=feat_real, h_feat=h_feat, cxt_feat=cxt_feat, ref_rotation=ref_rotation,
                    ref_translation=ref_translation, depth=depth, internel_k=internel_k, init_flow=init_flow)
         for k, t in ins.items():

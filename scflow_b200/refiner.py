@@ -261,9 +261,12 @@ class SCFlowRefiner(BaseModule):
         from . import formatting
         return formatting.format_data_test(data_batch, self.renderer)
 
-    def train_step(self, data_batch, optimizer, **kwargs):
-        raise NotImplementedError('training needs the backward pass of the refinement loop, which is not built yet (the forward '
-                                  'value of the loss is available as SCFlowRefiner.loss under torch.no_grad()); see DESIGN.md')
+    def train_step(self, data_batch, optimizer=None, **kwargs):
+        """base_refiner.py:325-336: the loss WITH its autograd graph plus the logging dict; backward / all-reduce / optimizer
+        are the caller's (mmcv's OptimizerHook in the reference; ``scflow_b200.training.Trainer`` here)."""
+        loss, log_imgs, log_vars, _, _ = self.loss(data_batch)
+        n = len(data_batch['img_metas']) if 'img_metas' in data_batch else int(data_batch['labels'].shape[0])
+        return dict(loss=loss, log_vars=log_vars, log_imgs=log_imgs, num_samples=n)
 
     def loss_functions(self):
         """(pose, flow, mask) SequenceLoss modules built from the reference's config keys (scflow_refiner.py:61-63)."""
@@ -275,37 +278,56 @@ class SCFlowRefiner(BaseModule):
         return self._loss_funcs
 
     def loss(self, data: Dict):
-        """Forward value of the training loss (scflow_refiner.py:184-258) for a collated training batch (formatted through
-        ``format_data_train_sup`` when a renderer is plugged in) or an already formatted one: keys ``gt_rotations,
-        gt_translations, ref_rotations, ref_translations, real_images, rendered_images, rendered_depths, rendered_masks,
-        gt_masks, internel_k, labels`` (what ``format_data_train_sup`` produces; the renderer is not part of this package).
-        Returns ``(loss, log_vars, seq_rotations, seq_translations)``.  FORWARD ONLY: the value carries no autograd graph
-        (the backward pass of the loop is not built yet), so it must be called under ``torch.no_grad()``."""
-        if torch.is_grad_enabled():
-            raise NotImplementedError('SCFlowRefiner.loss computes the forward value only (no backward yet): call it under torch.no_grad()')
+        """scflow_refiner.py:184-258 for a collated training batch (formatted through ``format_data_train_sup`` when a renderer is
+        plugged in) or an already formatted one: keys ``gt_rotations, gt_translations, ref_rotations, ref_translations,
+        real_images, rendered_images, rendered_depths, rendered_masks, gt_masks, internel_k, labels``.
+
+        * under ``torch.no_grad()``: forward value only, three fused kernels (``scf_refiner_loss``); returns
+          ``(loss, log_vars, seq_rotations, seq_translations)``;
+        * with autograd enabled (training): the differentiable graph (``scflow_b200/training.py``); returns the reference's
+          ``(loss, log_imgs, log_vars, seq_rotations, seq_translations)`` (``log_imgs`` is empty: visualisation is outside this
+          package)."""
         from . import loss as L
         from . import ops
         if 'rendered_images' not in data:         # a collated training batch: format it first (scflow_refiner.py:186)
             data = self.format_data_train_sup(data)
         pose_f, flow_f, mask_f = self.loss_functions()
+        train = torch.is_grad_enabled()
         outs = self.get_pose(data['rendered_images'], data['real_images'], data['ref_rotations'], data['ref_translations'],
-                             data['rendered_depths'], data['internel_k'], data['labels'])
+                             data['rendered_depths'], data['internel_k'], data['labels'], pose_head_label=data.get('pose_head_label'))
         flow_from_pose, flow_from_pred, seq_rot, seq_trs, seq_masks = outs[0], outs[1], outs[2], outs[3], outs[4]
-        depth = data['rendered_depths'].float().contiguous()
-        k = data['internel_k'].float().contiguous()
-        # GT flow (models/utils/pose.py:92-121): lift with the reference pose, project with the ground-truth pose
-        pts4 = ops.unproject(depth, k, data['ref_rotations'].float().contiguous(), data['ref_translations'].float().contiguous())
-        gt_flow = ops.reproject(pts4, k, data['gt_rotations'].float().contiguous(), data['gt_translations'].float().contiguous(),
-                                float(self.max_flow))
-        if self.filter_invalid_flow:
-            gt_flow = L.filter_flow_by_mask(gt_flow, data['gt_masks'].float().contiguous(), float(self.max_flow))
-        out, iters = L.refiner_loss(flow_from_pred, seq_masks, seq_rot, seq_trs, gt_flow, data['rendered_masks'], data['gt_rotations'],
-                                    data['gt_translations'], data['labels'], pose_f, flow_f, mask_f)
-        vals = out.tolist()            # one device->host read for the whole log (the reference does 3*iters + 4 .item() calls)
+        with torch.no_grad():
+            depth = data['rendered_depths'].float().contiguous()
+            k = data['internel_k'].float().contiguous()
+            # GT flow (models/utils/pose.py:92-121): lift with the reference pose, project with the ground-truth pose
+            pts4 = ops.unproject(depth, k, data['ref_rotations'].float().contiguous(), data['ref_translations'].float().contiguous())
+            gt_flow = ops.reproject(pts4, k, data['gt_rotations'].float().contiguous(), data['gt_translations'].float().contiguous(),
+                                    float(self.max_flow))
+            if self.filter_invalid_flow:
+                gt_flow = L.filter_flow_by_mask(gt_flow, data['gt_masks'].float().contiguous(), float(self.max_flow))
+        if train:
+            from . import training
+            loss, terms = training.refiner_loss_train(outs, gt_flow, data['rendered_masks'].float(), data['gt_rotations'].float(),
+                                                      data['gt_translations'].float(), data['labels'], pose_f, flow_f, mask_f,
+                                                      float(self.max_flow))
+            iters = len(flow_from_pred)
+            vals = torch.cat([terms['loss'].reshape(1), terms['loss_pose'].reshape(1), terms['loss_flow'].reshape(1),
+                              terms['loss_mask'].reshape(1), terms['seq_pose'], terms['seq_flow'], terms['seq_mask']]).tolist()
+        else:
+            out, iters = L.refiner_loss(flow_from_pred, seq_masks, seq_rot, seq_trs, gt_flow, data['rendered_masks'], data['gt_rotations'],
+                                        data['gt_translations'], data['labels'], pose_f, flow_f, mask_f)
+            loss = out[0]
+            vals = out.tolist()        # one device->host read for the whole log (the reference does 3*iters + 4 .item() calls)
         log_vars = {}
+        for name in ('add', 'rot', 'trans'):
+            if f'init_{name}_error_mean' in data and name == 'add':
+                log_vars['init_add_mean'] = float(data['init_add_error_mean'])
+                log_vars['init_add_std'] = float(data['init_add_error_std'])
         for i in range(iters):
             log_vars[f'seq_{i}_pose_loss'] = vals[4 + i]
             log_vars[f'seq_{i}_flow_loss'] = vals[4 + iters + i]
             log_vars[f'seq_{i}_mask_loss'] = vals[4 + 2 * iters + i]
         log_vars.update(loss_mask=vals[3], loss_flow=vals[2], loss_pose=vals[1], loss=vals[0])
-        return out[0], log_vars, seq_rot, seq_trs
+        if train:
+            return loss, {}, log_vars, seq_rot, seq_trs
+        return loss, log_vars, seq_rot, seq_trs

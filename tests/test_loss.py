@@ -138,8 +138,8 @@ def test_gpu_refiner_loss_method_end_to_end():
                 real_images=sc['real_images'], rendered_images=sc['render_images'], rendered_depths=sc['depth'],
                 rendered_masks=c['rendered_mask'], gt_masks=c['gt_mask'], internel_k=sc['internel_k'], labels=sc['label'])
     data = {k: v.cuda() for k, v in data.items()}
-    with pytest.raises(NotImplementedError):
-        model.loss(data)                                   # needs no_grad: forward value only
+    with pytest.raises(RuntimeError, match='autograd is enabled'):
+        model.loss(data)                                   # eval() + autograd: refused (train() gives the differentiable graph)
     with torch.no_grad():
         loss, log_vars, seq_rot, seq_trs = model.loss(data)
         outs = O.get_pose(sd, sc['render_images'], sc['real_images'], sc['ref_rotation'], sc['ref_translation'], sc['depth'],
