@@ -42,6 +42,8 @@ def parse():
     ap.add_argument('--no-extras', action='store_true', help='skip the eager-GPU comparator and the config 1/3/4 lines')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
+                    help="'train': BASELINE config 5 - one optimisation step (forward + loss + backward + gradient all-reduce + clip + AdamW)")
     return ap.parse_args()
 
 
@@ -476,10 +478,110 @@ def extra_lines(S, O, args, dev, flush):
     return out
 
 
+def run_train(args):
+    """BASELINE config 5: YCB-V-like training step, 32 crops per GPU (256 at 8 GPUs), 8 iterations.  One step = forward (native
+    kernels for the gradient-free parts, torch ops elsewhere) + loss + backward + bucketed NCCL all-reduce of the 32.7 MB gradient
+    (overlapped with backward) + fused global-norm clip + AdamW.  Weak scaling; the collective is the all-reduce."""
+    import scflow_b200 as S
+    from scflow_b200 import _lib, dist as D
+    from scflow_b200.training import Trainer
+    from oracle import scflow_oracle as O
+    from oracle import loss_oracle as L           # synthetic training-batch generator only
+    from tests.util import scflow_model_cfg
+
+    rank, world, local_rank = D.init_from_env()
+    assert torch.cuda.is_available(), 'bench.py --mode train needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    b, iters = args.batch, args.iters
+    c = L.make_loss_case(args.seed + 1000 * rank, b, iters)
+    sym = {f'cls_{k + 1}': 1 for k, s_ in enumerate(c['symmetric']) if s_}
+    cfg = scflow_model_cfg(iters=iters, precision=1)
+    cfg.update(pose_loss_cfg=dict(type='SequenceLoss', gamma=0.8, loss_func_cfg=dict(
+                   type='DisentanglePointMatchingLoss', symmetry_types=sym, mesh_diameter=c['diameters'], loss_type='l1',
+                   disentangle_z=True, loss_weight=10.)),
+               flow_loss_cfg=dict(type='SequenceLoss', gamma=0.8, loss_func_cfg=dict(type='RAFTLoss', loss_weight=.1, max_flow=400.)),
+               mask_loss_cfg=dict(type='SequenceLoss', gamma=0.8, loss_func_cfg=dict(type='L1Loss', loss_weight=10.)))
+    model = S.build_refiner(cfg)
+    model.load_state_dict(O.make_model_weights(args.seed), strict=False)
+    model = model.to(dev).train()
+    model.loss_functions()[0].loss_func.set_meshes(c['meshes'])
+    sc = c['scene']
+    host = dict(gt_rotations=c['gt_rot'], gt_translations=c['gt_trs'], ref_rotations=sc['ref_rotation'], ref_translations=sc['ref_translation'],
+                real_images=sc['real_images'], rendered_images=sc['render_images'], rendered_depths=sc['depth'],
+                rendered_masks=c['rendered_mask'], gt_masks=c['gt_mask'], internel_k=sc['internel_k'], labels=sc['label'])
+    host = {k: v.contiguous().pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    trainer = Trainer(model, lr=4e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_norm=10.)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lib = _lib.load()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize(dev)
+
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(data):
+        out = trainer.train_step(data)
+        return out['loss']
+
+    c0 = lib.scf_launch_counter()
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    torch.cuda.synchronize(dev)
+    launches = (lib.scf_launch_counter() - c0) / max(args.warmup, 3)
+
+    def timed(e2e):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for s_, e_ in evs:
+            flush.zero_()
+            s_.record()
+            data = {k: v.to(dev, non_blocking=True) for k, v in host.items()} if e2e else resident
+            loss = step(data)
+            if e2e:
+                loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            e_.record()
+        barrier()
+        return sum(s_.elapsed_time(e_) for s_, e_ in evs) / args.steps
+    with ClockSampler(local_rank) as clocks:
+        ms = D.max_over_ranks(timed(False), dev)
+    e2e_ms = D.max_over_ranks(timed(True), dev)
+    grad_norm = trainer.grad_norm()
+    if rank == 0:
+        nparam = sum(p.numel() for p in trainer.params)
+        line = {
+            'metric': 'training crop-pairs/sec at 256x256, 8 GRU iters (forward + loss + backward + gradient all-reduce + clip + AdamW)',
+            'value': world * b / (ms * 1e-3), 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (native kernels: split-bf16 tcgen05 / fp32; torch backward with the framework defaults, cuDNN TF32 allowed as in '
+                     'the reference\'s training run)',
+            'data': 'synthetic',
+            'config': {'workload': f'YCB-V-like training step (BASELINE config 5): batch={b} per GPU ({b * world} global), {iters} iters, '
+                                   'AdamW lr 4e-4 wd 1e-4, grad clip 10', 'l2': 'L2 flushed (256 MB write) before every timed step',
+                       'parallelism': f'data parallel x{world}: bucketed NCCL all-reduce (SUM) of {nparam * 4 / 1e6:.1f} MB of gradients, '
+                                      'overlapped with backward', 'mode': 'train'},
+            'e2e': {'value': world * b / (e2e_ms * 1e-3), 'unit': 'pairs/s', 'ms_per_step': e2e_ms,
+                    'h2d_bytes_per_step': sum(v.numel() * v.element_size() for v in host.values()), 'd2h_bytes_per_step': 4},
+            'gpu_launches': int(launches * args.steps),
+            'clocks': clocks.summary(),
+            'train': {'parameters': nparam, 'grad_norm_last': grad_norm, 'buckets': len(trainer.buckets)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.mode == 'train':
+        run_train(args)
     else:
         run_ours(args)
 
