@@ -199,6 +199,15 @@ int scf_corr_lookup(const float* const* h_levels, int num_levels, int radius, co
 /* same gather, written as split-bf16 planes (channels beyond num_levels*(2r+1)^2 up to out_stride are zeroed) */
 int scf_corr_lookup_split(const float* const* h_levels, int num_levels, int radius, const float* flow8, const float* mask,
                           void* out_hl, long long plane_stride, int out_stride, int B, int H8, int W8, void* stream);
+/* Lookup fused with the motion encoder's first convolution (corr_lookup.py:102-136 + raft_decoder.py:152-155):
+ *   out[q, :] = relu(W[256 x 324] * lookup(levels, flow8)[q, :] + bias)   as split-bf16 NHWC [2][B*H8*W8][out_stride]
+ * in ONE kernel (4 levels, radius 4; B*H8*W8 % 128 == 0): the gathered 324-vector goes straight to shared memory as the tcgen05
+ * A operand and never reaches HBM.  packed_w: scf_lookup_conv_pack() of the OIHW [256, 324, 1, 1] weight (bf16 [2][256][4*96],
+ * every level's 81 channels padded to 96).  Neighbour indices are those of scf_corr_lookup (bit-exact). */
+size_t scf_lookup_conv_packed_bytes(void);
+int scf_lookup_conv_pack(const float* w_oihw, void* packed, void* stream);
+int scf_lookup_conv(const float* const* h_levels, const float* flow8, const float* mask, const void* packed_w, const float* bias,
+                    void* out_hl, long long out_plane_stride, int out_stride, int B, int H8, int W8, void* stream);
 /* debug/parity hook: integer neighbour indices of the lookup, bit-exact against the oracle.
  * x0,y0: int32 [B,H8,W8,2r+1] per level `level` (x0 indexed by a, y0 by b). */
 int scf_corr_lookup_taps(int level, int radius, const float* flow8, int32_t* x0, int32_t* y0, int B, int H8, int W8,

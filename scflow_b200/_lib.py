@@ -190,6 +190,10 @@ _SIGNATURES = {
     'scf_refiner_loss_scratch_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'scf_refiner_loss': (C.c_int, [C.POINTER(LossDesc), c_void_p]),
     'scf_gru_pass_fused': (C.c_int, [C.POINTER(GruPassDesc), c_void_p]),
+    'scf_lookup_conv_packed_bytes': (C.c_size_t, []),
+    'scf_lookup_conv_pack': (C.c_int, [c_void_p, c_void_p, c_void_p]),
+    'scf_lookup_conv': (C.c_int, [C.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, c_void_p]),
     'scf_clip_adamw': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_int, C.c_float, C.c_float, c_void_p, C.c_int, c_void_p, c_void_p]),
     'scf_encoder_packed_bytes': (C.c_size_t, []),

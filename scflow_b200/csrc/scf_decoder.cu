@@ -23,6 +23,10 @@ int pack_conv_weight_tc_foldx(const float* w_oihw, float* scratch, void* packed,
 int corr_build_dispatch(const float* feat_render, const float* feat_real, int B, int C, int H8, int W8, int num_levels,
                         float* const* levels, void* scratch, int precision, cudaStream_t st);
 int gru_pass_fused(const scf_gru_pass_desc& d, cudaStream_t st);
+bool lookup_conv_ok(int num_levels, int radius, int B, int H8, int W8);
+bool lookup_conv_requested();
+int lookup_conv_fused(const float* const* levels, const float* flow8, const float* mask, const void* w_lk, const float* bias,
+                      void* out_hl, long long out_plane, int out_stride, int B, int H8, int W8, cudaStream_t st);
 int corr_build_presplit(void* scratch, int B, int C, int H8, int W8, int num_levels, float* const* levels, cudaStream_t st);
 
 thread_local char g_err[512] = {0};
@@ -92,6 +96,7 @@ struct Arena {
   size_t gn_w[3], gn_b[3];
   size_t fc0_w, fc0_b, fc1_w, fc1_b, rot_w, rot_b, tr_w, tr_b;
   size_t fold_scratch;        // floats: staging of a folded thin-input weight while packing
+  size_t lk_off;              // bytes: corr_net[0] repacked per pyramid level for the fused lookup + convolution (0 = none)
   size_t total_floats;
   size_t total_bytes;         // fp32 section + tensor-core section
   int nc, rot_rows, tr_rows;
@@ -174,6 +179,11 @@ static void build_arena(const scf_decoder_cfg& cfg, Arena& a) {
       p.tc_off = boff;
       boff += ((size_t)2 * p.tc_kh * p.tc_kw * p.cout_pad * p.cin_pad * 2 + 1023) / 1024 * 1024;
     }
+  }
+  a.lk_off = 0;
+  if (cfg.precision == 1 && cfg.num_levels == 4 && cfg.radius == 4) {
+    a.lk_off = boff;
+    boff += (scf_lookup_conv_packed_bytes() + 1023) / 1024 * 1024;
   }
   a.total_bytes = boff;
 }
@@ -362,6 +372,7 @@ int scf_decoder_pack(const scf_decoder_cfg* cfg, const float* const* h_weights, 
       o_off += p.src_cout[s];
     }
   }
+  if (a.lk_off) SCF_TRY(scf_lookup_conv_pack(h_weights[SCF_W_CORR0_W], reinterpret_cast<char*>(packed) + a.lk_off, st));
   if (cfg->pose_head) {
     const int gw[3] = {SCF_W_PH_G0_W, SCF_W_PH_G1_W, SCF_W_PH_G2_W}, gb[3] = {SCF_W_PH_G0_B, SCF_W_PH_G1_B, SCF_W_PH_G2_B};
     for (int i = 0; i < 3; ++i) {
@@ -555,9 +566,15 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
         SCF_CUDA(cudaEventRecord(side_all->join_a, side_all->s));
         lst = st;
       }
-      SCF_TRY(scf_corr_lookup_split(levels, cfg->num_levels, cfg->radius, flow8, cfg->mask_corr ? F(ws.maskprev) : nullptr,
-                                    S(ws.s_corr), (long long)BP * ws.corr_stride_s, ws.corr_stride_s, B, H8, W8, st));
-      SCF_TRY(convtc(PC_CORR0, {{S(ws.s_corr), ws.corr_stride_s, 0, ws.corr_stride_s}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_c1), 256, 0));
+      if (a.lk_off && lookup_conv_requested() && lookup_conv_ok(cfg->num_levels, cfg->radius, B, H8, W8)) {
+        // pyramid lookup + corr_net[0] (1x1, 324 -> 256, ReLU) in one kernel: the 324-channel tensor never reaches HBM
+        SCF_TRY(lookup_conv_fused(levels, flow8, cfg->mask_corr ? F(ws.maskprev) : nullptr, reinterpret_cast<const char*>(packed) + a.lk_off,
+                                  pw + a.pc[PC_CORR0].b_off, S(ws.s_c1), (long long)BP * 256, 256, B, H8, W8, st));
+      } else {
+        SCF_TRY(scf_corr_lookup_split(levels, cfg->num_levels, cfg->radius, flow8, cfg->mask_corr ? F(ws.maskprev) : nullptr,
+                                      S(ws.s_corr), (long long)BP * ws.corr_stride_s, ws.corr_stride_s, B, H8, W8, st));
+        SCF_TRY(convtc(PC_CORR0, {{S(ws.s_corr), ws.corr_stride_s, 0, ws.corr_stride_s}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_c1), 256, 0));
+      }
       SCF_TRY(convtc(PC_CORR1, {{S(ws.s_c1), 256, 0, 256}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_cf), 256, 0));
       if (ovl & 2) SCF_CUDA(cudaStreamWaitEvent(st, side_all->join_a, 0));
       // motion features = [conv output (126) | flow (2)] (raft_decoder.py MotionEncoder: cat([out, flow])); the flow channels

@@ -365,6 +365,23 @@ def make_tc_gru_zr_bench(h, cxt, mot, wz, wr, bias, z, rh):
     return launch, f'conv_tc_kernel (GRU z|r 1x5, tcgen05 split-bf16, N=256, K={k}; context term hoisted out of the loop)', 3, k
 
 
+def lookup_conv(levels: Sequence[torch.Tensor], flow8_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """CorrLookup + corr_net[0] in one kernel (scf_lookup_conv): ``weight`` OIHW [256, 324, 1, 1]; returns the split-bf16
+    activation [2, B, H8, W8, 256] (hi, lo planes) of relu(conv1x1(lookup))."""
+    _req(flow8_nhwc, 'flow8')
+    _req(weight, 'weight')
+    b, h8, w8, _ = flow8_nhwc.shape
+    lib = _lib.load()
+    packed = torch.empty(lib.scf_lookup_conv_packed_bytes(), device=weight.device, dtype=torch.uint8)
+    check(lib.scf_lookup_conv_pack(ptr(weight), ptr(packed), stream_ptr()), 'scf_lookup_conv_pack')
+    out = torch.empty(2, b, h8, w8, 256, device=weight.device, dtype=torch.bfloat16)
+    arr = (C.c_void_p * len(levels))(*[_req(t, 'level').data_ptr() for t in levels])
+    check(lib.scf_lookup_conv(arr, ptr(flow8_nhwc), ptr(mask), ptr(packed), ptr(bias), ptr(out), out[0].numel(), 256, b, h8, w8, stream_ptr()),
+          'scf_lookup_conv')
+    return out
+
+
 class GruPassFused:
     """One SepConvGRU pass as ONE kernel (scf_gru_pass_fused; raft_decoder.py:245-253).  Built from the reference's weights
     ``conv_z/r/q.{pass}.conv.weight`` [128,384,kh,kw] and biases; the context columns' contribution (loop invariant) is

@@ -95,3 +95,31 @@ def test_corr_pyramid_one_kernel_matches_build_plus_pools(b, h8, monkeypatch):
         assert a.shape == r.shape == c.shape
         assert float((a.cpu() - r).abs().max()) < 2e-4, f'level {l} vs oracle'
         assert torch.equal(a, c), f'level {l}: fused and GEMM + pool forms differ (max {float((a - c).abs().max()):.2e})'
+
+
+@pytest.mark.parametrize('b,mag', [(1, 3.0), (3, 12.0), (37, 40.0)])
+def test_lookup_fused_with_first_motion_encoder_conv(b, mag):
+    """N1: lookup + corr_net[0] (1x1, 324 -> 256, bias, ReLU) in one kernel vs (a) the oracle's lookup + fp64 matmul and (b) the
+    stand-alone lookup kernel (whose neighbour indices are tested bit-exact) followed by the same matmul."""
+    import scflow_b200 as S
+    from oracle import scflow_oracle as O
+    f = O.make_features(41, b, 32, 32)
+    pyr = O.correlation_pyramid(f['feat_render'], f['feat_real'], 4)
+    g = torch.Generator().manual_seed(7)
+    flow = mag * torch.randn(b, 2, 32, 32, generator=g)
+    flow[0, :, :2, :] = torch.round(flow[0, :, :2, :])            # integral centres: the round-trip floor cases
+    flow[-1, :, -1, :] = 0.
+    w = torch.randn(256, 324, 1, 1, generator=g) * 0.05
+    bias = torch.randn(256, generator=g) * 0.1
+    corr = O.corr_lookup(pyr, flow, 4)                                                  # [b, 324, 32, 32]
+    ref = torch.relu(torch.einsum('oc,bchw->bohw', w[:, :, 0, 0].double(), corr.double()) + bias.double().view(1, -1, 1, 1)).float()
+    flow8 = flow.permute(0, 2, 3, 1).contiguous().cuda()
+    levels = [p.cuda() for p in pyr]
+    out = S.ops.lookup_conv(levels, flow8, w.cuda(), bias.cuda())
+    got = S.ops.unsplit(out).cpu()
+    err = float((got - ref).abs().max())
+    print(f'lookup + conv1x1 fused, B={b}: max |err| {err:.2e} (|ref| max {float(ref.abs().max()):.2f})')
+    assert err < 2e-4
+    own = S.ops.corr_lookup_nhwc(levels, flow8, 4)[..., :324].permute(0, 3, 1, 2).cpu()
+    ref2 = torch.relu(torch.einsum('oc,bchw->bohw', w[:, :, 0, 0].double(), own.double()) + bias.double().view(1, -1, 1, 1)).float()
+    assert float((got - ref2).abs().max()) < 1e-4
