@@ -25,6 +25,9 @@ int corr_build_dispatch(const float* feat_render, const float* feat_real, int B,
 int gru_pass_fused(const scf_gru_pass_desc& d, cudaStream_t st);
 bool lookup_conv_ok(int num_levels, int radius, int B, int H8, int W8);
 bool lookup_conv_requested();
+int pack_predict_tc(const float* wf_oihw, const float* wm_oihw, void* packed, int hidden, int cout_pad, cudaStream_t st);
+int predict_gather(const float* d, int ld, const float* bf, const float* bm, float* dflow, float* mask8, int B, int H, int W,
+                   cudaStream_t st);
 int lookup_conv_fused(const float* const* levels, const float* flow8, const float* mask, const void* w_lk, const float* bias,
                       void* out_hl, long long out_plane, int out_stride, int B, int H8, int W8, cudaStream_t st);
 int corr_build_presplit(void* scratch, int B, int C, int H8, int W8, int num_levels, float* const* levels, cudaStream_t st);
@@ -96,6 +99,7 @@ struct Arena {
   size_t gn_w[3], gn_b[3];
   size_t fc0_w, fc0_b, fc1_w, fc1_b, rot_w, rot_b, tr_w, tr_b;
   size_t fold_scratch;        // floats: staging of a folded thin-input weight while packing
+  size_t pd_off;              // bytes: the two predict layers as one 1x1 convolution 512 -> 19 (tap-wise partial products), bf16 [2][32][512]
   size_t lk_off;              // bytes: corr_net[0] repacked per pyramid level for the fused lookup + convolution (0 = none)
   size_t total_floats;
   size_t total_bytes;         // fp32 section + tensor-core section
@@ -180,6 +184,11 @@ static void build_arena(const scf_decoder_cfg& cfg, Arena& a) {
       boff += ((size_t)2 * p.tc_kh * p.tc_kw * p.cout_pad * p.cin_pad * 2 + 1023) / 1024 * 1024;
     }
   }
+  a.pd_off = 0;
+  if (cfg.precision == 1) {
+    a.pd_off = boff;
+    boff += ((size_t)2 * 32 * 512 * 2 + 1023) / 1024 * 1024;
+  }
   a.lk_off = 0;
   if (cfg.precision == 1 && cfg.num_levels == 4 && cfg.radius == 4) {
     a.lk_off = boff;
@@ -223,7 +232,7 @@ __global__ void identity_delta_kernel(float* d_rot, float* d_trs, int B, int rot
 // ------------------------------------------------------------------ workspace
 struct Workspace {
   size_t corr_scratch, lvl[8], pts4, flow8, flow8b, flowm, maskprev, corr, c1, cf, f1, h[2], cxt, motion, z, rh, hd, dflow,
-      mask8, df1, df2, mf1, mf2, p1, p2, p3, fc0, fc1;
+      mask8, pd, df1, df2, mf1, mf2, p1, p2, p3, fc0, fc1;
   // precision 1: split-bf16 planes [2][B*P][C] (byte offsets) and their plane strides in elements
   size_t s_corr, s_c1, s_cf, s_f1, s_h[2], s_cxt, s_motion, s_rh, s_hd, s_df1, s_mf1, s_df2, s_mf2, s_p1, s_p2;
   size_t s_t7;                  // x-folded 2-channel flow map [2][B*P][16] feeding the 7x1 tensor-core form of the 7x7 flow encoders
@@ -256,7 +265,7 @@ static void build_workspace(const scf_decoder_cfg& cfg, int B, int H, int W, Wor
   w.h[0] = take(BP * 128 * 4); w.h[1] = take(BP * 128 * 4);
   w.cxt = take(BP * 128 * 4); w.motion = take(BP * 128 * 4);
   w.z = take(BP * 128 * 4); w.rh = take(BP * 128 * 4);
-  w.hd = take(BP * 512 * 4); w.dflow = take(BP * 8); w.mask8 = take(BP * 4);
+  w.hd = take(BP * 512 * 4); w.dflow = take(BP * 8); w.mask8 = take(BP * 4); w.pd = take(BP * 32 * 4);
   w.df1 = take(BP * 128 * 4); w.df2 = take(BP * 64 * 4); w.mf1 = take(BP * 64 * 4); w.mf2 = take(BP * 32 * 4);
   w.p1 = take(BP / 4 * 128 * 4 + 1024); w.p2 = take(BP / 16 * 128 * 4 + 1024); w.p3 = take(BP / 64 * 128 * 4 + 1024);
   w.fc0 = take((size_t)B * 1024 * 4); w.fc1 = take((size_t)B * 256 * 4);
@@ -372,6 +381,7 @@ int scf_decoder_pack(const scf_decoder_cfg* cfg, const float* const* h_weights, 
       o_off += p.src_cout[s];
     }
   }
+  if (a.pd_off) SCF_TRY(pack_predict_tc(h_weights[SCF_W_FHP_W], h_weights[SCF_W_MHP_W], reinterpret_cast<char*>(packed) + a.pd_off, 256, 32, st));
   if (a.lk_off) SCF_TRY(scf_lookup_conv_pack(h_weights[SCF_W_CORR0_W], reinterpret_cast<char*>(packed) + a.lk_off, st));
   if (cfg->pose_head) {
     const int gw[3] = {SCF_W_PH_G0_W, SCF_W_PH_G1_W, SCF_W_PH_G2_W}, gb[3] = {SCF_W_PH_G0_B, SCF_W_PH_G1_B, SCF_W_PH_G2_B};
@@ -608,9 +618,20 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       SCF_TRY(convtc(PC_HEADS, {{S(ws.s_h[0]), 128, 0, 128}}, SCF_ACT_RELU, nullptr, 0, S(ws.s_hd), 512, 0));
       // both predict layers (3x3 256->2, 1x1 256->1 + sigmoid) in one streaming fp32 kernel over the split hidden map
       static const bool predict_tc = [] { const char* e = getenv("SCFLOW_PREDICT_TC"); return e ? atoi(e) != 0 : false; }();
+      static const bool predict_pd = [] { const char* e = getenv("SCFLOW_PREDICT_PD"); return e ? atoi(e) != 0 : true; }();
       if (predict_tc) {   // the two predict layers as tensor-core convolutions (N padded to 16; halo mode for the 3x3)
         SCF_TRY(convtc(PC_FHP, {{S(ws.s_hd), 512, 0, 256}}, SCF_ACT_NONE, F(ws.dflow), 2, nullptr, 0, 0));
         SCF_TRY(convtc(PC_MHP, {{S(ws.s_hd), 512, 256, 256}}, SCF_ACT_SIGMOID, F(ws.mask8), 1, nullptr, 0, 0));
+      } else if (predict_pd && a.pd_off) {
+        // both predict layers: one 1x1 tensor-core convolution 512 -> 19 tap-wise partial products + a 9-tap gather (scf_predict.cu)
+        scf_tc_conv_desc d = {};
+        d.seg[0].ptr = S(ws.s_hd); d.seg[0].plane_stride = (long long)BP * 512; d.seg[0].stride = 512; d.seg[0].coff = 0; d.seg[0].nch = 512;
+        d.nseg = 1; d.B = B; d.H = H8; d.W = W8; d.kh = d.kw = 1; d.stride = 1;
+        d.w = reinterpret_cast<const char*>(packed) + a.pd_off; d.cin_pad = 512; d.cout_pad = 32; d.cout = 32;
+        d.scale = 1.f; d.epi = SCF_EPI_ACT; d.act = SCF_ACT_NONE;
+        d.out_f32 = F(ws.pd); d.out_f32_stride = 32; d.out_f32_coff = 0;
+        SCF_TRY(conv2d_tc(d, lst));
+        SCF_TRY(predict_gather(F(ws.pd), 32, pw + a.pc[PC_FHP].b_off, pw + a.pc[PC_MHP].b_off, F(ws.dflow), F(ws.mask8), B, H8, W8, st));
       } else
       SCF_TRY(heads_predict(S(ws.s_hd), (long long)BP * 512, 512, 256, pw + a.pc[PC_FHP].w_off, a.pc[PC_FHP].ldw, pw + a.pc[PC_FHP].b_off,
                             pw + a.pc[PC_MHP].w_off, a.pc[PC_MHP].ldw, pw + a.pc[PC_MHP].b_off, F(ws.dflow), F(ws.mask8), B, H8, W8, st));

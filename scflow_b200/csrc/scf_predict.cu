@@ -162,4 +162,59 @@ int heads_predict(const void* hd_hl, long long plane, int stride, int hidden, co
   return check_launch("heads_predict_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Predict layers, re-associated so that the 512-channel hidden map is read ONCE, without a halo, by the tensor cores:
+//   d[p][2 t + o] = <W_flow[o, :, tap t], hidden_flow[p, :]>  (t = 0..8, o = 0..1),   d[p][18] = <w_mask, hidden_mask[p, :]>
+// is a 1x1 convolution 512 -> 19 (scf_conv2d_tc, weights packed by pack_predict_tc below); the 3x3 convolution is then the sum
+// of its nine taps' partial products at the neighbouring pixels (zero outside the map = the convolution's zero padding):
+//   dflow[p][o] = b_o + sum_t d[p + offset_t][2 t + o] ;  mask[p] = sigmoid(d[p][18] + b_m).
+__global__ void pack_predict_tc_kernel(const float* __restrict__ wf, const float* __restrict__ wm, __nv_bfloat16* __restrict__ packed,
+                                       int hidden, int cout_pad) {
+  // packed: [2 planes][cout_pad rows][2 * hidden]
+  const int total = cout_pad * 2 * hidden;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c = idx % (2 * hidden), o = idx / (2 * hidden);
+    float v = 0.f;
+    if (o < 18 && c < hidden) v = wf[(((o & 1) * hidden) + c) * 9 + (o >> 1)];       // OIHW [2, hidden, 3, 3], tap = ky*3 + kx
+    else if (o == 18 && c >= hidden) v = wm[c - hidden];                              // [1, hidden, 1, 1]
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    packed[idx] = hi;
+    packed[(long long)total + idx] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(256) predict_gather_kernel(const float* __restrict__ d, int ld, const float* __restrict__ bf,
+                                                             const float* __restrict__ bm, float* __restrict__ dflow,
+                                                             float* __restrict__ mask8, int H, int W, long long npix) {
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(pix % W), y = (int)((pix / W) % H);
+    float a0 = __ldg(bf), a1 = __ldg(bf + 1);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(d + (pix + (long long)(t / 3 - 1) * W + (t % 3 - 1)) * ld + 2 * t));
+        a0 += v.x; a1 += v.y;
+      }
+    }
+    reinterpret_cast<float2*>(dflow)[pix] = make_float2(a0, a1);
+    mask8[pix] = 1.f / (1.f + expf(-(__ldg(d + pix * ld + 18) + __ldg(bm))));
+  }
+}
+
+int pack_predict_tc(const float* wf_oihw, const float* wm_oihw, void* packed, int hidden, int cout_pad, cudaStream_t st) {
+  SCF_REQUIRE(wf_oihw && wm_oihw && packed && hidden > 0 && cout_pad >= 19, SCF_ERR_ARG, "pack_predict_tc: bad args");
+  pack_predict_tc_kernel<<<64, 256, 0, st>>>(wf_oihw, wm_oihw, reinterpret_cast<__nv_bfloat16*>(packed), hidden, cout_pad);
+  return check_launch("pack_predict_tc_kernel");
+}
+
+int predict_gather(const float* d, int ld, const float* bf, const float* bm, float* dflow, float* mask8, int B, int H, int W,
+                   cudaStream_t st) {
+  SCF_REQUIRE(d && bf && bm && dflow && mask8 && ld >= 19 && ld % 2 == 0, SCF_ERR_ARG, "predict_gather: bad args");
+  const long long npix = (long long)B * H * W;
+  predict_gather_kernel<<<cdiv(npix, 256), 256, 0, st>>>(d, ld, bf, bm, dflow, mask8, H, W, npix);
+  return check_launch("predict_gather_kernel");
+}
+
 }  // namespace scf
