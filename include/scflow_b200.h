@@ -144,6 +144,10 @@ typedef struct scf_tc_conv_desc {
   int out_pad_writable;               /* non-zero: the outputs' padding channels [cout, round_up(cout, 8)) may be overwritten
                                        * (with act(0)); lets layers with cout % 8 != 0 leave through TMA stores, which clip
                                        * the channel axis at 16 B granularity */
+  int ksplit; long long split_stride; /* ksplit > 1: split-K over the kernel taps for layers with few pixel tiles - split k contracts
+                                       * taps [k*taps/ksplit, ...) and writes its PARTIAL sums to out_f32 + k*split_stride elements;
+                                       * the caller adds the ksplit maps.  Plain linear layers only (no bias / activation / other
+                                       * outputs), taps % ksplit == 0 */
 } scf_tc_conv_desc;
 /* upper bound, in 128-pixel-tile units, of the pixel tiles scf_conv2d_tc may use for this output geometry whichever tiling it
  * chooses (size of the `stats` buffer = tiles*4*2*cout floats, zero-initialised), and the 128-pixel tiles per sample (0 if a

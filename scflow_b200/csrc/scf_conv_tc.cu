@@ -70,6 +70,10 @@ struct TcParams {
   __nv_bfloat16* out2_hl; long long out2_hl_plane; int out2_hl_stride;
   const float* pre; int pre_stride;   // GRU epilogues: fp32 map added before the gate non-linearity
   float* stats;                       // EPI_ACT: [m_tiles][4 warps][2][cout] partial sums / sums of squares of the output
+  // tap split (split-K over the kernel taps, for layers with fewer pixel tiles than SMs): tile t = (split ks, N tile, pixel tile);
+  // split ks contracts taps [ks * taps_per_split, ...) only and writes its PARTIAL sums (no bias, no activation) to
+  // out_f32 + ks * split_stride; the consumer adds the partial maps (scf_pose_head.cu: group norm)
+  int ksplit, taps_per_split; long long split_stride;
 };
 
 // ---- compact epilogue helpers (the whole epilogue loop body must stay well inside the instruction cache: a first
@@ -310,6 +314,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (threadIdx.x == 0) stamp(0);
 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int tiles_per_split = p.num_tiles / p.ksplit;      // pixel tiles x N tiles
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0);
@@ -355,10 +360,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint32_t phase = 0, hpa = 0;
       const int w_rows = p.BN / p.cluster;
       for (int t = tile0; t < p.num_tiles; t += tile_step) {
-        const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
+        const int ks = t / tiles_per_split, t2 = t - ks * tiles_per_split;
+        const int nt = t2 / p.m_tiles, mt = t2 - nt * p.m_tiles;
         const int b = (mt / tiles_per_img) * p.TB, tr = mt % tiles_per_img;
         const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
         const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * p.BN;
+        const int tap_lo = ks * p.taps_per_split, tap_hi = tap_lo + p.taps_per_split < p.num_taps ? tap_lo + p.taps_per_split : p.num_taps;
         if (p.halo) {
           // one halo tile per channel chunk, then one weight tile per tap (own ring)
           for (int s = 0; s < p.nseg; ++s) {
@@ -388,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           continue;
         }
-        for (int tap = 0; tap < p.num_taps; ++tap) {
+        for (int tap = tap_lo; tap < tap_hi; ++tap) {
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
           const int cx = x0 * p.sx + kx - p.pw, cy = y0 * p.sy + ky - p.ph;
           for (int s = 0; s < p.nseg; ++s) {
@@ -517,7 +524,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         int c = 0;
         bool ninit0 = true, ninit1 = true;
-        for (int tap = 0; tap < p.num_taps; ++tap) {
+        const int mks = t / tiles_per_split;
+        const int mtap_lo = mks * p.taps_per_split, mtap_hi = mtap_lo + p.taps_per_split < p.num_taps ? mtap_lo + p.taps_per_split : p.num_taps;
+        for (int tap = mtap_lo; tap < mtap_hi; ++tap) {
           for (int sg = 0; sg < p.nseg; ++sg) {
             for (int cc = 0; cc < p.seg_chunks[sg]; ++cc, ++c) {
               const int ks = (cc == p.seg_chunks[sg] - 1) ? p.seg_last_ks[sg] : p.bk / 16;   // skip all-zero k-steps of a ragged chunk
@@ -608,7 +617,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int it = 0;
     for (int t = tile0; t < p.num_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
-      const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
+      const int ks = t / tiles_per_split, t2 = t - ks * tiles_per_split;
+      const int nt = t2 / p.m_tiles, mt = t2 - nt * p.m_tiles;
+      float* const out_f32_t = p.out_f32 ? p.out_f32 + (long long)ks * p.split_stride : nullptr;      // this split's partial map
       const int b = (mt / tiles_per_img) * p.TB, tr = mt % tiles_per_img;
       const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
       const int y = ty * p.TH + h, x = tx * p.TW + w, n0 = nt * p.BN;
@@ -726,12 +737,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           } else if (EPI == SCF_EPI_GRU_ZR) {
             if (p.direct_st) {
               if (valid) {
-                if (nb < half) row_store_f32x32(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v);
+                if (nb < half) row_store_f32x32(out_f32_t + pix * p.out_f32_stride + p.out_f32_coff + nb, v);
                 else row_store_split32(p.out2_hl + pix * p.out2_hl_stride + (nb - half), p.out2_hl_plane, v);
               }
             } else if (nb < half) {            // z gate -> fp32 (read back by the q convolution's epilogue)
-              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, rp, v);
-              stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, rp, v + 16);
+              stage_store_f32(sbuf, lane, out_f32_t + p.out_f32_coff + nb, p.out_f32_stride, rp, v);
+              stage_store_f32(sbuf, lane, out_f32_t + p.out_f32_coff + nb + 16, p.out_f32_stride, rp, v + 16);
             } else {
               stage_store_split32(sbuf, lane, p.out2_hl + (nb - half), p.out2_hl_plane, p.out2_hl_stride, rp, v);
             }
@@ -747,7 +758,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     d[i] = make_uint4(__float_as_uint(v[hh * 16 + 4 * i]), __float_as_uint(v[hh * 16 + 4 * i + 1]),
                                       __float_as_uint(v[hh * 16 + 4 * i + 2]), __float_as_uint(v[hh * 16 + 4 * i + 3]));
                   float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
-                  stage_store64_stats(sbuf, lane, reinterpret_cast<char*>(p.out_f32 + p.out_f32_coff + nb + hh * 16),
+                  stage_store64_stats(sbuf, lane, reinterpret_cast<char*>(out_f32_t + p.out_f32_coff + nb + hh * 16),
                                       (long long)p.out_f32_stride * 4, rp, d, s4, q4);
 #pragma unroll
                   for (int off = 4; off < 32; off <<= 1) {
@@ -764,10 +775,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                   }
                 }
               } else if (p.direct_st) {
-                if (valid) row_store_f32x32(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v);
+                if (valid) row_store_f32x32(out_f32_t + pix * p.out_f32_stride + p.out_f32_coff + nb, v);
               } else {
-                stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb, p.out_f32_stride, rp, v);
-                stage_store_f32(sbuf, lane, p.out_f32 + p.out_f32_coff + nb + 16, p.out_f32_stride, rp, v + 16);
+                stage_store_f32(sbuf, lane, out_f32_t + p.out_f32_coff + nb, p.out_f32_stride, rp, v);
+                stage_store_f32(sbuf, lane, out_f32_t + p.out_f32_coff + nb + 16, p.out_f32_stride, rp, v + 16);
               }
             }
             if (p.out_hl) {
@@ -820,7 +831,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = act_ct<ACT>(v[i]);
-          if (p.out_f32) store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, nvalid);
+          if (p.out_f32) store_f32x16(out_f32_t + pix * p.out_f32_stride + p.out_f32_coff + nb, v, nvalid);
           if (p.out_hl) store_split16(p.out_hl + pix * p.out_hl_stride + p.out_hl_coff + nb, p.out_hl_plane, v, nvalid);
         } else if (EPI == SCF_EPI_GRU_ZR) {    // cout = 2*Ch, Ch % 16 == 0: a group is entirely z or entirely r
           if (p.pre) {
@@ -832,7 +843,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = sigmoid_fast(v[i]);
           if (nb < half) {                     // z gate -> fp32 (read back by the q convolution's epilogue)
-            store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, 16);
+            store_f32x16(out_f32_t + pix * p.out_f32_stride + p.out_f32_coff + nb, v, 16);
           } else {                             // r gate -> r*h as split-bf16, the q convolution's first input segment
             float hv[16];
             load16(p.aux0 + pix * p.aux0_stride + (nb - half), hv);
@@ -851,7 +862,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           load16(p.aux1 + pix * p.aux1_stride + nb, zv);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = (1.f - zv[i]) * hv[i] + zv[i] * tanh_fast(v[i]);
-          if (p.out_f32) store_f32x16(p.out_f32 + pix * p.out_f32_stride + p.out_f32_coff + nb, v, 16);
+          if (p.out_f32) store_f32x16(out_f32_t + pix * p.out_f32_stride + p.out_f32_coff + nb, v, 16);
           if (p.out_hl) store_split16(p.out_hl + pix * p.out_hl_stride + p.out_hl_coff + nb, p.out_hl_plane, v, 16);
         }
       }
@@ -1728,7 +1739,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   if (d.stats)
     SCF_REQUIRE(d.cout % 32 == 0 && d.out_f32 && d.epi == SCF_EPI_ACT && reinterpret_cast<uintptr_t>(d.stats) % 16 == 0,
                 SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: stats need an fp32 output, cout %% 32 == 0 and the plain epilogue");
-  if (tct_eligible(d)) return conv2d_tct(d, st);
+  if (d.ksplit <= 1 && tct_eligible(d)) return conv2d_tct(d, st);
   TcParams p = {};
   p.nseg = d.nseg;
   const int stride = d.stride == 2 ? 2 : 1;
@@ -1872,6 +1883,15 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
         smem = 1024 + tc_header(8) + sa * a_stage + sb * b_stage;
       }
     }
+  }
+  // ---- tap split: requested by the caller (d.ksplit > 1) for plain linear layers whose partial maps it will add itself
+  p.ksplit = 1; p.taps_per_split = p.num_taps; p.split_stride = 0;
+  if (d.ksplit > 1) {
+    SCF_REQUIRE(!p.halo && d.epi == SCF_EPI_ACT && d.act == SCF_ACT_NONE && !d.bias && !d.aux0 && !d.stats && d.out_f32 && !d.out_hl &&
+                    !d.w_batched && p.num_taps % d.ksplit == 0 && d.split_stride > 0,
+                SCF_ERR_ARG, "scf_conv2d_tc: tap split needs a plain linear fp32-output layer (no bias / activation) and num_taps %% ksplit == 0");
+    p.ksplit = d.ksplit; p.taps_per_split = p.num_taps / d.ksplit; p.split_stride = d.split_stride;
+    p.num_tiles *= p.ksplit;
   }
   g_last_m_tiles = p.m_tiles;
   g_last_tiles_per_img = p.TB == 1 ? p.tiles_x * p.tiles_y : 0;

@@ -25,6 +25,8 @@ int corr_build_dispatch(const float* feat_render, const float* feat_real, int B,
 int gru_pass_fused(const scf_gru_pass_desc& d, cudaStream_t st);
 bool lookup_conv_ok(int num_levels, int radius, int B, int H8, int W8);
 bool lookup_conv_requested();
+int group_norm_relu_partials(float* x, int nsplit, long long split_stride, const float* gamma, const float* beta, int B, int HW, int C,
+                             int num_groups, float eps, void* out_hl, long long plane_stride, cudaStream_t stream);
 int pack_predict_tc(const float* wf_oihw, const float* wm_oihw, void* packed, int hidden, int cout_pad, cudaStream_t st);
 int predict_gather(const float* d, int ld, const float* bf, const float* bm, float* dflow, float* mask8, int B, int H, int W,
                    cudaStream_t st);
@@ -267,7 +269,8 @@ static void build_workspace(const scf_decoder_cfg& cfg, int B, int H, int W, Wor
   w.z = take(BP * 128 * 4); w.rh = take(BP * 128 * 4);
   w.hd = take(BP * 512 * 4); w.dflow = take(BP * 8); w.mask8 = take(BP * 4); w.pd = take(BP * 32 * 4);
   w.df1 = take(BP * 128 * 4); w.df2 = take(BP * 64 * 4); w.mf1 = take(BP * 64 * 4); w.mf2 = take(BP * 32 * 4);
-  w.p1 = take(BP / 4 * 128 * 4 + 1024); w.p2 = take(BP / 16 * 128 * 4 + 1024); w.p3 = take(BP / 64 * 128 * 4 + 1024);
+  // pose-head maps: up to 9 partial maps each (tap split of the stride-2 convolutions)
+  w.p1 = take(9 * (BP / 4 * 128 * 4 + 1024)); w.p2 = take(9 * (BP / 16 * 128 * 4 + 1024)); w.p3 = take(9 * (BP / 64 * 128 * 4 + 1024));
   w.fc0 = take((size_t)B * 1024 * 4); w.fc1 = take((size_t)B * 256 * 4);
   w.corr_stride_s = (cfg.num_levels * k * k + 7) / 8 * 8;
   if (cfg.precision == 1) {
@@ -500,6 +503,8 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
   struct SSeg { void* ptr; int stride, coff, nch; };
   int tc_hin = H8, tc_win = W8, tc_stride = 1;      // geometry of the next convtc call (pose head overrides it)
   int pad_writable = 0;
+  int tc_ksplit = 1;                                // tap split of the next convtc call (pose head)
+  long long tc_split_stride = 0;
   auto convtc = [&](int id, std::initializer_list<SSeg> segs, int act, float* out_f32, int f32_stride, void* out_hl,
                     int hl_stride, int hl_coff, int epi = SCF_EPI_ACT, const float* aux0 = nullptr, const float* aux1 = nullptr,
                     void* out2_hl = nullptr, const float* pre = nullptr, int pre_stride = 0) -> int {
@@ -521,6 +526,7 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
     d.out2_hl = out2_hl; d.out2_hl_plane = (long long)BP * 128; d.out2_hl_stride = 128;
     if (pre) { d.pre = pre; d.pre_stride = pre_stride; d.bias = nullptr; }   // the bias is part of the precomputed map
     d.out_pad_writable = pad_writable;
+    d.ksplit = tc_ksplit; d.split_stride = tc_split_stride;
     return conv2d_tc(d, lst);
   };
 
@@ -707,20 +713,33 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       const int h1 = (H8 - 1) / 2 + 1, w1 = (W8 - 1) / 2 + 1, h2 = (h1 - 1) / 2 + 1, w2 = (w1 - 1) / 2 + 1,
                 h3 = (h2 - 1) / 2 + 1, w3 = (w2 - 1) / 2 + 1;
       if (tcp) {
-        // stride-2 convolutions on the tensor cores (TMA element strides), GroupNorm emits the next conv's split-bf16 input
+        // stride-2 convolutions on the tensor cores (TMA element strides), GroupNorm emits the next conv's split-bf16 input.
+        // These maps have few pixel tiles (B=32: 64 / 16 / 4 tiles of 128 pixels for 148 SMs) and a long reduction (9 taps x
+        // 128-224 channels), so the taps are split over CTAs and the GroupNorm adds the partial maps when it loads them.
+        static const bool ph_split = [] { const char* e = getenv("SCFLOW_PH_SPLIT"); return e ? atoi(e) != 0 : true; }();
+        auto pick_split = [&](int out_pix) {
+          const int tiles = cdiv((long long)B * out_pix, 128);
+          if (!ph_split) return 1;
+          return tiles * 9 <= 160 ? 9 : (tiles * 3 <= 200 ? 3 : 1);
+        };
         tc_stride = 2;
         tc_hin = H8; tc_win = W8;
+        tc_ksplit = pick_split(h1 * w1); tc_split_stride = (long long)B * h1 * w1 * 128 + 256;
         SCF_TRY(convtc(PC_PH0, {{S(ws.s_h[0]), 128, 0, 128}, {S(ws.s_df2), 64, 0, 64}, {S(ws.s_mf2), 32, 0, 32}}, SCF_ACT_NONE,
                        F(ws.p1), 128, nullptr, 0, 0));
-        SCF_TRY(scf_group_norm_relu_split(F(ws.p1), pw + a.gn_w[0], pw + a.gn_b[0], B, h1 * w1, 128, 32, 1e-5f, S(ws.s_p1),
-                                          (long long)B * h1 * w1 * 128, st));
+        SCF_TRY(group_norm_relu_partials(F(ws.p1), tc_ksplit, tc_split_stride, pw + a.gn_w[0], pw + a.gn_b[0], B, h1 * w1, 128, 32, 1e-5f,
+                                         S(ws.s_p1), (long long)B * h1 * w1 * 128, st));
         tc_hin = h1; tc_win = w1;
+        tc_ksplit = pick_split(h2 * w2); tc_split_stride = (long long)B * h2 * w2 * 128 + 256;
         SCF_TRY(convtc(PC_PH1, {{S(ws.s_p1), 128, 0, 128}}, SCF_ACT_NONE, F(ws.p2), 128, nullptr, 0, 0));
-        SCF_TRY(scf_group_norm_relu_split(F(ws.p2), pw + a.gn_w[1], pw + a.gn_b[1], B, h2 * w2, 128, 32, 1e-5f, S(ws.s_p2),
-                                          (long long)B * h2 * w2 * 128, st));
+        SCF_TRY(group_norm_relu_partials(F(ws.p2), tc_ksplit, tc_split_stride, pw + a.gn_w[1], pw + a.gn_b[1], B, h2 * w2, 128, 32, 1e-5f,
+                                         S(ws.s_p2), (long long)B * h2 * w2 * 128, st));
         tc_hin = h2; tc_win = w2;
+        tc_ksplit = pick_split(h3 * w3); tc_split_stride = (long long)B * h3 * w3 * 128 + 256;
         SCF_TRY(convtc(PC_PH2, {{S(ws.s_p2), 128, 0, 128}}, SCF_ACT_NONE, F(ws.p3), 128, nullptr, 0, 0));
-        SCF_TRY(scf_group_norm_relu(F(ws.p3), pw + a.gn_w[2], pw + a.gn_b[2], B, h3 * w3, 128, 32, 1e-5f, st));
+        SCF_TRY(group_norm_relu_partials(F(ws.p3), tc_ksplit, tc_split_stride, pw + a.gn_w[2], pw + a.gn_b[2], B, h3 * w3, 128, 32, 1e-5f,
+                                         nullptr, 0, st));
+        tc_ksplit = 1; tc_split_stride = 0;
         tc_stride = 1; tc_hin = H8; tc_win = W8;
       } else {
       SCF_TRY(conv(PC_PH0, {{h, 128, 0, 128}, {F(ws.df2), 64, 0, 64}, {F(ws.mf2), 32, 0, 32}}, H8, W8, h1, w1, 2, SCF_ACT_NONE,

@@ -5,6 +5,9 @@
 
 namespace scf {
 
+int group_norm_relu_partials(float* x, int nsplit, long long split_stride, const float* gamma, const float* beta, int B, int HW, int C,
+                             int num_groups, float eps, void* out_hl, long long plane_stride, cudaStream_t stream);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -44,9 +47,12 @@ __global__ void __launch_bounds__(256) group_norm_relu_kernel(float* __restrict_
 // sample's values stay in registers between the three steps (mean, variance about the mean, normalise), so the map is
 // read once.  Optional split-bf16 copy of the result for a following tensor-core convolution.  HW <= 32*GN_MAXP.
 constexpr int GN_MAXP = 8;
+// ``nsplit`` > 1: x holds nsplit partial maps ``split_stride`` floats apart (split-K convolution); they are added on load
+// and the result is written to the first one.
 __global__ void __launch_bounds__(256) group_norm_relu_c4_kernel(float* __restrict__ x, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, int HW, float eps,
-                                                                 __nv_bfloat16* __restrict__ out_hl, long long plane) {
+                                                                 __nv_bfloat16* __restrict__ out_hl, long long plane, int nsplit,
+                                                                 long long split_stride) {
   __shared__ float red[32][9];
   __shared__ float stat[8];
   const int b = blockIdx.x, gl = threadIdx.x & 7, r = threadIdx.x >> 3;
@@ -59,6 +65,11 @@ __global__ void __launch_bounds__(256) group_norm_relu_c4_kernel(float* __restri
   for (int j = 0; j < GN_MAXP; ++j) {
     const int p = r + 32 * j;
     v[j] = p < HW ? base[(long long)p * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p < HW)
+      for (int k = 1; k < nsplit; ++k) {
+        const float4 u = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base + (long long)p * 32) + k * split_stride);
+        v[j].x += u.x; v[j].y += u.y; v[j].z += u.z; v[j].w += u.w;
+      }
     s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
   }
   red[r][gl] = s;
@@ -234,20 +245,31 @@ extern "C" {
 
 int scf_group_norm_relu_split(float* x, const float* gamma, const float* beta, int B, int HW, int C, int num_groups, float eps,
                               void* out_hl, long long plane_stride, void* stream) {
-  SCF_REQUIRE(x && gamma && beta && B > 0 && HW > 0, SCF_ERR_ARG, "scf_group_norm_relu_split: bad args");
+  return scf::group_norm_relu_partials(x, 1, 0, gamma, beta, B, HW, C, num_groups, eps, out_hl, plane_stride, (cudaStream_t)stream);
+}
+}  // extern "C"
+
+namespace scf {
+int group_norm_relu_partials(float* x, int nsplit, long long split_stride, const float* gamma, const float* beta, int B, int HW, int C,
+                             int num_groups, float eps, void* out_hl, long long plane_stride, cudaStream_t stream) {
+  SCF_REQUIRE(x && gamma && beta && B > 0 && HW > 0 && nsplit >= 1 && split_stride % 4 == 0, SCF_ERR_ARG, "scf_group_norm_relu_split: bad args");
   SCF_REQUIRE(C == 128 && num_groups == 32, SCF_ERR_UNSUPPORTED, "scf_group_norm_relu_split: C=128, 32 groups only");
   SCF_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(gamma) % 16 == 0 &&
                   reinterpret_cast<uintptr_t>(beta) % 16 == 0, SCF_ERR_ALIGN, "scf_group_norm_relu_split: 16B alignment required");
   if (HW > 32 * scf::GN_MAXP) {     // large maps: the generic one-warp-per-(sample, group) kernel (no split copy available)
-    SCF_REQUIRE(out_hl == nullptr, SCF_ERR_UNSUPPORTED, "scf_group_norm_relu_split: maps above %d pixels are not supported", 32 * scf::GN_MAXP);
+    SCF_REQUIRE(out_hl == nullptr && nsplit == 1, SCF_ERR_UNSUPPORTED, "scf_group_norm_relu_split: maps above %d pixels are not supported", 32 * scf::GN_MAXP);
     const int warps = B * num_groups;
     scf::group_norm_relu_kernel<<<scf::cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, B, HW, C, num_groups, eps);
     return scf::check_launch("group_norm_relu_kernel");
   }
   scf::group_norm_relu_c4_kernel<<<dim3(B, 4), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, HW, eps,
-                                                                     reinterpret_cast<__nv_bfloat16*>(out_hl), plane_stride);
+                                                                     reinterpret_cast<__nv_bfloat16*>(out_hl), plane_stride, nsplit,
+                                                                     split_stride);
   return scf::check_launch("group_norm_relu_c4_kernel");
 }
+}  // namespace scf
+
+extern "C" {
 
 int scf_group_norm_relu(float* x, const float* gamma, const float* beta, int B, int HW, int C, int num_groups, float eps,
                         void* stream) {
