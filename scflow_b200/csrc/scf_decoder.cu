@@ -27,6 +27,9 @@ bool lookup_conv_ok(int num_levels, int radius, int B, int H8, int W8);
 bool lookup_conv_requested();
 int group_norm_relu_partials(float* x, int nsplit, long long split_stride, const float* gamma, const float* beta, int B, int HW, int C,
                              int num_groups, float eps, void* out_hl, long long plane_stride, cudaStream_t stream);
+int pose_fc_tail(const float* x, const float* w0, const float* b0, int I0, int O0, const float* w1, const float* b1, int O1,
+                 const float* rot_w, const float* rot_b, const float* tr_w, const float* tr_b, const int64_t* label, float* d_rot,
+                 float* d_trs, int B, int rot_dim, int num_class, float* part0, float* part1, int ks0, int ks1, cudaStream_t st);
 int pack_predict_tc(const float* wf_oihw, const float* wm_oihw, void* packed, int hidden, int cout_pad, cudaStream_t st);
 int predict_gather(const float* d, int ld, const float* bf, const float* bm, float* dflow, float* mask8, int B, int H, int W,
                    cudaStream_t st);
@@ -271,7 +274,7 @@ static void build_workspace(const scf_decoder_cfg& cfg, int B, int H, int W, Wor
   w.df1 = take(BP * 128 * 4); w.df2 = take(BP * 64 * 4); w.mf1 = take(BP * 64 * 4); w.mf2 = take(BP * 32 * 4);
   // pose-head maps: up to 9 partial maps each (tap split of the stride-2 convolutions)
   w.p1 = take(9 * (BP / 4 * 128 * 4 + 1024)); w.p2 = take(9 * (BP / 16 * 128 * 4 + 1024)); w.p3 = take(9 * (BP / 64 * 128 * 4 + 1024));
-  w.fc0 = take((size_t)B * 1024 * 4); w.fc1 = take((size_t)B * 256 * 4);
+  w.fc0 = take((size_t)8 * B * 1024 * 4); w.fc1 = take((size_t)8 * B * 256 * 4);       // up to 8 split-K partial maps
   w.corr_stride_s = (cfg.num_levels * k * k + 7) / 8 * 8;
   if (cfg.precision == 1) {
     auto split = [&](int ch) { return take(BP * ch * 2 * 2); };
@@ -750,10 +753,19 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       SCF_TRY(conv(PC_PH2, {{F(ws.p2), 128, 0, 128}}, h2, w2, h3, w3, 2, SCF_ACT_NONE, F(ws.p3), 128, 0));
       SCF_TRY(scf_group_norm_relu(F(ws.p3), pw + a.gn_w[2], pw + a.gn_b[2], B, h3 * w3, 128, 32, 1e-5f, st));
       }
-      SCF_TRY(scf_linear(F(ws.p3), pw + a.fc0_w, pw + a.fc0_b, F(ws.fc0), B, 2048, 1024, SCF_ACT_RELU, st));
-      SCF_TRY(scf_linear(F(ws.fc0), pw + a.fc1_w, pw + a.fc1_b, F(ws.fc1), B, 1024, 256, SCF_ACT_RELU, st));
-      SCF_TRY(scf_pose_project(F(ws.fc1), pw + a.rot_w, pw + a.rot_b, pw + a.tr_w, pw + a.tr_b, io->label, drot_k, dtrs_k, B,
-                               256, cfg->rot_dim, cfg->num_class, st));
+      // (measured, B = 32: the split-K form is 0.04 ms per step SLOWER - the FC kernels' fixed costs, not their weight stream,
+      // dominate - so it is opt-in)
+      static const bool fc_split = [] { const char* e = getenv("SCFLOW_FC_SPLIT"); return e ? atoi(e) != 0 : false; }();
+      if (fc_split && B <= 32) {
+        // small batch: the FC layers as split-K weight streams over 4x more blocks, bias / ReLU applied by the consumer
+        SCF_TRY(pose_fc_tail(F(ws.p3), pw + a.fc0_w, pw + a.fc0_b, 2048, 1024, pw + a.fc1_w, pw + a.fc1_b, 256, pw + a.rot_w, pw + a.rot_b,
+                             pw + a.tr_w, pw + a.tr_b, io->label, drot_k, dtrs_k, B, cfg->rot_dim, cfg->num_class, F(ws.fc0), F(ws.fc1), 4, 4, st));
+      } else {
+        SCF_TRY(scf_linear(F(ws.p3), pw + a.fc0_w, pw + a.fc0_b, F(ws.fc0), B, 2048, 1024, SCF_ACT_RELU, st));
+        SCF_TRY(scf_linear(F(ws.fc0), pw + a.fc1_w, pw + a.fc1_b, F(ws.fc1), B, 1024, 256, SCF_ACT_RELU, st));
+        SCF_TRY(scf_pose_project(F(ws.fc1), pw + a.rot_w, pw + a.rot_b, pw + a.tr_w, pw + a.tr_b, io->label, drot_k, dtrs_k, B,
+                                 256, cfg->rot_dim, cfg->num_class, st));
+      }
     } else {
       identity_delta_kernel<<<cdiv(B, 64), 64, 0, st>>>(drot_k, dtrs_k, B, cfg->rot_dim);
       SCF_TRY(check_launch("identity_delta_kernel"));

@@ -14,6 +14,22 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// acc[j] = this lane's partial sum of sample j (j = 0..31).  Transpose-reduce: after the call lane l holds (return value) the
+// sum over all lanes of sample l - 31 shuffles (16 + 8 + 4 + 2 + 1) instead of 32 full butterflies (160).
+__device__ __forceinline__ float transpose_reduce32(float (&acc)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float send = up ? acc[j] : acc[j + off];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      acc[j] = (up ? acc[j + off] : acc[j]) + recv;
+    }
+  }
+  return acc[0];
+}
+
 // one warp per (sample, group); NHWC [B,HW,C]; two-pass mean / biased variance like torch.group_norm
 __global__ void __launch_bounds__(256) group_norm_relu_kernel(float* __restrict__ x, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int B, int HW, int C,
@@ -166,15 +182,123 @@ __global__ void __launch_bounds__(256) linear_smem_kernel(const float* __restric
         }
       }
     }
-    // lane j ends up with the full sum of sample j (butterfly transpose-reduce)
-    float mine = 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float t = warp_sum(acc[j]);
-      if (lane == j) mine = t;
-    }
+    // lane j ends up with the full sum of sample j
+    const float mine = transpose_reduce32(acc, lane);
     if (o < O && lane < nb) y[(long long)(b0 + lane) * O + o] = act_apply(mine + (bias ? bias[o] : 0.f), act);
   }
+}
+
+// Split-K form of the FC layers for small batches: with B <= 32 samples an FC layer is a weight stream (fc0: 8 MB) that a
+// handful of blocks cannot pull from L2 fast enough, and one block's serial sweep over I = 2048 is pure latency.  grid =
+// (O / 8, KS): block (ob, ks) forms the partial dot products of 8 output rows over input columns [ks * I / KS, ...) and writes
+// them raw to part[ks][b][o]; bias and activation of THIS layer are applied by whoever reads the partials next (the next layer's
+// x staging below, or pose_project) - `xin` describes that for this layer's own input: x = act(sum_s xin.part[s] + xin.bias).
+struct LinIn { const float* p; int nsplit; long long split_stride; const float* bias; int relu; };
+
+__device__ __forceinline__ float4 lin_load4(const LinIn& in, long long off, int col) {
+  float4 v = __ldg(reinterpret_cast<const float4*>(in.p + off));
+  for (int s = 1; s < in.nsplit; ++s) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(in.p + s * in.split_stride + off));
+    v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+  }
+  if (in.bias) {
+    const float4 bq = __ldg(reinterpret_cast<const float4*>(in.bias + col));
+    v.x += bq.x; v.y += bq.y; v.z += bq.z; v.w += bq.w;
+  }
+  if (in.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  return v;
+}
+
+__global__ void __launch_bounds__(256) linear_splitk_kernel(const LinIn xin, const float* __restrict__ w, float* __restrict__ part,
+                                                            int B, int I, int O, int krange) {
+  __shared__ __align__(16) float xs[32][LIN_KC];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int o = blockIdx.x * 8 + wid, ks = blockIdx.y;
+  const int kbeg = ks * krange, kend = kbeg + krange < I ? kbeg + krange : I;
+  const float* wr = w + (long long)(o < O ? o : O - 1) * I;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  for (int k0 = kbeg; k0 < kend; k0 += LIN_KC) {
+    // this chunk's weights first (their latency overlaps the x staging)
+    float4 wv[LIN_KC / 128];
+#pragma unroll
+    for (int h = 0; h < LIN_KC / 128; ++h) {
+      const int k = k0 + h * 128 + lane * 4;
+      wv[h] = k < kend ? __ldg(reinterpret_cast<const float4*>(wr + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * (LIN_KC / 4); idx += 256) {
+      const int bb = idx / (LIN_KC / 4), c4 = idx - bb * (LIN_KC / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bb < B && k0 + c4 * 4 < kend) v = lin_load4(xin, (long long)bb * I + k0 + c4 * 4, k0 + c4 * 4);
+      reinterpret_cast<float4*>(&xs[bb][0])[c4] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < LIN_KC / 128; ++h) {
+      const int k = h * 128 + lane * 4;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float4 xv = *reinterpret_cast<const float4*>(&xs[j][k]);
+        acc[j] = fmaf(wv[h].x, xv.x, fmaf(wv[h].y, xv.y, fmaf(wv[h].z, xv.z, fmaf(wv[h].w, xv.w, acc[j]))));
+      }
+    }
+  }
+  const float mine = transpose_reduce32(acc, lane);
+  if (o < O && lane < B) part[((long long)ks * B + lane) * O + o] = mine;
+}
+
+// pose_project over split-K partials of the last FC layer: x = relu(sum_s part[s] + bias)
+__global__ void __launch_bounds__(256) pose_project_partials_kernel(const LinIn xin, const float* __restrict__ rot_w,
+                                                                    const float* __restrict__ rot_b, const float* __restrict__ tr_w,
+                                                                    const float* __restrict__ tr_b, const int64_t* __restrict__ label,
+                                                                    float* __restrict__ d_rot, float* __restrict__ d_trs, int B, int I,
+                                                                    int rot_dim, int num_class) {
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int rows = rot_dim + 3;
+  if (wid >= B * rows) return;
+  const int b = wid / rows, r = wid - b * rows;
+  long long cls = 0;
+  if (num_class > 0) {
+    cls = label[0];
+    if (cls < 0) cls = 0;
+    if (cls >= num_class) cls = num_class - 1;
+  }
+  const float* wr;
+  float bo;
+  if (r < rot_dim) { wr = rot_w + (cls * rot_dim + r) * I; bo = rot_b[cls * rot_dim + r]; }
+  else { wr = tr_w + (cls * 3 + (r - rot_dim)) * I; bo = tr_b[cls * 3 + (r - rot_dim)]; }
+  float acc = 0.f;
+  for (int i = lane * 4; i < I; i += 128) {
+    const float4 xv = lin_load4(xin, (long long)b * I + i, i);
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + i));
+    acc = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc))));
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (r < rot_dim) d_rot[b * rot_dim + r] = acc + bo;
+    else d_trs[b * 3 + (r - rot_dim)] = acc + bo;
+  }
+}
+
+// The pose head's FC tail for B <= 32 (pose_head.py:203-210): fc0 (relu) -> fc1 (relu) -> class-selected projection as three
+// launches over split-K partial sums.  part0: [ks0][B][O0], part1: [ks1][B][O1] scratch.
+int pose_fc_tail(const float* x, const float* w0, const float* b0, int I0, int O0, const float* w1, const float* b1, int O1,
+                 const float* rot_w, const float* rot_b, const float* tr_w, const float* tr_b, const int64_t* label, float* d_rot,
+                 float* d_trs, int B, int rot_dim, int num_class, float* part0, float* part1, int ks0, int ks1, cudaStream_t st) {
+  SCF_REQUIRE(B >= 1 && B <= 32 && I0 % (ks0 * 4) == 0 && O0 % (ks1 * 4) == 0 && O0 % 4 == 0 && O1 % 4 == 0, SCF_ERR_ARG, "pose_fc_tail: bad shape");
+  LinIn in0 = {x, 1, 0, nullptr, 0};
+  linear_splitk_kernel<<<dim3(cdiv(O0, 8), ks0), 256, 0, st>>>(in0, w0, part0, B, I0, O0, I0 / ks0);
+  SCF_TRY(check_launch("linear_splitk_kernel"));
+  LinIn in1 = {part0, ks0, (long long)B * O0, b0, 1};
+  linear_splitk_kernel<<<dim3(cdiv(O1, 8), ks1), 256, 0, st>>>(in1, w1, part1, B, O0, O1, O0 / ks1);
+  SCF_TRY(check_launch("linear_splitk_kernel"));
+  LinIn in2 = {part1, ks1, (long long)B * O1, b1, 1};
+  const int warps = B * (rot_dim + 3);
+  pose_project_partials_kernel<<<cdiv(warps, 8), 256, 0, st>>>(in2, rot_w, rot_b, tr_w, tr_b, label, d_rot, d_trs, B, O1, rot_dim, num_class);
+  return check_launch("pose_project_partials_kernel");
 }
 
 // y[b,o] = act(W[o,:] . x[b,:] + bias[o]); one warp per output row, 8 samples per sweep of the row
