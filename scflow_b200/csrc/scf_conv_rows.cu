@@ -1,0 +1,405 @@
+// 3x3 stride-1 convolutions of 64 -> 64 channels on large maps: the four residual-block convolutions of the RAFT encoders'
+// first stage (models/backbone/resnet.py:14-94 BasicBlock.conv1 / conv2 at 1/2 resolution, 64 channels), the biggest bucket
+// of the encoder time.  On the generic pixels-as-rows tile such a layer issues 9 taps x 4 k-steps x 3 split-bf16 products
+// = 108 MMAs of N = 64 per 128-pixel tile, and an M = 128 tcgen05.mma costs the same ~61 ns for every N <= 128: half of the
+// tensor core's width is idle.  This kernel re-associates the sum instead ("rolling rows"):
+//     out[y][x] = sum_ky  Q_ky[y + ky - 1][x],     Q_ky[r][x] = sum_kx W(ky, kx) . in[r][x + kx - 1]
+//   * a tile is ONE input row r of 128 pixels (+1 halo pixel each side; TMA zero fill = the convolution's padding), fetched
+//     once as two 130 x 128 B SWIZZLE_128B planes (hi, lo); the three x-shifts are row-shifted A descriptors on that tile;
+//   * the B operand stacks the three ky taps of one kx along N: [W(2,kx) | W(1,kx) | W(0,kx)] = 192 rows, so ONE MMA of
+//     N = 192 yields Q_2[r], Q_1[r], Q_0[r] = the contributions of input row r to out[r-1], out[r], out[r+1]:
+//     3 kx x 4 k-steps x 3 products = 36 MMAs per row instead of 108;
+//   * TMEM is a ring of eight 64-column slots, one per OUTPUT row in flight; consecutive output rows sit in consecutive
+//     slots, so the three row sums accumulate in place in the tensor core: input row r adds into slots of out[r-1], out[r]
+//     (accumulate) and opens out[r+1] (first MMA of the step issued separately with accumulate = 0 for that slot).  A step
+//     whose three slots wrap around the ring issues two MMAs (N = 128 + 64) per product;
+//   * all 9 taps of the weights (2 planes x 72 KB) stay resident in shared memory for the CTA's lifetime; a CTA owns a
+//     contiguous range of (image, column strip, row) units, re-reading one halo row at each end of a range;
+//   * epilogue: one thread per pixel reads its 64 channels from the finished slot, adds bias (+ residual), optional ReLU,
+//     writes fp32 and / or split-bf16 NHWC with 32 B vector stores and (InstanceNorm) the per-(row, warp) partial sums of the
+//     output and its square through a 31-shuffle transpose-reduce - deterministic, no atomics.
+#include "scf_common.cuh"
+#include "scf_tc.cuh"
+#include <mutex>
+#include <stdlib.h>
+
+namespace scf {
+
+using namespace tc;
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box, const cuuint32_t* elem_strides, CUtensorMapDataType dtype, CUtensorMapSwizzle swz);
+extern thread_local int g_last_m_tiles, g_last_tiles_per_img, g_last_stat_rows_per_img;
+
+constexpr int CR_M = 128, CR_C = 64, CR_EW = 4, CR_ASTAGES = 2, CR_SLOTS = 8;
+constexpr uint32_t CR_AROWS = CR_M + 2;                                   // pixels per tile row incl. the x halo
+constexpr uint32_t CR_APLANE = (CR_AROWS * 128u + 1023u) & ~1023u;        // 17 KB
+constexpr uint32_t CR_ASTAGE = 2 * CR_APLANE;
+constexpr uint32_t CR_WBLK = CR_C * 128u;                                 // one tap, one plane: 64 output rows x 128 B
+constexpr uint32_t CR_WKX = 3 * CR_WBLK;                                  // the three ky taps of one kx, stacked along N
+constexpr uint32_t CR_WPLANE = 3 * CR_WKX;
+constexpr uint32_t CR_WBYTES = 2 * CR_WPLANE;                             // 144 KB
+constexpr int CR_SMEM = 1024 + 1024 + (int)CR_WBYTES + CR_ASTAGES * (int)CR_ASTAGE;
+static_assert(CR_SMEM <= 232448, "conv_rows_kernel does not fit in shared memory");
+
+struct RowsParams {
+  int N, H, W, TX;                 // images, map size, 128-pixel column strips per row
+  long long U;                     // work units = N * TX * H output rows of one strip
+  const float* bias; int relu;
+  float* out_f32; int of_stride, of_coff;
+  __nv_bfloat16* out_hl; long long oh_plane; int oh_stride, oh_coff;
+  const float* res; int res_stride;
+  float* stats; int stat_rows;     // rows of [2][64] partial sums per image: (y * TX + xt) * 4 + warp
+  int al32;                        // 32 B vector accesses allowed: bit 0 fp32 output, bit 1 split output, bit 2 residual input
+  int dbg;                         // timing experiments (SCFLOW_ROWS_DBG): 1 no MMAs, 2 no global stores, 4 no activation loads
+};
+
+// The three roles (TMA producer, MMA issuer, epilogue) walk the same schedule: the CTA's unit range, cut into segments at
+// strip boundaries; a segment with output rows [y0, y1) consumes input rows max(y0-1, 0) .. min(y1, H-1).  `seq` numbers the
+// CTA's output rows consecutively (TMEM slot = seq & 7).
+template <class F>
+__device__ __forceinline__ void rows_for_each_step(const RowsParams& p, F&& f) {
+  long long u = p.U * blockIdx.x / gridDim.x;
+  const long long u1 = p.U * (blockIdx.x + 1) / gridDim.x;
+  uint32_t seq = 0;
+  while (u < u1) {
+    const int strip = (int)(u / p.H), y0 = (int)(u - (long long)strip * p.H);
+    const int y1 = (u1 - u) < (long long)(p.H - y0) ? y0 + (int)(u1 - u) : p.H;
+    const int img = strip / p.TX, xt = strip - img * p.TX;
+    const int r0 = y0 > 0 ? y0 - 1 : 0, r1 = y1 < p.H ? y1 : p.H - 1;
+    for (int r = r0; r <= r1; ++r) f(img, xt, r, y0, y1, seq);
+    seq += (uint32_t)(y1 - y0);
+    u += y1 - y0;
+  }
+}
+
+__device__ __forceinline__ float transpose_reduce32_rows(float (&acc)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float send = up ? acc[j] : acc[j + off];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      acc[j] = (up ? acc[j + off] : acc[j]) + recv;
+    }
+  }
+  return acc[0];
+}
+
+template <int MODE>       // bit 0: residual input, bit 1: InstanceNorm partial sums
+__global__ void __launch_bounds__(64 + 32 * CR_EW, 1)
+conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const RowsParams p) {
+  constexpr bool RES = (MODE & 1) != 0, STATS = (MODE & 2) != 0;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = sb, bar_empty = sb + 16, bar_w = sb + 32, bar_tfull = sb + 64, bar_tempty = sb + 128, tmem_slot = sb + 192,
+                 bias_s = sb + 256;
+  const uint32_t w0 = sb + 1024, a0 = w0 + CR_WBYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  griddep_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmW);
+    for (int s = 0; s < CR_ASTAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < CR_SLOTS; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, CR_EW); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  griddep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // weights, once: tap (ky, kx) of plane pl lands in the kx stack at row block 2 - ky (the slot order out[r-1], out[r], out[r+1])
+      mbar_arrive_expect_tx(bar_w, CR_WBYTES);
+      for (int pl = 0; pl < 2; ++pl)
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx)
+            tma_load_4d(w0 + pl * CR_WPLANE + kx * CR_WKX + (2 - ky) * CR_WBLK, &tmW, bar_w, 0, 0, ky * 3 + kx, pl);
+      int stage = 0;
+      uint32_t phase = 0;
+      rows_for_each_step(p, [&](int img, int xt, int r, int, int, uint32_t) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+        const uint32_t full = bar_full + 8 * stage, dst = a0 + stage * CR_ASTAGE;
+        if (p.dbg & 4) mbar_arrive(full);
+        else {
+          mbar_arrive_expect_tx(full, 2 * CR_AROWS * 128u);
+          tma_load_5d(dst, &tmA, full, 0, xt * CR_M - 1, r, img, 0);
+          tma_load_5d(dst + CR_APLANE, &tmA, full, 0, xt * CR_M - 1, r, img, 1);
+        }
+        if (++stage == CR_ASTAGES) { stage = 0; phase ^= 1u; }
+      });
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc_bf16(CR_M, 64), idesc2 = make_idesc_bf16(CR_M, 128), idesc3 = make_idesc_bf16(CR_M, 192);
+      int stage = 0;
+      uint32_t phase = 0;
+      mbar_wait(bar_w, 0);
+      tc_fence_after();
+      rows_for_each_step(p, [&](int, int, int r, int y0, int y1, uint32_t seq) {
+        const int lo = r - 1 > y0 ? r - 1 : y0, hi = r + 1 < y1 - 1 ? r + 1 : y1 - 1;
+        // output rows touched for the first time by this input row: out[r+1], and out[0] at the top of an image
+        const int n_fresh = (hi == r + 1 ? 1 : 0) + ((r == 0 && lo == 0) ? 1 : 0);
+        for (int y = hi - n_fresh + 1; y <= hi; ++y) {
+          const uint32_t sq = seq + (uint32_t)(y - y0);
+          mbar_wait(bar_tempty + 8 * (sq & 7u), ((sq >> 3) & 1u) ^ 1u);
+        }
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        // the step's output rows lo..hi sit in consecutive ring slots; a window that wraps is issued as two column ranges.
+        // Everything that depends on the step is computed here once: the 36 products below only add immediates.
+        const int sa = (int)((seq + (uint32_t)(lo - y0)) & 7u), n = hi - lo + 1;
+        const int n1 = n < CR_SLOTS - sa ? n : CR_SLOTS - sa, n2 = n - n1;
+        const uint32_t d1 = tmem_base + (uint32_t)(sa * 64), d2 = tmem_base;
+        const uint32_t i1 = n1 == 3 ? idesc3 : n1 == 2 ? idesc2 : idesc1, i2 = n2 == 2 ? idesc2 : idesc1;
+        const uint32_t at = a0 + stage * CR_ASTAGE;
+        const uint64_t a_hi0 = make_smem_desc_sw128(at, 1024), a_lo0 = make_smem_desc_sw128(at + CR_APLANE, 1024);
+        const uint32_t wrow = w0 + (uint32_t)(lo - r + 1) * CR_WBLK;                    // ky block of row lo
+        const uint64_t b1_hi0 = make_smem_desc_sw128(wrow, 1024), b1_lo0 = make_smem_desc_sw128(wrow + CR_WPLANE, 1024);
+        const uint64_t b2_hi0 = b1_hi0 + (uint64_t)(((uint32_t)n1 * CR_WBLK) >> 4), b2_lo0 = b1_lo0 + (uint64_t)(((uint32_t)n1 * CR_WBLK) >> 4);
+        if (!(p.dbg & 1)) {
+          {
+            // first product of the step: rows opened by this input row start from zero, the others accumulate
+            const int nf = n_fresh;
+            if (nf == 0) {
+              umma_bf16(d1, a_hi0, b1_hi0, i1, 1u);
+              if (n2) umma_bf16(d2, a_hi0, b2_hi0, i2, 1u);
+            } else {
+              for (int y = lo; y <= hi; ++y) {      // row by row (N = 64 each): at most three instructions, once per step
+                const uint32_t sl = (seq + (uint32_t)(y - y0)) & 7u;
+                umma_bf16(tmem_base + sl * 64u, a_hi0, b1_hi0 + (uint64_t)(((uint32_t)(y - lo) * CR_WBLK) >> 4), idesc1, y > hi - nf ? 0u : 1u);
+              }
+            }
+            umma_bf16(d1, a_hi0, b1_lo0, i1, 1u);
+            umma_bf16(d1, a_lo0, b1_hi0, i1, 1u);
+            if (n2) { umma_bf16(d2, a_hi0, b2_lo0, i2, 1u); umma_bf16(d2, a_lo0, b2_hi0, i2, 1u); }
+          }
+#pragma unroll
+          for (int kk = 1; kk < 12; ++kk) {
+            const int kx = kk >> 2, k = kk & 3;
+            const uint64_t ao = (uint64_t)((kx * 128 + k * 32) >> 4), wo = (uint64_t)((kx * (int)CR_WKX + k * 32) >> 4);
+            umma_bf16(d1, a_hi0 + ao, b1_hi0 + wo, i1, 1u);
+            umma_bf16(d1, a_hi0 + ao, b1_lo0 + wo, i1, 1u);
+            umma_bf16(d1, a_lo0 + ao, b1_hi0 + wo, i1, 1u);
+            if (n2) {
+              umma_bf16(d2, a_hi0 + ao, b2_hi0 + wo, i2, 1u);
+              umma_bf16(d2, a_hi0 + ao, b2_lo0 + wo, i2, 1u);
+              umma_bf16(d2, a_lo0 + ao, b2_hi0 + wo, i2, 1u);
+            }
+          }
+        }
+        umma_commit(bar_empty + 8 * stage);
+        if (++stage == CR_ASTAGES) { stage = 0; phase ^= 1u; }
+        if (lo == r - 1) umma_commit(bar_tfull + 8 * ((seq + (uint32_t)(r - 1 - y0)) & 7u));
+        if (r == p.H - 1 && y1 == p.H) umma_commit(bar_tfull + 8 * ((seq + (uint32_t)(r - y0)) & 7u));
+      });
+    }
+  } else {
+    // ================= epilogue: thread = pixel (TMEM lane) of the finished output row
+    const int q = warp & 3, et = (int)threadIdx.x - 64;
+    if (et < CR_C) {
+      const float b = p.bias ? __ldg(p.bias + et) : 0.f;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * (uint32_t)et), "f"(b) : "memory");
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * CR_EW) : "memory");
+    rows_for_each_step(p, [&](int img, int xt, int r, int y0, int y1, uint32_t seq) {
+      auto do_row = [&](int y) {
+        const uint32_t sq = seq + (uint32_t)(y - y0), slot = sq & 7u;
+        const int x = xt * CR_M + q * 32 + lane;
+        const bool valid = x < p.W;
+        const long long pix = ((long long)img * p.H + y) * p.W + x;
+        float4 rs[RES ? 16 : 1];
+        if (RES) {
+          const float* rp = p.res + pix * p.res_stride;
+          if (!valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else if (p.al32 & 4) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("ld.global.cs.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                           : "=f"(rs[2 * j].x), "=f"(rs[2 * j].y), "=f"(rs[2 * j].z), "=f"(rs[2 * j].w), "=f"(rs[2 * j + 1].x), "=f"(rs[2 * j + 1].y),
+                             "=f"(rs[2 * j + 1].z), "=f"(rs[2 * j + 1].w)
+                           : "l"(rp + 8 * j));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rs[j] = __ldcs(reinterpret_cast<const float4*>(rp) + j);
+          }
+        }
+        mbar_wait(bar_tfull + 8 * slot, (sq >> 3) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 64u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[32];
+          tmem_ld32(taddr + (uint32_t)(h * 32), v);
+          if (h == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 b;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_s + (uint32_t)(h * 128 + j * 16)));
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            if (RES) { v[4 * j] += rs[h * 8 + j].x; v[4 * j + 1] += rs[h * 8 + j].y; v[4 * j + 2] += rs[h * 8 + j].z; v[4 * j + 3] += rs[h * 8 + j].w; }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (valid && !(p.dbg & 2)) {
+            if (p.out_f32) {
+              float* o = p.out_f32 + pix * p.of_stride + p.of_coff + h * 32;
+              if (p.al32 & 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + 8 * j), "f"(v[8 * j]), "f"(v[8 * j + 1]),
+                               "f"(v[8 * j + 2]), "f"(v[8 * j + 3]), "f"(v[8 * j + 4]), "f"(v[8 * j + 5]), "f"(v[8 * j + 6]), "f"(v[8 * j + 7]) : "memory");
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+            }
+            if (p.out_hl) {
+              uint32_t hw[16], lw[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(v[2 * j], h0, l0);
+                split_bf16(v[2 * j + 1], h1, l1);
+                hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              __nv_bfloat16* oh = p.out_hl + pix * p.oh_stride + p.oh_coff + h * 32;
+              __nv_bfloat16* ol = oh + p.oh_plane;
+              if (p.al32 & 2) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(oh + 16 * j), "r"(hw[8 * j]), "r"(hw[8 * j + 1]),
+                               "r"(hw[8 * j + 2]), "r"(hw[8 * j + 3]), "r"(hw[8 * j + 4]), "r"(hw[8 * j + 5]), "r"(hw[8 * j + 6]), "r"(hw[8 * j + 7]) : "memory");
+                  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ol + 16 * j), "r"(lw[8 * j]), "r"(lw[8 * j + 1]),
+                               "r"(lw[8 * j + 2]), "r"(lw[8 * j + 3]), "r"(lw[8 * j + 4]), "r"(lw[8 * j + 5]), "r"(lw[8 * j + 6]), "r"(lw[8 * j + 7]) : "memory");
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  reinterpret_cast<uint4*>(oh)[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+                  reinterpret_cast<uint4*>(ol)[j] = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+                }
+              }
+            }
+          }
+          if (STATS) {
+            float s2[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; s2[i] = v[i] * v[i]; }
+            const float m1 = transpose_reduce32_rows(v, lane), m2 = transpose_reduce32_rows(s2, lane);
+            float* o = p.stats + (((long long)img * p.stat_rows + (long long)(y * p.TX + xt) * 4 + q) * 2) * CR_C + h * 32 + lane;
+            o[0] = m1;
+            o[CR_C] = m2;
+          }
+        }
+      };
+      const int lo = r - 1 > y0 ? r - 1 : y0;
+      if (lo == r - 1) do_row(r - 1);
+      if (r == p.H - 1 && y1 == p.H) do_row(p.H - 1);
+    });
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
+// SCFLOW_TC_ROWS (default 1): 3x3 / stride 1 / 64 -> 64 channel layers on maps at least 96 pixels wide take this kernel
+bool conv2d_rows_eligible(const scf_tc_conv_desc& d) {
+  const char* e = getenv("SCFLOW_TC_ROWS");
+  if (e && atoi(e) == 0) return false;
+  const int sx = d.stride_x ? d.stride_x : (d.stride == 2 ? 2 : 1), sy = d.stride_y ? d.stride_y : (d.stride == 2 ? 2 : 1);
+  if (d.kh != 3 || d.kw != 3 || sx != 1 || sy != 1 || d.nseg != 1 || d.seg[0].nch != CR_C || d.cin_pad != CR_C || d.cout != CR_C ||
+      d.cout_pad != CR_C || d.w_batched || d.ksplit > 1 || d.w_plane_stride != 0)
+    return false;
+  if (d.epi != SCF_EPI_ACT || (d.act != SCF_ACT_NONE && d.act != SCF_ACT_RELU) || d.pre || d.aux1 || d.out2_hl || d.scale != 1.f) return false;
+  if (d.W < 96 || (long long)d.B * d.H * cdiv(d.W, CR_M) < 148) return false;
+  auto al16 = [](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0; };
+  if (!al16(d.seg[0].ptr) || d.seg[0].stride % 8 || d.seg[0].coff % 8 || (d.seg[0].plane_stride * 2) % 16) return false;
+  if (d.out_f32 && (!al16(d.out_f32) || d.out_f32_stride % 4 || d.out_f32_coff % 4)) return false;
+  if (d.out_hl && (!al16(d.out_hl) || d.out_hl_stride % 8 || d.out_hl_coff % 8 || (d.out_hl_plane * 2) % 16)) return false;
+  if (d.aux0 && (!al16(d.aux0) || d.aux0_stride % 4)) return false;
+  return true;
+}
+
+int conv2d_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
+  RowsParams p = {};
+  p.N = d.B; p.H = d.H; p.W = d.W; p.TX = cdiv(d.W, CR_M);
+  p.U = (long long)d.B * p.TX * d.H;
+  p.bias = d.bias; p.relu = d.act == SCF_ACT_RELU ? 1 : 0;
+  p.out_f32 = d.out_f32; p.of_stride = d.out_f32_stride; p.of_coff = d.out_f32_coff;
+  p.out_hl = reinterpret_cast<__nv_bfloat16*>(d.out_hl); p.oh_plane = d.out_hl_plane; p.oh_stride = d.out_hl_stride; p.oh_coff = d.out_hl_coff;
+  p.res = d.aux0; p.res_stride = d.aux0_stride;
+  p.stats = d.stats; p.stat_rows = d.H * p.TX * 4;
+  {
+    auto al32 = [](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % 32 == 0; };
+    if (d.out_f32 && al32(d.out_f32) && d.out_f32_stride % 8 == 0 && d.out_f32_coff % 8 == 0) p.al32 |= 1;
+    if (d.out_hl && al32(d.out_hl) && d.out_hl_stride % 16 == 0 && d.out_hl_coff % 16 == 0 && (d.out_hl_plane * 2) % 32 == 0) p.al32 |= 2;
+    if (d.aux0 && al32(d.aux0) && d.aux0_stride % 8 == 0) p.al32 |= 4;
+    const char* de = getenv("SCFLOW_ROWS_DBG");
+    p.dbg = de ? atoi(de) : 0;
+  }
+  CUtensorMap tmA, tmW;
+  {
+    const scf_tc_seg& sg = d.seg[0];
+    const char* base = reinterpret_cast<const char*>(sg.ptr) + (size_t)sg.coff * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)CR_C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B, 2};
+    cuuint64_t str[4] = {(cuuint64_t)sg.stride * 2, (cuuint64_t)d.W * sg.stride * 2, (cuuint64_t)d.H * d.W * sg.stride * 2,
+                         (cuuint64_t)sg.plane_stride * 2};
+    cuuint32_t box[5] = {(cuuint32_t)CR_C, CR_AROWS, 1, 1, 1};
+    SCF_TRY(encode_map(&tmA, base, 5, dims, str, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B));
+    cuuint64_t wd[4] = {(cuuint64_t)CR_C, (cuuint64_t)CR_C, 9, 2};
+    cuuint64_t ws[3] = {(cuuint64_t)CR_C * 2, (cuuint64_t)CR_C * CR_C * 2, (cuuint64_t)9 * CR_C * CR_C * 2};
+    cuuint32_t wb[4] = {(cuuint32_t)CR_C, (cuuint32_t)CR_C, 1, 1};
+    SCF_REQUIRE(reinterpret_cast<uintptr_t>(d.w) % 16 == 0, SCF_ERR_ALIGN, "scf_conv2d_tc: packed weight must be 16B aligned");
+    SCF_TRY(encode_map(&tmW, d.w, 4, wd, ws, wb, nullptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    SCF_CUDA(cudaGetDevice(&dev));
+    SCF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const RowsParams);
+  static const KernelFn table[4] = {conv_rows_kernel<0>, conv_rows_kernel<1>, conv_rows_kernel<2>, conv_rows_kernel<3>};
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    for (int i = 0; i < 4 && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM);
+  });
+  SCF_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "cudaFuncSetAttribute(conv_rows_kernel): %s", cudaGetErrorString(attr_err));
+  g_last_m_tiles = (int)p.U; g_last_tiles_per_img = p.TX * d.H; g_last_stat_rows_per_img = p.stat_rows;
+  static const bool pdl = [] { const char* e = getenv("SCFLOW_PDL"); return e ? atoi(e) != 0 : true; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(p.U < num_sms ? p.U : num_sms)); cfg.blockDim = dim3(64 + 32 * CR_EW);
+  cfg.dynamicSmemBytes = CR_SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  const int mode = (d.aux0 ? 1 : 0) | (d.stats ? 2 : 0);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, table[mode], tmA, tmW, p);
+  if (le != cudaSuccess) { cudaGetLastError(); set_error("conv_rows_kernel launch: %s", cudaGetErrorString(le)); g_launches++; return (int)le; }
+  return check_launch("conv_rows_kernel");
+}
+
+}  // namespace scf

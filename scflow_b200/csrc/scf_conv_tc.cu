@@ -1481,6 +1481,9 @@ int conv2d_tc_max_tiles(int B, int Hout, int Wout) {
     const int eq = (2 * t + 3) / 4;
     if (eq > best) best = eq;
   }
+  // rolling-rows kernel (scf_conv_rows.cu): 4 rows per (output row, 128-pixel column strip)
+  const int rr = B * Hout * cdiv(Wout, 128);
+  if (rr > best) best = rr;
   return best;
 }
 
@@ -1708,6 +1711,9 @@ static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
   return check_launch("conv_tct_kernel");
 }
 
+bool conv2d_rows_eligible(const scf_tc_conv_desc& d);
+int conv2d_rows(const scf_tc_conv_desc& d, cudaStream_t st);
+
 int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   SCF_REQUIRE(d.nseg >= 1 && d.nseg <= 3, SCF_ERR_ARG, "scf_conv2d_tc: nseg must be 1..3");
   SCF_REQUIRE(d.w && d.B > 0 && d.H > 0 && d.W > 0 && d.cout > 0, SCF_ERR_ARG, "scf_conv2d_tc: null pointer or empty shape");
@@ -1739,6 +1745,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   if (d.stats)
     SCF_REQUIRE(d.cout % 32 == 0 && d.out_f32 && d.epi == SCF_EPI_ACT && reinterpret_cast<uintptr_t>(d.stats) % 16 == 0,
                 SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: stats need an fp32 output, cout %% 32 == 0 and the plain epilogue");
+  if (conv2d_rows_eligible(d)) return conv2d_rows(d, st);
   if (d.ksplit <= 1 && tct_eligible(d)) return conv2d_tct(d, st);
   TcParams p = {};
   p.nseg = d.nseg;

@@ -158,3 +158,63 @@ def test_conv_tc_small_n_variants(S, monkeypatch, transposed, cin, cout, k, hw, 
         rows = st.view(-1, 2, cout).double().sum(0).cpu()
         assert float((rows[0] - ref.double().sum((0, 2, 3))).abs().max()) < 1e-2
         assert float((rows[1] - ref.double().pow(2).sum((0, 2, 3))).abs().max()) < 2e-2
+
+
+ROWS_CASES = [
+    # (H, W), B, residual, stats, act, out_hl channel offset
+    ((128, 128), 2, False, True, 'none', 16),     # encoder stage 1 (InstanceNorm): raw fp32 + partial sums, full-width strips
+    ((128, 128), 2, True, False, 'relu', 16),     # encoder stage 1 (folded BatchNorm): residual + ReLU, fp32 + split outputs
+    ((96, 160), 1, True, True, 'relu', 8),        # two column strips, the second ragged (32 of 128 pixels); 16 B store path
+    ((80, 96), 2, False, False, 'relu', 0),       # one ragged strip; CTA ranges cut inside images
+    ((7, 128), 24, False, True, 'none', 0),       # images shorter than the TMEM ring: many segment starts / ends per CTA
+]
+
+
+@pytest.mark.parametrize('hw,b,residual,stats,act,hl_coff', ROWS_CASES)
+def test_conv_rows_kernel_matches_fp64_and_generic_tile(S, monkeypatch, hw, b, residual, stats, act, hl_coff):
+    """scf_conv_rows.cu (3x3, 64 -> 64, rolling-rows accumulation in TMEM) against an fp64 convolution and against the generic
+    tile (SCFLOW_TC_ROWS=0): outputs, InstanceNorm partial sums, untouched neighbouring channels."""
+    cin = cout = 64
+    gen = torch.Generator().manual_seed(hw[0] * 1000 + hw[1] + b)
+    x = torch.randn(b, cin, *hw, generator=gen)
+    w = torch.randn(cout, cin, 3, 3, generator=gen) / math.sqrt(cin * 9)
+    bias = 0.1 * torch.randn(cout, generator=gen)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+    res = torch.randn(b, *hw, cout, generator=gen) if residual else None
+    if residual:
+        ref = ref + res.permute(0, 3, 1, 2).double()
+    if act == 'relu':
+        ref = torch.relu(ref)
+    ref = ref.float()
+    xs = S.ops.split_nchw(x.cuda())
+    pw = S.ops.pack_conv_weight_tc([w.cuda()])
+    n_tiles, _ = S.ops.conv2d_tc_tiles(b, *hw)
+    outs = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('SCFLOW_TC_ROWS', mode)
+        out_f32 = torch.full((b, *hw, cout + 8), 7.0, device='cuda')
+        out_hl = torch.full((2, b, *hw, cout + 32), 7.0, device='cuda', dtype=torch.bfloat16)
+        st = torch.zeros(n_tiles * 4 * 2 * cout, device='cuda') if stats else None
+        S.ops.conv2d_tc([(xs, 0, cin)], pw, bias.cuda(), cout, 3, act=act, out_f32=out_f32, out_hl=out_hl, out_hl_coff=hl_coff,
+                        aux0=None if res is None else res.cuda(), stats=st)
+        torch.cuda.synchronize()
+        got = out_f32[..., :cout].permute(0, 3, 1, 2).cpu()
+        got_hl = S.ops.unsplit(out_hl)[:, hl_coff:hl_coff + cout].cpu()
+        err, err_hl = float((got - ref).abs().max()), float((got_hl - ref).abs().max())
+        print(f'conv rows={mode} hw={hw} b={b}: max err f32 {err:.3e}, split {err_hl:.3e}')
+        assert err < 5e-5 and err_hl < 1e-4
+        assert bool((out_f32[..., cout:] == 7.0).all()) and bool((out_hl[..., :hl_coff] == 7.0).all()) and \
+            bool((out_hl[..., hl_coff + cout:] == 7.0).all())
+        if stats:
+            # the partial sums describe the kernel's OWN fp32 output (what InstanceNorm normalises) ...
+            rows = st.view(-1, 2, cout).double().sum(0).cpu()
+            own = out_f32[..., :cout].double().cpu()
+            assert float((rows[0] - own.sum((0, 1, 2))).abs().max()) < 1e-3
+            assert float((rows[1] - own.pow(2).sum((0, 1, 2))).abs().max()) < 1e-3
+            # ... and agree with the fp64 reference to the split-bf16 products' relative accuracy
+            sq = ref.double().pow(2).sum((0, 2, 3))
+            assert float((rows[0] - ref.double().sum((0, 2, 3))).abs().max()) < 2e-2
+            assert float(((rows[1] - sq).abs() / sq).max()) < 2e-5
+        outs[mode] = got
+    # same products, different summation order inside the fp32 accumulator
+    assert float((outs['1'] - outs['0']).abs().max()) < 2e-5
