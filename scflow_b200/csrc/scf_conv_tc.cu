@@ -1482,7 +1482,7 @@ int conv2d_tc_max_tiles(int B, int Hout, int Wout) {
     if (eq > best) best = eq;
   }
   // rolling-rows kernel (scf_conv_rows.cu): 4 rows per (output row, 128-pixel column strip)
-  const int rr = B * Hout * cdiv(Wout, 128);
+  const int rr = Wout >= 96 ? B * Hout * cdiv(Wout, 128) : 0;      // (the kernel only takes maps at least 96 pixels wide)
   if (rr > best) best = rr;
   return best;
 }

@@ -27,6 +27,11 @@ bool lookup_conv_ok(int num_levels, int radius, int B, int H8, int W8);
 bool lookup_conv_requested();
 int group_norm_relu_partials(float* x, int nsplit, long long split_stride, const float* gamma, const float* beta, int B, int HW, int C,
                              int num_groups, float eps, void* out_hl, long long plane_stride, cudaStream_t stream);
+int fc_tc(const float* x, int x_nsplit, long long x_split_stride, const float* x_bias, int x_relu, const void* w_packed, float* part,
+          int B, int I, int O, int KR, cudaStream_t st);
+int pose_project_partials(const float* part, int nsplit, long long split_stride, const float* bias, const float* rot_w, const float* rot_b,
+                          const float* tr_w, const float* tr_b, const int64_t* label, float* d_rot, float* d_trs, int B, int I,
+                          int rot_dim, int num_class, cudaStream_t st);
 int pose_fc_tail(const float* x, const float* w0, const float* b0, int I0, int O0, const float* w1, const float* b1, int O1,
                  const float* rot_w, const float* rot_b, const float* tr_w, const float* tr_b, const int64_t* label, float* d_rot,
                  float* d_trs, int B, int rot_dim, int num_class, float* part0, float* part1, int ks0, int ks1, cudaStream_t st);
@@ -105,6 +110,7 @@ struct Arena {
   size_t fc0_w, fc0_b, fc1_w, fc1_b, rot_w, rot_b, tr_w, tr_b;
   size_t fold_scratch;        // floats: staging of a folded thin-input weight while packing
   size_t pd_off;              // bytes: the two predict layers as one 1x1 convolution 512 -> 19 (tap-wise partial products), bf16 [2][32][512]
+  size_t fc_off[2];           // bytes: fc0 / fc1 as split-bf16 [2][O][I] for the tcgen05 FC layers (0 = none)
   size_t lk_off;              // bytes: corr_net[0] repacked per pyramid level for the fused lookup + convolution (0 = none)
   size_t total_floats;
   size_t total_bytes;         // fp32 section + tensor-core section
@@ -194,6 +200,11 @@ static void build_arena(const scf_decoder_cfg& cfg, Arena& a) {
     a.pd_off = boff;
     boff += ((size_t)2 * 32 * 512 * 2 + 1023) / 1024 * 1024;
   }
+  a.fc_off[0] = a.fc_off[1] = 0;
+  if (cfg.precision == 1 && cfg.pose_head) {
+    a.fc_off[0] = boff; boff += (size_t)2 * 1024 * 2048 * 2;
+    a.fc_off[1] = boff; boff += (size_t)2 * 256 * 1024 * 2;
+  }
   a.lk_off = 0;
   if (cfg.precision == 1 && cfg.num_levels == 4 && cfg.radius == 4) {
     a.lk_off = boff;
@@ -274,7 +285,7 @@ static void build_workspace(const scf_decoder_cfg& cfg, int B, int H, int W, Wor
   w.df1 = take(BP * 128 * 4); w.df2 = take(BP * 64 * 4); w.mf1 = take(BP * 64 * 4); w.mf2 = take(BP * 32 * 4);
   // pose-head maps: up to 9 partial maps each (tap split of the stride-2 convolutions)
   w.p1 = take(9 * (BP / 4 * 128 * 4 + 1024)); w.p2 = take(9 * (BP / 16 * 128 * 4 + 1024)); w.p3 = take(9 * (BP / 64 * 128 * 4 + 1024));
-  w.fc0 = take((size_t)8 * B * 1024 * 4); w.fc1 = take((size_t)8 * B * 256 * 4);       // up to 8 split-K partial maps
+  w.fc0 = take((size_t)16 * B * 1024 * 4); w.fc1 = take((size_t)16 * B * 256 * 4);     // up to 16 split-K partial maps
   w.corr_stride_s = (cfg.num_levels * k * k + 7) / 8 * 8;
   if (cfg.precision == 1) {
     auto split = [&](int ch) { return take(BP * ch * 2 * 2); };
@@ -403,6 +414,12 @@ int scf_decoder_pack(const scf_decoder_cfg* cfg, const float* const* h_weights, 
     SCF_CUDA(cudaMemcpyAsync(base + a.fc0_b, h_weights[SCF_W_PH_FC0_B], 1024 * 4, cudaMemcpyDeviceToDevice, st));
     SCF_CUDA(cudaMemcpyAsync(base + a.fc1_w, h_weights[SCF_W_PH_FC1_W], (size_t)256 * 1024 * 4, cudaMemcpyDeviceToDevice, st));
     SCF_CUDA(cudaMemcpyAsync(base + a.fc1_b, h_weights[SCF_W_PH_FC1_B], 256 * 4, cudaMemcpyDeviceToDevice, st));
+    if (a.fc_off[0]) {
+      // the tcgen05 FC layers read split-bf16 [2][O][I] copies (fc0 with its columns already permuted to the NHWC flatten)
+      char* pb = reinterpret_cast<char*>(packed);
+      SCF_TRY(scf_pack_conv_weight_tc(base + a.fc0_w, pb + a.fc_off[0], 1024, 2048, 1, 1, 2048, 1024, 0, st));
+      SCF_TRY(scf_pack_conv_weight_tc(base + a.fc1_w, pb + a.fc_off[1], 256, 1024, 1, 1, 1024, 256, 0, st));
+    }
     SCF_CUDA(cudaMemcpyAsync(base + a.rot_w, h_weights[SCF_W_PH_ROT_W], (size_t)a.rot_rows * 256 * 4, cudaMemcpyDeviceToDevice, st));
     SCF_CUDA(cudaMemcpyAsync(base + a.rot_b, h_weights[SCF_W_PH_ROT_B], (size_t)a.rot_rows * 4, cudaMemcpyDeviceToDevice, st));
     SCF_CUDA(cudaMemcpyAsync(base + a.tr_w, h_weights[SCF_W_PH_TR_W], (size_t)a.tr_rows * 256 * 4, cudaMemcpyDeviceToDevice, st));
@@ -756,7 +773,18 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
       // (measured, B = 32: the split-K form is 0.04 ms per step SLOWER - the FC kernels' fixed costs, not their weight stream,
       // dominate - so it is opt-in)
       static const bool fc_split = [] { const char* e = getenv("SCFLOW_FC_SPLIT"); return e ? atoi(e) != 0 : false; }();
-      if (fc_split && B <= 32) {
+      static const bool fc_tcore = [] { const char* e = getenv("SCFLOW_FC_TC"); return e ? atoi(e) != 0 : true; }();
+      if (fc_tcore && tcp && a.fc_off[0] && B <= 32) {
+        // small batch: both FC layers on tcgen05, split-K over 8 blocks per 128 output rows; each consumer sums the producer's
+        // partial maps and applies its bias / ReLU while it forms its own operand
+        const char* pb = reinterpret_cast<const char*>(packed);
+        static const int kr0 = [] { const char* e = getenv("SCFLOW_FC_KR0"); const int v = e ? atoi(e) : 256; return v == 128 ? 128 : 256; }();
+        static const int kr1 = [] { const char* e = getenv("SCFLOW_FC_KR1"); const int v = e ? atoi(e) : 64; return v == 128 ? 128 : 64; }();
+        SCF_TRY(fc_tc(F(ws.p3), 1, 0, nullptr, 0, pb + a.fc_off[0], F(ws.fc0), B, 2048, 1024, kr0, st));
+        SCF_TRY(fc_tc(F(ws.fc0), 2048 / kr0, (long long)B * 1024, pw + a.fc0_b, 1, pb + a.fc_off[1], F(ws.fc1), B, 1024, 256, kr1, st));
+        SCF_TRY(pose_project_partials(F(ws.fc1), 1024 / kr1, (long long)B * 256, pw + a.fc1_b, pw + a.rot_w, pw + a.rot_b, pw + a.tr_w, pw + a.tr_b,
+                                      io->label, drot_k, dtrs_k, B, 256, cfg->rot_dim, cfg->num_class, st));
+      } else if (fc_split && B <= 32) {
         // small batch: the FC layers as split-K weight streams over 4x more blocks, bias / ReLU applied by the consumer
         SCF_TRY(pose_fc_tail(F(ws.p3), pw + a.fc0_w, pw + a.fc0_b, 2048, 1024, pw + a.fc1_w, pw + a.fc1_b, 256, pw + a.rot_w, pw + a.rot_b,
                              pw + a.tr_w, pw + a.tr_b, io->label, drot_k, dtrs_k, B, cfg->rot_dim, cfg->num_class, F(ws.fc0), F(ws.fc1), 4, 4, st));

@@ -283,6 +283,16 @@ __global__ void __launch_bounds__(256) pose_project_partials_kernel(const LinIn 
   }
 }
 
+// class-selected projection over the split-K partial maps of the last FC layer (x = relu(sum_s part[s] + bias))
+int pose_project_partials(const float* part, int nsplit, long long split_stride, const float* bias, const float* rot_w, const float* rot_b,
+                          const float* tr_w, const float* tr_b, const int64_t* label, float* d_rot, float* d_trs, int B, int I,
+                          int rot_dim, int num_class, cudaStream_t st) {
+  LinIn in = {part, nsplit, split_stride, bias, 1};
+  const int warps = B * (rot_dim + 3);
+  pose_project_partials_kernel<<<cdiv(warps, 8), 256, 0, st>>>(in, rot_w, rot_b, tr_w, tr_b, label, d_rot, d_trs, B, I, rot_dim, num_class);
+  return check_launch("pose_project_partials_kernel");
+}
+
 // The pose head's FC tail for B <= 32 (pose_head.py:203-210): fc0 (relu) -> fc1 (relu) -> class-selected projection as three
 // launches over split-K partial sums.  part0: [ks0][B][O0], part1: [ks1][B][O1] scratch.
 int pose_fc_tail(const float* x, const float* w0, const float* b0, int I0, int O0, const float* w1, const float* b1, int O1,

@@ -177,6 +177,25 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: 
     return y
 
 
+def linear_tc(x: torch.Tensor, w: torch.Tensor, kr: int = 256, x_bias: Optional[torch.Tensor] = None, x_relu: bool = False) -> torch.Tensor:
+    """Split-K tcgen05 FC layer (scf_linear_tc): returns the raw partial sums [I / kr, B, O]; ``x`` is [B, I] or a stack of partial
+    maps [S, B, I] of the previous layer (summed, + ``x_bias``, ReLU if ``x_relu``, while the operand is formed)."""
+    _req(x, 'x')
+    nsplit = 1 if x.dim() == 2 else x.shape[0]
+    bsz, i = x.shape[-2:]
+    if w.dtype == torch.float32:                       # [O, I] fp32 -> split-bf16 [2, 1, O, I]
+        _req(w, 'w')
+        o = w.shape[0]
+        packed = pack_conv_weight_tc([w.reshape(o, i, 1, 1).contiguous()], cin_pad=i)
+    else:
+        packed = _req(w, 'w', torch.bfloat16)
+        o = w.shape[-2]
+    part = torch.empty(i // kr, bsz, o, device=x.device, dtype=torch.float32)
+    check(_lib.load().scf_linear_tc(ptr(x), nsplit, bsz * i, ptr(x_bias), int(x_relu), ptr(packed), ptr(part), bsz, i, o, kr, stream_ptr()),
+          'scf_linear_tc')
+    return part
+
+
 def pose_project(x, rot_w, rot_b, tr_w, tr_b, label, rot_dim: int, num_class: int):
     _req(x, 'x')
     bsz, i = x.shape

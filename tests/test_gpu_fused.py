@@ -123,3 +123,27 @@ def test_lookup_fused_with_first_motion_encoder_conv(b, mag):
     own = S.ops.corr_lookup_nhwc(levels, flow8, 4)[..., :324].permute(0, 3, 1, 2).cpu()
     ref2 = torch.relu(torch.einsum('oc,bchw->bohw', w[:, :, 0, 0].double(), own.double()) + bias.double().view(1, -1, 1, 1)).float()
     assert float((got - ref2).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize('b', [32, 5, 1])
+def test_linear_tc_split_k_chain_matches_fp64(b):
+    """The pose head's FC tail on tcgen05 (scf_linear_tc; pose_head.py:203-210): fc0 writes raw split-K partial maps, fc1 sums them,
+    adds fc0's bias and ReLU while forming its operand; the sums of fc1's maps + bias + ReLU equal the fp64 layers."""
+    import scflow_b200 as S
+    gen = torch.Generator().manual_seed(40 + b)
+    x = torch.relu(torch.randn(b, 2048, generator=gen))
+    w0, b0 = torch.randn(1024, 2048, generator=gen) / 2048 ** 0.5, 0.1 * torch.randn(1024, generator=gen)
+    w1, b1 = torch.randn(256, 1024, generator=gen) / 1024 ** 0.5, 0.1 * torch.randn(256, generator=gen)
+    y0 = torch.relu(x.double() @ w0.double().t() + b0.double())
+    y1 = torch.relu(y0 @ w1.double().t() + b1.double())
+    p0 = S.ops.linear_tc(x.cuda(), w0.cuda(), kr=256)
+    assert p0.shape == (8, b, 1024)
+    got0 = torch.relu(p0.sum(0).cpu().double() + b0.double())
+    p1 = S.ops.linear_tc(p0, w1.cuda(), kr=128, x_bias=b0.cuda(), x_relu=True)
+    assert p1.shape == (8, b, 256)
+    got1 = torch.relu(p1.sum(0).cpu().double() + b1.double())
+    e0, e1 = float((got0 - y0).abs().max()), float((got1 - y1).abs().max())
+    print(f'linear_tc B={b}: fc0 max err {e0:.3e}, fc1 max err {e1:.3e} (|y1| max {float(y1.abs().max()):.2f})')
+    assert e0 < 2e-5 and e1 < 2e-5
+    # deterministic: a second launch reproduces the partial maps bit for bit
+    assert torch.equal(p0, S.ops.linear_tc(x.cuda(), w0.cuda(), kr=256))
