@@ -15,7 +15,7 @@
 //     whose three slots wrap around the ring issues two MMAs (N = 128 + 64) per product;
 //   * all 9 taps of the weights (2 planes x 72 KB) stay resident in shared memory for the CTA's lifetime; a CTA owns a
 //     contiguous range of (image, column strip, row) units, re-reading one halo row at each end of a range;
-//   * epilogue: one thread per pixel reads its 64 channels from the finished slot, adds bias (+ residual), optional ReLU,
+//   * epilogue: eight warps, one thread per (pixel, 32-channel half) reads its channels from the finished slot, adds bias (+ residual), optional ReLU,
 //     writes fp32 and / or split-bf16 NHWC with 32 B vector stores and (InstanceNorm) the per-(row, warp) partial sums of the
 //     output and its square through a 31-shuffle transpose-reduce - deterministic, no atomics.
 #include "scf_common.cuh"
@@ -31,7 +31,7 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dim
                const cuuint32_t* box, const cuuint32_t* elem_strides, CUtensorMapDataType dtype, CUtensorMapSwizzle swz);
 extern thread_local int g_last_m_tiles, g_last_tiles_per_img, g_last_stat_rows_per_img;
 
-constexpr int CR_M = 128, CR_C = 64, CR_EW = 4, CR_ASTAGES = 2, CR_SLOTS = 8;
+constexpr int CR_M = 128, CR_C = 64, CR_EW = 8, CR_ASTAGES = 2, CR_SLOTS = 8;
 constexpr uint32_t CR_AROWS = CR_M + 2;                                   // pixels per tile row incl. the x halo
 constexpr uint32_t CR_APLANE = (CR_AROWS * 128u + 1023u) & ~1023u;        // 17 KB
 constexpr uint32_t CR_ASTAGE = 2 * CR_APLANE;
@@ -202,7 +202,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ================= epilogue: thread = pixel (TMEM lane) of the finished output row
-    const int q = warp & 3, et = (int)threadIdx.x - 64;
+    // the two warps of a lane quarter take one 32-channel half each
+    const int q = warp & 3, h = (warp - 2) >> 2, et = (int)threadIdx.x - 64;
     if (et < CR_C) {
       const float b = p.bias ? __ldg(p.bias + et) : 0.f;
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * (uint32_t)et), "f"(b) : "memory");
@@ -214,42 +215,39 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int x = xt * CR_M + q * 32 + lane;
         const bool valid = x < p.W;
         const long long pix = ((long long)img * p.H + y) * p.W + x;
-        float4 rs[RES ? 16 : 1];
+        float4 rs[RES ? 8 : 1];
         if (RES) {
-          const float* rp = p.res + pix * p.res_stride;
+          const float* rp = p.res + pix * p.res_stride + h * 32;
           if (!valid) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 8; ++j) rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           } else if (p.al32 & 4) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < 4; ++j)
               asm volatile("ld.global.cs.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                            : "=f"(rs[2 * j].x), "=f"(rs[2 * j].y), "=f"(rs[2 * j].z), "=f"(rs[2 * j].w), "=f"(rs[2 * j + 1].x), "=f"(rs[2 * j + 1].y),
                              "=f"(rs[2 * j + 1].z), "=f"(rs[2 * j + 1].w)
                            : "l"(rp + 8 * j));
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) rs[j] = __ldcs(reinterpret_cast<const float4*>(rp) + j);
+            for (int j = 0; j < 8; ++j) rs[j] = __ldcs(reinterpret_cast<const float4*>(rp) + j);
           }
         }
         mbar_wait(bar_tfull + 8 * slot, (sq >> 3) & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 64u;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        {
           float v[32];
           tmem_ld32(taddr + (uint32_t)(h * 32), v);
-          if (h == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
-          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 b;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_s + (uint32_t)(h * 128 + j * 16)));
             v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            if (RES) { v[4 * j] += rs[h * 8 + j].x; v[4 * j + 1] += rs[h * 8 + j].y; v[4 * j + 2] += rs[h * 8 + j].z; v[4 * j + 3] += rs[h * 8 + j].w; }
+            if (RES) { v[4 * j] += rs[j].x; v[4 * j + 1] += rs[j].y; v[4 * j + 2] += rs[j].z; v[4 * j + 3] += rs[j].w; }
           }
           if (p.relu) {
 #pragma unroll

@@ -276,6 +276,112 @@ __global__ void __launch_bounds__(256) corr_lookup_l4r4_smem_kernel(const Lookup
   }
 }
 
+// Third form of the same lookup ("lean"): identical arithmetic and staging idea as corr_lookup_l4r4_smem_kernel, but with the
+// index work stripped down - the SASS of the kernel above is 55 % integer instructions (divisions by 12 and 9 per staged texel and
+// per tap, 64-bit pixel decomposition, per-tap range checks) and the kernel is issue-bound.  Here: lanes stage a region as
+// (row pair, 16 columns) so every address is base + immediate; the tap -> (a, b) decomposition is done once per lane for the
+// three rounds; region-relative tap coordinates are clamped with one unsigned min instead of a four-way range branch; stores use
+// one per-lane base pointer per plane.  Outputs are bit-identical to the two kernels above.
+// TH, TW > 0: the query map size is a compile-time constant (32 x 32 = 256x256 crops), which turns every level size, row stride
+// and range bound into an immediate; TH = TW = 0 reads them from the parameters.
+template <int TH, int TW>
+__global__ void __launch_bounds__(256) corr_lookup_l4r4_lean_kernel(const LookupParams p) {
+  constexpr int R = 4, K = 9, KK = 81, L = 4, ROUNDS = 3, NIT = LK_ROWS / 2;
+  __shared__ float reg[8][L][LK_ROWS * LK_RS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned q = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (q >= (unsigned)p.nq) return;
+  const unsigned W8 = TW > 0 ? (unsigned)TW : (unsigned)p.W8, P = TH > 0 ? (unsigned)(TH * TW) : (unsigned)(p.H8 * p.W8);
+  const unsigned pix = q % P;
+  const unsigned y = pix / W8, x = pix - y * W8;
+  const float2 f = *reinterpret_cast<const float2*>(p.flow8 + (size_t)q * 2);
+  const float gx0 = __fadd_rn((float)x, f.x), gy0 = __fadd_rn((float)y, f.y);
+  const float mval = p.mask ? p.mask[q] : 1.f;
+  int i0[L], xlo[L], ylo[L];
+  float w0[L], w1[L];
+  {
+    const bool isx = lane < K;
+    const int off = (isx ? lane : lane - K) - R;
+    float inv = 1.f;
+#pragma unroll
+    for (int l = 0; l < L; ++l, inv *= 0.5f) {
+      const float c = __fmul_rn(isx ? gx0 : gy0, inv);
+      const int wl = TW > 0 ? (TW >> l) : p.wl[l], hl = TH > 0 ? (TH >> l) : p.hl[l];
+      const float ic = lookup_coord(c, off, isx ? wl : hl);
+      const float fl = floorf(ic);
+      i0[l] = (int)fminf(fmaxf(fl, -65536.f), 65536.f);
+      w1[l] = ic - fl;
+      w0[l] = (fl + 1.f) - ic;
+      xlo[l] = __shfl_sync(0xffffffffu, i0[l], 0);
+      ylo[l] = __shfl_sync(0xffffffffu, i0[l], K);
+    }
+  }
+  // ---- stage the regions: lane = (row parity, column), six row pairs per level; all 24 loads issued before the first use
+  const int rr = lane >> 4, cc = lane & 15;
+  float st[L][NIT];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const int wl = TW > 0 ? (TW >> l) : p.wl[l], hl = TH > 0 ? (TH >> l) : p.hl[l];
+    const int xx = xlo[l] + cc, yy0 = ylo[l] + rr;
+    const bool xin = cc < LK_RS && (unsigned)xx < (unsigned)wl;
+    const float* src = p.lvl[l] + (size_t)q * (unsigned)(hl * wl) + (yy0 * wl + xx);
+#pragma unroll
+    for (int i = 0; i < NIT; ++i)
+      st[l][i] = (xin && (unsigned)(yy0 + 2 * i) < (unsigned)hl) ? __ldg(src + 2 * i * wl) : 0.f;
+  }
+  if (cc < LK_RS) {
+    float* dst = &reg[wid][0][rr * LK_RS + cc];
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) dst[l * (LK_ROWS * LK_RS) + 2 * i * LK_RS] = st[l][i];
+  }
+  __syncwarp();
+  // ---- taps: tap = round * 32 + lane -> (a, b), once for all levels
+  int ta[ROUNDS], tb[ROUNDS];
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const int tap = r * 32 + lane, tc = tap < KK ? tap : KK - 1;
+    ta[r] = tc / K;
+    tb[r] = K + tc - ta[r] * K;
+  }
+  float* outq = p.out ? p.out + (size_t)q * p.out_stride + p.out_coff + lane : nullptr;
+  __nv_bfloat16* outh = p.out_hl ? p.out_hl + (size_t)q * p.out_stride + lane : nullptr;
+  __nv_bfloat16* outl = outh + p.out_hl_plane;
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const int x0 = __shfl_sync(0xffffffffu, i0[l], ta[r]), y0 = __shfl_sync(0xffffffffu, i0[l], tb[r]);
+      const float wx0 = __shfl_sync(0xffffffffu, w0[l], ta[r]), wx1 = __shfl_sync(0xffffffffu, w1[l], ta[r]);
+      const float wy0 = __shfl_sync(0xffffffffu, w0[l], tb[r]), wy1 = __shfl_sync(0xffffffffu, w1[l], tb[r]);
+      // floor coordinates grow with the window index, so these are 0..10 (the min only guards the shared-memory access)
+      const unsigned rx = min((unsigned)(x0 - xlo[l]), (unsigned)(LK_RS - 2)), ry = min((unsigned)(y0 - ylo[l]), (unsigned)(LK_ROWS - 2));
+      const float* s0 = &reg[wid][l][ry * LK_RS + rx];
+      const float v00 = s0[0], v01 = s0[1], v10 = s0[LK_RS], v11 = s0[LK_RS + 1];
+      float acc = 0.f;
+      acc += v00 * (wx0 * wy0);
+      acc += v01 * (wx1 * wy0);
+      acc += v10 * (wx0 * wy1);
+      acc += v11 * (wx1 * wy1);
+      acc *= mval;
+      if (r < ROUNDS - 1 || lane < KK - 32 * (ROUNDS - 1)) {
+        if (outq) outq[l * KK + r * 32] = acc;
+        if (outh) {
+          __nv_bfloat16 hi, lo;
+          tc::split_bf16(acc, hi, lo);
+          outh[l * KK + r * 32] = hi;
+          outl[l * KK + r * 32] = lo;
+        }
+      }
+    }
+  }
+  if (outh) {
+    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+    for (int c = L * KK + lane; c < p.out_stride; c += 32) { outh[c - lane] = zero; outl[c - lane] = zero; }
+  }
+}
+
 __global__ void corr_lookup_taps_kernel(int level, int radius, const float* __restrict__ flow8, int32_t* __restrict__ x0,
                                         int32_t* __restrict__ y0, int H8, int W8, long long nq) {
   const int k = 2 * radius + 1;
@@ -374,7 +480,13 @@ static int corr_lookup_impl(const float* const* h_levels, int num_levels, int ra
   p.out_stride = out_stride; p.out_coff = out_coff; p.H8 = H8; p.W8 = W8; p.nq = (long long)B * H8 * W8;
   const int wpb = 8;
   if (num_levels == 4 && radius == 4) {
-    static const bool staged = [] { const char* e = getenv("SCFLOW_LOOKUP_SMEM"); return e ? atoi(e) != 0 : true; }();
+    // SCFLOW_LOOKUP_SMEM: 0 gathers from global memory, 1 shared-memory staged regions, 2 (default) the same with lean index work
+    static const int staged = [] { const char* e = getenv("SCFLOW_LOOKUP_SMEM"); return e ? atoi(e) : 2; }();
+    if (staged >= 2 && p.nq < (1ll << 31)) {
+      if (H8 == 32 && W8 == 32) scf::corr_lookup_l4r4_lean_kernel<32, 32><<<scf::cdiv(p.nq, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(p);
+      else scf::corr_lookup_l4r4_lean_kernel<0, 0><<<scf::cdiv(p.nq, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(p);
+      return scf::check_launch("corr_lookup_l4r4_lean_kernel");
+    }
     if (staged) {
       scf::corr_lookup_l4r4_smem_kernel<<<scf::cdiv(p.nq, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(p);
       return scf::check_launch("corr_lookup_l4r4_smem_kernel");

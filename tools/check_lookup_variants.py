@@ -16,11 +16,11 @@ if len(sys.argv) > 1:
     torch.save(out.cpu(), sys.argv[1])
 else:
     outs = []
-    for v in ('0', '1'):
+    for v in ('0', '1', '2'):
         path = f'/tmp/lookup_{v}.pt'
         subprocess.check_call([sys.executable, __file__, path], env=dict(os.environ, SCFLOW_LOOKUP_SMEM=v))
         import torch
         outs.append(torch.load(path))
-    same = torch.equal(outs[0], outs[1])
-    print('staged lookup == direct lookup bit for bit:', same, tuple(outs[0].shape), float(outs[0].abs().sum()))
+    same = torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    print('direct == staged == lean lookup bit for bit:', same, tuple(outs[0].shape), float(outs[0].abs().sum()))
     sys.exit(0 if same else 1)
