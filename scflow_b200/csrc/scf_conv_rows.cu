@@ -16,8 +16,9 @@
 //   * all 9 taps of the weights (2 planes x 72 KB) stay resident in shared memory for the CTA's lifetime; a CTA owns a
 //     contiguous range of (image, column strip, row) units, re-reading one halo row at each end of a range;
 //   * epilogue: eight warps, one thread per (pixel, 32-channel half) reads its channels from the finished slot, adds bias (+ residual), optional ReLU,
-//     writes fp32 and / or split-bf16 NHWC with 32 B vector stores and (InstanceNorm) the per-(row, warp) partial sums of the
-//     output and its square through a 31-shuffle transpose-reduce - deterministic, no atomics.
+//     writes fp32 and / or split-bf16 NHWC with 32 B vector stores; (InstanceNorm) the sums of the output and of its square stay in
+//     registers per pixel column and leave once per CTA segment through a 31-shuffle transpose-reduce - a few rows of partial
+//     sums per image, deterministic, no atomics.
 #include "scf_common.cuh"
 #include "scf_tc.cuh"
 #include <mutex>
@@ -43,13 +44,15 @@ constexpr int CR_SMEM = 1024 + 1024 + (int)CR_WBYTES + CR_ASTAGES * (int)CR_ASTA
 static_assert(CR_SMEM <= 232448, "conv_rows_kernel does not fit in shared memory");
 
 struct RowsParams {
-  int N, H, W, TX;                 // images, map size, 128-pixel column strips per row
+  int N, H, W, TX;                 // images, OUTPUT map size, 128-pixel column strips per row
+  int Hin;                         // stem kernel only: input rows (H = Hin / 2 output rows)
   long long U;                     // work units = N * TX * H output rows of one strip
   const float* bias; int relu;
   float* out_f32; int of_stride, of_coff;
   __nv_bfloat16* out_hl; long long oh_plane; int oh_stride, oh_coff;
   const float* res; int res_stride;
-  float* stats; int stat_rows;     // rows of [2][64] partial sums per image: (y * TX + xt) * 4 + warp
+  float* stats; int stat_rows;     // rows of [2][64] partial sums per image: (xt * stat_k + segment ordinal) * 4 + warp; zeroed by the launcher
+  int stat_k;                      // upper bound of the CTA segments that can touch one (image, strip)
   int al32;                        // 32 B vector accesses allowed: bit 0 fp32 output, bit 1 split output, bit 2 residual input
   int dbg;                         // timing experiments (SCFLOW_ROWS_DBG): 1 no MMAs, 2 no global stores, 4 no activation loads
 };
@@ -85,6 +88,123 @@ __device__ __forceinline__ float transpose_reduce32_rows(float (&acc)[32], int l
     }
   }
   return acc[0];
+}
+
+// Epilogue of one finished output row: thread = (pixel of the 128-pixel strip, 32-channel half h); `sq` = the row's sequence number
+// in this CTA (TMEM slot sq & 7).  bias (+ residual) (+ ReLU) -> fp32 and / or split-bf16 NHWC, optional InstanceNorm partial sums.
+template <bool RES, bool STATS>
+__device__ __forceinline__ void rows_epilogue_row(const RowsParams& p, uint32_t tmem_base, uint32_t bar_tfull, uint32_t bar_tempty,
+                                            uint32_t bias_s, uint32_t sq, int img, int xt, int y, int q, int h, int lane,
+                                            float (&acc1)[STATS ? 32 : 1], float (&acc2)[STATS ? 32 : 1]) {
+  const uint32_t slot = sq & 7u;
+  const int x = xt * CR_M + q * 32 + lane;
+  const bool valid = x < p.W;
+  const long long pix = ((long long)img * p.H + y) * p.W + x;
+  float4 rs[RES ? 8 : 1];
+  if (RES) {
+    const float* rp = p.res + pix * p.res_stride + h * 32;
+    if (!valid) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (p.al32 & 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        asm volatile("ld.global.cs.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=f"(rs[2 * j].x), "=f"(rs[2 * j].y), "=f"(rs[2 * j].z), "=f"(rs[2 * j].w), "=f"(rs[2 * j + 1].x), "=f"(rs[2 * j + 1].y),
+                       "=f"(rs[2 * j + 1].z), "=f"(rs[2 * j + 1].w)
+                     : "l"(rp + 8 * j));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rs[j] = __ldcs(reinterpret_cast<const float4*>(rp) + j);
+    }
+  }
+  mbar_wait(bar_tfull + 8 * slot, (sq >> 3) & 1u);
+  tc_fence_after();
+  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 64u;
+  {
+    float v[32];
+    tmem_ld32(taddr + (uint32_t)(h * 32), v);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_s + (uint32_t)(h * 128 + j * 16)));
+      v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      if (RES) { v[4 * j] += rs[j].x; v[4 * j + 1] += rs[j].y; v[4 * j + 2] += rs[j].z; v[4 * j + 3] += rs[j].w; }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (valid && !(p.dbg & 2)) {
+      if (p.out_f32) {
+        float* o = p.out_f32 + pix * p.of_stride + p.of_coff + h * 32;
+        if (p.al32 & 1) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + 8 * j), "f"(v[8 * j]), "f"(v[8 * j + 1]),
+                         "f"(v[8 * j + 2]), "f"(v[8 * j + 3]), "f"(v[8 * j + 4]), "f"(v[8 * j + 5]), "f"(v[8 * j + 6]), "f"(v[8 * j + 7]) : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+      if (p.out_hl) {
+        uint32_t hw[16], lw[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(v[2 * j], h0, l0);
+          split_bf16(v[2 * j + 1], h1, l1);
+          hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        __nv_bfloat16* oh = p.out_hl + pix * p.oh_stride + p.oh_coff + h * 32;
+        __nv_bfloat16* ol = oh + p.oh_plane;
+        if (p.al32 & 2) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(oh + 16 * j), "r"(hw[8 * j]), "r"(hw[8 * j + 1]),
+                         "r"(hw[8 * j + 2]), "r"(hw[8 * j + 3]), "r"(hw[8 * j + 4]), "r"(hw[8 * j + 5]), "r"(hw[8 * j + 6]), "r"(hw[8 * j + 7]) : "memory");
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ol + 16 * j), "r"(lw[8 * j]), "r"(lw[8 * j + 1]),
+                         "r"(lw[8 * j + 2]), "r"(lw[8 * j + 3]), "r"(lw[8 * j + 4]), "r"(lw[8 * j + 5]), "r"(lw[8 * j + 6]), "r"(lw[8 * j + 7]) : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            reinterpret_cast<uint4*>(oh)[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+            reinterpret_cast<uint4*>(ol)[j] = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+          }
+        }
+      }
+    }
+    if (STATS) {
+      // InstanceNorm partial sums stay in registers (this thread's pixel column, 32 channels) until the CTA's segment ends
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float t = valid ? v[i] : 0.f;
+        acc1[i] += t;
+        acc2[i] = fmaf(t, t, acc2[i]);
+      }
+    }
+  }
+}
+
+// End of a CTA segment (consecutive output rows of one image strip): the warp's per-pixel-column sums are reduced across its 32
+// pixels (31-shuffle transpose-reduce) and written as ONE row of partial sums per (segment, warp): a handful of rows per image
+// instead of four per output row, deterministic.  ordinal = this CTA's rank among the CTAs that share the strip.
+__device__ __forceinline__ void rows_stats_flush(const RowsParams& p, int img, int xt, int strip, int q, int h, int lane, float (&acc1)[32],
+                                                 float (&acc2)[32]) {
+  const int first = (int)((((long long)strip * p.H + 1) * gridDim.x - 1) / p.U);        // CTA that owns the strip's first unit
+  const int ordinal = (int)blockIdx.x - first;
+  const float m1 = transpose_reduce32_rows(acc1, lane), m2 = transpose_reduce32_rows(acc2, lane);
+  float* o = p.stats + (((long long)img * p.stat_rows + (long long)(xt * p.stat_k + ordinal) * 4 + q) * 2) * CR_C + h * 32 + lane;
+  o[0] = m1;
+  o[CR_C] = m2;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
 }
 
 template <int MODE>       // bit 0: residual input, bit 1: InstanceNorm partial sums
@@ -209,102 +329,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * (uint32_t)et), "f"(b) : "memory");
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * CR_EW) : "memory");
+    float acc1[STATS ? 32 : 1], acc2[STATS ? 32 : 1];
+#pragma unroll
+    for (int i = 0; i < (STATS ? 32 : 1); ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
     rows_for_each_step(p, [&](int img, int xt, int r, int y0, int y1, uint32_t seq) {
       auto do_row = [&](int y) {
-        const uint32_t sq = seq + (uint32_t)(y - y0), slot = sq & 7u;
-        const int x = xt * CR_M + q * 32 + lane;
-        const bool valid = x < p.W;
-        const long long pix = ((long long)img * p.H + y) * p.W + x;
-        float4 rs[RES ? 8 : 1];
-        if (RES) {
-          const float* rp = p.res + pix * p.res_stride + h * 32;
-          if (!valid) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          } else if (p.al32 & 4) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              asm volatile("ld.global.cs.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                           : "=f"(rs[2 * j].x), "=f"(rs[2 * j].y), "=f"(rs[2 * j].z), "=f"(rs[2 * j].w), "=f"(rs[2 * j + 1].x), "=f"(rs[2 * j + 1].y),
-                             "=f"(rs[2 * j + 1].z), "=f"(rs[2 * j + 1].w)
-                           : "l"(rp + 8 * j));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rs[j] = __ldcs(reinterpret_cast<const float4*>(rp) + j);
-          }
-        }
-        mbar_wait(bar_tfull + 8 * slot, (sq >> 3) & 1u);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 64u;
-        {
-          float v[32];
-          tmem_ld32(taddr + (uint32_t)(h * 32), v);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 b;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_s + (uint32_t)(h * 128 + j * 16)));
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            if (RES) { v[4 * j] += rs[j].x; v[4 * j + 1] += rs[j].y; v[4 * j + 2] += rs[j].z; v[4 * j + 3] += rs[j].w; }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (valid && !(p.dbg & 2)) {
-            if (p.out_f32) {
-              float* o = p.out_f32 + pix * p.of_stride + p.of_coff + h * 32;
-              if (p.al32 & 1) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + 8 * j), "f"(v[8 * j]), "f"(v[8 * j + 1]),
-                               "f"(v[8 * j + 2]), "f"(v[8 * j + 3]), "f"(v[8 * j + 4]), "f"(v[8 * j + 5]), "f"(v[8 * j + 6]), "f"(v[8 * j + 7]) : "memory");
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              }
-            }
-            if (p.out_hl) {
-              uint32_t hw[16], lw[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(v[2 * j], h0, l0);
-                split_bf16(v[2 * j + 1], h1, l1);
-                hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-              }
-              __nv_bfloat16* oh = p.out_hl + pix * p.oh_stride + p.oh_coff + h * 32;
-              __nv_bfloat16* ol = oh + p.oh_plane;
-              if (p.al32 & 2) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(oh + 16 * j), "r"(hw[8 * j]), "r"(hw[8 * j + 1]),
-                               "r"(hw[8 * j + 2]), "r"(hw[8 * j + 3]), "r"(hw[8 * j + 4]), "r"(hw[8 * j + 5]), "r"(hw[8 * j + 6]), "r"(hw[8 * j + 7]) : "memory");
-                  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ol + 16 * j), "r"(lw[8 * j]), "r"(lw[8 * j + 1]),
-                               "r"(lw[8 * j + 2]), "r"(lw[8 * j + 3]), "r"(lw[8 * j + 4]), "r"(lw[8 * j + 5]), "r"(lw[8 * j + 6]), "r"(lw[8 * j + 7]) : "memory");
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  reinterpret_cast<uint4*>(oh)[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
-                  reinterpret_cast<uint4*>(ol)[j] = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
-                }
-              }
-            }
-          }
-          if (STATS) {
-            float s2[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; s2[i] = v[i] * v[i]; }
-            const float m1 = transpose_reduce32_rows(v, lane), m2 = transpose_reduce32_rows(s2, lane);
-            float* o = p.stats + (((long long)img * p.stat_rows + (long long)(y * p.TX + xt) * 4 + q) * 2) * CR_C + h * 32 + lane;
-            o[0] = m1;
-            o[CR_C] = m2;
-          }
-        }
+        rows_epilogue_row<RES, STATS>(p, tmem_base, bar_tfull, bar_tempty, bias_s, seq + (uint32_t)(y - y0), img, xt, y, q, h, lane, acc1, acc2);
+        if constexpr (STATS) { if (y == y1 - 1) rows_stats_flush(p, img, xt, img * p.TX + xt, q, h, lane, acc1, acc2); }
       };
       const int lo = r - 1 > y0 ? r - 1 : y0;
       if (lo == r - 1) do_row(r - 1);
@@ -314,6 +345,260 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// The encoders' stem (resnet.py / raft_encoder.py: 7x7 stride-2 convolution 3 -> 64) in the same rolling-rows form.  Its input is
+// the x-folded image (im2col along x: 7 taps x 3 channels = 21 -> 32 channels per OUTPUT column), so what remains is a 7x1
+// convolution with vertical stride 2:  out[y] = sum_ky W7[ky] . in[2y + ky - 3].  Input row r therefore feeds the output rows
+// y = (r + 3 - ky) / 2 for the ky of r's parity class: even rows three of them (ky = 5, 3, 1), odd rows four (ky = 6, 4, 2, 0) - again
+// consecutive output rows = consecutive TMEM slots, so ONE MMA per product of N = 192 / 256 over a per-parity weight stack replaces
+// 3 / 4 MMAs of N = 64: 12 MMAs per output row instead of 42.  K = 32 per row (two k-steps), tiles are 128 pixels x 64 B
+// (SWIZZLE_64B), four 16 KB stages.  The kernel is bound by its epilogue (32 KB of fp32 output per row), which it shares with the
+// 3x3 kernel above.
+constexpr int CS_ASTAGES = 4;
+constexpr uint32_t CS_APLANE = CR_M * 64u, CS_ASTAGE = 2 * CS_APLANE;             // 8 KB per plane
+constexpr uint32_t CS_WBLK = CR_C * 64u;                                          // one tap, one plane: 64 rows x 64 B
+constexpr uint32_t CS_WODD = 0, CS_WEVEN = 4 * CS_WBLK, CS_WPLANE = 7 * CS_WBLK;   // [ky6|ky4|ky2|ky0] then [ky5|ky3|ky1]
+constexpr uint32_t CS_WBYTES = 2 * CS_WPLANE;                                     // 56 KB
+constexpr int CS_SMEM = 1024 + 1024 + (int)CS_WBYTES + CS_ASTAGES * (int)CS_ASTAGE;
+
+// schedule of the stem: a segment with output rows [y0, y1) consumes input rows max(2*y0 - 3, 0) .. min(2*(y1-1) + 3, Hin - 1)
+template <class F>
+__device__ __forceinline__ void stem_for_each_step(const RowsParams& p, F&& f) {
+  long long u = p.U * blockIdx.x / gridDim.x;
+  const long long u1 = p.U * (blockIdx.x + 1) / gridDim.x;
+  uint32_t seq = 0;
+  while (u < u1) {
+    const int strip = (int)(u / p.H), y0 = (int)(u - (long long)strip * p.H);
+    const int y1 = (u1 - u) < (long long)(p.H - y0) ? y0 + (int)(u1 - u) : p.H;
+    const int img = strip / p.TX, xt = strip - img * p.TX;
+    const int r0 = 2 * y0 - 3 > 0 ? 2 * y0 - 3 : 0, r1 = 2 * (y1 - 1) + 3 < p.Hin - 1 ? 2 * (y1 - 1) + 3 : p.Hin - 1;
+    for (int r = r0; r <= r1; ++r) {
+      const int m = r >> 1;                                    // window of output rows: m-1 .. m+1 (even r) / m+2 (odd r)
+      const int lo = m - 1 > y0 ? m - 1 : y0, top = m + 1 + (r & 1), hi = top < y1 - 1 ? top : y1 - 1;
+      if (lo <= hi) f(img, xt, r, y0, y1, lo, hi, seq);
+    }
+    seq += (uint32_t)(y1 - y0);
+    u += y1 - y0;
+  }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(64 + 32 * CR_EW, 1)
+conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const RowsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = sb, bar_empty = sb + 32, bar_w = sb + 64, bar_tfull = sb + 128, bar_tempty = sb + 192, tmem_slot = sb + 72,
+                 bias_s = sb + 256;
+  const uint32_t w0 = sb + 1024, a0 = w0 + CS_WBYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  griddep_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmW);
+    for (int s = 0; s < CS_ASTAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < CR_SLOTS; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, CR_EW); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  griddep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, CS_WBYTES);
+      for (int pl = 0; pl < 2; ++pl)
+        for (int ky = 0; ky < 7; ++ky) {
+          const uint32_t blk = (ky & 1) ? CS_WEVEN + (uint32_t)((5 - ky) >> 1) * CS_WBLK : CS_WODD + (uint32_t)((6 - ky) >> 1) * CS_WBLK;
+          tma_load_4d(w0 + pl * CS_WPLANE + blk, &tmW, bar_w, 0, 0, ky, pl);
+        }
+      int stage = 0;
+      uint32_t phase = 0;
+      stem_for_each_step(p, [&](int img, int xt, int r, int, int, int, int, uint32_t) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+        const uint32_t full = bar_full + 8 * stage, dst = a0 + stage * CS_ASTAGE;
+        if (p.dbg & 4) mbar_arrive(full);
+        else {
+          mbar_arrive_expect_tx(full, CS_ASTAGE);
+          tma_load_5d(dst, &tmA, full, 0, xt * CR_M, r, img, 0);
+          tma_load_5d(dst + CS_APLANE, &tmA, full, 0, xt * CR_M, r, img, 1);
+        }
+        if (++stage == CS_ASTAGES) { stage = 0; phase ^= 1u; }
+      });
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id1 = make_idesc_bf16(CR_M, 64), id2 = make_idesc_bf16(CR_M, 128), id3 = make_idesc_bf16(CR_M, 192), id4 = make_idesc_bf16(CR_M, 256);
+      auto idesc_of = [&](int n) { return n == 4 ? id4 : n == 3 ? id3 : n == 2 ? id2 : id1; };
+      int stage = 0;
+      uint32_t phase = 0;
+      mbar_wait(bar_w, 0);
+      tc_fence_after();
+      stem_for_each_step(p, [&](int, int, int r, int y0, int, int lo, int hi, uint32_t seq) {
+        const int m = r >> 1, n = hi - lo + 1;
+        // rows opened by this input row: y with 2y - 3 == r (odd r: the window's top row), and every row when r == 0
+        const int n_fresh = r == 0 ? n : ((r & 1) && hi == m + 2 ? 1 : 0);
+        for (int y = hi - n_fresh + 1; y <= hi; ++y) {
+          const uint32_t sq = seq + (uint32_t)(y - y0);
+          mbar_wait(bar_tempty + 8 * (sq & 7u), ((sq >> 3) & 1u) ^ 1u);
+        }
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        const int sa = (int)((seq + (uint32_t)(lo - y0)) & 7u);
+        const int n1 = n < CR_SLOTS - sa ? n : CR_SLOTS - sa, n2 = n - n1;
+        const uint32_t d1 = tmem_base + (uint32_t)(sa * 64), d2 = tmem_base;
+        const uint32_t at = a0 + stage * CS_ASTAGE;
+        const uint64_t a_hi0 = make_smem_desc_sw64(at, 512), a_lo0 = make_smem_desc_sw64(at + CS_APLANE, 512);
+        // weight block of row lo inside this parity's stack: blocks are ordered by ascending output row (descending ky)
+        const uint32_t wrow = w0 + ((r & 1) ? CS_WODD : CS_WEVEN) + (uint32_t)(lo - (m - 1)) * CS_WBLK;
+        const uint64_t b1_hi0 = make_smem_desc_sw64(wrow, 512), b1_lo0 = make_smem_desc_sw64(wrow + CS_WPLANE, 512);
+        const uint64_t bo2 = (uint64_t)(((uint32_t)n1 * CS_WBLK) >> 4);
+        const uint32_t in1 = idesc_of(n1), in2 = idesc_of(n2);
+        if (!(p.dbg & 1)) {
+          if (n_fresh == 0) {
+            umma_bf16(d1, a_hi0, b1_hi0, in1, 1u);
+            if (n2) umma_bf16(d2, a_hi0, b1_hi0 + bo2, in2, 1u);
+          } else {
+            for (int y = lo; y <= hi; ++y) {        // first product row by row: fresh rows start from zero
+              const uint32_t sl = (seq + (uint32_t)(y - y0)) & 7u;
+              umma_bf16(tmem_base + sl * 64u, a_hi0, b1_hi0 + (uint64_t)(((uint32_t)(y - lo) * CS_WBLK) >> 4), id1, y > hi - n_fresh ? 0u : 1u);
+            }
+          }
+          umma_bf16(d1, a_hi0, b1_lo0, in1, 1u);
+          umma_bf16(d1, a_lo0, b1_hi0, in1, 1u);
+          if (n2) { umma_bf16(d2, a_hi0, b1_lo0 + bo2, in2, 1u); umma_bf16(d2, a_lo0, b1_hi0 + bo2, in2, 1u); }
+          const uint64_t ko = (uint64_t)(32 >> 4);            // second k-step: channels 16..31
+          umma_bf16(d1, a_hi0 + ko, b1_hi0 + ko, in1, 1u);
+          umma_bf16(d1, a_hi0 + ko, b1_lo0 + ko, in1, 1u);
+          umma_bf16(d1, a_lo0 + ko, b1_hi0 + ko, in1, 1u);
+          if (n2) {
+            umma_bf16(d2, a_hi0 + ko, b1_hi0 + bo2 + ko, in2, 1u);
+            umma_bf16(d2, a_hi0 + ko, b1_lo0 + bo2 + ko, in2, 1u);
+            umma_bf16(d2, a_lo0 + ko, b1_hi0 + bo2 + ko, in2, 1u);
+          }
+        }
+        umma_commit(bar_empty + 8 * stage);
+        if (++stage == CS_ASTAGES) { stage = 0; phase ^= 1u; }
+        // finished rows: 2y + 3 == r, and at the last input row every row still open
+        for (int y = lo; y <= hi; ++y)
+          if (2 * y + 3 == r || r == p.Hin - 1) umma_commit(bar_tfull + 8 * ((seq + (uint32_t)(y - y0)) & 7u));
+      });
+    }
+  } else {
+    const int q = warp & 3, h = (warp - 2) >> 2, et = (int)threadIdx.x - 64;
+    if (et < CR_C) {
+      const float b = p.bias ? __ldg(p.bias + et) : 0.f;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * (uint32_t)et), "f"(b) : "memory");
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * CR_EW) : "memory");
+    float acc1[STATS ? 32 : 1], acc2[STATS ? 32 : 1];
+#pragma unroll
+    for (int i = 0; i < (STATS ? 32 : 1); ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
+    stem_for_each_step(p, [&](int img, int xt, int r, int y0, int y1, int lo, int hi, uint32_t seq) {
+      for (int y = lo; y <= hi; ++y)
+        if (2 * y + 3 == r || r == p.Hin - 1) {
+          rows_epilogue_row<false, STATS>(p, tmem_base, bar_tfull, bar_tempty, bias_s, seq + (uint32_t)(y - y0), img, xt, y, q, h, lane, acc1, acc2);
+          if constexpr (STATS) { if (y == y1 - 1) rows_stats_flush(p, img, xt, img * p.TX + xt, q, h, lane, acc1, acc2); }
+        }
+    });
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
+// 7x1 kernel, vertical stride 2, 32 (x-folded) input channels -> 64: the encoders' stem after im2col_x_split
+bool conv2d_stem_rows_eligible(const scf_tc_conv_desc& d) {
+  const char* e = getenv("SCFLOW_TC_ROWS");
+  if (e && atoi(e) == 0) return false;
+  const char* se = getenv("SCFLOW_TC_ROWS_STEM");
+  if (se && atoi(se) == 0) return false;
+  const int sx = d.stride_x ? d.stride_x : (d.stride == 2 ? 2 : 1), sy = d.stride_y ? d.stride_y : (d.stride == 2 ? 2 : 1);
+  if (d.kh != 7 || d.kw != 1 || sx != 1 || sy != 2 || d.nseg != 1 || d.seg[0].nch != 32 || d.cin_pad != 32 || d.cout != CR_C ||
+      d.cout_pad != CR_C || d.w_batched || d.ksplit > 1 || d.w_plane_stride != 0)
+    return false;
+  if (d.epi != SCF_EPI_ACT || (d.act != SCF_ACT_NONE && d.act != SCF_ACT_RELU) || d.pre || d.aux0 || d.aux1 || d.out2_hl || d.scale != 1.f) return false;
+  if (d.H % 2 || d.H < 8 || d.W < 96 || (long long)d.B * (d.H / 2) * cdiv(d.W, CR_M) < 148) return false;
+  auto al16 = [](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0; };
+  if (!al16(d.seg[0].ptr) || d.seg[0].stride % 8 || d.seg[0].coff % 8 || (d.seg[0].plane_stride * 2) % 16) return false;
+  if (d.out_f32 && (!al16(d.out_f32) || d.out_f32_stride % 4 || d.out_f32_coff % 4)) return false;
+  if (d.out_hl && (!al16(d.out_hl) || d.out_hl_stride % 8 || d.out_hl_coff % 8 || (d.out_hl_plane * 2) % 16)) return false;
+  return true;
+}
+
+int conv2d_stem_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
+  RowsParams p = {};
+  p.N = d.B; p.Hin = d.H; p.H = d.H / 2; p.W = d.W; p.TX = cdiv(d.W, CR_M);
+  p.U = (long long)d.B * p.TX * p.H;
+  p.bias = d.bias; p.relu = d.act == SCF_ACT_RELU ? 1 : 0;
+  p.out_f32 = d.out_f32; p.of_stride = d.out_f32_stride; p.of_coff = d.out_f32_coff;
+  p.out_hl = reinterpret_cast<__nv_bfloat16*>(d.out_hl); p.oh_plane = d.out_hl_plane; p.oh_stride = d.out_hl_stride; p.oh_coff = d.out_hl_coff;
+  p.stats = d.stats;
+  {
+    auto al32 = [](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % 32 == 0; };
+    if (d.out_f32 && al32(d.out_f32) && d.out_f32_stride % 8 == 0 && d.out_f32_coff % 8 == 0) p.al32 |= 1;
+    if (d.out_hl && al32(d.out_hl) && d.out_hl_stride % 16 == 0 && d.out_hl_coff % 16 == 0 && (d.out_hl_plane * 2) % 32 == 0) p.al32 |= 2;
+    const char* de = getenv("SCFLOW_ROWS_DBG");
+    p.dbg = de ? atoi(de) : 0;
+  }
+  CUtensorMap tmA, tmW;
+  {
+    const scf_tc_seg& sg = d.seg[0];
+    const char* base = reinterpret_cast<const char*>(sg.ptr) + (size_t)sg.coff * 2;
+    cuuint64_t dims[5] = {32, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B, 2};
+    cuuint64_t str[4] = {(cuuint64_t)sg.stride * 2, (cuuint64_t)d.W * sg.stride * 2, (cuuint64_t)d.H * d.W * sg.stride * 2,
+                         (cuuint64_t)sg.plane_stride * 2};
+    cuuint32_t box[5] = {32, (cuuint32_t)CR_M, 1, 1, 1};
+    SCF_TRY(encode_map(&tmA, base, 5, dims, str, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B));
+    cuuint64_t wd[4] = {32, (cuuint64_t)CR_C, 7, 2};
+    cuuint64_t ws[3] = {32 * 2, (cuuint64_t)CR_C * 32 * 2, (cuuint64_t)7 * CR_C * 32 * 2};
+    cuuint32_t wb[4] = {32, (cuuint32_t)CR_C, 1, 1};
+    SCF_REQUIRE(reinterpret_cast<uintptr_t>(d.w) % 16 == 0, SCF_ERR_ALIGN, "scf_conv2d_tc: packed weight must be 16B aligned");
+    SCF_TRY(encode_map(&tmW, d.w, 4, wd, ws, wb, nullptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B));
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    SCF_CUDA(cudaGetDevice(&dev));
+    SCF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_stem_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_stem_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM);
+  });
+  SCF_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "cudaFuncSetAttribute(conv_stem_rows_kernel): %s", cudaGetErrorString(attr_err));
+  const unsigned grid = (unsigned)(p.U < num_sms ? p.U : num_sms);
+  {
+    // a strip's H units are shared by at most ceil(H / floor(U / grid)) + 1 consecutive CTAs (never more than H)
+    const int upc = (int)(p.U / grid), k = cdiv(p.H, upc) + 1;
+    p.stat_k = k < p.H ? k : p.H;
+    p.stat_rows = p.TX * p.stat_k * 4;
+    if (p.stats) SCF_CUDA(cudaMemsetAsync(p.stats, 0, (size_t)p.N * p.stat_rows * 2 * CR_C * sizeof(float), st));
+  }
+  g_last_m_tiles = (int)p.U; g_last_tiles_per_img = p.TX * p.H; g_last_stat_rows_per_img = p.stat_rows;
+  static const bool pdl = [] { const char* e = getenv("SCFLOW_PDL"); return e ? atoi(e) != 0 : true; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * CR_EW);
+  cfg.dynamicSmemBytes = CS_SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  cudaError_t le = d.stats ? cudaLaunchKernelEx(&cfg, conv_stem_rows_kernel<true>, tmA, tmW, p)
+                           : cudaLaunchKernelEx(&cfg, conv_stem_rows_kernel<false>, tmA, tmW, p);
+  if (le != cudaSuccess) { cudaGetLastError(); set_error("conv_stem_rows_kernel launch: %s", cudaGetErrorString(le)); g_launches++; return (int)le; }
+  return check_launch("conv_stem_rows_kernel");
 }
 
 // SCFLOW_TC_ROWS (default 1): 3x3 / stride 1 / 64 -> 64 channel layers on maps at least 96 pixels wide take this kernel
@@ -342,7 +627,7 @@ int conv2d_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.out_f32 = d.out_f32; p.of_stride = d.out_f32_stride; p.of_coff = d.out_f32_coff;
   p.out_hl = reinterpret_cast<__nv_bfloat16*>(d.out_hl); p.oh_plane = d.out_hl_plane; p.oh_stride = d.out_hl_stride; p.oh_coff = d.out_hl_coff;
   p.res = d.aux0; p.res_stride = d.aux0_stride;
-  p.stats = d.stats; p.stat_rows = d.H * p.TX * 4;
+  p.stats = d.stats;
   {
     auto al32 = [](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % 32 == 0; };
     if (d.out_f32 && al32(d.out_f32) && d.out_f32_stride % 8 == 0 && d.out_f32_coff % 8 == 0) p.al32 |= 1;
@@ -381,10 +666,18 @@ int conv2d_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
       attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM);
   });
   SCF_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "cudaFuncSetAttribute(conv_rows_kernel): %s", cudaGetErrorString(attr_err));
+  const unsigned grid = (unsigned)(p.U < num_sms ? p.U : num_sms);
+  {
+    // a strip's H units are shared by at most ceil(H / floor(U / grid)) + 1 consecutive CTAs (never more than H)
+    const int upc = (int)(p.U / grid), k = cdiv(p.H, upc) + 1;
+    p.stat_k = k < p.H ? k : p.H;
+    p.stat_rows = p.TX * p.stat_k * 4;
+    if (p.stats) SCF_CUDA(cudaMemsetAsync(p.stats, 0, (size_t)p.N * p.stat_rows * 2 * CR_C * sizeof(float), st));
+  }
   g_last_m_tiles = (int)p.U; g_last_tiles_per_img = p.TX * d.H; g_last_stat_rows_per_img = p.stat_rows;
   static const bool pdl = [] { const char* e = getenv("SCFLOW_PDL"); return e ? atoi(e) != 0 : true; }();
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(p.U < num_sms ? p.U : num_sms)); cfg.blockDim = dim3(64 + 32 * CR_EW);
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * CR_EW);
   cfg.dynamicSmemBytes = CR_SMEM; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   int na = 0;

@@ -1713,6 +1713,8 @@ static int conv2d_tct(const scf_tc_conv_desc& d, cudaStream_t st) {
 
 bool conv2d_rows_eligible(const scf_tc_conv_desc& d);
 int conv2d_rows(const scf_tc_conv_desc& d, cudaStream_t st);
+bool conv2d_stem_rows_eligible(const scf_tc_conv_desc& d);
+int conv2d_stem_rows(const scf_tc_conv_desc& d, cudaStream_t st);
 
 int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
   SCF_REQUIRE(d.nseg >= 1 && d.nseg <= 3, SCF_ERR_ARG, "scf_conv2d_tc: nseg must be 1..3");
@@ -1746,6 +1748,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
     SCF_REQUIRE(d.cout % 32 == 0 && d.out_f32 && d.epi == SCF_EPI_ACT && reinterpret_cast<uintptr_t>(d.stats) % 16 == 0,
                 SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: stats need an fp32 output, cout %% 32 == 0 and the plain epilogue");
   if (conv2d_rows_eligible(d)) return conv2d_rows(d, st);
+  if (conv2d_stem_rows_eligible(d)) return conv2d_stem_rows(d, st);
   if (d.ksplit <= 1 && tct_eligible(d)) return conv2d_tct(d, st);
   TcParams p = {};
   p.nseg = d.nseg;

@@ -218,3 +218,44 @@ def test_conv_rows_kernel_matches_fp64_and_generic_tile(S, monkeypatch, hw, b, r
         outs[mode] = got
     # same products, different summation order inside the fp32 accumulator
     assert float((outs['1'] - outs['0']).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize('hw,b,stats,act', [((256, 128), 2, True, 'none'), ((96, 160), 2, False, 'relu'), ((30, 128), 11, True, 'none')])
+def test_conv_stem_rows_kernel_matches_fp64_and_generic_tile(S, monkeypatch, hw, b, stats, act):
+    """The encoders' stem after the x-fold (7x1 kernel, vertical stride 2, 32 -> 64 channels) on the rolling-rows kernel
+    (conv_stem_rows_kernel) against an fp64 convolution and the generic tile (SCFLOW_TC_ROWS=0)."""
+    cin, cout = 32, 64
+    gen = torch.Generator().manual_seed(hw[0] + 7 * hw[1] + b)
+    x = torch.randn(b, cin, *hw, generator=gen)
+    w = torch.randn(cout, cin, 7, 1, generator=gen) / math.sqrt(cin * 7)
+    bias = 0.1 * torch.randn(cout, generator=gen)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), stride=(2, 1), padding=(3, 0))
+    if act == 'relu':
+        ref = torch.relu(ref)
+    ref = ref.float()
+    ho, wo = ref.shape[-2:]
+    xs = S.ops.split_nchw(x.cuda())
+    pw = S.ops.pack_conv_weight_tc([w.cuda()])
+    n_tiles, _ = S.ops.conv2d_tc_tiles(b, ho, wo)
+    outs = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('SCFLOW_TC_ROWS', mode)
+        out_f32 = torch.full((b, ho, wo, cout), 7.0, device='cuda')
+        out_hl = torch.full((2, b, ho, wo, cout), 7.0, device='cuda', dtype=torch.bfloat16)
+        st = torch.zeros(n_tiles * 4 * 2 * cout, device='cuda') if stats else None
+        S.ops.conv2d_tc([(xs, 0, cin)], pw, bias.cuda(), cout, (7, 1), act=act, out_f32=out_f32, out_hl=None if stats else out_hl,
+                        stride_xy=(1, 2), stats=st)
+        torch.cuda.synchronize()
+        got = out_f32.permute(0, 3, 1, 2).cpu()
+        err = float((got - ref).abs().max())
+        print(f'stem rows={mode} hw={hw} b={b}: max err f32 {err:.3e}')
+        assert err < 5e-5
+        if not stats:
+            assert float((S.ops.unsplit(out_hl).cpu() - ref).abs().max()) < 1e-4
+        else:
+            rows = st.view(-1, 2, cout).double().sum(0).cpu()
+            own = out_f32.double().cpu()
+            assert float((rows[0] - own.sum((0, 1, 2))).abs().max()) < 1e-3
+            assert float((rows[1] - own.pow(2).sum((0, 1, 2))).abs().max()) < 1e-3
+        outs[mode] = got
+    assert float((outs['1'] - outs['0']).abs().max()) < 2e-5
