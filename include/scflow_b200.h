@@ -231,9 +231,12 @@ int scf_linear(const float* x, const float* w, const float* bias, float* y, int 
  * [ks*KR, (ks+1)*KR) and writes RAW partial sums part[ks][b][o] (fp32, I/KR maps of B*O floats); the consumer adds the maps, this
  * layer's bias and activation.  The layer's own input may itself be such a stack of partial maps: x = act(sum_s x[s*x_split_stride
  * + b*I + i] + x_bias[i]) with x_nsplit maps, x_relu != 0 for ReLU (x_nsplit = 1, x_bias = NULL, x_relu = 0: plain input).
- * w_packed: scf_pack_conv_weight_tc(w, ., O, I, 1, 1, I, O, 0) = split-bf16 [2][O][I].  KR: multiple of 64, <= 256, divides I. */
+ * w_packed: scf_pack_conv_weight_tc(w, ., O, I, 1, 1, I, O, 0) = split-bf16 [2][O][I].  KR: multiple of 64, <= 256, divides I.
+ * y != NULL (needs I / KR == 8): the eight K-range blocks of a row tile run as one thread-block cluster and reduce their partial
+ * tiles through distributed shared memory in fixed order: y[b][o] = act(W x + bias) (relu != 0: ReLU) is written directly and
+ * `part` is not used. */
 int scf_linear_tc(const float* x, int x_nsplit, long long x_split_stride, const float* x_bias, int x_relu, const void* w_packed,
-                  float* part, int B, int I, int O, int KR, void* stream);
+                  float* part, float* y, const float* bias, int relu, int B, int I, int O, int KR, void* stream);
 /* final pose projection with the reference's class selection: rows of class label[0] (device int64) only.
  * rot_w [rot_dim*num_class, I], tr_w [3*num_class, I]; outputs d_rot [B,rot_dim], d_trs [B,3]. num_class<=0: single-class head */
 int scf_pose_project(const float* x, const float* rot_w, const float* rot_b, const float* tr_w, const float* tr_b,

@@ -176,8 +176,8 @@ _SIGNATURES = {
     'scf_group_norm_relu_split': (C.c_int, [c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_void_p,
                                             C.c_longlong, c_void_p]),
     'scf_linear': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
-    'scf_linear_tc': (C.c_int, [c_void_p, C.c_int, C.c_longlong, c_void_p, C.c_int, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                c_void_p]),
+    'scf_linear_tc': (C.c_int, [c_void_p, C.c_int, C.c_longlong, c_void_p, C.c_int, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int,
+                                C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
     'scf_pose_project': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
     'scf_pose_update': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, c_void_p]),

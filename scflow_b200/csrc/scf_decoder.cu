@@ -28,7 +28,7 @@ bool lookup_conv_requested();
 int group_norm_relu_partials(float* x, int nsplit, long long split_stride, const float* gamma, const float* beta, int B, int HW, int C,
                              int num_groups, float eps, void* out_hl, long long plane_stride, cudaStream_t stream);
 int fc_tc(const float* x, int x_nsplit, long long x_split_stride, const float* x_bias, int x_relu, const void* w_packed, float* part,
-          int B, int I, int O, int KR, cudaStream_t st);
+          float* y, const float* bias, int relu, int B, int I, int O, int KR, cudaStream_t st);
 int pose_project_partials(const float* part, int nsplit, long long split_stride, const float* bias, const float* rot_w, const float* rot_b,
                           const float* tr_w, const float* tr_b, const int64_t* label, float* d_rot, float* d_trs, int B, int I,
                           int rot_dim, int num_class, cudaStream_t st);
@@ -778,12 +778,20 @@ int scf_decoder_forward(const scf_decoder_cfg* cfg, const void* packed, const sc
         // small batch: both FC layers on tcgen05, split-K over 8 blocks per 128 output rows; each consumer sums the producer's
         // partial maps and applies its bias / ReLU while it forms its own operand
         const char* pb = reinterpret_cast<const char*>(packed);
-        static const int kr0 = [] { const char* e = getenv("SCFLOW_FC_KR0"); const int v = e ? atoi(e) : 256; return v == 128 ? 128 : 256; }();
-        static const int kr1 = [] { const char* e = getenv("SCFLOW_FC_KR1"); const int v = e ? atoi(e) : 64; return v == 128 ? 128 : 64; }();
-        SCF_TRY(fc_tc(F(ws.p3), 1, 0, nullptr, 0, pb + a.fc_off[0], F(ws.fc0), B, 2048, 1024, kr0, st));
-        SCF_TRY(fc_tc(F(ws.fc0), 2048 / kr0, (long long)B * 1024, pw + a.fc0_b, 1, pb + a.fc_off[1], F(ws.fc1), B, 1024, 256, kr1, st));
-        SCF_TRY(pose_project_partials(F(ws.fc1), 1024 / kr1, (long long)B * 256, pw + a.fc1_b, pw + a.rot_w, pw + a.rot_b, pw + a.tr_w, pw + a.tr_b,
-                                      io->label, drot_k, dtrs_k, B, 256, cfg->rot_dim, cfg->num_class, st));
+        // SCFLOW_FC_REDUCE (default 1): each layer = one launch, the 8 K-range blocks of a row tile reduce in a cluster; 0: raw
+        // split-K partial maps that the consumer sums while it forms its operand
+        static const bool fc_reduce = [] { const char* e = getenv("SCFLOW_FC_REDUCE"); return e ? atoi(e) != 0 : true; }();
+        if (fc_reduce) {
+          SCF_TRY(fc_tc(F(ws.p3), 1, 0, nullptr, 0, pb + a.fc_off[0], nullptr, F(ws.fc0), pw + a.fc0_b, 1, B, 2048, 1024, 256, st));
+          SCF_TRY(fc_tc(F(ws.fc0), 1, 0, nullptr, 0, pb + a.fc_off[1], nullptr, F(ws.fc1), pw + a.fc1_b, 1, B, 1024, 256, 128, st));
+          SCF_TRY(scf_pose_project(F(ws.fc1), pw + a.rot_w, pw + a.rot_b, pw + a.tr_w, pw + a.tr_b, io->label, drot_k, dtrs_k, B,
+                                   256, cfg->rot_dim, cfg->num_class, st));
+        } else {
+          SCF_TRY(fc_tc(F(ws.p3), 1, 0, nullptr, 0, pb + a.fc_off[0], F(ws.fc0), nullptr, nullptr, 0, B, 2048, 1024, 256, st));
+          SCF_TRY(fc_tc(F(ws.fc0), 8, (long long)B * 1024, pw + a.fc0_b, 1, pb + a.fc_off[1], F(ws.fc1), nullptr, nullptr, 0, B, 1024, 256, 64, st));
+          SCF_TRY(pose_project_partials(F(ws.fc1), 16, (long long)B * 256, pw + a.fc1_b, pw + a.rot_w, pw + a.rot_b, pw + a.tr_w, pw + a.tr_b,
+                                        io->label, drot_k, dtrs_k, B, 256, cfg->rot_dim, cfg->num_class, st));
+        }
       } else if (fc_split && B <= 32) {
         // small batch: the FC layers as split-K weight streams over 4x more blocks, bias / ReLU applied by the consumer
         SCF_TRY(pose_fc_tail(F(ws.p3), pw + a.fc0_w, pw + a.fc0_b, 2048, 1024, pw + a.fc1_w, pw + a.fc1_b, 256, pw + a.rot_w, pw + a.rot_b,

@@ -7,8 +7,11 @@
 //     (the PREVIOUS layer's split-K partial sums, its bias and ReLU are applied here, so no reduction kernel runs in between),
 //     splits it to bf16 hi / lo and writes the 16 B unit into the SWIZZLE_128B operand tile;
 //   * KR / 16 k-steps x 3 products (hi*hi + hi*lo + lo*hi) of M = 128, N = 32 into one 32-column TMEM accumulator;
-//   * epilogue: lane = output row, column = sample; the raw partial sums leave as part[ks][b][o] (coalesced along o).  Bias and
-//     activation of THIS layer are applied by the consumer (the next FC layer or the pose projection), deterministic order.
+//   * epilogue, split-K form: lane = output row, column = sample; the raw partial sums leave as part[ks][b][o] (coalesced along o);
+//     bias and activation of THIS layer are applied by the consumer (the next FC layer or the pose projection);
+//   * epilogue, reduced form (I / KR = 8): the eight K-range blocks of a row tile are one thread-block cluster; each parks its
+//     partial tile in shared memory and block `rank` sums samples [4 rank, 4 rank + 4) over the eight tiles through distributed
+//     shared memory in fixed order, adds bias, applies ReLU and writes y[b][o]: one launch = one complete layer, deterministic.
 #include "scf_common.cuh"
 #include "scf_tc.cuh"
 #include <mutex>
@@ -30,7 +33,9 @@ constexpr int FC_SMEM = 1024 + 1024 + FC_MAXCH * (int)(FC_WCHUNK + FC_XCHUNK);
 struct FcIn { const float* p; int nsplit; long long split_stride; const float* bias; int relu; };
 struct FcParams {
   FcIn x;
-  float* part;           // [ks][B][O]
+  float* part;           // [ks][B][O] raw partial sums (split-K mode)
+  float* y;              // [B][O] = act(sum_ks + bias) (cluster mode: the I / KR blocks of a row tile form one cluster)
+  const float* bias; int relu;
   int B, I, O, KR;
 };
 
@@ -133,12 +138,47 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FcParams p) {
     tc_fence_after();
     float v[32];
     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v);
-    if (o < p.O) {
-      float* dst = p.part + ((long long)ks * p.B) * p.O + o;
+    if (!p.y) {
+      if (o < p.O) {
+        float* dst = p.part + ((long long)ks * p.B) * p.O + o;
+#pragma unroll
+        for (int b = 0; b < FC_N; ++b)
+          if (b < p.B) dst[(long long)b * p.O] = v[b];
+      }
+    } else {
+      // cluster mode: park this block's partial tile [32 samples][128 rows] in shared memory (the operand tiles are dead: every
+      // MMA has completed) for the cross-block reduction below
 #pragma unroll
       for (int b = 0; b < FC_N; ++b)
-        if (b < p.B) dst[(long long)b * p.O] = v[b];
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(x0 + (uint32_t)((b * FC_M + q * 32 + lane) * 4)), "f"(v[b]) : "memory");
     }
+  }
+  if (p.y) {
+    // split-K reduction through distributed shared memory: block `rank` of the cluster sums samples [4 * rank, 4 * rank + 4) over
+    // the eight partial tiles in fixed order (deterministic), adds the bias, applies the activation and writes the layer's output
+    __syncwarp();
+    cluster_sync_all();
+    const uint32_t rank = cluster_ctarank();
+    if (warp >= 1) {
+      const int ol = (warp & 3) * 32 + lane, o = mo * FC_M + ol;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int b = (int)rank * 4 + j;
+        float acc = 0.f;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+          float t;
+          asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(t) : "r"(mapa_shared(x0 + (uint32_t)((b * FC_M + ol) * 4), k)) : "memory");
+          acc += t;
+        }
+        if (b < p.B && o < p.O) {
+          acc += p.bias ? __ldg(p.bias + o) : 0.f;
+          p.y[(long long)b * p.O + o] = p.relu ? fmaxf(acc, 0.f) : acc;
+        }
+      }
+    }
+    __syncwarp();
+    cluster_sync_all();          // peers may still be reading this block's tile
   }
   tc_fence_before();
   __syncthreads();
@@ -148,8 +188,9 @@ fc_tc_kernel(const __grid_constant__ CUtensorMap tmW, const FcParams p) {
 // part[ks][b][o] = sum over inputs [ks*KR, (ks+1)*KR) of W[o][i] * x[b][i];  x = act(sum_s xin.p[s] + xin.bias) (see FcIn).
 // w_packed: split-bf16 [2][O][I] as written by scf_pack_conv_weight_tc(w, ., O, I, 1, 1, I, O, 0).
 int fc_tc(const float* x, int x_nsplit, long long x_split_stride, const float* x_bias, int x_relu, const void* w_packed, float* part,
-          int B, int I, int O, int KR, cudaStream_t st) {
-  SCF_REQUIRE(x && w_packed && part, SCF_ERR_ARG, "fc_tc: null pointer");
+          float* y, const float* bias, int relu, int B, int I, int O, int KR, cudaStream_t st) {
+  SCF_REQUIRE(x && w_packed && (part || y), SCF_ERR_ARG, "fc_tc: null pointer");
+  SCF_REQUIRE(!y || I / KR == 8, SCF_ERR_ARG, "fc_tc: the reduced form needs exactly 8 K-ranges (one cluster of 8 blocks per row tile): I / KR = %d", I / (KR > 0 ? KR : 1));
   SCF_REQUIRE(B >= 1 && B <= FC_N && KR % 64 == 0 && KR >= 64 && KR <= 64 * FC_MAXCH && I % KR == 0 && O % 4 == 0, SCF_ERR_ARG,
               "fc_tc: needs B <= 32, KR a multiple of 64 up to 256 dividing I (B %d, I %d, O %d, KR %d)", B, I, O, KR);
   SCF_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(w_packed) % 16 == 0 && (x_split_stride % 4) == 0 &&
@@ -157,7 +198,7 @@ int fc_tc(const float* x, int x_nsplit, long long x_split_stride, const float* x
               SCF_ERR_ALIGN, "fc_tc: buffers must be 16B aligned");
   FcParams p = {};
   p.x.p = x; p.x.nsplit = x_nsplit < 1 ? 1 : x_nsplit; p.x.split_stride = x_split_stride; p.x.bias = x_bias; p.x.relu = x_relu;
-  p.part = part; p.B = B; p.I = I; p.O = O; p.KR = KR;
+  p.part = part; p.y = y; p.bias = bias; p.relu = relu; p.B = B; p.I = I; p.O = O; p.KR = KR;
   CUtensorMap tmW;
   {
     cuuint64_t dims[3] = {(cuuint64_t)I, (cuuint64_t)O, 2};
@@ -173,11 +214,16 @@ int fc_tc(const float* x, int x_nsplit, long long x_split_stride, const float* x
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)cdiv(O, FC_M), (unsigned)(I / KR)); cfg.blockDim = dim3(FC_THREADS);
   cfg.dynamicSmemBytes = FC_SMEM; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   int na = 0;
   if (pdl) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (y) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 8; attr[na].val.clusterDim.z = 1;
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
@@ -191,8 +237,8 @@ int fc_tc(const float* x, int x_nsplit, long long x_split_stride, const float* x
 extern "C" {
 
 int scf_linear_tc(const float* x, int x_nsplit, long long x_split_stride, const float* x_bias, int x_relu, const void* w_packed,
-                  float* part, int B, int I, int O, int KR, void* stream) {
-  return scf::fc_tc(x, x_nsplit, x_split_stride, x_bias, x_relu, w_packed, part, B, I, O, KR, (cudaStream_t)stream);
+                  float* part, float* y, const float* bias, int relu, int B, int I, int O, int KR, void* stream) {
+  return scf::fc_tc(x, x_nsplit, x_split_stride, x_bias, x_relu, w_packed, part, y, bias, relu, B, I, O, KR, (cudaStream_t)stream);
 }
 
 }  // extern "C"

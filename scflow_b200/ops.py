@@ -177,9 +177,12 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: 
     return y
 
 
-def linear_tc(x: torch.Tensor, w: torch.Tensor, kr: int = 256, x_bias: Optional[torch.Tensor] = None, x_relu: bool = False) -> torch.Tensor:
+def linear_tc(x: torch.Tensor, w: torch.Tensor, kr: int = 256, x_bias: Optional[torch.Tensor] = None, x_relu: bool = False,
+              reduce: bool = False, bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
     """Split-K tcgen05 FC layer (scf_linear_tc): returns the raw partial sums [I / kr, B, O]; ``x`` is [B, I] or a stack of partial
-    maps [S, B, I] of the previous layer (summed, + ``x_bias``, ReLU if ``x_relu``, while the operand is formed)."""
+    maps [S, B, I] of the previous layer (summed, + ``x_bias``, ReLU if ``x_relu``, while the operand is formed).
+    ``reduce=True`` (I / kr must be 8): the K-range blocks reduce through distributed shared memory and the call returns the
+    finished layer output act(W x + bias) [B, O]."""
     _req(x, 'x')
     nsplit = 1 if x.dim() == 2 else x.shape[0]
     bsz, i = x.shape[-2:]
@@ -190,10 +193,11 @@ def linear_tc(x: torch.Tensor, w: torch.Tensor, kr: int = 256, x_bias: Optional[
     else:
         packed = _req(w, 'w', torch.bfloat16)
         o = w.shape[-2]
-    part = torch.empty(i // kr, bsz, o, device=x.device, dtype=torch.float32)
-    check(_lib.load().scf_linear_tc(ptr(x), nsplit, bsz * i, ptr(x_bias), int(x_relu), ptr(packed), ptr(part), bsz, i, o, kr, stream_ptr()),
-          'scf_linear_tc')
-    return part
+    part = None if reduce else torch.empty(i // kr, bsz, o, device=x.device, dtype=torch.float32)
+    y = torch.empty(bsz, o, device=x.device, dtype=torch.float32) if reduce else None
+    check(_lib.load().scf_linear_tc(ptr(x), nsplit, bsz * i, ptr(x_bias), int(x_relu), ptr(packed), ptr(part), ptr(y), ptr(bias), int(relu),
+                                    bsz, i, o, kr, stream_ptr()), 'scf_linear_tc')
+    return y if reduce else part
 
 
 def pose_project(x, rot_w, rot_b, tr_w, tr_b, label, rot_dim: int, num_class: int):

@@ -147,3 +147,10 @@ def test_linear_tc_split_k_chain_matches_fp64(b):
     assert e0 < 2e-5 and e1 < 2e-5
     # deterministic: a second launch reproduces the partial maps bit for bit
     assert torch.equal(p0, S.ops.linear_tc(x.cuda(), w0.cuda(), kr=256))
+    # reduced form: the eight K-range blocks of a row tile reduce through distributed shared memory; one launch = one layer
+    r0 = S.ops.linear_tc(x.cuda(), w0.cuda(), kr=256, reduce=True, bias=b0.cuda(), relu=True)
+    r1 = S.ops.linear_tc(r0, w1.cuda(), kr=128, reduce=True, bias=b1.cuda(), relu=True)
+    f0, f1 = float((r0.cpu().double() - y0).abs().max()), float((r1.cpu().double() - y1).abs().max())
+    print(f'linear_tc reduced B={b}: fc0 max err {f0:.3e}, fc1 max err {f1:.3e}')
+    assert r0.shape == (b, 1024) and r1.shape == (b, 256) and f0 < 2e-5 and f1 < 2e-5
+    assert torch.equal(r0, S.ops.linear_tc(x.cuda(), w0.cuda(), kr=256, reduce=True, bias=b0.cuda(), relu=True))
