@@ -362,6 +362,12 @@ constexpr uint32_t CS_WBLK = CR_C * 64u;                                        
 constexpr uint32_t CS_WODD = 0, CS_WEVEN = 4 * CS_WBLK, CS_WPLANE = 7 * CS_WBLK;   // [ky6|ky4|ky2|ky0] then [ky5|ky3|ky1]
 constexpr uint32_t CS_WBYTES = 2 * CS_WPLANE;                                     // 56 KB
 constexpr int CS_SMEM = 1024 + 1024 + (int)CS_WBYTES + CS_ASTAGES * (int)CS_ASTAGE;
+// FOLD variant: the kernel reads the fp32 NCHW image itself and forms the x-folded split-bf16 tile in shared memory (two converter
+// warps), which removes the im2col_x_split launch and its 4.2 MB-per-image intermediate.  Raw stage = two TMA boxes of
+// [3 channels][132 columns] fp32 covering input columns 256*xt - 4 .. 256*xt + 259.
+constexpr int CS_RAW_COLS = 132, CS_CONV_WARPS = 2;
+constexpr uint32_t CS_RAW_BOX = 3 * CS_RAW_COLS * 4, CS_RAW_BOX_PITCH = 1664, CS_RAW_STAGE = 2 * CS_RAW_BOX_PITCH;      // TMA destinations: 128 B aligned
+constexpr int CS_SMEM_FOLD = CS_SMEM + CS_ASTAGES * (int)CS_RAW_STAGE;
 
 // schedule of the stem: a segment with output rows [y0, y1) consumes input rows max(2*y0 - 3, 0) .. min(2*(y1-1) + 3, Hin - 1)
 template <class F>
@@ -384,19 +390,22 @@ __device__ __forceinline__ void stem_for_each_step(const RowsParams& p, F&& f) {
   }
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(64 + 32 * CR_EW, 1)
+template <bool STATS, bool FOLD>
+__global__ void __launch_bounds__(64 + 32 * CR_EW + (FOLD ? 32 * CS_CONV_WARPS : 0), 1)
 conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const RowsParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = sb, bar_empty = sb + 32, bar_w = sb + 64, bar_tfull = sb + 128, bar_tempty = sb + 192, tmem_slot = sb + 72,
-                 bias_s = sb + 256;
-  const uint32_t w0 = sb + 1024, a0 = w0 + CS_WBYTES;
+                 bias_s = sb + 256, bar_rfull = sb + 512, bar_rempty = sb + 544;
+  const uint32_t w0 = sb + 1024, a0 = w0 + CS_WBYTES, raw0 = a0 + CS_ASTAGES * CS_ASTAGE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   griddep_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmW);
-    for (int s = 0; s < CS_ASTAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < CS_ASTAGES; ++s) {
+      mbar_init(bar_full + 8 * s, FOLD ? CS_CONV_WARPS : 1); mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_rempty + 8 * s, CS_CONV_WARPS);
+    }
     mbar_init(bar_w, 1);
     for (int s = 0; s < CR_SLOTS; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, CR_EW); }
     fence_barrier_init();
@@ -409,7 +418,56 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   griddep_wait();
 
-  if (warp == 0) {
+  if (FOLD && warp >= 2 + CR_EW) {
+    // ================= converters: raw fp32 image row -> x-folded split-bf16 tile (element kx * 3 + c = in[c][2x + kx - 3]; 21 of 32)
+    const int ct = (int)threadIdx.x - 32 * (2 + CR_EW);          // 0..63: output columns ct and ct + 64 of the strip
+    int stage = 0;
+    uint32_t phase = 0;
+    stem_for_each_step(p, [&](int, int, int, int, int, int, int, uint32_t) {
+      mbar_wait(bar_rfull + 8 * stage, phase);
+      mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+      const uint32_t rs = raw0 + stage * CS_RAW_STAGE, as = a0 + stage * CS_ASTAGE;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int x = ct + 64 * half;
+        float v[24];
+#pragma unroll
+        for (int e = 0; e < 21; ++e) {
+          const int kx = e / 3, c = e - 3 * kx;
+          const int idx = 2 * x + kx + 1;                         // column relative to the first box (input x = 256 xt - 4 + idx)
+          const uint32_t off = (uint32_t)((c * CS_RAW_COLS + idx) * 4) + (idx >= CS_RAW_COLS ? CS_RAW_BOX_PITCH - CS_RAW_COLS * 4u : 0u);
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[e]) : "r"(rs + off));
+        }
+        v[21] = v[22] = v[23] = 0.f;
+        uint32_t hw[12], lw[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(v[2 * i], h0, l0);
+          split_bf16(v[2 * i + 1], h1, l1);
+          hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        // SWIZZLE_64B: 16 B unit j of row x sits at unit j ^ ((x >> 1) & 3)
+        const uint32_t row = as + (uint32_t)x * 64u, sw = ((uint32_t)x >> 1) & 3u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t a = row + ((((uint32_t)j) ^ sw) << 4);
+          if (j < 3) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hw[4 * j]), "r"(hw[4 * j + 1]), "r"(hw[4 * j + 2]), "r"(hw[4 * j + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + CS_APLANE), "r"(lw[4 * j]), "r"(lw[4 * j + 1]), "r"(lw[4 * j + 2]), "r"(lw[4 * j + 3]) : "memory");
+          } else {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + CS_APLANE), "r"(0u) : "memory");
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar_full + 8 * stage); mbar_arrive(bar_rempty + 8 * stage); }
+      if (++stage == CS_ASTAGES) { stage = 0; phase ^= 1u; }
+    });
+  } else if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_w, CS_WBYTES);
       for (int pl = 0; pl < 2; ++pl)
@@ -420,13 +478,21 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       stem_for_each_step(p, [&](int img, int xt, int r, int, int, int, int, uint32_t) {
-        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-        const uint32_t full = bar_full + 8 * stage, dst = a0 + stage * CS_ASTAGE;
-        if (p.dbg & 4) mbar_arrive(full);
-        else {
-          mbar_arrive_expect_tx(full, CS_ASTAGE);
-          tma_load_5d(dst, &tmA, full, 0, xt * CR_M, r, img, 0);
-          tma_load_5d(dst + CS_APLANE, &tmA, full, 0, xt * CR_M, r, img, 1);
+        if (FOLD) {
+          mbar_wait(bar_rempty + 8 * stage, phase ^ 1u);
+          const uint32_t full = bar_rfull + 8 * stage, dst = raw0 + stage * CS_RAW_STAGE;
+          mbar_arrive_expect_tx(full, 2 * CS_RAW_BOX);
+          tma_load_4d(dst, &tmA, full, 2 * xt * CR_M - 4, r, 0, img);
+          tma_load_4d(dst + CS_RAW_BOX_PITCH, &tmA, full, 2 * xt * CR_M - 4 + CS_RAW_COLS, r, 0, img);
+        } else {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          const uint32_t full = bar_full + 8 * stage, dst = a0 + stage * CS_ASTAGE;
+          if (p.dbg & 4) mbar_arrive(full);
+          else {
+            mbar_arrive_expect_tx(full, CS_ASTAGE);
+            tma_load_5d(dst, &tmA, full, 0, xt * CR_M, r, img, 0);
+            tma_load_5d(dst + CS_APLANE, &tmA, full, 0, xt * CR_M, r, img, 1);
+          }
         }
         if (++stage == CS_ASTAGES) { stage = 0; phase ^= 1u; }
       });
@@ -531,7 +597,8 @@ bool conv2d_stem_rows_eligible(const scf_tc_conv_desc& d) {
   return true;
 }
 
-int conv2d_stem_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
+// images != nullptr: FOLD variant (the kernel x-folds the fp32 NCHW image itself; d.seg is ignored, d.H x 2*d.W is the image size)
+static int conv2d_stem_rows_impl(const scf_tc_conv_desc& d, const float* images, cudaStream_t st) {
   RowsParams p = {};
   p.N = d.B; p.Hin = d.H; p.H = d.H / 2; p.W = d.W; p.TX = cdiv(d.W, CR_M);
   p.U = (long long)d.B * p.TX * p.H;
@@ -547,7 +614,13 @@ int conv2d_stem_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
     p.dbg = de ? atoi(de) : 0;
   }
   CUtensorMap tmA, tmW;
-  {
+  if (images) {
+    const cuuint64_t Wi = 2ull * d.W;
+    cuuint64_t dims[4] = {Wi, (cuuint64_t)d.H, 3, (cuuint64_t)d.B};
+    cuuint64_t str[3] = {Wi * 4, (cuuint64_t)d.H * Wi * 4, 3ull * d.H * Wi * 4};
+    cuuint32_t box[4] = {(cuuint32_t)CS_RAW_COLS, 1, 3, 1};
+    SCF_TRY(encode_map(&tmA, images, 4, dims, str, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  } else {
     const scf_tc_seg& sg = d.seg[0];
     const char* base = reinterpret_cast<const char*>(sg.ptr) + (size_t)sg.coff * 2;
     cuuint64_t dims[5] = {32, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B, 2};
@@ -555,6 +628,8 @@ int conv2d_stem_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
                          (cuuint64_t)sg.plane_stride * 2};
     cuuint32_t box[5] = {32, (cuuint32_t)CR_M, 1, 1, 1};
     SCF_TRY(encode_map(&tmA, base, 5, dims, str, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B));
+  }
+  {
     cuuint64_t wd[4] = {32, (cuuint64_t)CR_C, 7, 2};
     cuuint64_t ws[3] = {32 * 2, (cuuint64_t)CR_C * 32 * 2, (cuuint64_t)7 * CR_C * 32 * 2};
     cuuint32_t wb[4] = {32, (cuuint32_t)CR_C, 1, 1};
@@ -570,8 +645,10 @@ int conv2d_stem_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_stem_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_stem_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM);
+    attr_err = cudaFuncSetAttribute(conv_stem_rows_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_stem_rows_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_stem_rows_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_FOLD);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_stem_rows_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_FOLD);
   });
   SCF_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "cudaFuncSetAttribute(conv_stem_rows_kernel): %s", cudaGetErrorString(attr_err));
   const unsigned grid = (unsigned)(p.U < num_sms ? p.U : num_sms);
@@ -585,8 +662,8 @@ int conv2d_stem_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
   g_last_m_tiles = (int)p.U; g_last_tiles_per_img = p.TX * p.H; g_last_stat_rows_per_img = p.stat_rows;
   static const bool pdl = [] { const char* e = getenv("SCFLOW_PDL"); return e ? atoi(e) != 0 : true; }();
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * CR_EW);
-  cfg.dynamicSmemBytes = CS_SMEM; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * CR_EW + (images ? 32 * CS_CONV_WARPS : 0));
+  cfg.dynamicSmemBytes = images ? CS_SMEM_FOLD : CS_SMEM; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   int na = 0;
   if (pdl) {
@@ -595,11 +672,26 @@ int conv2d_stem_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  cudaError_t le = d.stats ? cudaLaunchKernelEx(&cfg, conv_stem_rows_kernel<true>, tmA, tmW, p)
-                           : cudaLaunchKernelEx(&cfg, conv_stem_rows_kernel<false>, tmA, tmW, p);
+  cudaError_t le = images ? (d.stats ? cudaLaunchKernelEx(&cfg, conv_stem_rows_kernel<true, true>, tmA, tmW, p)
+                                     : cudaLaunchKernelEx(&cfg, conv_stem_rows_kernel<false, true>, tmA, tmW, p))
+                          : (d.stats ? cudaLaunchKernelEx(&cfg, conv_stem_rows_kernel<true, false>, tmA, tmW, p)
+                                     : cudaLaunchKernelEx(&cfg, conv_stem_rows_kernel<false, false>, tmA, tmW, p));
   if (le != cudaSuccess) { cudaGetLastError(); set_error("conv_stem_rows_kernel launch: %s", cudaGetErrorString(le)); g_launches++; return (int)le; }
   return check_launch("conv_stem_rows_kernel");
 }
+
+int conv2d_stem_rows(const scf_tc_conv_desc& d, cudaStream_t st) { return conv2d_stem_rows_impl(d, nullptr, st); }
+
+// The stem straight from the fp32 NCHW image [B, 3, d.H, 2 * d.W] (no im2col_x_split launch): SCFLOW_STEM_FOLD (default 1)
+bool conv2d_stem_rows_fold_ok(const scf_tc_conv_desc& d, const float* images) {
+  const char* fe = getenv("SCFLOW_STEM_FOLD");
+  if (fe && atoi(fe) == 0) return false;
+  scf_tc_conv_desc t = d;
+  static const __nv_bfloat16 dummy[8] = {};
+  t.seg[0].ptr = dummy; t.seg[0].stride = 32; t.seg[0].coff = 0; t.seg[0].nch = 32; t.seg[0].plane_stride = 8; t.nseg = 1;
+  return images && reinterpret_cast<uintptr_t>(images) % 16 == 0 && (2 * d.W) % 4 == 0 && conv2d_stem_rows_eligible(t);
+}
+int conv2d_stem_rows_fold(const float* images, const scf_tc_conv_desc& d, cudaStream_t st) { return conv2d_stem_rows_impl(d, images, st); }
 
 // SCFLOW_TC_ROWS (default 1): 3x3 / stride 1 / 64 -> 64 channel layers on maps at least 96 pixels wide take this kernel
 bool conv2d_rows_eligible(const scf_tc_conv_desc& d) {

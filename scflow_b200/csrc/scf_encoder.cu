@@ -12,6 +12,8 @@ namespace scf {
 int conv2d_f32(const scf_conv_desc& d, cudaStream_t st);
 int conv2d_thin(const scf_conv_desc& d, int in_nchw, cudaStream_t st);
 int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st);
+bool conv2d_stem_rows_fold_ok(const scf_tc_conv_desc& d, const float* images);
+int conv2d_stem_rows_fold(const float* images, const scf_tc_conv_desc& d, cudaStream_t st);
 void conv2d_tc_last_tiles(int* m_tiles, int* per_img, int* stat_rows);
 int conv2d_tc_max_tiles(int B, int Hout, int Wout);
 int im2col_x_split(const float* in, int nchw, int cin, int kw, void* out_hl, long long plane, int N, int H, int Wi, int sx,
@@ -311,7 +313,8 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
   // stride 2 -> 21 channels), then a 7x1 convolution with vertical stride 2 (see scf_conv_tc.cu)
   int h = H / 2, w = W / 2;
   long long npix = (long long)N * h * w;
-  SCF_TRY(im2col_x_split(images, /*nchw=*/1, 3, 7, S(ws.t0), (long long)N * H * w * a.cin_pad[0], N, H, W, 2, st));
+  // (when the rolling-rows stem kernel applies it x-folds the image itself: no im2col launch, no 4.2 MB-per-image intermediate)
+  bool stem_folded = false, stem_probed = false;
   auto stem_conv = [&](int act, float* of32, void* ohl, float* stats) -> int {
     scf_tc_conv_desc d = {};
     d.seg[0].ptr = S(ws.t0); d.seg[0].plane_stride = (long long)N * H * w * a.cin_pad[0]; d.seg[0].stride = a.cin_pad[0];
@@ -323,7 +326,12 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
     d.out_f32 = of32; d.out_f32_stride = 64;
     d.out_hl = ohl; d.out_hl_plane = npix * 64; d.out_hl_stride = 64;
     d.stats = stats;
-    return conv2d_tc(d, st);
+    if (!stem_probed) {
+      stem_probed = true;
+      stem_folded = conv2d_stem_rows_fold_ok(d, images);
+      if (!stem_folded) SCF_TRY(im2col_x_split(images, /*nchw=*/1, 3, 7, S(ws.t0), (long long)N * H * w * a.cin_pad[0], N, H, W, 2, st));
+    }
+    return stem_folded ? conv2d_stem_rows_fold(images, d, st) : conv2d_tc(d, st);
   };
   // InstanceNorm helpers
   auto in_stats = [&](const float* x, float* stat, int hw, int C) -> int {

@@ -219,6 +219,27 @@ def test_native_encoder_matches_oracle(norm):
     assert float((g2 - r2).abs().max()) < 2e-4 * max(float(r2.abs().max()), 1.0)
 
 
+@pytest.mark.parametrize('norm', ['IN', 'BN'])
+def test_encoder_stem_variants_are_bit_identical(norm, monkeypatch):
+    """The stem's three forms - generic tile, rolling rows over the im2col'd image, rolling rows x-folding the fp32 image in the
+    kernel - use the same split-bf16 operands; the two rolling forms also share the summation order, so they agree bit for bit."""
+    import scflow_b200 as S
+    enc = S.build_encoder(dict(type='RAFTEncoder', in_channels=3, out_channels=256, net_type='Basic', norm_cfg=dict(type=norm)))
+    enc.load_state_dict(O.make_encoder_weights(7, norm), strict=False)
+    enc = enc.cuda().eval()
+    x = O.make_scene(7, 4)['real_images'].cuda()
+    outs = {}
+    for name, env in (('fold', {}), ('im2col', {'SCFLOW_STEM_FOLD': '0'}), ('generic', {'SCFLOW_TC_ROWS_STEM': '0'})):
+        for k in ('SCFLOW_STEM_FOLD', 'SCFLOW_TC_ROWS_STEM'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with torch.no_grad():
+            outs[name] = enc(x).clone()
+    assert torch.equal(outs['fold'], outs['im2col'])
+    assert float((outs['fold'] - outs['generic']).abs().max()) < 1e-4 * float(outs['generic'].abs().max())
+
+
 @pytest.mark.parametrize('graph', [False, True])
 def test_native_feature_path_matches_generic_path_and_oracle(graph):
     """get_pose with the encoders writing the loop's inputs straight into the decoder workspace (no NCHW round trip) against
