@@ -148,6 +148,11 @@ typedef struct scf_tc_conv_desc {
                                        * taps [k*taps/ksplit, ...) and writes its PARTIAL sums to out_f32 + k*split_stride elements;
                                        * the caller adds the ksplit maps.  Plain linear layers only (no bias / activation / other
                                        * outputs), taps % ksplit == 0 */
+  const void* aux0_hl; long long aux0_hl_plane; int aux0_hl_stride;
+                                      /* EPI_ACT: the residual as split-bf16 NHWC planes (hi + lo, ~2^-17 relative) instead of the fp32
+                                       * map aux0 - lets a residual block keep its activations in split form only.  Served by the
+                                       * rolling-rows kernel (3x3, stride 1, 64 -> 64 channels, maps >= 96 pixels wide); other
+                                       * layers refuse it (SCF_ERR_UNSUPPORTED) */
 } scf_tc_conv_desc;
 /* upper bound, in 128-pixel-tile units, of the pixel tiles scf_conv2d_tc may use for this output geometry whichever tiling it
  * chooses (size of the `stats` buffer = tiles*4*2*cout floats, zero-initialised), and the 128-pixel tiles per sample (0 if a

@@ -53,6 +53,7 @@ class TcConvDesc(C.Structure):
         ('out2_hl', c_void_p), ('out2_hl_plane', C.c_longlong), ('out2_hl_stride', C.c_int),
         ('pre', c_void_p), ('pre_stride', C.c_int), ('stride_x', C.c_int), ('stride_y', C.c_int), ('w_plane_stride', C.c_longlong), ('stats', c_void_p),
         ('out_pad_writable', C.c_int), ('ksplit', C.c_int), ('split_stride', C.c_longlong),
+        ('aux0_hl', c_void_p), ('aux0_hl_plane', C.c_longlong), ('aux0_hl_stride', C.c_int),
     ]
 
 

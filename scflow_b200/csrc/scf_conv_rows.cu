@@ -51,10 +51,12 @@ struct RowsParams {
   float* out_f32; int of_stride, of_coff;
   __nv_bfloat16* out_hl; long long oh_plane; int oh_stride, oh_coff;
   const float* res; int res_stride;
+  const __nv_bfloat16* res_hl; long long res_hl_plane; int res_hl_stride;    // residual as split-bf16 planes (instead of res)
   float* stats; int stat_rows;     // rows of [2][64] partial sums per image: (xt * stat_k + segment ordinal) * 4 + warp; zeroed by the launcher
   int stat_k;                      // upper bound of the CTA segments that can touch one (image, strip)
   int al32;                        // 32 B vector accesses allowed: bit 0 fp32 output, bit 1 split output, bit 2 residual input
-  int dbg;                         // timing experiments (SCFLOW_ROWS_DBG): 1 no MMAs, 2 no global stores, 4 no activation loads
+  int dbg;                         // timing experiments (SCFLOW_ROWS_DBG): 1 no MMAs, 2 no global stores, 4 no activation loads, 8 no epilogue work
+  long long* dbg_times;            // optional [grid][8] clock64 totals of the MMA thread's phases (SCFLOW_ROWS_DBG_TIMES = hex pointer)
 };
 
 // The three roles (TMA producer, MMA issuer, epilogue) walk the same schedule: the CTA's unit range, cut into segments at
@@ -90,6 +92,49 @@ __device__ __forceinline__ float transpose_reduce32_rows(float (&acc)[32], int l
   return acc[0];
 }
 
+// 32 channels (128 B) of the fp32 residual map for one pixel
+__device__ __forceinline__ void rows_load_residual(const RowsParams& p, long long pix, bool valid, int h, float4 (&rs)[8]) {
+  if (p.res_hl) {
+    // hi + lo bf16 planes: 64 B each for this thread's 32 channels
+    uint4 hq[4], lq[4];
+    const uint4* hp = reinterpret_cast<const uint4*>(p.res_hl + pix * p.res_hl_stride + h * 32);
+    const uint4* lp = reinterpret_cast<const uint4*>(p.res_hl + p.res_hl_plane + pix * p.res_hl_stride + h * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hq[j] = valid ? __ldcs(hp + j) : make_uint4(0u, 0u, 0u, 0u);
+      lq[j] = valid ? __ldcs(lp + j) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t hw[4] = {hq[j].x, hq[j].y, hq[j].z, hq[j].w}, lw[4] = {lq[j].x, lq[j].y, lq[j].z, lq[j].w};
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+        f[2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+      }
+      rs[2 * j] = make_float4(f[0], f[1], f[2], f[3]);
+      rs[2 * j + 1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    return;
+  }
+  const float* rp = p.res + pix * p.res_stride + h * 32;
+  if (!valid) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (p.al32 & 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      asm volatile("ld.global.cs.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=f"(rs[2 * j].x), "=f"(rs[2 * j].y), "=f"(rs[2 * j].z), "=f"(rs[2 * j].w), "=f"(rs[2 * j + 1].x), "=f"(rs[2 * j + 1].y),
+                     "=f"(rs[2 * j + 1].z), "=f"(rs[2 * j + 1].w)
+                   : "l"(rp + 8 * j));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rs[j] = __ldcs(reinterpret_cast<const float4*>(rp) + j);
+  }
+}
+
 // Epilogue of one finished output row: thread = (pixel of the 128-pixel strip, 32-channel half h); `sq` = the row's sequence number
 // in this CTA (TMEM slot sq & 7).  bias (+ residual) (+ ReLU) -> fp32 and / or split-bf16 NHWC, optional InstanceNorm partial sums.
 template <bool RES, bool STATS>
@@ -100,26 +145,18 @@ __device__ __forceinline__ void rows_epilogue_row(const RowsParams& p, uint32_t 
   const int x = xt * CR_M + q * 32 + lane;
   const bool valid = x < p.W;
   const long long pix = ((long long)img * p.H + y) * p.W + x;
+  // residual values are requested before the accumulator is awaited (a one-row look-ahead was measured: no gain - the residual
+  // variant is bound by its 2x memory traffic, not by load latency)
   float4 rs[RES ? 8 : 1];
-  if (RES) {
-    const float* rp = p.res + pix * p.res_stride + h * 32;
-    if (!valid) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else if (p.al32 & 4) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        asm volatile("ld.global.cs.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=f"(rs[2 * j].x), "=f"(rs[2 * j].y), "=f"(rs[2 * j].z), "=f"(rs[2 * j].w), "=f"(rs[2 * j + 1].x), "=f"(rs[2 * j + 1].y),
-                       "=f"(rs[2 * j + 1].z), "=f"(rs[2 * j + 1].w)
-                     : "l"(rp + 8 * j));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) rs[j] = __ldcs(reinterpret_cast<const float4*>(rp) + j);
-    }
-  }
+  if constexpr (RES) rows_load_residual(p, pix, valid, h, rs);
   mbar_wait(bar_tfull + 8 * slot, (sq >> 3) & 1u);
   tc_fence_after();
+  if (p.dbg & 8) {                 // timing experiment: hand the slot back without reading it
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+    return;
+  }
   const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 64u;
   {
     float v[32];
@@ -505,7 +542,12 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       uint32_t phase = 0;
       mbar_wait(bar_w, 0);
       tc_fence_after();
+      long long tacc[6] = {0, 0, 0, 0, 0, 0};
+      long long tprev = clock64();
+      const long long tstart = tprev;
+      auto tick = [&](int k) { if (p.dbg_times) { const long long t = clock64(); tacc[k] += t - tprev; tprev = t; } };
       stem_for_each_step(p, [&](int, int, int r, int y0, int, int lo, int hi, uint32_t seq) {
+        tick(0);                                  // schedule arithmetic between steps
         const int m = r >> 1, n = hi - lo + 1;
         // rows opened by this input row: y with 2y - 3 == r (odd r: the window's top row), and every row when r == 0
         const int n_fresh = r == 0 ? n : ((r & 1) && hi == m + 2 ? 1 : 0);
@@ -513,8 +555,10 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const uint32_t sq = seq + (uint32_t)(y - y0);
           mbar_wait(bar_tempty + 8 * (sq & 7u), ((sq >> 3) & 1u) ^ 1u);
         }
+        tick(1);                                  // waiting for TMEM slots
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
+        tick(2);                                  // waiting for the operand tile
         const int sa = (int)((seq + (uint32_t)(lo - y0)) & 7u);
         const int n1 = n < CR_SLOTS - sa ? n : CR_SLOTS - sa, n2 = n - n1;
         const uint32_t d1 = tmem_base + (uint32_t)(sa * 64), d2 = tmem_base;
@@ -535,25 +579,38 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               umma_bf16(tmem_base + sl * 64u, a_hi0, b1_hi0 + (uint64_t)(((uint32_t)(y - lo) * CS_WBLK) >> 4), id1, y > hi - n_fresh ? 0u : 1u);
             }
           }
-          umma_bf16(d1, a_hi0, b1_lo0, in1, 1u);
-          umma_bf16(d1, a_lo0, b1_hi0, in1, 1u);
-          if (n2) { umma_bf16(d2, a_hi0, b1_lo0 + bo2, in2, 1u); umma_bf16(d2, a_lo0, b1_hi0 + bo2, in2, 1u); }
+          const bool all3 = !(p.dbg & 16);                    // timing experiment: bit 16 = hi*hi products only
+          if (all3) {
+            umma_bf16(d1, a_hi0, b1_lo0, in1, 1u);
+            umma_bf16(d1, a_lo0, b1_hi0, in1, 1u);
+            if (n2) { umma_bf16(d2, a_hi0, b1_lo0 + bo2, in2, 1u); umma_bf16(d2, a_lo0, b1_hi0 + bo2, in2, 1u); }
+          }
           const uint64_t ko = (uint64_t)(32 >> 4);            // second k-step: channels 16..31
           umma_bf16(d1, a_hi0 + ko, b1_hi0 + ko, in1, 1u);
-          umma_bf16(d1, a_hi0 + ko, b1_lo0 + ko, in1, 1u);
-          umma_bf16(d1, a_lo0 + ko, b1_hi0 + ko, in1, 1u);
+          if (all3) {
+            umma_bf16(d1, a_hi0 + ko, b1_lo0 + ko, in1, 1u);
+            umma_bf16(d1, a_lo0 + ko, b1_hi0 + ko, in1, 1u);
+          }
           if (n2) {
             umma_bf16(d2, a_hi0 + ko, b1_hi0 + bo2 + ko, in2, 1u);
-            umma_bf16(d2, a_hi0 + ko, b1_lo0 + bo2 + ko, in2, 1u);
-            umma_bf16(d2, a_lo0 + ko, b1_hi0 + bo2 + ko, in2, 1u);
+            if (all3) {
+              umma_bf16(d2, a_hi0 + ko, b1_lo0 + bo2 + ko, in2, 1u);
+              umma_bf16(d2, a_lo0 + ko, b1_hi0 + bo2 + ko, in2, 1u);
+            }
           }
         }
+        tick(3);                                  // descriptors + MMA issue
         umma_commit(bar_empty + 8 * stage);
         if (++stage == CS_ASTAGES) { stage = 0; phase ^= 1u; }
         // finished rows: 2y + 3 == r, and at the last input row every row still open
         for (int y = lo; y <= hi; ++y)
           if (2 * y + 3 == r || r == p.Hin - 1) umma_commit(bar_tfull + 8 * ((seq + (uint32_t)(y - y0)) & 7u));
+        tick(4);                                  // commits
       });
+      if (p.dbg_times) {
+        for (int k = 0; k < 5; ++k) p.dbg_times[(long long)blockIdx.x * 8 + k] = tacc[k];
+        p.dbg_times[(long long)blockIdx.x * 8 + 5] = clock64() - tstart;
+      }
     }
   } else {
     const int q = warp & 3, h = (warp - 2) >> 2, et = (int)threadIdx.x - 64;
@@ -612,6 +669,8 @@ static int conv2d_stem_rows_impl(const scf_tc_conv_desc& d, const float* images,
     if (d.out_hl && al32(d.out_hl) && d.out_hl_stride % 16 == 0 && d.out_hl_coff % 16 == 0 && (d.out_hl_plane * 2) % 32 == 0) p.al32 |= 2;
     const char* de = getenv("SCFLOW_ROWS_DBG");
     p.dbg = de ? atoi(de) : 0;
+    const char* dt = getenv("SCFLOW_ROWS_DBG_TIMES");
+    p.dbg_times = dt ? reinterpret_cast<long long*>(strtoull(dt, nullptr, 16)) : nullptr;
   }
   CUtensorMap tmA, tmW;
   if (images) {
@@ -708,6 +767,7 @@ bool conv2d_rows_eligible(const scf_tc_conv_desc& d) {
   if (d.out_f32 && (!al16(d.out_f32) || d.out_f32_stride % 4 || d.out_f32_coff % 4)) return false;
   if (d.out_hl && (!al16(d.out_hl) || d.out_hl_stride % 8 || d.out_hl_coff % 8 || (d.out_hl_plane * 2) % 16)) return false;
   if (d.aux0 && (!al16(d.aux0) || d.aux0_stride % 4)) return false;
+  if (d.aux0_hl && (d.aux0 || !al16(d.aux0_hl) || d.aux0_hl_stride % 8 || (d.aux0_hl_plane * 2) % 16)) return false;
   return true;
 }
 
@@ -719,6 +779,7 @@ int conv2d_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
   p.out_f32 = d.out_f32; p.of_stride = d.out_f32_stride; p.of_coff = d.out_f32_coff;
   p.out_hl = reinterpret_cast<__nv_bfloat16*>(d.out_hl); p.oh_plane = d.out_hl_plane; p.oh_stride = d.out_hl_stride; p.oh_coff = d.out_hl_coff;
   p.res = d.aux0; p.res_stride = d.aux0_stride;
+  p.res_hl = reinterpret_cast<const __nv_bfloat16*>(d.aux0_hl); p.res_hl_plane = d.aux0_hl_plane; p.res_hl_stride = d.aux0_hl_stride;
   p.stats = d.stats;
   {
     auto al32 = [](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % 32 == 0; };
@@ -779,7 +840,7 @@ int conv2d_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  const int mode = (d.aux0 ? 1 : 0) | (d.stats ? 2 : 0);
+  const int mode = ((d.aux0 || d.aux0_hl) ? 1 : 0) | (d.stats ? 2 : 0);
   cudaError_t le = cudaLaunchKernelEx(&cfg, table[mode], tmA, tmW, p);
   if (le != cudaSuccess) { cudaGetLastError(); set_error("conv_rows_kernel launch: %s", cudaGetErrorString(le)); g_launches++; return (int)le; }
   return check_launch("conv_rows_kernel");

@@ -1749,6 +1749,7 @@ int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st) {
                 SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: stats need an fp32 output, cout %% 32 == 0 and the plain epilogue");
   if (conv2d_rows_eligible(d)) return conv2d_rows(d, st);
   if (conv2d_stem_rows_eligible(d)) return conv2d_stem_rows(d, st);
+  SCF_REQUIRE(d.aux0_hl == nullptr, SCF_ERR_UNSUPPORTED, "scf_conv2d_tc: a split-bf16 residual (aux0_hl) is served by the rolling-rows kernel only");
   if (d.ksplit <= 1 && tct_eligible(d)) return conv2d_tct(d, st);
   TcParams p = {};
   p.nseg = d.nseg;

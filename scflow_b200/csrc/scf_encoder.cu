@@ -5,6 +5,7 @@
 // folded into the packed weights.
 // This is SURVEY.md §8(f) rank 1: the component feeding the refinement loop.
 #include "scf_common.cuh"
+#include <stdlib.h>
 #include "scf_tc.cuh"
 
 namespace scf {
@@ -13,6 +14,7 @@ int conv2d_f32(const scf_conv_desc& d, cudaStream_t st);
 int conv2d_thin(const scf_conv_desc& d, int in_nchw, cudaStream_t st);
 int conv2d_tc(const scf_tc_conv_desc& d, cudaStream_t st);
 bool conv2d_stem_rows_fold_ok(const scf_tc_conv_desc& d, const float* images);
+bool conv2d_rows_eligible(const scf_tc_conv_desc& d);
 int conv2d_stem_rows_fold(const float* images, const scf_tc_conv_desc& d, cudaStream_t st);
 void conv2d_tc_last_tiles(int* m_tiles, int* per_img, int* stat_rows);
 int conv2d_tc_max_tiles(int B, int Hout, int Wout);
@@ -350,7 +352,7 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
   };
   // tensor-core conv unit u on split input (hin x win), stride from the table
   auto tcconv = [&](int u, void* in_s, int hin, int win, int act, float* of32, void* ohl, const float* residual,
-                    float* stats = nullptr) -> int {
+                    float* stats = nullptr, const void* residual_hl = nullptr, bool probe_rows = false) -> int {
     const EncUnit& e = kUnits[u];
     scf_tc_conv_desc d = {};
     const long long in_pix = (long long)N * hin * win;
@@ -363,7 +365,9 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
     d.out_f32 = of32; d.out_f32_stride = e.cout;
     d.out_hl = ohl; d.out_hl_plane = (long long)N * ho * wo * e.cout; d.out_hl_stride = e.cout;
     d.aux0 = residual; d.aux0_stride = e.cout;
+    d.aux0_hl = residual_hl; d.aux0_hl_plane = (long long)N * ho * wo * e.cout; d.aux0_hl_stride = e.cout;
     d.stats = stats;
+    if (probe_rows) return conv2d_rows_eligible(d) ? 1 : 0;       // would this layer run on the rolling-rows kernel?
     return conv2d_tc(d, st);
   };
   // convolution + InstanceNorm statistics of its output: the conv epilogue emits per-tile partial sums when a tile never
@@ -386,8 +390,12 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
   };
 
   int cur = 0;                         // block input lives in xf[cur] (fp32) and xs[cur] (split)
+  // folded-BatchNorm encoder, 64-channel stage: when its convolutions run on the rolling-rows kernel the identity branch is read
+  // from the block input's split-bf16 planes, so no fp32 copy of the stem / block outputs is written at all
+  static const bool split_id_on = [] { const char* e = getenv("SCFLOW_ENC_SPLIT_ID"); return e ? atoi(e) != 0 : true; }();
+  const bool split_identity = split_id_on && !inorm && tcconv(2, S(ws.ts), h, w, SCF_ACT_RELU, nullptr, S(ws.xs[1]), nullptr, nullptr, S(ws.xs[0]), true) == 1;
   if (!inorm) {
-    SCF_TRY(stem_conv(SCF_ACT_RELU, F(ws.xf[0]), S(ws.xs[0]), nullptr));
+    SCF_TRY(stem_conv(SCF_ACT_RELU, split_identity ? nullptr : F(ws.xf[0]), S(ws.xs[0]), nullptr));
   } else {
     int per_img = 0;
     scf_conv2d_tc_tiles(N, h, w, &per_img);
@@ -423,12 +431,16 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
       }
     } else {   // eval-mode BatchNorm folded into the convolutions: everything happens in the conv epilogues
       SCF_TRY(tcconv(u1, S(ws.xs[cur]), h, w, SCF_ACT_RELU, nullptr, S(ws.ts), nullptr));
-      const float* identity = F(ws.xf[cur]);
-      if (ud >= 0) {
-        SCF_TRY(tcconv(ud, S(ws.xs[cur]), h, w, SCF_ACT_NONE, F(ws.raw2), nullptr, nullptr));
-        identity = F(ws.raw2);
+      if (split_identity && bi < 2) {
+        SCF_TRY(tcconv(u2, S(ws.ts), ho, wo, SCF_ACT_RELU, nullptr, S(ws.xs[nxt]), nullptr, nullptr, S(ws.xs[cur])));
+      } else {
+        const float* identity = F(ws.xf[cur]);
+        if (ud >= 0) {
+          SCF_TRY(tcconv(ud, S(ws.xs[cur]), h, w, SCF_ACT_NONE, F(ws.raw2), nullptr, nullptr));
+          identity = F(ws.raw2);
+        }
+        SCF_TRY(tcconv(u2, S(ws.ts), ho, wo, SCF_ACT_RELU, F(ws.xf[nxt]), S(ws.xs[nxt]), identity));
       }
-      SCF_TRY(tcconv(u2, S(ws.ts), ho, wo, SCF_ACT_RELU, F(ws.xf[nxt]), S(ws.xs[nxt]), identity));
     }
     cur = nxt; h = ho; w = wo;
   }

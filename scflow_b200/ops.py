@@ -313,7 +313,7 @@ def conv2d_tc(segs: Sequence, packed_w: torch.Tensor, bias: Optional[torch.Tenso
               out_f32: Optional[torch.Tensor] = None, out_f32_coff: int = 0, out_hl: Optional[torch.Tensor] = None,
               out_hl_coff: int = 0, epi: int = _lib.EPI_ACT, aux0=None, aux1=None, out2_hl=None, scale: float = 1.0,
               w_batched: bool = False, stride: int = 1, pre: Optional[torch.Tensor] = None, stride_xy=None,
-              stats: Optional[torch.Tensor] = None, out_pad_writable: bool = False):
+              stats: Optional[torch.Tensor] = None, out_pad_writable: bool = False, aux0_hl: Optional[torch.Tensor] = None):
     """tcgen05 convolution. ``segs`` = [(split tensor [2,B,H,W,stride], coff, nch), ...].
     ``pre``: fp32 NHWC map added before the GRU gate non-linearity; ``stride_xy``: per-axis strides; ``stats``: fp32
     [tiles*4*2*cout] buffer receiving per-tile InstanceNorm partial sums (see include/scflow_b200.h)."""
@@ -354,6 +354,9 @@ def conv2d_tc(segs: Sequence, packed_w: torch.Tensor, bias: Optional[torch.Tenso
         _req(stats, 'stats')
         d.stats = stats.data_ptr()
     d.out_pad_writable = int(out_pad_writable)
+    if aux0_hl is not None:                    # residual as split-bf16 planes [2, B, H, W, C] (rolling-rows kernel only)
+        _req_split(aux0_hl, 'aux0_hl')
+        d.aux0_hl, d.aux0_hl_plane, d.aux0_hl_stride = aux0_hl.data_ptr(), aux0_hl[0].numel(), aux0_hl.shape[-1]
     check(_lib.load().scf_conv2d_tc(C.byref(d), stream_ptr()), 'scf_conv2d_tc')
     return out_f32 if out_f32 is not None else out_hl
 

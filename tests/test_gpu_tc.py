@@ -259,3 +259,27 @@ def test_conv_stem_rows_kernel_matches_fp64_and_generic_tile(S, monkeypatch, hw,
             assert float((rows[1] - own.pow(2).sum((0, 1, 2))).abs().max()) < 1e-3
         outs[mode] = got
     assert float((outs['1'] - outs['0']).abs().max()) < 2e-5
+
+
+def test_conv_rows_kernel_split_residual(S):
+    """The residual of a 64-channel BasicBlock taken from the block input's split-bf16 planes (scf_tc_conv_desc.aux0_hl) equals the
+    fp32 residual to the planes' 2^-17 relative accuracy; layers outside the rolling-rows kernel refuse the option."""
+    gen = torch.Generator().manual_seed(77)
+    b, hw = 2, (128, 128)
+    x = torch.randn(b, 64, *hw, generator=gen)
+    w = torch.randn(64, 64, 3, 3, generator=gen) / 24.0
+    bias = 0.1 * torch.randn(64, generator=gen)
+    res = torch.randn(b, 64, *hw, generator=gen)
+    ref = torch.relu(F.conv2d(x.double(), w.double(), bias.double(), padding=1) + res.double()).float()
+    xs, rs = S.ops.split_nchw(x.cuda()), S.ops.split_nchw(res.cuda())
+    pw = S.ops.pack_conv_weight_tc([w.cuda()])
+    out_hl = torch.zeros(2, b, *hw, 64, device='cuda', dtype=torch.bfloat16)
+    S.ops.conv2d_tc([(xs, 0, 64)], pw, bias.cuda(), 64, 3, act='relu', out_hl=out_hl, aux0_hl=rs)
+    torch.cuda.synchronize()
+    err = float((S.ops.unsplit(out_hl).cpu() - ref).abs().max())
+    print(f'rows kernel, split residual: max err {err:.3e}')
+    assert err < 1e-4
+    xs2 = S.ops.split_nchw(x[:, :, :32, :32].contiguous().cuda())           # a 32 x 32 map stays on the generic tile
+    with pytest.raises(Exception, match='aux0_hl'):
+        S.ops.conv2d_tc([(xs2, 0, 64)], pw, bias.cuda(), 64, 3, act='relu', out_hl=torch.zeros(2, b, 32, 32, 64, device='cuda', dtype=torch.bfloat16),
+                        aux0_hl=S.ops.split_nchw(res[:, :, :32, :32].contiguous().cuda()))

@@ -32,3 +32,18 @@ for variant in ('in_raw', 'bn_relu'):
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
         print(f'stem rows={mode} {variant:8s} N={n}: {sorted(ts[1:])[2]:7.1f} us')
+
+if os.environ.get('TRACE'):
+    os.environ['SCFLOW_TC_ROWS'] = '1'
+    tb = torch.zeros(148 * 8, dtype=torch.int64, device='cuda')
+    os.environ['SCFLOW_ROWS_DBG_TIMES'] = hex(tb.data_ptr())
+    out_f32 = torch.empty(n, 128, 128, 64, device='cuda')
+    st = torch.zeros(n_tiles * 4 * 2 * 64, device='cuda')
+    flush.zero_()
+    S.ops.conv2d_tc([(xs, 0, 32)], pw, bias, 64, (7, 1), stride_xy=(1, 2), out_f32=out_f32, stats=st)
+    torch.cuda.synchronize()
+    del os.environ['SCFLOW_ROWS_DBG_TIMES']
+    t = tb.view(148, 8).double().mean(0) / 1.965e3            # cycles -> us at 1965 MHz
+    names = ['schedule arithmetic', 'wait TMEM slots', 'wait operand tile', 'descriptors + MMA issue', 'commits', 'MMA thread total']
+    for k, nme in enumerate(names):
+        print(f'  MMA thread: {nme:26s} {float(t[k]):7.1f} us')
