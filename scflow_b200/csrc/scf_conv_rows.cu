@@ -92,6 +92,13 @@ __device__ __forceinline__ float transpose_reduce32_rows(float (&acc)[32], int l
   return acc[0];
 }
 
+// zero 32 consecutive fp32 columns of this warp's TMEM lane quarter
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr + 16u), "r"(z) : "memory");
+}
+
 // 32 channels (128 B) of the fp32 residual map for one pixel
 __device__ __forceinline__ void rows_load_residual(const RowsParams& p, long long pix, bool valid, int h, float4 (&rs)[8]) {
   if (p.res_hl) {
@@ -137,11 +144,13 @@ __device__ __forceinline__ void rows_load_residual(const RowsParams& p, long lon
 
 // Epilogue of one finished output row: thread = (pixel of the 128-pixel strip, 32-channel half h); `sq` = the row's sequence number
 // in this CTA (TMEM slot sq & 7).  bias (+ residual) (+ ReLU) -> fp32 and / or split-bf16 NHWC, optional InstanceNorm partial sums.
-template <bool RES, bool STATS>
+template <bool RES, bool STATS, bool ALIAS = false>
 __device__ __forceinline__ void rows_epilogue_row(const RowsParams& p, uint32_t tmem_base, uint32_t bar_tfull, uint32_t bar_tempty,
                                             uint32_t bias_s, uint32_t sq, int img, int xt, int y, int q, int h, int lane,
                                             float (&acc1)[STATS ? 32 : 1], float (&acc2)[STATS ? 32 : 1]) {
-  const uint32_t slot = sq & 7u;
+  // ALIAS (3x3 kernel): ring of six logical slots in eight physical ones - rows whose window position ran past slot 5 keep part of
+  // their sum in the alias slots 6 / 7 (see conv_rows_kernel); every slot is handed back ZEROED, so all MMAs accumulate
+  const uint32_t gen = ALIAS ? sq / 6u : sq >> 3, slot = ALIAS ? sq - gen * 6u : sq & 7u;
   const int x = xt * CR_M + q * 32 + lane;
   const bool valid = x < p.W;
   const long long pix = ((long long)img * p.H + y) * p.W + x;
@@ -149,21 +158,33 @@ __device__ __forceinline__ void rows_epilogue_row(const RowsParams& p, uint32_t 
   // variant is bound by its 2x memory traffic, not by load latency)
   float4 rs[RES ? 8 : 1];
   if constexpr (RES) rows_load_residual(p, pix, valid, h, rs);
-  mbar_wait(bar_tfull + 8 * slot, (sq >> 3) & 1u);
+  mbar_wait(bar_tfull + 8 * slot, gen & 1u);
   tc_fence_after();
+  const bool aliased = ALIAS && slot < 2u;
   if (p.dbg & 8) {                 // timing experiment: hand the slot back without reading it
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+    if (lane == 0) { mbar_arrive(bar_tempty + 8 * slot); if (aliased) mbar_arrive(bar_tempty + 8 * (slot + 6u)); }
     return;
   }
   const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 64u;
   {
     float v[32];
     tmem_ld32(taddr + (uint32_t)(h * 32), v);
+    if constexpr (ALIAS) {
+      if (aliased) {
+        float v2[32];
+        tmem_ld32(taddr + (uint32_t)(6 * 64 + h * 32), v2);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += v2[i];
+        tmem_zero32(taddr + (uint32_t)(6 * 64 + h * 32));
+      }
+      tmem_zero32(taddr + (uint32_t)(h * 32));
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+    if (lane == 0) { mbar_arrive(bar_tempty + 8 * slot); if (aliased) mbar_arrive(bar_tempty + 8 * (slot + 6u)); }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float4 b;
@@ -244,10 +265,17 @@ __device__ __forceinline__ void rows_stats_flush(const RowsParams& p, int img, i
   for (int i = 0; i < 32; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
 }
 
-template <int MODE>       // bit 0: residual input, bit 1: InstanceNorm partial sums
+// MODE bit 0: residual input, bit 1: InstanceNorm partial sums, bit 2: ALIAS slot scheme.
+// ALIAS: the eight 64-column TMEM slots are a ring of SIX logical slots (output row with sequence number q lives in slot q % 6) plus
+// two alias slots.  A step's window of n <= 3 rows starts at logical slot s = q(lo) % 6 and is written to the physical slots
+// s .. s + n - 1 WITHOUT wrapping - a position past slot 5 lands in alias slot 6 or 7 - so every product is ONE MMA (the plain
+// ring of eight issues N = 128 + 64 on the two of eight steps whose window wraps: +12 % MMA time).  Rows of logical slot 0 / 1
+// therefore hold part of their sum in slot 6 / 7; the epilogue adds the two parts.  Slots are handed back zeroed (tcgen05.st), so
+// every MMA accumulates and the "first product of a row" special case disappears as well.
+template <int MODE>
 __global__ void __launch_bounds__(64 + 32 * CR_EW, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const RowsParams p) {
-  constexpr bool RES = (MODE & 1) != 0, STATS = (MODE & 2) != 0;
+  constexpr bool RES = (MODE & 1) != 0, STATS = (MODE & 2) != 0, ALIAS = (MODE & 4) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = sb, bar_empty = sb + 16, bar_w = sb + 32, bar_tfull = sb + 64, bar_tempty = sb + 128, tmem_slot = sb + 192,
@@ -301,6 +329,40 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       rows_for_each_step(p, [&](int, int, int r, int y0, int y1, uint32_t seq) {
         const int lo = r - 1 > y0 ? r - 1 : y0, hi = r + 1 < y1 - 1 ? r + 1 : y1 - 1;
+        if constexpr (ALIAS) {
+          // rows that enter the window with this input row (out[r+1]; every row of the window at the segment's first input row)
+          // take over their slot - and its alias for logical slots 0 / 1 - once the previous occupant has been read and zeroed
+          const bool seg_first = r == (y0 > 0 ? y0 - 1 : 0);
+          for (int y = seg_first ? lo : r + 1; y <= hi; ++y) {
+            const uint32_t sq = seq + (uint32_t)(y - y0), g = sq / 6u, l = sq - g * 6u;
+            mbar_wait(bar_tempty + 8 * l, g & 1u);
+            if (l < 2u) mbar_wait(bar_tempty + 8 * (l + 6u), g & 1u);
+          }
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sql = seq + (uint32_t)(lo - y0), base = sql - (sql / 6u) * 6u;
+          const int n = hi - lo + 1;
+          const uint32_t d1 = tmem_base + base * 64u, i1 = n == 3 ? idesc3 : n == 2 ? idesc2 : idesc1;
+          const uint32_t at = a0 + stage * CR_ASTAGE;
+          const uint64_t a_hi0 = make_smem_desc_sw128(at, 1024), a_lo0 = make_smem_desc_sw128(at + CR_APLANE, 1024);
+          const uint32_t wrow = w0 + (uint32_t)(lo - r + 1) * CR_WBLK;
+          const uint64_t b_hi0 = make_smem_desc_sw128(wrow, 1024), b_lo0 = make_smem_desc_sw128(wrow + CR_WPLANE, 1024);
+          if (!(p.dbg & 1)) {
+#pragma unroll
+            for (int kk = 0; kk < 12; ++kk) {
+              const int kx = kk >> 2, k = kk & 3;
+              const uint64_t ao = (uint64_t)((kx * 128 + k * 32) >> 4), wo = (uint64_t)((kx * (int)CR_WKX + k * 32) >> 4);
+              umma_bf16(d1, a_hi0 + ao, b_hi0 + wo, i1, 1u);
+              umma_bf16(d1, a_hi0 + ao, b_lo0 + wo, i1, 1u);
+              umma_bf16(d1, a_lo0 + ao, b_hi0 + wo, i1, 1u);
+            }
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == CR_ASTAGES) { stage = 0; phase ^= 1u; }
+          if (lo == r - 1) { const uint32_t sq = seq + (uint32_t)(r - 1 - y0); umma_commit(bar_tfull + 8 * (sq - (sq / 6u) * 6u)); }
+          if (r == p.H - 1 && y1 == p.H) { const uint32_t sq = seq + (uint32_t)(r - y0); umma_commit(bar_tfull + 8 * (sq - (sq / 6u) * 6u)); }
+          return;
+        }
         // output rows touched for the first time by this input row: out[r+1], and out[0] at the top of an image
         const int n_fresh = (hi == r + 1 ? 1 : 0) + ((r == 0 && lo == 0) ? 1 : 0);
         for (int y = hi - n_fresh + 1; y <= hi; ++y) {
@@ -369,9 +431,18 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float acc1[STATS ? 32 : 1], acc2[STATS ? 32 : 1];
 #pragma unroll
     for (int i = 0; i < (STATS ? 32 : 1); ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
+    if constexpr (ALIAS) {
+      // all eight slots start zeroed; this first release completes phase 0 of every slot barrier
+      for (uint32_t ps = 0; ps < (uint32_t)CR_SLOTS; ++ps) tmem_zero32(tmem_base + ((uint32_t)(q * 32) << 16) + ps * 64u + (uint32_t)(h * 32));
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0)
+        for (uint32_t ps = 0; ps < (uint32_t)CR_SLOTS; ++ps) mbar_arrive(bar_tempty + 8 * ps);
+    }
     rows_for_each_step(p, [&](int img, int xt, int r, int y0, int y1, uint32_t seq) {
       auto do_row = [&](int y) {
-        rows_epilogue_row<RES, STATS>(p, tmem_base, bar_tfull, bar_tempty, bias_s, seq + (uint32_t)(y - y0), img, xt, y, q, h, lane, acc1, acc2);
+        rows_epilogue_row<RES, STATS, ALIAS>(p, tmem_base, bar_tfull, bar_tempty, bias_s, seq + (uint32_t)(y - y0), img, xt, y, q, h, lane, acc1, acc2);
         if constexpr (STATS) { if (y == y1 - 1) rows_stats_flush(p, img, xt, img * p.TX + xt, q, h, lane, acc1, acc2); }
       };
       const int lo = r - 1 > y0 ? r - 1 : y0;
@@ -811,11 +882,12 @@ int conv2d_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
     SCF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const RowsParams);
-  static const KernelFn table[4] = {conv_rows_kernel<0>, conv_rows_kernel<1>, conv_rows_kernel<2>, conv_rows_kernel<3>};
+  static const KernelFn table[8] = {conv_rows_kernel<0>, conv_rows_kernel<1>, conv_rows_kernel<2>, conv_rows_kernel<3>,
+                                    conv_rows_kernel<4>, conv_rows_kernel<5>, conv_rows_kernel<6>, conv_rows_kernel<7>};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    for (int i = 0; i < 4 && attr_err == cudaSuccess; ++i)
+    for (int i = 0; i < 8 && attr_err == cudaSuccess; ++i)
       attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM);
   });
   SCF_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "cudaFuncSetAttribute(conv_rows_kernel): %s", cudaGetErrorString(attr_err));
@@ -840,7 +912,9 @@ int conv2d_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  const int mode = ((d.aux0 || d.aux0_hl) ? 1 : 0) | (d.stats ? 2 : 0);
+  // SCFLOW_ROWS_ALIAS (default 1): six logical TMEM slots + two alias slots, no wrapped windows
+  const char* ae = getenv("SCFLOW_ROWS_ALIAS");
+  const int mode = ((d.aux0 || d.aux0_hl) ? 1 : 0) | (d.stats ? 2 : 0) | ((ae ? atoi(ae) != 0 : true) ? 4 : 0);
   cudaError_t le = cudaLaunchKernelEx(&cfg, table[mode], tmA, tmW, p);
   if (le != cudaSuccess) { cudaGetLastError(); set_error("conv_rows_kernel launch: %s", cudaGetErrorString(le)); g_launches++; return (int)le; }
   return check_launch("conv_rows_kernel");

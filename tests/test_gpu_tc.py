@@ -190,8 +190,9 @@ def test_conv_rows_kernel_matches_fp64_and_generic_tile(S, monkeypatch, hw, b, r
     pw = S.ops.pack_conv_weight_tc([w.cuda()])
     n_tiles, _ = S.ops.conv2d_tc_tiles(b, *hw)
     outs = {}
-    for mode in ('1', '0'):
-        monkeypatch.setenv('SCFLOW_TC_ROWS', mode)
+    for mode in ('1', 'ring8', '0'):       # rolling rows with the alias-slot TMEM scheme (default) / plain ring of eight / generic tile
+        monkeypatch.setenv('SCFLOW_TC_ROWS', '0' if mode == '0' else '1')
+        monkeypatch.setenv('SCFLOW_ROWS_ALIAS', '0' if mode == 'ring8' else '1')
         out_f32 = torch.full((b, *hw, cout + 8), 7.0, device='cuda')
         out_hl = torch.full((2, b, *hw, cout + 32), 7.0, device='cuda', dtype=torch.bfloat16)
         st = torch.zeros(n_tiles * 4 * 2 * cout, device='cuda') if stats else None
@@ -217,7 +218,7 @@ def test_conv_rows_kernel_matches_fp64_and_generic_tile(S, monkeypatch, hw, b, r
             assert float(((rows[1] - sq).abs() / sq).max()) < 2e-5
         outs[mode] = got
     # same products, different summation order inside the fp32 accumulator
-    assert float((outs['1'] - outs['0']).abs().max()) < 2e-5
+    assert float((outs['1'] - outs['0']).abs().max()) < 2e-5 and float((outs['ring8'] - outs['0']).abs().max()) < 2e-5
 
 
 @pytest.mark.parametrize('hw,b,stats,act', [((256, 128), 2, True, 'none'), ((96, 160), 2, False, 'relu'), ((30, 128), 11, True, 'none')])
