@@ -78,6 +78,32 @@ __device__ __forceinline__ void rows_for_each_step(const RowsParams& p, F&& f) {
   }
 }
 
+// The same schedule as rows_for_each_step / stem_for_each_step as a resumable iterator (STEM selects the stem's input-row range).  The
+// MMA-issuing thread uses it to prepare step i + 1 (barrier waits, descriptors) BETWEEN the MMAs and the commits of step i: the
+// tensor pipe's queue is shallow, so scalar work done after a commit would run against an idle pipe.
+template <bool STEM>
+struct RowsStepIter {
+  long long u, u1;
+  uint32_t seq;
+  int H, Hin, TX, img, xt, y0, y1, r, r1;
+  __device__ __forceinline__ RowsStepIter(const RowsParams& p)
+      : u(p.U * blockIdx.x / gridDim.x), u1(p.U * (blockIdx.x + 1) / gridDim.x), seq(0), H(p.H), Hin(p.Hin), TX(p.TX), img(0), xt(0), y0(0),
+        y1(0), r(1), r1(0) {}
+  // advances to the next step; false when the CTA's range is exhausted.  Afterwards img, xt, r, y0, y1, seq describe the step
+  __device__ __forceinline__ bool next() {
+    if (r < r1) { ++r; return true; }
+    if (r1 >= r && y1 > y0) { seq += (uint32_t)(y1 - y0); u += y1 - y0; }       // leaving a segment
+    if (u >= u1) return false;
+    const int strip = (int)(u / H);
+    y0 = (int)(u - (long long)strip * H);
+    y1 = (u1 - u) < (long long)(H - y0) ? y0 + (int)(u1 - u) : H;
+    img = strip / TX; xt = strip - img * TX;
+    if (STEM) { r = 2 * y0 - 3 > 0 ? 2 * y0 - 3 : 0; r1 = 2 * (y1 - 1) + 3 < Hin - 1 ? 2 * (y1 - 1) + 3 : Hin - 1; }
+    else { r = y0 > 0 ? y0 - 1 : 0; r1 = y1 < H ? y1 : H - 1; }
+    return true;
+  }
+};
+
 __device__ __forceinline__ float transpose_reduce32_rows(float (&acc)[32], int lane) {
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -327,42 +353,67 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       mbar_wait(bar_w, 0);
       tc_fence_after();
-      rows_for_each_step(p, [&](int, int, int r, int y0, int y1, uint32_t seq) {
-        const int lo = r - 1 > y0 ? r - 1 : y0, hi = r + 1 < y1 - 1 ? r + 1 : y1 - 1;
-        if constexpr (ALIAS) {
+      if constexpr (ALIAS) {
+        // ---- alias-slot scheme, software-pipelined: prep(i + 1) runs between the MMAs and the commits of step i
+        struct Prep { uint32_t d1, i1, stage, c0, c1; uint64_t a_hi0, a_lo0, b_hi0, b_lo0; };
+        auto prep = [&](const RowsStepIter<false>& s, int stg, uint32_t ph) -> Prep {
+          const int r = s.r, y0 = s.y0, y1 = s.y1;
+          const int lo = r - 1 > y0 ? r - 1 : y0, hi = r + 1 < y1 - 1 ? r + 1 : y1 - 1;
           // rows that enter the window with this input row (out[r+1]; every row of the window at the segment's first input row)
           // take over their slot - and its alias for logical slots 0 / 1 - once the previous occupant has been read and zeroed
           const bool seg_first = r == (y0 > 0 ? y0 - 1 : 0);
           for (int y = seg_first ? lo : r + 1; y <= hi; ++y) {
-            const uint32_t sq = seq + (uint32_t)(y - y0), g = sq / 6u, l = sq - g * 6u;
+            const uint32_t sq = s.seq + (uint32_t)(y - y0), g = sq / 6u, l = sq - g * 6u;
             mbar_wait(bar_tempty + 8 * l, g & 1u);
             if (l < 2u) mbar_wait(bar_tempty + 8 * (l + 6u), g & 1u);
           }
-          mbar_wait(bar_full + 8 * stage, phase);
+          mbar_wait(bar_full + 8 * stg, ph);
           tc_fence_after();
-          const uint32_t sql = seq + (uint32_t)(lo - y0), base = sql - (sql / 6u) * 6u;
+          Prep P;
+          const uint32_t sql = s.seq + (uint32_t)(lo - y0), base = sql - (sql / 6u) * 6u;
           const int n = hi - lo + 1;
-          const uint32_t d1 = tmem_base + base * 64u, i1 = n == 3 ? idesc3 : n == 2 ? idesc2 : idesc1;
-          const uint32_t at = a0 + stage * CR_ASTAGE;
-          const uint64_t a_hi0 = make_smem_desc_sw128(at, 1024), a_lo0 = make_smem_desc_sw128(at + CR_APLANE, 1024);
+          P.d1 = tmem_base + base * 64u; P.i1 = n == 3 ? idesc3 : n == 2 ? idesc2 : idesc1; P.stage = (uint32_t)stg;
+          const uint32_t at = a0 + stg * CR_ASTAGE;
+          P.a_hi0 = make_smem_desc_sw128(at, 1024); P.a_lo0 = make_smem_desc_sw128(at + CR_APLANE, 1024);
           const uint32_t wrow = w0 + (uint32_t)(lo - r + 1) * CR_WBLK;
-          const uint64_t b_hi0 = make_smem_desc_sw128(wrow, 1024), b_lo0 = make_smem_desc_sw128(wrow + CR_WPLANE, 1024);
-          if (!(p.dbg & 1)) {
+          P.b_hi0 = make_smem_desc_sw128(wrow, 1024); P.b_lo0 = make_smem_desc_sw128(wrow + CR_WPLANE, 1024);
+          // finished rows -> barrier addresses (0 = none)
+          P.c0 = P.c1 = 0u;
+          if (lo == r - 1) { const uint32_t sq = s.seq + (uint32_t)(r - 1 - y0); P.c0 = bar_tfull + 8 * (sq - (sq / 6u) * 6u); }
+          if (r == p.H - 1 && y1 == p.H) { const uint32_t sq = s.seq + (uint32_t)(r - y0); P.c1 = bar_tfull + 8 * (sq - (sq / 6u) * 6u); }
+          return P;
+        };
+        RowsStepIter<false> itr(p);
+        bool have = itr.next();
+        Prep P = {};
+        if (have) P = prep(itr, stage, phase);
+        auto issue_groups = [&](const Prep& P, int kk0, int kk1) {
+          if (p.dbg & 1) return;
 #pragma unroll
-            for (int kk = 0; kk < 12; ++kk) {
-              const int kx = kk >> 2, k = kk & 3;
-              const uint64_t ao = (uint64_t)((kx * 128 + k * 32) >> 4), wo = (uint64_t)((kx * (int)CR_WKX + k * 32) >> 4);
-              umma_bf16(d1, a_hi0 + ao, b_hi0 + wo, i1, 1u);
-              umma_bf16(d1, a_hi0 + ao, b_lo0 + wo, i1, 1u);
-              umma_bf16(d1, a_lo0 + ao, b_hi0 + wo, i1, 1u);
-            }
+          for (int kk = kk0; kk < kk1; ++kk) {
+            const int kx = kk >> 2, k = kk & 3;
+            const uint64_t ao = (uint64_t)((kx * 128 + k * 32) >> 4), wo = (uint64_t)((kx * (int)CR_WKX + k * 32) >> 4);
+            umma_bf16(P.d1, P.a_hi0 + ao, P.b_hi0 + wo, P.i1, 1u);
+            umma_bf16(P.d1, P.a_hi0 + ao, P.b_lo0 + wo, P.i1, 1u);
+            umma_bf16(P.d1, P.a_lo0 + ao, P.b_hi0 + wo, P.i1, 1u);
           }
-          umma_commit(bar_empty + 8 * stage);
+        };
+        while (have) {
+          issue_groups(P, 0, 8);
+          // the next step is prepared while these MMAs are queued
           if (++stage == CR_ASTAGES) { stage = 0; phase ^= 1u; }
-          if (lo == r - 1) { const uint32_t sq = seq + (uint32_t)(r - 1 - y0); umma_commit(bar_tfull + 8 * (sq - (sq / 6u) * 6u)); }
-          if (r == p.H - 1 && y1 == p.H) { const uint32_t sq = seq + (uint32_t)(r - y0); umma_commit(bar_tfull + 8 * (sq - (sq / 6u) * 6u)); }
-          return;
+          have = itr.next();
+          Prep Pn = {};
+          if (have) Pn = prep(itr, stage, phase);
+          issue_groups(P, 8, 12);
+          umma_commit(bar_empty + 8 * P.stage);
+          if (P.c0) umma_commit(P.c0);
+          if (P.c1) umma_commit(P.c1);
+          P = Pn;
         }
+      } else
+      rows_for_each_step(p, [&](int, int, int r, int y0, int y1, uint32_t seq) {
+        const int lo = r - 1 > y0 ? r - 1 : y0, hi = r + 1 < y1 - 1 ? r + 1 : y1 - 1;
         // output rows touched for the first time by this input row: out[r+1], and out[0] at the top of an image
         const int n_fresh = (hi == r + 1 ? 1 : 0) + ((r == 0 && lo == 0) ? 1 : 0);
         for (int y = hi - n_fresh + 1; y <= hi; ++y) {
@@ -498,7 +549,9 @@ __device__ __forceinline__ void stem_for_each_step(const RowsParams& p, F&& f) {
   }
 }
 
-template <bool STATS, bool FOLD>
+// ALIAS: the slot scheme of conv_rows_kernel (six logical + two alias slots, slots handed back zeroed, every MMA accumulates); a
+// four-row window that starts at logical slot 5 puts its last row at that row's home slot 2 with a second MMA (one step in twelve).
+template <bool STATS, bool FOLD, bool ALIAS>
 __global__ void __launch_bounds__(64 + 32 * CR_EW + (FOLD ? 32 * CS_CONV_WARPS : 0), 1)
 conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const RowsParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -617,6 +670,78 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       long long tprev = clock64();
       const long long tstart = tprev;
       auto tick = [&](int k) { if (p.dbg_times) { const long long t = clock64(); tacc[k] += t - tprev; tprev = t; } };
+      if constexpr (ALIAS) {
+        // ---- alias-slot scheme, software-pipelined: prep(i + 1) runs between the MMAs and the commits of step i
+        struct Prep { uint32_t d1, d2, in1, n2, stage, c0, c1, c2, c3; uint64_t a_hi0, a_lo0, b_hi0, b_lo0, bo2; };
+        auto prep = [&](const RowsStepIter<true>& st, int stg, uint32_t ph) -> Prep {
+          const int r = st.r, y0 = st.y0, y1 = st.y1, m = r >> 1;
+          const int lo = m - 1 > y0 ? m - 1 : y0, top = m + 1 + (r & 1), hi = top < y1 - 1 ? top : y1 - 1, n = hi - lo + 1;
+          const bool seg_first = r == (2 * y0 - 3 > 0 ? 2 * y0 - 3 : 0);
+          for (int y = seg_first ? lo : m + 2; y <= hi && (seg_first || (r & 1)); ++y) {
+            const uint32_t sq = st.seq + (uint32_t)(y - y0), g = sq / 6u, l = sq - g * 6u;
+            mbar_wait(bar_tempty + 8 * l, g & 1u);
+            if (l < 2u) mbar_wait(bar_tempty + 8 * (l + 6u), g & 1u);
+          }
+          tick(1);
+          mbar_wait(bar_full + 8 * stg, ph);
+          tc_fence_after();
+          tick(2);
+          Prep P;
+          const uint32_t sql = st.seq + (uint32_t)(lo - y0), base = sql - (sql / 6u) * 6u;
+          const int n1 = (int)base + n <= CR_SLOTS ? n : CR_SLOTS - (int)base;                   // n2 = 1 only for base 5, n 4
+          P.n2 = (uint32_t)(n - n1);
+          P.d1 = tmem_base + base * 64u; P.d2 = tmem_base + 2u * 64u; P.in1 = idesc_of(n1); P.stage = (uint32_t)stg;
+          const uint32_t at = a0 + stg * CS_ASTAGE;
+          P.a_hi0 = make_smem_desc_sw64(at, 512); P.a_lo0 = make_smem_desc_sw64(at + CS_APLANE, 512);
+          const uint32_t wrow = w0 + ((r & 1) ? CS_WODD : CS_WEVEN) + (uint32_t)(lo - (m - 1)) * CS_WBLK;
+          P.b_hi0 = make_smem_desc_sw64(wrow, 512); P.b_lo0 = make_smem_desc_sw64(wrow + CS_WPLANE, 512);
+          P.bo2 = (uint64_t)(((uint32_t)n1 * CS_WBLK) >> 4);
+          // finished rows (2y + 3 == r; every open row at the last input row) -> barrier addresses, 0 = none
+          auto done_bar = [&](int j) -> uint32_t {
+            const int y = lo + j;
+            if (y > hi || !(2 * y + 3 == r || r == p.Hin - 1)) return 0u;
+            const uint32_t sq = st.seq + (uint32_t)(y - y0);
+            return bar_tfull + 8 * (sq - (sq / 6u) * 6u);
+          };
+          P.c0 = done_bar(0); P.c1 = done_bar(1); P.c2 = done_bar(2); P.c3 = done_bar(3);
+          tick(0);
+          return P;
+        };
+        RowsStepIter<true> itr(p);
+        bool have = itr.next();
+        Prep P = {};
+        if (have) P = prep(itr, stage, phase);
+        auto issue_k = [&](const Prep& P, int k) {
+          if (p.dbg & 1) return;
+          const uint64_t ko = (uint64_t)(k * 32 >> 4);
+          umma_bf16(P.d1, P.a_hi0 + ko, P.b_hi0 + ko, P.in1, 1u);
+          umma_bf16(P.d1, P.a_hi0 + ko, P.b_lo0 + ko, P.in1, 1u);
+          umma_bf16(P.d1, P.a_lo0 + ko, P.b_hi0 + ko, P.in1, 1u);
+          if (P.n2) {
+            umma_bf16(P.d2, P.a_hi0 + ko, P.b_hi0 + P.bo2 + ko, id1, 1u);
+            umma_bf16(P.d2, P.a_hi0 + ko, P.b_lo0 + P.bo2 + ko, id1, 1u);
+            umma_bf16(P.d2, P.a_lo0 + ko, P.b_hi0 + P.bo2 + ko, id1, 1u);
+          }
+        };
+        while (have) {
+          issue_k(P, 0);
+          tick(3);
+          // the next step is prepared while the first k-step's MMAs are queued
+          if (++stage == CS_ASTAGES) { stage = 0; phase ^= 1u; }
+          have = itr.next();
+          Prep Pn = {};
+          if (have) Pn = prep(itr, stage, phase);
+          issue_k(P, 1);
+          tick(3);
+          umma_commit(bar_empty + 8 * P.stage);
+          if (P.c0) umma_commit(P.c0);
+          if (P.c1) umma_commit(P.c1);
+          if (P.c2) umma_commit(P.c2);
+          if (P.c3) umma_commit(P.c3);
+          tick(4);
+          P = Pn;
+        }
+      } else
       stem_for_each_step(p, [&](int, int, int r, int y0, int, int lo, int hi, uint32_t seq) {
         tick(0);                                  // schedule arithmetic between steps
         const int m = r >> 1, n = hi - lo + 1;
@@ -693,10 +818,18 @@ conv_stem_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     float acc1[STATS ? 32 : 1], acc2[STATS ? 32 : 1];
 #pragma unroll
     for (int i = 0; i < (STATS ? 32 : 1); ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
+    if constexpr (ALIAS) {
+      for (uint32_t ps = 0; ps < (uint32_t)CR_SLOTS; ++ps) tmem_zero32(tmem_base + ((uint32_t)(q * 32) << 16) + ps * 64u + (uint32_t)(h * 32));
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0)
+        for (uint32_t ps = 0; ps < (uint32_t)CR_SLOTS; ++ps) mbar_arrive(bar_tempty + 8 * ps);
+    }
     stem_for_each_step(p, [&](int img, int xt, int r, int y0, int y1, int lo, int hi, uint32_t seq) {
       for (int y = lo; y <= hi; ++y)
         if (2 * y + 3 == r || r == p.Hin - 1) {
-          rows_epilogue_row<false, STATS>(p, tmem_base, bar_tfull, bar_tempty, bias_s, seq + (uint32_t)(y - y0), img, xt, y, q, h, lane, acc1, acc2);
+          rows_epilogue_row<false, STATS, ALIAS>(p, tmem_base, bar_tfull, bar_tempty, bias_s, seq + (uint32_t)(y - y0), img, xt, y, q, h, lane, acc1, acc2);
           if constexpr (STATS) { if (y == y1 - 1) rows_stats_flush(p, img, xt, img * p.TX + xt, q, h, lane, acc1, acc2); }
         }
     });
@@ -772,13 +905,17 @@ static int conv2d_stem_rows_impl(const scf_tc_conv_desc& d, const float* images,
     SCF_CUDA(cudaGetDevice(&dev));
     SCF_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  typedef void (*StemFn)(const CUtensorMap, const CUtensorMap, const RowsParams);
+  // index: bit 0 InstanceNorm sums, bit 1 FOLD (x-fold in the kernel), bit 2 alias-slot TMEM scheme
+  static const StemFn stem_table[8] = {conv_stem_rows_kernel<false, false, false>, conv_stem_rows_kernel<true, false, false>,
+                                       conv_stem_rows_kernel<false, true, false>,  conv_stem_rows_kernel<true, true, false>,
+                                       conv_stem_rows_kernel<false, false, true>,  conv_stem_rows_kernel<true, false, true>,
+                                       conv_stem_rows_kernel<false, true, true>,   conv_stem_rows_kernel<true, true, true>};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_stem_rows_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_stem_rows_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_stem_rows_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_FOLD);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_stem_rows_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_FOLD);
+    for (int i = 0; i < 8 && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(stem_table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (i & 2) ? CS_SMEM_FOLD : CS_SMEM);
   });
   SCF_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "cudaFuncSetAttribute(conv_stem_rows_kernel): %s", cudaGetErrorString(attr_err));
   const unsigned grid = (unsigned)(p.U < num_sms ? p.U : num_sms);
@@ -802,10 +939,9 @@ static int conv2d_stem_rows_impl(const scf_tc_conv_desc& d, const float* images,
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  cudaError_t le = images ? (d.stats ? cudaLaunchKernelEx(&cfg, conv_stem_rows_kernel<true, true>, tmA, tmW, p)
-                                     : cudaLaunchKernelEx(&cfg, conv_stem_rows_kernel<false, true>, tmA, tmW, p))
-                          : (d.stats ? cudaLaunchKernelEx(&cfg, conv_stem_rows_kernel<true, false>, tmA, tmW, p)
-                                     : cudaLaunchKernelEx(&cfg, conv_stem_rows_kernel<false, false>, tmA, tmW, p));
+  const char* ae = getenv("SCFLOW_ROWS_ALIAS");
+  const int which = (d.stats ? 1 : 0) | (images ? 2 : 0) | ((ae ? atoi(ae) != 0 : true) ? 4 : 0);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, stem_table[which], tmA, tmW, p);
   if (le != cudaSuccess) { cudaGetLastError(); set_error("conv_stem_rows_kernel launch: %s", cudaGetErrorString(le)); g_launches++; return (int)le; }
   return check_launch("conv_stem_rows_kernel");
 }

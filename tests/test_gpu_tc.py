@@ -239,8 +239,9 @@ def test_conv_stem_rows_kernel_matches_fp64_and_generic_tile(S, monkeypatch, hw,
     pw = S.ops.pack_conv_weight_tc([w.cuda()])
     n_tiles, _ = S.ops.conv2d_tc_tiles(b, ho, wo)
     outs = {}
-    for mode in ('1', '0'):
-        monkeypatch.setenv('SCFLOW_TC_ROWS', mode)
+    for mode in ('1', 'ring8', '0'):       # alias-slot TMEM scheme (default) / plain ring of eight / generic tile
+        monkeypatch.setenv('SCFLOW_TC_ROWS', '0' if mode == '0' else '1')
+        monkeypatch.setenv('SCFLOW_ROWS_ALIAS', '0' if mode == 'ring8' else '1')
         out_f32 = torch.full((b, ho, wo, cout), 7.0, device='cuda')
         out_hl = torch.full((2, b, ho, wo, cout), 7.0, device='cuda', dtype=torch.bfloat16)
         st = torch.zeros(n_tiles * 4 * 2 * cout, device='cuda') if stats else None
@@ -259,7 +260,7 @@ def test_conv_stem_rows_kernel_matches_fp64_and_generic_tile(S, monkeypatch, hw,
             assert float((rows[0] - own.sum((0, 1, 2))).abs().max()) < 1e-3
             assert float((rows[1] - own.pow(2).sum((0, 1, 2))).abs().max()) < 1e-3
         outs[mode] = got
-    assert float((outs['1'] - outs['0']).abs().max()) < 2e-5
+    assert float((outs['1'] - outs['0']).abs().max()) < 2e-5 and float((outs['ring8'] - outs['0']).abs().max()) < 2e-5
 
 
 def test_conv_rows_kernel_split_residual(S):
