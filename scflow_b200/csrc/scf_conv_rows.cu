@@ -54,7 +54,7 @@ struct RowsParams {
   const __nv_bfloat16* res_hl; long long res_hl_plane; int res_hl_stride;    // residual as split-bf16 planes (instead of res)
   float* stats; int stat_rows;     // rows of [2][64] partial sums per image: (xt * stat_k + segment ordinal) * 4 + warp; zeroed by the launcher
   int stat_k;                      // upper bound of the CTA segments that can touch one (image, strip)
-  int al32;                        // 32 B vector accesses allowed: bit 0 fp32 output, bit 1 split output, bit 2 residual input
+  int al32;                        // 32 B vector accesses allowed: bit 0 fp32 output, bit 1 split output, bit 2 fp32 residual, bit 3 split residual
   int dbg;                         // timing experiments (SCFLOW_ROWS_DBG): 1 no MMAs, 2 no global stores, 4 no activation loads, 8 no epilogue work
   long long* dbg_times;            // optional [grid][8] clock64 totals of the MMA thread's phases (SCFLOW_ROWS_DBG_TIMES = hex pointer)
 };
@@ -128,14 +128,28 @@ __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
 // 32 channels (128 B) of the fp32 residual map for one pixel
 __device__ __forceinline__ void rows_load_residual(const RowsParams& p, long long pix, bool valid, int h, float4 (&rs)[8]) {
   if (p.res_hl) {
-    // hi + lo bf16 planes: 64 B each for this thread's 32 channels
+    // hi + lo bf16 planes: 64 B each for this thread's 32 channels (two 32 B loads per plane when the planes are 32 B aligned)
     uint4 hq[4], lq[4];
-    const uint4* hp = reinterpret_cast<const uint4*>(p.res_hl + pix * p.res_hl_stride + h * 32);
-    const uint4* lp = reinterpret_cast<const uint4*>(p.res_hl + p.res_hl_plane + pix * p.res_hl_stride + h * 32);
+    const __nv_bfloat16* hp = p.res_hl + pix * p.res_hl_stride + h * 32;
+    const __nv_bfloat16* lp = hp + p.res_hl_plane;
+    if (!valid) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      hq[j] = valid ? __ldcs(hp + j) : make_uint4(0u, 0u, 0u, 0u);
-      lq[j] = valid ? __ldcs(lp + j) : make_uint4(0u, 0u, 0u, 0u);
+      for (int j = 0; j < 4; ++j) { hq[j] = make_uint4(0u, 0u, 0u, 0u); lq[j] = hq[j]; }
+    } else if (p.al32 & 8) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        asm volatile("ld.global.cs.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(hq[2 * j].x), "=r"(hq[2 * j].y), "=r"(hq[2 * j].z), "=r"(hq[2 * j].w), "=r"(hq[2 * j + 1].x), "=r"(hq[2 * j + 1].y),
+                       "=r"(hq[2 * j + 1].z), "=r"(hq[2 * j + 1].w)
+                     : "l"(hp + 16 * j));
+        asm volatile("ld.global.cs.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(lq[2 * j].x), "=r"(lq[2 * j].y), "=r"(lq[2 * j].z), "=r"(lq[2 * j].w), "=r"(lq[2 * j + 1].x), "=r"(lq[2 * j + 1].y),
+                       "=r"(lq[2 * j + 1].z), "=r"(lq[2 * j + 1].w)
+                     : "l"(lp + 16 * j));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { hq[j] = __ldcs(reinterpret_cast<const uint4*>(hp) + j); lq[j] = __ldcs(reinterpret_cast<const uint4*>(lp) + j); }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -993,6 +1007,7 @@ int conv2d_rows(const scf_tc_conv_desc& d, cudaStream_t st) {
     if (d.out_f32 && al32(d.out_f32) && d.out_f32_stride % 8 == 0 && d.out_f32_coff % 8 == 0) p.al32 |= 1;
     if (d.out_hl && al32(d.out_hl) && d.out_hl_stride % 16 == 0 && d.out_hl_coff % 16 == 0 && (d.out_hl_plane * 2) % 32 == 0) p.al32 |= 2;
     if (d.aux0 && al32(d.aux0) && d.aux0_stride % 8 == 0) p.al32 |= 4;
+    if (d.aux0_hl && al32(d.aux0_hl) && d.aux0_hl_stride % 16 == 0 && (d.aux0_hl_plane * 2) % 32 == 0) p.al32 |= 8;
     const char* de = getenv("SCFLOW_ROWS_DBG");
     p.dbg = de ? atoi(de) : 0;
   }

@@ -28,7 +28,8 @@ def run(mode, variant):
     out_hl = torch.empty(2, n, *hw, 64, device='cuda', dtype=torch.bfloat16)
     st = torch.zeros(n_tiles * 4 * 2 * 64, device='cuda')
     kw = dict(in_raw=dict(out_f32=out_f32, stats=st), bn_relu=dict(act='relu', out_hl=out_hl),
-              bn_res=dict(act='relu', out_f32=out_f32, out_hl=out_hl, aux0=x.permute(0, 2, 3, 1).contiguous()))[variant]
+              bn_res=dict(act='relu', out_f32=out_f32, out_hl=out_hl, aux0=x.permute(0, 2, 3, 1).contiguous()),
+              bn_res_hl=dict(act='relu', out_hl=out_hl, aux0_hl=xs))[variant]
     ts = []
     for i in range(6):
         flush.zero_()
@@ -42,6 +43,8 @@ def run(mode, variant):
     print(f'rows={mode} {variant:8s} N={n}: {t:7.1f} us  {flops / t * 1e-6:6.1f} TFLOP/s algorithmic')
 
 
-for variant in ('in_raw', 'bn_relu', 'bn_res'):
+for variant in ('in_raw', 'bn_relu', 'bn_res', 'bn_res_hl'):
     for mode in ('1', '0'):
+        if variant == 'bn_res_hl' and mode == '0':
+            continue                      # the split-bf16 residual exists on the rolling-rows kernel only
         run(mode, variant)
