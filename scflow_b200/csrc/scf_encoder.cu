@@ -155,9 +155,12 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __rest
                                                              const float* __restrict__ res, const float* __restrict__ res_stat,
                                                              const __nv_bfloat16* __restrict__ res_hl,
                                                              int relu, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hl,
-                                                             long long plane, int HW, int C, long long total8) {
+                                                             long long plane, int HW, int C, long long total8, int reverse) {
+  // reverse: sweep the map back to front - the producing convolution wrote its last images most recently (still in L2), and the
+  // consuming convolution starts at image 0, which this sweep then writes last
   const int c8n = C >> 3;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total8; idx += (long long)gridDim.x * blockDim.x) {
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total8; it += (long long)gridDim.x * blockDim.x) {
+    const long long idx = reverse ? total8 - 1 - it : it;
     const int cq = (int)(idx % c8n);
     const long long pix = idx / c8n;
     const long long n = pix / HW;
@@ -342,12 +345,13 @@ static int encoder_forward_impl(int norm, const void* packed, const float* image
     instnorm_finalize_kernel<<<cdiv(N * C, 128), 128, 0, st>>>(F(ws.part), stat, hw, C, 1e-5f, N);
     return check_launch("instnorm_finalize_kernel");
   };
+  static const bool apply_reverse = [] { const char* e = getenv("SCFLOW_IN_REVERSE"); return e ? atoi(e) != 0 : true; }();
   auto in_apply = [&](const float* x, const float* stat, const float* res, const float* res_stat, int relu, float* of32, void* ohl,
                       long long pixels, int hw, int C, const void* res_hl = nullptr) -> int {
     const long long total8 = pixels * C / 8;
     instnorm_apply_kernel<<<cdiv(total8, 256) < 148 * 16 ? cdiv(total8, 256) : 148 * 16, 256, 0, st>>>(
         x, stat, res, res_stat, reinterpret_cast<const __nv_bfloat16*>(res_hl), relu, of32, reinterpret_cast<__nv_bfloat16*>(ohl),
-        pixels * C, hw, C, total8);
+        pixels * C, hw, C, total8, apply_reverse ? 1 : 0);
     return check_launch("instnorm_apply_kernel");
   };
   // tensor-core conv unit u on split input (hin x win), stride from the table
