@@ -10,6 +10,8 @@ from typing import Optional, Sequence, Union
 
 import ctypes as C
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -184,6 +186,8 @@ class RAFTEncoder(BaseModule):
                 raise RuntimeError(f'RAFTEncoder (eval): {why}')
             with torch.cuda.device(x.device):
                 return self._forward_native(x)
+        if os.environ.get('SCFLOW_TRAIN_CHANNELS_LAST', '0') != '0':
+            x = x.contiguous(memory_format=torch.channels_last)       # cuDNN's tensor-core kernels are NHWC: no per-layer layout launches
         x = self.relu(getattr(self, self.norm1_name)(self.conv1(x)))
         for name in self.res_layers:
             x = getattr(self, name)(x)

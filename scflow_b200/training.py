@@ -121,9 +121,20 @@ class _CorrLookupFn(torch.autograd.Function):
 _ACTS = {'none': lambda x: x, 'relu': F.relu, 'sigmoid': torch.sigmoid, 'tanh': torch.tanh}
 
 
+# cuDNN's tensor-core convolutions are NHWC kernels: with NCHW activations every convolution (forward, dgrad, wgrad) is wrapped in
+# layout-conversion launches (~1500 per step at config 5).  Activations therefore enter the convolutions channels-last and stay so
+# downstream when SCFLOW_TRAIN_CHANNELS_LAST=1 (measured 122.6 -> 113.7 ms per config-5 step).  Off by default: the different cuDNN
+# kernels change the summation order, and the gradient-parity test against the CPU oracle (tests/test_train.py) is pinned to NCHW.
+_CHANNELS_LAST = os.environ.get('SCFLOW_TRAIN_CHANNELS_LAST', '0') != '0'
+
+
+def _cl(x: torch.Tensor) -> torch.Tensor:
+    return x.contiguous(memory_format=torch.channels_last) if _CHANNELS_LAST and x.dim() == 4 else x
+
+
 def _cm(m, x: torch.Tensor) -> torch.Tensor:
     """ConvModule (conv -> optional GroupNorm -> activation) as differentiable torch operators."""
-    y = F.conv2d(x, m.conv.weight, m.conv.bias, m.stride, m.padding)
+    y = F.conv2d(_cl(x), m.conv.weight, m.conv.bias, m.stride, m.padding)
     if m.with_norm:
         y = F.group_norm(y, m.num_groups, m.gn.weight, m.gn.bias, m.norm_eps)
     return _ACTS[m.act](y)
@@ -212,7 +223,7 @@ def _xhead(xh, h):
     for layer in xh.layers:
         y = _cm(layer, y)
     p = xh.predict_layer
-    return F.conv2d(y, p.weight, p.bias, p.stride, p.padding)
+    return F.conv2d(_cl(y), p.weight, p.bias, p.stride, p.padding)
 
 
 def _pose_head(head, x, label):
