@@ -46,8 +46,10 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     trainer.train_step(data)
     torch.cuda.synchronize()
 ev = prof.key_averages()
-cuda_total = sum(e.self_device_time_total for e in ev) / 1e3
-nk = sum(e.count for e in ev if e.self_device_time_total > 0)
+from torch.autograd import DeviceType
+kern = [e for e in prof.events() if e.device_type == DeviceType.CUDA]          # GPU-side records only (kernels, memcpy, memset)
+cuda_total = sum(e.device_time for e in kern) / 1e3
+nk = len(kern)
 print(f'train step B={b}: wall {wall:.1f} ms, summed GPU kernel time {cuda_total:.1f} ms, {nk} GPU launches')
 for e in sorted(ev, key=lambda e: -e.self_device_time_total)[:14]:
     print(f'  {e.self_device_time_total / 1e3:8.2f} ms  x{e.count:5d}  {e.key[:100]}')
