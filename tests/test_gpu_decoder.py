@@ -217,6 +217,13 @@ def test_native_encoder_matches_oracle(norm):
         g2 = enc(x2.cuda()).cpu()
         r2 = O.raft_encoder(sd, x2, norm)
     assert float((g2 - r2).abs().max()) < 2e-4 * max(float(r2.abs().max()), 1.0)
+    # full frame (BASELINE config 3): three 128-pixel column strips per row, the last one ragged, in the rolling-rows kernels
+    x3 = torch.rand(1, 3, 480, 640)
+    with torch.no_grad():
+        g3 = enc(x3.cuda()).cpu()
+        r3 = O.raft_encoder(sd, x3, norm)
+    assert g3.shape == r3.shape == (1, 256, 60, 80)
+    assert float((g3 - r3).abs().max()) < 2e-4 * max(float(r3.abs().max()), 1.0)
 
 
 @pytest.mark.parametrize('norm', ['IN', 'BN'])
