@@ -61,8 +61,10 @@ class ClockSampler:
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, keep_busy=None):
+        # keep_busy: callable running one more untimed step of the same workload; used when the timed region was too short for
+        # nvidia-smi (process start-up ~0.1-0.5 s on a busy 8-GPU box) to deliver a sample while the GPU was under that load
+        self.index, self.rows, self.proc, self.keep_busy = index, [], None, keep_busy
 
     def __enter__(self):
         try:
@@ -80,6 +82,9 @@ class ClockSampler:
 
     def __exit__(self, *a):
         if self.proc is not None:
+            t_end = time.time() + 3.0
+            while self.keep_busy is not None and len(self.rows) < 3 and time.time() < t_end:
+                self.keep_busy()                      # untimed: only keeps the same load on the GPU until samples arrive
             time.sleep(0.15)
             self.proc.terminate()
             self.thread.join(timeout=2)
@@ -223,7 +228,12 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
 
     # ---- value: inputs resident in HBM
-    with ClockSampler(local_rank) as clocks:
+    def busy():            # the step WITHOUT the pose all-gather: it may run on one rank alone (no collective)
+        with torch.no_grad():
+            model.get_pose(resident['render_images'], resident['real_images'], resident['ref_rotation'], resident['ref_translation'],
+                           resident['depth'], resident['internel_k'], resident['label'])
+        torch.cuda.synchronize(dev)
+    with ClockSampler(local_rank, keep_busy=busy) as clocks:
         ms_total = timed(lambda: step(resident), args.steps)
     ms_total = D.max_over_ranks(ms_total, dev)
     ms_step = ms_total / args.steps
