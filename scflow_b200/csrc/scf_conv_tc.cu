@@ -1323,6 +1323,7 @@ __global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ src, __nv_bf
 
 __global__ void split_copy_kernel(const float* __restrict__ src, int src_stride, int src_coff, __nv_bfloat16* __restrict__ dst,
                                   long long plane, int dst_stride, int dst_coff, long long npix, int nch) {
+  scf_pdl_enter();
   const long long total = npix * nch;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -1345,6 +1346,7 @@ __global__ void split_copy_kernel(const float* __restrict__ src, int src_stride,
 template <int CIN, int KW, bool NCHW>
 __global__ void __launch_bounds__(256) im2col_x_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long plane,
                                                              int N, int H, int Wi, int Wo, int sx, long long total) {
+  scf_pdl_enter();
   constexpr int KC = KW * CIN <= 16 ? 16 : 32;
   static_assert(KW * CIN <= 32, "folded row must fit 32 channels");
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -1398,8 +1400,8 @@ int im2col_x_split(const float* in, int nchw, int cin, int kw, void* out_hl, lon
   const long long total = (long long)N * H * Wo;
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_hl);
-  if (cin == 3 && kw == 7 && nchw) im2col_x_split_kernel<3, 7, true><<<blocks, 256, 0, st>>>(in, o, plane, N, H, Wi, Wo, sx, total);
-  else if (cin == 2 && kw == 7 && !nchw) im2col_x_split_kernel<2, 7, false><<<blocks, 256, 0, st>>>(in, o, plane, N, H, Wi, Wo, sx, total);
+  if (cin == 3 && kw == 7 && nchw) launch_pdl(im2col_x_split_kernel<3, 7, true>, dim3(blocks), dim3(256), 0, st, in, o, plane, N, H, Wi, Wo, sx, total);
+  else if (cin == 2 && kw == 7 && !nchw) launch_pdl(im2col_x_split_kernel<2, 7, false>, dim3(blocks), dim3(256), 0, st, in, o, plane, N, H, Wi, Wo, sx, total);
   else SCF_REQUIRE(false, SCF_ERR_UNSUPPORTED, "im2col_x_split: unsupported (cin %d, kw %d, nchw %d)", cin, kw, nchw);
   return check_launch("im2col_x_split_kernel");
 }
@@ -2117,7 +2119,7 @@ int scf_split_copy(const float* src, int src_stride, int src_coff, void* dst_hl,
   SCF_REQUIRE(src && dst_hl && npix > 0 && nch > 0, SCF_ERR_ARG, "scf_split_copy: bad args");
   const long long total = npix * nch;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  scf::split_copy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, src_stride, src_coff, reinterpret_cast<__nv_bfloat16*>(dst_hl),
+  scf::launch_pdl(scf::split_copy_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, src, src_stride, src_coff, reinterpret_cast<__nv_bfloat16*>(dst_hl),
                                                                   plane_stride, dst_stride, dst_coff, npix, nch);
   return scf::check_launch("split_copy_kernel");
 }

@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(256) corr_lookup_l4r4_smem_kernel(const Lookup
 // and range bound into an immediate; TH = TW = 0 reads them from the parameters.
 template <int TH, int TW>
 __global__ void __launch_bounds__(256) corr_lookup_l4r4_lean_kernel(const LookupParams p) {
+  scf_pdl_enter();
   constexpr int R = 4, K = 9, KK = 81, L = 4, ROUNDS = 3, NIT = LK_ROWS / 2;
   __shared__ float reg[8][L][LK_ROWS * LK_RS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -483,8 +484,8 @@ static int corr_lookup_impl(const float* const* h_levels, int num_levels, int ra
     // SCFLOW_LOOKUP_SMEM: 0 gathers from global memory, 1 shared-memory staged regions, 2 (default) the same with lean index work
     static const int staged = [] { const char* e = getenv("SCFLOW_LOOKUP_SMEM"); return e ? atoi(e) : 2; }();
     if (staged >= 2 && p.nq < (1ll << 31)) {
-      if (H8 == 32 && W8 == 32) scf::corr_lookup_l4r4_lean_kernel<32, 32><<<scf::cdiv(p.nq, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(p);
-      else scf::corr_lookup_l4r4_lean_kernel<0, 0><<<scf::cdiv(p.nq, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(p);
+      if (H8 == 32 && W8 == 32) scf::launch_pdl(scf::corr_lookup_l4r4_lean_kernel<32, 32>, dim3(scf::cdiv(p.nq, wpb)), dim3(wpb * 32), 0, (cudaStream_t)stream, p);
+      else scf::launch_pdl(scf::corr_lookup_l4r4_lean_kernel<0, 0>, dim3(scf::cdiv(p.nq, wpb)), dim3(wpb * 32), 0, (cudaStream_t)stream, p);
       return scf::check_launch("corr_lookup_l4r4_lean_kernel");
     }
     if (staged) {

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) reproject_kernel(const float4* __restrict
                                                         const float* __restrict__ rot, const float* __restrict__ trs,
                                                         float invalid, float* __restrict__ flow, int H, int W, int full_blocks,
                                                         float* __restrict__ flow8, int H8, int W8, float ry, float rx, float scale8) {
+  scf_pdl_enter();
   __shared__ float k[9], r[9], t[3];
   const int b = blockIdx.y;
   if (threadIdx.x < 9) { k[threadIdx.x] = K[b * 9 + threadIdx.x]; r[threadIdx.x] = rot[b * 9 + threadIdx.x]; }
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(256) reproject_kernel(const float4* __restrict
 __global__ void pose_update_kernel(const float* __restrict__ d_rot, const float* __restrict__ d_trs,
                                    const float* __restrict__ rot_in, const float* __restrict__ trs_in,
                                    float* __restrict__ rot_out, float* __restrict__ trs_out, int B) {
+  scf_pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float* o = d_rot + b * 6;
@@ -234,8 +236,8 @@ static int reproject_launch(const float* pts4, const float* K, const float* rot,
   // ATen area_pixel_compute_scale(align_corners=True): (in-1)/(out-1) in fp32, 0 when out == 1 (as scf_resize_bilinear)
   const float ry = H8 > 1 ? (float)(H - 1) / (float)(H8 - 1) : 0.f, rx = W8 > 1 ? (float)(W - 1) / (float)(W8 - 1) : 0.f;
   const float scale8 = flow8 ? 1.0f / (float)(H / H8) : 1.f;
-  scf::reproject_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(pts4), K, rot, trs, invalid, flow, H, W,
-                                                               full_blocks, flow8, H8, W8, ry, rx, scale8);
+  scf::launch_pdl(scf::reproject_kernel, grid, dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(pts4), K, rot, trs, invalid, flow, H, W,
+                  full_blocks, flow8, H8, W8, ry, rx, scale8);
   return scf::check_launch("reproject_kernel");
 }
 
@@ -254,8 +256,7 @@ int scf_reproject_down(const float* pts4, const float* K, const float* rot, cons
 int scf_pose_update(const float* d_rot, const float* d_trs, const float* rot_in, const float* trs_in, float* rot_out,
                     float* trs_out, int B, void* stream) {
   SCF_REQUIRE(d_rot && d_trs && rot_in && trs_in && rot_out && trs_out && B > 0, SCF_ERR_ARG, "scf_pose_update: bad args");
-  scf::pose_update_kernel<<<scf::cdiv(B, 64), 64, 0, (cudaStream_t)stream>>>(d_rot, d_trs, rot_in, trs_in, rot_out,
-                                                                            trs_out, B);
+  scf::launch_pdl(scf::pose_update_kernel, dim3(scf::cdiv(B, 64)), dim3(64), 0, (cudaStream_t)stream, d_rot, d_trs, rot_in, trs_in, rot_out, trs_out, B);
   return scf::check_launch("pose_update_kernel");
 }
 

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) group_norm_relu_c4_kernel(float* __restri
                                                                  const float* __restrict__ beta, int HW, float eps,
                                                                  __nv_bfloat16* __restrict__ out_hl, long long plane, int nsplit,
                                                                  long long split_stride) {
+  scf_pdl_enter();
   __shared__ float red[32][9];
   __shared__ float stat[8];
   const int b = blockIdx.x, gl = threadIdx.x & 7, r = threadIdx.x >> 3;
@@ -349,6 +350,7 @@ __global__ void __launch_bounds__(256) pose_project_kernel(const float* __restri
                                                            const float* __restrict__ tr_b, const int64_t* __restrict__ label,
                                                            float* __restrict__ d_rot, float* __restrict__ d_trs, int B, int I,
                                                            int rot_dim, int num_class) {
+  scf_pdl_enter();
   const int lane = threadIdx.x & 31;
   const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int rows = rot_dim + 3;
@@ -396,7 +398,7 @@ int group_norm_relu_partials(float* x, int nsplit, long long split_stride, const
     scf::group_norm_relu_kernel<<<scf::cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, B, HW, C, num_groups, eps);
     return scf::check_launch("group_norm_relu_kernel");
   }
-  scf::group_norm_relu_c4_kernel<<<dim3(B, 4), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, HW, eps,
+  scf::launch_pdl(scf::group_norm_relu_c4_kernel, dim3(B, 4), dim3(256), 0, (cudaStream_t)stream, x, gamma, beta, HW, eps,
                                                                      reinterpret_cast<__nv_bfloat16*>(out_hl), plane_stride, nsplit,
                                                                      split_stride);
   return scf::check_launch("group_norm_relu_c4_kernel");
@@ -433,7 +435,7 @@ int scf_pose_project(const float* x, const float* rot_w, const float* rot_b, con
               "scf_pose_project: bad args");
   SCF_REQUIRE(num_class <= 0 || label != nullptr, SCF_ERR_ARG, "scf_pose_project: multi-class head needs label");
   const int warps = B * (rot_dim + 3);
-  scf::pose_project_kernel<<<scf::cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>(x, rot_w, rot_b, tr_w, tr_b, label,
+  scf::launch_pdl(scf::pose_project_kernel, dim3(scf::cdiv(warps, 8)), dim3(256), 0, (cudaStream_t)stream, x, rot_w, rot_b, tr_w, tr_b, label,
                                                                                  d_rot, d_trs, B, I, rot_dim, num_class);
   return scf::check_launch("pose_project_kernel");
 }

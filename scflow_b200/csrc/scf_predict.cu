@@ -187,6 +187,7 @@ __global__ void pack_predict_tc_kernel(const float* __restrict__ wf, const float
 __global__ void __launch_bounds__(256) predict_gather_kernel(const float* __restrict__ d, int ld, const float* __restrict__ bf,
                                                              const float* __restrict__ bm, float* __restrict__ dflow,
                                                              float* __restrict__ mask8, int H, int W, long long npix) {
+  scf_pdl_enter();
   for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(pix % W), y = (int)((pix / W) % H);
     float a0 = __ldg(bf), a1 = __ldg(bf + 1);
@@ -213,7 +214,7 @@ int predict_gather(const float* d, int ld, const float* bf, const float* bm, flo
                    cudaStream_t st) {
   SCF_REQUIRE(d && bf && bm && dflow && mask8 && ld >= 19 && ld % 2 == 0, SCF_ERR_ARG, "predict_gather: bad args");
   const long long npix = (long long)B * H * W;
-  predict_gather_kernel<<<cdiv(npix, 256), 256, 0, st>>>(d, ld, bf, bm, dflow, mask8, H, W, npix);
+  launch_pdl(predict_gather_kernel, dim3(cdiv(npix, 256)), dim3(256), 0, st, d, ld, bf, bm, dflow, mask8, H, W, npix);
   return check_launch("predict_gather_kernel");
 }
 
